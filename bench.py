@@ -1,0 +1,471 @@
+#!/usr/bin/env python
+"""bench.py — SGD rating-updates/s on a Netflix-shaped synthetic problem at rank 64.
+
+Contract (one JSON line on stdout, printed by rank 0):
+  python bench.py --gpus N --steps K --warmup W          device arm (this repo's CUDA engine)
+  python bench.py --impl reference --gpus N ...          reference arm: the reference's own CPU
+                                                         code (oracle/_ref/mf_ref) on host cores
+A "step" is one epoch of the stratified SGD trainer over the whole training matrix.
+
+Workload = BASELINE.json configs[1]: modelMF SGD, rank 64, 480,189 x 17,770, ~100.5 M ratings
+(synthetic, Zipf-skewed positions, ratings from a rank-8 model + noise; random-init factors
+U(-0.01, 0.01) as model.cpp:2331-2350).  Inputs (ratings 0.8 GB + U 123 MB) exceed the 126 MB L2,
+so no explicit L2 flush is done between timed epochs.
+
+  value     epochs * valid-ratings / device time (CUDA events on the engine's stream, max over
+            ranks), inputs resident in HBM
+  e2e       the same metric through the C ABI with HOST buffers: every step uploads the rating
+            CSR and the factor matrices from pinned host memory, builds the stratum plan, runs
+            one epoch plus the per-epoch evaluation and downloads the factors
+  roofline  algorithmic bytes (16 r + 12 per update) / kernel time vs the measured
+            HBM copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline  the reference's OpenMP stratified SGD (trainSGDPar) on a row sample, host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RANK = 64
+SHAPE = (480_189, 17_770, 100_480_507)
+HP = dict(lr=0.005, ureg=0.05, ireg=0.05)
+FALLBACK_HBM_GBS = 6650.0
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def gen_problem(n_users, n_items, nnz, seed, device):
+    """Netflix-shaped training CSR (+ a 1 % validation CSR) generated with torch on `device`.
+    Returns dict of numpy arrays (host)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    dev = torch.device(device)
+
+    def zipf(n, s):
+        w = 1.0 / torch.arange(1, n + 1, dtype=torch.float64, device=dev).pow(s)
+        w = w[torch.randperm(n, generator=g, device=dev)]
+        return w / w.sum()
+
+    pu, pi = zipf(n_users, 0.9), zipf(n_items, 1.05)
+    ci = torch.cumsum(pi, 0)
+    total = int(nnz * 1.01)
+    keys = torch.empty(0, dtype=torch.int64, device=dev)
+    # every user and every item at least once (io.cpp:742-752)
+    base_u = torch.arange(n_users, device=dev, dtype=torch.int64)
+    base_i = torch.searchsorted(ci, torch.rand(n_users, generator=g, device=dev, dtype=torch.float64)).clamp_(max=n_items - 1)
+    base2_i = torch.arange(n_items, device=dev, dtype=torch.int64)
+    base2_u = torch.multinomial(pu.float(), n_items, replacement=True, generator=g)
+    keys = torch.unique(torch.cat([base_u * n_items + base_i, base2_u * n_items + base2_i]))
+    cap = 0.85 * n_items
+    for rnd in range(12):
+        need = total - keys.numel()
+        if need <= 0:
+            break
+        draw = int(need * (1.6 if rnd == 0 else 1.3)) + 1024
+        # user degrees ~ Zipf, capped so that no user exceeds ~85 % of the catalogue
+        deg = torch.clamp(pu * draw, max=cap).round().to(torch.int64)
+        u = torch.repeat_interleave(torch.arange(n_users, device=dev, dtype=torch.int64), deg)
+        i = torch.searchsorted(ci, torch.rand(u.numel(), generator=g, device=dev, dtype=torch.float64)).clamp_(max=n_items - 1)
+        keys = torch.unique(torch.cat([keys, u * n_items + i]))
+        del u, i, deg
+    if keys.numel() > total:
+        drop = torch.randperm(keys.numel(), generator=g, device=dev)[: keys.numel() - total]
+        mask = torch.ones(keys.numel(), dtype=torch.bool, device=dev)
+        mask[drop] = False
+        # never drop a user's or an item's covering pair: re-add them
+        keys = torch.unique(torch.cat([keys[mask], base_u * n_items + base_i, base2_u * n_items + base2_i]))
+    users = (keys // n_items).to(torch.int32)
+    items = (keys % n_items).to(torch.int32)
+    del keys
+    tr_rank = 8
+    us = torch.randn(n_users, tr_rank, generator=g, device=dev)
+    vs = torch.randn(n_items, tr_rank, generator=g, device=dev)
+    vals = torch.empty(users.numel(), dtype=torch.float32, device=dev)
+    step = 1 << 24
+    for s in range(0, users.numel(), step):
+        e = min(s + step, users.numel())
+        d = (us[users[s:e].long()] * vs[items[s:e].long()]).sum(1) / tr_rank ** 0.5
+        vals[s:e] = 3.6 + 1.1 * d + 0.3 * torch.randn(e - s, generator=g, device=dev)
+    vals = (torch.round(vals * 2) / 2).clamp_(1.0, 5.0)
+    # split: 1 % validation, never a user's/item's first rating
+    colour = torch.rand(users.numel(), generator=g, device=dev)
+    first_u = torch.ones(users.numel(), dtype=torch.bool, device=dev)
+    first_u[1:] = users[1:] != users[:-1]
+    order_i = torch.argsort(items.long() * n_users + users.long())
+    si = items[order_i]
+    fi = torch.ones(si.numel(), dtype=torch.bool, device=dev)
+    fi[1:] = si[1:] != si[:-1]
+    first_i = torch.zeros(users.numel(), dtype=torch.bool, device=dev)
+    first_i[order_i[fi]] = True
+    is_val = (colour < 0.01) & ~first_u & ~first_i
+    del order_i, si, fi, colour
+
+    def csr(mask):
+        u, i, v = users[mask], items[mask], vals[mask]
+        ptr = torch.zeros(n_users + 1, dtype=torch.int64, device=dev)
+        ptr[1:] = torch.cumsum(torch.bincount(u.long(), minlength=n_users), 0)
+        return ptr.cpu().numpy(), i.cpu().numpy(), v.cpu().numpy()
+
+    tr, va = csr(~is_val), csr(is_val)
+    return dict(n_users=n_users, n_items=n_items, train=tr, val=va)
+
+
+class Mat:
+    def __init__(self, nrows, ncols, t):
+        self.nrows, self.ncols = nrows, ncols
+        self.rowptr, self.rowind, self.rowval = t
+        self.colptr = self.colind = self.colval = None
+
+
+def pinned(a):
+    """Copy a numpy array into page-locked memory (torch's pinned allocator)."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    try:
+        t = t.pin_memory()
+    except Exception:
+        pass
+    return t.numpy(), t
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_hbm_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_arm(prob, steps, warmup, sample_users=None):
+    """Times the reference's OpenMP stratified SGD (ModelMF::trainSGDPar) on the first
+    `sample_users` users of the workload with every host core.  Uses oracle/_ref/mf_ref (the
+    reference's own code) when present, else the oracle port."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    from matfac_b200 import synth
+    cores = os.cpu_count() or 1
+    n_users, n_items = prob["n_users"], prob["n_items"]
+    ptr, ind, val = prob["train"]
+    if sample_users is None:
+        # ~4 M ratings: a few seconds of CPU work per epoch
+        sample_users = int(np.searchsorted(ptr, 4_000_000))
+        sample_users = max(1000, min(sample_users, n_users))
+    nnz_s = int(ptr[sample_users])
+    tr = synth.Csr(sample_users, n_items, ptr[: sample_users + 1].copy(), ind[:nnz_s], val[:nnz_s])
+    vptr, vind, vval = prob["val"]
+    vn = int(vptr[sample_users])
+    va = synth.Csr(sample_users, n_items, vptr[: sample_users + 1].copy(), vind[:vn], vval[:vn])
+    epochs = max(1, min(steps, 2))
+    sample = f"first {sample_users} users ({nnz_s} ratings) of the workload, trainSGDPar P={cores}, {epochs} epoch(s)"
+    kind = "port"
+    secs = None
+    if ol.have_ref():
+        try:
+            d = tempfile.mkdtemp(prefix="mfref_")
+            files = synth.write_split_files(d, tr, va, va)
+            res = ol.run_ref(files, os.path.join(d, "dump"), algo="mf", method="sgdpar", threads=cores, timeout=900,
+                             facdim=RANK, maxiter=1, seed=1, ureg=HP["ureg"], ireg=HP["ireg"], learnrate=HP["lr"])
+            for line in res["stdout"].splitlines():
+                if "subIterDuration:" in line:
+                    secs = float(line.split("subIterDuration:")[1].split()[0])
+            kind = "reference"
+            epochs = 1
+            sample = f"first {sample_users} users ({nnz_s} ratings) of the workload, mf_ref --mf_method sgdpar, OMP_NUM_THREADS={cores}, epoch 0"
+        except Exception as ex:  # fall back to the port
+            log("mf_ref failed, using the oracle port:", repr(ex)[:200])
+            secs = None
+    od = ol.OracleData(tr, va, va)
+    om = ol.OracleModel(od, algo="mf", facdim=RANK, maxiter=epochs, seed=1, nthreads=cores, ureg=HP["ureg"],
+                        ireg=HP["ireg"], learnrate=HP["lr"])
+    # ratings visited in an epoch of trainSGDPar: P schedules drawn with replacement (util.cpp:1077)
+    up, ip, sched = om.dsgd_plan(cores, epochs * cores)
+    users = np.repeat(np.arange(sample_users), np.diff(tr.rowptr))
+    bid = up[users].astype(np.int64) * cores + ip[tr.rowind]
+    blk = np.bincount(bid, minlength=cores * cores)
+    visited = sum(int(blk[a * cores + b]) for s in range(epochs * cores) for a, b in sched[s])
+    if secs is None:
+        om.train("sgdpar")
+        secs = float(np.sum(om.epoch_seconds()))
+    value = visited / secs
+    return dict(value=value, unit="rating-updates/s", cores=cores, kind=kind, sample=sample), secs / epochs * 1e3
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="device", choices=["device", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_users, n_items, nnz = (int(SHAPE[0] * args.scale), int(SHAPE[1] * max(args.scale, 0.05) if args.scale < 1 else SHAPE[1]),
+                             int(SHAPE[2] * args.scale))
+    config = {"workload": "modelMF SGD rank 64, Netflix-shaped synthetic ratings (BASELINE.json configs[1])",
+              "n_users": n_users, "n_items": n_items, "rank": RANK, "learnrate": HP["lr"], "ureg": HP["ureg"],
+              "ireg": HP["ireg"], "l2": "inputs larger than L2 (ratings 0.8 GB + U 123 MB), no flush"}
+
+    import torch
+    have_cuda = torch.cuda.is_available()
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        prob = gen_problem(n_users, n_items, nnz, 20260102, "cuda" if have_cuda else "cpu")
+        cb, ms = cpu_reference_arm(prob, args.steps, args.warmup)
+        config["train_nnz"] = int(prob["train"][0][-1])
+        line = {"impl": "reference", "metric": "sgd_rating_updates_per_sec", "value": cb["value"], "unit": "rating-updates/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "rating-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    if not have_cuda:
+        raise SystemExit("bench.py: no CUDA device — the device arm has no CPU fallback")
+    from matfac_b200 import engine as E
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    t0 = time.time()
+    prob = gen_problem(n_users, n_items, nnz, 20260102, f"cuda:{local_rank}")
+    ptr, ind, val = prob["train"]
+    train_nnz = int(ptr[-1])
+    config["train_nnz"] = train_nnz
+    log(f"[rank {rank}] data: {train_nnz} train ratings, max user degree {int(np.diff(ptr).max())}, gen {time.time()-t0:.1f}s")
+    torch.cuda.empty_cache()
+
+    rng = np.random.default_rng(1)
+    U0 = rng.uniform(-0.01, 0.01, size=(n_users, RANK)).astype(np.float32)
+    V0 = rng.uniform(-0.01, 0.01, size=(n_items, RANK)).astype(np.float32)
+    tr = Mat(n_users, n_items, prob["train"])
+    va = Mat(n_users, n_items, prob["val"])
+    bad_u = (np.diff(ptr) == 0).astype(np.uint8)
+    bad_i = (np.bincount(ind, minlength=n_items) == 0).astype(np.uint8)
+
+    eng = E.Engine(n_users, n_items, RANK, device=local_rank)
+    P = world
+    if world == 1:
+        eng.upload_csr(E.TRAIN, tr, with_csc=False)
+        eng.upload_csr(E.VAL, va, with_csc=False)
+        eng.set_masks(bad_u, bad_i)
+        eng.upload_factors(U0, V0)
+        eng.sgd_plan(1)
+        sched_blocks = [np.array([[0, 0]], np.int32)]
+        my_nnz_per_epoch = train_nnz
+    else:
+        # DSGD: user stratum g pinned to rank g, item blocks visited in a rotating permutation
+        prng = np.random.default_rng(7)
+        user_part = prng.integers(0, P, size=n_users).astype(np.int32)
+        item_part = prng.integers(0, P, size=n_items).astype(np.int32)
+        mine = user_part == rank
+        rows = np.repeat(mine, np.diff(ptr))
+        cnt = np.where(mine, np.diff(ptr), 0)
+        lptr = np.zeros(n_users + 1, np.int64)
+        np.cumsum(cnt, out=lptr[1:])
+        ltr = Mat(n_users, n_items, (lptr, ind[rows], val[rows]))
+        eng.upload_csr(E.TRAIN, ltr, with_csc=False)
+        eng.upload_csr(E.VAL, va, with_csc=False)
+        eng.set_masks(bad_u, bad_i)
+        eng.upload_factors(U0, V0)
+        up_local = np.where(mine, user_part, -1).astype(np.int32)
+        eng.sgd_plan(P, up_local, item_part)
+        sched_blocks = [np.array([[rank, (rank + s) % P]], np.int32) for s in range(P)]
+        my_nnz_per_epoch = int(lptr[-1])
+        item_ids = [np.nonzero(item_part == b)[0].astype(np.int32) for b in range(P)]
+        max_blk = max(len(x) for x in item_ids)
+        ld = eng.device_factors(E.ITEM)[1]
+        send = torch.zeros(max_blk * ld, dtype=torch.float32, device="cuda")
+        recv = [torch.zeros(max_blk * ld, dtype=torch.float32, device="cuda") for _ in range(P)]
+
+    def epoch(ep):
+        if world == 1:
+            eng.sgd_subepoch(sched_blocks[0], E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, ep)
+            return
+        for s in range(P):
+            eng.sgd_subepoch(sched_blocks[s], E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, ep * P + s)
+            # exchange step: every rank publishes the item block it just updated
+            b = (rank + s) % P
+            eng.pack_rows(E.ITEM, item_ids[b], send.data_ptr())
+            dist.all_gather(recv, send)
+            torch.cuda.synchronize()
+            for g in range(P):
+                if g != rank:
+                    eng.unpack_rows(E.ITEM, item_ids[(g + s) % P], recv[g].data_ptr())
+
+    def barrier():
+        eng.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for w in range(args.warmup):
+        epoch(w)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = E.launch_count()
+    t_host0 = time.perf_counter()
+    eng.event_record(0)
+    for k in range(args.steps):
+        epoch(args.warmup + k)
+    eng.event_record(1)
+    barrier()
+    t_host = time.perf_counter() - t_host0
+    ms_dev = eng.event_elapsed_ms(0, 1)
+    launches = E.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ms_dev if world == 1 else t_host * 1e3
+    total_nnz = my_nnz_per_epoch
+    if dist is not None:
+        t = torch.tensor([ms_total, float(my_nnz_per_epoch)], dtype=torch.float64, device="cuda")
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_total = float(tmax[0])
+        total_nnz = int(tsum[1])
+    ms_per_step = ms_total / args.steps
+    value = total_nnz / (ms_per_step * 1e-3)
+    val_rmse = eng.rmse(E.VAL)
+    log(f"[rank {rank}] {ms_per_step:.3f} ms/epoch, {value/1e9:.3f} G updates/s, val RMSE after {args.warmup+args.steps} epochs {val_rmse:.4f}")
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # roofline of the SGD update kernel (one launch per epoch at N = 1)
+    peak, peak_src = measured_hbm_gbs()
+    alg_bytes = (16 * RANK + 12) * float(my_nnz_per_epoch)
+    kern_ms = ms_dev / max(1, (args.steps * (1 if world == 1 else P)))
+    achieved = alg_bytes / (1 if world == 1 else P) / (kern_ms * 1e-3) / 1e9 if world == 1 else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                "kernel": "sgd_update_kernel<16,1,MF>", "algorithmic_bytes_per_update": 16 * RANK + 12,
+                "note": "achieved counts algorithmic bytes; u stays in registers over a user's run and V is L2 resident, "
+                        "so DRAM traffic is far below it (see profiles/)"}
+
+    # end-to-end through the C ABI with host buffers
+    e2e = None
+    if world == 1 and args.e2e_steps > 0:
+        h = {}
+        keep = []
+        for name, a in (("ptr", ptr), ("ind", ind), ("val", val), ("U", U0.copy()), ("V", V0.copy())):
+            h[name], t = pinned(a)
+            keep.append(t)
+        Uo = np.empty_like(U0); Vo = np.empty_like(V0)
+        Uo, tU = pinned(Uo); Vo, tV = pinned(Vo)
+        trp = Mat(n_users, n_items, (h["ptr"], h["ind"], h["val"]))
+        h2d = h["ptr"].nbytes + h["ind"].nbytes + h["val"].nbytes + h["U"].nbytes + h["V"].nbytes
+        d2h = Uo.nbytes + Vo.nbytes + 64
+        times = []
+        for s in range(args.e2e_steps + 1):
+            eng.sync()
+            t1 = time.perf_counter()
+            eng.upload_csr(E.TRAIN, trp, with_csc=False)
+            eng.upload_factors(h["U"], h["V"])
+            eng.sgd_plan(1)
+            eng.sgd_subepoch(sched_blocks[0], E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, s)
+            obj = eng.eval(E.TRAIN, E.CURRENT, E.MF, False, True)
+            vr = eng.eval(E.VAL)
+            eng.L.mfb_download_factors(eng.h, E.CURRENT, Uo.ctypes.data, RANK, Vo.ctypes.data, RANK)
+            eng.sync()
+            times.append(time.perf_counter() - t1)
+        t_e2e = float(np.mean(times[1:]))
+        e2e = {"value": train_nnz / t_e2e, "unit": "rating-updates/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e * 1e3,
+               "what": "per step: upload CSR + factors from pinned host memory, plan, 1 epoch, objective + val RMSE, download factors"}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu_baseline, _ = cpu_reference_arm(prob, 1, 0)
+        except Exception as ex:
+            cpu_baseline = {"value": None, "unit": "rating-updates/s", "cores": os.cpu_count(), "kind": "port",
+                            "sample": "failed: " + repr(ex)[:200]}
+
+    line = {"metric": "sgd_rating_updates_per_sec", "value": value, "unit": "rating-updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "val_rmse": val_rmse}
+    if e2e:
+        line["e2e"] = e2e
+    if cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

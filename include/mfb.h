@@ -1,0 +1,169 @@
+/*
+ * mfb.h — C ABI of the B200 training engine for mohit-shrma/matfac's hot path.
+ *
+ * The reference has no FFI layer: its boundary for this path is the C++ class API
+ * (model.h:56-216) called from main.cpp:1325-1382.  This header is the thin C boundary that
+ * sits directly under those method bodies; matfac_b200/host/ holds the C++ classes
+ * (Params / Data / Model / ModelMF / ModelInvPopMF / ModelDropoutSigmoid /
+ * ModelPoissonDropout) that keep the reference's signatures and call into this library.
+ * Each entry point names the reference statements it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a HOST pointer borrowed for the duration of the
+ *     call unless the name says "device"; the engine owns all device memory;
+ *   - every function returns 0 on success, non-zero on error with mfb_last_error() set;
+ *     CUDA errors are sticky and fatal for the engine (the C++ wrapper prints to stderr and
+ *     exit(-1)s, the reference's convention: model.cpp:1482-1483, main.cpp:62-64);
+ *   - an engine is bound to one CUDA device and one stream; calls are asynchronous on that
+ *     stream unless they return host data; not re-entrant (the reference's Model methods
+ *     are not either);
+ *   - there is NO CPU fallback: without a CUDA device mfb_create fails.
+ *
+ * Factor matrices cross the ABI row-major, [n][rank] fp32 with a leading dimension in
+ * floats; (row = user|item, col = latent dim) as in Model::uFac/iFac (model.h:37-38).
+ */
+#ifndef MFB_H
+#define MFB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mfb_engine mfb_engine;
+
+/* which rating matrix (Data::trainMat / valMat / testMat, datastruct.h:77-79) */
+enum { MFB_TRAIN = 0, MFB_VAL = 1, MFB_TEST = 2 };
+/* which factor set: the model being trained, or the best-validation snapshot (bestModel) */
+enum { MFB_CURRENT = 0, MFB_BEST = 1 };
+/* user side / item side */
+enum { MFB_USER = 0, MFB_ITEM = 1 };
+/* update / prediction rule */
+enum {
+  MFB_MF = 0,         /* ModelMF             modelMF.cpp:83-105,275-303     */
+  MFB_IFWMF = 1,      /* ModelInvPopMF       modelInvPopMF.cpp:152-180,356-391 */
+  MFB_TMF = 2,        /* ModelDropoutSigmoid modelDropoutSigmoid.cpp:145-194 */
+  MFB_TMFDROPOUT = 3  /* ModelPoissonDropout modelPoissonDropout.cpp:176-229 */
+};
+
+typedef struct mfb_config {
+  int32_t device;   /* CUDA device ordinal */
+  int32_t n_users;  /* Data::nUsers  (datastruct.cpp:23) */
+  int32_t n_items;  /* Data::nItems  (datastruct.cpp:91) */
+  int32_t rank;     /* Params::facDim */
+  int32_t reserved[4];
+} mfb_config;
+
+const char *mfb_last_error(void);
+/* number of kernels launched by all engines of this process since load (bench.py "gpu_launches") */
+uint64_t mfb_launch_count(void);
+
+int mfb_create(const mfb_config *cfg, mfb_engine **out);
+void mfb_destroy(mfb_engine *e);
+int mfb_sync(mfb_engine *e);
+
+/* Page-lock a host range so uploads run at full PCIe rate (optional). */
+int mfb_pin_host(void *ptr, uint64_t bytes);
+int mfb_unpin_host(void *ptr);
+
+/* ---- data (replaces the host-resident gk_csr_t of datastruct.cpp:16-18,49-51,72-74) ------
+ * CSR is required; CSC (gk_csr_CreateIndex(…, GK_CSR_COL)) is required for MFB_TRAIN when
+ * ALS or CCD++ will run, and may be NULL otherwise.  rowptr/colptr are int64 (ssize_t in
+ * gk_csr_t), indices int32, values fp32.  nrows may be smaller than n_users for val/test
+ * files that stop early; rows beyond nrows are empty. */
+int mfb_upload_csr(mfb_engine *e, int which, int32_t nrows, int32_t ncols, int64_t nnz,
+                   const int64_t *rowptr, const int32_t *rowind, const float *rowval,
+                   const int64_t *colptr, const int32_t *colind, const float *colval);
+
+/* invalidUsers / invalidItems (util.cpp:511-544 + modelMF.cpp:40-45) as one byte per id
+ * (1 = invalid), n_users resp. n_items entries.  Applied by mfb_eval, ALS and CCD++. */
+int mfb_set_masks(mfb_engine *e, const uint8_t *invalid_users, const uint8_t *invalid_items);
+
+/* Model::uFac / iFac in, e.g. the seeded initialisation of model.cpp:2331-2350. */
+int mfb_upload_factors(mfb_engine *e, const float *U, int64_t ldU, const float *V, int64_t ldV);
+/* which = MFB_CURRENT (*this) or MFB_BEST (bestModel); either pointer may be NULL. */
+int mfb_download_factors(mfb_engine *e, int which, float *U, int64_t ldU, float *V, int64_t ldV);
+
+/* Per-user / per-item auxiliaries of the frequency-aware models, all n_users / n_items long:
+ *   freq        userFreq / itemFreq (util.cpp:555-569) as int32
+ *   train       MFB_IFWMF: fp32 weight 1/(1+rho*invPop) of that side (modelInvPopMF.cpp:163-168);
+ *               MFB_TMF: int32 update rank of that side (modelDropoutSigmoid.cpp:158-170);
+ *               MFB_TMFDROPOUT: int32 Poisson mean lambda (modelPoissonDropout.cpp:189-196)
+ *   pred        int32 prediction rank of that side used by estRating
+ *               (modelDropoutSigmoid.cpp:5-24; modelPoissonDropout.cpp:5-23); ignored for IFWMF
+ * The side is picked per rating exactly as the reference does: the user's entry when
+ * userFreq[u] < itemFreq[i] (TMF) resp. itemFreq[i] > userFreq[u] (IFWMF), else the item's.
+ * variant = MFB_MF stores the frequencies only (the FreqAdap rule of CCD++ needs itemFreq).
+ * poisson_cdf (MFB_TMFDROPOUT only): [rank][rank] fp32, row l-1 = P(Poisson(l) <= k), k=0..rank-1. */
+int mfb_set_aux(mfb_engine *e, int variant, const int32_t *user_freq, const int32_t *item_freq,
+                const void *user_train, const void *item_train, const int32_t *user_pred,
+                const int32_t *item_pred, const float *poisson_cdf);
+
+/* ---- SGD (modelMF.cpp:4-151 train, :154-350 trainSGDPar, :1656-1810 hogTrain and the
+ *      IFWMF / TMF / TMF+Dropout trainers) --------------------------------------------------
+ * mfb_sgd_plan buckets the valid training ratings into the P x P stratum grid of
+ * modelMF.cpp:233-265 once (the reference rescans every rating in every sub-epoch, :283).
+ * user_part / item_part give the part of every id (-1 = not trained); P = 1 with NULL
+ * arrays makes the whole matrix one block (serial-SGD / Hogwild trainers).
+ * Inside a block the visiting order is the reference's: user-major, CSR order inside a row
+ * (modelMF.cpp:279-281); one sub-warp owns a user's run of ratings and keeps u in registers. */
+int mfb_sgd_plan(mfb_engine *e, int32_t P, const int32_t *user_part, const int32_t *item_part);
+
+/* One sub-epoch: the nb conflict-free blocks (user_part, item_part) of one updateSeq
+ * (util.cpp:1077-1107) run concurrently.  blocks = nb pairs.  seed/counter feed the
+ * counter-based Poisson draws of MFB_TMFDROPOUT. */
+int mfb_sgd_subepoch(mfb_engine *e, const int32_t *blocks, int32_t nb, int variant, float learn_rate,
+                     float ureg, float ireg, uint64_t seed, uint64_t counter);
+/* number of ratings the given blocks hold (for updates/s accounting) */
+int mfb_sgd_block_nnz(mfb_engine *e, const int32_t *blocks, int32_t nb, int64_t *nnz);
+
+/* ---- ALS (modelMF.cpp:795-882) -------------------------------------------------------------
+ * side = MFB_USER: for every valid user solve (sum_{i in row, r>0} v v^T + reg I) x = sum r v
+ * over the train CSR and overwrite U; MFB_ITEM: same over the CSC with the current U. */
+int mfb_als_half_step(mfb_engine *e, int side, float reg);
+
+/* ---- CCD++ (modelMF.cpp:1013-1121 trainCCDPP; :1258-1375 trainCCDPPFreqAdap) ---------------
+ * begin: residual := train values (gk_csr_Dup), U := 0 (:1020).  rank1: one pass of the k loop
+ * body (:1028-1120): add-back unless first_iter, `inner` alternations of the u_k / v_k
+ * closed-form updates, subtract, write column k.  item_freq_thresh > 0 applies the FreqAdap
+ * rule (:1336-1342): v_k(i) = 0 when itemFreq[i] < thresh and k > 0.  end: frees the residual. */
+int mfb_ccdpp_begin(mfb_engine *e);
+int mfb_ccdpp_rank1(mfb_engine *e, int32_t k, int first_iter, int32_t inner, float ureg, float ireg,
+                    int32_t item_freq_thresh);
+int mfb_ccdpp_end(mfb_engine *e);
+
+/* ---- evaluation (model.cpp:214-251 RMSE, :1770-1815 objective, modelInvPopMF.cpp:3-55) ----
+ * One fused pass over `which`: out[0] = sum of (weighted) squared errors over ratings whose
+ * user and item are valid, out[1] = their count, out[2] = sum_u |U_u|^2 and out[3] =
+ * sum_i |V_i|^2 over valid ids (the two norm terms are computed only when want_norms != 0).
+ * variant selects estRating (MFB_TMF / MFB_TMFDROPOUT truncate) and, for MFB_IFWMF with
+ * weighted != 0, the weighted error of the IFWMF objective.  factors = MFB_CURRENT | MFB_BEST. */
+int mfb_eval(mfb_engine *e, int which, int factors, int variant, int weighted, int want_norms,
+             double out[4]);
+
+/* bestModel = *this (model.cpp:1500-1504) and *this = bestModel (:1492) as device copies */
+int mfb_snapshot_best(mfb_engine *e);
+int mfb_restore_best(mfb_engine *e);
+
+/* ---- timing on the engine's stream (bench / per-epoch log line, modelMF.cpp:75,106-109) -- */
+int mfb_event_record(mfb_engine *e, int32_t slot /* 0..15 */);
+int mfb_event_elapsed_ms(mfb_engine *e, int32_t slot_a, int32_t slot_b, float *ms);
+
+/* ---- multi-GPU plumbing (one engine per rank; the exchange itself is NCCL on the host side)
+ * Device pointer and leading dimension (floats) of a factor matrix, and the engine's stream
+ * (a cudaStream_t) so a communicator can order its work after the engine's kernels. */
+int mfb_device_factors(mfb_engine *e, int side, void **dev_ptr, int64_t *ld);
+void *mfb_stream(mfb_engine *e);
+/* Gather / scatter `n` factor rows (ids = host int32 array) of `side` to / from a packed
+ * device buffer [n][ld] — moves a stratum's item block between ranks. */
+int mfb_pack_rows(mfb_engine *e, int side, const int32_t *ids, int32_t n, void *dev_buf);
+int mfb_unpack_rows(mfb_engine *e, int side, const int32_t *ids, int32_t n, const void *dev_buf);
+/* Restrict the rows this engine's ALS / CCD++ / eval kernels own to [begin, end) of `side`
+ * (row sharding across ranks); default is everything. */
+int mfb_set_row_range(mfb_engine *e, int side, int32_t begin, int32_t end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFB_H */

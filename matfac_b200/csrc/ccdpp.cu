@@ -1,0 +1,166 @@
+// CCD++ rank-one sweeps over the CSR and CSC residual copies.
+//
+// Replaces the k-loop body of ModelMF::trainCCDPP (modelMF.cpp:1027-1121) and
+// ::trainCCDPPFreqAdap (:1272-1375): residual add-back (:1034-1055), five alternations of the
+// closed-form u_k (:1062-1074) and v_k (:1078-1090) updates with fp64 numerator/denominator,
+// residual subtract (:1096-1116) and the column write-back (:1119-1120).  Both residual copies
+// (CSR order and CSC order) are kept, as gk_csr_Dup does (:1013), so that every pass streams.
+//
+// Pure streaming, HBM-bound: one warp per row segment reads indices and residuals with
+// coalesced loads and gathers the dense u_k / v_k vectors (a few MB, L2 resident).  Rows
+// longer than a chunk are split over warps that combine through fp64 atomics.
+#include "engine.h"
+
+namespace mfb {
+
+constexpr int kCcdChunk = 1024;
+
+struct CcdPass {
+  const int32_t *ind;
+  float *res;
+  const int32_t *seg_row, *seg_start, *seg_len, *seg_slot;
+  int n_seg;
+};
+
+// res[j] += sign * own[row] * other[ind[j]]
+__global__ void __launch_bounds__(256) ccd_resid_kernel(const CcdPass p, const float *__restrict__ own,
+                                                        const float *__restrict__ other, float sign) {
+  const int lane = threadIdx.x & 31;
+  const int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (seg >= p.n_seg) return;
+  const int row = p.seg_row[seg], start = p.seg_start[seg], len = p.seg_len[seg];
+  const float a = sign * __ldg(own + row);
+  for (int j = lane; j < len; j += 32) {
+    const int c = __ldg(p.ind + start + j);
+    // own*other is rounded to fp32 before it is added (modelMF.cpp:1041), hence no fma here
+    p.res[start + j] = __fadd_rn(p.res[start + j], __fmul_rn(a, __ldg(other + c)));
+  }
+}
+
+// own[row] = sum res*other / (reg + sum other^2), fp64 accumulation of fp32 products
+__global__ void __launch_bounds__(256) ccd_update_kernel(const CcdPass p, float *__restrict__ own,
+                                                         const float *__restrict__ other, float reg,
+                                                         double *__restrict__ acc, const Aux *__restrict__ aux_freq,
+                                                         int freq_thresh) {
+  const int lane = threadIdx.x & 31;
+  const int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (seg >= p.n_seg) return;
+  const int row = p.seg_row[seg], start = p.seg_start[seg], len = p.seg_len[seg], slot = p.seg_slot[seg];
+  double num = 0.0, den = 0.0;
+  for (int j = lane; j < len; j += 32) {
+    const int c = __ldg(p.ind + start + j);
+    const float o = __ldg(other + c);
+    num += (double)__fmul_rn(p.res[start + j], o);
+    den += (double)__fmul_rn(o, o);
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    num += __shfl_xor_sync(0xFFFFFFFFu, num, m);
+    den += __shfl_xor_sync(0xFFFFFFFFu, den, m);
+  }
+  if (lane == 0) {
+    if (slot < 0) {
+      float nv = (float)(num / ((double)reg + den));
+      if (freq_thresh > 0 && aux_freq[row].freq < freq_thresh) nv = 0.f;
+      own[row] = nv;
+    } else {
+      atomicAdd(acc + 2 * (size_t)slot, num);
+      atomicAdd(acc + 2 * (size_t)slot + 1, den);
+    }
+  }
+}
+
+__global__ void ccd_finalize_kernel(const int32_t *__restrict__ multi_row, int n_multi, double *__restrict__ acc,
+                                    float *__restrict__ own, float reg, const Aux *__restrict__ aux_freq,
+                                    int freq_thresh) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_multi) return;
+  const int row = multi_row[s];
+  float nv = (float)(acc[2 * (size_t)s] / ((double)reg + acc[2 * (size_t)s + 1]));
+  if (freq_thresh > 0 && aux_freq[row].freq < freq_thresh) nv = 0.f;
+  own[row] = nv;
+  acc[2 * (size_t)s] = 0.0;
+  acc[2 * (size_t)s + 1] = 0.0;
+}
+
+__global__ void col_extract_kernel(const float *__restrict__ F, int ld, int k, int n, float *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = F[(size_t)i * ld + k];
+}
+__global__ void col_insert_kernel(float *__restrict__ F, int ld, int k, int n, const float *__restrict__ in) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) F[(size_t)i * ld + k] = in[i];
+}
+
+int ccdpp_begin_impl(mfb_engine *e) {
+  DevCsr &m = e->mat[MFB_TRAIN];
+  cudaStream_t st = e->stream;
+  size_t nn = (size_t)(m.nnz > 0 ? m.nnz : 1);
+  if (!e->res_row) MFB_CUDA(cudaMalloc(&e->res_row, sizeof(float) * nn));
+  if (!e->res_col) MFB_CUDA(cudaMalloc(&e->res_col, sizeof(float) * nn));
+  if (!e->uk) MFB_CUDA(cudaMalloc(&e->uk, sizeof(float) * e->n_users));
+  if (!e->vk) MFB_CUDA(cudaMalloc(&e->vk, sizeof(float) * e->n_items));
+  // res = gk_csr_Dup(trainMat) (modelMF.cpp:1013); uFac.fill(0) (:1020)
+  MFB_CUDA(cudaMemcpyAsync(e->res_row, m.rowval, sizeof(float) * (size_t)m.nnz, cudaMemcpyDeviceToDevice, st));
+  MFB_CUDA(cudaMemcpyAsync(e->res_col, m.colval, sizeof(float) * (size_t)m.nnz, cudaMemcpyDeviceToDevice, st));
+  MFB_CUDA(cudaMemsetAsync(e->U, 0, sizeof(float) * (size_t)e->n_users * e->ld, st));
+  if (!m.ccd_rows.built)
+    MFB_TRY(build_seg_plan(e, m.rowptr, e->n_users, e->bad_user, e->row_begin[MFB_USER], e->row_end[MFB_USER],
+                           kCcdChunk, &m.ccd_rows));
+  if (!m.ccd_cols.built)
+    MFB_TRY(build_seg_plan(e, m.colptr, e->n_items, e->bad_item, e->row_begin[MFB_ITEM], e->row_end[MFB_ITEM],
+                           kCcdChunk, &m.ccd_cols));
+  size_t slots = (size_t)max(m.ccd_rows.n_multi, m.ccd_cols.n_multi);
+  if (slots > e->ccd_acc_slots) {
+    if (e->ccd_acc) MFB_CUDA(cudaFree(e->ccd_acc));
+    e->ccd_acc = nullptr;
+    MFB_CUDA(cudaMalloc(&e->ccd_acc, sizeof(double) * 2 * slots));
+    e->ccd_acc_slots = slots;
+  }
+  if (e->ccd_acc) MFB_CUDA(cudaMemsetAsync(e->ccd_acc, 0, sizeof(double) * 2 * e->ccd_acc_slots, st));
+  return 0;
+}
+
+int ccdpp_rank1_impl(mfb_engine *e, int32_t k, int first_iter, int32_t inner, float ureg, float ireg,
+                     int32_t item_freq_thresh) {
+  DevCsr &m = e->mat[MFB_TRAIN];
+  cudaStream_t st = e->stream;
+  const SegPlan &rp = m.ccd_rows, &cp = m.ccd_cols;
+  CcdPass rows{m.rowind, e->res_row, rp.row, rp.start, rp.len, rp.slot, rp.n_seg};
+  CcdPass cols{m.colind, e->res_col, cp.row, cp.start, cp.len, cp.slot, cp.n_seg};
+  const int tb = 256, wpb = tb / 32;
+  const int g_rows = (rp.n_seg + wpb - 1) / wpb, g_cols = (cp.n_seg + wpb - 1) / wpb;
+  // u_k = uFac.col(k); v_k = iFac.col(k)   (modelMF.cpp:1028-1029)
+  MFB_LAUNCH(col_extract_kernel, (e->n_users + 255) / 256, 256, 0, st, e->U, e->ld, k, e->n_users, e->uk);
+  MFB_LAUNCH(col_extract_kernel, (e->n_items + 255) / 256, 256, 0, st, e->V, e->ld, k, e->n_items, e->vk);
+  if (!first_iter) {
+    if (g_rows) MFB_LAUNCH(ccd_resid_kernel, g_rows, tb, 0, st, rows, e->uk, e->vk, 1.0f);
+    if (g_cols) MFB_LAUNCH(ccd_resid_kernel, g_cols, tb, 0, st, cols, e->vk, e->uk, 1.0f);
+  }
+  // the FreqAdap rule zeroes v_k of infrequent items for k > 0 (modelMF.cpp:1336-1342)
+  const int thresh = (item_freq_thresh > 0 && k > 0) ? item_freq_thresh : 0;
+  for (int s = 0; s < inner; s++) {
+    if (g_rows) MFB_LAUNCH(ccd_update_kernel, g_rows, tb, 0, st, rows, e->uk, e->vk, ureg, e->ccd_acc, e->aux_u, 0);
+    if (rp.n_multi)
+      MFB_LAUNCH(ccd_finalize_kernel, (rp.n_multi + 255) / 256, 256, 0, st, rp.multi_row, rp.n_multi, e->ccd_acc, e->uk,
+                 ureg, e->aux_u, 0);
+    if (g_cols) MFB_LAUNCH(ccd_update_kernel, g_cols, tb, 0, st, cols, e->vk, e->uk, ireg, e->ccd_acc, e->aux_i, thresh);
+    if (cp.n_multi)
+      MFB_LAUNCH(ccd_finalize_kernel, (cp.n_multi + 255) / 256, 256, 0, st, cp.multi_row, cp.n_multi, e->ccd_acc, e->vk,
+                 ireg, e->aux_i, thresh);
+  }
+  if (g_rows) MFB_LAUNCH(ccd_resid_kernel, g_rows, tb, 0, st, rows, e->uk, e->vk, -1.0f);
+  if (g_cols) MFB_LAUNCH(ccd_resid_kernel, g_cols, tb, 0, st, cols, e->vk, e->uk, -1.0f);
+  MFB_LAUNCH(col_insert_kernel, (e->n_users + 255) / 256, 256, 0, st, e->U, e->ld, k, e->n_users, e->uk);
+  MFB_LAUNCH(col_insert_kernel, (e->n_items + 255) / 256, 256, 0, st, e->V, e->ld, k, e->n_items, e->vk);
+  return 0;
+}
+
+int ccdpp_end_impl(mfb_engine *e) {
+  MFB_CUDA(cudaStreamSynchronize(e->stream));
+  cudaFree(e->res_row); cudaFree(e->res_col);
+  e->res_row = e->res_col = nullptr;
+  return 0;
+}
+
+}  // namespace mfb

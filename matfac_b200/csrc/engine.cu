@@ -1,0 +1,543 @@
+// Engine lifetime, device data layer and the C ABI entry points (include/mfb.h).
+//
+// Data layout in HBM (north_star item 1; replaces the host gk_csr_t + Eigen storage of
+// datastruct.cpp:16-18 and model.cpp:2337-2350):
+//   ratings   CSR and CSC as uploaded: int64 pointers, int32 indices, fp32 values;
+//   factors   row-major [n][ld] fp32, ld = rank rounded up to 4 floats so that a row is a
+//             whole number of 128-bit words; padding columns are kept at zero;
+//   masks     one byte per id; aux records 16 B per id.
+#include "engine.h"
+
+#include <cub/cub.cuh>
+
+#include <cstdio>
+#include <cstring>
+
+namespace mfb {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(const char *what, const char *file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "%s (%s:%d)", what, file, line);
+  g_last_error = buf;
+  return 1;
+}
+
+int fail_cuda(cudaError_t err, const char *expr, const char *file, int line) {
+  char buf[768];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) in `%s` (%s:%d)", (int)err, cudaGetErrorString(err), expr, file,
+           line);
+  g_last_error = buf;
+  return 2;
+}
+
+void SegPlan::release() {
+  cudaFree(row); cudaFree(start); cudaFree(len); cudaFree(slot); cudaFree(multi_row);
+  *this = SegPlan();
+}
+
+void DevCsr::release() {
+  cudaFree(rowptr); cudaFree(colptr); cudaFree(rowind); cudaFree(colind); cudaFree(rowval); cudaFree(colval);
+  eval_rows.release(); als_rows.release(); als_cols.release(); ccd_rows.release(); ccd_cols.release();
+  *this = DevCsr();
+}
+
+void SgdPlan::release() {
+  if (owns_ratings) { cudaFree(item); cudaFree(val); }
+  cudaFree(seg_user); cudaFree(seg_start); cudaFree(seg_len);
+  *this = SgdPlan();
+}
+
+int ensure_scratch(mfb_engine *e, size_t bytes) {
+  if (bytes <= e->scratch_bytes) return 0;
+  if (e->scratch) MFB_CUDA(cudaFree(e->scratch));
+  e->scratch = nullptr;
+  e->scratch_bytes = 0;
+  MFB_CUDA(cudaMalloc(&e->scratch, bytes));
+  e->scratch_bytes = bytes;
+  return 0;
+}
+
+// ---- segment plans -------------------------------------------------------------------------
+__global__ void seg_count_kernel(const int64_t *__restrict__ ptr, const uint8_t *__restrict__ mask, int32_t row_lo,
+                                 int32_t n, int32_t chunk, int32_t *__restrict__ nch, int32_t *__restrict__ multi) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int r = row_lo + i;
+  int64_t len = ptr[r + 1] - ptr[r];
+  int c = 0;
+  if (len > 0 && !(mask && mask[r])) c = chunk > 0 ? (int)((len + chunk - 1) / chunk) : 1;
+  nch[i] = c;
+  multi[i] = c > 1 ? 1 : 0;
+}
+
+__global__ void seg_fill_kernel(const int64_t *__restrict__ ptr, int32_t row_lo, int32_t n, int32_t chunk,
+                                const int32_t *__restrict__ nch, const int32_t *__restrict__ off,
+                                const int32_t *__restrict__ multi_off, int32_t *__restrict__ seg_row,
+                                int32_t *__restrict__ seg_start, int32_t *__restrict__ seg_len,
+                                int32_t *__restrict__ seg_slot, int32_t *__restrict__ multi_row) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = nch[i];
+  if (c == 0) return;
+  int r = row_lo + i;
+  int64_t b = ptr[r], len = ptr[r + 1] - b;
+  int slot = -1;
+  if (c > 1) {
+    slot = multi_off[i];
+    multi_row[slot] = r;
+  }
+  // even split so that no segment is tiny
+  int64_t per = (len + c - 1) / c;
+  for (int k = 0; k < c; k++) {
+    int s = off[i] + k;
+    int64_t lo = k * per, hi = lo + per < len ? lo + per : len;
+    seg_row[s] = r;
+    seg_start[s] = (int32_t)(b + lo);
+    seg_len[s] = (int32_t)(hi - lo);
+    seg_slot[s] = slot;
+  }
+}
+
+__global__ void iota_kernel(int32_t *p, int32_t n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+
+__global__ void gather4_kernel(const int32_t *__restrict__ perm, int32_t n, const int32_t *__restrict__ a0,
+                               const int32_t *__restrict__ a1, const int32_t *__restrict__ a2, int32_t *__restrict__ b0,
+                               int32_t *__restrict__ b1, int32_t *__restrict__ b2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int p = perm[i];
+  b0[i] = a0[p];
+  b1[i] = a1[p];
+  b2[i] = a2[p];
+}
+
+int build_seg_plan(mfb_engine *e, const int64_t *ptr, int32_t nrows, const uint8_t *mask, int32_t row_lo,
+                   int32_t row_hi, int32_t chunk, SegPlan *out) {
+  out->release();
+  if (row_hi > nrows) row_hi = nrows;
+  int32_t n = row_hi - row_lo;
+  out->built = true;
+  if (n <= 0 || ptr == nullptr) return 0;
+  cudaStream_t st = e->stream;
+  int32_t *nch, *multi, *off, *moff;
+  MFB_CUDA(cudaMalloc(&nch, sizeof(int32_t) * 4 * (size_t)(n + 1)));
+  multi = nch + (n + 1);
+  off = multi + (n + 1);
+  moff = off + (n + 1);
+  MFB_CUDA(cudaMemsetAsync(nch, 0, sizeof(int32_t) * 4 * (size_t)(n + 1), st));
+  int tb = 256, gb = (n + tb - 1) / tb;
+  MFB_LAUNCH(seg_count_kernel, gb, tb, 0, st, ptr, mask, row_lo, n, chunk, nch, multi);
+  size_t tmp_bytes = 0;
+  MFB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, nch, off, n + 1, st));
+  MFB_TRY(ensure_scratch(e, tmp_bytes));
+  MFB_CUDA(cub::DeviceScan::ExclusiveSum(e->scratch, tmp_bytes, nch, off, n + 1, st));
+  MFB_CUDA(cub::DeviceScan::ExclusiveSum(e->scratch, tmp_bytes, multi, moff, n + 1, st));
+  int32_t totals[2];
+  MFB_CUDA(cudaMemcpyAsync(&totals[0], off + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  MFB_CUDA(cudaMemcpyAsync(&totals[1], moff + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  MFB_CUDA(cudaStreamSynchronize(st));
+  int32_t ns = totals[0], nm = totals[1];
+  out->n_seg = ns;
+  out->n_multi = nm;
+  if (ns == 0) {
+    cudaFree(nch);
+    return 0;
+  }
+  // unsorted arrays + sort permutation
+  int32_t *tmp;
+  MFB_CUDA(cudaMalloc(&tmp, sizeof(int32_t) * 7 * (size_t)ns));
+  int32_t *u_row = tmp, *u_start = tmp + ns, *u_len = tmp + 2 * (size_t)ns, *u_slot = tmp + 3 * (size_t)ns,
+          *idx = tmp + 4 * (size_t)ns, *k_out = tmp + 5 * (size_t)ns, *p_out = tmp + 6 * (size_t)ns;
+  MFB_CUDA(cudaMalloc(&out->row, sizeof(int32_t) * ns));
+  MFB_CUDA(cudaMalloc(&out->start, sizeof(int32_t) * ns));
+  MFB_CUDA(cudaMalloc(&out->len, sizeof(int32_t) * ns));
+  MFB_CUDA(cudaMalloc(&out->slot, sizeof(int32_t) * ns));
+  MFB_CUDA(cudaMalloc(&out->multi_row, sizeof(int32_t) * (nm > 0 ? nm : 1)));
+  MFB_LAUNCH(seg_fill_kernel, gb, tb, 0, st, ptr, row_lo, n, chunk, nch, off, moff, u_row, u_start, u_len, u_slot,
+             out->multi_row);
+  int gs = (ns + tb - 1) / tb;
+  MFB_LAUNCH(iota_kernel, gs, tb, 0, st, idx, ns);
+  MFB_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, u_len, k_out, idx, p_out, ns, 0, 32, st));
+  MFB_TRY(ensure_scratch(e, tmp_bytes));
+  MFB_CUDA(cub::DeviceRadixSort::SortPairsDescending(e->scratch, tmp_bytes, u_len, k_out, idx, p_out, ns, 0, 32, st));
+  MFB_CUDA(cudaMemcpyAsync(out->len, k_out, sizeof(int32_t) * ns, cudaMemcpyDeviceToDevice, st));
+  MFB_LAUNCH(gather4_kernel, gs, tb, 0, st, p_out, ns, u_row, u_start, u_slot, out->row, out->start, out->slot);
+  MFB_CUDA(cudaMemcpyAsync(&out->max_len, out->len, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  MFB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(tmp);
+  cudaFree(nch);
+  return 0;
+}
+
+}  // namespace mfb
+
+using namespace mfb;
+
+// ---- C ABI ---------------------------------------------------------------------------------
+extern "C" const char *mfb_last_error(void) { return g_last_error.c_str(); }
+extern "C" uint64_t mfb_launch_count(void) { return g_launches.load(); }
+
+extern "C" int mfb_create(const mfb_config *cfg, mfb_engine **out) {
+  MFB_REQUIRE(cfg && out, "mfb_create: null argument");
+  MFB_REQUIRE(cfg->n_users > 0 && cfg->n_items > 0, "mfb_create: empty matrix");
+  MFB_REQUIRE(cfg->rank > 0 && cfg->rank <= 256, "mfb_create: rank must be in 1..256");
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev == 0) {
+    g_last_error = "mfb_create: no CUDA device (this engine has no CPU fallback)";
+    return 3;
+  }
+  MFB_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "mfb_create: bad device ordinal");
+  MFB_CUDA(cudaSetDevice(cfg->device));
+  mfb_engine *e = new mfb_engine();
+  e->device = cfg->device;
+  e->n_users = cfg->n_users;
+  e->n_items = cfg->n_items;
+  e->rank = cfg->rank;
+  e->ld = (cfg->rank + 3) / 4 * 4;
+  e->row_end[0] = e->n_users;
+  e->row_end[1] = e->n_items;
+  cudaDeviceProp prop;
+  MFB_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  e->sm_count = prop.multiProcessorCount;
+  MFB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 16; i++) MFB_CUDA(cudaEventCreate(&e->events[i]));
+  size_t ub = sizeof(float) * (size_t)e->n_users * e->ld, vb = sizeof(float) * (size_t)e->n_items * e->ld;
+  MFB_CUDA(cudaMalloc(&e->U, ub));
+  MFB_CUDA(cudaMalloc(&e->V, vb));
+  MFB_CUDA(cudaMalloc(&e->bestU, ub));
+  MFB_CUDA(cudaMalloc(&e->bestV, vb));
+  MFB_CUDA(cudaMemsetAsync(e->U, 0, ub, e->stream));
+  MFB_CUDA(cudaMemsetAsync(e->V, 0, vb, e->stream));
+  MFB_CUDA(cudaMemsetAsync(e->bestU, 0, ub, e->stream));
+  MFB_CUDA(cudaMemsetAsync(e->bestV, 0, vb, e->stream));
+  MFB_CUDA(cudaMalloc(&e->bad_user, e->n_users));
+  MFB_CUDA(cudaMalloc(&e->bad_item, e->n_items));
+  MFB_CUDA(cudaMemsetAsync(e->bad_user, 0, e->n_users, e->stream));
+  MFB_CUDA(cudaMemsetAsync(e->bad_item, 0, e->n_items, e->stream));
+  MFB_CUDA(cudaMalloc(&e->eval_out, sizeof(double) * 4));
+  MFB_CUDA(cudaMallocHost(&e->eval_out_host, sizeof(double) * 4));
+  *out = e;
+  return 0;
+}
+
+extern "C" void mfb_destroy(mfb_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  for (int w = 0; w < 3; w++) e->mat[w].release();
+  e->sgd.release();
+  cudaFree(e->U); cudaFree(e->V); cudaFree(e->bestU); cudaFree(e->bestV);
+  cudaFree(e->bad_user); cudaFree(e->bad_item); cudaFree(e->aux_u); cudaFree(e->aux_i); cudaFree(e->poisson_cdf);
+  cudaFree(e->eval_partial); cudaFree(e->eval_out); cudaFreeHost(e->eval_out_host);
+  cudaFree(e->als_ws); cudaFree(e->res_row); cudaFree(e->res_col); cudaFree(e->uk); cudaFree(e->vk);
+  cudaFree(e->ccd_acc); cudaFree(e->scratch);
+  for (int i = 0; i < 16; i++) cudaEventDestroy(e->events[i]);
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+extern "C" int mfb_sync(mfb_engine *e) {
+  MFB_REQUIRE(e, "null engine");
+  MFB_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+extern "C" int mfb_pin_host(void *ptr, uint64_t bytes) {
+  MFB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return 0;
+}
+extern "C" int mfb_unpin_host(void *ptr) {
+  MFB_CUDA(cudaHostUnregister(ptr));
+  return 0;
+}
+
+template <typename T>
+static int upload_array(mfb_engine *e, T **dst, const T *src, size_t n) {
+  MFB_CUDA(cudaMalloc(dst, sizeof(T) * (n > 0 ? n : 1)));
+  if (n > 0) MFB_CUDA(cudaMemcpyAsync(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice, e->stream));
+  return 0;
+}
+
+__global__ void fill_ptr_tail_kernel(int64_t *ptr, int32_t from, int32_t to, int64_t v) {
+  int i = from + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= to) ptr[i] = v;
+}
+
+extern "C" int mfb_upload_csr(mfb_engine *e, int which, int32_t nrows, int32_t ncols, int64_t nnz,
+                              const int64_t *rowptr, const int32_t *rowind, const float *rowval,
+                              const int64_t *colptr, const int32_t *colind, const float *colval) {
+  MFB_REQUIRE(e && which >= 0 && which < 3, "mfb_upload_csr: bad argument");
+  MFB_REQUIRE(rowptr && (nnz == 0 || (rowind && rowval)), "mfb_upload_csr: CSR arrays are required");
+  MFB_REQUIRE(nnz >= 0 && nnz < (int64_t)INT32_MAX, "mfb_upload_csr: nnz must fit in int32");
+  MFB_REQUIRE(nrows <= e->n_users && ncols <= e->n_items, "mfb_upload_csr: matrix larger than the engine");
+  MFB_CUDA(cudaSetDevice(e->device));
+  DevCsr &m = e->mat[which];
+  m.release();
+  if (which == MFB_TRAIN) e->sgd.release();
+  m.nrows = nrows;
+  m.ncols = ncols;
+  m.nnz = nnz;
+  // rowptr is padded to n_users + 1 entries so that every kernel can index any user
+  MFB_CUDA(cudaMalloc(&m.rowptr, sizeof(int64_t) * ((size_t)e->n_users + 1)));
+  MFB_CUDA(cudaMemcpyAsync(m.rowptr, rowptr, sizeof(int64_t) * ((size_t)nrows + 1), cudaMemcpyHostToDevice, e->stream));
+  if (nrows < e->n_users) {
+    int cnt = e->n_users - nrows;
+    MFB_LAUNCH(fill_ptr_tail_kernel, (cnt + 255) / 256, 256, 0, e->stream, m.rowptr, nrows + 1, e->n_users, nnz);
+  }
+  MFB_TRY(upload_array(e, &m.rowind, rowind, (size_t)nnz));
+  MFB_TRY(upload_array(e, &m.rowval, rowval, (size_t)nnz));
+  if (colptr) {
+    MFB_REQUIRE(nnz == 0 || (colind && colval), "mfb_upload_csr: incomplete CSC");
+    MFB_CUDA(cudaMalloc(&m.colptr, sizeof(int64_t) * ((size_t)e->n_items + 1)));
+    MFB_CUDA(cudaMemcpyAsync(m.colptr, colptr, sizeof(int64_t) * ((size_t)ncols + 1), cudaMemcpyHostToDevice, e->stream));
+    if (ncols < e->n_items) {
+      int cnt = e->n_items - ncols;
+      MFB_LAUNCH(fill_ptr_tail_kernel, (cnt + 255) / 256, 256, 0, e->stream, m.colptr, ncols + 1, e->n_items, nnz);
+    }
+    MFB_TRY(upload_array(e, &m.colind, colind, (size_t)nnz));
+    MFB_TRY(upload_array(e, &m.colval, colval, (size_t)nnz));
+  }
+  // the host arrays are only borrowed for the duration of the call
+  MFB_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+static void invalidate_plans(mfb_engine *e) {
+  for (int w = 0; w < 3; w++) {
+    e->mat[w].eval_rows.release();
+    e->mat[w].als_rows.release();
+    e->mat[w].als_cols.release();
+    e->mat[w].ccd_rows.release();
+    e->mat[w].ccd_cols.release();
+  }
+}
+
+extern "C" int mfb_set_masks(mfb_engine *e, const uint8_t *invalid_users, const uint8_t *invalid_items) {
+  MFB_REQUIRE(e && invalid_users && invalid_items, "mfb_set_masks: null argument");
+  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(cudaMemcpyAsync(e->bad_user, invalid_users, e->n_users, cudaMemcpyHostToDevice, e->stream));
+  MFB_CUDA(cudaMemcpyAsync(e->bad_item, invalid_items, e->n_items, cudaMemcpyHostToDevice, e->stream));
+  MFB_CUDA(cudaStreamSynchronize(e->stream));
+  invalidate_plans(e);
+  return 0;
+}
+
+extern "C" int mfb_set_row_range(mfb_engine *e, int side, int32_t begin, int32_t end) {
+  MFB_REQUIRE(e && (side == MFB_USER || side == MFB_ITEM), "mfb_set_row_range: bad argument");
+  int n = side == MFB_USER ? e->n_users : e->n_items;
+  MFB_REQUIRE(begin >= 0 && begin <= end && end <= n, "mfb_set_row_range: bad range");
+  e->row_begin[side] = begin;
+  e->row_end[side] = end;
+  invalidate_plans(e);
+  return 0;
+}
+
+extern "C" int mfb_upload_factors(mfb_engine *e, const float *U, int64_t ldU, const float *V, int64_t ldV) {
+  MFB_REQUIRE(e, "null engine");
+  MFB_CUDA(cudaSetDevice(e->device));
+  size_t w = sizeof(float) * (size_t)e->rank, dp = sizeof(float) * (size_t)e->ld;
+  if (U) {
+    MFB_REQUIRE(ldU >= e->rank, "mfb_upload_factors: ldU < rank");
+    MFB_CUDA(cudaMemcpy2DAsync(e->U, dp, U, sizeof(float) * (size_t)ldU, w, e->n_users, cudaMemcpyHostToDevice, e->stream));
+  }
+  if (V) {
+    MFB_REQUIRE(ldV >= e->rank, "mfb_upload_factors: ldV < rank");
+    MFB_CUDA(cudaMemcpy2DAsync(e->V, dp, V, sizeof(float) * (size_t)ldV, w, e->n_items, cudaMemcpyHostToDevice, e->stream));
+  }
+  MFB_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+extern "C" int mfb_download_factors(mfb_engine *e, int which, float *U, int64_t ldU, float *V, int64_t ldV) {
+  MFB_REQUIRE(e && (which == MFB_CURRENT || which == MFB_BEST), "mfb_download_factors: bad argument");
+  MFB_CUDA(cudaSetDevice(e->device));
+  const float *su = which == MFB_BEST ? e->bestU : e->U, *sv = which == MFB_BEST ? e->bestV : e->V;
+  size_t w = sizeof(float) * (size_t)e->rank, sp = sizeof(float) * (size_t)e->ld;
+  if (U) {
+    MFB_REQUIRE(ldU >= e->rank, "mfb_download_factors: ldU < rank");
+    MFB_CUDA(cudaMemcpy2DAsync(U, sizeof(float) * (size_t)ldU, su, sp, w, e->n_users, cudaMemcpyDeviceToHost, e->stream));
+  }
+  if (V) {
+    MFB_REQUIRE(ldV >= e->rank, "mfb_download_factors: ldV < rank");
+    MFB_CUDA(cudaMemcpy2DAsync(V, sizeof(float) * (size_t)ldV, sv, sp, w, e->n_items, cudaMemcpyDeviceToHost, e->stream));
+  }
+  MFB_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+extern "C" int mfb_set_aux(mfb_engine *e, int variant, const int32_t *user_freq, const int32_t *item_freq,
+                           const void *user_train, const void *item_train, const int32_t *user_pred,
+                           const int32_t *item_pred, const float *poisson_cdf) {
+  MFB_REQUIRE(e && user_freq && item_freq, "mfb_set_aux: null argument");
+  MFB_REQUIRE(variant >= MFB_MF && variant <= MFB_TMFDROPOUT, "mfb_set_aux: bad variant");
+  MFB_REQUIRE(variant == MFB_MF || (user_train && item_train), "mfb_set_aux: training payloads required");
+  MFB_REQUIRE(variant == MFB_MF || variant == MFB_IFWMF || (user_pred && item_pred), "mfb_set_aux: prediction ranks required");
+  MFB_REQUIRE(variant != MFB_TMFDROPOUT || poisson_cdf, "mfb_set_aux: poisson_cdf required");
+  MFB_CUDA(cudaSetDevice(e->device));
+  const int32_t *ut = (const int32_t *)user_train, *it = (const int32_t *)item_train;
+  std::vector<Aux> hu(e->n_users), hi(e->n_items);
+  for (int u = 0; u < e->n_users; u++) hu[u] = Aux{user_freq[u], ut ? ut[u] : 0, user_pred ? user_pred[u] : 0, 0};
+  for (int i = 0; i < e->n_items; i++) hi[i] = Aux{item_freq[i], it ? it[i] : 0, item_pred ? item_pred[i] : 0, 0};
+  if (!e->aux_u) MFB_CUDA(cudaMalloc(&e->aux_u, sizeof(Aux) * e->n_users));
+  if (!e->aux_i) MFB_CUDA(cudaMalloc(&e->aux_i, sizeof(Aux) * e->n_items));
+  MFB_CUDA(cudaMemcpyAsync(e->aux_u, hu.data(), sizeof(Aux) * e->n_users, cudaMemcpyHostToDevice, e->stream));
+  MFB_CUDA(cudaMemcpyAsync(e->aux_i, hi.data(), sizeof(Aux) * e->n_items, cudaMemcpyHostToDevice, e->stream));
+  if (poisson_cdf) {
+    size_t b = sizeof(float) * (size_t)e->rank * e->rank;
+    if (!e->poisson_cdf) MFB_CUDA(cudaMalloc(&e->poisson_cdf, b));
+    MFB_CUDA(cudaMemcpyAsync(e->poisson_cdf, poisson_cdf, b, cudaMemcpyHostToDevice, e->stream));
+  }
+  MFB_CUDA(cudaStreamSynchronize(e->stream));
+  e->aux_variant = variant;
+  return 0;
+}
+
+extern "C" int mfb_sgd_plan(mfb_engine *e, int32_t P, const int32_t *user_part, const int32_t *item_part) {
+  MFB_REQUIRE(e, "null engine");
+  MFB_REQUIRE(P >= 1 && P <= kMaxBlocks, "mfb_sgd_plan: P must be in 1..64");
+  MFB_REQUIRE(P == 1 || (user_part && item_part), "mfb_sgd_plan: partitions required for P > 1");
+  MFB_REQUIRE(e->mat[MFB_TRAIN].rowptr, "mfb_sgd_plan: upload the training matrix first");
+  MFB_CUDA(cudaSetDevice(e->device));
+  return sgd_plan_build(e, P, user_part, item_part);
+}
+
+extern "C" int mfb_sgd_subepoch(mfb_engine *e, const int32_t *blocks, int32_t nb, int variant, float learn_rate,
+                                float ureg, float ireg, uint64_t seed, uint64_t counter) {
+  MFB_REQUIRE(e && blocks, "mfb_sgd_subepoch: null argument");
+  MFB_REQUIRE(e->sgd.built, "mfb_sgd_subepoch: call mfb_sgd_plan first");
+  MFB_REQUIRE(nb >= 1 && nb <= kMaxBlocks, "mfb_sgd_subepoch: bad block count");
+  MFB_REQUIRE(variant >= MFB_MF && variant <= MFB_TMFDROPOUT, "mfb_sgd_subepoch: bad variant");
+  MFB_REQUIRE(variant == MFB_MF || e->aux_variant == variant, "mfb_sgd_subepoch: mfb_set_aux not called for this variant");
+  for (int i = 0; i < nb; i++)
+    MFB_REQUIRE(blocks[2 * i] >= 0 && blocks[2 * i] < e->sgd.P && blocks[2 * i + 1] >= 0 && blocks[2 * i + 1] < e->sgd.P,
+                "mfb_sgd_subepoch: block index out of range");
+  MFB_CUDA(cudaSetDevice(e->device));
+  return sgd_subepoch_launch(e, blocks, nb, variant, learn_rate, ureg, ireg, seed, counter);
+}
+
+extern "C" int mfb_sgd_block_nnz(mfb_engine *e, const int32_t *blocks, int32_t nb, int64_t *nnz) {
+  MFB_REQUIRE(e && blocks && nnz && e->sgd.built, "mfb_sgd_block_nnz: bad argument");
+  int64_t s = 0;
+  for (int i = 0; i < nb; i++) {
+    int a = blocks[2 * i], b = blocks[2 * i + 1];
+    MFB_REQUIRE(a >= 0 && a < e->sgd.P && b >= 0 && b < e->sgd.P, "mfb_sgd_block_nnz: block index out of range");
+    s += e->sgd.blk_nnz[(size_t)a * e->sgd.P + b];
+  }
+  *nnz = s;
+  return 0;
+}
+
+extern "C" int mfb_als_half_step(mfb_engine *e, int side, float reg) {
+  MFB_REQUIRE(e && (side == MFB_USER || side == MFB_ITEM), "mfb_als_half_step: bad argument");
+  MFB_REQUIRE(e->rank <= 128, "mfb_als_half_step: rank must be <= 128");
+  const DevCsr &m = e->mat[MFB_TRAIN];
+  MFB_REQUIRE(m.rowptr && (side == MFB_USER || m.colptr), "mfb_als_half_step: training CSR/CSC not uploaded");
+  MFB_CUDA(cudaSetDevice(e->device));
+  return als_half_step_launch(e, side, reg);
+}
+
+extern "C" int mfb_ccdpp_begin(mfb_engine *e) {
+  MFB_REQUIRE(e, "null engine");
+  MFB_REQUIRE(e->mat[MFB_TRAIN].rowptr && e->mat[MFB_TRAIN].colptr, "mfb_ccdpp_begin: training CSR and CSC required");
+  MFB_CUDA(cudaSetDevice(e->device));
+  return ccdpp_begin_impl(e);
+}
+extern "C" int mfb_ccdpp_rank1(mfb_engine *e, int32_t k, int first_iter, int32_t inner, float ureg, float ireg,
+                               int32_t item_freq_thresh) {
+  MFB_REQUIRE(e && e->res_row, "mfb_ccdpp_rank1: call mfb_ccdpp_begin first");
+  MFB_REQUIRE(k >= 0 && k < e->rank && inner >= 0, "mfb_ccdpp_rank1: bad argument");
+  MFB_REQUIRE(item_freq_thresh <= 0 || e->aux_i, "mfb_ccdpp_rank1: item frequencies (mfb_set_aux) required");
+  MFB_CUDA(cudaSetDevice(e->device));
+  return ccdpp_rank1_impl(e, k, first_iter, inner, ureg, ireg, item_freq_thresh);
+}
+extern "C" int mfb_ccdpp_end(mfb_engine *e) {
+  MFB_REQUIRE(e, "null engine");
+  MFB_CUDA(cudaSetDevice(e->device));
+  return ccdpp_end_impl(e);
+}
+
+extern "C" int mfb_eval(mfb_engine *e, int which, int factors, int variant, int weighted, int want_norms,
+                        double out[4]) {
+  MFB_REQUIRE(e && out && which >= 0 && which < 3, "mfb_eval: bad argument");
+  MFB_REQUIRE(factors == MFB_CURRENT || factors == MFB_BEST, "mfb_eval: bad factor set");
+  MFB_REQUIRE(variant >= MFB_MF && variant <= MFB_TMFDROPOUT, "mfb_eval: bad variant");
+  MFB_REQUIRE(e->mat[which].rowptr, "mfb_eval: matrix not uploaded");
+  MFB_REQUIRE(variant == MFB_MF || e->aux_variant == variant, "mfb_eval: mfb_set_aux not called for this variant");
+  MFB_CUDA(cudaSetDevice(e->device));
+  return eval_launch(e, which, factors, variant, weighted, want_norms, out);
+}
+
+extern "C" int mfb_snapshot_best(mfb_engine *e) {
+  MFB_REQUIRE(e, "null engine");
+  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(cudaMemcpyAsync(e->bestU, e->U, sizeof(float) * (size_t)e->n_users * e->ld, cudaMemcpyDeviceToDevice, e->stream));
+  MFB_CUDA(cudaMemcpyAsync(e->bestV, e->V, sizeof(float) * (size_t)e->n_items * e->ld, cudaMemcpyDeviceToDevice, e->stream));
+  return 0;
+}
+extern "C" int mfb_restore_best(mfb_engine *e) {
+  MFB_REQUIRE(e, "null engine");
+  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(cudaMemcpyAsync(e->U, e->bestU, sizeof(float) * (size_t)e->n_users * e->ld, cudaMemcpyDeviceToDevice, e->stream));
+  MFB_CUDA(cudaMemcpyAsync(e->V, e->bestV, sizeof(float) * (size_t)e->n_items * e->ld, cudaMemcpyDeviceToDevice, e->stream));
+  return 0;
+}
+
+extern "C" int mfb_event_record(mfb_engine *e, int32_t slot) {
+  MFB_REQUIRE(e && slot >= 0 && slot < 16, "mfb_event_record: bad slot");
+  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(cudaEventRecord(e->events[slot], e->stream));
+  return 0;
+}
+extern "C" int mfb_event_elapsed_ms(mfb_engine *e, int32_t a, int32_t b, float *ms) {
+  MFB_REQUIRE(e && ms && a >= 0 && a < 16 && b >= 0 && b < 16, "mfb_event_elapsed_ms: bad argument");
+  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(cudaEventSynchronize(e->events[b]));
+  MFB_CUDA(cudaEventElapsedTime(ms, e->events[a], e->events[b]));
+  return 0;
+}
+
+extern "C" int mfb_device_factors(mfb_engine *e, int side, void **dev_ptr, int64_t *ld) {
+  MFB_REQUIRE(e && dev_ptr && ld && (side == MFB_USER || side == MFB_ITEM), "mfb_device_factors: bad argument");
+  *dev_ptr = side == MFB_USER ? e->U : e->V;
+  *ld = e->ld;
+  return 0;
+}
+extern "C" void *mfb_stream(mfb_engine *e) { return e ? (void *)e->stream : nullptr; }
+
+__global__ void pack_rows_kernel(const float4 *__restrict__ src, const int32_t *__restrict__ ids, int32_t n, int nq,
+                                 float4 *__restrict__ dst, int unpack) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)n * nq) return;
+  int r = (int)(t / nq), q = (int)(t % nq);
+  int64_t a = (int64_t)ids[r] * nq + q;
+  if (unpack) const_cast<float4 *>(src)[a] = dst[t];
+  else dst[t] = src[a];
+}
+
+static int pack_impl(mfb_engine *e, int side, const int32_t *ids, int32_t n, void *dev_buf, int unpack) {
+  MFB_REQUIRE(e && ids && dev_buf && n >= 0 && (side == MFB_USER || side == MFB_ITEM), "mfb_pack_rows: bad argument");
+  if (n == 0) return 0;
+  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_TRY(ensure_scratch(e, sizeof(int32_t) * (size_t)n));
+  MFB_CUDA(cudaMemcpyAsync(e->scratch, ids, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+  int nq = e->ld / 4;
+  int64_t tot = (int64_t)n * nq;
+  float *base = side == MFB_USER ? e->U : e->V;
+  MFB_LAUNCH(pack_rows_kernel, (unsigned)((tot + 255) / 256), 256, 0, e->stream, (const float4 *)base,
+             (const int32_t *)e->scratch, n, nq, (float4 *)dev_buf, unpack);
+  MFB_CUDA(cudaStreamSynchronize(e->stream));  // ids are borrowed; scratch is reused
+  return 0;
+}
+extern "C" int mfb_pack_rows(mfb_engine *e, int side, const int32_t *ids, int32_t n, void *dev_buf) {
+  return pack_impl(e, side, ids, n, dev_buf, 0);
+}
+extern "C" int mfb_unpack_rows(mfb_engine *e, int side, const int32_t *ids, int32_t n, const void *dev_buf) {
+  return pack_impl(e, side, ids, n, const_cast<void *>(dev_buf), 1);
+}

@@ -1,0 +1,156 @@
+// Internal declarations shared by the engine's translation units (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/mfb.h"
+
+namespace mfb {
+
+extern thread_local std::string g_last_error;
+extern std::atomic<uint64_t> g_launches;
+
+int fail(const char *what, const char *file, int line);
+int fail_cuda(cudaError_t err, const char *expr, const char *file, int line);
+
+#define MFB_CUDA(expr)                                                     \
+  do {                                                                     \
+    cudaError_t _e = (expr);                                               \
+    if (_e != cudaSuccess) return mfb::fail_cuda(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+#define MFB_TRY(expr)          \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != 0) return _r;    \
+  } while (0)
+#define MFB_REQUIRE(cond, msg)                                   \
+  do {                                                           \
+    if (!(cond)) return mfb::fail(msg, __FILE__, __LINE__);      \
+  } while (0)
+// every kernel launch goes through this so that mfb_launch_count() is exact
+#define MFB_LAUNCH(kernel, grid, block, smem, stream, ...)                \
+  do {                                                                    \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);           \
+    mfb::g_launches.fetch_add(1, std::memory_order_relaxed);              \
+    MFB_CUDA(cudaGetLastError());                                         \
+  } while (0)
+
+// A list of row segments of a CSR/CSC matrix, sorted by length (longest first) so that the
+// block scheduler starts the long ones first.  Rows longer than `chunk` are split; such rows
+// get a slot in a per-row accumulator workspace (slot >= 0), single-segment rows slot = -1.
+struct SegPlan {
+  int32_t n_seg = 0;
+  int32_t n_multi = 0;         // rows split over several segments
+  int32_t max_len = 0;
+  int32_t *row = nullptr;      // [n_seg]
+  int32_t *start = nullptr;    // [n_seg] offset into the index/value arrays
+  int32_t *len = nullptr;      // [n_seg]
+  int32_t *slot = nullptr;     // [n_seg]
+  int32_t *multi_row = nullptr;  // [n_multi] row id of each slot
+  bool built = false;
+  void release();
+};
+
+struct DevCsr {
+  int32_t nrows = 0, ncols = 0;
+  int64_t nnz = 0;
+  int64_t *rowptr = nullptr, *colptr = nullptr;
+  int32_t *rowind = nullptr, *colind = nullptr;
+  float *rowval = nullptr, *colval = nullptr;
+  SegPlan eval_rows;   // chunked, for mfb_eval
+  SegPlan als_rows, als_cols;
+  SegPlan ccd_rows, ccd_cols;
+  void release();
+};
+
+// 16-byte per-id record of the frequency-aware models (see mfb_set_aux)
+struct __align__(16) Aux {
+  int32_t freq;
+  int32_t train;  // IFWMF: float bits; TMF: rank; TMFDROPOUT: lambda
+  int32_t pred;
+  int32_t pad;
+};
+
+constexpr int kMaxBlocks = 64;  // blocks per sub-epoch launch (P <= 64)
+
+struct SgdPlan {
+  int32_t P = 0;
+  int64_t nnz = 0;
+  int32_t n_seg = 0;
+  // ratings reordered block-major / user-major / CSR order; for P == 1 these alias the CSR
+  int32_t *item = nullptr;
+  float *val = nullptr;
+  bool owns_ratings = false;
+  int32_t *seg_user = nullptr, *seg_start = nullptr, *seg_len = nullptr;
+  std::vector<int32_t> blk_seg_off, blk_seg_cnt;  // [P*P]
+  std::vector<int64_t> blk_nnz;                   // [P*P]
+  bool built = false;
+  void release();
+};
+
+}  // namespace mfb
+
+struct mfb_engine {
+  int device = 0;
+  int n_users = 0, n_items = 0, rank = 0;
+  int ld = 0;  // leading dimension of the device factor matrices in floats (rank rounded up to 4)
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t events[16] = {};
+
+  float *U = nullptr, *V = nullptr;          // [n][ld] fp32, padding columns are zero
+  float *bestU = nullptr, *bestV = nullptr;  // bestModel snapshot
+  uint8_t *bad_user = nullptr, *bad_item = nullptr;  // 1 = invalid
+  mfb::Aux *aux_u = nullptr, *aux_i = nullptr;
+  float *poisson_cdf = nullptr;              // [rank][rank]
+  int aux_variant = -1;
+
+  mfb::DevCsr mat[3];
+  mfb::SgdPlan sgd;
+  int32_t row_begin[2] = {0, 0}, row_end[2] = {0, 0};
+
+  // evaluation scratch
+  double *eval_partial = nullptr;  // [eval_partial_cap][2]
+  int32_t eval_partial_cap = 0;
+  double *eval_out = nullptr;      // [4] device
+  double *eval_out_host = nullptr; // [4] pinned
+
+  // ALS scratch: per split row, an rp x rp Gram + rp rhs accumulator
+  float *als_ws = nullptr;
+  size_t als_ws_bytes = 0;
+
+  // CCD++ state
+  float *res_row = nullptr, *res_col = nullptr;  // residual (CSR order / CSC order)
+  float *uk = nullptr, *vk = nullptr;
+  double *ccd_acc = nullptr;  // [slots][2]
+  size_t ccd_acc_slots = 0;
+
+  // generic scratch for plan building (grown on demand)
+  void *scratch = nullptr;
+  size_t scratch_bytes = 0;
+};
+
+namespace mfb {
+
+int ensure_scratch(mfb_engine *e, size_t bytes);
+// Builds a SegPlan over rows [row_lo,row_hi) of ptr (device int64 [nrows+1]); rows whose mask
+// byte is set (mask may be null) or that are empty produce no segment.
+int build_seg_plan(mfb_engine *e, const int64_t *ptr, int32_t nrows, const uint8_t *mask, int32_t row_lo,
+                   int32_t row_hi, int32_t chunk, SegPlan *out);
+
+int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int32_t *item_part);
+int sgd_subepoch_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int variant, float lr, float ureg,
+                        float ireg, uint64_t seed, uint64_t counter);
+int eval_launch(mfb_engine *e, int which, int factors, int variant, int weighted, int want_norms, double out[4]);
+int als_half_step_launch(mfb_engine *e, int side, float reg);
+int ccdpp_begin_impl(mfb_engine *e);
+int ccdpp_rank1_impl(mfb_engine *e, int32_t k, int first_iter, int32_t inner, float ureg, float ireg,
+                     int32_t item_freq_thresh);
+int ccdpp_end_impl(mfb_engine *e);
+
+}  // namespace mfb

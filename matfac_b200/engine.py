@@ -1,0 +1,258 @@
+"""ctypes binding of the engine's C ABI (include/mfb.h -> matfac_b200/libmfb.so).
+
+This is the same boundary the C++ host classes in matfac_b200/host/ call; the Python side exists
+for the parity tests and bench.py.  There is no CPU fallback: if the shared library is missing
+or no CUDA device is present, construction fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmfb.so")
+
+TRAIN, VAL, TEST = 0, 1, 2
+CURRENT, BEST = 0, 1
+USER, ITEM = 0, 1
+MF, IFWMF, TMF, TMFDROPOUT = 0, 1, 2, 3
+VARIANT = {"mf": MF, "IFWMF": IFWMF, "TMF": TMF, "TMFDropout": TMFDROPOUT}
+
+# every symbol include/mfb.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "mfb_last_error", "mfb_launch_count", "mfb_create", "mfb_destroy", "mfb_sync", "mfb_pin_host",
+    "mfb_unpin_host", "mfb_upload_csr", "mfb_set_masks", "mfb_upload_factors", "mfb_download_factors",
+    "mfb_set_aux", "mfb_sgd_plan", "mfb_sgd_subepoch", "mfb_sgd_block_nnz", "mfb_als_half_step",
+    "mfb_ccdpp_begin", "mfb_ccdpp_rank1", "mfb_ccdpp_end", "mfb_eval", "mfb_snapshot_best",
+    "mfb_restore_best", "mfb_event_record", "mfb_event_elapsed_ms", "mfb_device_factors", "mfb_stream",
+    "mfb_pack_rows", "mfb_unpack_rows", "mfb_set_row_range",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("n_users", C.c_int32), ("n_items", C.c_int32), ("rank", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """Load libmfb.so and declare the prototypes.  Raises if the CUDA extension is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(matfac_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64
+    L.mfb_last_error.restype = C.c_char_p
+    L.mfb_launch_count.restype = u64
+    L.mfb_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.mfb_destroy.argtypes = [vp]
+    L.mfb_destroy.restype = None
+    L.mfb_sync.argtypes = [vp]
+    L.mfb_pin_host.argtypes = [vp, u64]
+    L.mfb_unpin_host.argtypes = [vp]
+    L.mfb_upload_csr.argtypes = [vp, C.c_int, i32, i32, i64, vp, vp, vp, vp, vp, vp]
+    L.mfb_set_masks.argtypes = [vp, vp, vp]
+    L.mfb_upload_factors.argtypes = [vp, vp, i64, vp, i64]
+    L.mfb_download_factors.argtypes = [vp, C.c_int, vp, i64, vp, i64]
+    L.mfb_set_aux.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+    L.mfb_sgd_plan.argtypes = [vp, i32, vp, vp]
+    L.mfb_sgd_subepoch.argtypes = [vp, vp, i32, C.c_int, f32, f32, f32, u64, u64]
+    L.mfb_sgd_block_nnz.argtypes = [vp, vp, i32, C.POINTER(i64)]
+    L.mfb_als_half_step.argtypes = [vp, C.c_int, f32]
+    L.mfb_ccdpp_begin.argtypes = [vp]
+    L.mfb_ccdpp_rank1.argtypes = [vp, i32, C.c_int, i32, f32, f32, i32]
+    L.mfb_ccdpp_end.argtypes = [vp]
+    L.mfb_eval.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.mfb_snapshot_best.argtypes = [vp]
+    L.mfb_restore_best.argtypes = [vp]
+    L.mfb_event_record.argtypes = [vp, i32]
+    L.mfb_event_elapsed_ms.argtypes = [vp, i32, i32, C.POINTER(f32)]
+    L.mfb_device_factors.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i64)]
+    L.mfb_stream.argtypes = [vp]
+    L.mfb_stream.restype = vp
+    L.mfb_pack_rows.argtypes = [vp, C.c_int, vp, i32, vp]
+    L.mfb_unpack_rows.argtypes = [vp, C.c_int, vp, i32, vp]
+    L.mfb_set_row_range.argtypes = [vp, C.c_int, i32, i32]
+    _lib = L
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _arr(a, dtype):
+    return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+
+
+class Engine:
+    """One engine = one CUDA device + one stream (mfb_engine)."""
+
+    def __init__(self, n_users: int, n_items: int, rank: int, device: int = 0):
+        self.L = load_library()
+        self.n_users, self.n_items, self.rank = int(n_users), int(n_items), int(rank)
+        cfg = Config(device, n_users, n_items, rank)
+        h = C.c_void_p()
+        self._check(self.L.mfb_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError(self.L.mfb_last_error().decode(errors="replace"))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mfb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- data ----
+    def upload_csr(self, which, mat, with_csc=True):
+        """mat: object with nrows, ncols, rowptr, rowind, rowval[, colptr, colind, colval]."""
+        rp, ri, rv = _arr(mat.rowptr, np.int64), _arr(mat.rowind, np.int32), _arr(mat.rowval, np.float32)
+        cp = ci = cv = None
+        if with_csc and getattr(mat, "colptr", None) is not None:
+            cp, ci, cv = _arr(mat.colptr, np.int64), _arr(mat.colind, np.int32), _arr(mat.colval, np.float32)
+        self._check(self.L.mfb_upload_csr(self.h, which, mat.nrows, mat.ncols, int(rp[-1]), _p(rp), _p(ri), _p(rv),
+                                          _p(cp), _p(ci), _p(cv)))
+
+    def set_masks(self, invalid_users, invalid_items):
+        iu, ii = _arr(invalid_users, np.uint8), _arr(invalid_items, np.uint8)
+        assert iu.shape[0] == self.n_users and ii.shape[0] == self.n_items
+        self._check(self.L.mfb_set_masks(self.h, _p(iu), _p(ii)))
+
+    def upload_factors(self, U=None, V=None):
+        U, V = _arr(U, np.float32), _arr(V, np.float32)
+        self._check(self.L.mfb_upload_factors(self.h, _p(U), 0 if U is None else U.shape[1], _p(V),
+                                              0 if V is None else V.shape[1]))
+
+    def download_factors(self, which=CURRENT):
+        U = np.empty((self.n_users, self.rank), np.float32)
+        V = np.empty((self.n_items, self.rank), np.float32)
+        self._check(self.L.mfb_download_factors(self.h, which, _p(U), self.rank, _p(V), self.rank))
+        return U, V
+
+    def set_aux(self, variant, user_freq, item_freq, user_train=None, item_train=None, user_pred=None,
+                item_pred=None, poisson_cdf=None):
+        def pad(a, n, dt):
+            if a is None:
+                return None
+            out = np.zeros(n, dtype=dt)
+            a = np.asarray(a)
+            out[:a.shape[0]] = a.astype(dt)
+            return out
+        tdt = np.float32 if variant == IFWMF else np.int32
+        args = [pad(user_freq, self.n_users, np.int32), pad(item_freq, self.n_items, np.int32),
+                pad(user_train, self.n_users, tdt), pad(item_train, self.n_items, tdt),
+                pad(user_pred, self.n_users, np.int32), pad(item_pred, self.n_items, np.int32),
+                _arr(poisson_cdf, np.float32)]
+        self._check(self.L.mfb_set_aux(self.h, variant, *[_p(a) for a in args]))
+
+    # ---- SGD ----
+    def sgd_plan(self, P=1, user_part=None, item_part=None):
+        up, ip = _arr(user_part, np.int32), _arr(item_part, np.int32)
+        self._check(self.L.mfb_sgd_plan(self.h, P, _p(up), _p(ip)))
+
+    def sgd_subepoch(self, blocks, variant=MF, lr=0.005, ureg=0.01, ireg=0.01, seed=0, counter=0):
+        b = _arr(blocks, np.int32).reshape(-1, 2)
+        self._check(self.L.mfb_sgd_subepoch(self.h, _p(b), b.shape[0], variant, lr, ureg, ireg, seed, counter))
+
+    def sgd_block_nnz(self, blocks):
+        b = _arr(blocks, np.int32).reshape(-1, 2)
+        out = C.c_int64()
+        self._check(self.L.mfb_sgd_block_nnz(self.h, _p(b), b.shape[0], C.byref(out)))
+        return out.value
+
+    # ---- ALS / CCD++ ----
+    def als_half_step(self, side, reg):
+        self._check(self.L.mfb_als_half_step(self.h, side, reg))
+
+    def ccdpp_begin(self):
+        self._check(self.L.mfb_ccdpp_begin(self.h))
+
+    def ccdpp_rank1(self, k, first_iter, inner=5, ureg=0.01, ireg=0.01, item_freq_thresh=0):
+        self._check(self.L.mfb_ccdpp_rank1(self.h, k, int(first_iter), inner, ureg, ireg, item_freq_thresh))
+
+    def ccdpp_end(self):
+        self._check(self.L.mfb_ccdpp_end(self.h))
+
+    # ---- evaluation ----
+    def eval(self, which, factors=CURRENT, variant=MF, weighted=False, want_norms=False):
+        out = np.zeros(4, np.float64)
+        self._check(self.L.mfb_eval(self.h, which, factors, variant, int(weighted), int(want_norms), _p(out)))
+        return out
+
+    def rmse(self, which, factors=CURRENT, variant=MF):
+        o = self.eval(which, factors, variant)
+        return float(np.sqrt(o[0] / o[1])) if o[1] > 0 else float("nan")
+
+    def objective(self, ureg, ireg, variant=MF):
+        o = self.eval(TRAIN, CURRENT, variant, weighted=(variant == IFWMF), want_norms=True)
+        return float(o[0] + ureg * o[2] + ireg * o[3])
+
+    def snapshot_best(self):
+        self._check(self.L.mfb_snapshot_best(self.h))
+
+    def restore_best(self):
+        self._check(self.L.mfb_restore_best(self.h))
+
+    # ---- timing / plumbing ----
+    def sync(self):
+        self._check(self.L.mfb_sync(self.h))
+
+    def event_record(self, slot):
+        self._check(self.L.mfb_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_float()
+        self._check(self.L.mfb_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
+
+    def device_factors(self, side):
+        p, ld = C.c_void_p(), C.c_int64()
+        self._check(self.L.mfb_device_factors(self.h, side, C.byref(p), C.byref(ld)))
+        return p.value, ld.value
+
+    def stream(self):
+        return self.L.mfb_stream(self.h)
+
+    def pack_rows(self, side, ids, dev_ptr):
+        ids = _arr(ids, np.int32)
+        self._check(self.L.mfb_pack_rows(self.h, side, _p(ids), ids.shape[0], C.c_void_p(dev_ptr)))
+
+    def unpack_rows(self, side, ids, dev_ptr):
+        ids = _arr(ids, np.int32)
+        self._check(self.L.mfb_unpack_rows(self.h, side, _p(ids), ids.shape[0], C.c_void_p(dev_ptr)))
+
+    def set_row_range(self, side, begin, end):
+        self._check(self.L.mfb_set_row_range(self.h, side, begin, end))
+
+
+def launch_count() -> int:
+    return int(load_library().mfb_launch_count())
+
+
+def pin_host(arr: np.ndarray):
+    L = load_library()
+    if L.mfb_pin_host(arr.ctypes.data_as(C.c_void_p), arr.nbytes) != 0:
+        raise EngineError(L.mfb_last_error().decode(errors="replace"))
+
+
+def unpin_host(arr: np.ndarray):
+    load_library().mfb_unpin_host(arr.ctypes.data_as(C.c_void_p))

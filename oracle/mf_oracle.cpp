@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cassert>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -197,6 +198,7 @@ struct mfo_model {
   std::vector<double> invPopU, invPopI;  // std::map<int,double> in the reference; 0 when absent
   std::vector<HistEntry> hist;
   int keepHistory = 0;
+  std::vector<double> epochSecs;  // the reference's subIterDuration (modelMF.cpp:75,106-109)
 
   float &u(int uu, int k) { return cur.U[(size_t)uu * facDim + k]; }
   float &v(int ii, int k) { return cur.V[(size_t)ii * facDim + k]; }
@@ -428,6 +430,13 @@ static void validIds(const mfo_model *m, const Csr &tr, std::vector<int> &trainU
     if (m->invalidItems.count(item) == 0) trainItems.push_back(item);
 }
 
+struct EpochTimer {
+  mfo_model *m;
+  std::chrono::steady_clock::time_point t0;
+  explicit EpochTimer(mfo_model *m) : m(m), t0(std::chrono::steady_clock::now()) {}
+  void stop() { m->epochSecs.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count()); }
+};
+
 // model.cpp:1471-1540 (validation variant).  Returns true to stop.
 struct StopState {
   int bestIter = -1;
@@ -548,6 +557,7 @@ static int trainSerialSgd(mfo_model *m, const mfo_data *d) {
   std::iota(inds.begin(), inds.end(), 0);
   int iter;
   for (iter = 0; iter < m->maxIter; iter++) {
+    EpochTimer tm(m);
     std::shuffle(inds.begin(), inds.end(), mt);
     const float learnRate = m->cur.learnRate, uReg = m->uReg, iReg = m->iReg;
     for (const auto &ind : inds) {
@@ -567,6 +577,7 @@ static int trainSerialSgd(mfo_model *m, const mfo_data *d) {
         for (int i = 0; i < r; i++) pv[i] -= learnRate * (-2.0 * diff * pu[i] + 2.0 * iReg * pv[i]);
       }
     }
+    tm.stop();
     if (iter % kObjIter == 0 || iter == m->maxIter - 1)
       if (isTerminateModel(m, d, iter, s)) { iter++; break; }
   }
@@ -586,6 +597,7 @@ static int trainHogwildSerial(mfo_model *m, const mfo_data *d) {
   std::vector<float> tmp(r);
   int iter;
   for (iter = 0; iter < m->maxIter; iter++) {
+    EpochTimer tm(m);
     std::shuffle(inds.begin(), inds.end(), mt);
     const float learnRate = m->cur.learnRate, uReg = m->uReg, iReg = m->iReg;
     for (size_t kk = 0; kk < inds.size(); kk++) {
@@ -602,6 +614,7 @@ static int trainHogwildSerial(mfo_model *m, const mfo_data *d) {
       for (int k = 0; k < r; k++) tmp[k] = learnRate * (a * pu[k] + bi * pv[k]);
       for (int k = 0; k < r; k++) pv[k] -= tmp[k];
     }
+    tm.stop();
     if (iter % kObjIter == 0 || iter == m->maxIter - 1)
       if (isTerminateModel(m, d, iter, s)) { iter++; break; }
   }
@@ -633,6 +646,7 @@ static int trainStratified(mfo_model *m, const mfo_data *d) {
   const int algo = m->algo;
   int iter;
   for (iter = 0; iter < m->maxIter; iter++) {
+    EpochTimer tm(m);
     const float learnRate = m->cur.learnRate, uReg = m->uReg, iReg = m->iReg;
     for (int k = 0; k < P; k++) {
       sgdUpdateBlockSeq(P, updateSeq, mt);
@@ -675,6 +689,7 @@ static int trainStratified(mfo_model *m, const mfo_data *d) {
         }
       }
     }
+    tm.stop();
     if (iter % kObjIter == 0 || iter == m->maxIter - 1)
       if (isTerminateModel(m, d, iter, s)) { iter++; break; }
   }
@@ -740,6 +755,7 @@ static int trainAls(mfo_model *m, const mfo_data *d) {
   preamble(m, d, s, nullptr, nullptr);
   int iter;
   for (iter = 0; iter < m->maxIter; iter++) {
+    EpochTimer tm(m);
 #pragma omp parallel
     {
       std::vector<float> YTY((size_t)r * r), b(r), x(r);
@@ -782,6 +798,7 @@ static int trainAls(mfo_model *m, const mfo_data *d) {
         for (int j = 0; j < r; j++) m->v(item, j) = x[j];
       }
     }
+    tm.stop();
     if (iter % kObjIter == 0 || iter == m->maxIter - 1)
       if (isTerminateModel(m, d, iter, s)) { iter++; break; }
   }
@@ -804,6 +821,7 @@ static int trainCcdpp(mfo_model *m, const mfo_data *d, bool freqAdap) {
   std::vector<float> u_k(nUsers), v_k(nItems);
   int iter;
   for (iter = 0; iter < m->maxIter; iter++) {
+    EpochTimer tm(m);
     if (!freqAdap) std::shuffle(dims.begin(), dims.end(), mt);  // commented out at :1271
     for (const auto &k : dims) {
       for (int u = 0; u < nUsers; u++) u_k[u] = m->u(u, k);
@@ -866,6 +884,7 @@ static int trainCcdpp(mfo_model *m, const mfo_data *d, bool freqAdap) {
       for (int u = 0; u < nUsers; u++) m->u(u, k) = u_k[u];
       for (int i = 0; i < nItems; i++) m->v(i, k) = v_k[i];
     }
+    tm.stop();
     if (iter % kObjIter == 0 || iter == m->maxIter - 1)
       if (isTerminateModel(m, d, iter, s)) { iter++; break; }
   }
@@ -875,6 +894,7 @@ static int trainCcdpp(mfo_model *m, const mfo_data *d, bool freqAdap) {
 extern "C" int mfo_train(mfo_model *m, const mfo_data *d, int method, int keep_history) {
   m->keepHistory = keep_history;
   m->hist.clear();
+  m->epochSecs.clear();
   int saved = omp_get_max_threads();
   int iters = 0;
   // dispatch table of main.cpp:1325-1370: TMF / TMFDropout always run their stratified train()
@@ -978,4 +998,21 @@ extern "C" void mfo_ifw_weights(const mfo_model *mc, const mfo_data *d, double *
   initIfw(m, d->mat[0], tu, ti);
   for (int u = 0; u < m->nUsers; u++) inv_pop_u[u] = m->invPopU[u];
   for (int i = 0; i < m->nItems; i++) inv_pop_i[i] = m->invPopI[i];
+}
+
+// dims visiting order of trainCCDPP: std::shuffle(dims, mt) once per epoch (modelMF.cpp:1000,1026)
+extern "C" void mfo_ccdpp_dim_order(int seed, int r, int n_epochs, int32_t *out) {
+  std::mt19937 mt(seed);
+  std::vector<int> dims(r);
+  std::iota(dims.begin(), dims.end(), 0);
+  for (int e = 0; e < n_epochs; e++) {
+    std::shuffle(dims.begin(), dims.end(), mt);
+    for (int k = 0; k < r; k++) out[(size_t)e * r + k] = dims[k];
+  }
+}
+
+extern "C" int mfo_epoch_seconds(const mfo_model *m, double *out, int cap) {
+  int n = (int)m->epochSecs.size();
+  for (int i = 0; i < n && i < cap; i++) out[i] = m->epochSecs[i];
+  return n;
 }

@@ -66,6 +66,8 @@ int mfo_history_len(const mfo_model *m);
 void mfo_get_history(const mfo_model *m, int epoch, float *U, float *V, double *objective,
                      double *val_rmse);
 float mfo_learn_rate(const mfo_model *m);
+/* wall seconds of each epoch body of the last mfo_train (the reference's subIterDuration); returns count */
+int mfo_epoch_seconds(const mfo_model *m, double *out, int cap);
 /* invalid masks as filled by the trainer (uint8 per id, 1 = invalid). */
 void mfo_get_invalid(const mfo_model *m, uint8_t *users, uint8_t *items);
 void mfo_compute_invalid(mfo_model *m, const mfo_data *d);
@@ -84,6 +86,8 @@ void mfo_dsgd_plan(const mfo_model *m, const mfo_data *d, int P, int n_subepochs
 void mfo_tmf_ranks(const mfo_model *m, int32_t *user_rank, int32_t *item_rank, int for_prediction);
 /* normalised popularity scores invPopU / invPopI (modelInvPopMF.cpp:98-114), 0 for invalid ids */
 void mfo_ifw_weights(const mfo_model *m, const mfo_data *d, double *inv_pop_u, double *inv_pop_i);
+/* dims order of trainCCDPP for n_epochs epochs: out[n_epochs][r] */
+void mfo_ccdpp_dim_order(int seed, int r, int n_epochs, int32_t *out);
 /* batched fp32 solve used by ALS (pivoted LDL^T), for unit checks: A is [n][r][r] row-major */
 void mfo_ldlt_solve(int n, int r, const float *A, const float *b, float *x);
 

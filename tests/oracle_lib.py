@@ -63,6 +63,7 @@ def lib():
         L.mfo_get_history.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mfo_learn_rate.restype = C.c_float
         L.mfo_learn_rate.argtypes = [C.c_void_p]
+        L.mfo_epoch_seconds.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.mfo_get_invalid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mfo_compute_invalid.argtypes = [C.c_void_p, C.c_void_p]
         L.mfo_rmse.restype = C.c_double
@@ -72,6 +73,7 @@ def lib():
         L.mfo_dsgd_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mfo_tmf_ranks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.mfo_ifw_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mfo_ccdpp_dim_order.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.mfo_ldlt_solve.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     return _lib
 
@@ -159,6 +161,11 @@ class OracleModel:
     def learn_rate(self):
         return float(lib().mfo_learn_rate(self.h))
 
+    def epoch_seconds(self):
+        out = np.zeros(4096, np.float64)
+        n = lib().mfo_epoch_seconds(self.h, _p(out), 4096)
+        return out[:n].copy()
+
     def compute_invalid(self):
         lib().mfo_compute_invalid(self.h, self.data.h)
 
@@ -194,6 +201,12 @@ class OracleModel:
         if getattr(self, "h", None):
             lib().mfo_model_free(self.h)
             self.h = None
+
+
+def ccdpp_dim_order(seed, r, n_epochs):
+    out = np.zeros((n_epochs, r), np.int32)
+    lib().mfo_ccdpp_dim_order(seed, r, n_epochs, _p(out))
+    return out
 
 
 def ldlt_solve(A, b):
