@@ -115,6 +115,18 @@ int mfb_sgd_plan(mfb_engine *e, int32_t P, const int32_t *user_part, const int32
  * counter-based Poisson draws of MFB_TMFDROPOUT. */
 int mfb_sgd_subepoch(mfb_engine *e, const int32_t *blocks, int32_t nb, int variant, float learn_rate,
                      float ureg, float ireg, uint64_t seed, uint64_t counter);
+/* One epoch of the serial / Hogwild trainers (modelMF.cpp:83-105 train, :1747-1763 hogTrain;
+ * modelInvPopMF.cpp:152-180): every valid rating once, in a fresh pseudo-random order per
+ * (seed, counter); a sub-warp owns one rating at a time, both factor rows are read with 128-bit
+ * loads and updated with vector reductions.  Needs mfb_sgd_plan(e, 1, NULL, NULL). */
+int mfb_sgd_epoch_flat(mfb_engine *e, int variant, float learn_rate, float ureg, float ireg, uint64_t seed,
+                       uint64_t counter);
+/* Tuning knobs: "sgd_workers" (concurrent sub-warps, 0 = automatic), "sgd_warps_per_sm",
+ * "sgd_max_hot_inflight" (bound on concurrent updates of the hottest item row, default 8),
+ * "sgd_atomic" (1 = item rows updated by reductions, 0 = plain stores), "sgd_rotate" (1 = every
+ * user run of the stratified kernel starts at a pseudo-random offset and wraps around, 0 = CSR
+ * order as in modelMF.cpp:280). */
+int mfb_set_option(mfb_engine *e, const char *name, double value);
 /* number of ratings the given blocks hold (for updates/s accounting) */
 int mfb_sgd_block_nnz(mfb_engine *e, const int32_t *blocks, int32_t nb, int64_t *nnz);
 

@@ -46,7 +46,7 @@ void DevCsr::release() {
 
 void SgdPlan::release() {
   if (owns_ratings) { cudaFree(item); cudaFree(val); }
-  cudaFree(seg_user); cudaFree(seg_start); cudaFree(seg_len);
+  cudaFree(seg_user); cudaFree(seg_start); cudaFree(seg_len); cudaFree(rat_user); cudaFree(work_counter);
   *this = SgdPlan();
 }
 
@@ -419,7 +419,32 @@ extern "C" int mfb_sgd_subepoch(mfb_engine *e, const int32_t *blocks, int32_t nb
     MFB_REQUIRE(blocks[2 * i] >= 0 && blocks[2 * i] < e->sgd.P && blocks[2 * i + 1] >= 0 && blocks[2 * i + 1] < e->sgd.P,
                 "mfb_sgd_subepoch: block index out of range");
   MFB_CUDA(cudaSetDevice(e->device));
+  if (e->opt_sgd_block_order == 1) return sgd_flat_launch(e, blocks, nb, variant, learn_rate, ureg, ireg, seed, counter);
   return sgd_subepoch_launch(e, blocks, nb, variant, learn_rate, ureg, ireg, seed, counter);
+}
+
+extern "C" int mfb_sgd_epoch_flat(mfb_engine *e, int variant, float learn_rate, float ureg, float ireg, uint64_t seed,
+                                  uint64_t counter) {
+  MFB_REQUIRE(e, "null engine");
+  MFB_REQUIRE(e->sgd.built && e->sgd.P == 1 && e->sgd.rat_user, "mfb_sgd_epoch_flat: call mfb_sgd_plan(P = 1) first");
+  const int32_t whole[2] = {0, 0};
+  MFB_REQUIRE(variant >= MFB_MF && variant <= MFB_TMFDROPOUT, "mfb_sgd_epoch_flat: bad variant");
+  MFB_REQUIRE(variant == MFB_MF || e->aux_variant == variant, "mfb_sgd_epoch_flat: mfb_set_aux not called for this variant");
+  MFB_CUDA(cudaSetDevice(e->device));
+  return sgd_flat_launch(e, whole, 1, variant, learn_rate, ureg, ireg, seed, counter);
+}
+
+extern "C" int mfb_set_option(mfb_engine *e, const char *name, double value) {
+  MFB_REQUIRE(e && name, "mfb_set_option: null argument");
+  std::string n(name);
+  if (n == "sgd_workers") e->opt_sgd_workers = (int)value;
+  else if (n == "sgd_warps_per_sm") e->opt_sgd_warps_per_sm = (int)value;
+  else if (n == "sgd_max_hot_inflight") e->opt_sgd_max_hot_inflight = value;
+  else if (n == "sgd_atomic") e->opt_sgd_atomic = (int)value;
+  else if (n == "sgd_rotate") e->opt_sgd_rotate = (int)value;
+  else if (n == "sgd_block_order") e->opt_sgd_block_order = (int)value;
+  else return mfb::fail("mfb_set_option: unknown option", __FILE__, __LINE__);
+  return 0;
 }
 
 extern "C" int mfb_sgd_block_nnz(mfb_engine *e, const int32_t *blocks, int32_t nb, int64_t *nnz) {

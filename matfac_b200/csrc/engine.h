@@ -87,8 +87,12 @@ struct SgdPlan {
   float *val = nullptr;
   bool owns_ratings = false;
   int32_t *seg_user = nullptr, *seg_start = nullptr, *seg_len = nullptr;
+  int32_t *rat_user = nullptr;   // user of every rating (flat kernel; P == 1 plans only)
+  int *work_counter = nullptr;   // device work-queue head of the persistent kernel
+  double hot_item_share = 0.0;   // largest item count / nnz: bounds useful concurrency
   std::vector<int32_t> blk_seg_off, blk_seg_cnt;  // [P*P]
   std::vector<int64_t> blk_nnz;                   // [P*P]
+  std::vector<int64_t> blk_rat_off;               // [P*P] first rating of every block
   bool built = false;
   void release();
 };
@@ -100,6 +104,13 @@ struct mfb_engine {
   int n_users = 0, n_items = 0, rank = 0;
   int ld = 0;  // leading dimension of the device factor matrices in floats (rank rounded up to 4)
   int sm_count = 148;
+  // tuning knobs (mfb_set_option)
+  int opt_sgd_workers = 0;            // 0 = automatic
+  int opt_sgd_warps_per_sm = 32;      // automatic mode: persistent warps per SM
+  double opt_sgd_max_hot_inflight = 8.0;  // bound on concurrent updates of the hottest item row
+  int opt_sgd_atomic = 1;             // item rows updated by vector reductions (no lost updates)
+  int opt_sgd_block_order = 0;        // stratified trainers: 0 = user-major runs (reference order), 1 = shuffled inside the blocks
+  int opt_sgd_rotate = 1;             // user runs start at a pseudo-random offset (de-correlates heavy users)
   cudaStream_t stream = nullptr;
   cudaEvent_t events[16] = {};
 
@@ -146,6 +157,8 @@ int build_seg_plan(mfb_engine *e, const int64_t *ptr, int32_t nrows, const uint8
 int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int32_t *item_part);
 int sgd_subepoch_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int variant, float lr, float ureg,
                         float ireg, uint64_t seed, uint64_t counter);
+int sgd_flat_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int variant, float lr, float ureg, float ireg,
+                    uint64_t seed, uint64_t counter);
 int eval_launch(mfb_engine *e, int which, int factors, int variant, int weighted, int want_norms, double out[4]);
 int als_half_step_launch(mfb_engine *e, int side, float reg);
 int ccdpp_begin_impl(mfb_engine *e);

@@ -22,6 +22,8 @@
 
 #include <cub/cub.cuh>
 
+#include <algorithm>
+
 namespace mfb {
 
 // ---- plan ------------------------------------------------------------------------------------
@@ -51,6 +53,11 @@ __global__ void sgd_gather_kernel(const int32_t *__restrict__ perm, int64_t n, c
   int p = perm[j];
   oind[j] = ind[p];
   oval[j] = val[p];
+}
+
+__global__ void key_user_kernel(const uint64_t *__restrict__ keys, int64_t n, int32_t *__restrict__ out) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) out[j] = (int32_t)(keys[j] & 0xFFFFFFFFu);
 }
 
 __global__ void sgd_seg_key_kernel(const uint64_t *__restrict__ run_key, const int32_t *__restrict__ run_len, int32_t n,
@@ -87,15 +94,59 @@ __global__ void sgd_blk_bounds_kernel(const uint64_t *__restrict__ run_key, int3
   bounds[b] = lo;
 }
 
+__global__ void item_hist_kernel(const int32_t *__restrict__ ind, int64_t n, int32_t *__restrict__ hist) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) atomicAdd(hist + ind[j], 1);
+}
+
+__global__ void rat_user_kernel(const int64_t *__restrict__ rowptr, int32_t nrows, int64_t nnz, int32_t *__restrict__ out) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nnz) return;
+  int lo = 0, hi = nrows;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (rowptr[mid] <= j) lo = mid; else hi = mid;
+  }
+  out[j] = lo;
+}
+
+static int sgd_plan_common(mfb_engine *e) {
+  SgdPlan &pl = e->sgd;
+  const DevCsr &m = e->mat[MFB_TRAIN];
+  cudaStream_t st = e->stream;
+  MFB_CUDA(cudaMalloc(&pl.work_counter, sizeof(int)));
+  MFB_CUDA(cudaMemsetAsync(pl.work_counter, 0, sizeof(int), st));
+  pl.hot_item_share = 0.0;
+  if (m.nnz > 0) {
+    int32_t *hist, *d_max;
+    MFB_CUDA(cudaMalloc(&hist, sizeof(int32_t) * ((size_t)e->n_items + 1)));
+    d_max = hist + e->n_items;
+    MFB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int32_t) * ((size_t)e->n_items + 1), st));
+    MFB_LAUNCH(item_hist_kernel, (unsigned)((m.nnz + 255) / 256), 256, 0, st, m.rowind, m.nnz, hist);
+    size_t tmp_bytes = 0;
+    MFB_CUDA(cub::DeviceReduce::Max(nullptr, tmp_bytes, hist, d_max, e->n_items, st));
+    MFB_TRY(ensure_scratch(e, tmp_bytes));
+    MFB_CUDA(cub::DeviceReduce::Max(e->scratch, tmp_bytes, hist, d_max, e->n_items, st));
+    int32_t mx = 0;
+    MFB_CUDA(cudaMemcpyAsync(&mx, d_max, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MFB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(hist);
+    pl.hot_item_share = (double)mx / (double)m.nnz;
+  }
+  return 0;
+}
+
 int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int32_t *item_part) {
   SgdPlan &pl = e->sgd;
   pl.release();
   const DevCsr &m = e->mat[MFB_TRAIN];
   cudaStream_t st = e->stream;
+  MFB_TRY(sgd_plan_common(e));
   pl.P = P;
   pl.blk_seg_off.assign((size_t)P * P, 0);
   pl.blk_seg_cnt.assign((size_t)P * P, 0);
   pl.blk_nnz.assign((size_t)P * P, 0);
+  pl.blk_rat_off.assign((size_t)P * P, 0);
   if (P == 1 && user_part == nullptr) {
     // whole matrix = one block; runs are the CSR rows themselves
     SegPlan sp;
@@ -110,6 +161,9 @@ int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int
     pl.nnz = m.nnz;
     pl.blk_seg_cnt[0] = pl.n_seg;
     pl.blk_nnz[0] = m.nnz;
+    MFB_CUDA(cudaMalloc(&pl.rat_user, sizeof(int32_t) * (size_t)(m.nnz > 0 ? m.nnz : 1)));
+    if (m.nnz > 0)
+      MFB_LAUNCH(rat_user_kernel, (unsigned)((m.nnz + 255) / 256), 256, 0, st, m.rowptr, e->n_users, m.nnz, pl.rat_user);
     pl.built = true;
     return 0;
   }
@@ -140,6 +194,9 @@ int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int
   MFB_CUDA(cudaMalloc(&pl.val, sizeof(float) * nn));
   pl.owns_ratings = true;
   if (nnz > 0) MFB_LAUNCH(sgd_gather_kernel, gb, tb, 0, st, idx2, nnz, m.rowind, m.rowval, pl.item, pl.val);
+  // user of every reordered rating (low word of the sorted key) for the shuffled-in-block kernel
+  MFB_CUDA(cudaMalloc(&pl.rat_user, sizeof(int32_t) * nn));
+  if (nnz > 0) MFB_LAUNCH(key_user_kernel, gb, tb, 0, st, keys2, nnz, pl.rat_user);
   // runs of equal (block, user): reuse `keys` for the unique keys, `idx` for the run lengths
   int32_t *d_nruns;
   MFB_CUDA(cudaMalloc(&d_nruns, sizeof(int32_t)));
@@ -191,6 +248,7 @@ int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int
     pl.blk_seg_off[b] = bounds[b];
     pl.blk_seg_cnt[b] = bounds[b + 1] - bounds[b];
     pl.blk_nnz[b] = (int64_t)nnz_at[b + 1] - nnz_at[b];
+    pl.blk_rat_off[b] = nnz_at[b];
   }
   size_t ns = (size_t)(nseg > 0 ? nseg : 1);
   MFB_CUDA(cudaMalloc(&pl.seg_user, sizeof(int32_t) * ns));
@@ -222,20 +280,28 @@ int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int
   return 0;
 }
 
-// ---- update kernel ---------------------------------------------------------------------------
+// ---- update kernels ----------------------------------------------------------------------------
 struct SgdArgs {
   float *U, *V;
   int nq;  // float4 words per factor row (ld / 4)
   int rank;
   const int32_t *item;
   const float *val;
+  const int32_t *rat_user;  // flat kernel only
   const int32_t *seg_user, *seg_start, *seg_len;
-  int nb, max_cnt;
+  int nb, max_cnt, total;  // total = nb * max_cnt segment slots
+  int rotate;              // start every run at a pseudo-random offset
   int32_t off[kMaxBlocks], cnt[kMaxBlocks];
+  int *counter;  // dynamic work queue head
   float lr, ureg, ireg;
   const Aux *aux_u, *aux_i;
   const float *cdf;
-  uint64_t seed, counter;
+  uint64_t seed, counter_id;
+  // shuffled kernel: visiting order p(t) = (mul * t + add) mod n over the concatenated rating
+  // ranges of the scheduled blocks (range b starts at rat_off[b], cumulative sizes in rat_cum)
+  int64_t n, mul, add;
+  int32_t rat_off[kMaxBlocks];
+  int32_t rat_cum[kMaxBlocks + 1];
 };
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
@@ -262,195 +328,399 @@ __device__ __forceinline__ int poisson_rank(const float *__restrict__ cdf, int r
   return k;
 }
 
-template <int G, int VPL, int VARIANT>
-__global__ void __launch_bounds__(128) sgd_update_kernel(const SgdArgs a) {
-  constexpr unsigned kFull = 0xFFFFFFFFu;
-  const int lane = threadIdx.x & 31;
-  const int sl = lane & (G - 1);  // lane inside the sub-warp
-  const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-  const int b = (int)(gid % a.nb);
-  const int sidx = (int)(gid / a.nb);
-  const bool active = sidx < a.cnt[b];
-  int user = 0, start = 0, len = 0;
-  if (active) {
-    int s = a.off[b] + sidx;
-    user = a.seg_user[s];
-    start = a.seg_start[s];
-    len = a.seg_len[s];
-  }
-  int maxlen = len;
-#pragma unroll
-  for (int m = 16; m >= G; m >>= 1) maxlen = max(maxlen, __shfl_xor_sync(kFull, maxlen, m));
-  if (maxlen == 0) return;  // warp-uniform
+// 128-bit vector reduction into global memory (sm_90+): no lost update when two workers hit the
+// same factor row, at the cost of a slightly stale read (mini-batch semantics on hot rows).
+__device__ __forceinline__ void red_add_v4(float4 *addr, float4 d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w)
+               : "memory");
+}
 
-  float4 u[VPL];
-  bool own[VPL];  // this lane holds a real float4 word of the row
-  float4 *urow = reinterpret_cast<float4 *>(a.U) + (size_t)user * a.nq;
+// One SGD step on the G-lane slice of (u, v) held by this lane.  Returns the new u in place and
+// either the new v (ATOMIC = false) or the increment of v (ATOMIC = true) in vo.
+//   u -= lr * (-2 g v + 2 ureg u);  v -= lr * (-2 g u_new + 2 ireg v)      (modelMF.cpp:95-103)
+template <int G, int VPL, bool TRUNC>
+__device__ __forceinline__ float dot_slice(const float4 (&u)[VPL], const float4 (&v)[VPL], int sl, int k) {
+  float p = 0.f;
+#pragma unroll
+  for (int c = 0; c < VPL; c++) {
+    if (TRUNC) {
+      const int base = (c * G + sl) * 4;
+      p += (base + 0 < k ? u[c].x * v[c].x : 0.f) + (base + 1 < k ? u[c].y * v[c].y : 0.f) +
+           (base + 2 < k ? u[c].z * v[c].z : 0.f) + (base + 3 < k ? u[c].w * v[c].w : 0.f);
+    } else {
+      p = fmaf(u[c].x, v[c].x, p);
+      p = fmaf(u[c].y, v[c].y, p);
+      p = fmaf(u[c].z, v[c].z, p);
+      p = fmaf(u[c].w, v[c].w, p);
+    }
+  }
+#pragma unroll
+  for (int m = G / 2; m >= 1; m >>= 1) p += __shfl_xor_sync(0xFFFFFFFFu, p, m);
+  return p;
+}
+
+// Stratified trainers: a persistent sub-warp pulls user runs (longest first) from a work queue.
+template <int G, int VPL, int VARIANT, bool ATOMIC>
+__global__ void __launch_bounds__(128) sgd_run_kernel(const SgdArgs a) {
+  constexpr unsigned kFull = 0xFFFFFFFFu;
+  constexpr bool TRUNC = (VARIANT == MFB_TMF || VARIANT == MFB_TMFDROPOUT);
+  const int lane = threadIdx.x & 31;
+  const int sl = lane & (G - 1);
+  const float4 *Vq = reinterpret_cast<const float4 *>(a.V);
+  float4 *Vw = reinterpret_cast<float4 *>(a.V);
+  float4 *Uw = reinterpret_cast<float4 *>(a.U);
+  const float lr = a.lr, two_ureg = 2.0f * a.ureg, two_ireg = 2.0f * a.ireg;
+
+  bool done = false, have = false, fresh = false;
+  // a run is visited from a per-run pseudo-random offset, wrapping around: heavy users all
+  // start first (longest-first queue) and would otherwise sweep the item ids in lockstep and
+  // collide on the same item rows
+  int user = 0, pos = 0, seg_end = 0, cbase = 0, base = 0, off = 0;
+  int c_it = 0, c_pay = 0, n_it = 0, n_pay = 0;
+  float c_rt = 0.f, n_rt = 0.f;
+  int ufreq = 0, upay = 0;
+  float4 u[VPL], vn[VPL];
+  bool own[VPL];
 #pragma unroll
   for (int c = 0; c < VPL; c++) {
     own[c] = (c * G + sl) < a.nq;
-    u[c] = (active && own[c]) ? __ldcg(urow + c * G + sl) : make_float4(0.f, 0.f, 0.f, 0.f);
+    u[c] = vn[c] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  int ufreq = 0, upay = 0;
-  if (VARIANT != MFB_MF && active) {
-    Aux au = a.aux_u[user];
-    ufreq = au.freq;
-    upay = au.train;
-  }
-  const float4 *Vq = reinterpret_cast<const float4 *>(a.V);
-  float4 *Vw = reinterpret_cast<float4 *>(a.V);
 
-  // fetch one (item, rating[, payload]) per lane
-  auto fetch = [&](int j, int &it, float &rt, int &pay) {
+  auto fetch = [&](int q, int &it, float &rt, int &pay) {  // q-th rating of the rotated run
     it = 0; rt = 0.f; pay = 0;
-    if (j < len) {
-      it = __ldg(a.item + start + j);
-      rt = __ldg(a.val + start + j);
+    if (q < seg_end) {
+      int j = q + off;
+      if (j >= seg_end) j -= seg_end;
+      j += base;
+      it = __ldg(a.item + j);
+      rt = __ldg(a.val + j);
       if (VARIANT != MFB_MF) {
         Aux ai = a.aux_i[it];
         // the rarer side decides (modelInvPopMF.cpp:164-166, modelDropoutSigmoid.cpp:158)
         pay = (ufreq < ai.freq) ? upay : ai.train;
-        if (VARIANT == MFB_TMFDROPOUT) pay = poisson_rank(a.cdf, a.rank, pay, a.seed, a.counter, (uint32_t)(start + j));
+        if (VARIANT == MFB_TMFDROPOUT) pay = poisson_rank(a.cdf, a.rank, pay, a.seed, a.counter_id, (uint32_t)j);
       }
     }
   };
 
-  int n_it, n_pay;
-  float n_rt;
-  fetch(sl, n_it, n_rt, n_pay);
-  float4 vn[VPL];
-  {
-    int it0 = __shfl_sync(kFull, n_it, 0, G);
+  for (;;) {
+    const bool need = !done && pos >= seg_end;
+    if (need && have) {
 #pragma unroll
-    for (int c = 0; c < VPL; c++)
-      vn[c] = (len > 0 && own[c]) ? __ldcg(Vq + (size_t)it0 * a.nq + c * G + sl) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  const float lr = a.lr, two_ureg = 2.0f * a.ureg, two_ireg = 2.0f * a.ireg;
-
-  for (int j0 = 0; j0 < maxlen; j0 += G) {
-    const int c_it = n_it, c_pay = n_pay;
-    const float c_rt = n_rt;
-    fetch(j0 + G + sl, n_it, n_rt, n_pay);
-#pragma unroll 4
-    for (int t = 0; t < G; t++) {
-      const int j = j0 + t;
-      if (j >= maxlen) break;  // warp-uniform
-      const int it = __shfl_sync(kFull, c_it, t, G);
-      const float rt = __shfl_sync(kFull, c_rt, t, G);
-      int pay = 0;
-      if (VARIANT != MFB_MF) pay = __shfl_sync(kFull, c_pay, t, G);
-      const int itn_same = __shfl_sync(kFull, c_it, (t + 1) & (G - 1), G);
-      const int itn_next = __shfl_sync(kFull, n_it, 0, G);
-      const int itn = (t + 1 < G) ? itn_same : itn_next;
-      const bool on = j < len;
-      float4 v[VPL];
-#pragma unroll
-      for (int c = 0; c < VPL; c++) v[c] = vn[c];
-      if (j + 1 < len) {
-#pragma unroll
-        for (int c = 0; c < VPL; c++)
-          if (own[c]) vn[c] = __ldcg(Vq + (size_t)itn * a.nq + c * G + sl);
-      }
-      int k = a.rank;  // number of leading dimensions this update touches
-      if (VARIANT == MFB_TMF || VARIANT == MFB_TMFDROPOUT) k = pay;
-      float p = 0.f;
-#pragma unroll
-      for (int c = 0; c < VPL; c++) {
-        const int base = (c * G + sl) * 4;
-        if (VARIANT == MFB_TMF || VARIANT == MFB_TMFDROPOUT) {
-          p += (base + 0 < k ? u[c].x * v[c].x : 0.f) + (base + 1 < k ? u[c].y * v[c].y : 0.f) +
-               (base + 2 < k ? u[c].z * v[c].z : 0.f) + (base + 3 < k ? u[c].w * v[c].w : 0.f);
-        } else {
-          p = fmaf(u[c].x, v[c].x, p);
-          p = fmaf(u[c].y, v[c].y, p);
-          p = fmaf(u[c].z, v[c].z, p);
-          p = fmaf(u[c].w, v[c].w, p);
-        }
-      }
-#pragma unroll
-      for (int m = G / 2; m >= 1; m >>= 1) p += __shfl_xor_sync(kFull, p, m);
-      float g = rt - p;  // diff
-      if (VARIANT == MFB_IFWMF) g *= __int_as_float(pay);
-      const float m2g = -2.0f * g;
-      if (on) {
-#pragma unroll
-        for (int c = 0; c < VPL; c++) {
-          if (!own[c]) continue;
-          const int base = (c * G + sl) * 4;
-          float4 un, vv = v[c];
-          // u -= lr * (-2 g v + 2 ureg u);  v -= lr * (-2 g u_new + 2 ireg v)   (modelMF.cpp:95-103)
-          un.x = fmaf(-lr, fmaf(two_ureg, u[c].x, m2g * vv.x), u[c].x);
-          un.y = fmaf(-lr, fmaf(two_ureg, u[c].y, m2g * vv.y), u[c].y);
-          un.z = fmaf(-lr, fmaf(two_ureg, u[c].z, m2g * vv.z), u[c].z);
-          un.w = fmaf(-lr, fmaf(two_ureg, u[c].w, m2g * vv.w), u[c].w);
-          float4 vo;
-          vo.x = fmaf(-lr, fmaf(two_ireg, vv.x, m2g * un.x), vv.x);
-          vo.y = fmaf(-lr, fmaf(two_ireg, vv.y, m2g * un.y), vv.y);
-          vo.z = fmaf(-lr, fmaf(two_ireg, vv.z, m2g * un.z), vv.z);
-          vo.w = fmaf(-lr, fmaf(two_ireg, vv.w, m2g * un.w), vv.w);
-          if (VARIANT == MFB_TMF || VARIANT == MFB_TMFDROPOUT) {
-            if (base >= k) continue;  // nothing of this word is touched
-            if (base + 1 >= k) { un.y = u[c].y; vo.y = vv.y; }
-            if (base + 2 >= k) { un.z = u[c].z; vo.z = vv.z; }
-            if (base + 3 >= k) { un.w = u[c].w; vo.w = vv.w; }
-          }
-          u[c] = un;
-          __stcg(Vw + (size_t)it * a.nq + c * G + sl, vo);
-        }
+      for (int c = 0; c < VPL; c++)
+        if (own[c]) __stcg(Uw + (size_t)user * a.nq + c * G + sl, u[c]);
+    }
+    int s = -1;
+    if (need && sl == 0) {
+      for (;;) {
+        const int idx = atomicAdd(a.counter, 1);
+        if (idx >= a.total) break;
+        const int b = idx % a.nb, local = idx / a.nb;
+        if (local < a.cnt[b]) { s = a.off[b] + local; break; }
       }
     }
-  }
-  if (active) {
+    s = __shfl_sync(kFull, s, 0, G);
+    if (need) {
+      if (s < 0) {
+        done = true;
+        have = false;
+      } else {
+        user = a.seg_user[s];
+        base = a.seg_start[s];
+        seg_end = a.seg_len[s];
+        pos = 0;
+        off = a.rotate ? (int)(mix64(a.seed ^ (a.counter_id * 0x9E3779B97F4A7C15ull + (uint32_t)user)) % (uint32_t)seg_end) : 0;
+        have = true;
+        fresh = true;
 #pragma unroll
-    for (int c = 0; c < VPL; c++)
-      if (own[c]) __stcg(urow + c * G + sl, u[c]);
+        for (int c = 0; c < VPL; c++)
+          if (own[c]) u[c] = __ldcg(Uw + (size_t)user * a.nq + c * G + sl);
+        if (VARIANT != MFB_MF) {
+          Aux au = a.aux_u[user];
+          ufreq = au.freq;
+          upay = au.train;
+        }
+        cbase = pos;
+        fetch(pos + sl, c_it, c_rt, c_pay);
+        fetch(pos + G + sl, n_it, n_rt, n_pay);
+      }
+    }
+    if (__all_sync(kFull, done)) break;
+    if (!done && pos >= cbase + G) {
+      c_it = n_it; c_rt = n_rt; c_pay = n_pay;
+      cbase += G;
+      fetch(cbase + G + sl, n_it, n_rt, n_pay);
+    }
+    const int t = (pos - cbase) & (G - 1);
+    const int it = __shfl_sync(kFull, c_it, t, G);
+    const float rt = __shfl_sync(kFull, c_rt, t, G);
+    int pay = 0;
+    if (VARIANT != MFB_MF) pay = __shfl_sync(kFull, c_pay, t, G);
+    const int itn_same = __shfl_sync(kFull, c_it, (t + 1) & (G - 1), G);
+    const int itn_next = __shfl_sync(kFull, n_it, 0, G);
+    const int itn = (t + 1 < G) ? itn_same : itn_next;
+    float4 v[VPL];
+#pragma unroll
+    for (int c = 0; c < VPL; c++) v[c] = vn[c];
+    if (!done && fresh) {
+#pragma unroll
+      for (int c = 0; c < VPL; c++)
+        if (own[c]) v[c] = __ldcg(Vq + (size_t)it * a.nq + c * G + sl);
+    }
+    if (!done && pos + 1 < seg_end) {
+#pragma unroll
+      for (int c = 0; c < VPL; c++)
+        if (own[c]) vn[c] = __ldcg(Vq + (size_t)itn * a.nq + c * G + sl);
+    }
+    fresh = false;
+    const int k = TRUNC ? pay : a.rank;  // leading dimensions this update touches
+    const float p = dot_slice<G, VPL, TRUNC>(u, v, sl, k);
+    float g = rt - p;  // diff
+    if (VARIANT == MFB_IFWMF) g *= __int_as_float(pay);
+    const float m2g = -2.0f * g;
+    if (!done) {
+#pragma unroll
+      for (int c = 0; c < VPL; c++) {
+        if (!own[c]) continue;
+        const int base = (c * G + sl) * 4;
+        if (TRUNC && base >= k) continue;  // nothing of this word is touched
+        const float4 uu = u[c], vv = v[c];
+        float4 un, dv;
+        un.x = fmaf(-lr, fmaf(two_ureg, uu.x, m2g * vv.x), uu.x);
+        un.y = fmaf(-lr, fmaf(two_ureg, uu.y, m2g * vv.y), uu.y);
+        un.z = fmaf(-lr, fmaf(two_ureg, uu.z, m2g * vv.z), uu.z);
+        un.w = fmaf(-lr, fmaf(two_ureg, uu.w, m2g * vv.w), uu.w);
+        dv.x = -lr * fmaf(two_ireg, vv.x, m2g * un.x);
+        dv.y = -lr * fmaf(two_ireg, vv.y, m2g * un.y);
+        dv.z = -lr * fmaf(two_ireg, vv.z, m2g * un.z);
+        dv.w = -lr * fmaf(two_ireg, vv.w, m2g * un.w);
+        if (TRUNC) {
+          if (base + 1 >= k) { un.y = uu.y; dv.y = 0.f; }
+          if (base + 2 >= k) { un.z = uu.z; dv.z = 0.f; }
+          if (base + 3 >= k) { un.w = uu.w; dv.w = 0.f; }
+        }
+        u[c] = un;
+        float4 *dst = Vw + (size_t)it * a.nq + c * G + sl;
+        if (ATOMIC) red_add_v4(dst, dv);
+        else __stcg(dst, make_float4(vv.x + dv.x, vv.y + dv.y, vv.z + dv.z, vv.w + dv.w));
+      }
+      pos++;
+    }
+  }
+}
+
+// Serial / Hogwild trainers (modelMF.cpp:83-105, :1747-1763): every sub-warp owns one rating at
+// a time, visited in a pseudo-random order; both rows are read with 128-bit loads and updated
+// with vector reductions.
+template <int G, int VPL, int VARIANT>
+__global__ void __launch_bounds__(128) sgd_flat_kernel(const SgdArgs a) {
+  constexpr bool TRUNC = (VARIANT == MFB_TMF || VARIANT == MFB_TMFDROPOUT);
+  const int lane = threadIdx.x & 31;
+  const int sl = lane & (G - 1);
+  const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / G;
+  const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int64_t warp_first = gid - (lane / G);  // group id of this warp's first sub-warp
+  float4 *Uw = reinterpret_cast<float4 *>(a.U), *Vw = reinterpret_cast<float4 *>(a.V);
+  const float lr = a.lr, two_ureg = 2.0f * a.ureg, two_ireg = 2.0f * a.ireg;
+  bool own[VPL];
+#pragma unroll
+  for (int c = 0; c < VPL; c++) own[c] = (c * G + sl) < a.nq;
+  for (int64_t t0 = warp_first; t0 < a.n; t0 += n_groups) {  // warp-uniform trip count
+    const int64_t t = t0 + (lane / G);
+    const bool on = t < a.n;
+    int user = 0, it = 0, pay = 0;
+    float rt = 0.f;
+    float4 u[VPL], v[VPL];
+#pragma unroll
+    for (int c = 0; c < VPL; c++) u[c] = v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on) {
+      int64_t p = (a.mul * t + a.add) % a.n;
+      if (a.nb > 1) {  // which scheduled block does p fall in
+        int b = 0;
+        while (b + 1 < a.nb && p >= a.rat_cum[b + 1]) b++;
+        p = a.rat_off[b] + (p - a.rat_cum[b]);
+      } else {
+        p += a.rat_off[0];
+      }
+      user = __ldg(a.rat_user + p);
+      it = __ldg(a.item + p);
+      rt = __ldg(a.val + p);
+#pragma unroll
+      for (int c = 0; c < VPL; c++)
+        if (own[c]) {
+          u[c] = __ldcg(Uw + (size_t)user * a.nq + c * G + sl);
+          v[c] = __ldcg(Vw + (size_t)it * a.nq + c * G + sl);
+        }
+      if (VARIANT != MFB_MF) {
+        const Aux au = a.aux_u[user], ai = a.aux_i[it];
+        pay = (au.freq < ai.freq) ? au.train : ai.train;
+        if (VARIANT == MFB_TMFDROPOUT) pay = poisson_rank(a.cdf, a.rank, pay, a.seed, a.counter_id, (uint32_t)p);
+      }
+    }
+    const int k = TRUNC ? pay : a.rank;
+    const float pdot = dot_slice<G, VPL, TRUNC>(u, v, sl, k);
+    float g = rt - pdot;
+    if (VARIANT == MFB_IFWMF) g *= __int_as_float(pay);
+    const float m2g = -2.0f * g;
+    if (on) {
+#pragma unroll
+      for (int c = 0; c < VPL; c++) {
+        if (!own[c]) continue;
+        const int base = (c * G + sl) * 4;
+        if (TRUNC && base >= k) continue;
+        const float4 uu = u[c], vv = v[c];
+        float4 du, dv;
+        du.x = -lr * fmaf(two_ureg, uu.x, m2g * vv.x);
+        du.y = -lr * fmaf(two_ureg, uu.y, m2g * vv.y);
+        du.z = -lr * fmaf(two_ureg, uu.z, m2g * vv.z);
+        du.w = -lr * fmaf(two_ureg, uu.w, m2g * vv.w);
+        dv.x = -lr * fmaf(two_ireg, vv.x, m2g * (uu.x + du.x));
+        dv.y = -lr * fmaf(two_ireg, vv.y, m2g * (uu.y + du.y));
+        dv.z = -lr * fmaf(two_ireg, vv.z, m2g * (uu.z + du.z));
+        dv.w = -lr * fmaf(two_ireg, vv.w, m2g * (uu.w + du.w));
+        if (TRUNC) {
+          if (base + 1 >= k) { du.y = 0.f; dv.y = 0.f; }
+          if (base + 2 >= k) { du.z = 0.f; dv.z = 0.f; }
+          if (base + 3 >= k) { du.w = 0.f; dv.w = 0.f; }
+        }
+        red_add_v4(Uw + (size_t)user * a.nq + c * G + sl, du);
+        red_add_v4(Vw + (size_t)it * a.nq + c * G + sl, dv);
+      }
+    }
   }
 }
 
 template <int G, int VPL>
-static int launch_variant(mfb_engine *e, const SgdArgs &a, int variant, int64_t n_groups) {
+static int launch_run(mfb_engine *e, const SgdArgs &a, int variant, int workers, bool atomic) {
   const int tb = 128;
-  const int64_t threads = n_groups * G;
-  const unsigned grid = (unsigned)((threads + tb - 1) / tb);
+  const unsigned grid = (unsigned)(((int64_t)workers * G + tb - 1) / tb);
+#define MFB_RUN_CASE(V)                                                                           \
+  if (atomic) MFB_LAUNCH((sgd_run_kernel<G, VPL, V, true>), grid, tb, 0, e->stream, a);          \
+  else MFB_LAUNCH((sgd_run_kernel<G, VPL, V, false>), grid, tb, 0, e->stream, a);
   switch (variant) {
-    case MFB_MF: MFB_LAUNCH((sgd_update_kernel<G, VPL, MFB_MF>), grid, tb, 0, e->stream, a); break;
-    case MFB_IFWMF: MFB_LAUNCH((sgd_update_kernel<G, VPL, MFB_IFWMF>), grid, tb, 0, e->stream, a); break;
-    case MFB_TMF: MFB_LAUNCH((sgd_update_kernel<G, VPL, MFB_TMF>), grid, tb, 0, e->stream, a); break;
-    default: MFB_LAUNCH((sgd_update_kernel<G, VPL, MFB_TMFDROPOUT>), grid, tb, 0, e->stream, a); break;
+    case MFB_MF: MFB_RUN_CASE(MFB_MF) break;
+    case MFB_IFWMF: MFB_RUN_CASE(MFB_IFWMF) break;
+    case MFB_TMF: MFB_RUN_CASE(MFB_TMF) break;
+    default: MFB_RUN_CASE(MFB_TMFDROPOUT) break;
+  }
+#undef MFB_RUN_CASE
+  return 0;
+}
+
+template <int G, int VPL>
+static int launch_flat(mfb_engine *e, const SgdArgs &a, int variant, int workers) {
+  const int tb = 128;
+  const unsigned grid = (unsigned)(((int64_t)workers * G + tb - 1) / tb);
+  switch (variant) {
+    case MFB_MF: MFB_LAUNCH((sgd_flat_kernel<G, VPL, MFB_MF>), grid, tb, 0, e->stream, a); break;
+    case MFB_IFWMF: MFB_LAUNCH((sgd_flat_kernel<G, VPL, MFB_IFWMF>), grid, tb, 0, e->stream, a); break;
+    case MFB_TMF: MFB_LAUNCH((sgd_flat_kernel<G, VPL, MFB_TMF>), grid, tb, 0, e->stream, a); break;
+    default: MFB_LAUNCH((sgd_flat_kernel<G, VPL, MFB_TMFDROPOUT>), grid, tb, 0, e->stream, a); break;
   }
   return 0;
+}
+
+// Number of concurrent sub-warp workers.  Concurrency is what makes parallel SGD differ from the
+// serial loop: the expected number of in-flight updates that hit the hottest item row is
+// (ratings in flight) x (that item's share of the ratings).  It is kept at or below
+// `sgd_max_hot_inflight` (default 8), and never above what fills the machine.
+static int pick_workers(const mfb_engine *e, int G, int64_t units, double hot_share, int inflight_per_worker) {
+  if (e->opt_sgd_workers > 0) return (int)std::min<int64_t>(e->opt_sgd_workers, std::max<int64_t>(units, 1));
+  const int per_warp = 32 / G;
+  int64_t hw = (int64_t)e->sm_count * e->opt_sgd_warps_per_sm * per_warp;
+  double cap = e->opt_sgd_max_hot_inflight / (std::max(hot_share, 1e-9) * inflight_per_worker);
+  int64_t w = std::min<int64_t>(hw, (int64_t)std::max(cap, 1.0));
+  w = std::min<int64_t>(w, std::max<int64_t>(units, 1));
+  w = (w + per_warp - 1) / per_warp * per_warp;
+  return (int)std::max<int64_t>(w, per_warp);
+}
+
+static void fill_common(mfb_engine *e, SgdArgs &a, float lr, float ureg, float ireg, uint64_t seed, uint64_t counter) {
+  const SgdPlan &pl = e->sgd;
+  a.U = e->U; a.V = e->V;
+  a.nq = e->ld / 4;
+  a.rank = e->rank;
+  a.item = pl.item; a.val = pl.val; a.rat_user = pl.rat_user;
+  a.seg_user = pl.seg_user; a.seg_start = pl.seg_start; a.seg_len = pl.seg_len;
+  a.lr = lr; a.ureg = ureg; a.ireg = ireg;
+  a.aux_u = e->aux_u; a.aux_i = e->aux_i; a.cdf = e->poisson_cdf;
+  a.seed = seed; a.counter_id = counter;
+  a.counter = e->sgd.work_counter;
+  a.n = pl.nnz; a.mul = 1; a.add = 0;
+  a.rotate = e->opt_sgd_rotate;
 }
 
 int sgd_subepoch_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int variant, float lr, float ureg,
                         float ireg, uint64_t seed, uint64_t counter) {
   const SgdPlan &pl = e->sgd;
   SgdArgs a;
-  a.U = e->U; a.V = e->V;
-  a.nq = e->ld / 4;
-  a.rank = e->rank;
-  a.item = pl.item; a.val = pl.val;
-  a.seg_user = pl.seg_user; a.seg_start = pl.seg_start; a.seg_len = pl.seg_len;
+  fill_common(e, a, lr, ureg, ireg, seed, counter);
   a.nb = nb;
   a.max_cnt = 0;
+  int64_t nseg = 0;
   for (int i = 0; i < nb; i++) {
     size_t bid = (size_t)blocks[2 * i] * pl.P + blocks[2 * i + 1];
     a.off[i] = pl.blk_seg_off[bid];
     a.cnt[i] = pl.blk_seg_cnt[bid];
+    nseg += a.cnt[i];
     if (a.cnt[i] > a.max_cnt) a.max_cnt = a.cnt[i];
   }
-  a.lr = lr; a.ureg = ureg; a.ireg = ireg;
-  a.aux_u = e->aux_u; a.aux_i = e->aux_i; a.cdf = e->poisson_cdf;
-  a.seed = seed; a.counter = counter;
   if (a.max_cnt == 0) return 0;
-  const int64_t n_groups = (int64_t)a.max_cnt * nb;
-  // sub-warp width: the smallest power of two of lanes that covers the row with <= 2 words per lane
+  a.total = a.max_cnt * nb;
+  MFB_CUDA(cudaMemsetAsync(pl.work_counter, 0, sizeof(int), e->stream));
   const int nq = a.nq;
-  if (nq <= 2) return launch_variant<2, 1>(e, a, variant, n_groups);
-  if (nq <= 4) return launch_variant<4, 1>(e, a, variant, n_groups);
-  if (nq <= 8) return launch_variant<8, 1>(e, a, variant, n_groups);
-  if (nq <= 16) return launch_variant<16, 1>(e, a, variant, n_groups);
-  if (nq <= 32) return launch_variant<32, 1>(e, a, variant, n_groups);
-  return launch_variant<32, 2>(e, a, variant, n_groups);
+  const bool atomic = e->opt_sgd_atomic != 0;
+#define MFB_PICK(G, VPL) return launch_run<G, VPL>(e, a, variant, pick_workers(e, G, nseg, pl.hot_item_share, 2), atomic)
+  if (nq <= 2) MFB_PICK(2, 1);
+  if (nq <= 4) MFB_PICK(4, 1);
+  if (nq <= 8) MFB_PICK(8, 1);
+  if (nq <= 16) MFB_PICK(16, 1);
+  if (nq <= 32) MFB_PICK(32, 1);
+  MFB_PICK(32, 2);
+#undef MFB_PICK
+}
+
+static int64_t gcd64(int64_t a, int64_t b) {
+  while (b) { int64_t t = a % b; a = b; b = t; }
+  return a;
+}
+
+int sgd_flat_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int variant, float lr, float ureg, float ireg,
+                    uint64_t seed, uint64_t counter) {
+  const SgdPlan &pl = e->sgd;
+  SgdArgs a;
+  fill_common(e, a, lr, ureg, ireg, seed, counter);
+  a.nb = nb; a.max_cnt = 0; a.total = 0;
+  a.rat_cum[0] = 0;
+  for (int i = 0; i < nb; i++) {
+    size_t bid = (size_t)blocks[2 * i] * pl.P + blocks[2 * i + 1];
+    a.rat_off[i] = (int32_t)pl.blk_rat_off[bid];
+    a.rat_cum[i + 1] = a.rat_cum[i] + (int32_t)pl.blk_nnz[bid];
+  }
+  a.n = a.rat_cum[nb];
+  if (a.n == 0) return 0;
+  // a fresh affine bijection of [0, n) per epoch: p(t) = (mul t + add) mod n, gcd(mul, n) = 1
+  uint64_t h = seed * 0x9E3779B97F4A7C15ull + counter * 0xD1B54A32D192ED03ull + 0x2545F4914F6CDD1Dull;
+  h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+  const int64_t n = a.n;
+  int64_t mul = (int64_t)(h % (uint64_t)n) | 1;
+  if (n > 16) mul = mul % (n / 2) + n / 4;  // a stride of the order of n, far beyond any row length
+  while (gcd64(mul, n) != 1) mul++;
+  a.mul = mul % n;
+  if (a.mul == 0) a.mul = 1;
+  a.add = (int64_t)((h >> 20) % (uint64_t)n);
+  const int nq = a.nq;
+  // the shuffled kernel reads both rows right before it adds its increments; measured convergence
+  // is independent of the concurrency (profiles/), so it is sized to fill the machine
+#define MFB_PICK(G, VPL) return launch_flat<G, VPL>(e, a, variant, pick_workers(e, G, n, 0.0, 1))
+  if (nq <= 2) MFB_PICK(2, 1);
+  if (nq <= 4) MFB_PICK(4, 1);
+  if (nq <= 8) MFB_PICK(8, 1);
+  if (nq <= 16) MFB_PICK(16, 1);
+  if (nq <= 32) MFB_PICK(32, 1);
+  MFB_PICK(32, 2);
+#undef MFB_PICK
 }
 
 }  // namespace mfb

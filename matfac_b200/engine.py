@@ -24,7 +24,7 @@ VARIANT = {"mf": MF, "IFWMF": IFWMF, "TMF": TMF, "TMFDropout": TMFDROPOUT}
 SYMBOLS = [
     "mfb_last_error", "mfb_launch_count", "mfb_create", "mfb_destroy", "mfb_sync", "mfb_pin_host",
     "mfb_unpin_host", "mfb_upload_csr", "mfb_set_masks", "mfb_upload_factors", "mfb_download_factors",
-    "mfb_set_aux", "mfb_sgd_plan", "mfb_sgd_subepoch", "mfb_sgd_block_nnz", "mfb_als_half_step",
+    "mfb_set_aux", "mfb_sgd_plan", "mfb_sgd_subepoch", "mfb_sgd_block_nnz", "mfb_sgd_epoch_flat", "mfb_set_option", "mfb_als_half_step",
     "mfb_ccdpp_begin", "mfb_ccdpp_rank1", "mfb_ccdpp_end", "mfb_eval", "mfb_snapshot_best",
     "mfb_restore_best", "mfb_event_record", "mfb_event_elapsed_ms", "mfb_device_factors", "mfb_stream",
     "mfb_pack_rows", "mfb_unpack_rows", "mfb_set_row_range",
@@ -68,6 +68,8 @@ def load_library():
     L.mfb_set_aux.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     L.mfb_sgd_plan.argtypes = [vp, i32, vp, vp]
     L.mfb_sgd_subepoch.argtypes = [vp, vp, i32, C.c_int, f32, f32, f32, u64, u64]
+    L.mfb_sgd_epoch_flat.argtypes = [vp, C.c_int, f32, f32, f32, u64, u64]
+    L.mfb_set_option.argtypes = [vp, C.c_char_p, C.c_double]
     L.mfb_sgd_block_nnz.argtypes = [vp, vp, i32, C.POINTER(i64)]
     L.mfb_als_half_step.argtypes = [vp, C.c_int, f32]
     L.mfb_ccdpp_begin.argtypes = [vp]
@@ -172,6 +174,12 @@ class Engine:
     def sgd_subepoch(self, blocks, variant=MF, lr=0.005, ureg=0.01, ireg=0.01, seed=0, counter=0):
         b = _arr(blocks, np.int32).reshape(-1, 2)
         self._check(self.L.mfb_sgd_subepoch(self.h, _p(b), b.shape[0], variant, lr, ureg, ireg, seed, counter))
+
+    def sgd_epoch_flat(self, variant=MF, lr=0.005, ureg=0.01, ireg=0.01, seed=0, counter=0):
+        self._check(self.L.mfb_sgd_epoch_flat(self.h, variant, lr, ureg, ireg, seed, counter))
+
+    def set_option(self, name, value):
+        self._check(self.L.mfb_set_option(self.h, name.encode(), float(value)))
 
     def sgd_block_nnz(self, blocks):
         b = _arr(blocks, np.int32).reshape(-1, 2)

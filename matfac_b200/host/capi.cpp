@@ -1,0 +1,77 @@
+// C entry point over the host classes for callers that hold the matrices in memory (bench.py,
+// the Python tests): builds a Data object from arrays, constructs the requested model, runs the
+// requested trainer — the same objects and calls as `mf` — and copies results out.
+#include <omp.h>
+
+#include <cstring>
+#include <memory>
+
+#include "device_session.h"
+#include "matfac_host.h"
+#include "modelDropoutSigmoid.h"
+#include "modelInvPopMF.h"
+#include "modelMF.h"
+#include "modelPoissonDropout.h"
+
+static gk_csr_t *fromArrays(const mfh_csr &m) { return gk_csr_FromArrays(m.nrows, m.rowptr, m.rowind, m.rowval); }
+
+extern "C" int mfh_train(const mfh_problem *p, mfh_result *out) {
+  if (!p || !out) return 1;
+  std::string empty, trainName = "<memory>", prefix = p->prefix ? p->prefix : "/tmp/matfac";
+  Params params(p->facdim, p->maxiter, 5, p->seed, p->ureg, p->ireg, p->learnrate, p->rhorms, p->alpha, trainName,
+                trainName, trainName, empty, empty, empty, empty, empty, prefix);
+  Data data(fromArrays(p->train), fromArrays(p->val), fromArrays(p->test), p->facdim, prefix.c_str());
+  params.nUsers = data.nUsers;
+  params.nItems = data.nItems;
+  const int savedThreads = omp_get_max_threads();
+  if (p->num_parts > 0) omp_set_num_threads(p->num_parts);  // P of the stratified trainers
+  auto freq = getRowColFreq(data.trainMat);
+  std::vector<double> userFreq = freq.first, itemFreq = freq.second, noRank;
+  std::unique_ptr<Model> model, best;
+  const std::string algo = p->algo ? p->algo : "mf", method = p->mf_method ? p->mf_method : "sgd";
+  if (algo == "mf") {
+    model.reset(new ModelMF(params, params.seed));
+    best.reset(new ModelMF(params, params.seed));
+  } else if (algo == "IFWMF") {
+    model.reset(new ModelInvPopMF(params, params.seed, userFreq, itemFreq));
+    best.reset(new ModelInvPopMF(params, params.seed, userFreq, itemFreq));
+  } else if (algo == "TMF") {
+    model.reset(new ModelDropoutSigmoid(params, params.seed, noRank, noRank, userFreq, itemFreq));
+    best.reset(new ModelDropoutSigmoid(params, params.seed, noRank, noRank, userFreq, itemFreq));
+  } else if (algo == "TMFDropout") {
+    model.reset(new ModelPoissonDropout(params, params.seed, noRank, noRank, userFreq, itemFreq));
+    best.reset(new ModelPoissonDropout(params, params.seed, noRank, noRank, userFreq, itemFreq));
+  } else {
+    return 2;
+  }
+  if (p->init_U && p->init_V) {
+    memcpy(model->uFac.data(), p->init_U, sizeof(float) * (size_t)data.nUsers * p->facdim);
+    memcpy(model->iFac.data(), p->init_V, sizeof(float) * (size_t)data.nItems * p->facdim);
+    best->uFac = model->uFac;
+    best->iFac = model->iFac;
+  }
+  std::unordered_set<int> invalidUsers, invalidItems;
+  if (algo == "mf" && method == "ccd++") model->trainCCDPPFreqAdap(data, *best, invalidUsers, invalidItems);
+  else if (algo == "mf" && method == "ccdpp_plain") model->trainCCDPP(data, *best, invalidUsers, invalidItems);
+  else if (algo == "mf" && method == "als") model->trainALS(data, *best, invalidUsers, invalidItems);
+  else if (algo == "mf" && method == "hogsgd") model->hogTrain(data, *best, invalidUsers, invalidItems);
+  else if ((algo == "mf" || algo == "IFWMF") && method == "sgdpar") model->trainSGDPar(data, *best, invalidUsers, invalidItems);
+  else model->train(data, *best, invalidUsers, invalidItems);
+
+  out->n_users = data.nUsers;
+  out->n_items = data.nItems;
+  out->learn_rate = model->learnRate;
+  out->best_val_rmse = best->RMSE(data.valMat, invalidUsers, invalidItems);
+  out->best_test_rmse = best->RMSE(data.testMat, invalidUsers, invalidItems);
+  out->last_val_rmse = model->RMSE(data.valMat, invalidUsers, invalidItems);
+  out->last_objective = model->objective(data, invalidUsers, invalidItems);
+  const size_t ub = sizeof(float) * (size_t)data.nUsers * p->facdim, vb = sizeof(float) * (size_t)data.nItems * p->facdim;
+  if (out->last_U) memcpy(out->last_U, model->uFac.data(), ub);
+  if (out->last_V) memcpy(out->last_V, model->iFac.data(), vb);
+  if (out->best_U) memcpy(out->best_U, best->uFac.data(), ub);
+  if (out->best_V) memcpy(out->best_V, best->iFac.data(), vb);
+  omp_set_num_threads(savedThreads);
+  return 0;
+}
+
+extern "C" void mfh_release_device(void) { matfac::DeviceSession::dropAll(); }

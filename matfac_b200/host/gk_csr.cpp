@@ -1,0 +1,187 @@
+// Self-contained gk_csr_t reader / index builder (see GKlib.h).  Parsing is split at line
+// boundaries over OpenMP threads: at Netflix scale the text parse is what dominates start-up.
+#include "GKlib.h"
+
+#ifndef MATFAC_HAVE_GKLIB
+#include <algorithm>
+#include <vector>
+
+static gk_csr_t *csr_alloc() {
+  gk_csr_t *m = (gk_csr_t *)calloc(1, sizeof(gk_csr_t));
+  return m;
+}
+
+void gk_csr_Free(gk_csr_t **mat) {
+  if (!mat || !*mat) return;
+  gk_csr_t *m = *mat;
+  free(m->rowptr); free(m->colptr); free(m->rowind); free(m->colind); free(m->rowval); free(m->colval);
+  free(m);
+  *mat = NULL;
+}
+
+namespace {
+struct Piece {  // one thread's share of the file
+  std::vector<int32_t> ind;
+  std::vector<float> val;
+  std::vector<int64_t> rowlen;
+  int32_t maxcol = -1;
+};
+}  // namespace
+
+gk_csr_t *gk_csr_Read(char *filename, int format, int readvals, int numbering) {
+  if (format != GK_CSR_FMT_CSR) {
+    fprintf(stderr, "gk_csr_Read: only GK_CSR_FMT_CSR is supported\n");
+    exit(-1);
+  }
+  FILE *fp = fopen(filename, "rb");
+  if (!fp) {
+    fprintf(stderr, "gk_csr_Read: cannot open %s\n", filename);
+    exit(-1);
+  }
+  fseek(fp, 0, SEEK_END);
+  size_t sz = (size_t)ftell(fp);
+  fseek(fp, 0, SEEK_SET);
+  char *buf = (char *)malloc(sz + 2);
+  if (fread(buf, 1, sz, fp) != sz) {
+    fprintf(stderr, "gk_csr_Read: short read on %s\n", filename);
+    exit(-1);
+  }
+  fclose(fp);
+  if (sz > 0 && buf[sz - 1] != '\n') buf[sz++] = '\n';
+  buf[sz] = '\0';
+
+  int nt = omp_get_max_threads();
+  if (sz < (size_t)1 << 20) nt = 1;
+  std::vector<size_t> cut(nt + 1, sz);
+  cut[0] = 0;
+  for (int t = 1; t < nt; t++) {
+    size_t p = sz / nt * t;
+    while (p < sz && buf[p] != '\n') p++;
+    cut[t] = p < sz ? p + 1 : sz;
+  }
+  std::vector<Piece> pieces(nt);
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+  for (int t = 0; t < nt; t++) {
+    Piece &pc = pieces[t];
+    char *p = buf + cut[t], *end = buf + cut[t + 1];
+    while (p < end) {
+      char *eol = (char *)memchr(p, '\n', end - p);
+      int64_t n = 0;
+      if (*p != '%') {  // comment lines carry no row
+        char *q = p;
+        while (q < eol) {
+          char *e;
+          long col = strtol(q, &e, 10);
+          if (e == q) break;
+          q = e;
+          col -= numbering;
+          pc.ind.push_back((int32_t)col);
+          if ((int32_t)col > pc.maxcol) pc.maxcol = (int32_t)col;
+          if (readvals) {
+            float v = strtof(q, &e);
+            if (e == q) {
+              fprintf(stderr, "gk_csr_Read: missing value in %s\n", filename);
+              exit(-1);
+            }
+            q = e;
+            pc.val.push_back(v);
+          }
+          n++;
+        }
+        pc.rowlen.push_back(n);
+      }
+      p = eol + 1;
+    }
+  }
+  free(buf);
+  size_t nrows = 0, nnz = 0;
+  int32_t maxcol = -1;
+  for (auto &pc : pieces) {
+    nrows += pc.rowlen.size();
+    nnz += pc.ind.size();
+    maxcol = std::max(maxcol, pc.maxcol);
+  }
+  gk_csr_t *m = csr_alloc();
+  m->nrows = (int32_t)nrows;
+  m->ncols = maxcol + 1;
+  m->rowptr = (ssize_t *)malloc(sizeof(ssize_t) * (nrows + 1));
+  m->rowind = (int32_t *)malloc(sizeof(int32_t) * (nnz ? nnz : 1));
+  m->rowval = readvals ? (float *)malloc(sizeof(float) * (nnz ? nnz : 1)) : NULL;
+  size_t r = 0, k = 0;
+  m->rowptr[0] = 0;
+  for (auto &pc : pieces) {
+    if (!pc.ind.empty()) memcpy(m->rowind + k, pc.ind.data(), sizeof(int32_t) * pc.ind.size());
+    if (readvals && !pc.val.empty()) memcpy(m->rowval + k, pc.val.data(), sizeof(float) * pc.val.size());
+    size_t kk = k;
+    for (int64_t len : pc.rowlen) {
+      kk += (size_t)len;
+      m->rowptr[++r] = (ssize_t)kk;
+    }
+    k += pc.ind.size();
+  }
+  return m;
+}
+
+void gk_csr_CreateIndex(gk_csr_t *mat, int what) {
+  if (what != GK_CSR_COL) {
+    fprintf(stderr, "gk_csr_CreateIndex: only GK_CSR_COL is supported\n");
+    exit(-1);
+  }
+  const int32_t nr = mat->nrows, nc = mat->ncols;
+  const ssize_t nnz = mat->rowptr[nr];
+  free(mat->colptr); free(mat->colind); free(mat->colval);
+  mat->colptr = (ssize_t *)calloc((size_t)nc + 1, sizeof(ssize_t));
+  mat->colind = (int32_t *)malloc(sizeof(int32_t) * (nnz ? nnz : 1));
+  mat->colval = mat->rowval ? (float *)malloc(sizeof(float) * (nnz ? nnz : 1)) : NULL;
+  for (ssize_t j = 0; j < nnz; j++) mat->colptr[mat->rowind[j] + 1]++;
+  for (int32_t c = 0; c < nc; c++) mat->colptr[c + 1] += mat->colptr[c];
+  std::vector<ssize_t> cursor(mat->colptr, mat->colptr + nc);
+  for (int32_t r = 0; r < nr; r++)
+    for (ssize_t j = mat->rowptr[r]; j < mat->rowptr[r + 1]; j++) {
+      const ssize_t d = cursor[mat->rowind[j]]++;
+      mat->colind[d] = r;
+      if (mat->colval) mat->colval[d] = mat->rowval[j];
+    }
+}
+
+template <typename T>
+static T *clone(const T *src, size_t n) {
+  if (!src) return NULL;
+  T *d = (T *)malloc(sizeof(T) * (n ? n : 1));
+  memcpy(d, src, sizeof(T) * n);
+  return d;
+}
+
+gk_csr_t *gk_csr_Dup(gk_csr_t *mat) {
+  gk_csr_t *m = csr_alloc();
+  m->nrows = mat->nrows;
+  m->ncols = mat->ncols;
+  if (mat->rowptr) {
+    const size_t nnz = (size_t)mat->rowptr[mat->nrows];
+    m->rowptr = clone(mat->rowptr, (size_t)mat->nrows + 1);
+    m->rowind = clone(mat->rowind, nnz);
+    m->rowval = clone(mat->rowval, nnz);
+  }
+  if (mat->colptr) {
+    const size_t nnz = (size_t)mat->colptr[mat->ncols];
+    m->colptr = clone(mat->colptr, (size_t)mat->ncols + 1);
+    m->colind = clone(mat->colind, nnz);
+    m->colval = clone(mat->colval, nnz);
+  }
+  return m;
+}
+
+gk_csr_t *gk_csr_FromArrays(int32_t nrows, const int64_t *rowptr, const int32_t *rowind, const float *rowval) {
+  gk_csr_t *m = csr_alloc();
+  const size_t nnz = (size_t)rowptr[nrows];
+  m->nrows = nrows;
+  m->rowptr = (ssize_t *)malloc(sizeof(ssize_t) * ((size_t)nrows + 1));
+  for (int32_t r = 0; r <= nrows; r++) m->rowptr[r] = (ssize_t)rowptr[r];
+  m->rowind = clone(rowind, nnz);
+  m->rowval = clone(rowval, nnz);
+  int32_t maxcol = -1;
+  for (size_t j = 0; j < nnz; j++) maxcol = std::max(maxcol, rowind[j]);
+  m->ncols = maxcol + 1;
+  return m;
+}
+#endif

@@ -1,0 +1,44 @@
+/* C view of the host library (libmatfac_host.so) for callers that are not C++: one call that
+ * runs a whole training job through the same classes as the `mf` binary.  All pointers are
+ * host pointers; matrices are CSR with int64 row pointers. */
+#ifndef MATFAC_HOST_H
+#define MATFAC_HOST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mfh_csr {
+  int32_t nrows;
+  const int64_t *rowptr;
+  const int32_t *rowind;
+  const float *rowval;
+} mfh_csr;
+
+typedef struct mfh_problem {
+  mfh_csr train, val, test;
+  const char *algo;      /* mf | IFWMF | TMF | TMFDropout           (main.cpp:45) */
+  const char *mf_method; /* sgd | sgdpar | hogsgd | als | ccd++ | ccdpp_plain (main.cpp:44) */
+  int32_t facdim, maxiter, seed;
+  int32_t num_parts;     /* P of the stratified trainers; 0 = omp_get_max_threads() like the reference */
+  float ureg, ireg, learnrate, rhorms, alpha;
+  const float *init_U, *init_V; /* optional [n][facdim] starting factors (NULL = seeded init) */
+  const char *prefix;
+} mfh_problem;
+
+typedef struct mfh_result {
+  int32_t n_users, n_items;
+  float learn_rate;
+  double best_val_rmse, best_test_rmse, last_val_rmse, last_objective;
+  float *last_U, *last_V, *best_U, *best_V; /* caller-allocated [n][facdim], may be NULL */
+} mfh_result;
+
+int mfh_train(const mfh_problem *p, mfh_result *out);
+void mfh_release_device(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

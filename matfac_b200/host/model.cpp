@@ -1,0 +1,429 @@
+// Model base class: state, seeded initialisation, device-backed evaluation, early stopping and
+// persistence.  Mirrors the reference's model.cpp for the functions on the training path
+// (ctor/init :2315-2366, estRating :547, RMSE :191/:214, objective :1694/:1770,
+// isTerminateModel :1471, save/load :31-188, modelSignature :11).
+#include "model.h"
+
+#include <omp.h>
+
+#include <cmath>
+
+#include "device_session.h"
+#include "io.h"
+
+using matfac::DeviceSession;
+
+// ---- construction --------------------------------------------------------------------------
+Model::Model(int p_nUsers, int p_nItems, int p_facDim)
+    : nUsers(p_nUsers), nItems(p_nItems), facDim(p_facDim), trainSeed(-1), origLearnRate(0), learnRate(0),
+      rhoRMS(0), alpha(0), maxIter(0), uReg(0), iReg(0), sing_a(0), sing_b(0), mu(0) {}
+
+// One std::default_random_engine stream seeded with params.seed feeds, in this order, uFac
+// (user outer, dimension inner), iFac, uBias, iBias through
+// uniform_real_distribution<double>(-0.01f, 0.01f) — the same calls as model.cpp:2331-2362, so
+// with the same libstdc++ the initial factors are bit-identical to the reference's.
+Model::Model(const Params &params)
+    : nUsers(params.nUsers), nItems(params.nItems), facDim(params.facDim), trainSeed(-1),
+      origLearnRate(params.learnRate), learnRate(params.learnRate), rhoRMS(params.rhoRMS), alpha(params.alpha),
+      maxIter(params.maxIter), uReg(params.uReg), iReg(params.iReg), sing_a(params.uReg), sing_b(params.iReg),
+      mu(0) {
+  std::default_random_engine generator(params.seed);
+  float lb = -0.01, ub = 0.01;
+  std::uniform_real_distribution<double> dist(lb, ub);
+  std::cout << "lb = " << lb << " ub = " << ub << std::endl;
+  uFac = Eigen::MatrixXf(nUsers, facDim);
+  for (int u = 0; u < nUsers; u++)
+    for (int k = 0; k < facDim; k++) uFac(u, k) = dist(generator);
+  iFac = Eigen::MatrixXf(nItems, facDim);
+  for (int i = 0; i < nItems; i++)
+    for (int k = 0; k < facDim; k++) iFac(i, k) = dist(generator);
+  uBias = Eigen::VectorXf(nUsers);
+  for (int u = 0; u < nUsers; u++) uBias(u) = dist(generator);
+  iBias = Eigen::VectorXf(nItems);
+  for (int i = 0; i < nItems; i++) iBias(i) = dist(generator);
+  singularVals = Eigen::VectorXf(facDim);
+}
+
+Model::Model(int p_nUsers, int p_nItems, const Params &params) : Model(params) {
+  nUsers = p_nUsers;
+  nItems = p_nItems;
+}
+
+Model::Model(const Params &params, int seed) : Model(params) { trainSeed = seed; }
+
+Model::Model(const Params &params, const char *uFacName, const char *iFacName, int seed) : Model(params, seed) {
+  std::cout << "\nLoading user factors: " << uFacName;
+  readMat(uFac, nUsers, facDim, uFacName);
+  std::cout << "\nLoading item factors: " << iFacName;
+  readMat(iFac, nItems, facDim, iFacName);
+}
+
+Model::Model(const Params &params, const char *uFacName, const char *iFacName, const char *uBFName,
+             const char *iBFName, const char *gBFName, int seed)
+    : Model(params, uFacName, iFacName, seed) {
+  uBias = readEigVector(uBFName);
+  iBias = readEigVector(iBFName);
+  std::vector<double> gBias = readDVector(gBFName);
+  mu = gBias.empty() ? 0 : gBias[0];
+}
+
+// ---- small host-side pieces ----------------------------------------------------------------
+double Model::estRating(int user, int item) { return uFac.row(user).dot(iFac.row(item)); }
+
+std::string Model::modelSignature() {
+  return std::to_string(nUsers) + "X" + std::to_string(nItems) + "_" + std::to_string(facDim) + "_" +
+         std::to_string(uReg) + "_" + std::to_string(iReg) + "_" + std::to_string(origLearnRate);
+}
+
+void Model::display() {
+  std::cout << "nUsers: " << nUsers << " nItems: " << nItems << std::endl;
+  std::cout << "facDim: " << facDim << std::endl;
+  std::cout << "uReg: " << uReg << " iReg: " << iReg << std::endl;
+  std::cout << "learnRate: " << learnRate << std::endl;
+  std::cout << "trainSeed: " << trainSeed;
+}
+
+void Model::copyScalarsFrom(const Model &o) {
+  nUsers = o.nUsers; nItems = o.nItems; facDim = o.facDim; trainSeed = o.trainSeed;
+  origLearnRate = o.origLearnRate; learnRate = o.learnRate; rhoRMS = o.rhoRMS; alpha = o.alpha;
+  maxIter = o.maxIter; uReg = o.uReg; iReg = o.iReg; sing_a = o.sing_a; sing_b = o.sing_b; mu = o.mu;
+}
+
+// ---- persistence (file names and text format of model.cpp:31-128, io.cpp:139-154) -----------
+void Model::saveFacs(std::string prefix) {
+  std::cout << "Saving model... " << prefix << std::endl;
+  const std::string sign = modelSignature();
+  const std::string uName = prefix + "_uFac_" + sign + ".mat", iName = prefix + "_iFac_" + sign + ".mat";
+  writeMat(uFac, nUsers, facDim, uName.c_str());
+  std::cout << "uFac Norm: " << uFac.norm() << std::endl;
+  writeMat(iFac, nItems, facDim, iName.c_str());
+  std::cout << "iFac Norm: " << iFac.norm() << std::endl;
+}
+
+void Model::save(std::string prefix) {
+  saveFacs(prefix);
+  const std::string sign = modelSignature();
+  writeVector(uBias, (prefix + "_uBias_" + sign + ".vec").c_str());
+  writeVector(iBias, (prefix + "_iBias_" + sign + ".vec").c_str());
+  std::vector<double> gBias = {mu};
+  writeVector(gBias, (prefix + "_" + sign + "_gBias").c_str());
+}
+
+void Model::loadFacs(std::string prefix) {
+  const std::string sign = modelSignature();
+  const std::string uName = prefix + "_uFac_" + sign + ".mat", iName = prefix + "_iFac_" + sign + ".mat";
+  if (isFileExist(uName.c_str())) readMat(uFac, nUsers, facDim, uName.c_str());
+  if (isFileExist(iName.c_str())) readMat(iFac, nItems, facDim, iName.c_str());
+  std::cout << "uFac Norm: " << uFac.norm() << " iFac Norm: " << iFac.norm() << std::endl;
+}
+
+void Model::load(std::string prefix) {
+  loadFacs(prefix);
+  const std::string sign = modelSignature();
+  const std::string ub = prefix + "_uBias_" + sign + ".vec", ib = prefix + "_iBias_" + sign + ".vec",
+                    gb = prefix + "_" + sign + "_gBias";
+  if (isFileExist(ub.c_str())) uBias = readEigVector(ub.c_str());
+  if (isFileExist(ib.c_str())) iBias = readEigVector(ib.c_str());
+  if (isFileExist(gb.c_str())) {
+    std::vector<double> g = readDVector(gb.c_str());
+    if (!g.empty()) mu = g[0];
+  }
+}
+
+void Model::load(const char *uFacName, const char *iFacName) {
+  readMat(uFac, nUsers, facDim, uFacName);
+  readMat(iFac, nItems, facDim, iFacName);
+}
+
+void Model::saveBinFacs(std::string prefix) {
+  const std::string sign = modelSignature();
+  writeMatBin(uFac, nUsers, facDim, (prefix + "_uFac_" + sign + ".binmat").c_str());
+  writeMatBin(iFac, nItems, facDim, (prefix + "_iFac_" + sign + ".binmat").c_str());
+}
+
+void Model::loadBinFacs(std::string prefix) {
+  const std::string sign = modelSignature();
+  readMatBin(uFac, nUsers, facDim, (prefix + "_uFac_" + sign + ".binmat").c_str());
+  readMatBin(iFac, nItems, facDim, (prefix + "_iFac_" + sign + ".binmat").c_str());
+}
+
+// ---- device-backed evaluation ---------------------------------------------------------------
+int Model::deviceVariant() const { return MFB_MF; }
+
+void Model::uploadAux(DeviceSession &, const Data *, std::unordered_set<int> &, std::unordered_set<int> &) {}
+
+void Model::uploadFactors(DeviceSession &s) {
+  s.check(mfb_upload_factors(s.eng, uFac.data(), facDim, iFac.data(), facDim));
+}
+
+// objective = true: weighted SSE over train + uReg |U|^2 + iReg |V|^2; false: RMSE over `which`
+double Model::deviceEval(DeviceSession &s, int which, bool objective) {
+  double out[4] = {0, 0, 0, 0};
+  const int variant = deviceVariant();
+  s.check(mfb_eval(s.eng, which, MFB_CURRENT, variant, objective && variant == MFB_IFWMF, objective, out));
+  if (objective) return out[0] + out[2] * uReg + out[3] * iReg;
+  return sqrt(out[0] / out[1]);
+}
+
+double Model::RMSE(gk_csr_t *mat, std::unordered_set<int> &invalidUsers, std::unordered_set<int> &invalidItems) {
+  if (dev_ && dev_->slotOf(mat) >= 0) return deviceEval(*dev_, dev_->slotOf(mat), false);  // inside a trainer
+  int which = 0;
+  DeviceSession &s = DeviceSession::forMatrix(mat, nUsers, nItems, facDim, &which);
+  s.setMasks(invalidUsers, invalidItems);
+  uploadFactors(s);
+  uploadAux(s, nullptr, invalidUsers, invalidItems);
+  return deviceEval(s, which, false);
+}
+
+double Model::RMSE(gk_csr_t *mat) {
+  std::unordered_set<int> none;
+  return RMSE(mat, none, none);
+}
+
+double Model::objective(const Data &data, std::unordered_set<int> &invalidUsers,
+                        std::unordered_set<int> &invalidItems) {
+  if (dev_ && dev_->slotOf(data.trainMat) >= 0) return deviceEval(*dev_, MFB_TRAIN, true);
+  DeviceSession &s = DeviceSession::forData(data, facDim);
+  s.setMasks(invalidUsers, invalidItems);
+  uploadFactors(s);
+  uploadAux(s, &data, invalidUsers, invalidItems);
+  return deviceEval(s, MFB_TRAIN, true);
+}
+
+double Model::objective(const Data &data) {
+  std::unordered_set<int> none;
+  return objective(data, none, none);
+}
+
+// ---- early stopping --------------------------------------------------------------------------
+bool Model::isTerminateModel(Model &bestModel, const Data &data, int iter, int &bestIter, double &bestObj,
+                             double &prevObj, double &bestValRMSE, double &prevValRMSE,
+                             std::unordered_set<int> &invalidUsers, std::unordered_set<int> &invalidItems) {
+  bool ret = false;
+  const double currObj = objective(data, invalidUsers, invalidItems);
+  double currValRMSE = -1;
+  if (data.valMat) {
+    currValRMSE = RMSE(data.valMat, invalidUsers, invalidItems);
+  } else {
+    std::cerr << "\nNo validation data" << std::endl;
+    exit(0);
+  }
+  const bool onDevice = dev_ != nullptr;
+  if (currObj != currObj || currValRMSE != currValRMSE) {
+    std::cout << "Found nan " << std::endl;
+    if (learnRate > 1e-5) {
+      // *this = bestModel; learnRate /= 2   (model.cpp:1490-1493)
+      copyScalarsFrom(bestModel);
+      if (onDevice) {
+        if (bestOnDevice_) {
+          dev_->check(mfb_restore_best(dev_->eng));
+        } else {
+          dev_->check(mfb_upload_factors(dev_->eng, bestModel.uFac.data(), facDim, bestModel.iFac.data(), facDim));
+        }
+      } else {
+        uFac = bestModel.uFac;
+        iFac = bestModel.iFac;
+      }
+      learnRate = learnRate / 2;
+      return false;
+    }
+    return true;
+  }
+  if (currValRMSE < bestValRMSE) {
+    // bestModel = *this (model.cpp:1500-1504): scalars now, factors as a device snapshot
+    bestModel.copyScalarsFrom(*this);
+    if (onDevice) {
+      dev_->check(mfb_snapshot_best(dev_->eng));
+      bestOnDevice_ = true;
+    } else {
+      bestModel.uFac = uFac;
+      bestModel.iFac = iFac;
+    }
+    bestValRMSE = currValRMSE;
+    bestIter = iter;
+  }
+  if (iter - bestIter >= 100) {
+    if (learnRate > 1e-5) learnRate = learnRate / 2;
+  }
+  if (iter - bestIter >= CHANCE_ITER) {
+    printf("\nNOT CONVERGED: bestIter:%d bestObj: %.10e bestValRMSE: %.10e currIter:%d currObj: %.10e currValRMSE: %.10e",
+           bestIter, bestObj, bestValRMSE, iter, currObj, currValRMSE);
+    ret = true;
+  }
+  if (fabs(prevObj - currObj) < EPS) {
+    printf("\nConverged in iteration: %d prevObj: %.10e currObj: %.10e bestValRMSE: %.10e", iter, prevObj, currObj,
+           bestValRMSE);
+    ret = true;
+  }
+  prevObj = currObj;
+  prevValRMSE = currValRMSE;
+  return ret;
+}
+
+bool Model::isTerminateModel(Model &bestModel, const Data &data, int iter, int &bestIter, double &bestObj,
+                             double &prevObj, std::unordered_set<int> &invalidUsers,
+                             std::unordered_set<int> &invalidItems) {
+  bool ret = false;
+  const double currObj = objective(data, invalidUsers, invalidItems);
+  if (iter > 0) {
+    if (currObj < bestObj) {
+      bestModel.copyScalarsFrom(*this);
+      if (dev_) {
+        dev_->check(mfb_snapshot_best(dev_->eng));
+        bestOnDevice_ = true;
+      } else {
+        bestModel.uFac = uFac;
+        bestModel.iFac = iFac;
+      }
+      bestObj = currObj;
+      bestIter = iter;
+    }
+    if (iter - bestIter >= 100) {
+      if (learnRate > 1e-5) learnRate = learnRate / 2;
+      else if (learnRate < 1e-5) learnRate = 1e-5;
+    }
+    if (iter - bestIter >= 500) ret = true;
+    if (fabs(prevObj - currObj) < EPS) ret = true;
+  }
+  if (iter == 0) {
+    bestObj = currObj;
+    bestIter = iter;
+  }
+  prevObj = currObj;
+  return ret;
+}
+
+// ---- trainer skeletons ------------------------------------------------------------------------
+// Common preamble of every trainer (modelMF.cpp:34-61): invalid ids, initial objective and
+// validation RMSE — plus the device set-up that replaces the host arrays.
+void Model::beginTraining(const Data &data, Model &bestModel, std::unordered_set<int> &invalidUsers,
+                          std::unordered_set<int> &invalidItems, Stop &st, const char *tag) {
+  (void)bestModel;
+  gk_csr_t *trainMat = data.trainMat;
+  std::vector<std::unordered_set<int>> uISet;
+  genStats(trainMat, uISet, std::to_string(trainSeed));
+  getInvalidUsersItems(trainMat, uISet, invalidUsers, invalidItems);
+  for (int u = trainMat->nrows; u < data.nUsers; u++) invalidUsers.insert(u);
+  for (int item = trainMat->ncols; item < data.nItems; item++) invalidItems.insert(item);
+
+  DeviceSession &s = DeviceSession::forData(data, facDim);
+  s.setMasks(invalidUsers, invalidItems);
+  uploadFactors(s);
+  uploadAux(s, &data, invalidUsers, invalidItems);
+  dev_ = &s;
+  bestOnDevice_ = false;
+
+  st.prevObj = objective(data, invalidUsers, invalidItems);
+  st.bestObj = st.prevObj;
+  st.bestValRMSE = st.prevValRMSE = RMSE(data.valMat, invalidUsers, invalidItems);
+  std::cout << "\nObj aftr svd: " << st.prevObj << " Train RMSE: " << RMSE(data.trainMat, invalidUsers, invalidItems)
+            << " Val RMSE: " << st.bestValRMSE;
+  std::cout << "\n" << tag << " trainSeed: " << trainSeed << " invalidUsers: " << invalidUsers.size()
+            << " invalidItems: " << invalidItems.size() << std::endl;
+}
+
+void Model::syncBest(Model &bestModel) {
+  if (dev_ && bestOnDevice_) {
+    dev_->check(mfb_download_factors(dev_->eng, MFB_BEST, bestModel.uFac.data(), facDim, bestModel.iFac.data(), facDim));
+    bestOnDevice_ = false;
+  }
+}
+
+void Model::endTraining(Model &bestModel) {
+  if (!dev_) return;
+  syncBest(bestModel);
+  dev_->check(mfb_download_factors(dev_->eng, MFB_CURRENT, uFac.data(), facDim, iFac.data(), facDim));
+  dev_ = nullptr;
+}
+
+bool Model::afterEpoch(const Data &data, Model &bestModel, int iter, Stop &st, std::unordered_set<int> &invalidUsers,
+                       std::unordered_set<int> &invalidItems, double subIterDuration, const char *tag, bool saves) {
+  if (!(iter % OBJ_ITER == 0 || iter == maxIter - 1)) return false;
+  if (isTerminateModel(bestModel, data, iter, st.bestIter, st.bestObj, st.prevObj, st.bestValRMSE, st.prevValRMSE,
+                       invalidUsers, invalidItems))
+    return true;
+  if (iter % DISP_ITER == 0) {
+    std::cout << tag << " trainSeed: " << trainSeed << " Iter: " << iter << " Objective: " << std::scientific
+              << st.prevObj << " Train RMSE: " << RMSE(data.trainMat, invalidUsers, invalidItems)
+              << " Val RMSE: " << st.prevValRMSE << " subIterDuration: " << subIterDuration << std::endl;
+  }
+  if (saves && (iter % SAVE_ITER == 0 || iter == maxIter - 1)) {
+    syncBest(bestModel);
+    bestModel.saveFacs(std::string(data.prefix));
+  }
+  return false;
+}
+
+static double elapsedSeconds(DeviceSession &s) {
+  float ms = 0;
+  s.check(mfb_event_elapsed_ms(s.eng, 0, 1, &ms));
+  return ms * 1e-3;
+}
+
+// Serial / Hogwild trainers on the device: every valid rating once per epoch in a fresh
+// pseudo-random order (the reference reshuffles each epoch: modelMF.cpp:76-81).
+void Model::runFlatSgd(const Data &data, Model &bestModel, std::unordered_set<int> &invalidUsers,
+                       std::unordered_set<int> &invalidItems, const char *tag, bool saves) {
+  Stop st;
+  beginTraining(data, bestModel, invalidUsers, invalidItems, st, tag);
+  DeviceSession &s = *dev_;
+  s.check(mfb_sgd_plan(s.eng, 1, nullptr, nullptr));
+  const int variant = deviceVariant();
+  for (int iter = 0; iter < maxIter; iter++) {
+    s.check(mfb_event_record(s.eng, 0));
+    s.check(mfb_sgd_epoch_flat(s.eng, variant, learnRate, uReg, iReg, (uint64_t)(uint32_t)trainSeed, (uint64_t)iter));
+    s.check(mfb_event_record(s.eng, 1));
+    const double dur = elapsedSeconds(s);
+    if (afterEpoch(data, bestModel, iter, st, invalidUsers, invalidItems, dur, tag, saves)) break;
+  }
+  endTraining(bestModel);
+  if (saves) bestModel.saveFacs(std::string(data.prefix));
+  std::cout << "\nBest model validation RMSE: " << bestModel.RMSE(data.valMat, invalidUsers, invalidItems) << std::endl;
+}
+
+// Stratified SGD (modelMF.cpp:154-350 and the IFWMF / TMF / TMF+Dropout twins): users and items
+// are shuffled by mt19937(trainSeed) and cut into P = omp_get_max_threads() parts with the
+// reference's boundary rule; every epoch draws P random permutation schedules from the same
+// engine.  All of that is host code calling libstdc++ exactly like the reference (bit-exact
+// partitions and schedules); the P conflict-free blocks of a schedule run as one device launch.
+void Model::runStratifiedSgd(const Data &data, Model &bestModel, std::unordered_set<int> &invalidUsers,
+                             std::unordered_set<int> &invalidItems, const char *tag, bool saves) {
+  Stop st;
+  beginTraining(data, bestModel, invalidUsers, invalidItems, st, tag);
+  DeviceSession &s = *dev_;
+  gk_csr_t *trainMat = data.trainMat;
+  std::vector<int> trainUsers = matfac::validIds(trainMat->nrows, invalidUsers);
+  std::vector<int> trainItems = matfac::validIds(trainMat->ncols, invalidItems);
+  std::mt19937 mt(trainSeed);
+  std::shuffle(trainUsers.begin(), trainUsers.end(), mt);
+  std::shuffle(trainItems.begin(), trainItems.end(), mt);
+  int P = omp_get_max_threads();
+  if (P > 64) P = 64;  // one launch carries at most 64 blocks
+  std::cout << "maxThreads: " << P << std::endl;
+  std::cout << "train users: " << trainUsers.size() << " usersPerPart: " << trainUsers.size() / P << std::endl;
+  std::cout << "train items: " << trainItems.size() << " itemsPerPart: " << trainItems.size() / P << std::endl;
+  std::vector<int> userPart = matfac::partitionIds(trainUsers, P, nUsers);
+  std::vector<int> itemPart = matfac::partitionIds(trainItems, P, nItems);
+  s.check(mfb_sgd_plan(s.eng, P, userPart.data(), itemPart.data()));
+  const int variant = deviceVariant();
+  std::vector<std::pair<int, int>> updateSeq;
+  std::vector<int32_t> blocks(2 * (size_t)P);
+  for (int iter = 0; iter < maxIter; iter++) {
+    s.check(mfb_event_record(s.eng, 0));
+    for (int k = 0; k < P; k++) {
+      sgdUpdateBlockSeq(P, updateSeq, mt);
+      for (int t = 0; t < P; t++) {
+        blocks[2 * t] = updateSeq[t].first;
+        blocks[2 * t + 1] = updateSeq[t].second;
+      }
+      s.check(mfb_sgd_subepoch(s.eng, blocks.data(), P, variant, learnRate, uReg, iReg, (uint64_t)(uint32_t)trainSeed,
+                               (uint64_t)iter * P + k));
+    }
+    s.check(mfb_event_record(s.eng, 1));
+    const double dur = elapsedSeconds(s);
+    if (afterEpoch(data, bestModel, iter, st, invalidUsers, invalidItems, dur, tag, saves)) break;
+  }
+  endTraining(bestModel);
+  if (saves) bestModel.saveFacs(std::string(data.prefix));
+  std::cout << "\nBest model validation RMSE: " << bestModel.RMSE(data.valMat, invalidUsers, invalidItems) << std::endl;
+}

@@ -1,0 +1,93 @@
+#include "modelMF.h"
+
+#include "device_session.h"
+
+using matfac::DeviceSession;
+
+void ModelMF::train(const Data &data, Model &bestModel, std::unordered_set<int> &invalidUsers,
+                    std::unordered_set<int> &invalidItems) {
+  std::cout << "\nModelMF::train trainSeed: " << trainSeed;
+  std::cout << "\nObj b4 svd: " << objective(data) << " Train RMSE: " << RMSE(data.trainMat)
+            << " Train nnz: " << data.trainNNZ << std::endl;
+  runFlatSgd(data, bestModel, invalidUsers, invalidItems, "ModelMF::train", true);
+}
+
+void ModelMF::hogTrain(const Data &data, Model &bestModel, std::unordered_set<int> &invalidUsers,
+                       std::unordered_set<int> &invalidItems) {
+  std::cout << "\nModelMF::hogTrain trainSeed: " << trainSeed;
+  runFlatSgd(data, bestModel, invalidUsers, invalidItems, "ModelMF::hogTrain", true);
+}
+
+void ModelMF::trainSGDPar(const Data &data, Model &bestModel, std::unordered_set<int> &invalidUsers,
+                          std::unordered_set<int> &invalidItems) {
+  std::cout << "\nModelMF::trainSGDPar trainSeed: " << trainSeed;
+  std::cout << "\nObj b4 svd: " << objective(data) << " Train RMSE: " << RMSE(data.trainMat)
+            << " Train nnz: " << data.trainNNZ << std::endl;
+  // the reference never writes factor files from this trainer (modelMF.cpp:337,346)
+  runStratifiedSgd(data, bestModel, invalidUsers, invalidItems, "ModelMF::trainSGDPar", false);
+}
+
+// One epoch = user half-step over the CSR, then item half-step over the CSC with the fresh U
+// (modelMF.cpp:795-882).
+void ModelMF::trainALS(const Data &data, Model &bestModel, std::unordered_set<int> &invalidUsers,
+                       std::unordered_set<int> &invalidItems) {
+  std::cout << "\nModelMF::trainALS trainSeed: " << trainSeed;
+  Stop st;
+  beginTraining(data, bestModel, invalidUsers, invalidItems, st, "ModelMF::trainALS");
+  DeviceSession &s = *dev_;
+  for (int iter = 0; iter < maxIter; iter++) {
+    s.check(mfb_event_record(s.eng, 0));
+    s.check(mfb_als_half_step(s.eng, MFB_USER, uReg));
+    s.check(mfb_als_half_step(s.eng, MFB_ITEM, iReg));
+    s.check(mfb_event_record(s.eng, 1));
+    float ms = 0;
+    s.check(mfb_event_elapsed_ms(s.eng, 0, 1, &ms));
+    if (afterEpoch(data, bestModel, iter, st, invalidUsers, invalidItems, ms * 1e-3, "ModelMF::trainALS", true)) break;
+  }
+  endTraining(bestModel);
+  bestModel.saveFacs(std::string(data.prefix));
+  std::cout << "\nBest model validation RMSE: " << bestModel.RMSE(data.valMat, invalidUsers, invalidItems) << std::endl;
+}
+
+void ModelMF::runCcdpp(const Data &data, Model &bestModel, std::unordered_set<int> &invalidUsers,
+                       std::unordered_set<int> &invalidItems, bool freqAdap, const char *tag) {
+  std::cout << "\n" << tag << " trainSeed: " << trainSeed;
+  Stop st;
+  beginTraining(data, bestModel, invalidUsers, invalidItems, st, tag);
+  DeviceSession &s = *dev_;
+  if (freqAdap) {
+    // itemFreq of the train matrix feeds the "fewer than 75 ratings" rule (modelMF.cpp:1204-1206,1336)
+    auto freq = getRowColFreq(data.trainMat);
+    std::vector<int32_t> uf(nUsers, 0), itf(nItems, 0);
+    for (size_t u = 0; u < freq.first.size(); u++) uf[u] = (int32_t)freq.first[u];
+    for (size_t i = 0; i < freq.second.size(); i++) itf[i] = (int32_t)freq.second[i];
+    s.check(mfb_set_aux(s.eng, MFB_MF, uf.data(), itf.data(), nullptr, nullptr, nullptr, nullptr, nullptr));
+  }
+  std::mt19937 mt(trainSeed);
+  std::vector<int> dims(facDim);
+  std::iota(dims.begin(), dims.end(), 0);
+  s.check(mfb_ccdpp_begin(s.eng));  // residual = ratings, U = 0 (modelMF.cpp:1013,1020)
+  for (int iter = 0; iter < maxIter; iter++) {
+    s.check(mfb_event_record(s.eng, 0));
+    if (!freqAdap) std::shuffle(dims.begin(), dims.end(), mt);  // commented out in the FreqAdap twin (:1271)
+    for (int k : dims) s.check(mfb_ccdpp_rank1(s.eng, k, iter == 0, 5, uReg, iReg, freqAdap ? 75 : 0));
+    s.check(mfb_event_record(s.eng, 1));
+    float ms = 0;
+    s.check(mfb_event_elapsed_ms(s.eng, 0, 1, &ms));
+    if (afterEpoch(data, bestModel, iter, st, invalidUsers, invalidItems, ms * 1e-3, tag, true)) break;
+  }
+  s.check(mfb_ccdpp_end(s.eng));
+  endTraining(bestModel);
+  bestModel.saveFacs(std::string(data.prefix));
+  std::cout << "\nBest model validation RMSE: " << bestModel.RMSE(data.valMat, invalidUsers, invalidItems) << std::endl;
+}
+
+void ModelMF::trainCCDPP(const Data &data, Model &bestModel, std::unordered_set<int> &invalidUsers,
+                         std::unordered_set<int> &invalidItems) {
+  runCcdpp(data, bestModel, invalidUsers, invalidItems, false, "ModelMF::trainCCDPP");
+}
+
+void ModelMF::trainCCDPPFreqAdap(const Data &data, Model &bestModel, std::unordered_set<int> &invalidUsers,
+                                 std::unordered_set<int> &invalidItems) {
+  runCcdpp(data, bestModel, invalidUsers, invalidItems, true, "ModelMF::trainCCDPPFreqAdap");
+}

@@ -1,0 +1,206 @@
+"""The C++ host side (matfac_b200/host: the reference's Params / Data / Model classes and the `mf`
+CLI over the C ABI).
+
+CPU part: everything the host computes before it touches the GPU — text-CSR parse, CSC index,
+seeded factor initialisation, invalid ids, stratum partitions, schedules, CCD++ dimension order —
+must be bit-identical to the oracle (and hence to the reference binary, see test_oracle.py).
+GPU part: whole training jobs through `mf`, compared with the oracle at the north_star tolerances.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from common import rel_err
+from matfac_b200 import synth
+from test_oracle import golden_problem
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MF = os.path.join(ROOT, "matfac_b200", "mf")
+HOST_SO = os.path.join(ROOT, "matfac_b200", "libmatfac_host.so")
+
+
+def run_mf(files, dump, threads=1, timeout=600, **flags):
+    os.makedirs(dump, exist_ok=True)
+    cmd = [MF, "--trainmat", files[0], "--valmat", files[1], "--testmat", files[2], "--prefix",
+           os.path.join(dump, "gpu"), "--dump", dump]
+    for k, v in flags.items():
+        cmd += ["--" + k, str(v)]
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+    p = subprocess.run(cmd, env=env, cwd=dump, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout)
+    out = p.stdout.decode(errors="replace")
+    assert p.returncode == 0, out[-3000:]
+    return out
+
+
+def read_vec(path, dtype=np.int32):
+    return ol.read_set(path) if dtype == np.int32 else None
+
+
+@pytest.mark.parametrize("threads", [1, 4, 7])
+def test_host_plan_is_bit_exact(tmp_path, threads):
+    assert os.path.exists(MF), "build the host library first (python __graft_entry__.py)"
+    files = synth.write_split_files(str(tmp_path), *golden_problem())
+    dump = str(tmp_path / "dry")
+    run_mf(files, dump, threads=threads, facdim=8, seed=3, dry_run=1)
+    od = ol.OracleData(files=files)
+    m = ol.OracleModel(od, algo="mf", facdim=8, seed=3, nthreads=threads)
+    U, V = m.factors()
+    assert np.array_equal(U, ol.read_mat(os.path.join(dump, "init_uFac.bin")))
+    assert np.array_equal(V, ol.read_mat(os.path.join(dump, "init_iFac.bin")))
+    up, ip, sched = m.dsgd_plan(threads, 24)
+    assert np.array_equal(up, ol.read_set(os.path.join(dump, "user_part.bin")))
+    assert np.array_equal(ip, ol.read_set(os.path.join(dump, "item_part.bin")))
+    assert np.array_equal(sched.ravel(), ol.read_set(os.path.join(dump, "schedule.bin")))
+    assert np.array_equal(ol.ccdpp_dim_order(3, 8, 3).ravel(), ol.read_set(os.path.join(dump, "ccdpp_dims.bin")))
+    m.compute_invalid()
+    bu, bi = m.invalid()
+    assert np.array_equal(np.nonzero(bu)[0], ol.read_set(os.path.join(dump, "invalidUsers.bin")))
+    assert np.array_equal(np.nonzero(bi)[0], ol.read_set(os.path.join(dump, "invalidItems.bin")))
+    for which, name in ((0, "train"), (1, "val"), (2, "test")):
+        d = ol.read_csr_dump(os.path.join(dump, f"{name}.csr.bin"))
+        ptr, ind, val = od.csr(which)
+        cptr, cind, cval = od.csc(which)
+        assert np.array_equal(ptr, d["rowptr"]) and np.array_equal(ind, d["rowind"]) and np.array_equal(val, d["rowval"])
+        assert np.array_equal(cptr, d["colptr"]) and np.array_equal(cind, d["colind"]) and np.array_equal(cval, d["colval"])
+
+
+def test_text_reader_handles_empty_rows_and_parallel_split(tmp_path):
+    """Empty lines are empty rows; the multi-threaded parse must agree with the serial one."""
+    rng = np.random.default_rng(0)
+    n_users, n_items = 8000, 300
+    lines, nnz = [], 0
+    for u in range(n_users):
+        k = 0 if u % 7 == 3 else int(rng.integers(1, 60))
+        items = np.sort(rng.choice(n_items, size=k, replace=False))
+        lines.append(" ".join(f"{i} {rng.integers(1, 11) / 2:g}" for i in items))
+        nnz += k
+    path = str(tmp_path / "big.csr")
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    assert os.path.getsize(path) > (1 << 20)  # large enough for the parallel path
+    files = [path, path, path]
+    for threads in (1, 5):
+        dump = str(tmp_path / f"dry{threads}")
+        run_mf(files, dump, threads=threads, facdim=2, dry_run=1)
+        d = ol.read_csr_dump(os.path.join(dump, "train.csr.bin"))
+        od = ol.OracleData(files=files)
+        ptr, ind, val = od.csr(0)
+        assert d["nrows"] == n_users and int(d["rowptr"][-1]) == nnz
+        assert np.array_equal(ptr, d["rowptr"]) and np.array_equal(ind, d["rowind"]) and np.array_equal(val, d["rowval"])
+
+
+def test_missing_flags_exit_like_the_reference(tmp_path):
+    p = subprocess.run([MF, "--trainmat", "x"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 255 and b"Missing either train, test or val matrix" in p.stderr  # exit(-1), main.cpp:53-58
+
+
+def test_host_library_exports_c_entry_points():
+    lib = C.CDLL(HOST_SO)
+    assert hasattr(lib, "mfh_train") and hasattr(lib, "mfh_release_device")
+
+
+# ---------------------------------------------------------------------------------------------
+BASE = dict(facdim=8, maxiter=6, seed=3, ureg=0.05, ireg=0.05, learnrate=0.005)
+
+
+def oracle_run(files, algo, method, threads, fl):
+    od = ol.OracleData(files=files)
+    m = ol.OracleModel(od, algo=algo, facdim=fl["facdim"], maxiter=fl["maxiter"], seed=fl["seed"], nthreads=threads,
+                       ureg=fl["ureg"], ireg=fl["ireg"], learnrate=fl["learnrate"], rhorms=fl.get("rhorms", 0.0),
+                       alpha=fl.get("alpha", 0.0))
+    m.train(method)
+    return m
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,extra", [("als", dict(ureg=0.1, ireg=0.1)), ("ccd++", {}), ("ccdpp_plain", {})])
+def test_cli_als_and_ccdpp_match_oracle(tmp_path, method, extra):
+    """Deterministic trainers through the whole stack: best and last factors within 1e-4."""
+    files = synth.write_split_files(str(tmp_path), *synth.make_splits(500, 300, 40000, seed=13))
+    fl = dict(BASE); fl.update(extra); fl["maxiter"] = 4
+    dump = str(tmp_path / "gpu")
+    out = run_mf(files, dump, threads=2, algo="mf", mf_method=method, **fl)
+    m = oracle_run(files, "mf", method, 2, fl)
+    U, V = m.factors(); bU, bV = m.factors(best=True)
+    for name, want in (("last_uFac", U), ("last_iFac", V), ("best_uFac", bU), ("best_iFac", bV)):
+        got = ol.read_mat(os.path.join(dump, name + ".bin"))
+        assert rel_err(got, want) < 1e-4, (name, rel_err(got, want))
+    res = dict(line.split(None, 1) for line in open(os.path.join(dump, "result.txt")))
+    assert abs(float(res["best_val_rmse"]) - m.rmse(1, best=True)) < 1e-4 * m.rmse(1, best=True)
+    assert abs(float(res["last_objective"]) - m.objective()) < 1e-4 * m.objective()
+    # factor files: the reference's names and text format (model.cpp:89-101, io.cpp:139-154)
+    sig = res["signature"].strip()
+    assert sig == f"{m.data.n_users}X{m.data.n_items}_8_{fl['ureg']:.6f}_{fl['ireg']:.6f}_{fl['learnrate']:.6f}"
+    ufile = os.path.join(dump, f"gpu_uFac_{sig}.mat")
+    assert os.path.exists(ufile) and os.path.exists(os.path.join(dump, f"gpu_iFac_{sig}.mat"))
+    rows = open(ufile).read().split("\n")
+    assert len(rows) == m.data.n_users + 1 and rows[0].endswith(" ") and len(rows[0].split()) == 8
+    assert np.allclose(np.loadtxt(ufile), ol.read_mat(os.path.join(dump, "best_uFac.bin")), rtol=2e-5, atol=1e-7)
+    assert "Best model validation RMSE" in out and "Validation RMSE:" in out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("algo,method,threads,extra", [
+    ("mf", "sgd", 1, {}), ("mf", "hogsgd", 1, {}), ("mf", "sgdpar", 4, {}), ("IFWMF", "sgd", 1, dict(rhorms=100.0)),
+    ("IFWMF", "sgdpar", 4, dict(rhorms=100.0)), ("TMF", "sgd", 4, dict(rhorms=20.0, alpha=0.5)),
+    ("TMFDropout", "sgd", 4, dict(rhorms=20.0, alpha=0.5))])
+def test_cli_sgd_trainers_converge_to_the_oracle_rmse(tmp_path, algo, method, threads, extra):
+    """SGD trainers through the whole stack: test/validation RMSE of the best model within 0.5 %
+    of the oracle's after the same number of epochs (north_star)."""
+    files = synth.write_split_files(str(tmp_path), *synth.make_splits(3000, 1500, 300000, seed=21))
+    fl = dict(BASE); fl.update(extra); fl.update(facdim=10, maxiter=40)
+    dump = str(tmp_path / "gpu")
+    run_mf(files, dump, threads=threads, algo=algo, mf_method=method, **fl)
+    m = oracle_run(files, algo, method, threads, fl)
+    res = dict(line.split(None, 1) for line in open(os.path.join(dump, "result.txt")))
+    for key, want in (("best_val_rmse", m.rmse(1, best=True)), ("best_test_rmse", m.rmse(2, best=True))):
+        got = float(res[key])
+        assert abs(got - want) <= 0.005 * want, (key, got, want)
+    assert abs(float(res["learn_rate"]) - m.learn_rate) < 1e-9
+
+
+@pytest.mark.gpu
+def test_c_entry_point_trains_from_memory():
+    class Csr(C.Structure):
+        _fields_ = [("nrows", C.c_int32), ("rowptr", C.c_void_p), ("rowind", C.c_void_p), ("rowval", C.c_void_p)]
+
+    class Problem(C.Structure):
+        _fields_ = [("train", Csr), ("val", Csr), ("test", Csr), ("algo", C.c_char_p), ("mf_method", C.c_char_p),
+                    ("facdim", C.c_int32), ("maxiter", C.c_int32), ("seed", C.c_int32), ("num_parts", C.c_int32),
+                    ("ureg", C.c_float), ("ireg", C.c_float), ("learnrate", C.c_float), ("rhorms", C.c_float),
+                    ("alpha", C.c_float), ("init_U", C.c_void_p), ("init_V", C.c_void_p), ("prefix", C.c_char_p)]
+
+    class Result(C.Structure):
+        _fields_ = [("n_users", C.c_int32), ("n_items", C.c_int32), ("learn_rate", C.c_float),
+                    ("best_val_rmse", C.c_double), ("best_test_rmse", C.c_double), ("last_val_rmse", C.c_double),
+                    ("last_objective", C.c_double), ("last_U", C.c_void_p), ("last_V", C.c_void_p),
+                    ("best_U", C.c_void_p), ("best_V", C.c_void_p)]
+
+    lib = C.CDLL(HOST_SO)
+    lib.mfh_train.argtypes = [C.POINTER(Problem), C.POINTER(Result)]
+    splits = synth.make_splits(500, 300, 40000, seed=13)
+    keep = []
+
+    def csr(m):
+        a = [np.ascontiguousarray(m.rowptr, np.int64), np.ascontiguousarray(m.rowind, np.int32),
+             np.ascontiguousarray(m.rowval, np.float32)]
+        keep.extend(a)
+        return Csr(m.nrows, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data)
+
+    p = Problem(csr(splits[0]), csr(splits[1]), csr(splits[2]), b"mf", b"als", 8, 3, 3, 0, 0.1, 0.1, 0.005, 0.0, 0.0,
+                None, None, b"/tmp/mfh_test")
+    od = ol.OracleData(*splits)
+    bU = np.zeros((od.n_users, 8), np.float32); bV = np.zeros((od.n_items, 8), np.float32)
+    r = Result()
+    r.best_U, r.best_V = bU.ctypes.data, bV.ctypes.data
+    assert lib.mfh_train(C.byref(p), C.byref(r)) == 0
+    m = ol.OracleModel(od, algo="mf", facdim=8, maxiter=3, seed=3, nthreads=2, ureg=0.1, ireg=0.1)
+    m.train("als")
+    oU, oV = m.factors(best=True)
+    assert rel_err(bU, oU) < 1e-4 and rel_err(bV, oV) < 1e-4
+    assert abs(r.best_val_rmse - m.rmse(1, best=True)) < 1e-4 * r.best_val_rmse
+    lib.mfh_release_device()
