@@ -5,7 +5,9 @@ Contract (one JSON line on stdout, printed by rank 0):
   python bench.py --gpus N --steps K --warmup W          device arm (this repo's CUDA engine)
   python bench.py --impl reference --gpus N ...          reference arm: the reference's own CPU
                                                          code (oracle/_ref/mf_ref) on host cores
-A "step" is one epoch of the stratified SGD trainer over the whole training matrix.
+A "step" is one SGD epoch over the whole training matrix: at N = 1 the serial-SGD trainer
+(ModelMF::train, the CLI default --mf_method sgd) on the shuffled kernel; at N > 1 the stratified
+trainer (DSGD: user strata pinned to ranks, item blocks exchanged after every sub-epoch).
 
 Workload = BASELINE.json configs[1]: modelMF SGD, rank 64, 480,189 x 17,770, ~100.5 M ratings
 (synthetic, Zipf-skewed positions, ratings from a rank-8 model + noise; random-init factors
@@ -39,7 +41,9 @@ sys.path.insert(0, ROOT)
 
 RANK = 64
 SHAPE = (480_189, 17_770, 100_480_507)
-HP = dict(lr=0.005, ureg=0.05, ireg=0.05)
+# learnrate 0.002: at 0.005 the reference itself diverges on this matrix in epoch 0 and falls back on
+# its NaN guard (restore + halve, model.cpp:1487-1498) — measured with the oracle, see DESIGN.md
+HP = dict(lr=0.002, ureg=0.05, ireg=0.05)
 FALLBACK_HBM_GBS = 6650.0
 
 
@@ -335,6 +339,7 @@ def main():
         eng.upload_factors(U0, V0)
         up_local = np.where(mine, user_part, -1).astype(np.int32)
         eng.sgd_plan(P, up_local, item_part)
+        eng.set_option("sgd_block_order", 1)  # shuffled inside the blocks: full concurrency
         sched_blocks = [np.array([[rank, (rank + s) % P]], np.int32) for s in range(P)]
         my_nnz_per_epoch = int(lptr[-1])
         item_ids = [np.nonzero(item_part == b)[0].astype(np.int32) for b in range(P)]
@@ -345,7 +350,7 @@ def main():
 
     def epoch(ep):
         if world == 1:
-            eng.sgd_subepoch(sched_blocks[0], E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, ep)
+            eng.sgd_epoch_flat(E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, ep)
             return
         for s in range(P):
             eng.sgd_subepoch(sched_blocks[s], E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, ep * P + s)
@@ -409,9 +414,31 @@ def main():
     achieved = alg_bytes / (1 if world == 1 else P) / (kern_ms * 1e-3) / 1e9 if world == 1 else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                "kernel": "sgd_update_kernel<16,1,MF>", "algorithmic_bytes_per_update": 16 * RANK + 12,
-                "note": "achieved counts algorithmic bytes; u stays in registers over a user's run and V is L2 resident, "
-                        "so DRAM traffic is far below it (see profiles/)"}
+                "kernel": "sgd_flat_kernel<16,1,MF>", "algorithmic_bytes_per_update": 16 * RANK + 12,
+                "note": "achieved counts algorithmic bytes (u,v read + reduced, 12 B rating record); V (4.5 MB) and part of "
+                        "U (123 MB) are L2 resident, so DRAM traffic is below it (see profiles/)"}
+
+    # the stratified trainer's kernel (user-major runs, concurrency capped for parity) for the record
+    stratified = None
+    if world == 1:
+        try:
+            P = 8
+            prng = np.random.default_rng(7)
+            eng.sgd_plan(P, prng.integers(0, P, n_users).astype(np.int32), prng.integers(0, P, n_items).astype(np.int32))
+            blocks = [np.stack([np.arange(P), (np.arange(P) + s) % P], 1).astype(np.int32) for s in range(P)]
+            for b in blocks:
+                eng.sgd_subepoch(b, E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, 0)
+            eng.event_record(2)
+            for ep in range(3):
+                for b in blocks:
+                    eng.sgd_subepoch(b, E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, ep + 1)
+            eng.event_record(3)
+            ms_s = eng.event_elapsed_ms(2, 3) / 3
+            stratified = {"P": P, "ms_per_epoch": ms_s, "value": train_nnz / (ms_s * 1e-3), "unit": "rating-updates/s",
+                          "what": "trainSGDPar kernel: user-major runs, hot-item concurrency capped at 8 (parity with the reference's order)"}
+            eng.sgd_plan(1)
+        except Exception as ex:
+            stratified = {"error": repr(ex)[:200]}
 
     # end-to-end through the C ABI with host buffers
     e2e = None
@@ -433,7 +460,7 @@ def main():
             eng.upload_csr(E.TRAIN, trp, with_csc=False)
             eng.upload_factors(h["U"], h["V"])
             eng.sgd_plan(1)
-            eng.sgd_subepoch(sched_blocks[0], E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, s)
+            eng.sgd_epoch_flat(E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, s)
             obj = eng.eval(E.TRAIN, E.CURRENT, E.MF, False, True)
             vr = eng.eval(E.VAL)
             eng.L.mfb_download_factors(eng.h, E.CURRENT, Uo.ctypes.data, RANK, Vo.ctypes.data, RANK)
@@ -460,6 +487,8 @@ def main():
         line["e2e"] = e2e
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
+    if stratified:
+        line["stratified"] = stratified
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

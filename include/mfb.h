@@ -123,7 +123,11 @@ int mfb_sgd_epoch_flat(mfb_engine *e, int variant, float learn_rate, float ureg,
                        uint64_t counter);
 /* Tuning knobs: "sgd_workers" (concurrent sub-warps, 0 = automatic), "sgd_warps_per_sm",
  * "sgd_max_hot_inflight" (bound on concurrent updates of the hottest item row, default 8),
- * "sgd_atomic" (1 = item rows updated by reductions, 0 = plain stores), "sgd_rotate" (1 = every
+ * "sgd_flat_hot_lr" (shuffled kernel: the hottest row's concurrency is capped at value / learn_rate,
+ * default 0.15), "sgd_flat_inflight_frac" (shuffled kernel: ratings in flight <= this fraction of
+ * the epoch, default 2e-4), "als_tensor_cores" (rank > 64: 1 = tcgen05 3xTF32 Gram, 0 = fp32 CUDA-core
+ * Gram), "sgd_block_order" (stratified trainers: 0 = user-major runs, 1 = shuffled inside the
+ * blocks), "sgd_atomic" (1 = item rows updated by reductions, 0 = plain stores), "sgd_rotate" (1 = every
  * user run of the stratified kernel starts at a pseudo-random offset and wraps around, 0 = CSR
  * order as in modelMF.cpp:280). */
 int mfb_set_option(mfb_engine *e, const char *name, double value);

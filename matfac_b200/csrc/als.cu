@@ -58,9 +58,8 @@ struct AlsSmem {
 
 // Cholesky of the register-tiled matrix (lower triangle meaningful), L written to shared
 // memory, then L L^T x = b solved by warp 0; x left in sm_b.
-template <int TR>
+template <int TR, class S>
 __device__ __forceinline__ void chol_solve(float (&acc)[TR][TR], float *sm, int tx, int ty) {
-  using S = AlsSmem<TR>;
   constexpr int RP = S::RP, LDL = S::LDL;
   float *Lm = sm + S::off_L, *colbuf = sm + S::off_col, *bv = sm + S::off_b;
   const int tid = ty * 16 + tx;
@@ -255,7 +254,7 @@ __global__ void __launch_bounds__(256, (TR == 8 ? 2 : 3)) als_gram_solve_kernel(
     for (int i = 0; i < TR; i++) bv[tile_idx<TR>(tx, i)] = bacc[i];
   }
   add_reg_diag<TR>(acc, tx, ty, a.rank, a.reg);
-  chol_solve<TR>(acc, sm, tx, ty);
+  chol_solve<TR, AlsSmem<TR>>(acc, sm, tx, ty);
   if (tid < a.ld) a.Fout[(size_t)row * a.ld + tid] = tid < a.rank ? bv[tid] : 0.f;
 }
 
@@ -276,7 +275,241 @@ __global__ void __launch_bounds__(256, (TR == 8 ? 2 : 3)) als_solve_ws_kernel(co
     for (int j = 0; j < TR; j++) acc[i][j] = w[tile_idx<TR>(ty, i) * RP + tile_idx<TR>(tx, j)];
   if (tid < RP) bv[tid] = w[RP * RP + tid];
   add_reg_diag<TR>(acc, tx, ty, a.rank, a.reg);
-  chol_solve<TR>(acc, sm, tx, ty);
+  chol_solve<TR, AlsSmem<TR>>(acc, sm, tx, ty);
+  if (tid < a.ld) a.Fout[(size_t)row * a.ld + tid] = tid < a.rank ? bv[tid] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-core Gram for rank 65..128 (padded to 128): tcgen05.mma kind::tf32, fp32 accumulator in
+// TMEM, 3xTF32 split so that the result keeps fp32-level accuracy (the 1e-4 parity bar of the
+// reference's fp32 ALS cannot be met by a single tf32 product: 10-bit mantissa).
+//
+//   G = sum_k f_k f_k^T over the gathered factor rows f_k = Fin[ind[k]]   (K = ratings)
+//   D[128 x 128] += A[128 x 8] * B[8 x 128] per instruction, A(m,k) = B(n,k)^T = f_k[m]:
+//   both operands are the SAME shared-memory tile, stored one rating per 512-byte row, i.e.
+//   "MN-major" for A and for B, in the canonical 128-byte-swizzled layout
+//   ((4,8,m),(8,k)) : ((1,4,LBO),(32,SBO)) of four 32-float column chunks.
+//   f = big + small with big = f truncated to tf32 (exact in tf32), small = f - big (exact in
+//   fp32); G ~= big big^T + big small^T + small big^T (the dropped term is 2^-22 relative).
+//
+// 256 threads: all of them gather / split / store the tiles (and accumulate the right-hand side
+// b = sum r f on CUDA cores), thread 0 issues the MMAs; tcgen05.commit on an mbarrier frees a
+// stage for the next gather, so tile t+1 is loaded while tile t multiplies.  The epilogue pulls
+// the accumulator out of TMEM (tcgen05.ld 32x32b), and the Cholesky solve runs as in the CUDA-core
+// kernel.
+constexpr int kTcKT = 32;       // ratings per stage
+constexpr int kTcStages = 2;
+constexpr uint32_t kTcPartBytes = kTcKT * 512;  // one (stage, big|small) tile: 32 rows x 128 floats
+
+struct AlsTcSmem {
+  static constexpr int RP = 128;
+  static constexpr int LDL = RP + 1;
+  // byte layout; the tile region is reused for the L matrix once the MMAs are done
+  static constexpr uint32_t tiles_bytes = kTcStages * 2 * kTcPartBytes;  // 65536
+  static constexpr uint32_t L_bytes = RP * LDL * 4;                       // 66048
+  static constexpr uint32_t region0 = 66560;                              // max of both, 1024-aligned
+  static constexpr int off_tile = 0;
+  static constexpr int off_L = 0;
+  static constexpr int off_col = region0 / 4;
+  static constexpr int off_b = off_col + 2 * RP;
+  static constexpr int off_bred = off_b + RP;            // [8][RP] partial right-hand sides
+  static constexpr int off_misc = off_bred + 8 * RP;     // mbarriers (3 x 8 B), tmem address
+  static constexpr size_t bytes = sizeof(float) * (off_misc + 16) + 1024;  // + slack for 1024-byte alignment
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+// SM100 shared-memory matrix descriptor: start address, leading / stride byte offsets (all >> 4),
+// descriptor version 1, 128-byte swizzle
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // version
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2) als_gram_tc_kernel(const AlsArgs a) {
+  using S = AlsTcSmem;
+  constexpr int RP = S::RP, TR = 8;
+  extern __shared__ uint8_t sm_raw[];
+  // 128-byte swizzle needs the tiles on a 1024-byte boundary
+  uint8_t *smb = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~(uintptr_t)1023);
+  float *sm = reinterpret_cast<float *>(smb);
+  float *bv = sm + S::off_b, *bred = sm + S::off_bred;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sm + S::off_misc);  // [0..1] stage free, [2] all done
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int seg = blockIdx.x;
+  const int row = a.seg_row[seg], start = a.seg_start[seg], len = a.seg_len[seg], slot = a.seg_slot[seg];
+  const int nq = a.ld >> 2;  // 16-byte units per factor row (<= 32)
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_init(smem_u32(&bars[2]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+
+  // instruction descriptor: D = F32, A = B = TF32, both MN-major, N = 128, M = 128
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t tiles = smem_u32(smb);
+  const int ntiles = (len + kTcKT - 1) / kTcKT;
+  const int q = lane;        // 16-byte unit of the factor row handled by this thread
+  float4 bacc = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t phase[kTcStages] = {0, 0};
+
+  for (int t = 0; t < ntiles; t++) {
+    const int s = t & 1;
+    if (t >= kTcStages) {  // the MMAs that read this stage two tiles ago must have finished
+      mbar_wait(smem_u32(&bars[s]), phase[s]);
+      phase[s] ^= 1;
+    }
+    const uint32_t big0 = tiles + (uint32_t)(s * 2) * kTcPartBytes, small0 = big0 + kTcPartBytes;
+    // gather 4 rows per thread (warp w handles rows w, w+8, w+16, w+24 of the tile)
+    float4 f[4];
+    float rt[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int k = warp + 8 * i, j = t * kTcKT + k;
+      f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rt[i] = 0.f;
+      if (j < len) {
+        const int it = __ldg(a.ind + start + j);
+        const float r = __ldg(a.val + start + j);
+        if (r > 0.f) {  // modelMF.cpp:819
+          rt[i] = r;
+          if (q < nq) f[i] = __ldg(reinterpret_cast<const float4 *>(a.Fin + (size_t)it * a.ld) + q);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int k = warp + 8 * i;
+      float4 bg, sl4;
+      bg.x = __uint_as_float(__float_as_uint(f[i].x) & 0xFFFFE000u);
+      bg.y = __uint_as_float(__float_as_uint(f[i].y) & 0xFFFFE000u);
+      bg.z = __uint_as_float(__float_as_uint(f[i].z) & 0xFFFFE000u);
+      bg.w = __uint_as_float(__float_as_uint(f[i].w) & 0xFFFFE000u);
+      sl4 = make_float4(f[i].x - bg.x, f[i].y - bg.y, f[i].z - bg.z, f[i].w - bg.w);
+      // chunk c = q / 8 (32 floats), unit w = q % 8, swizzled with the row inside the 8-row atom
+      const uint32_t off = (uint32_t)(q >> 3) * (kTcKT * 128) + (uint32_t)k * 128 + (uint32_t)(((q & 7) ^ (k & 7)) << 4);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(big0 + off), "f"(bg.x), "f"(bg.y), "f"(bg.z), "f"(bg.w) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(small0 + off), "f"(sl4.x), "f"(sl4.y), "f"(sl4.z), "f"(sl4.w) : "memory");
+      bacc.x = fmaf(rt[i], f[i].x, bacc.x);
+      bacc.y = fmaf(rt[i], f[i].y, bacc.y);
+      bacc.z = fmaf(rt[i], f[i].z, bacc.z);
+      bacc.w = fmaf(rt[i], f[i].w, bacc.w);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the tensor core
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int g = 0; g < kTcKT / 8; g++) {
+        const uint64_t db = umma_desc_sw128(big0 + g * 1024, kTcKT * 128, 1024);
+        const uint64_t ds = umma_desc_sw128(small0 + g * 1024, kTcKT * 128, 1024);
+        umma_tf32(tmem_d, db, db, idesc, (t > 0 || g > 0) ? 1u : 0u);
+        umma_tf32(tmem_d, db, ds, idesc, 1u);
+        umma_tf32(tmem_d, ds, db, idesc, 1u);
+      }
+      umma_commit(smem_u32(&bars[s]));
+      if (t == ntiles - 1) umma_commit(smem_u32(&bars[2]));
+    }
+  }
+  // right-hand side: reduce the 8 row slots
+  *reinterpret_cast<float4 *>(bred + warp * RP + q * 4) = bacc;
+  mbar_wait(smem_u32(&bars[2]), 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  __syncthreads();  // every thread is past the MMAs: the tile region may be overwritten
+  if (tid < RP) {
+    float sacc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) sacc += bred[w * RP + tid];
+    bv[tid] = sacc;
+  }
+  // accumulator: TMEM lane = Gram row, column = Gram column; warps 0..3 own lanes 32w..32w+31
+  float *Lm = sm + S::off_L;
+  if (warp < 4) {
+    const int grow = warp * 32 + lane;
+#pragma unroll
+    for (int c0 = 0; c0 < RP; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int c = 0; c < 32; c++) Lm[grow * S::LDL + c0 + c] = __uint_as_float(v[c]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_d) : "memory");
+
+  float acc[TR][TR];
+#pragma unroll
+  for (int i = 0; i < TR; i++)
+#pragma unroll
+    for (int j = 0; j < TR; j++) acc[i][j] = Lm[tile_idx<TR>(ty, i) * S::LDL + tile_idx<TR>(tx, j)];
+  if (slot >= 0) {
+    float *w = a.ws + (size_t)slot * (RP * RP + RP);
+#pragma unroll
+    for (int i = 0; i < TR; i++)
+#pragma unroll
+      for (int j = 0; j < TR; j++) atomicAdd(w + tile_idx<TR>(ty, i) * RP + tile_idx<TR>(tx, j), acc[i][j]);
+    if (tid < RP) atomicAdd(w + RP * RP + tid, bv[tid]);
+    return;
+  }
+  __syncthreads();  // everyone holds its tile: L may now be overwritten by the factorisation
+  add_reg_diag<TR>(acc, tx, ty, a.rank, a.reg);
+  chol_solve<TR, S>(acc, sm, tx, ty);
   if (tid < a.ld) a.Fout[(size_t)row * a.ld + tid] = tid < a.rank ? bv[tid] : 0.f;
 }
 
@@ -298,7 +531,12 @@ static int launch_als(mfb_engine *e, const AlsArgs &a, const SegPlan &sp) {
   }
   AlsArgs b = a;
   b.ws = e->als_ws;
-  if (sp.n_seg > 0) MFB_LAUNCH((als_gram_solve_kernel<TR>), sp.n_seg, 256, S::bytes, e->stream, b);
+  if (TR == 8 && e->opt_als_tensor_cores) {
+    MFB_CUDA(cudaFuncSetAttribute(als_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AlsTcSmem::bytes));
+    if (sp.n_seg > 0) MFB_LAUNCH(als_gram_tc_kernel, sp.n_seg, 256, AlsTcSmem::bytes, e->stream, b);
+  } else if (sp.n_seg > 0) {
+    MFB_LAUNCH((als_gram_solve_kernel<TR>), sp.n_seg, 256, S::bytes, e->stream, b);
+  }
   if (sp.n_multi > 0) MFB_LAUNCH((als_solve_ws_kernel<TR>), sp.n_multi, 256, S::bytes, e->stream, b);
   return 0;
 }

@@ -440,8 +440,11 @@ extern "C" int mfb_set_option(mfb_engine *e, const char *name, double value) {
   if (n == "sgd_workers") e->opt_sgd_workers = (int)value;
   else if (n == "sgd_warps_per_sm") e->opt_sgd_warps_per_sm = (int)value;
   else if (n == "sgd_max_hot_inflight") e->opt_sgd_max_hot_inflight = value;
+  else if (n == "sgd_flat_hot_lr") e->opt_sgd_flat_hot_lr = value;
+  else if (n == "sgd_flat_inflight_frac") e->opt_sgd_flat_inflight_frac = value;
   else if (n == "sgd_atomic") e->opt_sgd_atomic = (int)value;
   else if (n == "sgd_rotate") e->opt_sgd_rotate = (int)value;
+  else if (n == "als_tensor_cores") e->opt_als_tensor_cores = (int)value;
   else if (n == "sgd_block_order") e->opt_sgd_block_order = (int)value;
   else return mfb::fail("mfb_set_option: unknown option", __FILE__, __LINE__);
   return 0;

@@ -90,6 +90,7 @@ struct SgdPlan {
   int32_t *rat_user = nullptr;   // user of every rating (flat kernel; P == 1 plans only)
   int *work_counter = nullptr;   // device work-queue head of the persistent kernel
   double hot_item_share = 0.0;   // largest item count / nnz: bounds useful concurrency
+  double collision_mass = 0.0;   // sum over items of (count / nnz)^2: P(two random ratings share an item)
   std::vector<int32_t> blk_seg_off, blk_seg_cnt;  // [P*P]
   std::vector<int64_t> blk_nnz;                   // [P*P]
   std::vector<int64_t> blk_rat_off;               // [P*P] first rating of every block
@@ -108,9 +109,12 @@ struct mfb_engine {
   int opt_sgd_workers = 0;            // 0 = automatic
   int opt_sgd_warps_per_sm = 32;      // automatic mode: persistent warps per SM
   double opt_sgd_max_hot_inflight = 8.0;  // bound on concurrent updates of the hottest item row
+  double opt_sgd_flat_hot_lr = 0.15;  // shuffled kernel: cap on (hot-row concurrency x learning rate)
+  double opt_sgd_flat_inflight_frac = 2e-4;  // shuffled kernel: ratings in flight <= this fraction of the epoch
   int opt_sgd_atomic = 1;             // item rows updated by vector reductions (no lost updates)
   int opt_sgd_block_order = 0;        // stratified trainers: 0 = user-major runs (reference order), 1 = shuffled inside the blocks
-  int opt_sgd_rotate = 1;             // user runs start at a pseudo-random offset (de-correlates heavy users)
+  int opt_sgd_rotate = 0;             // user runs start at a pseudo-random offset (de-correlates heavy users)
+  int opt_als_tensor_cores = 1;       // rank > 64: Gram on tcgen05 (3xTF32); 0 = fp32 CUDA-core Gram
   cudaStream_t stream = nullptr;
   cudaEvent_t events[16] = {};
 

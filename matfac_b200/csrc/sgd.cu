@@ -99,6 +99,11 @@ __global__ void item_hist_kernel(const int32_t *__restrict__ ind, int64_t n, int
   if (j < n) atomicAdd(hist + ind[j], 1);
 }
 
+__global__ void sq_count_kernel(const int32_t *__restrict__ hist, int32_t n, double *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (double)hist[i] * (double)hist[i];
+}
+
 __global__ void rat_user_kernel(const int64_t *__restrict__ rowptr, int32_t nrows, int64_t nnz, int32_t *__restrict__ out) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nnz) return;
@@ -129,9 +134,19 @@ static int sgd_plan_common(mfb_engine *e) {
     MFB_CUDA(cub::DeviceReduce::Max(e->scratch, tmp_bytes, hist, d_max, e->n_items, st));
     int32_t mx = 0;
     MFB_CUDA(cudaMemcpyAsync(&mx, d_max, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    double *sq, *d_sum, sum = 0;
+    MFB_CUDA(cudaMalloc(&sq, sizeof(double) * ((size_t)e->n_items + 1)));
+    d_sum = sq + e->n_items;
+    MFB_LAUNCH(sq_count_kernel, (e->n_items + 255) / 256, 256, 0, st, hist, e->n_items, sq);
+    MFB_CUDA(cub::DeviceReduce::Sum(nullptr, tmp_bytes, sq, d_sum, e->n_items, st));
+    MFB_TRY(ensure_scratch(e, tmp_bytes));
+    MFB_CUDA(cub::DeviceReduce::Sum(e->scratch, tmp_bytes, sq, d_sum, e->n_items, st));
+    MFB_CUDA(cudaMemcpyAsync(&sum, d_sum, sizeof(double), cudaMemcpyDeviceToHost, st));
     MFB_CUDA(cudaStreamSynchronize(st));
     cudaFree(hist);
+    cudaFree(sq);
     pl.hot_item_share = (double)mx / (double)m.nnz;
+    pl.collision_mass = sum / ((double)m.nnz * (double)m.nnz);
   }
   return 0;
 }
@@ -297,9 +312,12 @@ struct SgdArgs {
   const Aux *aux_u, *aux_i;
   const float *cdf;
   uint64_t seed, counter_id;
-  // shuffled kernel: visiting order p(t) = (mul * t + add) mod n over the concatenated rating
-  // ranges of the scheduled blocks (range b starts at rat_off[b], cumulative sizes in rat_cum)
-  int64_t n, mul, add;
+  // shuffled kernel: visiting order p(t) = a keyed pseudo-random permutation of [0, n) over the
+  // concatenated rating ranges of the scheduled blocks (range b starts at rat_off[b], cumulative
+  // sizes in rat_cum).  The permutation is a 3-round multiply / xor-shift bijection on the next
+  // power of two with cycle walking.
+  int64_t n;
+  uint32_t perm_bits, perm_mul[3], perm_add[3];
   int32_t rat_off[kMaxBlocks];
   int32_t rat_cum[kMaxBlocks + 1];
 };
@@ -510,6 +528,21 @@ __global__ void __launch_bounds__(128) sgd_run_kernel(const SgdArgs a) {
   }
 }
 
+// Keyed bijection of [0, n): each round (odd multiply + add, xor-shift right) is a bijection of the
+// perm_bits-bit integers; values >= n are walked through again (at most ~2 rounds on average).
+__device__ __forceinline__ uint32_t permute_index(const SgdArgs &a, uint32_t x) {
+  const uint32_t mask = a.perm_bits >= 32 ? 0xFFFFFFFFu : ((1u << a.perm_bits) - 1u);
+  const uint32_t sh = (a.perm_bits + 1) / 2;
+  do {
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      x = (x * a.perm_mul[r] + a.perm_add[r]) & mask;
+      x ^= x >> sh;
+    }
+  } while (x >= (uint32_t)a.n);
+  return x;
+}
+
 // Serial / Hogwild trainers (modelMF.cpp:83-105, :1747-1763): every sub-warp owns one rating at
 // a time, visited in a pseudo-random order; both rows are read with 128-bit loads and updated
 // with vector reductions.
@@ -526,16 +559,12 @@ __global__ void __launch_bounds__(128) sgd_flat_kernel(const SgdArgs a) {
   bool own[VPL];
 #pragma unroll
   for (int c = 0; c < VPL; c++) own[c] = (c * G + sl) < a.nq;
-  for (int64_t t0 = warp_first; t0 < a.n; t0 += n_groups) {  // warp-uniform trip count
-    const int64_t t = t0 + (lane / G);
-    const bool on = t < a.n;
-    int user = 0, it = 0, pay = 0;
-    float rt = 0.f;
-    float4 u[VPL], v[VPL];
-#pragma unroll
-    for (int c = 0; c < VPL; c++) u[c] = v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (on) {
-      int64_t p = (a.mul * t + a.add) % a.n;
+  // the (user, item, rating) record of the next visit is fetched one iteration ahead, so that its
+  // latency is not in front of the two row gathers
+  auto fetch_record = [&](int64_t t, int64_t &p, int &user, int &it, float &rt) {
+    p = 0; user = 0; it = 0; rt = 0.f;
+    if (t < a.n) {
+      p = permute_index(a, (uint32_t)t);
       if (a.nb > 1) {  // which scheduled block does p fall in
         int b = 0;
         while (b + 1 < a.nb && p >= a.rat_cum[b + 1]) b++;
@@ -546,6 +575,24 @@ __global__ void __launch_bounds__(128) sgd_flat_kernel(const SgdArgs a) {
       user = __ldg(a.rat_user + p);
       it = __ldg(a.item + p);
       rt = __ldg(a.val + p);
+    }
+  };
+  int64_t n_p;
+  int n_user, n_it;
+  float n_rt;
+  fetch_record(warp_first + (lane / G), n_p, n_user, n_it, n_rt);
+  for (int64_t t0 = warp_first; t0 < a.n; t0 += n_groups) {  // warp-uniform trip count
+    const int64_t t = t0 + (lane / G);
+    const bool on = t < a.n;
+    const int64_t p = n_p;
+    const int user = n_user, it = n_it;
+    const float rt = n_rt;
+    fetch_record(t + n_groups, n_p, n_user, n_it, n_rt);
+    int pay = 0;
+    float4 u[VPL], v[VPL];
+#pragma unroll
+    for (int c = 0; c < VPL; c++) u[c] = v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on) {
 #pragma unroll
       for (int c = 0; c < VPL; c++)
         if (own[c]) {
@@ -647,7 +694,9 @@ static void fill_common(mfb_engine *e, SgdArgs &a, float lr, float ureg, float i
   a.aux_u = e->aux_u; a.aux_i = e->aux_i; a.cdf = e->poisson_cdf;
   a.seed = seed; a.counter_id = counter;
   a.counter = e->sgd.work_counter;
-  a.n = pl.nnz; a.mul = 1; a.add = 0;
+  a.n = pl.nnz;
+  a.perm_bits = 1;
+  for (int r = 0; r < 3; r++) { a.perm_mul[r] = 1; a.perm_add[r] = 0; }
   a.rotate = e->opt_sgd_rotate;
 }
 
@@ -681,11 +730,6 @@ int sgd_subepoch_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int va
 #undef MFB_PICK
 }
 
-static int64_t gcd64(int64_t a, int64_t b) {
-  while (b) { int64_t t = a % b; a = b; b = t; }
-  return a;
-}
-
 int sgd_flat_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int variant, float lr, float ureg, float ireg,
                     uint64_t seed, uint64_t counter) {
   const SgdPlan &pl = e->sgd;
@@ -700,20 +744,34 @@ int sgd_flat_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int varian
   }
   a.n = a.rat_cum[nb];
   if (a.n == 0) return 0;
-  // a fresh affine bijection of [0, n) per epoch: p(t) = (mul t + add) mod n, gcd(mul, n) = 1
-  uint64_t h = seed * 0x9E3779B97F4A7C15ull + counter * 0xD1B54A32D192ED03ull + 0x2545F4914F6CDD1Dull;
-  h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+  // a fresh keyed permutation of [0, n) per (seed, epoch): the reference reshuffles every epoch
   const int64_t n = a.n;
-  int64_t mul = (int64_t)(h % (uint64_t)n) | 1;
-  if (n > 16) mul = mul % (n / 2) + n / 4;  // a stride of the order of n, far beyond any row length
-  while (gcd64(mul, n) != 1) mul++;
-  a.mul = mul % n;
-  if (a.mul == 0) a.mul = 1;
-  a.add = (int64_t)((h >> 20) % (uint64_t)n);
+  a.perm_bits = 1;
+  while (((int64_t)1 << a.perm_bits) < n) a.perm_bits++;
+  uint64_t h = seed * 0x9E3779B97F4A7C15ull + counter * 0xD1B54A32D192ED03ull + 0x2545F4914F6CDD1Dull;
+  for (int r = 0; r < 3; r++) {
+    h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+    a.perm_mul[r] = (uint32_t)(h >> 7) | 1u;
+    a.perm_add[r] = (uint32_t)(h >> 33);
+  }
   const int nq = a.nq;
-  // the shuffled kernel reads both rows right before it adds its increments; measured convergence
-  // is independent of the concurrency (profiles/), so it is sized to fill the machine
-#define MFB_PICK(G, VPL) return launch_flat<G, VPL>(e, a, variant, pick_workers(e, G, n, 0.0, 1))
+  // The shuffled kernel reads both rows right before it adds its increments, so concurrency only
+  // turns the updates of a hot row into a mini-batch of c = (ratings in flight) x (the row's share
+  // of the ratings).  That is harmless while c * 2 * lr * |u|^2 stays well below 1 (measured: the
+  // validation curve is identical to four digits from c = 1 to c = 90 at lr = 0.002) and diverges
+  // beyond it, which only tiny matrices can reach; c is capped at sgd_flat_hot_lr / lr.
+  // A second bound keeps the ratings in flight below a fixed fraction of the epoch
+  // (sgd_flat_inflight_frac, default 2e-4): during the first epochs the factors grow exponentially
+  // from their 0.01-scale start, and on a small matrix a few hundred stale updates are a visible
+  // share of that growth (measured: +10 % RMSE after epoch 0 with 0.1 % of a 240 k-rating epoch in
+  // flight, < 0.5 % with 0.02 %).  On the bench matrix this bound is 20 k workers, i.e. inactive.
+  double hot_cap = e->opt_sgd_flat_hot_lr / std::max((double)lr, 1e-12);
+  if (pl.hot_item_share > 0)
+    hot_cap = std::min(hot_cap, std::max(e->opt_sgd_flat_inflight_frac * (double)n, 8.0) * pl.hot_item_share);
+  const double saved_cap = e->opt_sgd_max_hot_inflight;
+  e->opt_sgd_max_hot_inflight = hot_cap;
+  struct Restore { mfb_engine *e; double v; ~Restore() { e->opt_sgd_max_hot_inflight = v; } } restore{e, saved_cap};
+#define MFB_PICK(G, VPL) return launch_flat<G, VPL>(e, a, variant, pick_workers(e, G, n, pl.hot_item_share, 1))
   if (nq <= 2) MFB_PICK(2, 1);
   if (nq <= 4) MFB_PICK(4, 1);
   if (nq <= 8) MFB_PICK(8, 1);
