@@ -139,6 +139,10 @@ int mfb_sgd_block_nnz(mfb_engine *e, const int32_t *blocks, int32_t nb, int64_t 
  * over the train CSR and overwrite U; MFB_ITEM: same over the CSC with the current U. */
 int mfb_als_half_step(mfb_engine *e, int side, float reg);
 
+/* Diagnostics: the Gram matrix and right-hand side of ONE row as the production ALS kernels form
+ * them (no regulariser).  out = [R*R + R] floats with R = *padded_rank (64 or 128; rank > 32 only). */
+int mfb_debug_als_gram(mfb_engine *e, int side, int32_t row, float *out, int32_t *padded_rank);
+
 /* ---- CCD++ (modelMF.cpp:1013-1121 trainCCDPP; :1258-1375 trainCCDPPFreqAdap) ---------------
  * begin: residual := train values (gk_csr_Dup), U := 0 (:1020).  rank1: one pass of the k loop
  * body (:1028-1120): add-back unless first_iter, `inner` alternations of the u_k / v_k

@@ -285,12 +285,17 @@ __global__ void __launch_bounds__(256, (TR == 8 ? 2 : 3)) als_solve_ws_kernel(co
 // reference's fp32 ALS cannot be met by a single tf32 product: 10-bit mantissa).
 //
 //   G = sum_k f_k f_k^T over the gathered factor rows f_k = Fin[ind[k]]   (K = ratings)
-//   D[128 x 128] += A[128 x 8] * B[8 x 128] per instruction, A(m,k) = B(n,k)^T = f_k[m]:
-//   both operands are the SAME shared-memory tile, stored one rating per 512-byte row, i.e.
-//   "MN-major" for A and for B, in the canonical 128-byte-swizzled layout
-//   ((4,8,m),(8,k)) : ((1,4,LBO),(32,SBO)) of four 32-float column chunks.
-//   f = big + small with big = f truncated to tf32 (exact in tf32), small = f - big (exact in
-//   fp32); G ~= big big^T + big small^T + small big^T (the dropped term is 2^-22 relative).
+//   D[128 x 128] += A[128 x 8] * B[8 x 128] per instruction with A(m,k) = B(n,k) = f_k[m]: both
+//   operands are the SAME shared-memory tile.  kind::tf32 only multiplies K-major operands (an
+//   MN-major tile — the layout the gathered rows arrive in — returns zeros, measured with
+//   tools/tc_probe.cu), so the tile is transposed on the way into shared memory: every thread
+//   loads the same 16-byte unit of four consecutive ratings and stores four 16-byte K-vectors.
+//   Layout: no-swizzle K-major core matrices (8 factor dims x 4 ratings = 128 B), core stride along
+//   the factor dim SBO = 144 B (16 B of padding makes the transposing stores conflict free), core
+//   stride along the ratings LBO = 16 * 144 B.
+//   f = big + small with big = f rounded to tf32, small = f - big (exact in fp32) rounded to tf32
+//   (|small| <= 2^-11 |f|, its rounding error <= 2^-22 |f|); G ~= big big^T + big small^T + small big^T
+//   (the dropped small small^T term is 2^-22 relative).
 //
 // 256 threads: all of them gather / split / store the tiles (and accumulate the right-hand side
 // b = sum r f on CUDA cores), thread 0 issues the MMAs; tcgen05.commit on an mbarrier frees a
@@ -299,15 +304,17 @@ __global__ void __launch_bounds__(256, (TR == 8 ? 2 : 3)) als_solve_ws_kernel(co
 // kernel.
 constexpr int kTcKT = 32;       // ratings per stage
 constexpr int kTcStages = 2;
-constexpr uint32_t kTcPartBytes = kTcKT * 512;  // one (stage, big|small) tile: 32 rows x 128 floats
+constexpr uint32_t kTcSbo = 144;                       // bytes between 8-dim core matrices
+constexpr uint32_t kTcLbo = 16 * kTcSbo;               // bytes between 4-rating core matrices
+constexpr uint32_t kTcPartBytes = (kTcKT / 4) * kTcLbo;  // one (stage, big|small) tile: 18432 B
 
 struct AlsTcSmem {
   static constexpr int RP = 128;
   static constexpr int LDL = RP + 1;
   // byte layout; the tile region is reused for the L matrix once the MMAs are done
-  static constexpr uint32_t tiles_bytes = kTcStages * 2 * kTcPartBytes;  // 65536
+  static constexpr uint32_t tiles_bytes = kTcStages * 2 * kTcPartBytes;  // 73728
   static constexpr uint32_t L_bytes = RP * LDL * 4;                       // 66048
-  static constexpr uint32_t region0 = 66560;                              // max of both, 1024-aligned
+  static constexpr uint32_t region0 = tiles_bytes;                        // max of both
   static constexpr int off_tile = 0;
   static constexpr int off_L = 0;
   static constexpr int off_col = region0 / 4;
@@ -335,14 +342,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 // SM100 shared-memory matrix descriptor: start address, leading / stride byte offsets (all >> 4),
-// descriptor version 1, 128-byte swizzle
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// descriptor version 1, no swizzle.  K-major: LBO = stride between core matrices along K,
+// SBO = stride between 8-row core matrices along M/N (verified with tools/tc_probe.cu).
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;  // version
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -354,6 +361,12 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// round-to-nearest fp32 -> tf32 (the tensor core itself truncates the low 13 mantissa bits)
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -362,7 +375,7 @@ __global__ void __launch_bounds__(256, 2) als_gram_tc_kernel(const AlsArgs a) {
   using S = AlsTcSmem;
   constexpr int RP = S::RP, TR = 8;
   extern __shared__ uint8_t sm_raw[];
-  // 128-byte swizzle needs the tiles on a 1024-byte boundary
+  // keep the tiles on a 1024-byte boundary (not required without swizzle, harmless)
   uint8_t *smb = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~(uintptr_t)1023);
   float *sm = reinterpret_cast<float *>(smb);
   float *bv = sm + S::off_b, *bred = sm + S::off_bred;
@@ -389,8 +402,8 @@ __global__ void __launch_bounds__(256, 2) als_gram_tc_kernel(const AlsArgs a) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tmem_slot;
 
-  // instruction descriptor: D = F32, A = B = TF32, both MN-major, N = 128, M = 128
-  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+  // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
   const uint32_t tiles = smem_u32(smb);
   const int ntiles = (len + kTcKT - 1) / kTcKT;
   const int q = lane;        // 16-byte unit of the factor row handled by this thread
@@ -404,12 +417,12 @@ __global__ void __launch_bounds__(256, 2) als_gram_tc_kernel(const AlsArgs a) {
       phase[s] ^= 1;
     }
     const uint32_t big0 = tiles + (uint32_t)(s * 2) * kTcPartBytes, small0 = big0 + kTcPartBytes;
-    // gather 4 rows per thread (warp w handles rows w, w+8, w+16, w+24 of the tile)
+    // gather: warp w handles ratings 4w..4w+3 of the tile, lane q the q-th 16-byte unit of the row
     float4 f[4];
     float rt[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const int k = warp + 8 * i, j = t * kTcKT + k;
+      const int j = t * kTcKT + warp * 4 + i;
       f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       rt[i] = 0.f;
       if (j < len) {
@@ -421,19 +434,24 @@ __global__ void __launch_bounds__(256, 2) als_gram_tc_kernel(const AlsArgs a) {
         }
       }
     }
+    // transpose in registers: for factor dim 4q+e the four ratings form one 16-byte K-vector
+    const float fe[4][4] = {{f[0].x, f[1].x, f[2].x, f[3].x}, {f[0].y, f[1].y, f[2].y, f[3].y},
+                            {f[0].z, f[1].z, f[2].z, f[3].z}, {f[0].w, f[1].w, f[2].w, f[3].w}};
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int mdim = 4 * q + e;
+      float bg[4], sm4[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        bg[i] = round_tf32(fe[e][i]);
+        sm4[i] = round_tf32(fe[e][i] - bg[i]);
+      }
+      const uint32_t off = (uint32_t)warp * kTcLbo + (uint32_t)(mdim >> 3) * kTcSbo + (uint32_t)(mdim & 7) * 16;
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(big0 + off), "f"(bg[0]), "f"(bg[1]), "f"(bg[2]), "f"(bg[3]) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(small0 + off), "f"(sm4[0]), "f"(sm4[1]), "f"(sm4[2]), "f"(sm4[3]) : "memory");
+    }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const int k = warp + 8 * i;
-      float4 bg, sl4;
-      bg.x = __uint_as_float(__float_as_uint(f[i].x) & 0xFFFFE000u);
-      bg.y = __uint_as_float(__float_as_uint(f[i].y) & 0xFFFFE000u);
-      bg.z = __uint_as_float(__float_as_uint(f[i].z) & 0xFFFFE000u);
-      bg.w = __uint_as_float(__float_as_uint(f[i].w) & 0xFFFFE000u);
-      sl4 = make_float4(f[i].x - bg.x, f[i].y - bg.y, f[i].z - bg.z, f[i].w - bg.w);
-      // chunk c = q / 8 (32 floats), unit w = q % 8, swizzled with the row inside the 8-row atom
-      const uint32_t off = (uint32_t)(q >> 3) * (kTcKT * 128) + (uint32_t)k * 128 + (uint32_t)(((q & 7) ^ (k & 7)) << 4);
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(big0 + off), "f"(bg.x), "f"(bg.y), "f"(bg.z), "f"(bg.w) : "memory");
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(small0 + off), "f"(sl4.x), "f"(sl4.y), "f"(sl4.z), "f"(sl4.w) : "memory");
       bacc.x = fmaf(rt[i], f[i].x, bacc.x);
       bacc.y = fmaf(rt[i], f[i].y, bacc.y);
       bacc.z = fmaf(rt[i], f[i].z, bacc.z);
@@ -445,8 +463,8 @@ __global__ void __launch_bounds__(256, 2) als_gram_tc_kernel(const AlsArgs a) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int g = 0; g < kTcKT / 8; g++) {
-        const uint64_t db = umma_desc_sw128(big0 + g * 1024, kTcKT * 128, 1024);
-        const uint64_t ds = umma_desc_sw128(small0 + g * 1024, kTcKT * 128, 1024);
+        const uint64_t db = umma_desc_kmajor(big0 + g * 2 * kTcLbo, kTcLbo, kTcSbo);
+        const uint64_t ds = umma_desc_kmajor(small0 + g * 2 * kTcLbo, kTcLbo, kTcSbo);
         umma_tf32(tmem_d, db, db, idesc, (t > 0 || g > 0) ? 1u : 0u);
         umma_tf32(tmem_d, db, ds, idesc, 1u);
         umma_tf32(tmem_d, ds, db, idesc, 1u);
@@ -538,6 +556,51 @@ static int launch_als(mfb_engine *e, const AlsArgs &a, const SegPlan &sp) {
     MFB_LAUNCH((als_gram_solve_kernel<TR>), sp.n_seg, 256, S::bytes, e->stream, b);
   }
   if (sp.n_multi > 0) MFB_LAUNCH((als_solve_ws_kernel<TR>), sp.n_multi, 256, S::bytes, e->stream, b);
+  return 0;
+}
+
+// Diagnostics: Gram matrix and right-hand side of ONE row through the production kernels (split-row
+// path: partial sums land in the workspace).  out = [RP*RP + RP] floats, RP = padded rank.
+int als_debug_gram(mfb_engine *e, int side, int32_t row, float *out, int32_t *rp_out) {
+  DevCsr &m = e->mat[MFB_TRAIN];
+  const int64_t *ptr = side == MFB_USER ? m.rowptr : m.colptr;
+  int64_t be[2];
+  MFB_CUDA(cudaMemcpy(be, ptr + row, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost));
+  const int r = e->rank;
+  const int RP = r <= 16 ? 16 : r <= 32 ? 32 : r <= 64 ? 64 : 128;
+  *rp_out = RP;
+  int32_t h[5] = {row, (int32_t)be[0], (int32_t)(be[1] - be[0]), 0, row};
+  int32_t *d;
+  MFB_CUDA(cudaMalloc(&d, sizeof(h)));
+  MFB_CUDA(cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice));
+  float *ws;
+  const size_t wsb = sizeof(float) * ((size_t)RP * RP + RP);
+  MFB_CUDA(cudaMalloc(&ws, wsb));
+  MFB_CUDA(cudaMemset(ws, 0, wsb));
+  AlsArgs a;
+  a.Fin = side == MFB_USER ? e->V : e->U;
+  a.Fout = side == MFB_USER ? e->U : e->V;
+  a.ld = e->ld; a.rank = r;
+  a.ind = side == MFB_USER ? m.rowind : m.colind;
+  a.val = side == MFB_USER ? m.rowval : m.colval;
+  a.seg_row = d; a.seg_start = d + 1; a.seg_len = d + 2; a.seg_slot = d + 3; a.multi_row = d + 4;
+  a.ws = ws; a.reg = 0.f;
+  if (RP == 128 && e->opt_als_tensor_cores) {
+    MFB_CUDA(cudaFuncSetAttribute(als_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AlsTcSmem::bytes));
+    MFB_LAUNCH(als_gram_tc_kernel, 1, 256, AlsTcSmem::bytes, e->stream, a);
+  } else if (RP == 128) {
+    MFB_CUDA(cudaFuncSetAttribute(als_gram_solve_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AlsSmem<8>::bytes));
+    MFB_LAUNCH((als_gram_solve_kernel<8>), 1, 256, AlsSmem<8>::bytes, e->stream, a);
+  } else if (RP == 64) {
+    MFB_CUDA(cudaFuncSetAttribute(als_gram_solve_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AlsSmem<4>::bytes));
+    MFB_LAUNCH((als_gram_solve_kernel<4>), 1, 256, AlsSmem<4>::bytes, e->stream, a);
+  } else {
+    return fail("als_debug_gram: rank <= 32 not supported", __FILE__, __LINE__);
+  }
+  MFB_CUDA(cudaStreamSynchronize(e->stream));
+  MFB_CUDA(cudaMemcpy(out, ws, wsb, cudaMemcpyDeviceToHost));
+  cudaFree(ws);
+  cudaFree(d);
   return 0;
 }
 

@@ -471,6 +471,14 @@ extern "C" int mfb_als_half_step(mfb_engine *e, int side, float reg) {
   return als_half_step_launch(e, side, reg);
 }
 
+extern "C" int mfb_debug_als_gram(mfb_engine *e, int side, int32_t row, float *out, int32_t *padded_rank) {
+  MFB_REQUIRE(e && out && padded_rank && (side == MFB_USER || side == MFB_ITEM), "mfb_debug_als_gram: bad argument");
+  MFB_REQUIRE(row >= 0 && row < (side == MFB_USER ? e->n_users : e->n_items), "mfb_debug_als_gram: bad row");
+  MFB_REQUIRE(e->mat[MFB_TRAIN].rowptr && (side == MFB_USER || e->mat[MFB_TRAIN].colptr), "mfb_debug_als_gram: matrix not uploaded");
+  MFB_CUDA(cudaSetDevice(e->device));
+  return als_debug_gram(e, side, row, out, padded_rank);
+}
+
 extern "C" int mfb_ccdpp_begin(mfb_engine *e) {
   MFB_REQUIRE(e, "null engine");
   MFB_REQUIRE(e->mat[MFB_TRAIN].rowptr && e->mat[MFB_TRAIN].colptr, "mfb_ccdpp_begin: training CSR and CSC required");

@@ -165,6 +165,7 @@ int sgd_flat_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int varian
                     uint64_t seed, uint64_t counter);
 int eval_launch(mfb_engine *e, int which, int factors, int variant, int weighted, int want_norms, double out[4]);
 int als_half_step_launch(mfb_engine *e, int side, float reg);
+int als_debug_gram(mfb_engine *e, int side, int32_t row, float *out, int32_t *rp_out);
 int ccdpp_begin_impl(mfb_engine *e);
 int ccdpp_rank1_impl(mfb_engine *e, int32_t k, int first_iter, int32_t inner, float ureg, float ireg,
                      int32_t item_freq_thresh);

@@ -24,7 +24,7 @@ VARIANT = {"mf": MF, "IFWMF": IFWMF, "TMF": TMF, "TMFDropout": TMFDROPOUT}
 SYMBOLS = [
     "mfb_last_error", "mfb_launch_count", "mfb_create", "mfb_destroy", "mfb_sync", "mfb_pin_host",
     "mfb_unpin_host", "mfb_upload_csr", "mfb_set_masks", "mfb_upload_factors", "mfb_download_factors",
-    "mfb_set_aux", "mfb_sgd_plan", "mfb_sgd_subepoch", "mfb_sgd_block_nnz", "mfb_sgd_epoch_flat", "mfb_set_option", "mfb_als_half_step",
+    "mfb_set_aux", "mfb_sgd_plan", "mfb_sgd_subepoch", "mfb_sgd_block_nnz", "mfb_sgd_epoch_flat", "mfb_set_option", "mfb_als_half_step", "mfb_debug_als_gram",
     "mfb_ccdpp_begin", "mfb_ccdpp_rank1", "mfb_ccdpp_end", "mfb_eval", "mfb_snapshot_best",
     "mfb_restore_best", "mfb_event_record", "mfb_event_elapsed_ms", "mfb_device_factors", "mfb_stream",
     "mfb_pack_rows", "mfb_unpack_rows", "mfb_set_row_range",
@@ -72,6 +72,7 @@ def load_library():
     L.mfb_set_option.argtypes = [vp, C.c_char_p, C.c_double]
     L.mfb_sgd_block_nnz.argtypes = [vp, vp, i32, C.POINTER(i64)]
     L.mfb_als_half_step.argtypes = [vp, C.c_int, f32]
+    L.mfb_debug_als_gram.argtypes = [vp, C.c_int, i32, vp, C.POINTER(i32)]
     L.mfb_ccdpp_begin.argtypes = [vp]
     L.mfb_ccdpp_rank1.argtypes = [vp, i32, C.c_int, i32, f32, f32, i32]
     L.mfb_ccdpp_end.argtypes = [vp]
@@ -190,6 +191,13 @@ class Engine:
     # ---- ALS / CCD++ ----
     def als_half_step(self, side, reg):
         self._check(self.L.mfb_als_half_step(self.h, side, reg))
+
+    def debug_als_gram(self, side, row):
+        rp = C.c_int32()
+        out = np.zeros(128 * 128 + 128, np.float32)
+        self._check(self.L.mfb_debug_als_gram(self.h, side, row, _p(out), C.byref(rp)))
+        R = rp.value
+        return out[: R * R].reshape(R, R).copy(), out[R * R: R * R + R].copy()
 
     def ccdpp_begin(self):
         self._check(self.L.mfb_ccdpp_begin(self.h))
