@@ -45,6 +45,8 @@ SHAPE = (480_189, 17_770, 100_480_507)
 # its NaN guard (restore + halve, model.cpp:1487-1498) — measured with the oracle, see DESIGN.md
 HP = dict(lr=0.002, ureg=0.05, ireg=0.05)
 FALLBACK_HBM_GBS = 6650.0
+# dram__bytes_read.sum + dram__bytes_write.sum of the SGD kernel launches of one epoch (profiles/r1_sgd_flat.md)
+DRAM_TRAFFIC_BYTES_PER_EPOCH = None
 
 
 def log(*a):
@@ -323,47 +325,47 @@ def main():
         sched_blocks = [np.array([[0, 0]], np.int32)]
         my_nnz_per_epoch = train_nnz
     else:
-        # DSGD: user stratum g pinned to rank g, item blocks visited in a rotating permutation
+        # DSGD: user stratum g pinned to rank g (only its CSR rows are uploaded), P = N item
+        # blocks; after every sub-epoch the updated item block is stored straight into the next owner's V
+        # over NVLink by a kernel and ordered by device-side sequence flags (matfac_b200/csrc/comm.cu)
+        from matfac_b200 import dsgd
         prng = np.random.default_rng(7)
         user_part = prng.integers(0, P, size=n_users).astype(np.int32)
         item_part = prng.integers(0, P, size=n_items).astype(np.int32)
         mine = user_part == rank
-        rows = np.repeat(mine, np.diff(ptr))
-        cnt = np.where(mine, np.diff(ptr), 0)
-        lptr = np.zeros(n_users + 1, np.int64)
-        np.cumsum(cnt, out=lptr[1:])
-        ltr = Mat(n_users, n_items, (lptr, ind[rows], val[rows]))
+
+        def local_rows(t):
+            p_, i_, v_ = t
+            rows = np.repeat(mine, np.diff(p_))
+            lptr = np.zeros(n_users + 1, np.int64)
+            np.cumsum(np.where(mine, np.diff(p_), 0), out=lptr[1:])
+            return Mat(n_users, n_items, (lptr, i_[rows], v_[rows]))
+
+        ltr, lva = local_rows(prob["train"]), local_rows(prob["val"])
         eng.upload_csr(E.TRAIN, ltr, with_csc=False)
-        eng.upload_csr(E.VAL, va, with_csc=False)
+        eng.upload_csr(E.VAL, lva, with_csc=False)
         eng.set_masks(bad_u, bad_i)
         eng.upload_factors(U0, V0)
-        up_local = np.where(mine, user_part, -1).astype(np.int32)
-        eng.sgd_plan(P, up_local, item_part)
+        eng.sgd_plan(P, np.where(mine, user_part, -1).astype(np.int32), item_part)
         eng.set_option("sgd_block_order", 1)  # shuffled inside the blocks: full concurrency
-        sched_blocks = [np.array([[rank, (rank + s) % P]], np.int32) for s in range(P)]
-        my_nnz_per_epoch = int(lptr[-1])
-        item_ids = [np.nonzero(item_part == b)[0].astype(np.int32) for b in range(P)]
-        max_blk = max(len(x) for x in item_ids)
-        ld = eng.device_factors(E.ITEM)[1]
-        send = torch.zeros(max_blk * ld, dtype=torch.float32, device="cuda")
-        recv = [torch.zeros(max_blk * ld, dtype=torch.float32, device="cuda") for _ in range(P)]
+        blobs = [None] * world
+        dist.all_gather_object(blobs, eng.comm_init(rank, world))
+        eng.comm_connect(blobs)
+        my_nnz_per_epoch = int(ltr.rowptr[-1])
+        sched = dsgd.rotation_schedule(P, (args.warmup + args.steps) * P + 1)
+        transport = dsgd.EngineTransport(eng, rank)
 
     def epoch(ep):
         if world == 1:
             eng.sgd_epoch_flat(E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, ep)
             return
-        for s in range(P):
-            eng.sgd_subepoch(sched_blocks[s], E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, ep * P + s)
-            # exchange step: every rank publishes the item block it just updated
-            b = (rank + s) % P
-            eng.pack_rows(E.ITEM, item_ids[b], send.data_ptr())
-            dist.all_gather(recv, send)
-            torch.cuda.synchronize()
-            for g in range(P):
-                if g != rank:
-                    eng.unpack_rows(E.ITEM, item_ids[(g + s) % P], recv[g].data_ptr())
+        dsgd.run_steps(sched, ep * P, (ep + 1) * P, rank, transport,
+                       lambda block, t: eng.sgd_subepoch(np.array([[rank, block]], np.int32), E.MF, HP["lr"], HP["ureg"],
+                                                         HP["ireg"], 1, t))
 
     def barrier():
+        if dist is not None:
+            eng.comm_barrier()
         eng.sync()
         torch.cuda.synchronize()
         if dist is not None:
@@ -376,19 +378,20 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = E.launch_count()
-    t_host0 = time.perf_counter()
     eng.event_record(0)
     for k in range(args.steps):
         epoch(args.warmup + k)
     eng.event_record(1)
     barrier()
-    t_host = time.perf_counter() - t_host0
-    ms_dev = eng.event_elapsed_ms(0, 1)
+    ms_dev = eng.event_elapsed_ms(0, 1)  # CUDA events on the engine's stream: kernels + exchange + waits
     launches = E.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    ms_total = ms_dev if world == 1 else t_host * 1e3
+    ms_total = ms_dev
     total_nnz = my_nnz_per_epoch
+    nnz_per_rank = [my_nnz_per_epoch]
     if dist is not None:
+        if eng.comm_error():
+            raise SystemExit(f"[rank {rank}] a device-side wait timed out: the exchange schedule is broken")
         t = torch.tensor([ms_total, float(my_nnz_per_epoch)], dtype=torch.float64, device="cuda")
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -396,9 +399,20 @@ def main():
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms_total = float(tmax[0])
         total_nnz = int(tsum[1])
+        allnnz = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(allnnz, t[1:2].clone())
+        nnz_per_rank = [int(x.item()) for x in allnnz]
+        # every rank publishes the item block it holds, then evaluates its own users' validation rows
+        dsgd.publish(sched, (args.warmup + args.steps) * P - 1, rank, transport)
     ms_per_step = ms_total / args.steps
     value = total_nnz / (ms_per_step * 1e-3)
-    val_rmse = eng.rmse(E.VAL)
+    ev = eng.eval(E.VAL)
+    if dist is not None:
+        t = torch.tensor([ev[0], ev[1]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ev = [float(t[0]), float(t[1])]
+        eng.comm_barrier()
+    val_rmse = float(np.sqrt(ev[0] / ev[1])) if ev[1] > 0 else float("nan")
     log(f"[rank {rank}] {ms_per_step:.3f} ms/epoch, {value/1e9:.3f} G updates/s, val RMSE after {args.warmup+args.steps} epochs {val_rmse:.4f}")
 
     if rank != 0:
@@ -407,16 +421,21 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # roofline of the SGD update kernel (one launch per epoch at N = 1)
+    # roofline of the SGD update kernel.  N = 1: one launch (or one per user band) per epoch, timed by the
+    # events above.  N > 1: rank 0's share of the algorithmic bytes over the same wall of device time,
+    # which also holds the exchange pushes and flag waits of the sub-epochs.
     peak, peak_src = measured_hbm_gbs()
     alg_bytes = (16 * RANK + 12) * float(my_nnz_per_epoch)
-    kern_ms = ms_dev / max(1, (args.steps * (1 if world == 1 else P)))
-    achieved = alg_bytes / (1 if world == 1 else P) / (kern_ms * 1e-3) / 1e9 if world == 1 else None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+    achieved = alg_bytes * args.steps / (ms_dev * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": DRAM_TRAFFIC_BYTES_PER_EPOCH if world == 1 and args.scale == 1.0 else None, "peak_source": peak_src,
                 "kernel": "sgd_flat_kernel<16,1,MF>", "algorithmic_bytes_per_update": 16 * RANK + 12,
-                "note": "achieved counts algorithmic bytes (u,v read + reduced, 12 B rating record); V (4.5 MB) and part of "
-                        "U (123 MB) are L2 resident, so DRAM traffic is below it (see profiles/)"}
+                "launches_per_epoch": launches / args.steps,
+                "note": "achieved = algorithmic bytes (u,v read + reduced, 12 B rating record) of one epoch on this rank / its "
+                        "device time; traffic = dram__bytes_read+write per epoch from the ncu --set full capture in profiles/ "
+                        "(V and the current band of U are L2 resident, so DRAM traffic is far below the algorithmic bytes)"}
+    if world > 1:
+        roofline["per_rank_nnz"] = nnz_per_rank
 
     # the stratified trainer's kernel (user-major runs, concurrency capped for parity) for the record
     stratified = None

@@ -125,7 +125,10 @@ int mfb_sgd_epoch_flat(mfb_engine *e, int variant, float learn_rate, float ureg,
  * "sgd_max_hot_inflight" (bound on concurrent updates of the hottest item row, default 8),
  * "sgd_flat_hot_lr" (shuffled kernel: the hottest row's concurrency is capped at value / learn_rate,
  * default 0.15), "sgd_flat_inflight_frac" (shuffled kernel: ratings in flight <= this fraction of
- * the epoch, default 2e-4), "als_tensor_cores" (rank > 64: 1 = tcgen05 3xTF32 Gram, 0 = fp32 CUDA-core
+ * the epoch, default 2e-4), "sgd_flat_band_mb" (shuffled kernel, whole-matrix plans: the epoch visits
+ * the ratings in bands of users whose rows take this many MB, so that a band of U stays in L2; default
+ * 0 = one band, a uniformly shuffled epoch as in modelMF.cpp:76-81 (banding converges at a different rate
+ * per epoch than the reference's order); takes effect at the next mfb_sgd_plan), "als_tensor_cores" (rank > 64: 1 = tcgen05 3xTF32 Gram, 0 = fp32 CUDA-core
  * Gram), "sgd_block_order" (stratified trainers: 0 = user-major runs, 1 = shuffled inside the
  * blocks), "sgd_atomic" (1 = item rows updated by reductions, 0 = plain stores), "sgd_rotate" (1 = every
  * user run of the stratified kernel starts at a pseudo-random offset and wraps around, 0 = CSR
@@ -182,6 +185,32 @@ int mfb_unpack_rows(mfb_engine *e, int side, const int32_t *ids, int32_t n, cons
 /* Restrict the rows this engine's ALS / CCD++ / eval kernels own to [begin, end) of `side`
  * (row sharding across ranks); default is everything. */
 int mfb_set_row_range(mfb_engine *e, int side, int32_t begin, int32_t end);
+
+/* ---- peer-memory exchange between the engines of one node (one process per GPU, <= 8 ranks) ----
+ * The reference has one shared-memory address space (OpenMP threads write uFac / iFac in place,
+ * modelMF.cpp:275-303, :806-880); across GPUs the same effect is obtained by mapping every rank's
+ * factor matrices into every peer (CUDA IPC over NVLink / NVSwitch) and storing produced rows into
+ * the peers from inside the kernels.  Ordering uses 64-bit sequence flags in peer memory; nothing on
+ * this path synchronises with the host.
+ * init: allocates the flag words and returns this rank's handle blob (320 bytes) to be swapped by the
+ * caller's process group; connect: takes the `world` blobs in rank order and maps the peers.
+ * After connect, mfb_als_half_step and mfb_ccdpp_rank1 store the rows of this rank's row range
+ * (mfb_set_row_range) into all peers and end with a flag barrier. */
+int mfb_comm_init(mfb_engine *e, int32_t rank, int32_t world, uint8_t *handles_out, int64_t *handles_bytes);
+int mfb_comm_connect(mfb_engine *e, const uint8_t *all_handles, int64_t bytes);
+/* device-side barrier over all ranks on the engines' streams (every rank must call it) */
+int mfb_comm_barrier(mfb_engine *e);
+/* *timed_out = 1 when a device-side wait gave up (20 s): a peer died or the schedule is inconsistent */
+int mfb_comm_error(mfb_engine *e, int32_t *timed_out);
+/* DSGD exchange step: push the rows of item part `item_part` of the stratified plan
+ * into rank dst_rank's V and publish sequence number `seq` there (dst_rank = -1: into every peer, no
+ * flag); wait_block makes the stream wait until rank src_rank has published a sequence >= seq here.
+ * Pushes from one source must use increasing sequence numbers. */
+int mfb_dsgd_push_block(mfb_engine *e, int32_t item_part, int32_t dst_rank, uint64_t seq);
+int mfb_comm_wait_block(mfb_engine *e, int32_t src_rank, uint64_t seq);
+/* store n rows of `side` (host id list, or the range [first, first + n) when ids is NULL) into every
+ * peer, then barrier: assembles sharded results on all ranks */
+int mfb_comm_allgather_rows(mfb_engine *e, int side, const int32_t *ids, int32_t first, int32_t n);
 
 #ifdef __cplusplus
 }

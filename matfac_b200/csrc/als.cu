@@ -31,7 +31,19 @@ struct AlsArgs {
   const int32_t *multi_row;
   float *ws;
   float reg;
+  // row-sharded runs: the other ranks' copies of this side's factors (peer memory); every solved row
+  // is stored into all of them, i.e. the all-gather is fused into the solve epilogue
+  float *Fpeer[kMaxRanks - 1];
+  int n_peer;
 };
+
+__device__ __forceinline__ void store_solution(const AlsArgs &a, int row, int tid, const float *bv) {
+  if (tid < a.ld) {
+    const float x = tid < a.rank ? bv[tid] : 0.f;
+    a.Fout[(size_t)row * a.ld + tid] = x;
+    for (int p = 0; p < a.n_peer; p++) a.Fpeer[p][(size_t)row * a.ld + tid] = x;
+  }
+}
 
 template <int TR>
 __device__ __forceinline__ int tile_idx(int t, int i) {
@@ -255,7 +267,7 @@ __global__ void __launch_bounds__(256, (TR == 8 ? 2 : 3)) als_gram_solve_kernel(
   }
   add_reg_diag<TR>(acc, tx, ty, a.rank, a.reg);
   chol_solve<TR, AlsSmem<TR>>(acc, sm, tx, ty);
-  if (tid < a.ld) a.Fout[(size_t)row * a.ld + tid] = tid < a.rank ? bv[tid] : 0.f;
+  store_solution(a, row, tid, bv);
 }
 
 template <int TR>
@@ -276,7 +288,7 @@ __global__ void __launch_bounds__(256, (TR == 8 ? 2 : 3)) als_solve_ws_kernel(co
   if (tid < RP) bv[tid] = w[RP * RP + tid];
   add_reg_diag<TR>(acc, tx, ty, a.rank, a.reg);
   chol_solve<TR, AlsSmem<TR>>(acc, sm, tx, ty);
-  if (tid < a.ld) a.Fout[(size_t)row * a.ld + tid] = tid < a.rank ? bv[tid] : 0.f;
+  store_solution(a, row, tid, bv);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -528,7 +540,7 @@ __global__ void __launch_bounds__(256, 2) als_gram_tc_kernel(const AlsArgs a) {
   __syncthreads();  // everyone holds its tile: L may now be overwritten by the factorisation
   add_reg_diag<TR>(acc, tx, ty, a.rank, a.reg);
   chol_solve<TR, S>(acc, sm, tx, ty);
-  if (tid < a.ld) a.Fout[(size_t)row * a.ld + tid] = tid < a.rank ? bv[tid] : 0.f;
+  store_solution(a, row, tid, bv);
 }
 
 template <int TR>
@@ -584,7 +596,7 @@ int als_debug_gram(mfb_engine *e, int side, int32_t row, float *out, int32_t *rp
   a.ind = side == MFB_USER ? m.rowind : m.colind;
   a.val = side == MFB_USER ? m.rowval : m.colval;
   a.seg_row = d; a.seg_start = d + 1; a.seg_len = d + 2; a.seg_slot = d + 3; a.multi_row = d + 4;
-  a.ws = ws; a.reg = 0.f;
+  a.ws = ws; a.reg = 0.f; a.n_peer = 0;
   if (RP == 128 && e->opt_als_tensor_cores) {
     MFB_CUDA(cudaFuncSetAttribute(als_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AlsTcSmem::bytes));
     MFB_LAUNCH(als_gram_tc_kernel, 1, 256, AlsTcSmem::bytes, e->stream, a);
@@ -626,11 +638,17 @@ int als_half_step_launch(mfb_engine *e, int side, float reg) {
   a.multi_row = sp.multi_row;
   a.ws = nullptr;
   a.reg = reg;
+  a.n_peer = 0;
+  const Comm &c = e->comm;
+  if (c.connected)
+    for (int p = 0; p < c.world; p++)
+      if (p != c.rank) a.Fpeer[a.n_peer++] = side == MFB_USER ? c.U[p] : c.V[p];
   const int r = e->rank;
-  if (r <= 16) return launch_als<1>(e, a, sp);
-  if (r <= 32) return launch_als<2>(e, a, sp);
-  if (r <= 64) return launch_als<4>(e, a, sp);
-  return launch_als<8>(e, a, sp);
+  if (r <= 16) MFB_TRY(launch_als<1>(e, a, sp));
+  else if (r <= 32) MFB_TRY(launch_als<2>(e, a, sp));
+  else if (r <= 64) MFB_TRY(launch_als<4>(e, a, sp));
+  else MFB_TRY(launch_als<8>(e, a, sp));
+  return comm_barrier_launch(e);  // every rank's rows have landed before the next half-step reads them
 }
 
 }  // namespace mfb

@@ -15,6 +15,17 @@ namespace mfb {
 
 constexpr int kCcdChunk = 1024;
 
+// row-sharded runs: the other ranks' copies of the dense u_k / v_k vector being produced (peer memory);
+// every new entry is stored into all of them, so the all-gather rides on the update pass itself
+struct CcdPeers {
+  float *p[kMaxRanks - 1];
+  int n;
+};
+__device__ __forceinline__ void store_all(float *own, const CcdPeers &pe, int row, float v) {
+  own[row] = v;
+  for (int i = 0; i < pe.n; i++) pe.p[i][row] = v;
+}
+
 struct CcdPass {
   const int32_t *ind;
   float *res;
@@ -41,7 +52,7 @@ __global__ void __launch_bounds__(256) ccd_resid_kernel(const CcdPass p, const f
 __global__ void __launch_bounds__(256) ccd_update_kernel(const CcdPass p, float *__restrict__ own,
                                                          const float *__restrict__ other, float reg,
                                                          double *__restrict__ acc, const Aux *__restrict__ aux_freq,
-                                                         int freq_thresh) {
+                                                         int freq_thresh, const CcdPeers pe) {
   const int lane = threadIdx.x & 31;
   const int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (seg >= p.n_seg) return;
@@ -62,7 +73,7 @@ __global__ void __launch_bounds__(256) ccd_update_kernel(const CcdPass p, float 
     if (slot < 0) {
       float nv = (float)(num / ((double)reg + den));
       if (freq_thresh > 0 && aux_freq[row].freq < freq_thresh) nv = 0.f;
-      own[row] = nv;
+      store_all(own, pe, row, nv);
     } else {
       atomicAdd(acc + 2 * (size_t)slot, num);
       atomicAdd(acc + 2 * (size_t)slot + 1, den);
@@ -72,24 +83,25 @@ __global__ void __launch_bounds__(256) ccd_update_kernel(const CcdPass p, float 
 
 __global__ void ccd_finalize_kernel(const int32_t *__restrict__ multi_row, int n_multi, double *__restrict__ acc,
                                     float *__restrict__ own, float reg, const Aux *__restrict__ aux_freq,
-                                    int freq_thresh) {
+                                    int freq_thresh, const CcdPeers pe) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_multi) return;
   const int row = multi_row[s];
   float nv = (float)(acc[2 * (size_t)s] / ((double)reg + acc[2 * (size_t)s + 1]));
   if (freq_thresh > 0 && aux_freq[row].freq < freq_thresh) nv = 0.f;
-  own[row] = nv;
+  store_all(own, pe, row, nv);
   acc[2 * (size_t)s] = 0.0;
   acc[2 * (size_t)s + 1] = 0.0;
 }
 
-__global__ void col_extract_kernel(const float *__restrict__ F, int ld, int k, int n, float *__restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = F[(size_t)i * ld + k];
+__global__ void col_extract_kernel(const float *__restrict__ F, int ld, int k, int lo, int hi, float *__restrict__ out,
+                                   const CcdPeers pe) {
+  const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < hi) store_all(out, pe, i, F[(size_t)i * ld + k]);
 }
-__global__ void col_insert_kernel(float *__restrict__ F, int ld, int k, int n, const float *__restrict__ in) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) F[(size_t)i * ld + k] = in[i];
+__global__ void col_insert_kernel(float *__restrict__ F, int ld, int k, int lo, int hi, const float *__restrict__ in) {
+  const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < hi) F[(size_t)i * ld + k] = in[i];
 }
 
 int ccdpp_begin_impl(mfb_engine *e) {
@@ -130,9 +142,19 @@ int ccdpp_rank1_impl(mfb_engine *e, int32_t k, int first_iter, int32_t inner, fl
   CcdPass cols{m.colind, e->res_col, cp.row, cp.start, cp.len, cp.slot, cp.n_seg};
   const int tb = 256, wpb = tb / 32;
   const int g_rows = (rp.n_seg + wpb - 1) / wpb, g_cols = (cp.n_seg + wpb - 1) / wpb;
+  // row-sharded: this rank owns users [ulo, uhi) and items [ilo, ihi); every new u_k / v_k entry is also
+  // stored into the peers' vectors and a flag barrier closes each pass
+  const int ulo = e->row_begin[MFB_USER], uhi = e->row_end[MFB_USER], ilo = e->row_begin[MFB_ITEM], ihi = e->row_end[MFB_ITEM];
+  CcdPeers pu, pv;
+  pu.n = pv.n = 0;
+  const Comm &c = e->comm;
+  if (c.connected)
+    for (int p = 0; p < c.world; p++)
+      if (p != c.rank) { pu.p[pu.n++] = c.uk[p]; pv.p[pv.n++] = c.vk[p]; }
   // u_k = uFac.col(k); v_k = iFac.col(k)   (modelMF.cpp:1028-1029)
-  MFB_LAUNCH(col_extract_kernel, (e->n_users + 255) / 256, 256, 0, st, e->U, e->ld, k, e->n_users, e->uk);
-  MFB_LAUNCH(col_extract_kernel, (e->n_items + 255) / 256, 256, 0, st, e->V, e->ld, k, e->n_items, e->vk);
+  if (uhi > ulo) MFB_LAUNCH(col_extract_kernel, (uhi - ulo + 255) / 256, 256, 0, st, e->U, e->ld, k, ulo, uhi, e->uk, pu);
+  if (ihi > ilo) MFB_LAUNCH(col_extract_kernel, (ihi - ilo + 255) / 256, 256, 0, st, e->V, e->ld, k, ilo, ihi, e->vk, pv);
+  MFB_TRY(comm_barrier_launch(e));
   if (!first_iter) {
     if (g_rows) MFB_LAUNCH(ccd_resid_kernel, g_rows, tb, 0, st, rows, e->uk, e->vk, 1.0f);
     if (g_cols) MFB_LAUNCH(ccd_resid_kernel, g_cols, tb, 0, st, cols, e->vk, e->uk, 1.0f);
@@ -140,23 +162,31 @@ int ccdpp_rank1_impl(mfb_engine *e, int32_t k, int first_iter, int32_t inner, fl
   // the FreqAdap rule zeroes v_k of infrequent items for k > 0 (modelMF.cpp:1336-1342)
   const int thresh = (item_freq_thresh > 0 && k > 0) ? item_freq_thresh : 0;
   for (int s = 0; s < inner; s++) {
-    if (g_rows) MFB_LAUNCH(ccd_update_kernel, g_rows, tb, 0, st, rows, e->uk, e->vk, ureg, e->ccd_acc, e->aux_u, 0);
+    if (g_rows) MFB_LAUNCH(ccd_update_kernel, g_rows, tb, 0, st, rows, e->uk, e->vk, ureg, e->ccd_acc, e->aux_u, 0, pu);
     if (rp.n_multi)
       MFB_LAUNCH(ccd_finalize_kernel, (rp.n_multi + 255) / 256, 256, 0, st, rp.multi_row, rp.n_multi, e->ccd_acc, e->uk,
-                 ureg, e->aux_u, 0);
-    if (g_cols) MFB_LAUNCH(ccd_update_kernel, g_cols, tb, 0, st, cols, e->vk, e->uk, ireg, e->ccd_acc, e->aux_i, thresh);
+                 ureg, e->aux_u, 0, pu);
+    MFB_TRY(comm_barrier_launch(e));
+    if (g_cols) MFB_LAUNCH(ccd_update_kernel, g_cols, tb, 0, st, cols, e->vk, e->uk, ireg, e->ccd_acc, e->aux_i, thresh, pv);
     if (cp.n_multi)
       MFB_LAUNCH(ccd_finalize_kernel, (cp.n_multi + 255) / 256, 256, 0, st, cp.multi_row, cp.n_multi, e->ccd_acc, e->vk,
-                 ireg, e->aux_i, thresh);
+                 ireg, e->aux_i, thresh, pv);
+    MFB_TRY(comm_barrier_launch(e));
   }
   if (g_rows) MFB_LAUNCH(ccd_resid_kernel, g_rows, tb, 0, st, rows, e->uk, e->vk, -1.0f);
   if (g_cols) MFB_LAUNCH(ccd_resid_kernel, g_cols, tb, 0, st, cols, e->vk, e->uk, -1.0f);
-  MFB_LAUNCH(col_insert_kernel, (e->n_users + 255) / 256, 256, 0, st, e->U, e->ld, k, e->n_users, e->uk);
-  MFB_LAUNCH(col_insert_kernel, (e->n_items + 255) / 256, 256, 0, st, e->V, e->ld, k, e->n_items, e->vk);
+  if (uhi > ulo) MFB_LAUNCH(col_insert_kernel, (uhi - ulo + 255) / 256, 256, 0, st, e->U, e->ld, k, ulo, uhi, e->uk);
+  if (ihi > ilo) MFB_LAUNCH(col_insert_kernel, (ihi - ilo + 255) / 256, 256, 0, st, e->V, e->ld, k, ilo, ihi, e->vk);
   return 0;
 }
 
+int comm_allgather_range(mfb_engine *e, int side, int first, int n);
+
 int ccdpp_end_impl(mfb_engine *e) {
+  if (e->comm.connected) {  // assemble the sharded factors on every rank
+    MFB_TRY(comm_allgather_range(e, MFB_USER, e->row_begin[MFB_USER], e->row_end[MFB_USER] - e->row_begin[MFB_USER]));
+    MFB_TRY(comm_allgather_range(e, MFB_ITEM, e->row_begin[MFB_ITEM], e->row_end[MFB_ITEM] - e->row_begin[MFB_ITEM]));
+  }
   MFB_CUDA(cudaStreamSynchronize(e->stream));
   cudaFree(e->res_row); cudaFree(e->res_col);
   e->res_row = e->res_col = nullptr;

@@ -47,6 +47,7 @@ void DevCsr::release() {
 void SgdPlan::release() {
   if (owns_ratings) { cudaFree(item); cudaFree(val); }
   cudaFree(seg_user); cudaFree(seg_start); cudaFree(seg_len); cudaFree(rat_user); cudaFree(work_counter);
+  cudaFree(part_items);
   *this = SgdPlan();
 }
 
@@ -238,6 +239,13 @@ extern "C" void mfb_destroy(mfb_engine *e) {
   cudaFree(e->eval_partial); cudaFree(e->eval_out); cudaFreeHost(e->eval_out_host);
   cudaFree(e->als_ws); cudaFree(e->res_row); cudaFree(e->res_col); cudaFree(e->uk); cudaFree(e->vk);
   cudaFree(e->ccd_acc); cudaFree(e->scratch);
+  if (e->comm.connected)
+    for (int r = 0; r < e->comm.world; r++) {
+      if (r == e->comm.rank) continue;
+      cudaIpcCloseMemHandle(e->comm.U[r]); cudaIpcCloseMemHandle(e->comm.V[r]); cudaIpcCloseMemHandle(e->comm.uk[r]);
+      cudaIpcCloseMemHandle(e->comm.vk[r]); cudaIpcCloseMemHandle(e->comm.flags[r]);
+    }
+  cudaFree(e->comm.own_flags);
   for (int i = 0; i < 16; i++) cudaEventDestroy(e->events[i]);
   cudaStreamDestroy(e->stream);
   delete e;
@@ -442,6 +450,7 @@ extern "C" int mfb_set_option(mfb_engine *e, const char *name, double value) {
   else if (n == "sgd_max_hot_inflight") e->opt_sgd_max_hot_inflight = value;
   else if (n == "sgd_flat_hot_lr") e->opt_sgd_flat_hot_lr = value;
   else if (n == "sgd_flat_inflight_frac") e->opt_sgd_flat_inflight_frac = value;
+  else if (n == "sgd_flat_band_mb") e->opt_sgd_flat_band_mb = value;
   else if (n == "sgd_atomic") e->opt_sgd_atomic = (int)value;
   else if (n == "sgd_rotate") e->opt_sgd_rotate = (int)value;
   else if (n == "als_tensor_cores") e->opt_als_tensor_cores = (int)value;

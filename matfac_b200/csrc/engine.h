@@ -77,6 +77,19 @@ struct __align__(16) Aux {
 };
 
 constexpr int kMaxBlocks = 64;  // blocks per sub-epoch launch (P <= 64)
+constexpr int kMaxRanks = 8;    // engines of one node that exchange through peer memory
+constexpr int kFlagSlots = 64;  // 64-bit flag words per engine: [0,8) barrier arrivals, [8,16) block arrivals
+
+// Peer-memory view of the other ranks' engines (same node, one process per GPU; CUDA IPC mappings
+// over NVLink / NVSwitch).  Index = rank; the own entry points at the local buffers.
+struct Comm {
+  int rank = 0, world = 1;
+  bool connected = false;
+  float *U[kMaxRanks] = {}, *V[kMaxRanks] = {}, *uk[kMaxRanks] = {}, *vk[kMaxRanks] = {};
+  unsigned long long *flags[kMaxRanks] = {};
+  unsigned long long *own_flags = nullptr;  // [kFlagSlots] + ticket + error word
+  uint64_t barrier_seq = 0;
+};
 
 struct SgdPlan {
   int32_t P = 0;
@@ -94,6 +107,11 @@ struct SgdPlan {
   std::vector<int32_t> blk_seg_off, blk_seg_cnt;  // [P*P]
   std::vector<int64_t> blk_nnz;                   // [P*P]
   std::vector<int64_t> blk_rat_off;               // [P*P] first rating of every block
+  std::vector<int32_t> item_count;                // ratings per item over the uploaded rows (host copy)
+  std::vector<double> blk_hot_share;              // [P*P] hottest item's share of the block's ratings
+  std::vector<int64_t> band_rat_off;              // P == 1: rating offsets of the user bands of the shuffled kernel
+  int32_t *part_items = nullptr;                  // item ids grouped by item part (device)
+  std::vector<int32_t> part_item_off;             // [P+1]
   bool built = false;
   void release();
 };
@@ -111,6 +129,7 @@ struct mfb_engine {
   double opt_sgd_max_hot_inflight = 8.0;  // bound on concurrent updates of the hottest item row
   double opt_sgd_flat_hot_lr = 0.15;  // shuffled kernel: cap on (hot-row concurrency x learning rate)
   double opt_sgd_flat_inflight_frac = 2e-4;  // shuffled kernel: ratings in flight <= this fraction of the epoch
+  double opt_sgd_flat_band_mb = 0.0;  // shuffled kernel: user rows per band (MB of U), 0 = one band (the reference's order)
   int opt_sgd_atomic = 1;             // item rows updated by vector reductions (no lost updates)
   int opt_sgd_block_order = 0;        // stratified trainers: 0 = user-major runs (reference order), 1 = shuffled inside the blocks
   int opt_sgd_rotate = 0;             // user runs start at a pseudo-random offset (de-correlates heavy users)
@@ -145,6 +164,8 @@ struct mfb_engine {
   double *ccd_acc = nullptr;  // [slots][2]
   size_t ccd_acc_slots = 0;
 
+  mfb::Comm comm;
+
   // generic scratch for plan building (grown on demand)
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -170,5 +191,6 @@ int ccdpp_begin_impl(mfb_engine *e);
 int ccdpp_rank1_impl(mfb_engine *e, int32_t k, int first_iter, int32_t inner, float ureg, float ireg,
                      int32_t item_freq_thresh);
 int ccdpp_end_impl(mfb_engine *e);
+int comm_barrier_launch(mfb_engine *e);
 
 }  // namespace mfb

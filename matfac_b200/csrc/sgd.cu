@@ -23,6 +23,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cmath>
 
 namespace mfb {
 
@@ -142,6 +143,8 @@ static int sgd_plan_common(mfb_engine *e) {
     MFB_TRY(ensure_scratch(e, tmp_bytes));
     MFB_CUDA(cub::DeviceReduce::Sum(e->scratch, tmp_bytes, sq, d_sum, e->n_items, st));
     MFB_CUDA(cudaMemcpyAsync(&sum, d_sum, sizeof(double), cudaMemcpyDeviceToHost, st));
+    pl.item_count.resize((size_t)e->n_items);
+    MFB_CUDA(cudaMemcpyAsync(pl.item_count.data(), hist, sizeof(int32_t) * (size_t)e->n_items, cudaMemcpyDeviceToHost, st));
     MFB_CUDA(cudaStreamSynchronize(st));
     cudaFree(hist);
     cudaFree(sq);
@@ -179,10 +182,36 @@ int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int
     MFB_CUDA(cudaMalloc(&pl.rat_user, sizeof(int32_t) * (size_t)(m.nnz > 0 ? m.nnz : 1)));
     if (m.nnz > 0)
       MFB_LAUNCH(rat_user_kernel, (unsigned)((m.nnz + 255) / 256), 256, 0, st, m.rowptr, e->n_users, m.nnz, pl.rat_user);
+    // user bands of the shuffled kernel: equal user counts, rating offsets read back from rowptr
+    {
+      const double row_bytes = sizeof(float) * (double)e->ld;
+      int nbands = 1;
+      if (e->opt_sgd_flat_band_mb > 0)
+        nbands = (int)std::ceil((double)e->n_users * row_bytes / (e->opt_sgd_flat_band_mb * 1048576.0));
+      nbands = std::max(1, std::min(nbands, std::min(64, e->n_users)));
+      pl.band_rat_off.assign((size_t)nbands + 1, 0);
+      for (int b = 0; b <= nbands; b++) {
+        const int64_t u = (int64_t)e->n_users * b / nbands;
+        MFB_CUDA(cudaMemcpyAsync(&pl.band_rat_off[b], m.rowptr + u, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      }
+      MFB_CUDA(cudaStreamSynchronize(st));
+    }
     pl.built = true;
     return 0;
   }
   int64_t nnz = m.nnz;
+  {  // item ids grouped by item part: the rows an exchange step moves between ranks
+    pl.part_item_off.assign((size_t)P + 1, 0);
+    for (int i = 0; i < e->n_items; i++)
+      if (item_part[i] >= 0 && item_part[i] < P) pl.part_item_off[item_part[i] + 1]++;
+    for (int b = 0; b < P; b++) pl.part_item_off[b + 1] += pl.part_item_off[b];
+    std::vector<int32_t> ids((size_t)std::max(pl.part_item_off[P], 1)), fill(pl.part_item_off.begin(), pl.part_item_off.end() - 1);
+    for (int i = 0; i < e->n_items; i++)
+      if (item_part[i] >= 0 && item_part[i] < P) ids[fill[item_part[i]]++] = i;
+    MFB_CUDA(cudaMalloc(&pl.part_items, sizeof(int32_t) * ids.size()));
+    MFB_CUDA(cudaMemcpyAsync(pl.part_items, ids.data(), sizeof(int32_t) * ids.size(), cudaMemcpyHostToDevice, st));
+    MFB_CUDA(cudaStreamSynchronize(st));
+  }
   int32_t *d_up, *d_ip;
   MFB_CUDA(cudaMalloc(&d_up, sizeof(int32_t) * e->n_users));
   MFB_CUDA(cudaMalloc(&d_ip, sizeof(int32_t) * e->n_items));
@@ -265,6 +294,26 @@ int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int
     pl.blk_nnz[b] = (int64_t)nnz_at[b + 1] - nnz_at[b];
     pl.blk_rat_off[b] = nnz_at[b];
   }
+  {  // hottest item row of every block: its share of the block's ratings bounds the useful concurrency.
+     // Item counts are over the locally uploaded rows; they are spread over the user parts present here.
+    std::vector<int32_t> part_max((size_t)P, 0);
+    for (int i = 0; i < e->n_items; i++)
+      if (item_part[i] >= 0 && item_part[i] < P && !pl.item_count.empty())
+        part_max[item_part[i]] = std::max(part_max[item_part[i]], pl.item_count[i]);
+    int local_parts = 0;
+    for (int a = 0; a < P; a++) {
+      int64_t t = 0;
+      for (int b = 0; b < P; b++) t += pl.blk_nnz[(size_t)a * P + b];
+      if (t > 0) local_parts++;
+    }
+    pl.blk_hot_share.assign((size_t)P * P, 0.0);
+    for (int a = 0; a < P; a++)
+      for (int b = 0; b < P; b++) {
+        const int64_t bn = pl.blk_nnz[(size_t)a * P + b];
+        if (bn > 0)
+          pl.blk_hot_share[(size_t)a * P + b] = std::min(1.0, (double)part_max[b] / std::max(local_parts, 1) / (double)bn);
+      }
+  }
   size_t ns = (size_t)(nseg > 0 ? nseg : 1);
   MFB_CUDA(cudaMalloc(&pl.seg_user, sizeof(int32_t) * ns));
   MFB_CUDA(cudaMalloc(&pl.seg_start, sizeof(int32_t) * ns));
@@ -322,7 +371,7 @@ struct SgdArgs {
   int32_t rat_cum[kMaxBlocks + 1];
 };
 
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
   x += 0x9E3779B97F4A7C15ull;
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
   x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
@@ -730,9 +779,22 @@ int sgd_subepoch_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int va
 #undef MFB_PICK
 }
 
+// keyed permutation parameters of one launch: a fresh order per (seed, epoch, band)
+static void fill_perm(SgdArgs &a, int64_t n, uint64_t seed, uint64_t counter, uint64_t salt) {
+  a.n = n;
+  a.perm_bits = 1;
+  while (((int64_t)1 << a.perm_bits) < n) a.perm_bits++;
+  uint64_t h = seed * 0x9E3779B97F4A7C15ull + counter * 0xD1B54A32D192ED03ull + salt * 0xA24BAED4963EE407ull + 0x2545F4914F6CDD1Dull;
+  for (int r = 0; r < 3; r++) {
+    h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+    a.perm_mul[r] = (uint32_t)(h >> 7) | 1u;
+    a.perm_add[r] = (uint32_t)(h >> 33);
+  }
+}
+
 int sgd_flat_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int variant, float lr, float ureg, float ireg,
                     uint64_t seed, uint64_t counter) {
-  const SgdPlan &pl = e->sgd;
+  SgdPlan &pl = e->sgd;
   SgdArgs a;
   fill_common(e, a, lr, ureg, ireg, seed, counter);
   a.nb = nb; a.max_cnt = 0; a.total = 0;
@@ -742,18 +804,8 @@ int sgd_flat_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int varian
     a.rat_off[i] = (int32_t)pl.blk_rat_off[bid];
     a.rat_cum[i + 1] = a.rat_cum[i] + (int32_t)pl.blk_nnz[bid];
   }
-  a.n = a.rat_cum[nb];
-  if (a.n == 0) return 0;
-  // a fresh keyed permutation of [0, n) per (seed, epoch): the reference reshuffles every epoch
-  const int64_t n = a.n;
-  a.perm_bits = 1;
-  while (((int64_t)1 << a.perm_bits) < n) a.perm_bits++;
-  uint64_t h = seed * 0x9E3779B97F4A7C15ull + counter * 0xD1B54A32D192ED03ull + 0x2545F4914F6CDD1Dull;
-  for (int r = 0; r < 3; r++) {
-    h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
-    a.perm_mul[r] = (uint32_t)(h >> 7) | 1u;
-    a.perm_add[r] = (uint32_t)(h >> 33);
-  }
+  const int64_t n_all = a.rat_cum[nb];
+  if (n_all == 0) return 0;
   const int nq = a.nq;
   // The shuffled kernel reads both rows right before it adds its increments, so concurrency only
   // turns the updates of a hot row into a mini-batch of c = (ratings in flight) x (the row's share
@@ -765,20 +817,54 @@ int sgd_flat_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int varian
   // from their 0.01-scale start, and on a small matrix a few hundred stale updates are a visible
   // share of that growth (measured: +10 % RMSE after epoch 0 with 0.1 % of a 240 k-rating epoch in
   // flight, < 0.5 % with 0.02 %).  On the bench matrix this bound is 20 k workers, i.e. inactive.
+  // Stratified plans: the hottest row's share is taken inside the scheduled blocks (an item's ratings
+  // are concentrated in one item block), the in-flight bound against all the ratings this engine trains.
+  double hot_share = pl.hot_item_share;
+  if (!pl.blk_hot_share.empty()) {
+    hot_share = 0.0;
+    for (int i = 0; i < nb; i++)
+      hot_share = std::max(hot_share, pl.blk_hot_share[(size_t)blocks[2 * i] * pl.P + blocks[2 * i + 1]] *
+                                          (double)pl.blk_nnz[(size_t)blocks[2 * i] * pl.P + blocks[2 * i + 1]] / (double)n_all);
+  }
   double hot_cap = e->opt_sgd_flat_hot_lr / std::max((double)lr, 1e-12);
-  if (pl.hot_item_share > 0)
-    hot_cap = std::min(hot_cap, std::max(e->opt_sgd_flat_inflight_frac * (double)n, 8.0) * pl.hot_item_share);
+  if (hot_share > 0)
+    hot_cap = std::min(hot_cap, std::max(e->opt_sgd_flat_inflight_frac * (double)std::max<int64_t>(pl.nnz, n_all), 8.0) * hot_share);
   const double saved_cap = e->opt_sgd_max_hot_inflight;
   e->opt_sgd_max_hot_inflight = hot_cap;
   struct Restore { mfb_engine *e; double v; ~Restore() { e->opt_sgd_max_hot_inflight = v; } } restore{e, saved_cap};
-#define MFB_PICK(G, VPL) return launch_flat<G, VPL>(e, a, variant, pick_workers(e, G, n, pl.hot_item_share, 1))
-  if (nq <= 2) MFB_PICK(2, 1);
-  if (nq <= 4) MFB_PICK(4, 1);
-  if (nq <= 8) MFB_PICK(8, 1);
-  if (nq <= 16) MFB_PICK(16, 1);
-  if (nq <= 32) MFB_PICK(32, 1);
-  MFB_PICK(32, 2);
+  auto launch = [&](const SgdArgs &b) -> int {
+#define MFB_PICK(G, VPL) return launch_flat<G, VPL>(e, b, variant, pick_workers(e, G, n_all, hot_share, 1))
+    if (nq <= 2) MFB_PICK(2, 1);
+    if (nq <= 4) MFB_PICK(4, 1);
+    if (nq <= 8) MFB_PICK(8, 1);
+    if (nq <= 16) MFB_PICK(16, 1);
+    if (nq <= 32) MFB_PICK(32, 1);
+    MFB_PICK(32, 2);
 #undef MFB_PICK
+  };
+  // User bands (option sgd_flat_band_mb, off by default): the epoch visits the ratings band by band, in a
+  // fresh random order inside each band and a rotated band order per epoch, so that a band's user rows
+  // stay in the 126 MB L2.  Measured on the bench matrix (gpurun_out/band_sweep.log, profiles/): only
+  // 3-6 % faster (the kernel is bound by latency and L2 reductions, not by the U misses) and the
+  // validation curve leaves the reference's (a uniformly shuffled epoch, modelMF.cpp:76-81) by up to
+  // 10 % at equal epochs — hence not the default.
+  const int nbands = (nb == 1 && pl.P == 1) ? (int)pl.band_rat_off.size() - 1 : 0;
+  if (nbands > 1) {
+    const int first = (int)(mix64(seed ^ (counter * 0x9E3779B97F4A7C15ull)) % (uint64_t)nbands);
+    for (int k = 0; k < nbands; k++) {
+      const int b = (first + k) % nbands;
+      const int64_t lo = pl.band_rat_off[b], n = pl.band_rat_off[b + 1] - lo;
+      if (n <= 0) continue;
+      SgdArgs c = a;
+      c.rat_off[0] = (int32_t)lo;
+      c.rat_cum[1] = (int32_t)n;
+      fill_perm(c, n, seed, counter, (uint64_t)b + 1);
+      MFB_TRY(launch(c));
+    }
+    return 0;
+  }
+  fill_perm(a, n_all, seed, counter, 0);
+  return launch(a);
 }
 
 }  // namespace mfb

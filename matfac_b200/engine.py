@@ -28,6 +28,8 @@ SYMBOLS = [
     "mfb_ccdpp_begin", "mfb_ccdpp_rank1", "mfb_ccdpp_end", "mfb_eval", "mfb_snapshot_best",
     "mfb_restore_best", "mfb_event_record", "mfb_event_elapsed_ms", "mfb_device_factors", "mfb_stream",
     "mfb_pack_rows", "mfb_unpack_rows", "mfb_set_row_range",
+    "mfb_comm_init", "mfb_comm_connect", "mfb_comm_barrier", "mfb_comm_error", "mfb_dsgd_push_block",
+    "mfb_comm_wait_block", "mfb_comm_allgather_rows",
 ]
 
 
@@ -87,6 +89,13 @@ def load_library():
     L.mfb_pack_rows.argtypes = [vp, C.c_int, vp, i32, vp]
     L.mfb_unpack_rows.argtypes = [vp, C.c_int, vp, i32, vp]
     L.mfb_set_row_range.argtypes = [vp, C.c_int, i32, i32]
+    L.mfb_comm_init.argtypes = [vp, i32, i32, vp, C.POINTER(i64)]
+    L.mfb_comm_connect.argtypes = [vp, vp, i64]
+    L.mfb_comm_barrier.argtypes = [vp]
+    L.mfb_comm_error.argtypes = [vp, C.POINTER(i32)]
+    L.mfb_dsgd_push_block.argtypes = [vp, i32, i32, u64]
+    L.mfb_comm_wait_block.argtypes = [vp, i32, u64]
+    L.mfb_comm_allgather_rows.argtypes = [vp, C.c_int, vp, i32, i32]
     _lib = L
     return L
 
@@ -258,6 +267,39 @@ class Engine:
 
     def set_row_range(self, side, begin, end):
         self._check(self.L.mfb_set_row_range(self.h, side, begin, end))
+
+    # ---- peer-memory exchange (one engine per rank of one node) ----
+    def comm_init(self, rank, world) -> bytes:
+        buf = (C.c_uint8 * 512)()
+        n = C.c_int64()
+        self._check(self.L.mfb_comm_init(self.h, rank, world, buf, C.byref(n)))
+        return bytes(buf[: n.value])
+
+    def comm_connect(self, blobs):
+        """blobs: the handle blobs of all ranks in rank order (e.g. from all_gather_object)."""
+        data = b"".join(blobs)
+        buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+        self._check(self.L.mfb_comm_connect(self.h, buf, len(data)))
+
+    def comm_barrier(self):
+        self._check(self.L.mfb_comm_barrier(self.h))
+
+    def comm_error(self) -> bool:
+        v = C.c_int32()
+        self._check(self.L.mfb_comm_error(self.h, C.byref(v)))
+        return bool(v.value)
+
+    def dsgd_push_block(self, item_part, dst_rank, seq):
+        self._check(self.L.mfb_dsgd_push_block(self.h, item_part, dst_rank, seq))
+
+    def comm_wait_block(self, src_rank, seq):
+        self._check(self.L.mfb_comm_wait_block(self.h, src_rank, seq))
+
+    def comm_allgather_rows(self, side, ids=None, first=0, n=0):
+        ids = _arr(ids, np.int32)
+        if ids is not None:
+            n = ids.shape[0]
+        self._check(self.L.mfb_comm_allgather_rows(self.h, side, _p(ids), first, n))
 
 
 def launch_count() -> int:
