@@ -45,6 +45,7 @@ SHAPE = (480_189, 17_770, 100_480_507)
 # its NaN guard (restore + halve, model.cpp:1487-1498) — measured with the oracle, see DESIGN.md
 HP = dict(lr=0.002, ureg=0.05, ireg=0.05)
 FALLBACK_HBM_GBS = 6650.0
+ITEM_SHARE_CAP = 232_944 / 100_480_507
 # dram__bytes_read.sum + dram__bytes_write.sum of the SGD kernel launches of one epoch (profiles/r1_sgd_flat.md)
 DRAM_TRAFFIC_BYTES_PER_EPOCH = None
 
@@ -68,6 +69,11 @@ def gen_problem(n_users, n_items, nnz, seed, device):
         return w / w.sum()
 
     pu, pi = zipf(n_users, 0.9), zipf(n_items, 1.05)
+    # head of the item distribution as in the real Netflix Prize data: the most-rated title holds
+    # 232,944 of 100,480,507 ratings (0.232 %); an uncapped Zipf(1.05) head would hold twice that
+    for _ in range(8):
+        pi = pi.clamp(max=ITEM_SHARE_CAP)
+        pi = pi / pi.sum()
     ci = torch.cumsum(pi, 0)
     total = int(nnz * 1.01)
     keys = torch.empty(0, dtype=torch.int64, device=dev)
@@ -329,9 +335,8 @@ def main():
         # blocks; after every sub-epoch the updated item block is stored straight into the next owner's V
         # over NVLink by a kernel and ordered by device-side sequence flags (matfac_b200/csrc/comm.cu)
         from matfac_b200 import dsgd
-        prng = np.random.default_rng(7)
-        user_part = prng.integers(0, P, size=n_users).astype(np.int32)
-        item_part = prng.integers(0, P, size=n_items).astype(np.int32)
+        user_part = dsgd.balanced_partition(np.diff(ptr), P)
+        item_part = dsgd.balanced_partition(np.bincount(ind, minlength=n_items), P)
         mine = user_part == rank
 
         def local_rows(t):

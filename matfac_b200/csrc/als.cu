@@ -68,89 +68,182 @@ struct AlsSmem {
   static constexpr size_t bytes = sizeof(float) * total_floats;
 };
 
-// Cholesky of the register-tiled matrix (lower triangle meaningful), L written to shared
-// memory, then L L^T x = b solved by warp 0; x left in sm_b.
+// ---- blocked Cholesky + both triangular solves on the register-tiled matrix ---------------------
+// The 16 x 16 thread grid holds A as TR x TR tiles: thread (tx, ty) owns rows tile_idx(tx, .) and
+// columns tile_idx(ty, .) (A is symmetric, so the accumulation's acc[i][j] is read as T(a, b) =
+// acc[b][a]).  Right-looking block algorithm over the 16 tile columns j (a symmetric permutation of
+// the matrix, which an SPD factorisation does not mind):
+//   1. thread (j, j) factors its diagonal tile in registers and forward-substitutes its slice of the
+//      right-hand side (the rhs rides along as one more row of the matrix);
+//   2. threads (R > j, C = j) — half a warp — solve their tile against L_jj^T and publish it;
+//   3. threads (R >= C > j) subtract P_R P_C^T from their tile, diagonal threads also update the rhs.
+// Two barriers per tile column instead of one per scalar column; the strictly-lower tiles keep L in
+// registers, so the backward substitution L^T x = y needs only the 16 x TR vector in shared memory.
+template <int N>
+__device__ __forceinline__ void lds_vec(const float *p, float (&o)[N]) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < N / 4; q++) {
+      const float4 v = *reinterpret_cast<const float4 *>(p + 4 * q);
+      o[4 * q] = v.x; o[4 * q + 1] = v.y; o[4 * q + 2] = v.z; o[4 * q + 3] = v.w;
+    }
+  } else if constexpr (N == 2) {
+    const float2 v = *reinterpret_cast<const float2 *>(p);
+    o[0] = v.x; o[1] = v.y;
+  } else {
+#pragma unroll
+    for (int q = 0; q < N; q++) o[q] = p[q];
+  }
+}
+template <int N>
+__device__ __forceinline__ void sts_vec(float *p, const float (&o)[N]) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < N / 4; q++)
+      *reinterpret_cast<float4 *>(p + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+  } else if constexpr (N == 2) {
+    *reinterpret_cast<float2 *>(p) = make_float2(o[0], o[1]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < N; q++) p[q] = o[q];
+  }
+}
+
+template <int TR>
+struct CholScratch {  // floats, carved from the (by then free) L / tile region
+  static constexpr int T2 = TR * TR;
+  static constexpr int TS = T2 + 4;                       // padded tile stride: conflict-free 128-bit loads
+  static constexpr int off_pan = 0;                       // [2][16][TS] panel tiles, transposed
+  static constexpr int off_dg = 2 * 16 * TS;              // [2][T2 + TR] L_jj and 1 / diag
+  static constexpr int off_y = off_dg + 2 * (T2 + TR);    // [16][TR] y, then z, then x
+  static constexpr int total = off_y + 16 * TR;
+};
+
+#define MFB_T(a, b) acc[b][a]
 template <int TR, class S>
 __device__ __forceinline__ void chol_solve(float (&acc)[TR][TR], float *sm, int tx, int ty) {
-  constexpr int RP = S::RP, LDL = S::LDL;
-  float *Lm = sm + S::off_L, *colbuf = sm + S::off_col, *bv = sm + S::off_b;
-  const int tid = ty * 16 + tx;
-  constexpr int NH = TR <= 4 ? 1 : TR / 4;  // strided groups
-  constexpr int IW = TR <= 4 ? TR : 4;      // local columns per group
-  int step = 0;
+  using K = CholScratch<TR>;
+  static_assert(K::total <= S::RP * S::LDL, "Cholesky scratch must fit the L region");
+  float *pan = sm + S::off_L + K::off_pan, *dg = sm + S::off_L + K::off_dg, *yb = sm + S::off_L + K::off_y;
+  float *bv = sm + S::off_b;
+  const int R = tx, C = ty;
+  const bool on_diag = R == C;
+  float rhs[TR], dinv[TR];
+  __syncthreads();  // the right-hand side is complete, the L / tile region is free
 #pragma unroll
-  for (int h = 0; h < NH; h++) {
-    for (int kb = 0; kb < 16; kb++) {
+  for (int a = 0; a < TR; a++) {
+    rhs[a] = on_diag ? bv[tile_idx<TR>(R, a)] : 0.f;
+    dinv[a] = 0.f;
+  }
+  for (int j = 0; j < 16; j++) {
+    float *pj = pan + (j & 1) * 16 * K::TS;
+    float *dj = dg + (j & 1) * (K::T2 + TR);
+    if (on_diag && R == j) {
 #pragma unroll
-      for (int i4 = 0; i4 < IW; i4++, step++) {
-        const int ic = h * 4 + i4;  // static local column (for TR <= 4: h = 0, ic = i4)
-        const int k = tile_idx<TR>(kb, ic);
-        float *cb = colbuf + (step & 1) * RP;
-        if (tx == kb) {
+      for (int c = 0; c < TR; c++) {
+        const float d = MFB_T(c, c);
+        float r = d > 0.f ? rsqrtf(d) : 0.f;
+        r = r * fmaf(-0.5f * d * r, r, 1.5f);  // one Newton step on the hardware approximation
+        dinv[c] = r;
+        MFB_T(c, c) = d * r;
+        rhs[c] *= r;
 #pragma unroll
-          for (int i = 0; i < TR; i++) cb[tile_idx<TR>(ty, i)] = acc[i][ic];
+        for (int a = c + 1; a < TR; a++) {
+          MFB_T(a, c) *= r;
+          rhs[a] = fmaf(-MFB_T(a, c), rhs[c], rhs[a]);
         }
-        __syncthreads();
-        const float d = cb[k];
-        const float inv = d > 0.f ? 1.0f / d : 0.f;
-        if (tid < RP && tid >= k) Lm[tid * LDL + k] = d > 0.f ? cb[tid] / sqrtf(d) : 0.f;
-        float cj[TR];
 #pragma unroll
-        for (int j = 0; j < TR; j++) cj[j] = cb[tile_idx<TR>(tx, j)];
+        for (int a = c + 1; a < TR; a++)
 #pragma unroll
-        for (int i = 0; i < TR; i++) {
-          const float s = cb[tile_idx<TR>(ty, i)] * inv;
+          for (int b = c + 1; b <= a; b++) MFB_T(a, b) = fmaf(-MFB_T(a, c), MFB_T(b, c), MFB_T(a, b));
+      }
 #pragma unroll
-          for (int j = 0; j < TR; j++) acc[i][j] = fmaf(-s, cj[j], acc[i][j]);
+      for (int a = 0; a < TR; a++) {
+        float row[TR];
+#pragma unroll
+        for (int b = 0; b < TR; b++) row[b] = MFB_T(a, b);
+        sts_vec<TR>(dj + a * TR, row);
+      }
+      sts_vec<TR>(dj + K::T2, dinv);
+      sts_vec<TR>(yb + j * TR, rhs);
+    }
+    __syncthreads();
+    if (C == j && R > j) {
+      float L[TR][TR], di[TR];
+#pragma unroll
+      for (int a = 0; a < TR; a++) lds_vec<TR>(dj + a * TR, L[a]);
+      lds_vec<TR>(dj + K::T2, di);
+#pragma unroll
+      for (int a = 0; a < TR; a++)
+#pragma unroll
+        for (int c = 0; c < TR; c++) {
+          float sacc = MFB_T(a, c);
+#pragma unroll
+          for (int k = 0; k < c; k++) sacc = fmaf(-MFB_T(a, k), L[c][k], sacc);
+          MFB_T(a, c) = sacc * di[c];
+        }
+#pragma unroll
+      for (int c = 0; c < TR; c++) {
+        float col[TR];
+#pragma unroll
+        for (int a = 0; a < TR; a++) col[a] = MFB_T(a, c);
+        sts_vec<TR>(pj + R * K::TS + c * TR, col);
+      }
+    }
+    __syncthreads();
+    if (C > j && R >= C) {
+      float yj[TR];
+#pragma unroll
+      for (int c = 0; c < TR; c++) yj[c] = 0.f;
+      if (on_diag) lds_vec<TR>(yb + j * TR, yj);
+#pragma unroll
+      for (int c = 0; c < TR; c++) {
+        float pr[TR], pc[TR];
+        lds_vec<TR>(pj + R * K::TS + c * TR, pr);
+        lds_vec<TR>(pj + C * K::TS + c * TR, pc);
+#pragma unroll
+        for (int a = 0; a < TR; a++) {
+#pragma unroll
+          for (int b = 0; b < TR; b++) MFB_T(a, b) = fmaf(-pr[a], pc[b], MFB_T(a, b));
+          rhs[a] = fmaf(-pr[a], yj[c], rhs[a]);
         }
       }
     }
   }
-  __syncthreads();
-  if (tid < 32) {
-    const int lane = tid;
-    constexpr int PER = (RP + 31) / 32;
-    // forward: L y = b (column oriented)
-    float bl[PER];
+  // L^T x = y, from the last tile column backwards
+  for (int i = 15; i >= 0; i--) {
+    if (on_diag && R == i) {
+      float z[TR], x[TR];
+      lds_vec<TR>(yb + i * TR, z);
 #pragma unroll
-    for (int q = 0; q < PER; q++) bl[q] = (q * 32 + lane) < RP ? bv[q * 32 + lane] : 0.f;
-    for (int k = 0; k < RP; k++) {
-      const float diag = Lm[k * LDL + k];
-      float yk = 0.f;
+      for (int c = TR - 1; c >= 0; c--) {
+        float sacc = z[c];
 #pragma unroll
-      for (int q = 0; q < PER; q++)
-        if ((k >> 5) == q) yk = bl[q];
-      yk = __shfl_sync(0xFFFFFFFFu, yk, k & 31);
-      yk = diag != 0.f ? yk / diag : 0.f;
-#pragma unroll
-      for (int q = 0; q < PER; q++) {
-        const int i = q * 32 + lane;
-        if (i == k) bl[q] = yk;
-        else if (i > k && i < RP) bl[q] = fmaf(-Lm[i * LDL + k], yk, bl[q]);
+        for (int a = c + 1; a < TR; a++) sacc = fmaf(-MFB_T(a, c), x[a], sacc);
+        x[c] = sacc * dinv[c];
       }
+      sts_vec<TR>(yb + i * TR, x);
+#pragma unroll
+      for (int c = 0; c < TR; c++) bv[tile_idx<TR>(i, c)] = x[c];
     }
-    // backward: L^T x = y (row oriented)
-    for (int k = RP - 1; k >= 0; k--) {
-      const float diag = Lm[k * LDL + k];
-      float xk = 0.f;
+    __syncthreads();
+    if (R == i && C < i) {
+      float x[TR], z[TR];
+      lds_vec<TR>(yb + i * TR, x);
+      lds_vec<TR>(yb + C * TR, z);
 #pragma unroll
-      for (int q = 0; q < PER; q++)
-        if ((k >> 5) == q) xk = bl[q];
-      xk = __shfl_sync(0xFFFFFFFFu, xk, k & 31);
-      xk = diag != 0.f ? xk / diag : 0.f;
+      for (int c = 0; c < TR; c++) {
+        float sacc = z[c];
 #pragma unroll
-      for (int q = 0; q < PER; q++) {
-        const int i = q * 32 + lane;
-        if (i == k) bl[q] = xk;
-        else if (i < k) bl[q] = fmaf(-Lm[k * LDL + i], xk, bl[q]);
+        for (int a = 0; a < TR; a++) sacc = fmaf(-MFB_T(a, c), x[a], sacc);
+        z[c] = sacc;
       }
+      sts_vec<TR>(yb + C * TR, z);
     }
-#pragma unroll
-    for (int q = 0; q < PER; q++)
-      if ((q * 32 + lane) < RP) bv[q * 32 + lane] = bl[q];
+    __syncthreads();
   }
-  __syncthreads();
 }
+#undef MFB_T
 
 template <int TR>
 __device__ __forceinline__ void add_reg_diag(float (&acc)[TR][TR], int tx, int ty, int rank, float reg) {

@@ -30,6 +30,27 @@ def random_schedule(world: int, n_steps: int, seed: int) -> np.ndarray:
     return np.stack([rng.permutation(world) for _ in range(n_steps)]).astype(np.int32)
 
 
+def balanced_partition(weights, P: int) -> np.ndarray:
+    """Longest-processing-time greedy split of ids into P parts of (nearly) equal total weight; ids
+    with weight 0 get part -1 (never trained).  The reference cuts a shuffled id list into equal
+    COUNTS (modelMF.cpp:233-265); with one stratum per GPU the sub-epoch lasts as long as its heaviest
+    block, so the multi-GPU driver balances ratings instead and spreads the heaviest rows over the
+    parts (the hottest item row of a block bounds that block's useful concurrency)."""
+    import heapq
+    w = np.asarray(weights, dtype=np.int64)
+    part = np.full(w.shape[0], -1, np.int32)
+    order = np.argsort(-w, kind="stable")
+    heap = [(0, p) for p in range(P)]
+    heapq.heapify(heap)
+    for i in order:
+        if w[i] <= 0:
+            break
+        load, p = heapq.heappop(heap)
+        part[i] = p
+        heapq.heappush(heap, (load + int(w[i]), p))
+    return part
+
+
 def route(schedule: np.ndarray, t: int, rank: int):
     """(block, dst, src) of `rank` in sub-epoch t: the item part it updates, the rank that needs that
     part in sub-epoch t+1 (-1 at the end of the schedule) and the rank whose sub-epoch t-1 output it

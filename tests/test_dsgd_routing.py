@@ -110,3 +110,16 @@ def test_two_rank_gloo_run_matches_serial_execution(tmp_path, kind):
     out = str(tmp_path / "v.npy")
     mp.spawn(_worker, args=(world, _free_port(), sched, n_items, item_part, world, out), nprocs=world, join=True)
     np.testing.assert_allclose(np.load(out), _serial(sched, world, n_items, item_part, epochs), rtol=0, atol=0)
+
+
+def test_balanced_partition_equalises_ratings_and_spreads_the_head():
+    rng = np.random.default_rng(0)
+    w = rng.zipf(1.3, 5000).clip(max=4000)
+    w[::50] = 0  # ids without ratings are never trained
+    for P in (2, 8):
+        part = dsgd.balanced_partition(w, P)
+        assert np.all(part[w == 0] == -1) and np.all(part[w > 0] >= 0) and part.max() == P - 1
+        loads = np.bincount(part[part >= 0], weights=w[part >= 0], minlength=P)
+        assert loads.max() - loads.min() <= w.max()
+        heavy = np.argsort(-w, kind="stable")[:P]
+        assert sorted(part[heavy]) == list(range(P))  # the P heaviest rows land in P different parts
