@@ -19,7 +19,7 @@
 namespace mfb {
 
 constexpr int kAlsTile = 32;    // factor rows staged per pipeline stage
-constexpr int kAlsChunk = 2048; // ratings per CTA before a row is split
+constexpr int kAlsChunk = 4096; // ratings per CTA before a row is split
 
 struct AlsArgs {
   const float *Fin;  // opposite side's factors [.][ld]
@@ -35,6 +35,7 @@ struct AlsArgs {
   // is stored into all of them, i.e. the all-gather is fused into the solve epilogue
   float *Fpeer[kMaxRanks - 1];
   int n_peer;
+  int seg0;  // first segment of this launch (segments are sorted longest first)
 };
 
 __device__ __forceinline__ void store_solution(const AlsArgs &a, int row, int tid, const float *bv) {
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(256, (TR == 8 ? 2 : 3)) als_gram_solve_kernel(
   float *tile = sm + S::off_tile, *bv = sm + S::off_b, *rate = sm + S::off_rate;
   int *item = reinterpret_cast<int *>(sm + S::off_item);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int seg = blockIdx.x;
+  const int seg = a.seg0 + blockIdx.x;
   const int row = a.seg_row[seg], start = a.seg_start[seg], len = a.seg_len[seg], slot = a.seg_slot[seg];
   const int nq = a.ld >> 2;
 
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(256, 2) als_gram_tc_kernel(const AlsArgs a) {
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid & 15, ty = tid >> 4;
-  const int seg = blockIdx.x;
+  const int seg = a.seg0 + blockIdx.x;
   const int row = a.seg_row[seg], start = a.seg_start[seg], len = a.seg_len[seg], slot = a.seg_slot[seg];
   const int nq = a.ld >> 2;  // 16-byte units per factor row (<= 32)
 
@@ -636,6 +637,96 @@ __global__ void __launch_bounds__(256, 2) als_gram_tc_kernel(const AlsArgs a) {
   store_solution(a, row, tid, bv);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Short rows (fewer ratings than half the padded rank): the same solution through the dual system.
+//   x = (F^T F + reg I)^-1 F^T r  =  F^T (F F^T + reg I)^-1 r          (push-through identity)
+// with F the len x rank matrix of gathered factor rows.  The dual Gram F F^T is len x len, so a user
+// with 20 ratings costs a 32 x 32 factorisation instead of a 128 x 128 one — and most rows of a
+// ratings matrix are short (power-law degrees).  Same tile Cholesky as above on a 16*TR-padded system
+// (padding rows are zero: their diagonal is reg, their right-hand side 0, their alpha 0).
+template <int TR>
+struct AlsDualSmem {
+  static constexpr int RP = 16 * TR;
+  static constexpr int LDL = RP + 1;
+  static constexpr int LDF = 132;  // row stride of the staged factor rows: 128 + 4 keeps 128-bit loads conflict free
+  static constexpr int off_F = 0;
+  static constexpr int off_L = off_F + RP * LDF;
+  static constexpr int off_b = off_L + (RP * LDL + 3) / 4 * 4;
+  static constexpr int total_floats = off_b + RP;
+  static constexpr size_t bytes = sizeof(float) * total_floats;
+};
+
+template <int TR>
+__global__ void __launch_bounds__(256, 4) als_dual_kernel(const AlsArgs a) {
+  using S = AlsDualSmem<TR>;
+  constexpr int RP = S::RP, LDF = S::LDF;
+  extern __shared__ __align__(16) float sm[];
+  float *F = sm + S::off_F, *bv = sm + S::off_b;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int seg = a.seg0 + blockIdx.x;
+  const int row = a.seg_row[seg], start = a.seg_start[seg], len = a.seg_len[seg];
+  const int nq = a.ld >> 2;
+  // stage the rated factor rows (rating > 0, modelMF.cpp:819); staged row m sits in tile (m % 16),
+  // element m / 16, i.e. at position (m % 16) * TR + m / 16 of the right-hand side
+  for (int i = tid; i < RP * 32; i += 256) {
+    const int m = i >> 5, q = i & 31;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m < len && q < nq && __ldg(a.val + start + m) > 0.f)
+      v = __ldg(reinterpret_cast<const float4 *>(a.Fin + (size_t)__ldg(a.ind + start + m) * a.ld) + q);
+    *reinterpret_cast<float4 *>(F + m * LDF + q * 4) = v;
+  }
+  if (tid < RP) {
+    float r = 0.f;
+    if (tid < len) r = fmaxf(__ldg(a.val + start + tid), 0.f);
+    bv[(tid & 15) * TR + (tid >> 4)] = r;
+  }
+  __syncthreads();
+  float acc[TR][TR];
+#pragma unroll
+  for (int i = 0; i < TR; i++)
+#pragma unroll
+    for (int j = 0; j < TR; j++) acc[i][j] = 0.f;
+  for (int q = 0; q < nq; q++) {
+    float4 fa[TR], fb[TR];
+#pragma unroll
+    for (int i = 0; i < TR; i++) {
+      fa[i] = *reinterpret_cast<const float4 *>(F + (i * 16 + ty) * LDF + q * 4);
+      fb[i] = *reinterpret_cast<const float4 *>(F + (i * 16 + tx) * LDF + q * 4);
+    }
+#pragma unroll
+    for (int i = 0; i < TR; i++)
+#pragma unroll
+      for (int j = 0; j < TR; j++) {
+        acc[i][j] = fmaf(fa[i].x, fb[j].x, acc[i][j]);
+        acc[i][j] = fmaf(fa[i].y, fb[j].y, acc[i][j]);
+        acc[i][j] = fmaf(fa[i].z, fb[j].z, acc[i][j]);
+        acc[i][j] = fmaf(fa[i].w, fb[j].w, acc[i][j]);
+      }
+  }
+  if (tx == ty) {
+#pragma unroll
+    for (int i = 0; i < TR; i++) acc[i][i] += a.reg;
+  }
+  chol_solve<TR, S>(acc, sm, tx, ty);  // alpha, in the right-hand side's layout
+  if (tid < a.ld) {
+    float x = 0.f;
+    for (int m = 0; m < RP; m++) x = fmaf(bv[(m & 15) * TR + (m >> 4)], F[m * LDF + tid], x);
+    if (tid >= a.rank) x = 0.f;
+    a.Fout[(size_t)row * a.ld + tid] = x;
+    for (int p = 0; p < a.n_peer; p++) a.Fpeer[p][(size_t)row * a.ld + tid] = x;
+  }
+}
+
+template <int TRD>
+static int launch_dual(mfb_engine *e, AlsArgs b, int seg0, int count) {
+  if (count <= 0) return 0;
+  using S = AlsDualSmem<TRD>;
+  MFB_CUDA(cudaFuncSetAttribute(als_dual_kernel<TRD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
+  b.seg0 = seg0;
+  MFB_LAUNCH((als_dual_kernel<TRD>), count, 256, S::bytes, e->stream, b);
+  return 0;
+}
+
 template <int TR>
 static int launch_als(mfb_engine *e, const AlsArgs &a, const SegPlan &sp) {
   using S = AlsSmem<TR>;
@@ -654,11 +745,21 @@ static int launch_als(mfb_engine *e, const AlsArgs &a, const SegPlan &sp) {
   }
   AlsArgs b = a;
   b.ws = e->als_ws;
+  // segments are sorted longest first: [0, n_primal) go through the rank x rank normal equations, the
+  // shorter ones through the dual system whose padded size is at most half of that
+  const int n64 = sp.n_longer[0], n32 = sp.n_longer[1], n16 = sp.n_longer[2];
+  int n_primal = sp.n_seg;
+  if (e->opt_als_dual) n_primal = TR == 8 ? n64 : TR == 4 ? n32 : TR == 2 ? n16 : sp.n_seg;
   if (TR == 8 && e->opt_als_tensor_cores) {
     MFB_CUDA(cudaFuncSetAttribute(als_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AlsTcSmem::bytes));
-    if (sp.n_seg > 0) MFB_LAUNCH(als_gram_tc_kernel, sp.n_seg, 256, AlsTcSmem::bytes, e->stream, b);
-  } else if (sp.n_seg > 0) {
-    MFB_LAUNCH((als_gram_solve_kernel<TR>), sp.n_seg, 256, S::bytes, e->stream, b);
+    if (n_primal > 0) MFB_LAUNCH(als_gram_tc_kernel, n_primal, 256, AlsTcSmem::bytes, e->stream, b);
+  } else if (n_primal > 0) {
+    MFB_LAUNCH((als_gram_solve_kernel<TR>), n_primal, 256, S::bytes, e->stream, b);
+  }
+  if (n_primal < sp.n_seg) {
+    if (TR == 8) MFB_TRY(launch_dual<4>(e, b, n64, n32 - n64));
+    if (TR >= 4) MFB_TRY(launch_dual<2>(e, b, n32, n16 - n32));
+    if (TR >= 2) MFB_TRY(launch_dual<1>(e, b, n16, sp.n_seg - n16));
   }
   if (sp.n_multi > 0) MFB_LAUNCH((als_solve_ws_kernel<TR>), sp.n_multi, 256, S::bytes, e->stream, b);
   return 0;
@@ -689,7 +790,7 @@ int als_debug_gram(mfb_engine *e, int side, int32_t row, float *out, int32_t *rp
   a.ind = side == MFB_USER ? m.rowind : m.colind;
   a.val = side == MFB_USER ? m.rowval : m.colval;
   a.seg_row = d; a.seg_start = d + 1; a.seg_len = d + 2; a.seg_slot = d + 3; a.multi_row = d + 4;
-  a.ws = ws; a.reg = 0.f; a.n_peer = 0;
+  a.ws = ws; a.reg = 0.f; a.n_peer = 0; a.seg0 = 0;
   if (RP == 128 && e->opt_als_tensor_cores) {
     MFB_CUDA(cudaFuncSetAttribute(als_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AlsTcSmem::bytes));
     MFB_LAUNCH(als_gram_tc_kernel, 1, 256, AlsTcSmem::bytes, e->stream, a);
@@ -732,6 +833,7 @@ int als_half_step_launch(mfb_engine *e, int side, float reg) {
   a.ws = nullptr;
   a.reg = reg;
   a.n_peer = 0;
+  a.seg0 = 0;
   const Comm &c = e->comm;
   if (c.connected)
     for (int p = 0; p < c.world; p++)

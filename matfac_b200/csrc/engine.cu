@@ -10,6 +10,7 @@
 
 #include <cub/cub.cuh>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 
@@ -119,7 +120,7 @@ __global__ void gather4_kernel(const int32_t *__restrict__ perm, int32_t n, cons
 }
 
 int build_seg_plan(mfb_engine *e, const int64_t *ptr, int32_t nrows, const uint8_t *mask, int32_t row_lo,
-                   int32_t row_hi, int32_t chunk, SegPlan *out) {
+                   int32_t row_hi, int32_t chunk, SegPlan *out, bool by_length) {
   out->release();
   if (row_hi > nrows) row_hi = nrows;
   int32_t n = row_hi - row_lo;
@@ -163,6 +164,19 @@ int build_seg_plan(mfb_engine *e, const int64_t *ptr, int32_t nrows, const uint8
   MFB_LAUNCH(seg_fill_kernel, gb, tb, 0, st, ptr, row_lo, n, chunk, nch, off, moff, u_row, u_start, u_len, u_slot,
              out->multi_row);
   int gs = (ns + tb - 1) / tb;
+  if (!by_length) {
+    // memory order: consecutive warps stream consecutive rows (the pure streaming passes of CCD++ and
+    // the evaluation want DRAM-page locality more than longest-first scheduling)
+    MFB_CUDA(cudaMemcpyAsync(out->row, u_row, sizeof(int32_t) * ns, cudaMemcpyDeviceToDevice, st));
+    MFB_CUDA(cudaMemcpyAsync(out->start, u_start, sizeof(int32_t) * ns, cudaMemcpyDeviceToDevice, st));
+    MFB_CUDA(cudaMemcpyAsync(out->len, u_len, sizeof(int32_t) * ns, cudaMemcpyDeviceToDevice, st));
+    MFB_CUDA(cudaMemcpyAsync(out->slot, u_slot, sizeof(int32_t) * ns, cudaMemcpyDeviceToDevice, st));
+    MFB_CUDA(cudaStreamSynchronize(st));
+    out->max_len = chunk;
+    cudaFree(tmp);
+    cudaFree(nch);
+    return 0;
+  }
   MFB_LAUNCH(iota_kernel, gs, tb, 0, st, idx, ns);
   MFB_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, u_len, k_out, idx, p_out, ns, 0, 32, st));
   MFB_TRY(ensure_scratch(e, tmp_bytes));
@@ -170,7 +184,12 @@ int build_seg_plan(mfb_engine *e, const int64_t *ptr, int32_t nrows, const uint8
   MFB_CUDA(cudaMemcpyAsync(out->len, k_out, sizeof(int32_t) * ns, cudaMemcpyDeviceToDevice, st));
   MFB_LAUNCH(gather4_kernel, gs, tb, 0, st, p_out, ns, u_row, u_start, u_slot, out->row, out->start, out->slot);
   MFB_CUDA(cudaMemcpyAsync(&out->max_len, out->len, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  std::vector<int32_t> hl((size_t)ns);
+  MFB_CUDA(cudaMemcpyAsync(hl.data(), out->len, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, st));
   MFB_CUDA(cudaStreamSynchronize(st));
+  const int32_t cuts[3] = {64, 32, 16};
+  for (int k = 0; k < 3; k++)  // lengths are sorted descending
+    out->n_longer[k] = (int32_t)(std::partition_point(hl.begin(), hl.end(), [&](int32_t v) { return v > cuts[k]; }) - hl.begin());
   cudaFree(tmp);
   cudaFree(nch);
   return 0;
@@ -454,6 +473,7 @@ extern "C" int mfb_set_option(mfb_engine *e, const char *name, double value) {
   else if (n == "sgd_atomic") e->opt_sgd_atomic = (int)value;
   else if (n == "sgd_rotate") e->opt_sgd_rotate = (int)value;
   else if (n == "als_tensor_cores") e->opt_als_tensor_cores = (int)value;
+  else if (n == "als_dual") e->opt_als_dual = (int)value;
   else if (n == "sgd_block_order") e->opt_sgd_block_order = (int)value;
   else return mfb::fail("mfb_set_option: unknown option", __FILE__, __LINE__);
   return 0;

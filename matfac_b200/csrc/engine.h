@@ -47,6 +47,7 @@ struct SegPlan {
   int32_t n_seg = 0;
   int32_t n_multi = 0;         // rows split over several segments
   int32_t max_len = 0;
+  int32_t n_longer[3] = {0, 0, 0};  // segments longer than 64 / 32 / 16 ratings (they sort first)
   int32_t *row = nullptr;      // [n_seg]
   int32_t *start = nullptr;    // [n_seg] offset into the index/value arrays
   int32_t *len = nullptr;      // [n_seg]
@@ -133,6 +134,7 @@ struct mfb_engine {
   int opt_sgd_atomic = 1;             // item rows updated by vector reductions (no lost updates)
   int opt_sgd_block_order = 0;        // stratified trainers: 0 = user-major runs (reference order), 1 = shuffled inside the blocks
   int opt_sgd_rotate = 0;             // user runs start at a pseudo-random offset (de-correlates heavy users)
+  int opt_als_dual = 1;               // short rows: solve the len x len dual system instead of rank x rank
   int opt_als_tensor_cores = 1;       // rank > 64: Gram on tcgen05 (3xTF32); 0 = fp32 CUDA-core Gram
   cudaStream_t stream = nullptr;
   cudaEvent_t events[16] = {};
@@ -174,10 +176,11 @@ struct mfb_engine {
 namespace mfb {
 
 int ensure_scratch(mfb_engine *e, size_t bytes);
-// Builds a SegPlan over rows [row_lo,row_hi) of ptr (device int64 [nrows+1]); rows whose mask
+// Builds a SegPlan over rows [row_lo,row_hi) of ptr (device int64 [nrows+1]), sorted longest first
+// (by_length) or left in memory order; rows whose mask
 // byte is set (mask may be null) or that are empty produce no segment.
 int build_seg_plan(mfb_engine *e, const int64_t *ptr, int32_t nrows, const uint8_t *mask, int32_t row_lo,
-                   int32_t row_hi, int32_t chunk, SegPlan *out);
+                   int32_t row_hi, int32_t chunk, SegPlan *out, bool by_length = true);
 
 int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int32_t *item_part);
 int sgd_subepoch_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int variant, float lr, float ureg,

@@ -308,6 +308,33 @@ def test_als_ill_conditioned_rows_are_as_accurate_as_the_reference(rank):
     eng.close()
 
 
+@pytest.mark.parametrize("rank", [24, 64, 128])
+def test_als_short_rows_dual_system_matches_normal_equations(rank):
+    """Rows with fewer ratings than half the padded rank are solved through the dual system
+    F^T (F F^T + reg I)^-1 r; the result must agree with the rank x rank normal equations
+    (modelMF.cpp:806-841) as closely as two fp32 evaluations can, and with the float64 solution."""
+    splits = small_problem(700, 500, 25000, seed=17)
+    tr = splits[0]
+    lens = np.diff(tr.rowptr)
+    assert (lens <= 16).sum() > 20 and ((lens > 16) & (lens <= 64)).sum() > 20
+    om = oracle_model(splits, "mf", rank, maxiter=1, ureg=0.1, ireg=0.1, nthreads=8)
+    eng, _ = make_engine(splits, om, rank)
+    U0, V0 = om.factors()
+    V0 = (V0 * 30).astype(np.float32)  # O(0.3) entries: a Gram that is not dwarfed by the regulariser
+    out = {}
+    for dual in (0, 1):
+        eng.set_option("als_dual", dual)
+        eng.upload_factors(U0, V0)
+        eng.als_half_step(E.USER, 0.1)
+        out[dual], _ = eng.download_factors()
+    truth = _als_f64(tr.rowptr, tr.rowind, tr.rowval, V0, rank, 0.1, tr.nrows)
+    ok = lens > 0
+    e0, e1 = rel_err(out[0][ok], truth[ok]), rel_err(out[1][ok], truth[ok])
+    assert e1 <= 2.0 * e0 + 1e-6, (e0, e1)
+    assert rel_err(out[1][ok], out[0][ok]) < 1e-4
+    eng.close()
+
+
 def test_als_long_rows_are_split():
     """A row longer than the per-CTA chunk goes through the workspace path."""
     from matfac_b200 import synth

@@ -75,6 +75,9 @@ def main():
     out = {"algo": args.algo, "rank": r, "n_users": n_users, "n_items": n_items, "train_nnz": train_nnz}
     if args.algo == "als":
         eng.set_option("als_tensor_cores", args.tc)
+        eng.set_option("als_dual", int(os.environ.get("ALS_DUAL", "1")))
+        lens = np.diff(ptr)
+        out.update(als_dual=int(os.environ.get("ALS_DUAL", "1")), users_le16=int((lens <= 16).sum()), users_le32=int((lens <= 32).sum()), users_le64=int((lens <= 64).sum()))
         eng.als_half_step(E.USER, args.reg)
         eng.als_half_step(E.ITEM, args.reg)  # warm-up epoch (plans are built here)
         eng.sync()
