@@ -47,7 +47,7 @@ HP = dict(lr=0.002, ureg=0.05, ireg=0.05)
 FALLBACK_HBM_GBS = 6650.0
 ITEM_SHARE_CAP = 232_944 / 100_480_507
 # dram__bytes_read.sum + dram__bytes_write.sum of the SGD kernel launches of one epoch (profiles/r1_sgd_flat.md)
-DRAM_TRAFFIC_BYTES_PER_EPOCH = None
+DRAM_TRAFFIC_BYTES_PER_EPOCH = 62.6e9
 
 
 def log(*a):
@@ -137,6 +137,28 @@ def gen_problem(n_users, n_items, nnz, seed, device):
     return dict(n_users=n_users, n_items=n_items, train=tr, val=va)
 
 
+def shared_problem(n_users, n_items, nnz, seed, rank, dist, device):
+    """N > 1: rank 0 generates the matrix and broadcasts it — the torch generator is not bit-reproducible across
+    processes (atomics in unique / scatter), and every rank must partition the SAME matrix."""
+    import torch
+    prob = gen_problem(n_users, n_items, nnz, seed, device) if rank == 0 else None
+    head = torch.zeros(2, dtype=torch.int64, device=device)
+    if rank == 0:
+        head[0], head[1] = int(prob["train"][0][-1]), int(prob["val"][0][-1])
+    dist.broadcast(head, 0)
+    out = {"n_users": n_users, "n_items": n_items}
+    for name, n in (("train", int(head[0])), ("val", int(head[1]))):
+        arrs = []
+        for k, (dt, ln) in enumerate(((torch.int64, n_users + 1), (torch.int32, n), (torch.float32, n))):
+            t = torch.from_numpy(prob[name][k]).to(device) if rank == 0 else torch.empty(ln, dtype=dt, device=device)
+            dist.broadcast(t, 0)
+            arrs.append(t.cpu().numpy())
+            del t
+        out[name] = tuple(arrs)
+    torch.cuda.empty_cache()
+    return out
+
+
 class Mat:
     def __init__(self, nrows, ncols, t):
         self.nrows, self.ncols = nrows, ncols
@@ -203,6 +225,86 @@ def measured_hbm_gbs():
     return FALLBACK_HBM_GBS, "fallback"
 
 
+
+def csc_on_device(n_users, n_items, ptr, ind, val, device):
+    """gk_csr_CreateIndex(mat, GK_CSR_COL) as a stable sort by column (torch, set-up only)."""
+    import torch
+    dev = torch.device(device)
+    ind_d = torch.from_numpy(ind).to(dev)
+    deg = torch.from_numpy(np.diff(ptr)).to(dev)
+    rows = torch.repeat_interleave(torch.arange(n_users, device=dev, dtype=torch.int32), deg)
+    order = torch.sort(ind_d.long() * n_users + rows.long()).indices  # (col, row) ascending == stable by col
+    colind = rows[order].cpu().numpy()
+    colval = torch.from_numpy(val).to(dev)[order].cpu().numpy()
+    cnt = torch.bincount(ind_d.long(), minlength=n_items)
+    colptr = np.zeros(n_items + 1, np.int64)
+    colptr[1:] = torch.cumsum(cnt, 0).cpu().numpy()
+    del ind_d, deg, rows, order, cnt
+    torch.cuda.empty_cache()
+    return colptr, colind, colval
+
+
+def solver_timings(prob, device_index, peak_gbs):
+    """The other trainers of the path on the same matrix (BASELINE.json: 'ALS epoch sec'):
+    ALS at rank 64 and 128, CCD++ (FreqAdap) at rank 64 and the objective pass, CUDA events, one GPU."""
+    from matfac_b200 import engine as E
+    n_users, n_items = prob["n_users"], prob["n_items"]
+    ptr, ind, val = prob["train"]
+    nnz = int(ptr[-1])
+    tr = Mat(n_users, n_items, prob["train"])
+    bad_u = (np.diff(ptr) == 0).astype(np.uint8)
+    cnt_i = np.bincount(ind, minlength=n_items)
+    out = {}
+    for r in (64, 128):
+        rng = np.random.default_rng(1)
+        eng = E.Engine(n_users, n_items, r, device=device_index)
+        eng.upload_csr(E.TRAIN, tr, with_csc=False)
+        eng.build_csc(E.TRAIN)  # gk_csr_CreateIndex on the device
+        eng.set_masks(bad_u, (cnt_i == 0).astype(np.uint8))
+        eng.set_aux(E.MF, np.diff(ptr).astype(np.int32), cnt_i.astype(np.int32))
+        eng.upload_factors(rng.uniform(-0.01, 0.01, (n_users, r)).astype(np.float32),
+                           rng.uniform(-0.01, 0.01, (n_items, r)).astype(np.float32))
+        eng.als_half_step(E.USER, 0.1)
+        eng.als_half_step(E.ITEM, 0.1)  # warm-up epoch: plans are built here
+        ms = []
+        for _ in range(2):
+            eng.event_record(0)
+            eng.als_half_step(E.USER, 0.1)
+            eng.als_half_step(E.ITEM, 0.1)
+            eng.event_record(1)
+            ms.append(eng.event_elapsed_ms(0, 1))
+        m = float(np.median(ms))
+        out[f"als_rank{r}"] = {"epoch_ms": m, "epoch_sec": m * 1e-3, "gram_tflops_algorithmic": 4.0 * r * r * nnz / (m * 1e-3) / 1e12,
+                               "gather_gbs": 2.0 * nnz * r * 4 / (m * 1e-3) / 1e9,
+                               "gram": "tcgen05 kind::tf32 x3 split, fp32 TMEM accumulator" if r > 64 else "fp32 FMA register tiles"}
+        if r == 64:
+            eng.upload_factors(rng.uniform(-0.01, 0.01, (n_users, r)).astype(np.float32),
+                               rng.uniform(-0.01, 0.01, (n_items, r)).astype(np.float32))
+            eng.ccdpp_begin()
+            for k in range(4):
+                eng.ccdpp_rank1(k, True, 5, 0.05, 0.05, 75)
+            eng.event_record(0)
+            for k in range(8):
+                eng.ccdpp_rank1(k, False, 5, 0.05, 0.05, 75)
+            eng.event_record(1)
+            mk = eng.event_elapsed_ms(0, 1) / 8
+            eng.ccdpp_end()
+            gbs = 128.0 * nnz / (mk * 1e-3) / 1e9
+            out["ccdpp_rank64"] = {"ms_per_rank_one_step": mk, "epoch_ms": mk * r, "algorithmic_gbs": gbs, "frac_of_hbm": gbs / peak_gbs,
+                                   "what": "trainCCDPPFreqAdap k-loop body, 128 B per rating per rank-one step (SURVEY 8d)"}
+            for _ in range(2):
+                eng.eval(E.TRAIN, E.CURRENT, E.MF, False, True)
+            eng.event_record(0)
+            for _ in range(3):
+                eng.eval(E.TRAIN, E.CURRENT, E.MF, False, True)
+            eng.event_record(1)
+            me = eng.event_elapsed_ms(0, 1) / 3
+            out["objective_rank64"] = {"ms_per_pass": me, "algorithmic_gbs": (8.0 + 8.0 * r) * nnz / (me * 1e-3) / 1e9,
+                                       "what": "objective + norms over the train matrix, 8 + 8r B per rating; u is reused from registers"}
+        eng.close()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 def cpu_reference_arm(prob, steps, warmup, sample_users=None):
     """Times the reference's OpenMP stratified SGD (ModelMF::trainSGDPar) on the first
@@ -259,7 +361,17 @@ def cpu_reference_arm(prob, steps, warmup, sample_users=None):
 
 
 # ---------------------------------------------------------------------------------------------
+def _protect_stdout():
+    """Libraries (NCCL's version banner, torchrun's OMP notice) write to fd 1; the contract is ONE JSON line on
+    stdout.  Route fd 1 to stderr for the duration of the run and keep the real stdout for the final line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
+    real_stdout = _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -267,7 +379,8 @@ def main():
     ap.add_argument("--impl", default="device", choices=["device", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--no-solvers", action="store_true", help="skip the ALS / CCD++ / objective timings")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -292,7 +405,7 @@ def main():
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "rating-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
         return 0
 
     if not have_cuda:
@@ -305,7 +418,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     t0 = time.time()
-    prob = gen_problem(n_users, n_items, nnz, 20260102, f"cuda:{local_rank}")
+    if world > 1:
+        prob = shared_problem(n_users, n_items, nnz, 20260102, rank, dist, f"cuda:{local_rank}")
+    else:
+        prob = gen_problem(n_users, n_items, nnz, 20260102, f"cuda:{local_rank}")
     ptr, ind, val = prob["train"]
     train_nnz = int(ptr[-1])
     config["train_nnz"] = train_nnz
@@ -477,22 +593,29 @@ def main():
         trp = Mat(n_users, n_items, (h["ptr"], h["ind"], h["val"]))
         h2d = h["ptr"].nbytes + h["ind"].nbytes + h["val"].nbytes + h["U"].nbytes + h["V"].nbytes
         d2h = Uo.nbytes + Vo.nbytes + 64
-        times = []
+        times, parts = [], []
         for s in range(args.e2e_steps + 1):
             eng.sync()
             t1 = time.perf_counter()
             eng.upload_csr(E.TRAIN, trp, with_csc=False)
             eng.upload_factors(h["U"], h["V"])
+            t2 = time.perf_counter()
             eng.sgd_plan(1)
+            t3 = time.perf_counter()
             eng.sgd_epoch_flat(E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, s)
             obj = eng.eval(E.TRAIN, E.CURRENT, E.MF, False, True)
             vr = eng.eval(E.VAL)
+            t4 = time.perf_counter()
             eng.L.mfb_download_factors(eng.h, E.CURRENT, Uo.ctypes.data, RANK, Vo.ctypes.data, RANK)
             eng.sync()
-            times.append(time.perf_counter() - t1)
-        t_e2e = float(np.mean(times[1:]))
+            t5 = time.perf_counter()
+            times.append(t5 - t1)
+            parts.append([t2 - t1, t3 - t2, t4 - t3, t5 - t4])
+        t_e2e = float(np.median(times[1:]))
+        pm = np.median(np.array(parts[1:]), axis=0) * 1e3
         e2e = {"value": train_nnz / t_e2e, "unit": "rating-updates/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e * 1e3,
+               "ms_breakdown": {"upload": float(pm[0]), "plan": float(pm[1]), "epoch_and_eval": float(pm[2]), "download": float(pm[3])},
                "what": "per step: upload CSR + factors from pinned host memory, plan, 1 epoch, objective + val RMSE, download factors"}
 
     cpu_baseline = None
@@ -513,7 +636,14 @@ def main():
         line["cpu_baseline"] = cpu_baseline
     if stratified:
         line["stratified"] = stratified
-    print(json.dumps(line), flush=True)
+    if world == 1 and not args.no_solvers:
+        try:
+            eng.close()
+            torch.cuda.empty_cache()
+            line["solvers"] = solver_timings(prob, local_rank, peak)
+        except Exception as ex:
+            line["solvers"] = {"error": repr(ex)[:300]}
+    print(json.dumps(line), file=real_stdout, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -76,6 +76,13 @@ int mfb_upload_csr(mfb_engine *e, int which, int32_t nrows, int32_t ncols, int64
                    const int64_t *rowptr, const int32_t *rowind, const float *rowval,
                    const int64_t *colptr, const int32_t *colind, const float *colval);
 
+/* Build the column index of an uploaded matrix on the device: gk_csr_CreateIndex(mat, GK_CSR_COL)
+ * (datastruct.cpp:18,51,74) as a stable radix sort by column — colind ascends inside every column, exactly
+ * the arrays the reference's counting sort produces.  n_items + 1 pointers (columns beyond ncols are empty).
+ * mfb_download_csc copies them to the host (colptr int64 [n_items + 1], colind / colval [nnz]). */
+int mfb_build_csc(mfb_engine *e, int which);
+int mfb_download_csc(mfb_engine *e, int which, int64_t *colptr, int32_t *colind, float *colval);
+
 /* invalidUsers / invalidItems (util.cpp:511-544 + modelMF.cpp:40-45) as one byte per id
  * (1 = invalid), n_users resp. n_items entries.  Applied by mfb_eval, ALS and CCD++. */
 int mfb_set_masks(mfb_engine *e, const uint8_t *invalid_users, const uint8_t *invalid_items);
@@ -165,6 +172,13 @@ int mfb_ccdpp_end(mfb_engine *e);
  * weighted != 0, the weighted error of the IFWMF objective.  factors = MFB_CURRENT | MFB_BEST. */
 int mfb_eval(mfb_engine *e, int which, int factors, int variant, int weighted, int want_norms,
              double out[4]);
+
+/* Filtered evaluation in one pass (quartileRMSEs, main.cpp:700-768, which calls Model::RMSE(mat, filtItems, ...)
+ * model.cpp:348-394, ::SE :397-443 and ::RMSEU :446-486 once per part): user_group[n_users] / item_group[n_items]
+ * give every id a group 0..7 or 255 (in no group).  out[((side * 8) + g) * 2 + {0,1}] = sum of squared errors and
+ * count of the ratings (valid user and item) whose item (side 0) resp. user (side 1) is in group g. */
+int mfb_eval_groups(mfb_engine *e, int which, int factors, int variant, const uint8_t *user_group,
+                    const uint8_t *item_group, double out[32]);
 
 /* bestModel = *this (model.cpp:1500-1504) and *this = bestModel (:1492) as device copies */
 int mfb_snapshot_best(mfb_engine *e);

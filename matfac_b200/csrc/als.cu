@@ -16,6 +16,8 @@
 
 #include <cuda_pipeline.h>
 
+#include <algorithm>
+
 namespace mfb {
 
 constexpr int kAlsTile = 32;    // factor rows staged per pipeline stage
@@ -35,7 +37,7 @@ struct AlsArgs {
   // is stored into all of them, i.e. the all-gather is fused into the solve epilogue
   float *Fpeer[kMaxRanks - 1];
   int n_peer;
-  int seg0;  // first segment of this launch (segments are sorted longest first)
+  int seg0, nseg;  // segments [seg0, seg0 + nseg) of the plan belong to this launch (sorted longest first)
 };
 
 __device__ __forceinline__ void store_solution(const AlsArgs &a, int row, int tid, const float *bv) {
@@ -170,19 +172,20 @@ __device__ __forceinline__ void chol_solve(float (&acc)[TR][TR], float *sm, int 
     }
     __syncthreads();
     if (C == j && R > j) {
-      float L[TR][TR], di[TR];
-#pragma unroll
-      for (int a = 0; a < TR; a++) lds_vec<TR>(dj + a * TR, L[a]);
+      float di[TR];
       lds_vec<TR>(dj + K::T2, di);
 #pragma unroll
-      for (int a = 0; a < TR; a++)
+      for (int c = 0; c < TR; c++) {
+        float Lc[TR];  // row c of L_jj, one row at a time keeps the register peak below the tile itself
+        lds_vec<TR>(dj + c * TR, Lc);
 #pragma unroll
-        for (int c = 0; c < TR; c++) {
+        for (int a = 0; a < TR; a++) {
           float sacc = MFB_T(a, c);
 #pragma unroll
-          for (int k = 0; k < c; k++) sacc = fmaf(-MFB_T(a, k), L[c][k], sacc);
+          for (int k = 0; k < c; k++) sacc = fmaf(-MFB_T(a, k), Lc[k], sacc);
           MFB_T(a, c) = sacc * di[c];
         }
+      }
 #pragma unroll
       for (int c = 0; c < TR; c++) {
         float col[TR];
@@ -516,16 +519,10 @@ __global__ void __launch_bounds__(256, 2) als_gram_tc_kernel(const AlsArgs a) {
   float4 bacc = make_float4(0.f, 0.f, 0.f, 0.f);
   uint32_t phase[kTcStages] = {0, 0};
 
-  for (int t = 0; t < ntiles; t++) {
-    const int s = t & 1;
-    if (t >= kTcStages) {  // the MMAs that read this stage two tiles ago must have finished
-      mbar_wait(smem_u32(&bars[s]), phase[s]);
-      phase[s] ^= 1;
-    }
-    const uint32_t big0 = tiles + (uint32_t)(s * 2) * kTcPartBytes, small0 = big0 + kTcPartBytes;
-    // gather: warp w handles ratings 4w..4w+3 of the tile, lane q the q-th 16-byte unit of the row
-    float4 f[4];
-    float rt[4];
+  // gather of one 32-rating tile: warp w takes ratings 4w..4w+3, lane q the q-th 16-byte unit of the row
+  float4 f[4];
+  float rt[4];
+  auto gather = [&](int t) {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const int j = t * kTcKT + warp * 4 + i;
@@ -540,6 +537,15 @@ __global__ void __launch_bounds__(256, 2) als_gram_tc_kernel(const AlsArgs a) {
         }
       }
     }
+  };
+  gather(0);
+  for (int t = 0; t < ntiles; t++) {
+    const int s = t & 1;
+    if (t >= kTcStages) {  // the MMAs that read this stage two tiles ago must have finished
+      mbar_wait(smem_u32(&bars[s]), phase[s]);
+      phase[s] ^= 1;
+    }
+    const uint32_t big0 = tiles + (uint32_t)(s * 2) * kTcPartBytes, small0 = big0 + kTcPartBytes;
     // transpose in registers: for factor dim 4q+e the four ratings form one 16-byte K-vector
     const float fe[4][4] = {{f[0].x, f[1].x, f[2].x, f[3].x}, {f[0].y, f[1].y, f[2].y, f[3].y},
                             {f[0].z, f[1].z, f[2].z, f[3].z}, {f[0].w, f[1].w, f[2].w, f[3].w}};
@@ -563,6 +569,7 @@ __global__ void __launch_bounds__(256, 2) als_gram_tc_kernel(const AlsArgs a) {
       bacc.z = fmaf(rt[i], f[i].z, bacc.z);
       bacc.w = fmaf(rt[i], f[i].w, bacc.w);
     }
+    if (t + 1 < ntiles) gather(t + 1);  // in flight while this tile is fenced and multiplied
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the tensor core
     __syncthreads();
     if (tid == 0) {
@@ -790,7 +797,7 @@ int als_debug_gram(mfb_engine *e, int side, int32_t row, float *out, int32_t *rp
   a.ind = side == MFB_USER ? m.rowind : m.colind;
   a.val = side == MFB_USER ? m.rowval : m.colval;
   a.seg_row = d; a.seg_start = d + 1; a.seg_len = d + 2; a.seg_slot = d + 3; a.multi_row = d + 4;
-  a.ws = ws; a.reg = 0.f; a.n_peer = 0; a.seg0 = 0;
+  a.ws = ws; a.reg = 0.f; a.n_peer = 0; a.seg0 = 0; a.nseg = 1;
   if (RP == 128 && e->opt_als_tensor_cores) {
     MFB_CUDA(cudaFuncSetAttribute(als_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AlsTcSmem::bytes));
     MFB_LAUNCH(als_gram_tc_kernel, 1, 256, AlsTcSmem::bytes, e->stream, a);
@@ -834,6 +841,7 @@ int als_half_step_launch(mfb_engine *e, int side, float reg) {
   a.reg = reg;
   a.n_peer = 0;
   a.seg0 = 0;
+  a.nseg = 0;
   const Comm &c = e->comm;
   if (c.connected)
     for (int p = 0; p < c.world; p++)

@@ -33,11 +33,6 @@ struct CcdPass {
   int n_seg;
 };
 
-// Both streaming kernels give every lane four independent elements per trip (indices, gathers and
-// residuals of 128 ratings are in flight per warp before the first use): the passes are bound by
-// load latency, not by arithmetic.
-constexpr int kCcdIlp = 4;
-
 // res[j] += sign * own[row] * other[ind[j]]
 __global__ void __launch_bounds__(256) ccd_resid_kernel(const CcdPass p, const float *__restrict__ own,
                                                         const float *__restrict__ other, float sign) {
@@ -46,25 +41,10 @@ __global__ void __launch_bounds__(256) ccd_resid_kernel(const CcdPass p, const f
   if (seg >= p.n_seg) return;
   const int row = p.seg_row[seg], start = p.seg_start[seg], len = p.seg_len[seg];
   const float a = sign * __ldg(own + row);
-  const int32_t *ind = p.ind + start;
-  float *res = p.res + start;
-  for (int j0 = 0; j0 < len; j0 += 32 * kCcdIlp) {
-    int c[kCcdIlp];
-    float r[kCcdIlp], o[kCcdIlp];
-#pragma unroll
-    for (int q = 0; q < kCcdIlp; q++) {
-      const int j = j0 + q * 32 + lane;
-      c[q] = j < len ? __ldg(ind + j) : -1;
-      r[q] = j < len ? res[j] : 0.f;
-    }
-#pragma unroll
-    for (int q = 0; q < kCcdIlp; q++) o[q] = c[q] >= 0 ? __ldg(other + c[q]) : 0.f;
-#pragma unroll
-    for (int q = 0; q < kCcdIlp; q++) {
-      const int j = j0 + q * 32 + lane;
-      // own*other is rounded to fp32 before it is added (modelMF.cpp:1041), hence no fma here
-      if (j < len) res[j] = __fadd_rn(r[q], __fmul_rn(a, o[q]));
-    }
+  for (int j = lane; j < len; j += 32) {
+    const int c = __ldg(p.ind + start + j);
+    // own*other is rounded to fp32 before it is added (modelMF.cpp:1041), hence no fma here
+    p.res[start + j] = __fadd_rn(p.res[start + j], __fmul_rn(a, __ldg(other + c)));
   }
 }
 
@@ -77,25 +57,12 @@ __global__ void __launch_bounds__(256) ccd_update_kernel(const CcdPass p, float 
   const int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (seg >= p.n_seg) return;
   const int row = p.seg_row[seg], start = p.seg_start[seg], len = p.seg_len[seg], slot = p.seg_slot[seg];
-  const int32_t *ind = p.ind + start;
-  const float *res = p.res + start;
   double num = 0.0, den = 0.0;
-  for (int j0 = 0; j0 < len; j0 += 32 * kCcdIlp) {
-    int c[kCcdIlp];
-    float r[kCcdIlp], o[kCcdIlp];
-#pragma unroll
-    for (int q = 0; q < kCcdIlp; q++) {
-      const int j = j0 + q * 32 + lane;
-      c[q] = j < len ? __ldg(ind + j) : -1;
-      r[q] = j < len ? res[j] : 0.f;
-    }
-#pragma unroll
-    for (int q = 0; q < kCcdIlp; q++) o[q] = c[q] >= 0 ? __ldg(other + c[q]) : 0.f;
-#pragma unroll
-    for (int q = 0; q < kCcdIlp; q++) {  // padding lanes add exact zeros
-      num += (double)__fmul_rn(r[q], o[q]);
-      den += (double)__fmul_rn(o[q], o[q]);
-    }
+  for (int j = lane; j < len; j += 32) {
+    const int c = __ldg(p.ind + start + j);
+    const float o = __ldg(other + c);
+    num += (double)__fmul_rn(p.res[start + j], o);
+    den += (double)__fmul_rn(o, o);
   }
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) {
@@ -151,10 +118,10 @@ int ccdpp_begin_impl(mfb_engine *e) {
   MFB_CUDA(cudaMemsetAsync(e->U, 0, sizeof(float) * (size_t)e->n_users * e->ld, st));
   if (!m.ccd_rows.built)
     MFB_TRY(build_seg_plan(e, m.rowptr, e->n_users, e->bad_user, e->row_begin[MFB_USER], e->row_end[MFB_USER],
-                           kCcdChunk, &m.ccd_rows, false));
+                           kCcdChunk, &m.ccd_rows));
   if (!m.ccd_cols.built)
     MFB_TRY(build_seg_plan(e, m.colptr, e->n_items, e->bad_item, e->row_begin[MFB_ITEM], e->row_end[MFB_ITEM],
-                           kCcdChunk, &m.ccd_cols, false));
+                           kCcdChunk, &m.ccd_cols));
   size_t slots = (size_t)max(m.ccd_rows.n_multi, m.ccd_cols.n_multi);
   if (slots > e->ccd_acc_slots) {
     if (e->ccd_acc) MFB_CUDA(cudaFree(e->ccd_acc));

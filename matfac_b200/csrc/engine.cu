@@ -306,32 +306,130 @@ extern "C" int mfb_upload_csr(mfb_engine *e, int which, int32_t nrows, int32_t n
   MFB_REQUIRE(nrows <= e->n_users && ncols <= e->n_items, "mfb_upload_csr: matrix larger than the engine");
   MFB_CUDA(cudaSetDevice(e->device));
   DevCsr &m = e->mat[which];
-  m.release();
+  // same shape as the resident matrix (an epoch loop that re-uploads its input): keep the allocations,
+  // cudaFree / cudaMalloc of GB-sized buffers cost milliseconds each
+  const bool reuse = m.rowptr && m.nnz == nnz && m.nrows == nrows && m.ncols == ncols && ((colptr != nullptr) == (m.colptr != nullptr));
+  if (reuse) {
+    m.eval_rows.release(); m.als_rows.release(); m.als_cols.release(); m.ccd_rows.release(); m.ccd_cols.release();
+  } else {
+    m.release();
+  }
   if (which == MFB_TRAIN) e->sgd.release();
   m.nrows = nrows;
   m.ncols = ncols;
   m.nnz = nnz;
+  const size_t nn = (size_t)(nnz > 0 ? nnz : 1);
   // rowptr is padded to n_users + 1 entries so that every kernel can index any user
-  MFB_CUDA(cudaMalloc(&m.rowptr, sizeof(int64_t) * ((size_t)e->n_users + 1)));
+  if (!reuse) {
+    MFB_CUDA(cudaMalloc(&m.rowptr, sizeof(int64_t) * ((size_t)e->n_users + 1)));
+    MFB_CUDA(cudaMalloc(&m.rowind, sizeof(int32_t) * nn));
+    MFB_CUDA(cudaMalloc(&m.rowval, sizeof(float) * nn));
+  }
   MFB_CUDA(cudaMemcpyAsync(m.rowptr, rowptr, sizeof(int64_t) * ((size_t)nrows + 1), cudaMemcpyHostToDevice, e->stream));
   if (nrows < e->n_users) {
     int cnt = e->n_users - nrows;
     MFB_LAUNCH(fill_ptr_tail_kernel, (cnt + 255) / 256, 256, 0, e->stream, m.rowptr, nrows + 1, e->n_users, nnz);
   }
-  MFB_TRY(upload_array(e, &m.rowind, rowind, (size_t)nnz));
-  MFB_TRY(upload_array(e, &m.rowval, rowval, (size_t)nnz));
+  if (nnz > 0) {
+    MFB_CUDA(cudaMemcpyAsync(m.rowind, rowind, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, e->stream));
+    MFB_CUDA(cudaMemcpyAsync(m.rowval, rowval, sizeof(float) * (size_t)nnz, cudaMemcpyHostToDevice, e->stream));
+  }
   if (colptr) {
     MFB_REQUIRE(nnz == 0 || (colind && colval), "mfb_upload_csr: incomplete CSC");
-    MFB_CUDA(cudaMalloc(&m.colptr, sizeof(int64_t) * ((size_t)e->n_items + 1)));
+    if (!reuse) {
+      MFB_CUDA(cudaMalloc(&m.colptr, sizeof(int64_t) * ((size_t)e->n_items + 1)));
+      MFB_CUDA(cudaMalloc(&m.colind, sizeof(int32_t) * nn));
+      MFB_CUDA(cudaMalloc(&m.colval, sizeof(float) * nn));
+    }
     MFB_CUDA(cudaMemcpyAsync(m.colptr, colptr, sizeof(int64_t) * ((size_t)ncols + 1), cudaMemcpyHostToDevice, e->stream));
     if (ncols < e->n_items) {
       int cnt = e->n_items - ncols;
       MFB_LAUNCH(fill_ptr_tail_kernel, (cnt + 255) / 256, 256, 0, e->stream, m.colptr, ncols + 1, e->n_items, nnz);
     }
-    MFB_TRY(upload_array(e, &m.colind, colind, (size_t)nnz));
-    MFB_TRY(upload_array(e, &m.colval, colval, (size_t)nnz));
+    if (nnz > 0) {
+      MFB_CUDA(cudaMemcpyAsync(m.colind, colind, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, e->stream));
+      MFB_CUDA(cudaMemcpyAsync(m.colval, colval, sizeof(float) * (size_t)nnz, cudaMemcpyHostToDevice, e->stream));
+    }
   }
   // the host arrays are only borrowed for the duration of the call
+  MFB_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+
+// ---- device-side column index (gk_csr_CreateIndex(mat, GK_CSR_COL), datastruct.cpp:18,51,74) ----
+__global__ void nnz_row_kernel(const int64_t *__restrict__ rowptr, int32_t nrows, int64_t nnz, int32_t *__restrict__ out,
+                               int32_t *__restrict__ idx) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nnz) return;
+  int lo = 0, hi = nrows;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (rowptr[mid] <= j) lo = mid; else hi = mid;
+  }
+  out[j] = lo;
+  idx[j] = (int32_t)j;
+}
+__global__ void csc_fill_kernel(const int32_t *__restrict__ perm, int64_t nnz, const int32_t *__restrict__ nz_row,
+                                const float *__restrict__ rowval, int32_t *__restrict__ colind, float *__restrict__ colval) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nnz) return;
+  const int p = perm[j];
+  colind[j] = nz_row[p];
+  colval[j] = rowval[p];
+}
+__global__ void col_count_kernel(const int32_t *__restrict__ ind, int64_t nnz, unsigned long long *__restrict__ cnt) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < nnz) atomicAdd(cnt + ind[j] + 1, 1ull);
+}
+
+extern "C" int mfb_build_csc(mfb_engine *e, int which) {
+  MFB_REQUIRE(e && which >= 0 && which < 3, "mfb_build_csc: bad argument");
+  DevCsr &m = e->mat[which];
+  MFB_REQUIRE(m.rowptr, "mfb_build_csc: matrix not uploaded");
+  MFB_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = e->stream;
+  cudaFree(m.colptr); cudaFree(m.colind); cudaFree(m.colval);
+  m.colptr = nullptr; m.colind = nullptr; m.colval = nullptr;
+  m.als_cols.release(); m.ccd_cols.release();
+  const int64_t nnz = m.nnz;
+  const size_t nn = (size_t)(nnz > 0 ? nnz : 1);
+  MFB_CUDA(cudaMalloc(&m.colptr, sizeof(int64_t) * ((size_t)e->n_items + 1)));
+  MFB_CUDA(cudaMalloc(&m.colind, sizeof(int32_t) * nn));
+  MFB_CUDA(cudaMalloc(&m.colval, sizeof(float) * nn));
+  MFB_CUDA(cudaMemsetAsync(m.colptr, 0, sizeof(int64_t) * ((size_t)e->n_items + 1), st));
+  if (nnz == 0) return 0;
+  int32_t *nz_row, *idx, *keys_out, *perm;
+  MFB_CUDA(cudaMalloc(&nz_row, sizeof(int32_t) * nn * 4));
+  idx = nz_row + nn; keys_out = idx + nn; perm = keys_out + nn;
+  const unsigned gb = (unsigned)((nnz + 255) / 256);
+  MFB_LAUNCH(nnz_row_kernel, gb, 256, 0, st, m.rowptr, e->n_users, nnz, nz_row, idx);
+  // stable LSD radix sort by column: rows stay ascending inside a column, as the reference's counting sort leaves them
+  int end_bit = 1;
+  while ((1ll << end_bit) < (long long)e->n_items) end_bit++;
+  size_t tmp_bytes = 0;
+  MFB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, m.rowind, keys_out, idx, perm, (int)nnz, 0, end_bit, st));
+  MFB_TRY(ensure_scratch(e, tmp_bytes));
+  MFB_CUDA(cub::DeviceRadixSort::SortPairs(e->scratch, tmp_bytes, m.rowind, keys_out, idx, perm, (int)nnz, 0, end_bit, st));
+  MFB_LAUNCH(csc_fill_kernel, gb, 256, 0, st, perm, nnz, nz_row, m.rowval, m.colind, m.colval);
+  // colptr: counts shifted by one, then an inclusive scan in place
+  MFB_LAUNCH(col_count_kernel, gb, 256, 0, st, m.rowind, nnz, reinterpret_cast<unsigned long long *>(m.colptr));
+  MFB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, m.colptr, m.colptr, e->n_items + 1, st));
+  MFB_TRY(ensure_scratch(e, tmp_bytes));
+  MFB_CUDA(cub::DeviceScan::InclusiveSum(e->scratch, tmp_bytes, m.colptr, m.colptr, e->n_items + 1, st));
+  MFB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(nz_row);
+  return 0;
+}
+
+extern "C" int mfb_download_csc(mfb_engine *e, int which, int64_t *colptr, int32_t *colind, float *colval) {
+  MFB_REQUIRE(e && which >= 0 && which < 3 && colptr && colind && colval, "mfb_download_csc: bad argument");
+  const DevCsr &m = e->mat[which];
+  MFB_REQUIRE(m.colptr, "mfb_download_csc: no column index on the device");
+  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(cudaMemcpyAsync(colptr, m.colptr, sizeof(int64_t) * ((size_t)e->n_items + 1), cudaMemcpyDeviceToHost, e->stream));
+  MFB_CUDA(cudaMemcpyAsync(colind, m.colind, sizeof(int32_t) * (size_t)m.nnz, cudaMemcpyDeviceToHost, e->stream));
+  MFB_CUDA(cudaMemcpyAsync(colval, m.colval, sizeof(float) * (size_t)m.nnz, cudaMemcpyDeviceToHost, e->stream));
   MFB_CUDA(cudaStreamSynchronize(e->stream));
   return 0;
 }
@@ -537,6 +635,17 @@ extern "C" int mfb_eval(mfb_engine *e, int which, int factors, int variant, int 
   MFB_REQUIRE(variant == MFB_MF || e->aux_variant == variant, "mfb_eval: mfb_set_aux not called for this variant");
   MFB_CUDA(cudaSetDevice(e->device));
   return eval_launch(e, which, factors, variant, weighted, want_norms, out);
+}
+
+extern "C" int mfb_eval_groups(mfb_engine *e, int which, int factors, int variant, const uint8_t *user_group,
+                               const uint8_t *item_group, double out[32]) {
+  MFB_REQUIRE(e && out && user_group && item_group && which >= 0 && which < 3, "mfb_eval_groups: bad argument");
+  MFB_REQUIRE(factors == MFB_CURRENT || factors == MFB_BEST, "mfb_eval_groups: bad factor set");
+  MFB_REQUIRE(variant >= MFB_MF && variant <= MFB_TMFDROPOUT, "mfb_eval_groups: bad variant");
+  MFB_REQUIRE(e->mat[which].rowptr, "mfb_eval_groups: matrix not uploaded");
+  MFB_REQUIRE(variant == MFB_MF || e->aux_variant == variant, "mfb_eval_groups: mfb_set_aux not called for this variant");
+  MFB_CUDA(cudaSetDevice(e->device));
+  return eval_groups_launch(e, which, factors, variant, user_group, item_group, out);
 }
 
 extern "C" int mfb_snapshot_best(mfb_engine *e) {

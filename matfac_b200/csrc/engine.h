@@ -188,6 +188,8 @@ int sgd_subepoch_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int va
 int sgd_flat_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int variant, float lr, float ureg, float ireg,
                     uint64_t seed, uint64_t counter);
 int eval_launch(mfb_engine *e, int which, int factors, int variant, int weighted, int want_norms, double out[4]);
+int eval_groups_launch(mfb_engine *e, int which, int factors, int variant, const uint8_t *user_group,
+                       const uint8_t *item_group, double *out);
 int als_half_step_launch(mfb_engine *e, int side, float reg);
 int als_debug_gram(mfb_engine *e, int side, int32_t row, float *out, int32_t *rp_out);
 int ccdpp_begin_impl(mfb_engine *e);

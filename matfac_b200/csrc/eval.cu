@@ -241,4 +241,208 @@ int eval_launch(mfb_engine *e, int which, int factors, int variant, int weighted
   return 0;
 }
 
+
+// ---- grouped evaluation: squared error and count per item group and per user group in ONE pass --------
+// Replaces the eight filtered passes of quartileRMSEs (main.cpp:700-768): Model::RMSE(mat, filtItems, ...)
+// (model.cpp:348-394), ::SE (:397-443) and ::RMSEU (:446-486), which probe an unordered_set per rating.
+// Every id carries a group byte (255 = in no group); a rating adds its squared error to the bin of its
+// item's group and to the bin of its user's group.  Bins live in registers (compare-select, no indexing).
+constexpr int kEvalGroups = 8;
+
+struct EvalGroupArgs {
+  EvalArgs e;
+  const uint8_t *user_group, *item_group;
+  double *partial;  // [grid][2 sides][kEvalGroups][2]
+};
+
+template <int G, int VPL, int VARIANT>
+__global__ void __launch_bounds__(128) eval_group_kernel(const EvalGroupArgs ga) {
+  constexpr unsigned kFull = 0xFFFFFFFFu;
+  const EvalArgs &a = ga.e;
+  const int lane = threadIdx.x & 31;
+  const int sl = lane & (G - 1);
+  const int seg = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
+  const bool active = seg < a.n_seg;
+  int user = 0, start = 0, len = 0;
+  if (active) {
+    user = a.seg_row[seg];
+    start = a.seg_start[seg];
+    len = a.seg_len[seg];
+  }
+  int maxlen = len;
+#pragma unroll
+  for (int m = 16; m >= G; m >>= 1) maxlen = max(maxlen, __shfl_xor_sync(kFull, maxlen, m));
+  double isse[kEvalGroups], icnt[kEvalGroups], usse = 0.0, ucnt = 0.0;
+#pragma unroll
+  for (int g = 0; g < kEvalGroups; g++) isse[g] = icnt[g] = 0.0;
+  const int ugrp = active ? ga.user_group[user] : 255;
+  if (maxlen > 0) {
+    float4 u[VPL];
+    bool own[VPL];
+    const float4 *urow = reinterpret_cast<const float4 *>(a.U) + (size_t)user * a.nq;
+#pragma unroll
+    for (int c = 0; c < VPL; c++) {
+      own[c] = (c * G + sl) < a.nq;
+      u[c] = (active && own[c]) ? __ldcg(urow + c * G + sl) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    int ufreq = 0, upred = 0;
+    if (VARIANT != MFB_MF && active) {
+      Aux au = a.aux_u[user];
+      ufreq = au.freq; upred = au.pred;
+    }
+    const float4 *Vq = reinterpret_cast<const float4 *>(a.V);
+    for (int j0 = 0; j0 < maxlen; j0 += G) {
+      int c_it = -1, c_pay = 0, c_grp = 255;
+      float c_rt = 0.f;
+      if (j0 + sl < len) {
+        int it = __ldg(a.ind + start + j0 + sl);
+        c_rt = __ldg(a.val + start + j0 + sl);
+        if (!a.bad_item[it]) {
+          c_it = it;
+          c_grp = ga.item_group[it];
+          if (VARIANT == MFB_TMF || VARIANT == MFB_TMFDROPOUT) {
+            Aux ai = a.aux_i[it];
+            c_pay = (ufreq < ai.freq) ? upred : ai.pred;
+          }
+        }
+      }
+#pragma unroll 4
+      for (int t = 0; t < G; t++) {
+        if (j0 + t >= maxlen) break;
+        const int it = __shfl_sync(kFull, c_it, t, G);
+        const float rt = __shfl_sync(kFull, c_rt, t, G);
+        const int grp = __shfl_sync(kFull, c_grp, t, G);
+        int k = a.rank;
+        if (VARIANT == MFB_TMF || VARIANT == MFB_TMFDROPOUT) k = __shfl_sync(kFull, c_pay, t, G);
+        const bool on = it >= 0;
+        float p = 0.f;
+        if (on) {
+#pragma unroll
+          for (int c = 0; c < VPL; c++) {
+            if (!own[c]) continue;
+            const float4 v = __ldcg(Vq + (size_t)it * a.nq + c * G + sl);
+            const int base = (c * G + sl) * 4;
+            if (VARIANT == MFB_TMF || VARIANT == MFB_TMFDROPOUT) {
+              p += (base + 0 < k ? u[c].x * v.x : 0.f) + (base + 1 < k ? u[c].y * v.y : 0.f) +
+                   (base + 2 < k ? u[c].z * v.z : 0.f) + (base + 3 < k ? u[c].w * v.w : 0.f);
+            } else {
+              p = fmaf(u[c].x, v.x, p);
+              p = fmaf(u[c].y, v.y, p);
+              p = fmaf(u[c].z, v.z, p);
+              p = fmaf(u[c].w, v.w, p);
+            }
+          }
+        }
+#pragma unroll
+        for (int m = G / 2; m >= 1; m >>= 1) p += __shfl_xor_sync(kFull, p, m);
+        if (on && sl == 0) {
+          const double diff = (double)rt - (double)p;
+          const double d2 = diff * diff;
+          usse += d2;
+          ucnt += 1.0;
+#pragma unroll
+          for (int g = 0; g < kEvalGroups; g++)
+            if (grp == g) { isse[g] += d2; icnt[g] += 1.0; }
+        }
+      }
+    }
+  }
+  // CTA reduction through shared memory (fixed order): bins [side][group][sse|count]
+  __shared__ double flat[2 * kEvalGroups * 2];
+  for (int i = threadIdx.x; i < 2 * kEvalGroups * 2; i += blockDim.x) flat[i] = 0.0;
+  __syncthreads();
+  // one sub-warp leader at a time adds its bins: serialised per CTA, but only 128 / G leaders exist
+  for (int turn = 0; turn < (int)blockDim.x / G; turn++) {
+    if (sl == 0 && (int)(threadIdx.x / G) == turn) {
+#pragma unroll
+      for (int g = 0; g < kEvalGroups; g++) {
+        flat[(0 * kEvalGroups + g) * 2 + 0] += isse[g];
+        flat[(0 * kEvalGroups + g) * 2 + 1] += icnt[g];
+      }
+      if (ugrp < kEvalGroups) {
+        flat[(1 * kEvalGroups + ugrp) * 2 + 0] += usse;
+        flat[(1 * kEvalGroups + ugrp) * 2 + 1] += ucnt;
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < 2 * kEvalGroups * 2; i += blockDim.x)
+    ga.partial[(size_t)blockIdx.x * (2 * kEvalGroups * 2) + i] = flat[i];
+}
+
+// out[i] = sum over CTAs of partial[cta][i], i < 32 (fixed order: deterministic)
+__global__ void __launch_bounds__(256) eval_group_final_kernel(const double *__restrict__ partial, int n_cta, double *__restrict__ out) {
+  __shared__ double sh[8][32];
+  const int bin = threadIdx.x & 31, stripe = threadIdx.x >> 5;
+  double acc = 0.0;
+  for (int c = stripe; c < n_cta; c += 8) acc += partial[(size_t)c * 32 + bin];
+  sh[stripe][bin] = acc;
+  __syncthreads();
+  if (stripe == 0) {
+    double t = 0.0;
+    for (int s2 = 0; s2 < 8; s2++) t += sh[s2][bin];
+    out[bin] = t;
+  }
+}
+
+template <int G, int VPL>
+static int launch_eval_group(mfb_engine *e, const EvalGroupArgs &a, int variant, unsigned grid) {
+  switch (variant) {
+    case MFB_MF: MFB_LAUNCH((eval_group_kernel<G, VPL, MFB_MF>), grid, 128, 0, e->stream, a); break;
+    case MFB_IFWMF: MFB_LAUNCH((eval_group_kernel<G, VPL, MFB_IFWMF>), grid, 128, 0, e->stream, a); break;
+    case MFB_TMF: MFB_LAUNCH((eval_group_kernel<G, VPL, MFB_TMF>), grid, 128, 0, e->stream, a); break;
+    default: MFB_LAUNCH((eval_group_kernel<G, VPL, MFB_TMFDROPOUT>), grid, 128, 0, e->stream, a); break;
+  }
+  return 0;
+}
+
+int eval_groups_launch(mfb_engine *e, int which, int factors, int variant, const uint8_t *user_group,
+                       const uint8_t *item_group, double *out /* [2][kEvalGroups][2] */) {
+  DevCsr &m = e->mat[which];
+  if (!m.eval_rows.built)
+    MFB_TRY(build_seg_plan(e, m.rowptr, e->n_users, e->bad_user, e->row_begin[MFB_USER], e->row_end[MFB_USER], 512,
+                           &m.eval_rows));
+  const SegPlan &sp = m.eval_rows;
+  for (int i = 0; i < 2 * kEvalGroups * 2; i++) out[i] = 0.0;
+  if (sp.n_seg == 0) return 0;
+  const int nq = e->ld / 4;
+  int G = 2;
+  while (G < 32 && G < nq) G <<= 1;
+  const int segs_per_cta = 128 / G;
+  const int grid = (sp.n_seg + segs_per_cta - 1) / segs_per_cta;
+  uint8_t *d_groups;
+  double *d_partial;
+  MFB_CUDA(cudaMalloc(&d_groups, (size_t)e->n_users + e->n_items));
+  MFB_CUDA(cudaMalloc(&d_partial, sizeof(double) * 32 * ((size_t)grid + 1)));
+  MFB_CUDA(cudaMemcpyAsync(d_groups, user_group, e->n_users, cudaMemcpyHostToDevice, e->stream));
+  MFB_CUDA(cudaMemcpyAsync(d_groups + e->n_users, item_group, e->n_items, cudaMemcpyHostToDevice, e->stream));
+  EvalGroupArgs ga;
+  EvalArgs &a = ga.e;
+  a.U = factors == MFB_BEST ? e->bestU : e->U;
+  a.V = factors == MFB_BEST ? e->bestV : e->V;
+  a.nq = nq; a.rank = e->rank;
+  a.ind = m.rowind; a.val = m.rowval;
+  a.seg_row = sp.row; a.seg_start = sp.start; a.seg_len = sp.len; a.n_seg = sp.n_seg;
+  a.bad_item = e->bad_item;
+  a.aux_u = e->aux_u; a.aux_i = e->aux_i;
+  a.weighted = 0;
+  a.partial = nullptr;
+  ga.user_group = d_groups;
+  ga.item_group = d_groups + e->n_users;
+  ga.partial = d_partial;
+  if (nq <= 2) MFB_TRY((launch_eval_group<2, 1>(e, ga, variant, grid)));
+  else if (nq <= 4) MFB_TRY((launch_eval_group<4, 1>(e, ga, variant, grid)));
+  else if (nq <= 8) MFB_TRY((launch_eval_group<8, 1>(e, ga, variant, grid)));
+  else if (nq <= 16) MFB_TRY((launch_eval_group<16, 1>(e, ga, variant, grid)));
+  else if (nq <= 32) MFB_TRY((launch_eval_group<32, 1>(e, ga, variant, grid)));
+  else MFB_TRY((launch_eval_group<32, 2>(e, ga, variant, grid)));
+  double *d_out = d_partial + (size_t)grid * 32;
+  MFB_LAUNCH(eval_group_final_kernel, 1, 256, 0, e->stream, d_partial, grid, d_out);
+  MFB_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * 32, cudaMemcpyDeviceToHost, e->stream));
+  MFB_CUDA(cudaStreamSynchronize(e->stream));
+  cudaFree(d_groups);
+  cudaFree(d_partial);
+  return 0;
+}
+
 }  // namespace mfb

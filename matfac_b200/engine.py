@@ -25,10 +25,10 @@ SYMBOLS = [
     "mfb_last_error", "mfb_launch_count", "mfb_create", "mfb_destroy", "mfb_sync", "mfb_pin_host",
     "mfb_unpin_host", "mfb_upload_csr", "mfb_set_masks", "mfb_upload_factors", "mfb_download_factors",
     "mfb_set_aux", "mfb_sgd_plan", "mfb_sgd_subepoch", "mfb_sgd_block_nnz", "mfb_sgd_epoch_flat", "mfb_set_option", "mfb_als_half_step", "mfb_debug_als_gram",
-    "mfb_ccdpp_begin", "mfb_ccdpp_rank1", "mfb_ccdpp_end", "mfb_eval", "mfb_snapshot_best",
+    "mfb_ccdpp_begin", "mfb_ccdpp_rank1", "mfb_ccdpp_end", "mfb_eval", "mfb_eval_groups", "mfb_snapshot_best",
     "mfb_restore_best", "mfb_event_record", "mfb_event_elapsed_ms", "mfb_device_factors", "mfb_stream",
     "mfb_pack_rows", "mfb_unpack_rows", "mfb_set_row_range",
-    "mfb_comm_init", "mfb_comm_connect", "mfb_comm_barrier", "mfb_comm_error", "mfb_dsgd_push_block",
+    "mfb_build_csc", "mfb_download_csc", "mfb_comm_init", "mfb_comm_connect", "mfb_comm_barrier", "mfb_comm_error", "mfb_dsgd_push_block",
     "mfb_comm_wait_block", "mfb_comm_allgather_rows",
 ]
 
@@ -64,6 +64,8 @@ def load_library():
     L.mfb_pin_host.argtypes = [vp, u64]
     L.mfb_unpin_host.argtypes = [vp]
     L.mfb_upload_csr.argtypes = [vp, C.c_int, i32, i32, i64, vp, vp, vp, vp, vp, vp]
+    L.mfb_build_csc.argtypes = [vp, C.c_int]
+    L.mfb_download_csc.argtypes = [vp, C.c_int, vp, vp, vp]
     L.mfb_set_masks.argtypes = [vp, vp, vp]
     L.mfb_upload_factors.argtypes = [vp, vp, i64, vp, i64]
     L.mfb_download_factors.argtypes = [vp, C.c_int, vp, i64, vp, i64]
@@ -79,6 +81,7 @@ def load_library():
     L.mfb_ccdpp_rank1.argtypes = [vp, i32, C.c_int, i32, f32, f32, i32]
     L.mfb_ccdpp_end.argtypes = [vp]
     L.mfb_eval.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.mfb_eval_groups.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.mfb_snapshot_best.argtypes = [vp]
     L.mfb_restore_best.argtypes = [vp]
     L.mfb_event_record.argtypes = [vp, i32]
@@ -143,6 +146,15 @@ class Engine:
             cp, ci, cv = _arr(mat.colptr, np.int64), _arr(mat.colind, np.int32), _arr(mat.colval, np.float32)
         self._check(self.L.mfb_upload_csr(self.h, which, mat.nrows, mat.ncols, int(rp[-1]), _p(rp), _p(ri), _p(rv),
                                           _p(cp), _p(ci), _p(cv)))
+
+    def build_csc(self, which=TRAIN):
+        """Column index built on the device from the uploaded CSR (gk_csr_CreateIndex)."""
+        self._check(self.L.mfb_build_csc(self.h, which))
+
+    def download_csc(self, which, nnz):
+        cp = np.zeros(self.n_items + 1, np.int64); ci = np.zeros(nnz, np.int32); cv = np.zeros(nnz, np.float32)
+        self._check(self.L.mfb_download_csc(self.h, which, _p(cp), _p(ci), _p(cv)))
+        return cp, ci, cv
 
     def set_masks(self, invalid_users, invalid_items):
         iu, ii = _arr(invalid_users, np.uint8), _arr(invalid_items, np.uint8)
@@ -222,6 +234,14 @@ class Engine:
         out = np.zeros(4, np.float64)
         self._check(self.L.mfb_eval(self.h, which, factors, variant, int(weighted), int(want_norms), _p(out)))
         return out
+
+    def eval_groups(self, which, user_group, item_group, factors=CURRENT, variant=MF):
+        """(sse, count) per item group and per user group in one pass: returns array [2 sides][8 groups][2]."""
+        ug, ig = _arr(user_group, np.uint8), _arr(item_group, np.uint8)
+        assert ug.shape[0] == self.n_users and ig.shape[0] == self.n_items
+        out = np.zeros(32, np.float64)
+        self._check(self.L.mfb_eval_groups(self.h, which, factors, variant, _p(ug), _p(ig), _p(out)))
+        return out.reshape(2, 8, 2)
 
     def rmse(self, which, factors=CURRENT, variant=MF):
         o = self.eval(which, factors, variant)

@@ -11,7 +11,11 @@
 //                   needs no GPU
 #include <omp.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstring>
+#include <fstream>
+#include <iostream>
 #include <map>
 #include <memory>
 
@@ -99,6 +103,72 @@ std::vector<double> percentileRanks(const std::vector<double> &freq) {
   std::vector<double> rank(freq.size(), 0);
   for (int i = 0; i < (int)freq.size(); i++) rank[pairs[i].first] = double(freq.size() - i) / double(freq.size());
   return rank;
+}
+
+// Frequency quartiles of main.cpp:1109-1169 (setAdapRank / getUserItemRankMap): ids sorted by decreasing
+// training frequency with the same std::sort + descComp call, cut into four parts of 25 % of the ids.
+typedef std::vector<std::pair<int, std::vector<int>>> Parts;
+
+static bool descCompPair(const std::pair<int, double> a, const std::pair<int, double> b) { return a.second > b.second; }
+
+static Parts frequencyQuartiles(const std::vector<double> &freq) {
+  std::vector<std::pair<int, double>> pairs;
+  for (int i = 0; i < (int)freq.size(); i++) pairs.push_back(std::make_pair(i, freq[i]));
+  std::sort(pairs.begin(), pairs.end(), descCompPair);
+  Parts parts;
+  const int n = (int)pairs.size();
+  int i = 0, partInd = 0;
+  while (i < n) {
+    int end = i + 0.25 * ((float)n);
+    if (end > n || partInd == 3) end = n;
+    std::vector<int> ids;
+    for (int k = i; k < end; k++) ids.push_back(pairs[k].first);
+    parts.push_back(std::make_pair(partInd, ids));
+    i = end;
+    partInd++;
+  }
+  return parts;
+}
+
+// itemPartition.txt / userPartition.txt (main.cpp:1091-1107, :1412-1413)
+static void writePartition(const Parts &parts, const std::unordered_set<int> &invalid, const char *name) {
+  std::ofstream f(name);
+  if (!f.is_open()) return;
+  for (auto &part : parts)
+    for (int id : part.second)
+      if (invalid.count(id) == 0) f << part.first << " " << id << std::endl;
+}
+
+// quartileRMSEs (main.cpp:700-768): same lines on stdout; the eight filtered passes per matrix are one
+// grouped device pass (Model::groupSE)
+static void quartileRMSEs(Model &bestModel, const Data &data, const Parts &partItems, const Parts &partUsers,
+                          std::unordered_set<int> &invalidUsers, std::unordered_set<int> &invalidItems) {
+  std::vector<uint8_t> ug(data.nUsers, 255), ig(data.nItems, 255);
+  for (auto &p : partUsers)
+    for (int u : p.second)
+      if (u < data.nUsers) ug[u] = (uint8_t)p.first;
+  for (auto &p : partItems)
+    for (int i : p.second)
+      if (i < data.nItems) ig[i] = (uint8_t)p.first;
+  std::cout << std::endl;
+  std::cout << "Train RMSE: " << bestModel.RMSE(data.trainMat, invalidUsers, invalidItems) << std::endl;
+  std::cout << "Test RMSE: " << bestModel.RMSE(data.testMat, invalidUsers, invalidItems) << std::endl;
+  std::cout << "Val RMSE: " << bestModel.RMSE(data.valMat, invalidUsers, invalidItems) << std::endl;
+  const char *names[2] = {"Test RMSE: ", "Validation RMSE: "};
+  gk_csr_t *mats[2] = {data.testMat, data.valMat};
+  for (int m = 0; m < 2; m++) {
+    double out[32];
+    bestModel.groupSE(mats[m], ug, ig, invalidUsers, invalidItems, out);
+    std::cout << names[m] << std::endl;
+    std::cout << "Items Part: ";
+    for (auto &p : partItems) std::cout << (int)out[(0 * 8 + p.first) * 2 + 1] << " "
+                                        << sqrt(out[(0 * 8 + p.first) * 2] / out[(0 * 8 + p.first) * 2 + 1]) << " ";
+    std::cout << std::endl;
+    std::cout << "Users Part: ";
+    for (auto &p : partUsers) std::cout << (int)out[(1 * 8 + p.first) * 2 + 1] << " "
+                                        << sqrt(out[(1 * 8 + p.first) * 2] / out[(1 * 8 + p.first) * 2 + 1]) << " ";
+    std::cout << std::endl;
+  }
 }
 
 }  // namespace
@@ -229,6 +299,13 @@ int main(int argc, char **argv) {
   std::cout << "\nValidation RMSE: " << valRMSE << std::endl;
   mfModel->display();
   std::cout << std::endl;
+
+  // tail / head report of main.cpp:1407-1413
+  std::cout << "invalid users: " << invalidUsers.size() << " invalid items: " << invalidItems.size() << std::endl;
+  const Parts partItems = frequencyQuartiles(itemFreq), partUsers = frequencyQuartiles(userFreq);
+  quartileRMSEs(*bestModel, data, partItems, partUsers, invalidUsers, invalidItems);
+  writePartition(partItems, invalidItems, "itemPartition.txt");
+  writePartition(partUsers, invalidUsers, "userPartition.txt");
 
   if (!dumpDir.empty()) {
     dumpMat(mfModel->uFac, mfModel->nUsers, mfModel->facDim, dumpDir + "/last_uFac.bin");

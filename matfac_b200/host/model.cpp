@@ -180,6 +180,51 @@ double Model::RMSE(gk_csr_t *mat) {
   return RMSE(mat, none, none);
 }
 
+void Model::groupSE(gk_csr_t *mat, const std::vector<uint8_t> &userGroup, const std::vector<uint8_t> &itemGroup,
+                    std::unordered_set<int> &invalidUsers, std::unordered_set<int> &invalidItems, double out[32]) {
+  std::vector<uint8_t> ug(nUsers, 255), ig(nItems, 255);
+  for (size_t i = 0; i < userGroup.size() && i < ug.size(); i++) ug[i] = userGroup[i];
+  for (size_t i = 0; i < itemGroup.size() && i < ig.size(); i++) ig[i] = itemGroup[i];
+  int which = 0;
+  DeviceSession *s = dev_ && dev_->slotOf(mat) >= 0 ? dev_ : nullptr;
+  if (s) {
+    which = s->slotOf(mat);
+  } else {
+    s = &DeviceSession::forMatrix(mat, nUsers, nItems, facDim, &which);
+    s->setMasks(invalidUsers, invalidItems);
+    uploadFactors(*s);
+    uploadAux(*s, nullptr, invalidUsers, invalidItems);
+  }
+  s->check(mfb_eval_groups(s->eng, which, MFB_CURRENT, deviceVariant(), ug.data(), ig.data(), out));
+}
+
+static std::vector<uint8_t> groupOf(const std::unordered_set<int> &ids, int n) {
+  std::vector<uint8_t> g(n, 255);
+  for (int id : ids)
+    if (id >= 0 && id < n) g[id] = 0;
+  return g;
+}
+
+std::pair<int, double> Model::SE(gk_csr_t *mat, std::unordered_set<int> &filtItems, std::unordered_set<int> &invalidUsers,
+                                 std::unordered_set<int> &invalidItems) {
+  double out[32];
+  groupSE(mat, std::vector<uint8_t>(nUsers, 255), groupOf(filtItems, nItems), invalidUsers, invalidItems, out);
+  return std::make_pair((int)out[1], out[0]);
+}
+
+std::pair<int, double> Model::RMSE(gk_csr_t *mat, std::unordered_set<int> &filtItems, std::unordered_set<int> &invalidUsers,
+                                   std::unordered_set<int> &invalidItems) {
+  auto se = SE(mat, filtItems, invalidUsers, invalidItems);
+  return std::make_pair(se.first, sqrt(se.second / se.first));
+}
+
+std::pair<int, double> Model::RMSEU(gk_csr_t *mat, std::unordered_set<int> &filtUsers, std::unordered_set<int> &invalidUsers,
+                                    std::unordered_set<int> &invalidItems) {
+  double out[32];
+  groupSE(mat, groupOf(filtUsers, nUsers), std::vector<uint8_t>(nItems, 255), invalidUsers, invalidItems, out);
+  return std::make_pair((int)out[16 + 1], sqrt(out[16] / out[16 + 1]));
+}
+
 double Model::objective(const Data &data, std::unordered_set<int> &invalidUsers,
                         std::unordered_set<int> &invalidItems) {
   if (dev_ && dev_->slotOf(data.trainMat) >= 0) return deviceEval(*dev_, MFB_TRAIN, true);

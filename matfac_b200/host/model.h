@@ -92,6 +92,18 @@ class Model {
                         std::unordered_set<int> &invalidUsers, std::unordered_set<int> &invalidItems);
   double RMSE(gk_csr_t *mat);
   double RMSE(gk_csr_t *mat, std::unordered_set<int> &invalidUsers, std::unordered_set<int> &invalidItems);
+  // filtered variants (model.cpp:348-486): {count, RMSE} / {count, squared error} over the ratings whose item
+  // (RMSE, SE) resp. user (RMSEU) is in the filter set
+  std::pair<int, double> RMSE(gk_csr_t *mat, std::unordered_set<int> &filtItems, std::unordered_set<int> &invalidUsers,
+                              std::unordered_set<int> &invalidItems);
+  std::pair<int, double> SE(gk_csr_t *mat, std::unordered_set<int> &filtItems, std::unordered_set<int> &invalidUsers,
+                            std::unordered_set<int> &invalidItems);
+  std::pair<int, double> RMSEU(gk_csr_t *mat, std::unordered_set<int> &filtUsers, std::unordered_set<int> &invalidUsers,
+                               std::unordered_set<int> &invalidItems);
+  // all parts of quartileRMSEs (main.cpp:700-768) in ONE device pass: userGroup / itemGroup give every id a part
+  // 0..7 or 255; out[((side * 8) + part) * 2 + {0, 1}] = squared error, count (side 0 = items, 1 = users)
+  void groupSE(gk_csr_t *mat, const std::vector<uint8_t> &userGroup, const std::vector<uint8_t> &itemGroup,
+               std::unordered_set<int> &invalidUsers, std::unordered_set<int> &invalidItems, double out[32]);
   virtual double estRating(int user, int item);
   std::string modelSignature();
   void display();

@@ -385,6 +385,68 @@ def test_ccdpp_matches_oracle(rank, freq_adap):
     eng.close()
 
 
+def test_device_column_index_is_bit_exact():
+    """mfb_build_csc == gk_csr_CreateIndex(mat, GK_CSR_COL): the oracle's CSC arrays, bit for bit, including
+    empty rows / columns and a matrix narrower than the engine."""
+    splits = small_problem(700, 500, 25000, seed=17)
+    tr = splits[0]
+    od = ol.OracleData(*splits)
+    eng = E.Engine(od.n_users, od.n_items + 3, 8)
+    eng.upload_csr(E.TRAIN, tr, with_csc=False)
+    eng.build_csc(E.TRAIN)
+    cp, ci, cv = eng.download_csc(E.TRAIN, tr.nnz)
+    wp, wi, wv = od.csc(0)
+    assert np.array_equal(cp[: tr.ncols + 1], wp) and np.all(cp[tr.ncols:] == tr.nnz)
+    assert np.array_equal(ci, wi) and np.array_equal(cv, wv)
+    # ALS on the device-built index equals ALS on the uploaded one
+    eng2 = E.Engine(od.n_users, od.n_items + 3, 8)
+    eng2.upload_csr(E.TRAIN, tr, with_csc=True)
+    rng = np.random.default_rng(0)
+    U0 = rng.uniform(-0.1, 0.1, (od.n_users, 8)).astype(np.float32)
+    V0 = rng.uniform(-0.1, 0.1, (od.n_items + 3, 8)).astype(np.float32)
+    outs = []
+    for g in (eng, eng2):
+        g.upload_factors(U0, V0)
+        g.als_half_step(E.ITEM, 0.1)
+        outs.append(g.download_factors()[1])
+        g.close()
+    assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("algo", ["mf", "TMF"])
+def test_grouped_evaluation_matches_filtered_rmse(algo):
+    """mfb_eval_groups against the definition of Model::RMSE(mat, filtItems, ...) / RMSEU (model.cpp:348-486):
+    per item quartile and per user quartile squared error and count, invalid ids skipped, ids in no group ignored."""
+    splits = small_problem(700, 500, 25000, seed=17)
+    tr, va, te = splits
+    rank = 16
+    om = oracle_model(splits, algo, rank, maxiter=3, learnrate=0.01, **ALGO_FLAGS[algo])
+    om.train("sgdpar" if algo != "mf" else "sgd")
+    eng, variant = make_engine(splits, om, rank, algo)
+    U, V = om.factors()
+    bu, bi = om.invalid()
+    rng = np.random.default_rng(4)
+    ug = rng.integers(0, 5, eng.n_users).astype(np.uint8); ug[ug == 4] = 255
+    ig = rng.integers(0, 5, eng.n_items).astype(np.uint8); ig[ig == 4] = 255
+    got = eng.eval_groups(E.TEST, ug, ig, E.CURRENT, variant)
+    tot = eng.eval(E.TEST, E.CURRENT, variant)
+    if algo == "mf":
+        users = np.repeat(np.arange(te.nrows), np.diff(te.rowptr))
+        ok = (bu[users] == 0) & (bi[te.rowind] == 0)
+        err2 = (te.rowval - np.einsum("ij,ij->i", U[users].astype(np.float64), V[te.rowind].astype(np.float64))) ** 2
+        for g in range(4):
+            for side, grp in ((0, ig[te.rowind]), (1, ug[users])):
+                sel = ok & (grp == g)
+                assert got[side, g, 1] == sel.sum()
+                assert abs(got[side, g, 0] - err2[sel].sum()) <= 1e-5 * max(err2[sel].sum(), 1e-12)
+    # all ratings in one group == the plain evaluation, for every estRating variant
+    one = eng.eval_groups(E.TEST, np.zeros(eng.n_users, np.uint8), np.zeros(eng.n_items, np.uint8), E.CURRENT, variant)
+    for side in (0, 1):
+        assert one[side, 0, 1] == tot[1] and abs(one[side, 0, 0] - tot[0]) <= 1e-9 * tot[0]
+    assert np.all(got[:, 4:, :] == 0)
+    eng.close()
+
+
 def test_snapshot_and_restore_best():
     splits = small_problem()
     om = oracle_model(splits, "mf", 10)

@@ -209,3 +209,41 @@ def test_c_entry_point_trains_from_memory():
     assert rel_err(bU, oU) < 1e-4 and rel_err(bV, oV) < 1e-4
     assert abs(r.best_val_rmse - m.rmse(1, best=True)) < 1e-4 * r.best_val_rmse
     lib.mfh_release_device()
+
+
+@pytest.mark.gpu
+def test_cli_quartile_report_and_partition_files(tmp_path):
+    """The tail / head report main() prints after training (quartileRMSEs, main.cpp:700-768, :1407-1413): four item
+    parts and four user parts by decreasing training frequency, {count, RMSE} per part on test and validation, and
+    itemPartition.txt / userPartition.txt.  Checked against the dumped best factors."""
+    splits = synth.make_splits(500, 300, 40000, seed=13)
+    tr, va, te = splits
+    files = synth.write_split_files(str(tmp_path), *splits)
+    fl = dict(BASE); fl.update(ureg=0.1, ireg=0.1); fl["maxiter"] = 3
+    dump = str(tmp_path / "gpu")
+    out = run_mf(files, dump, threads=2, algo="mf", mf_method="als", **fl)
+    U = ol.read_mat(os.path.join(dump, "best_uFac.bin")).astype(np.float64)
+    V = ol.read_mat(os.path.join(dump, "best_iFac.bin")).astype(np.float64)
+    bad_u = set(ol.read_set(os.path.join(dump, "invalidUsers.bin")).tolist())
+    bad_i = set(ol.read_set(os.path.join(dump, "invalidItems.bin")).tolist())
+    ipart = np.loadtxt(os.path.join(dump, "itemPartition.txt"), dtype=np.int64)
+    upart = np.loadtxt(os.path.join(dump, "userPartition.txt"), dtype=np.int64)
+    assert sorted(set(ipart[:, 0])) == [0, 1, 2, 3] and sorted(set(upart[:, 0])) == [0, 1, 2, 3]
+    # parts are cut by decreasing training frequency
+    ifreq = np.bincount(tr.rowind, minlength=V.shape[0])
+    assert ifreq[ipart[ipart[:, 0] == 0, 1]].min() >= ifreq[ipart[ipart[:, 0] == 3, 1]].max()
+    lines = out.splitlines()
+    k = max(i for i, l in enumerate(lines) if l.startswith("Test RMSE:") and l.strip() == "Test RMSE:")
+    items_line = [float(x) for x in lines[k + 1].replace("Items Part:", "").split()]
+    users_line = [float(x) for x in lines[k + 2].replace("Users Part:", "").split()]
+    users = np.repeat(np.arange(te.nrows), np.diff(te.rowptr))
+    ok = np.array([u not in bad_u for u in users]) & np.array([i not in bad_i for i in te.rowind])
+    err2 = (te.rowval - np.einsum("ij,ij->i", U[users], V[te.rowind])) ** 2
+    ig = np.full(V.shape[0], -1); ig[ipart[:, 1]] = ipart[:, 0]
+    ug = np.full(U.shape[0], -1); ug[upart[:, 1]] = upart[:, 0]
+    for g in range(4):
+        for line, grp in ((items_line, ig[te.rowind]), (users_line, ug[users])):
+            sel = ok & (grp == g)
+            assert int(line[2 * g]) == sel.sum()
+            if sel.sum():
+                assert abs(line[2 * g + 1] - np.sqrt(err2[sel].mean())) < 2e-4 * np.sqrt(err2[sel].mean())

@@ -23,22 +23,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 
-def csc_on_device(n_users, n_items, ptr, ind, val, device):
-    """gk_csr_CreateIndex(mat, GK_CSR_COL) as a stable sort by column (torch, set-up only)."""
-    import torch
-    dev = torch.device(device)
-    ind_d = torch.from_numpy(ind).to(dev)
-    deg = torch.from_numpy(np.diff(ptr)).to(dev)
-    rows = torch.repeat_interleave(torch.arange(n_users, device=dev, dtype=torch.int32), deg)
-    order = torch.sort(ind_d.long() * n_users + rows.long()).indices  # (col, row) ascending == stable by col
-    colind = rows[order].cpu().numpy()
-    colval = torch.from_numpy(val).to(dev)[order].cpu().numpy()
-    cnt = torch.bincount(ind_d.long(), minlength=n_items)
-    colptr = np.zeros(n_items + 1, np.int64)
-    colptr[1:] = torch.cumsum(cnt, 0).cpu().numpy()
-    del ind_d, deg, rows, order, cnt
-    torch.cuda.empty_cache()
-    return colptr, colind, colval
+csc_on_device = bench.csc_on_device
 
 
 def main():
@@ -52,27 +37,58 @@ def main():
     args = ap.parse_args()
     import torch
     from matfac_b200 import engine as E
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_users, n_items, nnz = int(bench.SHAPE[0] * args.scale), bench.SHAPE[1], int(bench.SHAPE[2] * args.scale)
     t0 = time.time()
-    prob = bench.gen_problem(n_users, n_items, nnz, 20260102, "cuda:0")
+    if world > 1:
+        prob = bench.shared_problem(n_users, n_items, nnz, 20260102, rank, dist, f"cuda:{local}")
+    else:
+        prob = bench.gen_problem(n_users, n_items, nnz, 20260102, f"cuda:{local}")
     ptr, ind, val = prob["train"]
     train_nnz = int(ptr[-1])
     tr = bench.Mat(n_users, n_items, prob["train"])
-    tr.colptr, tr.colind, tr.colval = csc_on_device(n_users, n_items, ptr, ind, val, "cuda:0")
+    tr.colptr, tr.colind, tr.colval = csc_on_device(n_users, n_items, ptr, ind, val, f"cuda:{local}")
     va = bench.Mat(n_users, n_items, prob["val"])
     bench.log(f"data {train_nnz} ratings in {time.time()-t0:.1f}s")
     r = args.rank
     rng = np.random.default_rng(1)
     U0 = rng.uniform(-0.01, 0.01, size=(n_users, r)).astype(np.float32)
     V0 = rng.uniform(-0.01, 0.01, size=(n_items, r)).astype(np.float32)
-    eng = E.Engine(n_users, n_items, r)
+    eng = E.Engine(n_users, n_items, r, device=local)
     eng.upload_csr(E.TRAIN, tr, with_csc=True)
     eng.upload_csr(E.VAL, va, with_csc=False)
     eng.set_masks((np.diff(ptr) == 0).astype(np.uint8), (np.bincount(ind, minlength=n_items) == 0).astype(np.uint8))
     eng.set_aux(E.MF, np.diff(ptr).astype(np.int32), np.bincount(ind, minlength=n_items).astype(np.int32))
     eng.upload_factors(U0, V0)
     peak_gbs, _ = bench.measured_hbm_gbs()
-    out = {"algo": args.algo, "rank": r, "n_users": n_users, "n_items": n_items, "train_nnz": train_nnz}
+    out = {"algo": args.algo, "rank": r, "n_users": n_users, "n_items": n_items, "train_nnz": train_nnz, "n_gpus": world}
+    if world > 1:
+        # rows sharded in contiguous ranges of (nearly) equal rating counts; every solved row / updated entry
+        # is stored into all peers by the kernel that produces it (matfac_b200/csrc/comm.cu)
+        blobs = [None] * world
+        dist.all_gather_object(blobs, eng.comm_init(rank, world))
+        eng.comm_connect(blobs)
+        ucut = np.searchsorted(ptr, np.linspace(0, train_nnz, world + 1)).astype(int)
+        icut = np.searchsorted(tr.colptr, np.linspace(0, train_nnz, world + 1)).astype(int)
+        ucut[0] = icut[0] = 0
+        ucut[-1], icut[-1] = n_users, n_items
+        eng.set_row_range(E.USER, int(ucut[rank]), int(ucut[rank + 1]))
+        eng.set_row_range(E.ITEM, int(icut[rank]), int(icut[rank + 1]))
+
+    def finish(ms_list):
+        """max over ranks of the per-rank median"""
+        m = float(np.median(ms_list))
+        if dist is not None:
+            t = torch.tensor([m], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            m = float(t.item())
+        return m
+
     if args.algo == "als":
         eng.set_option("als_tensor_cores", args.tc)
         eng.set_option("als_dual", int(os.environ.get("ALS_DUAL", "1")))
@@ -92,12 +108,19 @@ def main():
             ms_u.append(eng.event_elapsed_ms(0, 1))
             ms_i.append(eng.event_elapsed_ms(1, 2))
         rp = 16 if r <= 16 else 32 if r <= 32 else 64 if r <= 64 else 128
-        ms = float(np.median(ms_u) + np.median(ms_i))
+        ms_u, ms_i = [finish(ms_u)], [finish(ms_i)]
+        ms = float(ms_u[0] + ms_i[0])
         gram_flop = 4.0 * r * r * train_nnz
         out.update(tensor_cores=args.tc, ms_user=float(np.median(ms_u)), ms_item=float(np.median(ms_i)), epoch_ms=ms,
                    gram_tflops_alg=gram_flop / (ms * 1e-3) / 1e12,
                    tensor_tflops_issued=(3 if (args.tc and r > 64) else 1) * 4.0 * rp * rp * train_nnz / (ms * 1e-3) / 1e12,
-                   gather_gbs=2.0 * train_nnz * r * 4 / (ms * 1e-3) / 1e9, val_rmse=eng.rmse(E.VAL))
+                   gather_gbs=2.0 * train_nnz * r * 4 / (ms * 1e-3) / 1e9)
+        ev = eng.eval(E.VAL)
+        if dist is not None:
+            t = torch.tensor([ev[0], ev[1]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t)
+            ev = [float(t[0]), float(t[1])]
+        out.update(val_rmse=float(np.sqrt(ev[0] / max(ev[1], 1))))
     elif args.algo == "ccdpp":
         eng.ccdpp_begin()
         dims = min(r, 8)
@@ -109,7 +132,7 @@ def main():
             eng.ccdpp_rank1(k, False, 5, 0.05, 0.05, 75)
         eng.event_record(1)
         eng.sync()
-        ms_k = eng.event_elapsed_ms(0, 1) / dims
+        ms_k = finish([eng.event_elapsed_ms(0, 1)]) / dims
         out.update(ms_per_rank1=ms_k, epoch_ms=ms_k * r, algorithmic_gbs=128.0 * train_nnz / (ms_k * 1e-3) / 1e9,
                    frac_of_hbm=128.0 * train_nnz / (ms_k * 1e-3) / 1e9 / peak_gbs, dims_timed=dims)
         eng.ccdpp_end()
@@ -123,11 +146,17 @@ def main():
             eng.event_record(1)
             eng.sync()
             ms.append(eng.event_elapsed_ms(0, 1))
-        m = float(np.median(ms))
+        m = finish(ms)
         gbs = (8.0 + 8.0 * r) * train_nnz / (m * 1e-3) / 1e9
         out.update(ms_objective_pass=m, algorithmic_gbs=gbs, frac_of_hbm=gbs / peak_gbs)
-    print(json.dumps(out), flush=True)
+    if world > 1:
+        out["comm_error"] = eng.comm_error()
+        eng.comm_barrier(); eng.sync(); dist.barrier()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
     eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
