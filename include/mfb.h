@@ -137,7 +137,8 @@ int mfb_sgd_epoch_flat(mfb_engine *e, int variant, float learn_rate, float ureg,
  * 0 = one band, a uniformly shuffled epoch as in modelMF.cpp:76-81 (banding converges at a different rate
  * per epoch than the reference's order); takes effect at the next mfb_sgd_plan), "als_tensor_cores" (rank > 64: 1 = tcgen05 3xTF32 Gram, 0 = fp32 CUDA-core
  * Gram), "als_dual" (1 = rows with fewer ratings than half the padded rank are solved through the len x len
- * dual system F (F F^T + reg I)^-1 r, default; 0 = always the rank x rank normal equations), "sgd_block_order" (stratified trainers: 0 = user-major runs, 1 = shuffled inside the
+ * dual system F (F F^T + reg I)^-1 r, default; 0 = always the rank x rank normal equations), "als_chunk" (ratings
+ * one CTA accumulates before a row is split over several CTAs that add into a workspace, default 16384), "sgd_block_order" (stratified trainers: 0 = user-major runs, 1 = shuffled inside the
  * blocks), "sgd_atomic" (1 = item rows updated by reductions, 0 = plain stores), "sgd_rotate" (1 = every
  * user run of the stratified kernel starts at a pseudo-random offset and wraps around, 0 = CSR
  * order as in modelMF.cpp:280). */

@@ -21,7 +21,6 @@
 namespace mfb {
 
 constexpr int kAlsTile = 32;    // factor rows staged per pipeline stage
-constexpr int kAlsChunk = 4096; // ratings per CTA before a row is split
 
 struct AlsArgs {
   const float *Fin;  // opposite side's factors [.][ld]
@@ -823,10 +822,10 @@ int als_half_step_launch(mfb_engine *e, int side, float reg) {
   if (!sp.built) {
     if (side == MFB_USER)
       MFB_TRY(build_seg_plan(e, m.rowptr, e->n_users, e->bad_user, e->row_begin[MFB_USER], e->row_end[MFB_USER],
-                             kAlsChunk, &sp));
+                             e->opt_als_chunk, &sp));
     else
       MFB_TRY(build_seg_plan(e, m.colptr, e->n_items, e->bad_item, e->row_begin[MFB_ITEM], e->row_end[MFB_ITEM],
-                             kAlsChunk, &sp));
+                             e->opt_als_chunk, &sp));
   }
   AlsArgs a;
   a.Fin = side == MFB_USER ? e->V : e->U;

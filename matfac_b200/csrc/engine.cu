@@ -568,10 +568,17 @@ extern "C" int mfb_set_option(mfb_engine *e, const char *name, double value) {
   else if (n == "sgd_flat_hot_lr") e->opt_sgd_flat_hot_lr = value;
   else if (n == "sgd_flat_inflight_frac") e->opt_sgd_flat_inflight_frac = value;
   else if (n == "sgd_flat_band_mb") e->opt_sgd_flat_band_mb = value;
+  else if (n == "sgd_flat_user_store") e->opt_sgd_flat_user_store = (int)value;
   else if (n == "sgd_atomic") e->opt_sgd_atomic = (int)value;
   else if (n == "sgd_rotate") e->opt_sgd_rotate = (int)value;
   else if (n == "als_tensor_cores") e->opt_als_tensor_cores = (int)value;
   else if (n == "als_dual") e->opt_als_dual = (int)value;
+  else if (n == "als_chunk") {
+    if (value < 64) return mfb::fail("mfb_set_option: als_chunk must be >= 64", __FILE__, __LINE__);
+    e->opt_als_chunk = (int)value;
+    e->mat[MFB_TRAIN].als_rows.release();
+    e->mat[MFB_TRAIN].als_cols.release();
+  }
   else if (n == "sgd_block_order") e->opt_sgd_block_order = (int)value;
   else return mfb::fail("mfb_set_option: unknown option", __FILE__, __LINE__);
   return 0;

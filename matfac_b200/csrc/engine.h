@@ -131,9 +131,11 @@ struct mfb_engine {
   double opt_sgd_flat_hot_lr = 0.15;  // shuffled kernel: cap on (hot-row concurrency x learning rate)
   double opt_sgd_flat_inflight_frac = 2e-4;  // shuffled kernel: ratings in flight <= this fraction of the epoch
   double opt_sgd_flat_band_mb = 0.0;  // shuffled kernel: user rows per band (MB of U), 0 = one band (the reference's order)
+  int opt_sgd_flat_user_store = 0;    // shuffled kernel: 1 = user rows by plain stores (Hogwild on U), 0 = reductions
   int opt_sgd_atomic = 1;             // item rows updated by vector reductions (no lost updates)
   int opt_sgd_block_order = 0;        // stratified trainers: 0 = user-major runs (reference order), 1 = shuffled inside the blocks
   int opt_sgd_rotate = 0;             // user runs start at a pseudo-random offset (de-correlates heavy users)
+  int opt_als_chunk = 16384;          // ratings per CTA before a row is split over several CTAs
   int opt_als_dual = 1;               // short rows: solve the len x len dual system instead of rank x rank
   int opt_als_tensor_cores = 1;       // rank > 64: Gram on tcgen05 (3xTF32); 0 = fp32 CUDA-core Gram
   cudaStream_t stream = nullptr;

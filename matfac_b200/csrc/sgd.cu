@@ -355,6 +355,7 @@ struct SgdArgs {
   const int32_t *seg_user, *seg_start, *seg_len;
   int nb, max_cnt, total;  // total = nb * max_cnt segment slots
   int rotate;              // start every run at a pseudo-random offset
+  int user_store;          // shuffled kernel: user rows written back with plain stores instead of reductions
   int32_t off[kMaxBlocks], cnt[kMaxBlocks];
   int *counter;  // dynamic work queue head
   float lr, ureg, ireg;
@@ -680,7 +681,8 @@ __global__ void __launch_bounds__(128) sgd_flat_kernel(const SgdArgs a) {
           if (base + 2 >= k) { du.z = 0.f; dv.z = 0.f; }
           if (base + 3 >= k) { du.w = 0.f; dv.w = 0.f; }
         }
-        red_add_v4(Uw + (size_t)user * a.nq + c * G + sl, du);
+        if (a.user_store) __stcg(Uw + (size_t)user * a.nq + c * G + sl, make_float4(uu.x + du.x, uu.y + du.y, uu.z + du.z, uu.w + du.w));
+        else red_add_v4(Uw + (size_t)user * a.nq + c * G + sl, du);
         red_add_v4(Vw + (size_t)it * a.nq + c * G + sl, dv);
       }
     }
@@ -747,6 +749,7 @@ static void fill_common(mfb_engine *e, SgdArgs &a, float lr, float ureg, float i
   a.perm_bits = 1;
   for (int r = 0; r < 3; r++) { a.perm_mul[r] = 1; a.perm_add[r] = 0; }
   a.rotate = e->opt_sgd_rotate;
+  a.user_store = e->opt_sgd_flat_user_store;
 }
 
 int sgd_subepoch_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int variant, float lr, float ureg,

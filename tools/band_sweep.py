@@ -17,7 +17,9 @@ eng = E.Engine(n_users, n_items, R)
 eng.upload_csr(E.TRAIN, bench.Mat(n_users, n_items, prob["train"]), with_csc=False)
 eng.upload_csr(E.VAL, bench.Mat(n_users, n_items, prob["val"]), with_csc=False)
 eng.set_masks((np.diff(ptr) == 0).astype(np.uint8), (np.bincount(ind, minlength=n_items) == 0).astype(np.uint8))
+ustore = int(os.environ.get("USTORE", "0"))
 for wps in (32, 64):
+    eng.set_option("sgd_flat_user_store", ustore)
     eng.set_option("sgd_flat_band_mb", mb)
     eng.set_option("sgd_warps_per_sm", wps)
     eng.sgd_plan(1)
@@ -29,4 +31,4 @@ for wps in (32, 64):
         eng.event_record(1)
         ms.append(eng.event_elapsed_ms(0, 1))
         rm.append(eng.rmse(E.VAL))
-    print(f"band_mb {mb:5.0f} warps/SM {wps} ms/epoch {np.median(ms[1:]):7.3f} G/s {int(ptr[-1])/np.median(ms[1:])/1e6:6.2f} val " + " ".join(f"{x:.4f}" for x in rm), flush=True)
+    print(f"ustore {ustore} band_mb {mb:5.0f} warps/SM {wps} ms/epoch {np.median(ms[1:]):7.3f} G/s {int(ptr[-1])/np.median(ms[1:])/1e6:6.2f} val " + " ".join(f"{x:.4f}" for x in rm), flush=True)

@@ -27,6 +27,7 @@ csc_on_device = bench.csc_on_device
 
 
 def main():
+    real_stdout = bench._protect_stdout()  # only the JSON line goes to stdout (NCCL prints its banner on fd 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--algo", default="als", choices=["als", "ccdpp", "eval"])
     ap.add_argument("--rank", type=int, default=128)
@@ -92,6 +93,9 @@ def main():
     if args.algo == "als":
         eng.set_option("als_tensor_cores", args.tc)
         eng.set_option("als_dual", int(os.environ.get("ALS_DUAL", "1")))
+        if "ALS_CHUNK" in os.environ:
+            eng.set_option("als_chunk", int(os.environ["ALS_CHUNK"]))
+            out["als_chunk"] = int(os.environ["ALS_CHUNK"])
         lens = np.diff(ptr)
         out.update(als_dual=int(os.environ.get("ALS_DUAL", "1")), users_le16=int((lens <= 16).sum()), users_le32=int((lens <= 32).sum()), users_le64=int((lens <= 64).sum()))
         eng.als_half_step(E.USER, args.reg)
@@ -153,7 +157,7 @@ def main():
         out["comm_error"] = eng.comm_error()
         eng.comm_barrier(); eng.sync(); dist.barrier()
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=real_stdout, flush=True)
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
