@@ -47,7 +47,7 @@ void DevCsr::release() {
 
 void SgdPlan::release() {
   if (owns_ratings) { cudaFree(item); cudaFree(val); }
-  cudaFree(seg_user); cudaFree(seg_start); cudaFree(seg_len); cudaFree(rat_user); cudaFree(work_counter);
+  cudaFree(seg_user); cudaFree(seg_start); cudaFree(seg_len); cudaFree(rat_user); cudaFree(work_counter); cudaFree(recs);
   cudaFree(part_items);
   *this = SgdPlan();
 }
@@ -569,6 +569,7 @@ extern "C" int mfb_set_option(mfb_engine *e, const char *name, double value) {
   else if (n == "sgd_flat_inflight_frac") e->opt_sgd_flat_inflight_frac = value;
   else if (n == "sgd_flat_band_mb") e->opt_sgd_flat_band_mb = value;
   else if (n == "sgd_flat_user_store") e->opt_sgd_flat_user_store = (int)value;
+  else if (n == "sgd_flat_debug") e->opt_sgd_flat_debug = (int)value;
   else if (n == "sgd_atomic") e->opt_sgd_atomic = (int)value;
   else if (n == "sgd_rotate") e->opt_sgd_rotate = (int)value;
   else if (n == "als_tensor_cores") e->opt_als_tensor_cores = (int)value;

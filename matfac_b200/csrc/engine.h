@@ -101,7 +101,8 @@ struct SgdPlan {
   float *val = nullptr;
   bool owns_ratings = false;
   int32_t *seg_user = nullptr, *seg_start = nullptr, *seg_len = nullptr;
-  int32_t *rat_user = nullptr;   // user of every rating (flat kernel; P == 1 plans only)
+  int32_t *rat_user = nullptr;   // user of every rating
+  void *recs = nullptr;          // int4 {user, item, rating bits, 0} per rating, shuffled inside every block range
   int *work_counter = nullptr;   // device work-queue head of the persistent kernel
   double hot_item_share = 0.0;   // largest item count / nnz: bounds useful concurrency
   double collision_mass = 0.0;   // sum over items of (count / nnz)^2: P(two random ratings share an item)
@@ -132,6 +133,7 @@ struct mfb_engine {
   double opt_sgd_flat_inflight_frac = 2e-4;  // shuffled kernel: ratings in flight <= this fraction of the epoch
   double opt_sgd_flat_band_mb = 0.0;  // shuffled kernel: user rows per band (MB of U), 0 = one band (the reference's order)
   int opt_sgd_flat_user_store = 0;    // shuffled kernel: 1 = user rows by plain stores (Hogwild on U), 0 = reductions
+  int opt_sgd_flat_debug = 0;         // timing diagnostics of the shuffled kernel (results are wrong when set)
   int opt_sgd_atomic = 1;             // item rows updated by vector reductions (no lost updates)
   int opt_sgd_block_order = 0;        // stratified trainers: 0 = user-major runs (reference order), 1 = shuffled inside the blocks
   int opt_sgd_rotate = 0;             // user runs start at a pseudo-random offset (de-correlates heavy users)

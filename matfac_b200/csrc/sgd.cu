@@ -116,6 +116,66 @@ __global__ void rat_user_kernel(const int64_t *__restrict__ rowptr, int32_t nrow
   out[j] = lo;
 }
 
+// ---- physically shuffled rating records for the shuffled kernel -------------------------------
+// The epoch order of the serial trainers is a random permutation (modelMF.cpp:76-81).  Fetching
+// (user, item, rating) through a permuted index costs three random 4-byte DRAM reads per rating —
+// measured: 11.3 of the kernel's 17.2 ms (tools/flat_limits.py).  So the records are shuffled ONCE, at
+// plan time, inside every block range (whole matrix, user band or P x P stratum block) into an array of
+// 16-byte records; an epoch then visits groups of 32 consecutive records (one coalesced 512-byte load per
+// warp) in a freshly keyed pseudo-random order of the groups.  Every rating is visited once per epoch, the
+// neighbours inside a group are random ratings, and the order of the groups changes every epoch.
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x);
+
+__device__ __forceinline__ uint32_t keyed_bijection(uint32_t x, uint32_t n, uint64_t key) {
+  // multiply / xor-shift rounds on the next power of two, cycle-walking back into [0, n)
+  uint32_t bits = 1;
+  while ((1ull << bits) < n) bits++;
+  const uint32_t mask = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
+  const uint32_t sh = (bits + 1) / 2;
+  const uint64_t h0 = mix64(key), h1 = mix64(key ^ 0x9E3779B97F4A7C15ull), h2 = mix64(key + 0x632BE59BD9B4E019ull);
+  const uint32_t m0 = (uint32_t)(h0 >> 7) | 1u, m1 = (uint32_t)(h1 >> 7) | 1u, m2 = (uint32_t)(h2 >> 7) | 1u;
+  const uint32_t a0 = (uint32_t)(h0 >> 40), a1 = (uint32_t)(h1 >> 40), a2 = (uint32_t)(h2 >> 40);
+  do {
+    x = (x * m0 + a0) & mask; x ^= x >> sh;
+    x = (x * m1 + a1) & mask; x ^= x >> sh;
+    x = (x * m2 + a2) & mask; x ^= x >> sh;
+  } while (x >= n);
+  return x;
+}
+
+__global__ void sgd_shuffle_records_kernel(const int32_t *__restrict__ rat_user, const int32_t *__restrict__ item,
+                                           const float *__restrict__ val, int64_t n, const int64_t *__restrict__ blk_off,
+                                           int nblk, uint64_t seed, int4 *__restrict__ recs) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  int lo = 0, hi = nblk;  // block b with blk_off[b] <= q < blk_off[b + 1]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (blk_off[mid] <= q) lo = mid; else hi = mid;
+  }
+  const int64_t off = blk_off[lo];
+  const uint32_t nb = (uint32_t)(blk_off[lo + 1] - off);
+  const int64_t j = off + keyed_bijection((uint32_t)(q - off), nb, seed * 0x100000001B3ull + (uint64_t)lo);
+  recs[q] = make_int4(__ldg(rat_user + j), __ldg(item + j), __float_as_int(__ldg(val + j)), 0);
+}
+
+// builds pl.recs from (rat_user, item, val); ranges = starts of the shuffle blocks (ascending) + end
+static int sgd_build_records(mfb_engine *e, const std::vector<int64_t> &ranges) {
+  SgdPlan &pl = e->sgd;
+  cudaStream_t st = e->stream;
+  const int64_t n = ranges.back();
+  MFB_CUDA(cudaMalloc(&pl.recs, sizeof(int4) * (size_t)(n > 0 ? n : 1)));
+  if (n == 0) return 0;
+  int64_t *d_off;
+  MFB_CUDA(cudaMalloc(&d_off, sizeof(int64_t) * ranges.size()));
+  MFB_CUDA(cudaMemcpyAsync(d_off, ranges.data(), sizeof(int64_t) * ranges.size(), cudaMemcpyHostToDevice, st));
+  MFB_LAUNCH(sgd_shuffle_records_kernel, (unsigned)((n + 255) / 256), 256, 0, st, pl.rat_user, pl.item, pl.val, n, d_off,
+             (int)ranges.size() - 1, 0x5EEDULL, reinterpret_cast<int4 *>(pl.recs));
+  MFB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_off);
+  return 0;
+}
+
 static int sgd_plan_common(mfb_engine *e) {
   SgdPlan &pl = e->sgd;
   const DevCsr &m = e->mat[MFB_TRAIN];
@@ -196,6 +256,7 @@ int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int
       }
       MFB_CUDA(cudaStreamSynchronize(st));
     }
+    MFB_TRY(sgd_build_records(e, pl.band_rat_off));
     pl.built = true;
     return 0;
   }
@@ -340,6 +401,14 @@ int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int
   }
   MFB_CUDA(cudaStreamSynchronize(st));
   cudaFree(keys); cudaFree(keys2); cudaFree(idx); cudaFree(idx2); cudaFree(d_up); cudaFree(d_ip);
+  {  // shuffle blocks = the P x P stratum blocks (block-major order, the dropped bucket excluded)
+    std::vector<int64_t> ranges;
+    for (int b = 0; b < nblk; b++)
+      if (pl.blk_nnz[b] > 0) ranges.push_back(pl.blk_rat_off[b]);
+    ranges.push_back(kept);
+    if (ranges.size() == 1) ranges.insert(ranges.begin(), 0);
+    MFB_TRY(sgd_build_records(e, ranges));
+  }
   pl.built = true;
   return 0;
 }
@@ -356,20 +425,22 @@ struct SgdArgs {
   int nb, max_cnt, total;  // total = nb * max_cnt segment slots
   int rotate;              // start every run at a pseudo-random offset
   int user_store;          // shuffled kernel: user rows written back with plain stores instead of reductions
+  int debug;               // shuffled kernel, timing diagnostics: 1 skip U write, 2 skip V write, 4 skip u load, 8 skip v load
   int32_t off[kMaxBlocks], cnt[kMaxBlocks];
   int *counter;  // dynamic work queue head
   float lr, ureg, ireg;
   const Aux *aux_u, *aux_i;
   const float *cdf;
   uint64_t seed, counter_id;
-  // shuffled kernel: visiting order p(t) = a keyed pseudo-random permutation of [0, n) over the
-  // concatenated rating ranges of the scheduled blocks (range b starts at rat_off[b], cumulative
-  // sizes in rat_cum).  The permutation is a 3-round multiply / xor-shift bijection on the next
-  // power of two with cycle walking.
-  int64_t n;
+  // shuffled kernel: the scheduled ranges of the shuffled record array are cut into groups of 32
+  // records; the groups are visited in the order p(t) = a keyed pseudo-random permutation of [0, n)
+  // (3-round multiply / xor-shift bijection on the next power of two with cycle walking).
+  int64_t n;  // number of 32-record groups of this launch
   uint32_t perm_bits, perm_mul[3], perm_add[3];
-  int32_t rat_off[kMaxBlocks];
-  int32_t rat_cum[kMaxBlocks + 1];
+  const int4 *recs;                  // shuffled records (see sgd_shuffle_records_kernel)
+  int32_t rat_off[kMaxBlocks];       // first record of every scheduled range
+  int32_t rat_len[kMaxBlocks];       // records in the range
+  int32_t grp_cum[kMaxBlocks + 1];   // cumulative group counts of the ranges
 };
 
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
@@ -593,97 +664,109 @@ __device__ __forceinline__ uint32_t permute_index(const SgdArgs &a, uint32_t x) 
   return x;
 }
 
-// Serial / Hogwild trainers (modelMF.cpp:83-105, :1747-1763): every sub-warp owns one rating at
-// a time, visited in a pseudo-random order; both rows are read with 128-bit loads and updated
-// with vector reductions.
+// Serial / Hogwild trainers (modelMF.cpp:83-105, :1747-1763): a warp takes a group of 32 shuffled
+// records with one coalesced 512-byte load (the next group is fetched while the current one is
+// processed) and works through it 32 / G ratings at a time — every sub-warp of G lanes owns one rating:
+// both factor rows are read with 128-bit loads and updated with vector reductions.
 template <int G, int VPL, int VARIANT>
 __global__ void __launch_bounds__(128) sgd_flat_kernel(const SgdArgs a) {
+  constexpr unsigned kFull = 0xFFFFFFFFu;
   constexpr bool TRUNC = (VARIANT == MFB_TMF || VARIANT == MFB_TMFDROPOUT);
+  constexpr int PER = 32 / G;  // ratings a warp has in flight
   const int lane = threadIdx.x & 31;
-  const int sl = lane & (G - 1);
-  const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / G;
-  const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-  const int64_t warp_first = gid - (lane / G);  // group id of this warp's first sub-warp
+  const int sl = lane & (G - 1), sub = lane / G;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   float4 *Uw = reinterpret_cast<float4 *>(a.U), *Vw = reinterpret_cast<float4 *>(a.V);
   const float lr = a.lr, two_ureg = 2.0f * a.ureg, two_ireg = 2.0f * a.ireg;
   bool own[VPL];
 #pragma unroll
   for (int c = 0; c < VPL; c++) own[c] = (c * G + sl) < a.nq;
-  // the (user, item, rating) record of the next visit is fetched one iteration ahead, so that its
-  // latency is not in front of the two row gathers
-  auto fetch_record = [&](int64_t t, int64_t &p, int &user, int &it, float &rt) {
-    p = 0; user = 0; it = 0; rt = 0.f;
+  // lane `lane` holds record `lane` of the group; q0 = its position in the record array (RNG counter)
+  auto fetch_group = [&](int64_t t, int4 &rec, int &cnt, uint32_t &q0) {
+    rec = make_int4(0, 0, 0, 0); cnt = 0; q0 = 0;
     if (t < a.n) {
-      p = permute_index(a, (uint32_t)t);
-      if (a.nb > 1) {  // which scheduled block does p fall in
-        int b = 0;
-        while (b + 1 < a.nb && p >= a.rat_cum[b + 1]) b++;
-        p = a.rat_off[b] + (p - a.rat_cum[b]);
-      } else {
-        p += a.rat_off[0];
-      }
-      user = __ldg(a.rat_user + p);
-      it = __ldg(a.item + p);
-      rt = __ldg(a.val + p);
+      uint32_t g = permute_index(a, (uint32_t)t);
+      int b = 0;
+      while (b + 1 < a.nb && g >= (uint32_t)a.grp_cum[b + 1]) b++;
+      g -= (uint32_t)a.grp_cum[b];
+      cnt = min(32, a.rat_len[b] - (int)g * 32);
+      q0 = (uint32_t)a.rat_off[b] + g * 32u;
+      if (lane < cnt) rec = __ldcs(a.recs + q0 + lane);
     }
   };
-  int64_t n_p;
-  int n_user, n_it;
-  float n_rt;
-  fetch_record(warp_first + (lane / G), n_p, n_user, n_it, n_rt);
-  for (int64_t t0 = warp_first; t0 < a.n; t0 += n_groups) {  // warp-uniform trip count
-    const int64_t t = t0 + (lane / G);
-    const bool on = t < a.n;
-    const int64_t p = n_p;
-    const int user = n_user, it = n_it;
-    const float rt = n_rt;
-    fetch_record(t + n_groups, n_p, n_user, n_it, n_rt);
-    int pay = 0;
-    float4 u[VPL], v[VPL];
+  int4 n_rec;
+  int n_cnt;
+  uint32_t n_q0;
+  fetch_group(wid, n_rec, n_cnt, n_q0);
+  for (int64_t t = wid; t < a.n; t += n_warps) {  // warp-uniform trip count
+    const int4 rec = n_rec;
+    const int cnt = n_cnt;
+    const uint32_t q0 = n_q0;
+    fetch_group(t + n_warps, n_rec, n_cnt, n_q0);
+#pragma unroll 2
+    for (int i = 0; i < G; i++) {
+      if (i * PER >= cnt) break;  // warp-uniform
+      const int r = i * PER + sub;
+      const bool on = r < cnt;
+      const int user = __shfl_sync(kFull, rec.x, r), it = __shfl_sync(kFull, rec.y, r);
+      const float rt = __int_as_float(__shfl_sync(kFull, rec.z, r));
+      int pay = 0;
+      float4 u[VPL], v[VPL];
 #pragma unroll
-    for (int c = 0; c < VPL; c++) u[c] = v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (on) {
+      for (int c = 0; c < VPL; c++) u[c] = v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (on) {
 #pragma unroll
-      for (int c = 0; c < VPL; c++)
-        if (own[c]) {
-          u[c] = __ldcg(Uw + (size_t)user * a.nq + c * G + sl);
-          v[c] = __ldcg(Vw + (size_t)it * a.nq + c * G + sl);
+        for (int c = 0; c < VPL; c++)
+          if (own[c]) {
+            if (!(a.debug & 4)) u[c] = __ldcg(Uw + (size_t)user * a.nq + c * G + sl);
+            if (!(a.debug & 8)) v[c] = __ldcg(Vw + (size_t)it * a.nq + c * G + sl);
+          }
+        if (VARIANT != MFB_MF) {
+          const Aux au = a.aux_u[user], ai = a.aux_i[it];
+          pay = (au.freq < ai.freq) ? au.train : ai.train;
+          if (VARIANT == MFB_TMFDROPOUT) pay = poisson_rank(a.cdf, a.rank, pay, a.seed, a.counter_id, q0 + (uint32_t)r);
         }
-      if (VARIANT != MFB_MF) {
-        const Aux au = a.aux_u[user], ai = a.aux_i[it];
-        pay = (au.freq < ai.freq) ? au.train : ai.train;
-        if (VARIANT == MFB_TMFDROPOUT) pay = poisson_rank(a.cdf, a.rank, pay, a.seed, a.counter_id, (uint32_t)p);
       }
-    }
-    const int k = TRUNC ? pay : a.rank;
-    const float pdot = dot_slice<G, VPL, TRUNC>(u, v, sl, k);
-    float g = rt - pdot;
-    if (VARIANT == MFB_IFWMF) g *= __int_as_float(pay);
-    const float m2g = -2.0f * g;
-    if (on) {
+      const int k = TRUNC ? pay : a.rank;
+      const float pdot = dot_slice<G, VPL, TRUNC>(u, v, sl, k);
+      float g = rt - pdot;
+      if (VARIANT == MFB_IFWMF) g *= __int_as_float(pay);
+      const float m2g = -2.0f * g;
+      if (on) {
 #pragma unroll
-      for (int c = 0; c < VPL; c++) {
-        if (!own[c]) continue;
-        const int base = (c * G + sl) * 4;
-        if (TRUNC && base >= k) continue;
-        const float4 uu = u[c], vv = v[c];
-        float4 du, dv;
-        du.x = -lr * fmaf(two_ureg, uu.x, m2g * vv.x);
-        du.y = -lr * fmaf(two_ureg, uu.y, m2g * vv.y);
-        du.z = -lr * fmaf(two_ureg, uu.z, m2g * vv.z);
-        du.w = -lr * fmaf(two_ureg, uu.w, m2g * vv.w);
-        dv.x = -lr * fmaf(two_ireg, vv.x, m2g * (uu.x + du.x));
-        dv.y = -lr * fmaf(two_ireg, vv.y, m2g * (uu.y + du.y));
-        dv.z = -lr * fmaf(two_ireg, vv.z, m2g * (uu.z + du.z));
-        dv.w = -lr * fmaf(two_ireg, vv.w, m2g * (uu.w + du.w));
-        if (TRUNC) {
-          if (base + 1 >= k) { du.y = 0.f; dv.y = 0.f; }
-          if (base + 2 >= k) { du.z = 0.f; dv.z = 0.f; }
-          if (base + 3 >= k) { du.w = 0.f; dv.w = 0.f; }
+        for (int c = 0; c < VPL; c++) {
+          if (!own[c]) continue;
+          const int base = (c * G + sl) * 4;
+          if (TRUNC && base >= k) continue;
+          const float4 uu = u[c], vv = v[c];
+          float4 du, dv;
+          du.x = -lr * fmaf(two_ureg, uu.x, m2g * vv.x);
+          du.y = -lr * fmaf(two_ureg, uu.y, m2g * vv.y);
+          du.z = -lr * fmaf(two_ureg, uu.z, m2g * vv.z);
+          du.w = -lr * fmaf(two_ureg, uu.w, m2g * vv.w);
+          dv.x = -lr * fmaf(two_ireg, vv.x, m2g * (uu.x + du.x));
+          dv.y = -lr * fmaf(two_ireg, vv.y, m2g * (uu.y + du.y));
+          dv.z = -lr * fmaf(two_ireg, vv.z, m2g * (uu.z + du.z));
+          dv.w = -lr * fmaf(two_ireg, vv.w, m2g * (uu.w + du.w));
+          if (TRUNC) {
+            if (base + 1 >= k) { du.y = 0.f; dv.y = 0.f; }
+            if (base + 2 >= k) { du.z = 0.f; dv.z = 0.f; }
+            if (base + 3 >= k) { du.w = 0.f; dv.w = 0.f; }
+          }
+          if (a.debug & 1) {  // diagnostics only (option sgd_flat_debug): keep the value alive without writing
+            if (du.x == 12345.678f) Uw[0] = du;
+          } else if (a.user_store) {
+            __stcg(Uw + (size_t)user * a.nq + c * G + sl, make_float4(uu.x + du.x, uu.y + du.y, uu.z + du.z, uu.w + du.w));
+          } else {
+            red_add_v4(Uw + (size_t)user * a.nq + c * G + sl, du);
+          }
+          if (a.debug & 2) {
+            if (dv.x == 12345.678f) Vw[0] = dv;
+          } else {
+            red_add_v4(Vw + (size_t)it * a.nq + c * G + sl, dv);
+          }
         }
-        if (a.user_store) __stcg(Uw + (size_t)user * a.nq + c * G + sl, make_float4(uu.x + du.x, uu.y + du.y, uu.z + du.z, uu.w + du.w));
-        else red_add_v4(Uw + (size_t)user * a.nq + c * G + sl, du);
-        red_add_v4(Vw + (size_t)it * a.nq + c * G + sl, dv);
       }
     }
   }
@@ -750,6 +833,7 @@ static void fill_common(mfb_engine *e, SgdArgs &a, float lr, float ureg, float i
   for (int r = 0; r < 3; r++) { a.perm_mul[r] = 1; a.perm_add[r] = 0; }
   a.rotate = e->opt_sgd_rotate;
   a.user_store = e->opt_sgd_flat_user_store;
+  a.debug = e->opt_sgd_flat_debug;
 }
 
 int sgd_subepoch_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int variant, float lr, float ureg,
@@ -782,7 +866,7 @@ int sgd_subepoch_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int va
 #undef MFB_PICK
 }
 
-// keyed permutation parameters of one launch: a fresh order per (seed, epoch, band)
+// keyed permutation parameters of one launch: a fresh order of the groups per (seed, epoch, band)
 static void fill_perm(SgdArgs &a, int64_t n, uint64_t seed, uint64_t counter, uint64_t salt) {
   a.n = n;
   a.perm_bits = 1;
@@ -800,14 +884,17 @@ int sgd_flat_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int varian
   SgdPlan &pl = e->sgd;
   SgdArgs a;
   fill_common(e, a, lr, ureg, ireg, seed, counter);
+  a.recs = reinterpret_cast<const int4 *>(pl.recs);
   a.nb = nb; a.max_cnt = 0; a.total = 0;
-  a.rat_cum[0] = 0;
+  a.grp_cum[0] = 0;
+  int64_t n_all = 0;
   for (int i = 0; i < nb; i++) {
     size_t bid = (size_t)blocks[2 * i] * pl.P + blocks[2 * i + 1];
     a.rat_off[i] = (int32_t)pl.blk_rat_off[bid];
-    a.rat_cum[i + 1] = a.rat_cum[i] + (int32_t)pl.blk_nnz[bid];
+    a.rat_len[i] = (int32_t)pl.blk_nnz[bid];
+    a.grp_cum[i + 1] = a.grp_cum[i] + (int32_t)((pl.blk_nnz[bid] + 31) / 32);
+    n_all += pl.blk_nnz[bid];
   }
-  const int64_t n_all = a.rat_cum[nb];
   if (n_all == 0) return 0;
   const int nq = a.nq;
   // The shuffled kernel reads both rows right before it adds its increments, so concurrency only
@@ -835,8 +922,8 @@ int sgd_flat_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int varian
   const double saved_cap = e->opt_sgd_max_hot_inflight;
   e->opt_sgd_max_hot_inflight = hot_cap;
   struct Restore { mfb_engine *e; double v; ~Restore() { e->opt_sgd_max_hot_inflight = v; } } restore{e, saved_cap};
-  auto launch = [&](const SgdArgs &b) -> int {
-#define MFB_PICK(G, VPL) return launch_flat<G, VPL>(e, b, variant, pick_workers(e, G, n_all, hot_share, 1))
+  auto launch = [&](const SgdArgs &b, int64_t n_ratings) -> int {
+#define MFB_PICK(G, VPL) return launch_flat<G, VPL>(e, b, variant, pick_workers(e, G, n_ratings, hot_share, 1))
     if (nq <= 2) MFB_PICK(2, 1);
     if (nq <= 4) MFB_PICK(4, 1);
     if (nq <= 8) MFB_PICK(8, 1);
@@ -848,9 +935,8 @@ int sgd_flat_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int varian
   // User bands (option sgd_flat_band_mb, off by default): the epoch visits the ratings band by band, in a
   // fresh random order inside each band and a rotated band order per epoch, so that a band's user rows
   // stay in the 126 MB L2.  Measured on the bench matrix (gpurun_out/band_sweep.log, profiles/): only
-  // 3-6 % faster (the kernel is bound by latency and L2 reductions, not by the U misses) and the
-  // validation curve leaves the reference's (a uniformly shuffled epoch, modelMF.cpp:76-81) by up to
-  // 10 % at equal epochs — hence not the default.
+  // 3-6 % faster and the validation curve leaves the reference's (a uniformly shuffled epoch,
+  // modelMF.cpp:76-81) by up to 10 % at equal epochs — hence not the default.
   const int nbands = (nb == 1 && pl.P == 1) ? (int)pl.band_rat_off.size() - 1 : 0;
   if (nbands > 1) {
     const int first = (int)(mix64(seed ^ (counter * 0x9E3779B97F4A7C15ull)) % (uint64_t)nbands);
@@ -860,14 +946,15 @@ int sgd_flat_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int varian
       if (n <= 0) continue;
       SgdArgs c = a;
       c.rat_off[0] = (int32_t)lo;
-      c.rat_cum[1] = (int32_t)n;
-      fill_perm(c, n, seed, counter, (uint64_t)b + 1);
-      MFB_TRY(launch(c));
+      c.rat_len[0] = (int32_t)n;
+      c.grp_cum[1] = (int32_t)((n + 31) / 32);
+      fill_perm(c, c.grp_cum[1], seed, counter, (uint64_t)b + 1);
+      MFB_TRY(launch(c, n));
     }
     return 0;
   }
-  fill_perm(a, n_all, seed, counter, 0);
-  return launch(a);
+  fill_perm(a, a.grp_cum[nb], seed, counter, 0);
+  return launch(a, n_all);
 }
 
 }  // namespace mfb
