@@ -115,6 +115,7 @@ struct SgdPlan {
   int32_t *part_items = nullptr;                  // item ids grouped by item part (device)
   std::vector<int32_t> part_item_off;             // [P+1]
   bool built = false;
+  bool runs_built = true;  // user runs present (P == 1 plans build them lazily)
   void release();
 };
 

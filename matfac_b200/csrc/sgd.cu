@@ -226,19 +226,14 @@ int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int
   pl.blk_nnz.assign((size_t)P * P, 0);
   pl.blk_rat_off.assign((size_t)P * P, 0);
   if (P == 1 && user_part == nullptr) {
-    // whole matrix = one block; runs are the CSR rows themselves
-    SegPlan sp;
-    MFB_TRY(build_seg_plan(e, m.rowptr, e->n_users, e->bad_user, 0, e->n_users, 0, &sp));
+    // whole matrix = one block; the user runs of the user-major kernel (the CSR rows themselves) are built
+    // on first use (sgd_ensure_runs): the shuffled kernel does not need them
     pl.item = m.rowind;
     pl.val = m.rowval;
     pl.owns_ratings = false;
-    pl.n_seg = sp.n_seg;
-    pl.seg_user = sp.row; pl.seg_start = sp.start; pl.seg_len = sp.len;
-    sp.row = sp.start = sp.len = nullptr;
-    sp.release();
     pl.nnz = m.nnz;
-    pl.blk_seg_cnt[0] = pl.n_seg;
     pl.blk_nnz[0] = m.nnz;
+    pl.runs_built = false;
     MFB_CUDA(cudaMalloc(&pl.rat_user, sizeof(int32_t) * (size_t)(m.nnz > 0 ? m.nnz : 1)));
     if (m.nnz > 0)
       MFB_LAUNCH(rat_user_kernel, (unsigned)((m.nnz + 255) / 256), 256, 0, st, m.rowptr, e->n_users, m.nnz, pl.rat_user);
@@ -836,8 +831,24 @@ static void fill_common(mfb_engine *e, SgdArgs &a, float lr, float ureg, float i
   a.debug = e->opt_sgd_flat_debug;
 }
 
+static int sgd_ensure_runs(mfb_engine *e) {
+  SgdPlan &pl = e->sgd;
+  if (pl.runs_built) return 0;
+  const DevCsr &m = e->mat[MFB_TRAIN];
+  SegPlan sp;
+  MFB_TRY(build_seg_plan(e, m.rowptr, e->n_users, e->bad_user, 0, e->n_users, 0, &sp));
+  pl.n_seg = sp.n_seg;
+  pl.seg_user = sp.row; pl.seg_start = sp.start; pl.seg_len = sp.len;
+  sp.row = sp.start = sp.len = nullptr;
+  sp.release();
+  pl.blk_seg_cnt[0] = pl.n_seg;
+  pl.runs_built = true;
+  return 0;
+}
+
 int sgd_subepoch_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int variant, float lr, float ureg,
                         float ireg, uint64_t seed, uint64_t counter) {
+  MFB_TRY(sgd_ensure_runs(e));
   const SgdPlan &pl = e->sgd;
   SgdArgs a;
   fill_common(e, a, lr, ureg, ireg, seed, counter);
