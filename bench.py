@@ -509,6 +509,10 @@ def main():
         eng.upload_csr(E.VAL, lva, with_csc=False)
         eng.set_masks(bad_u, bad_i)
         eng.upload_factors(U0, V0)
+        # in-flight budget of the shuffled kernel per rank: 8e-4 of the rank's ratings (default 2e-4, calibrated for the
+        # first epochs of small matrices).  tools/dsgd_sweep.py on this matrix, 8 x 8 strata: validation RMSE after 10
+        # epochs 0.5348 at 8e-4 against 0.5321 at 2e-4, epoch 3.5 ms against 6.9 ms (profiles/r1_dsgd_scaling.md)
+        eng.set_option("sgd_flat_inflight_frac", 8e-4)
         eng.sgd_plan(P, np.where(mine, user_part, -1).astype(np.int32), item_part)
         eng.set_option("sgd_block_order", 1)  # shuffled inside the blocks: full concurrency
         blobs = [None] * world
@@ -592,12 +596,14 @@ def main():
     achieved = alg_bytes * args.steps / (ms_dev * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": DRAM_TRAFFIC_BYTES_PER_EPOCH if world == 1 and args.scale == 1.0 else None, "peak_source": peak_src,
-                "kernel": "sgd_flat_kernel<16,1,MF>", "algorithmic_bytes_per_update": 16 * RANK + 12,
+                "kernel": "sgd_flat_kernel<16,1,MF> + sgd_hot_kernel<4,4,MF> (hot item rows, concurrent stream)",
+                "algorithmic_bytes_per_update": 16 * RANK + 12,
                 "launches_per_epoch": launches / args.steps,
                 "note": "achieved = algorithmic bytes (u,v read + reduced, 12 B rating record, SURVEY 8d) of one epoch on this rank / "
-                        "its device time; traffic = dram__bytes_read+write per epoch from the ncu --set full capture in profiles/. "
+                        "its device time (both kernels of the epoch run concurrently inside the timed region); traffic = "
+                        "dram__bytes_read+write of the two kernels per epoch from the ncu --set full captures in profiles/. "
                         "U (123 MB) and V (4.5 MB) stay in the 126 MB L2, so DRAM traffic is a tenth of the algorithmic bytes and "
-                        "frac can exceed 1: the kernel is bound by L2 reductions, not by HBM (profiles/r1_sgd_flat.md)"}
+                        "frac can exceed 1: the epoch is bound by L2 reductions and instruction issue, not by HBM (profiles/r1_sgd_flat.md)"}
     if world > 1:
         roofline["per_rank_nnz"] = nnz_per_rank
 

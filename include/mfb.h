@@ -132,7 +132,9 @@ int mfb_sgd_epoch_flat(mfb_engine *e, int variant, float learn_rate, float ureg,
  * "sgd_max_hot_inflight" (bound on concurrent updates of the hottest item row, default 8),
  * "sgd_flat_hot_lr" (shuffled kernel: the hottest row's concurrency is capped at value / learn_rate,
  * default 0.15), "sgd_flat_inflight_frac" (shuffled kernel: ratings in flight <= this fraction of
- * the epoch, default 2e-4), "sgd_flat_band_mb" (shuffled kernel, whole-matrix plans: the epoch visits
+ * the epoch, default 2e-4), "sgd_flat_launch_lr" (shuffled kernel: ratings in flight <= value / learn_rate x the
+ * ratings of the launch, default 1.2e-5: a short launch — one stratum block — must not be in flight all at once),
+ * "sgd_flat_band_mb" (shuffled kernel, whole-matrix plans: the epoch visits
  * the ratings in bands of users whose rows take this many MB, so that a band of U stays in L2; default
  * 0 = one band, a uniformly shuffled epoch as in modelMF.cpp:76-81 (banding converges at a different rate
  * per epoch than the reference's order); takes effect at the next mfb_sgd_plan), "als_tensor_cores" (rank > 64: 1 = tcgen05 3xTF32 Gram, 0 = fp32 CUDA-core
@@ -145,6 +147,22 @@ int mfb_sgd_epoch_flat(mfb_engine *e, int variant, float learn_rate, float ureg,
 int mfb_set_option(mfb_engine *e, const char *name, double value);
 /* number of ratings the given blocks hold (for updates/s accounting) */
 int mfb_sgd_block_nnz(mfb_engine *e, const int32_t *blocks, int32_t nb, int64_t *nnz);
+/* Diagnostics: the rating records of one stratum block as the shuffled kernel visits them.  records =
+ * [mfb_sgd_block_nnz of the block][4] int32 {user, item, rating bits, 0}: first *cold_records records in the
+ * block's shuffled order, then one contiguous list per hot item (options "sgd_hot", "sgd_hot_min_count",
+ * "sgd_hot_inflight", "sgd_hot_max_lists": an item of which the shuffled kernel would keep more than sgd_hot_inflight
+ * (default 16) updates in flight when it runs the block on the whole machine, and that holds at least
+ * sgd_hot_min_count (default 1024) of the block's ratings, is trained by one CTA that keeps the item row in shared
+ * memory — the sgd_hot_max_lists (default and maximum 127) most rated ones when there are more; "sgd_hot_batch" ratings per mini-batch round of such a CTA, 0 = automatic).
+ * lists = [*n_lists][3] int32 {item, first record relative to the block, records}; lists may be NULL or hold
+ * sgd_hot_max_lists (<= 127) entries. */
+int mfb_debug_sgd_records(mfb_engine *e, int32_t user_part, int32_t item_part, int32_t *records,
+                          int64_t *cold_records, int32_t *lists, int32_t *n_lists);
+/* Diagnostics: out = {sum over users of degree x |u|^2, sum of degrees, ratings per round the hot CTAs last used}.
+ * The batch of a hot CTA is bounded on the device by sgd_hot_stab / (learn_rate x out[0] / out[1]) (option
+ * "sgd_hot_stab", default 0.5: a mini-batch of T ratings of one item is only stable while learn_rate x T x |u|^2 < 1)
+ * and on the host by 64 and by sgd_flat_hot_lr / learn_rate; zeros when the plan has no hot lists. */
+int mfb_debug_sgd_hot_batch(mfb_engine *e, double out[3]);
 
 /* ---- ALS (modelMF.cpp:795-882) -------------------------------------------------------------
  * side = MFB_USER: for every valid user solve (sum_{i in row, r>0} v v^T + reg I) x = sum r v

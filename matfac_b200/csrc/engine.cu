@@ -48,7 +48,7 @@ void DevCsr::release() {
 void SgdPlan::release() {
   if (owns_ratings) { cudaFree(item); cudaFree(val); }
   cudaFree(seg_user); cudaFree(seg_start); cudaFree(seg_len); cudaFree(rat_user); cudaFree(work_counter); cudaFree(recs);
-  cudaFree(part_items);
+  cudaFree(part_items); cudaFree(hot_lists); cudaFree(hot_stat);
   *this = SgdPlan();
 }
 
@@ -227,6 +227,13 @@ extern "C" int mfb_create(const mfb_config *cfg, mfb_engine **out) {
   MFB_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
   e->sm_count = prop.multiProcessorCount;
   MFB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  {
+    int lo_prio = 0, hi_prio = 0;
+    MFB_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    MFB_CUDA(cudaStreamCreateWithPriority(&e->stream_hot, cudaStreamNonBlocking, hi_prio));
+    MFB_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    MFB_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  }
   for (int i = 0; i < 16; i++) MFB_CUDA(cudaEventCreate(&e->events[i]));
   size_t ub = sizeof(float) * (size_t)e->n_users * e->ld, vb = sizeof(float) * (size_t)e->n_items * e->ld;
   MFB_CUDA(cudaMalloc(&e->U, ub));
@@ -266,6 +273,8 @@ extern "C" void mfb_destroy(mfb_engine *e) {
     }
   cudaFree(e->comm.own_flags);
   for (int i = 0; i < 16; i++) cudaEventDestroy(e->events[i]);
+  cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join);
+  cudaStreamDestroy(e->stream_hot);
   cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -567,11 +576,23 @@ extern "C" int mfb_set_option(mfb_engine *e, const char *name, double value) {
   else if (n == "sgd_max_hot_inflight") e->opt_sgd_max_hot_inflight = value;
   else if (n == "sgd_flat_hot_lr") e->opt_sgd_flat_hot_lr = value;
   else if (n == "sgd_flat_inflight_frac") e->opt_sgd_flat_inflight_frac = value;
+  else if (n == "sgd_flat_launch_lr") e->opt_sgd_flat_launch_lr = value;
   else if (n == "sgd_flat_band_mb") e->opt_sgd_flat_band_mb = value;
   else if (n == "sgd_flat_user_store") e->opt_sgd_flat_user_store = (int)value;
   else if (n == "sgd_flat_debug") e->opt_sgd_flat_debug = (int)value;
   else if (n == "sgd_atomic") e->opt_sgd_atomic = (int)value;
   else if (n == "sgd_rotate") e->opt_sgd_rotate = (int)value;
+  else if (n == "sgd_hot") e->opt_sgd_hot = (int)value;
+  else if (n == "sgd_hot_min_count") e->opt_sgd_hot_min_count = (int)value;
+  else if (n == "sgd_hot_inflight") e->opt_sgd_hot_inflight = value;
+  else if (n == "sgd_hot_max_lists") {
+    if (value < 1 || value > 127) return mfb::fail("mfb_set_option: sgd_hot_max_lists must be in 1..127", __FILE__, __LINE__);
+    e->opt_sgd_hot_max_lists = (int)value;
+  }
+  else if (n == "sgd_hot_batch") e->opt_sgd_hot_batch = (int)value;
+  else if (n == "sgd_hot_pace") e->opt_sgd_hot_pace = (int)value;
+  else if (n == "sgd_hot_stab") e->opt_sgd_hot_stab = value;
+  else if (n == "sgd_hot_stages") e->opt_sgd_hot_stages = (int)value;
   else if (n == "als_tensor_cores") e->opt_als_tensor_cores = (int)value;
   else if (n == "als_dual") e->opt_als_dual = (int)value;
   else if (n == "als_chunk") {
@@ -595,6 +616,21 @@ extern "C" int mfb_sgd_block_nnz(mfb_engine *e, const int32_t *blocks, int32_t n
   }
   *nnz = s;
   return 0;
+}
+
+extern "C" int mfb_debug_sgd_records(mfb_engine *e, int32_t user_part, int32_t item_part, int32_t *records,
+                                     int64_t *cold_records, int32_t *lists, int32_t *n_lists) {
+  MFB_REQUIRE(e && e->sgd.built && e->sgd.recs, "mfb_debug_sgd_records: call mfb_sgd_plan first");
+  MFB_REQUIRE(user_part >= 0 && user_part < e->sgd.P && item_part >= 0 && item_part < e->sgd.P,
+              "mfb_debug_sgd_records: block index out of range");
+  MFB_CUDA(cudaSetDevice(e->device));
+  return sgd_debug_records(e, user_part, item_part, records, cold_records, lists, n_lists);
+}
+
+extern "C" int mfb_debug_sgd_hot_batch(mfb_engine *e, double out[3]) {
+  MFB_REQUIRE(e && out && e->sgd.built, "mfb_debug_sgd_hot_batch: call mfb_sgd_plan first");
+  MFB_CUDA(cudaSetDevice(e->device));
+  return sgd_debug_hot_batch(e, out);
 }
 
 extern "C" int mfb_als_half_step(mfb_engine *e, int side, float reg) {

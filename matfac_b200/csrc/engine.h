@@ -114,6 +114,17 @@ struct SgdPlan {
   std::vector<int64_t> band_rat_off;              // P == 1: rating offsets of the user bands of the shuffled kernel
   int32_t *part_items = nullptr;                  // item ids grouped by item part (device)
   std::vector<int32_t> part_item_off;             // [P+1]
+  // Hot item rows (sgd_hot_kernel): inside every block range the records of the items that hold at least
+  // sgd_hot_min_count of the block's ratings are moved behind the block's cold records, one contiguous list per
+  // item; a list is trained by one CTA that keeps the item row in shared memory.
+  std::vector<int64_t> blk_cold_nnz;              // [P*P] records of the block's cold range (starts at blk_rat_off)
+  std::vector<int32_t> blk_hot_off, blk_hot_cnt;  // [P*P] the block's lists inside hot_lists
+  std::vector<double> blk_cold_share;             // [P*P] hottest cold item's share of the block's cold ratings
+  void *hot_lists = nullptr;                      // device int4 {item, first record, records, 0} per list
+  int32_t n_hot = 0;
+  int64_t hot_nnz = 0;                            // records in hot lists
+  double *hot_stat = nullptr;                     // device [3]: sum degree x |u|^2, sum degree, last batch used
+  int hot_stat_age = 0;                           // launches since the statistic was refreshed
   bool built = false;
   bool runs_built = true;  // user runs present (P == 1 plans build them lazily)
   void release();
@@ -132,16 +143,27 @@ struct mfb_engine {
   double opt_sgd_max_hot_inflight = 8.0;  // bound on concurrent updates of the hottest item row
   double opt_sgd_flat_hot_lr = 0.15;  // shuffled kernel: cap on (hot-row concurrency x learning rate)
   double opt_sgd_flat_inflight_frac = 2e-4;  // shuffled kernel: ratings in flight <= this fraction of the epoch
+  double opt_sgd_flat_launch_lr = 1.2e-5;  // shuffled kernel: ratings in flight <= value / learnrate x ratings of the launch
   double opt_sgd_flat_band_mb = 0.0;  // shuffled kernel: user rows per band (MB of U), 0 = one band (the reference's order)
   int opt_sgd_flat_user_store = 0;    // shuffled kernel: 1 = user rows by plain stores (Hogwild on U), 0 = reductions
   int opt_sgd_flat_debug = 0;         // timing diagnostics of the shuffled kernel (results are wrong when set)
   int opt_sgd_atomic = 1;             // item rows updated by vector reductions (no lost updates)
   int opt_sgd_block_order = 0;        // stratified trainers: 0 = user-major runs (reference order), 1 = shuffled inside the blocks
   int opt_sgd_rotate = 0;             // user runs start at a pseudo-random offset (de-correlates heavy users)
+  int opt_sgd_hot = 1;                // shuffled kernel: hot item rows trained by dedicated CTAs (row in shared memory)
+  int opt_sgd_hot_min_count = 1024;   // a hot list holds at least this many ratings
+  double opt_sgd_hot_inflight = 16.0; // an item is hot inside a block when the shuffled kernel would keep more updates of its row in flight
+  int opt_sgd_hot_max_lists = 127;    // hot items per block (<= 127)
+  int opt_sgd_hot_stages = 8;         // rounds a hot CTA stages ahead (4 or 8; rank > 128: 4)
+  double opt_sgd_hot_stab = 0.5;      // hot CTAs: mini-batch <= value / (learnrate x rating-weighted mean |u|^2)
+  int opt_sgd_hot_pace = 1;           // hot CTAs advance through their list in step with the shuffled kernel
+  int opt_sgd_hot_batch = 0;          // ratings per round of a hot CTA, 0 = automatic (<= 64 and <= sgd_flat_hot_lr / learnrate)
   int opt_als_chunk = 16384;          // ratings per CTA before a row is split over several CTAs
   int opt_als_dual = 1;               // short rows: solve the len x len dual system instead of rank x rank
   int opt_als_tensor_cores = 1;       // rank > 64: Gram on tcgen05 (3xTF32); 0 = fp32 CUDA-core Gram
   cudaStream_t stream = nullptr;
+  cudaStream_t stream_hot = nullptr;  // hot-row CTAs run next to the shuffled kernel (forked from / joined into `stream`)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t events[16] = {};
 
   float *U = nullptr, *V = nullptr;          // [n][ld] fp32, padding columns are zero
@@ -192,6 +214,9 @@ int sgd_subepoch_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int va
                         float ireg, uint64_t seed, uint64_t counter);
 int sgd_flat_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int variant, float lr, float ureg, float ireg,
                     uint64_t seed, uint64_t counter);
+int sgd_debug_hot_batch(mfb_engine *e, double out[3]);
+int sgd_debug_records(mfb_engine *e, int32_t a, int32_t b, int32_t *recs_out, int64_t *cold_nnz, int32_t *lists_out,
+                      int32_t *n_lists);
 int eval_launch(mfb_engine *e, int which, int factors, int variant, int weighted, int want_norms, double out[4]);
 int eval_groups_launch(mfb_engine *e, int which, int factors, int variant, const uint8_t *user_group,
                        const uint8_t *item_group, double *out);

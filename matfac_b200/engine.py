@@ -24,7 +24,7 @@ VARIANT = {"mf": MF, "IFWMF": IFWMF, "TMF": TMF, "TMFDropout": TMFDROPOUT}
 SYMBOLS = [
     "mfb_last_error", "mfb_launch_count", "mfb_create", "mfb_destroy", "mfb_sync", "mfb_pin_host",
     "mfb_unpin_host", "mfb_upload_csr", "mfb_set_masks", "mfb_upload_factors", "mfb_download_factors",
-    "mfb_set_aux", "mfb_sgd_plan", "mfb_sgd_subepoch", "mfb_sgd_block_nnz", "mfb_sgd_epoch_flat", "mfb_set_option", "mfb_als_half_step", "mfb_debug_als_gram",
+    "mfb_set_aux", "mfb_sgd_plan", "mfb_sgd_subepoch", "mfb_sgd_block_nnz", "mfb_debug_sgd_records", "mfb_debug_sgd_hot_batch", "mfb_sgd_epoch_flat", "mfb_set_option", "mfb_als_half_step", "mfb_debug_als_gram",
     "mfb_ccdpp_begin", "mfb_ccdpp_rank1", "mfb_ccdpp_end", "mfb_eval", "mfb_eval_groups", "mfb_snapshot_best",
     "mfb_restore_best", "mfb_event_record", "mfb_event_elapsed_ms", "mfb_device_factors", "mfb_stream",
     "mfb_pack_rows", "mfb_unpack_rows", "mfb_set_row_range",
@@ -75,6 +75,8 @@ def load_library():
     L.mfb_sgd_epoch_flat.argtypes = [vp, C.c_int, f32, f32, f32, u64, u64]
     L.mfb_set_option.argtypes = [vp, C.c_char_p, C.c_double]
     L.mfb_sgd_block_nnz.argtypes = [vp, vp, i32, C.POINTER(i64)]
+    L.mfb_debug_sgd_records.argtypes = [vp, i32, i32, vp, C.POINTER(i64), vp, C.POINTER(i32)]
+    L.mfb_debug_sgd_hot_batch.argtypes = [vp, vp]
     L.mfb_als_half_step.argtypes = [vp, C.c_int, f32]
     L.mfb_debug_als_gram.argtypes = [vp, C.c_int, i32, vp, C.POINTER(i32)]
     L.mfb_ccdpp_begin.argtypes = [vp]
@@ -208,6 +210,21 @@ class Engine:
         out = C.c_int64()
         self._check(self.L.mfb_sgd_block_nnz(self.h, _p(b), b.shape[0], C.byref(out)))
         return out.value
+
+    def debug_sgd_records(self, user_part=0, item_part=0):
+        """(records [n][4] int32, cold record count, lists [h][3] int32) of one stratum block (diagnostics)."""
+        n = self.sgd_block_nnz([[user_part, item_part]])
+        recs = np.zeros((max(n, 1), 4), np.int32)
+        lists = np.zeros((127, 3), np.int32)
+        cold, h = C.c_int64(), C.c_int32()
+        self._check(self.L.mfb_debug_sgd_records(self.h, user_part, item_part, _p(recs), C.byref(cold), _p(lists), C.byref(h)))
+        return recs[:n], cold.value, lists[:h.value].copy()
+
+    def debug_sgd_hot_batch(self):
+        """[sum degree x |u|^2, sum degree, ratings per round the hot CTAs last used] (diagnostics)."""
+        out = np.zeros(3, np.float64)
+        self._check(self.L.mfb_debug_sgd_hot_batch(self.h, _p(out)))
+        return out
 
     # ---- ALS / CCD++ ----
     def als_half_step(self, side, reg):

@@ -187,16 +187,20 @@ def test_sgd_rmse_parity(algo, method, P, rank):
     eng.close()
 
 
-def test_sgd_shuffled_block_order_matches_serial_quality():
+@pytest.mark.parametrize("hot_min_count", [4096, 60])
+def test_sgd_shuffled_block_order_matches_serial_quality(hot_min_count):
     """Stratified trainer with the shuffled-inside-blocks order (the multi-GPU path): same final
-    RMSE as the oracle's serial SGD within 0.5 %."""
+    RMSE as the oracle's serial SGD within 0.5 %.  hot_min_count = 60 forces hot-row lists in every block."""
     splits = small_problem(3000, 1500, 300000, seed=21)
     epochs, P = 40, 4
     om, want = _oracle_curve(splits, "mf", "sgd", 10, epochs, 1, 3, {})
     om0 = oracle_model(splits, "mf", 10, maxiter=epochs, nthreads=P, seed=3, learnrate=0.005)
     eng, variant = make_engine(splits, om0, 10, with_csc=False)
     up, ip, sched = om0.dsgd_plan(P, epochs * P)
+    eng.set_option("sgd_hot_min_count", hot_min_count)
+    eng.set_option("sgd_hot_inflight", 0)  # the count threshold alone decides
     eng.sgd_plan(P, up, ip)
+    assert (len(eng.debug_sgd_records(1, 2)[2]) > 0) == (hot_min_count == 60)
     eng.set_option("sgd_block_order", 1)
     rot = np.array([[[a, (a + s) % P] for a in range(P)] for s in range(P)], np.int32)  # Latin-square rotation
     for ep in range(epochs):
@@ -204,6 +208,146 @@ def test_sgd_shuffled_block_order_matches_serial_quality():
             eng.sgd_subepoch(rot[k], variant, 0.005, HP["ureg"], HP["ireg"], 3, ep * P + k)
     got = eng.rmse(E.VAL)
     assert abs(got - want[-1]) <= 0.005 * want[-1], (got, want[-1])
+    eng.close()
+
+
+def _block_triples(tr, up, ip, a, b):
+    users = np.repeat(np.arange(tr.nrows, dtype=np.int64), np.diff(tr.rowptr))
+    m = (up[users] == a) & (ip[tr.rowind] == b)
+    return users[m], tr.rowind[m].astype(np.int64), tr.rowval[m].view(np.int32).astype(np.int64)
+
+
+@pytest.mark.parametrize("P", [1, 3])
+def test_sgd_hot_lists_partition_the_block_records(P):
+    """Plan check, bit-exact: the shuffled records of every stratum block are a permutation of the block's
+    ratings; the hot lists hold exactly all ratings of their item inside the block, every item with at least
+    sgd_hot_min_count ratings in the block has a list (the sgd_hot_max_lists = 64 most rated ones when there are
+    more), and no cold record belongs to a hot item."""
+    splits = small_problem(3000, 1500, 300000, seed=21)
+    tr = splits[0]
+    om = oracle_model(splits, "mf", 16, nthreads=P)
+    eng, variant = make_engine(splits, om, 16, with_csc=False)
+    eng.set_option("sgd_hot_min_count", 150)
+    eng.set_option("sgd_hot_inflight", 0)  # the count threshold alone decides
+    eng.set_option("sgd_hot_max_lists", 64)
+    if P == 1:
+        up, ip = np.zeros(tr.nrows, np.int32), np.zeros(tr.ncols, np.int32)
+        eng.sgd_plan(1)
+    else:
+        up, ip, _ = om.dsgd_plan(P, P)
+        eng.sgd_plan(P, up, ip)
+    n_lists_total = 0
+    for a in range(P):
+        for b in range(P):
+            recs, cold, lists = eng.debug_sgd_records(a, b)
+            u, i, v = _block_triples(tr, np.asarray(up), np.asarray(ip), a, b)
+            want = np.sort((u << 44) | (i << 32) | (v & 0xFFFFFFFF) >> 8)
+            got = np.sort((recs[:, 0].astype(np.int64) << 44) | (recs[:, 1].astype(np.int64) << 32)
+                          | (recs[:, 2].astype(np.int64) & 0xFFFFFFFF) >> 8)
+            assert np.array_equal(got, want), (a, b)
+            counts = np.bincount(i, minlength=tr.ncols)
+            cand = [it for it in np.lexsort((np.arange(tr.ncols), -counts)) if counts[it] >= 150][:64]  # sgd_hot_max_lists
+            hot_items = set(int(c) for c in cand)
+            assert lists[:, 0].tolist() == [int(c) for c in cand], (a, b)
+            end = cold
+            for item, first, n in lists:
+                assert first == end and n == counts[item] and np.all(recs[first:first + n, 1] == item)
+                end = first + n
+            assert end == len(recs)
+            assert not np.isin(recs[:cold, 1], list(hot_items)).any()
+            n_lists_total += len(lists)
+    assert n_lists_total > 0
+    eng.close()
+
+
+@pytest.mark.parametrize("algo,rank,P", [("mf", 64, 1), ("mf", 10, 2), ("IFWMF", 16, 1), ("TMF", 64, 2), ("mf", 128, 1)])
+def test_sgd_hot_rows_visit_every_rating_once(algo, rank, P):
+    """Linear regime: with a tiny learning rate one epoch moves the factors by lr x the summed per-rating
+    gradients at the starting point, whatever the order and the concurrency.  The epoch of the shuffled kernel
+    with its hot-row CTAs (forced on: sgd_hot_min_count = 150) must reproduce that sum for U and for V — a list
+    that was skipped, trained twice or applied to the wrong row shows up at first order."""
+    splits = small_problem(3000, 1500, 300000, seed=21)
+    tr = splits[0]
+    flags = dict(ALGO_FLAGS[algo])
+    om = oracle_model(splits, algo, rank, nthreads=P, **({"rhorms": 100.0} if algo == "IFWMF" else {}))
+    eng, variant = make_engine(splits, om, rank, algo, rho=100.0 if algo == "IFWMF" else flags.get("rhorms", 0.0), with_csc=False)
+    eng.set_option("sgd_hot_min_count", 150)
+    eng.set_option("sgd_hot_inflight", 0)  # the count threshold alone decides
+    rng = np.random.default_rng(5)
+    U0 = rng.normal(0, 0.2, (tr.nrows, rank)).astype(np.float32)
+    V0 = rng.normal(0, 0.2, (tr.ncols, rank)).astype(np.float32)
+    lr, ureg, ireg = 2e-6, 0.05, 0.05
+    users = np.repeat(np.arange(tr.nrows), np.diff(tr.rowptr))
+    items = tr.rowind.astype(np.int64)
+
+    def run(hot):
+        eng.set_option("sgd_hot", hot)
+        eng.upload_factors(U0, V0)
+        if P == 1:
+            eng.sgd_plan(1)
+            eng.sgd_epoch_flat(variant, lr, ureg, ireg, 3, 0)
+        else:
+            up, ip, _ = om.dsgd_plan(P, P)
+            eng.sgd_plan(P, up, ip)
+            eng.set_option("sgd_block_order", 1)
+            for k in range(P):
+                eng.sgd_subepoch(np.array([[a, (a + k) % P] for a in range(P)], np.int32), variant, lr, ureg, ireg, 3, k)
+        _, cold, lists = eng.debug_sgd_records(0, 0)
+        U1, V1 = eng.download_factors()
+        return (U1.astype(np.float64) - U0) / lr, (V1.astype(np.float64) - V0) / lr, len(lists)
+
+    dU_hot, dV_hot, n_hot = run(1)
+    dU_cold, dV_cold, n_cold = run(0)
+    assert n_hot > 0 and n_cold == 0
+    # the all-cold epoch (vector reductions only, tested against the oracle elsewhere) is the yardstick
+    assert rel_err(dU_hot, dU_cold) < 2e-2 and rel_err(dV_hot, dV_cold) < 2e-2
+    if algo == "mf":
+        U64, V64 = U0.astype(np.float64), V0.astype(np.float64)
+        e = tr.rowval - np.einsum("ij,ij->i", U64[users], V64[items])
+        gU = np.zeros_like(U64); gV = np.zeros_like(V64)
+        np.add.at(gU, users, 2 * e[:, None] * V64[items] - 2 * ureg * U64[users])
+        np.add.at(gV, items, 2 * e[:, None] * U64[users] - 2 * ireg * V64[items])
+        assert rel_err(dU_hot, gU) < 2e-2 and rel_err(dV_hot, gV) < 2e-2
+        hot_items = np.nonzero(np.bincount(items, minlength=tr.ncols) >= 1000)[0]
+        assert rel_err(dV_hot[hot_items], gV[hot_items]) < 2e-2
+    eng.close()
+
+
+@pytest.mark.parametrize("algo,rank,warps", [("mf", 10, 0), ("mf", 64, 4), ("mf", 64, 8), ("IFWMF", 16, 2)])
+def test_sgd_hot_rows_rmse_parity(algo, rank, warps):
+    """Validation RMSE at equal epochs against the oracle's serial SGD with the hot-row CTAs forced on
+    (a third of the ratings go through them at sgd_hot_min_count = 300): same bars as test_sgd_rmse_parity."""
+    splits = small_problem(3000, 1500, 300000, seed=21)
+    epochs = 40
+    flags = dict(ALGO_FLAGS[algo])
+    if algo == "IFWMF":
+        flags["rhorms"] = 100.0
+    method = "sgd"
+    om, want = _oracle_curve(splits, algo, method, rank, epochs, 1, 3, flags)
+    others = [_oracle_curve(splits, algo, method, rank, epochs, 1, s, flags)[1] for s in (4, 5)]
+    spread = np.max(np.abs(np.stack(others) - want[None, :]), axis=0)
+    om0 = oracle_model(splits, algo, rank, maxiter=epochs, nthreads=1, seed=3, learnrate=0.005, **flags)
+    eng, variant = make_engine(splits, om0, rank, algo, rho=flags.get("rhorms", 0.0), with_csc=False)
+    eng.set_option("sgd_hot_min_count", 300)
+    eng.set_option("sgd_hot_inflight", 0)
+    eng.set_option("sgd_hot_batch", warps)
+    eng.sgd_plan(1)
+    _, cold, lists = eng.debug_sgd_records(0, 0)
+    assert len(lists) > 20 and cold < 0.8 * splits[0].nnz
+    got = []
+    for ep in range(epochs):
+        eng.sgd_epoch_flat(variant, 0.005, HP["ureg"], HP["ireg"], 3, ep)
+        got.append(eng.rmse(E.VAL, E.CURRENT, variant))
+    got = np.array(got)
+    assert np.all(np.isfinite(got))
+    tol = 0.025 * want + spread
+    for ep in range(3):
+        lo = min(want[ep:ep + 2]) - 0.15 * want[ep] - spread[ep]
+        hi = max(want[max(ep - 1, 0):ep + 1]) + 0.15 * want[ep] + spread[ep]
+        assert lo <= got[ep] <= hi, (ep, got[ep], want[max(ep - 1, 0):ep + 2])
+    worst = 3 + np.argmax(np.abs(got[3:] - want[3:]) - tol[3:])
+    assert np.all(np.abs(got[3:] - want[3:]) <= tol[3:]), (worst, got[worst], want[worst], spread[worst])
+    assert np.all(np.abs(got[-3:] - want[-3:]) <= 0.005 * want[-3:]), (got[-3:], want[-3:])
     eng.close()
 
 
