@@ -741,10 +741,10 @@ static int launch_als(mfb_engine *e, const AlsArgs &a, const SegPlan &sp) {
   if (sp.n_multi > 0) {
     size_t need = sizeof(float) * (size_t)sp.n_multi * (S::RP * S::RP + S::RP);
     if (need > e->als_ws_bytes) {
-      if (e->als_ws) MFB_CUDA(cudaFree(e->als_ws));
+      if (e->als_ws) MFB_CUDA(dev_free(e->als_ws));
       e->als_ws = nullptr;
       e->als_ws_bytes = 0;
-      MFB_CUDA(cudaMalloc(&e->als_ws, need));
+      MFB_CUDA(dev_alloc(&e->als_ws, need));
       e->als_ws_bytes = need;
     }
     MFB_CUDA(cudaMemsetAsync(e->als_ws, 0, need, e->stream));
@@ -783,11 +783,11 @@ int als_debug_gram(mfb_engine *e, int side, int32_t row, float *out, int32_t *rp
   *rp_out = RP;
   int32_t h[5] = {row, (int32_t)be[0], (int32_t)(be[1] - be[0]), 0, row};
   int32_t *d;
-  MFB_CUDA(cudaMalloc(&d, sizeof(h)));
+  MFB_CUDA(dev_alloc(&d, sizeof(h)));
   MFB_CUDA(cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice));
   float *ws;
   const size_t wsb = sizeof(float) * ((size_t)RP * RP + RP);
-  MFB_CUDA(cudaMalloc(&ws, wsb));
+  MFB_CUDA(dev_alloc(&ws, wsb));
   MFB_CUDA(cudaMemset(ws, 0, wsb));
   AlsArgs a;
   a.Fin = side == MFB_USER ? e->V : e->U;
@@ -811,8 +811,8 @@ int als_debug_gram(mfb_engine *e, int side, int32_t row, float *out, int32_t *rp
   }
   MFB_CUDA(cudaStreamSynchronize(e->stream));
   MFB_CUDA(cudaMemcpy(out, ws, wsb, cudaMemcpyDeviceToHost));
-  cudaFree(ws);
-  cudaFree(d);
+  dev_free(ws);
+  dev_free(d);
   return 0;
 }
 

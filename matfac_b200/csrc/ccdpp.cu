@@ -108,10 +108,10 @@ int ccdpp_begin_impl(mfb_engine *e) {
   DevCsr &m = e->mat[MFB_TRAIN];
   cudaStream_t st = e->stream;
   size_t nn = (size_t)(m.nnz > 0 ? m.nnz : 1);
-  if (!e->res_row) MFB_CUDA(cudaMalloc(&e->res_row, sizeof(float) * nn));
-  if (!e->res_col) MFB_CUDA(cudaMalloc(&e->res_col, sizeof(float) * nn));
-  if (!e->uk) MFB_CUDA(cudaMalloc(&e->uk, sizeof(float) * e->n_users));
-  if (!e->vk) MFB_CUDA(cudaMalloc(&e->vk, sizeof(float) * e->n_items));
+  if (!e->res_row) MFB_CUDA(dev_alloc(&e->res_row, sizeof(float) * nn));
+  if (!e->res_col) MFB_CUDA(dev_alloc(&e->res_col, sizeof(float) * nn));
+  if (!e->uk) MFB_CUDA(dev_alloc(&e->uk, sizeof(float) * e->n_users));
+  if (!e->vk) MFB_CUDA(dev_alloc(&e->vk, sizeof(float) * e->n_items));
   // res = gk_csr_Dup(trainMat) (modelMF.cpp:1013); uFac.fill(0) (:1020)
   MFB_CUDA(cudaMemcpyAsync(e->res_row, m.rowval, sizeof(float) * (size_t)m.nnz, cudaMemcpyDeviceToDevice, st));
   MFB_CUDA(cudaMemcpyAsync(e->res_col, m.colval, sizeof(float) * (size_t)m.nnz, cudaMemcpyDeviceToDevice, st));
@@ -124,9 +124,9 @@ int ccdpp_begin_impl(mfb_engine *e) {
                            kCcdChunk, &m.ccd_cols));
   size_t slots = (size_t)max(m.ccd_rows.n_multi, m.ccd_cols.n_multi);
   if (slots > e->ccd_acc_slots) {
-    if (e->ccd_acc) MFB_CUDA(cudaFree(e->ccd_acc));
+    if (e->ccd_acc) MFB_CUDA(dev_free(e->ccd_acc));
     e->ccd_acc = nullptr;
-    MFB_CUDA(cudaMalloc(&e->ccd_acc, sizeof(double) * 2 * slots));
+    MFB_CUDA(dev_alloc(&e->ccd_acc, sizeof(double) * 2 * slots));
     e->ccd_acc_slots = slots;
   }
   if (e->ccd_acc) MFB_CUDA(cudaMemsetAsync(e->ccd_acc, 0, sizeof(double) * 2 * e->ccd_acc_slots, st));
@@ -188,7 +188,7 @@ int ccdpp_end_impl(mfb_engine *e) {
     MFB_TRY(comm_allgather_range(e, MFB_ITEM, e->row_begin[MFB_ITEM], e->row_end[MFB_ITEM] - e->row_begin[MFB_ITEM]));
   }
   MFB_CUDA(cudaStreamSynchronize(e->stream));
-  cudaFree(e->res_row); cudaFree(e->res_col);
+  dev_free(e->res_row); dev_free(e->res_col);
   e->res_row = e->res_col = nullptr;
   return 0;
 }

@@ -153,10 +153,10 @@ extern "C" int mfb_comm_init(mfb_engine *e, int32_t rank, int32_t world, uint8_t
   Comm &c = e->comm;
   c.rank = rank;
   c.world = world;
-  if (!e->uk) MFB_CUDA(cudaMalloc(&e->uk, sizeof(float) * e->n_users));
-  if (!e->vk) MFB_CUDA(cudaMalloc(&e->vk, sizeof(float) * e->n_items));
+  if (!e->uk) MFB_CUDA(dev_alloc(&e->uk, sizeof(float) * e->n_users));
+  if (!e->vk) MFB_CUDA(dev_alloc(&e->vk, sizeof(float) * e->n_items));
   if (!c.own_flags) {
-    MFB_CUDA(cudaMalloc(&c.own_flags, sizeof(unsigned long long) * (kFlagSlots + 2)));
+    MFB_CUDA(dev_alloc(&c.own_flags, sizeof(unsigned long long) * (kFlagSlots + 2)));
     MFB_CUDA(cudaMemset(c.own_flags, 0, sizeof(unsigned long long) * (kFlagSlots + 2)));
   }
   CommHandles h;

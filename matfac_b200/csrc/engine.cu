@@ -8,6 +8,10 @@
 //   masks     one byte per id; aux records 16 B per id.
 #include "engine.h"
 
+#include <map>
+#include <mutex>
+#include <unordered_map>
+
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -34,30 +38,112 @@ int fail_cuda(cudaError_t err, const char *expr, const char *file, int line) {
   return 2;
 }
 
+// ---- cached device allocations -------------------------------------------------------------
+namespace {
+struct DevCache {
+  std::mutex mu;
+  std::unordered_map<void *, std::pair<int, size_t>> live;             // block -> (device, size)
+  std::multimap<std::pair<int, size_t>, void *> idle;                  // (device, size) -> block
+  size_t idle_bytes = 0;
+};
+DevCache &dev_cache() { static DevCache c; return c; }
+constexpr size_t kDevCacheMaxIdle = (size_t)16 << 30;
+}  // namespace
+
+cudaError_t dev_alloc_bytes(void **p, size_t bytes) {
+  if (bytes == 0) bytes = 1;
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) return err;
+  DevCache &c = dev_cache();
+  {
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.idle.lower_bound({dev, bytes});
+    if (it != c.idle.end() && it->first.first == dev && it->first.second <= bytes + bytes / 4 + 4096) {
+      *p = it->second;
+      c.live[*p] = it->first;
+      c.idle_bytes -= it->first.second;
+      c.idle.erase(it);
+      return cudaSuccess;
+    }
+  }
+  err = cudaMalloc(p, bytes);
+  if (err != cudaSuccess) {  // out of memory: give the cached blocks back and retry once
+    (void)cudaGetLastError();
+    dev_cache_release(dev);
+    err = cudaMalloc(p, bytes);
+    if (err != cudaSuccess) return err;
+  }
+  std::lock_guard<std::mutex> lock(c.mu);
+  c.live[*p] = {dev, bytes};
+  return cudaSuccess;
+}
+
+cudaError_t dev_free(void *p) {
+  if (!p) return cudaSuccess;
+  DevCache &c = dev_cache();
+  std::pair<int, size_t> key;
+  {
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.live.find(p);
+    if (it == c.live.end()) return cudaFree(p);  // not ours (never happens inside the engine)
+    key = it->second;
+    c.live.erase(it);
+    if (c.idle_bytes + key.second <= kDevCacheMaxIdle) {
+      c.idle.emplace(key, p);
+      c.idle_bytes += key.second;
+      return cudaSuccess;
+    }
+  }
+  return cudaFree(p);
+}
+
+void dev_cache_release(int device) {
+  DevCache &c = dev_cache();
+  std::vector<void *> blocks;
+  {
+    std::lock_guard<std::mutex> lock(c.mu);
+    for (auto it = c.idle.begin(); it != c.idle.end();) {
+      if (it->first.first == device) {
+        blocks.push_back(it->second);
+        c.idle_bytes -= it->first.second;
+        it = c.idle.erase(it);
+      } else {
+        ++it;
+      }
+    }
+  }
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur != device) cudaSetDevice(device);
+  for (void *b : blocks) cudaFree(b);
+  if (cur != device) cudaSetDevice(cur);
+}
+
 void SegPlan::release() {
-  cudaFree(row); cudaFree(start); cudaFree(len); cudaFree(slot); cudaFree(multi_row);
+  dev_free(row); dev_free(start); dev_free(len); dev_free(slot); dev_free(multi_row);
   *this = SegPlan();
 }
 
 void DevCsr::release() {
-  cudaFree(rowptr); cudaFree(colptr); cudaFree(rowind); cudaFree(colind); cudaFree(rowval); cudaFree(colval);
+  dev_free(rowptr); dev_free(colptr); dev_free(rowind); dev_free(colind); dev_free(rowval); dev_free(colval);
   eval_rows.release(); als_rows.release(); als_cols.release(); ccd_rows.release(); ccd_cols.release();
   *this = DevCsr();
 }
 
 void SgdPlan::release() {
-  if (owns_ratings) { cudaFree(item); cudaFree(val); }
-  cudaFree(seg_user); cudaFree(seg_start); cudaFree(seg_len); cudaFree(rat_user); cudaFree(work_counter); cudaFree(recs);
-  cudaFree(part_items); cudaFree(hot_lists); cudaFree(hot_stat);
+  if (owns_ratings) { dev_free(item); dev_free(val); }
+  dev_free(seg_user); dev_free(seg_start); dev_free(seg_len); dev_free(rat_user); dev_free(work_counter); dev_free(recs);
+  dev_free(part_items); dev_free(hot_lists); dev_free(hot_stat);
   *this = SgdPlan();
 }
 
 int ensure_scratch(mfb_engine *e, size_t bytes) {
   if (bytes <= e->scratch_bytes) return 0;
-  if (e->scratch) MFB_CUDA(cudaFree(e->scratch));
+  if (e->scratch) MFB_CUDA(dev_free(e->scratch));
   e->scratch = nullptr;
   e->scratch_bytes = 0;
-  MFB_CUDA(cudaMalloc(&e->scratch, bytes));
+  MFB_CUDA(dev_alloc(&e->scratch, bytes));
   e->scratch_bytes = bytes;
   return 0;
 }
@@ -128,7 +214,7 @@ int build_seg_plan(mfb_engine *e, const int64_t *ptr, int32_t nrows, const uint8
   if (n <= 0 || ptr == nullptr) return 0;
   cudaStream_t st = e->stream;
   int32_t *nch, *multi, *off, *moff;
-  MFB_CUDA(cudaMalloc(&nch, sizeof(int32_t) * 4 * (size_t)(n + 1)));
+  MFB_CUDA(dev_alloc(&nch, sizeof(int32_t) * 4 * (size_t)(n + 1)));
   multi = nch + (n + 1);
   off = multi + (n + 1);
   moff = off + (n + 1);
@@ -148,19 +234,19 @@ int build_seg_plan(mfb_engine *e, const int64_t *ptr, int32_t nrows, const uint8
   out->n_seg = ns;
   out->n_multi = nm;
   if (ns == 0) {
-    cudaFree(nch);
+    dev_free(nch);
     return 0;
   }
   // unsorted arrays + sort permutation
   int32_t *tmp;
-  MFB_CUDA(cudaMalloc(&tmp, sizeof(int32_t) * 7 * (size_t)ns));
+  MFB_CUDA(dev_alloc(&tmp, sizeof(int32_t) * 7 * (size_t)ns));
   int32_t *u_row = tmp, *u_start = tmp + ns, *u_len = tmp + 2 * (size_t)ns, *u_slot = tmp + 3 * (size_t)ns,
           *idx = tmp + 4 * (size_t)ns, *k_out = tmp + 5 * (size_t)ns, *p_out = tmp + 6 * (size_t)ns;
-  MFB_CUDA(cudaMalloc(&out->row, sizeof(int32_t) * ns));
-  MFB_CUDA(cudaMalloc(&out->start, sizeof(int32_t) * ns));
-  MFB_CUDA(cudaMalloc(&out->len, sizeof(int32_t) * ns));
-  MFB_CUDA(cudaMalloc(&out->slot, sizeof(int32_t) * ns));
-  MFB_CUDA(cudaMalloc(&out->multi_row, sizeof(int32_t) * (nm > 0 ? nm : 1)));
+  MFB_CUDA(dev_alloc(&out->row, sizeof(int32_t) * ns));
+  MFB_CUDA(dev_alloc(&out->start, sizeof(int32_t) * ns));
+  MFB_CUDA(dev_alloc(&out->len, sizeof(int32_t) * ns));
+  MFB_CUDA(dev_alloc(&out->slot, sizeof(int32_t) * ns));
+  MFB_CUDA(dev_alloc(&out->multi_row, sizeof(int32_t) * (nm > 0 ? nm : 1)));
   MFB_LAUNCH(seg_fill_kernel, gb, tb, 0, st, ptr, row_lo, n, chunk, nch, off, moff, u_row, u_start, u_len, u_slot,
              out->multi_row);
   int gs = (ns + tb - 1) / tb;
@@ -173,8 +259,8 @@ int build_seg_plan(mfb_engine *e, const int64_t *ptr, int32_t nrows, const uint8
     MFB_CUDA(cudaMemcpyAsync(out->slot, u_slot, sizeof(int32_t) * ns, cudaMemcpyDeviceToDevice, st));
     MFB_CUDA(cudaStreamSynchronize(st));
     out->max_len = chunk;
-    cudaFree(tmp);
-    cudaFree(nch);
+    dev_free(tmp);
+    dev_free(nch);
     return 0;
   }
   MFB_LAUNCH(iota_kernel, gs, tb, 0, st, idx, ns);
@@ -190,8 +276,8 @@ int build_seg_plan(mfb_engine *e, const int64_t *ptr, int32_t nrows, const uint8
   const int32_t cuts[3] = {64, 32, 16};
   for (int k = 0; k < 3; k++)  // lengths are sorted descending
     out->n_longer[k] = (int32_t)(std::partition_point(hl.begin(), hl.end(), [&](int32_t v) { return v > cuts[k]; }) - hl.begin());
-  cudaFree(tmp);
-  cudaFree(nch);
+  dev_free(tmp);
+  dev_free(nch);
   return 0;
 }
 
@@ -236,19 +322,19 @@ extern "C" int mfb_create(const mfb_config *cfg, mfb_engine **out) {
   }
   for (int i = 0; i < 16; i++) MFB_CUDA(cudaEventCreate(&e->events[i]));
   size_t ub = sizeof(float) * (size_t)e->n_users * e->ld, vb = sizeof(float) * (size_t)e->n_items * e->ld;
-  MFB_CUDA(cudaMalloc(&e->U, ub));
-  MFB_CUDA(cudaMalloc(&e->V, vb));
-  MFB_CUDA(cudaMalloc(&e->bestU, ub));
-  MFB_CUDA(cudaMalloc(&e->bestV, vb));
+  MFB_CUDA(dev_alloc(&e->U, ub));
+  MFB_CUDA(dev_alloc(&e->V, vb));
+  MFB_CUDA(dev_alloc(&e->bestU, ub));
+  MFB_CUDA(dev_alloc(&e->bestV, vb));
   MFB_CUDA(cudaMemsetAsync(e->U, 0, ub, e->stream));
   MFB_CUDA(cudaMemsetAsync(e->V, 0, vb, e->stream));
   MFB_CUDA(cudaMemsetAsync(e->bestU, 0, ub, e->stream));
   MFB_CUDA(cudaMemsetAsync(e->bestV, 0, vb, e->stream));
-  MFB_CUDA(cudaMalloc(&e->bad_user, e->n_users));
-  MFB_CUDA(cudaMalloc(&e->bad_item, e->n_items));
+  MFB_CUDA(dev_alloc(&e->bad_user, e->n_users));
+  MFB_CUDA(dev_alloc(&e->bad_item, e->n_items));
   MFB_CUDA(cudaMemsetAsync(e->bad_user, 0, e->n_users, e->stream));
   MFB_CUDA(cudaMemsetAsync(e->bad_item, 0, e->n_items, e->stream));
-  MFB_CUDA(cudaMalloc(&e->eval_out, sizeof(double) * 4));
+  MFB_CUDA(dev_alloc(&e->eval_out, sizeof(double) * 4));
   MFB_CUDA(cudaMallocHost(&e->eval_out_host, sizeof(double) * 4));
   *out = e;
   return 0;
@@ -260,23 +346,25 @@ extern "C" void mfb_destroy(mfb_engine *e) {
   cudaStreamSynchronize(e->stream);
   for (int w = 0; w < 3; w++) e->mat[w].release();
   e->sgd.release();
-  cudaFree(e->U); cudaFree(e->V); cudaFree(e->bestU); cudaFree(e->bestV);
-  cudaFree(e->bad_user); cudaFree(e->bad_item); cudaFree(e->aux_u); cudaFree(e->aux_i); cudaFree(e->poisson_cdf);
-  cudaFree(e->eval_partial); cudaFree(e->eval_out); cudaFreeHost(e->eval_out_host);
-  cudaFree(e->als_ws); cudaFree(e->res_row); cudaFree(e->res_col); cudaFree(e->uk); cudaFree(e->vk);
-  cudaFree(e->ccd_acc); cudaFree(e->scratch);
+  dev_free(e->U); dev_free(e->V); dev_free(e->bestU); dev_free(e->bestV);
+  dev_free(e->bad_user); dev_free(e->bad_item); dev_free(e->aux_u); dev_free(e->aux_i); dev_free(e->poisson_cdf);
+  dev_free(e->eval_partial); dev_free(e->eval_out); cudaFreeHost(e->eval_out_host);
+  dev_free(e->als_ws); dev_free(e->res_row); dev_free(e->res_col); dev_free(e->uk); dev_free(e->vk);
+  dev_free(e->ccd_acc); dev_free(e->scratch);
+  const int destroyed_device = e->device;
   if (e->comm.connected)
     for (int r = 0; r < e->comm.world; r++) {
       if (r == e->comm.rank) continue;
       cudaIpcCloseMemHandle(e->comm.U[r]); cudaIpcCloseMemHandle(e->comm.V[r]); cudaIpcCloseMemHandle(e->comm.uk[r]);
       cudaIpcCloseMemHandle(e->comm.vk[r]); cudaIpcCloseMemHandle(e->comm.flags[r]);
     }
-  cudaFree(e->comm.own_flags);
+  dev_free(e->comm.own_flags);
   for (int i = 0; i < 16; i++) cudaEventDestroy(e->events[i]);
   cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join);
   cudaStreamDestroy(e->stream_hot);
   cudaStreamDestroy(e->stream);
   delete e;
+  mfb::dev_cache_release(destroyed_device);
 }
 
 extern "C" int mfb_sync(mfb_engine *e) {
@@ -296,7 +384,7 @@ extern "C" int mfb_unpin_host(void *ptr) {
 
 template <typename T>
 static int upload_array(mfb_engine *e, T **dst, const T *src, size_t n) {
-  MFB_CUDA(cudaMalloc(dst, sizeof(T) * (n > 0 ? n : 1)));
+  MFB_CUDA(dev_alloc(dst, sizeof(T) * (n > 0 ? n : 1)));
   if (n > 0) MFB_CUDA(cudaMemcpyAsync(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice, e->stream));
   return 0;
 }
@@ -330,9 +418,9 @@ extern "C" int mfb_upload_csr(mfb_engine *e, int which, int32_t nrows, int32_t n
   const size_t nn = (size_t)(nnz > 0 ? nnz : 1);
   // rowptr is padded to n_users + 1 entries so that every kernel can index any user
   if (!reuse) {
-    MFB_CUDA(cudaMalloc(&m.rowptr, sizeof(int64_t) * ((size_t)e->n_users + 1)));
-    MFB_CUDA(cudaMalloc(&m.rowind, sizeof(int32_t) * nn));
-    MFB_CUDA(cudaMalloc(&m.rowval, sizeof(float) * nn));
+    MFB_CUDA(dev_alloc(&m.rowptr, sizeof(int64_t) * ((size_t)e->n_users + 1)));
+    MFB_CUDA(dev_alloc(&m.rowind, sizeof(int32_t) * nn));
+    MFB_CUDA(dev_alloc(&m.rowval, sizeof(float) * nn));
   }
   MFB_CUDA(cudaMemcpyAsync(m.rowptr, rowptr, sizeof(int64_t) * ((size_t)nrows + 1), cudaMemcpyHostToDevice, e->stream));
   if (nrows < e->n_users) {
@@ -346,9 +434,9 @@ extern "C" int mfb_upload_csr(mfb_engine *e, int which, int32_t nrows, int32_t n
   if (colptr) {
     MFB_REQUIRE(nnz == 0 || (colind && colval), "mfb_upload_csr: incomplete CSC");
     if (!reuse) {
-      MFB_CUDA(cudaMalloc(&m.colptr, sizeof(int64_t) * ((size_t)e->n_items + 1)));
-      MFB_CUDA(cudaMalloc(&m.colind, sizeof(int32_t) * nn));
-      MFB_CUDA(cudaMalloc(&m.colval, sizeof(float) * nn));
+      MFB_CUDA(dev_alloc(&m.colptr, sizeof(int64_t) * ((size_t)e->n_items + 1)));
+      MFB_CUDA(dev_alloc(&m.colind, sizeof(int32_t) * nn));
+      MFB_CUDA(dev_alloc(&m.colval, sizeof(float) * nn));
     }
     MFB_CUDA(cudaMemcpyAsync(m.colptr, colptr, sizeof(int64_t) * ((size_t)ncols + 1), cudaMemcpyHostToDevice, e->stream));
     if (ncols < e->n_items) {
@@ -398,18 +486,18 @@ extern "C" int mfb_build_csc(mfb_engine *e, int which) {
   MFB_REQUIRE(m.rowptr, "mfb_build_csc: matrix not uploaded");
   MFB_CUDA(cudaSetDevice(e->device));
   cudaStream_t st = e->stream;
-  cudaFree(m.colptr); cudaFree(m.colind); cudaFree(m.colval);
+  dev_free(m.colptr); dev_free(m.colind); dev_free(m.colval);
   m.colptr = nullptr; m.colind = nullptr; m.colval = nullptr;
   m.als_cols.release(); m.ccd_cols.release();
   const int64_t nnz = m.nnz;
   const size_t nn = (size_t)(nnz > 0 ? nnz : 1);
-  MFB_CUDA(cudaMalloc(&m.colptr, sizeof(int64_t) * ((size_t)e->n_items + 1)));
-  MFB_CUDA(cudaMalloc(&m.colind, sizeof(int32_t) * nn));
-  MFB_CUDA(cudaMalloc(&m.colval, sizeof(float) * nn));
+  MFB_CUDA(dev_alloc(&m.colptr, sizeof(int64_t) * ((size_t)e->n_items + 1)));
+  MFB_CUDA(dev_alloc(&m.colind, sizeof(int32_t) * nn));
+  MFB_CUDA(dev_alloc(&m.colval, sizeof(float) * nn));
   MFB_CUDA(cudaMemsetAsync(m.colptr, 0, sizeof(int64_t) * ((size_t)e->n_items + 1), st));
   if (nnz == 0) return 0;
   int32_t *nz_row, *idx, *keys_out, *perm;
-  MFB_CUDA(cudaMalloc(&nz_row, sizeof(int32_t) * nn * 4));
+  MFB_CUDA(dev_alloc(&nz_row, sizeof(int32_t) * nn * 4));
   idx = nz_row + nn; keys_out = idx + nn; perm = keys_out + nn;
   const unsigned gb = (unsigned)((nnz + 255) / 256);
   MFB_LAUNCH(nnz_row_kernel, gb, 256, 0, st, m.rowptr, e->n_users, nnz, nz_row, idx);
@@ -427,7 +515,7 @@ extern "C" int mfb_build_csc(mfb_engine *e, int which) {
   MFB_TRY(ensure_scratch(e, tmp_bytes));
   MFB_CUDA(cub::DeviceScan::InclusiveSum(e->scratch, tmp_bytes, m.colptr, m.colptr, e->n_items + 1, st));
   MFB_CUDA(cudaStreamSynchronize(st));
-  cudaFree(nz_row);
+  dev_free(nz_row);
   return 0;
 }
 
@@ -519,13 +607,13 @@ extern "C" int mfb_set_aux(mfb_engine *e, int variant, const int32_t *user_freq,
   std::vector<Aux> hu(e->n_users), hi(e->n_items);
   for (int u = 0; u < e->n_users; u++) hu[u] = Aux{user_freq[u], ut ? ut[u] : 0, user_pred ? user_pred[u] : 0, 0};
   for (int i = 0; i < e->n_items; i++) hi[i] = Aux{item_freq[i], it ? it[i] : 0, item_pred ? item_pred[i] : 0, 0};
-  if (!e->aux_u) MFB_CUDA(cudaMalloc(&e->aux_u, sizeof(Aux) * e->n_users));
-  if (!e->aux_i) MFB_CUDA(cudaMalloc(&e->aux_i, sizeof(Aux) * e->n_items));
+  if (!e->aux_u) MFB_CUDA(dev_alloc(&e->aux_u, sizeof(Aux) * e->n_users));
+  if (!e->aux_i) MFB_CUDA(dev_alloc(&e->aux_i, sizeof(Aux) * e->n_items));
   MFB_CUDA(cudaMemcpyAsync(e->aux_u, hu.data(), sizeof(Aux) * e->n_users, cudaMemcpyHostToDevice, e->stream));
   MFB_CUDA(cudaMemcpyAsync(e->aux_i, hi.data(), sizeof(Aux) * e->n_items, cudaMemcpyHostToDevice, e->stream));
   if (poisson_cdf) {
     size_t b = sizeof(float) * (size_t)e->rank * e->rank;
-    if (!e->poisson_cdf) MFB_CUDA(cudaMalloc(&e->poisson_cdf, b));
+    if (!e->poisson_cdf) MFB_CUDA(dev_alloc(&e->poisson_cdf, b));
     MFB_CUDA(cudaMemcpyAsync(e->poisson_cdf, poisson_cdf, b, cudaMemcpyHostToDevice, e->stream));
   }
   MFB_CUDA(cudaStreamSynchronize(e->stream));

@@ -15,6 +15,17 @@ namespace mfb {
 extern thread_local std::string g_last_error;
 extern std::atomic<uint64_t> g_launches;
 
+// Device allocations of the engine go through a small per-process cache of whole cudaMalloc blocks: a plan or an
+// upload that is repeated with the same sizes (every step of the bench's end-to-end arm, every epoch's evaluation
+// plan after a re-upload) gets its buffers back without a cudaMalloc / cudaFree pair — each costs a host
+// round trip and a device synchronisation, together more than the kernels of a plan on a busy host.  Blocks are never
+// split (CUDA IPC handles stay valid), at most 16 GB are kept, mfb_destroy releases everything cached on its device.
+cudaError_t dev_alloc_bytes(void **p, size_t bytes);
+cudaError_t dev_free(void *p);
+void dev_cache_release(int device);
+template <class T>
+inline cudaError_t dev_alloc(T **p, size_t bytes) { return dev_alloc_bytes(reinterpret_cast<void **>(p), bytes); }
+
 int fail(const char *what, const char *file, int line);
 int fail_cuda(cudaError_t err, const char *expr, const char *file, int line);
 

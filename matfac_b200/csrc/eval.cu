@@ -204,9 +204,9 @@ int eval_launch(mfb_engine *e, int which, int factors, int variant, int weighted
   const int grid_norm = want_norms ? 2 * e->sm_count : 0;
   const int need = 2 * grid_sse + 2 * grid_norm + 8;
   if (need > e->eval_partial_cap) {
-    if (e->eval_partial) MFB_CUDA(cudaFree(e->eval_partial));
+    if (e->eval_partial) MFB_CUDA(dev_free(e->eval_partial));
     e->eval_partial = nullptr;
-    MFB_CUDA(cudaMalloc(&e->eval_partial, sizeof(double) * (size_t)need));
+    MFB_CUDA(dev_alloc(&e->eval_partial, sizeof(double) * (size_t)need));
     e->eval_partial_cap = need;
   }
   double *p_sse = e->eval_partial, *p_un = p_sse + 2 * (size_t)grid_sse, *p_in = p_un + grid_norm;
@@ -412,8 +412,8 @@ int eval_groups_launch(mfb_engine *e, int which, int factors, int variant, const
   const int grid = (sp.n_seg + segs_per_cta - 1) / segs_per_cta;
   uint8_t *d_groups;
   double *d_partial;
-  MFB_CUDA(cudaMalloc(&d_groups, (size_t)e->n_users + e->n_items));
-  MFB_CUDA(cudaMalloc(&d_partial, sizeof(double) * 32 * ((size_t)grid + 1)));
+  MFB_CUDA(dev_alloc(&d_groups, (size_t)e->n_users + e->n_items));
+  MFB_CUDA(dev_alloc(&d_partial, sizeof(double) * 32 * ((size_t)grid + 1)));
   MFB_CUDA(cudaMemcpyAsync(d_groups, user_group, e->n_users, cudaMemcpyHostToDevice, e->stream));
   MFB_CUDA(cudaMemcpyAsync(d_groups + e->n_users, item_group, e->n_items, cudaMemcpyHostToDevice, e->stream));
   EvalGroupArgs ga;
@@ -440,8 +440,8 @@ int eval_groups_launch(mfb_engine *e, int which, int factors, int variant, const
   MFB_LAUNCH(eval_group_final_kernel, 1, 256, 0, e->stream, d_partial, grid, d_out);
   MFB_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * 32, cudaMemcpyDeviceToHost, e->stream));
   MFB_CUDA(cudaStreamSynchronize(e->stream));
-  cudaFree(d_groups);
-  cudaFree(d_partial);
+  dev_free(d_groups);
+  dev_free(d_partial);
   return 0;
 }
 

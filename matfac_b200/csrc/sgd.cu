@@ -215,10 +215,10 @@ static int sgd_build_records(mfb_engine *e, const std::vector<int64_t> &ranges, 
   pl.hot_nnz = 0;
   for (size_t r = 0; r < range_bid.size(); r++) pl.blk_cold_nnz[range_bid[r]] = ranges[r + 1] - ranges[r];
   if (range_bid.empty() && nblk == 1) pl.blk_cold_nnz[0] = n;  // user bands: the launch cuts the range itself
-  MFB_CUDA(cudaMalloc(&pl.recs, sizeof(int4) * (size_t)(n > 0 ? n : 1)));
+  MFB_CUDA(dev_alloc(&pl.recs, sizeof(int4) * (size_t)(n > 0 ? n : 1)));
   if (n == 0) return 0;
   int64_t *d_off;
-  MFB_CUDA(cudaMalloc(&d_off, sizeof(int64_t) * ranges.size()));
+  MFB_CUDA(dev_alloc(&d_off, sizeof(int64_t) * ranges.size()));
   MFB_CUDA(cudaMemcpyAsync(d_off, ranges.data(), sizeof(int64_t) * ranges.size(), cudaMemcpyHostToDevice, st));
   const unsigned grid = (unsigned)((n + 255) / 256);
 
@@ -234,18 +234,18 @@ static int sgd_build_records(mfb_engine *e, const std::vector<int64_t> &ranges, 
   if (try_hot) {
     std::vector<char> have(nblk, 0);
     for (int r = 0; r < nrng; r++) { range_row[r] = range_bid[r] / P; have[range_bid[r]] = 1; }
-    MFB_CUDA(cudaMalloc(&d_row, sizeof(int32_t) * (size_t)nrng));
+    MFB_CUDA(dev_alloc(&d_row, sizeof(int32_t) * (size_t)nrng));
     MFB_CUDA(cudaMemcpyAsync(d_row, range_row.data(), sizeof(int32_t) * (size_t)nrng, cudaMemcpyHostToDevice, st));
     const int32_t *counts = pl.item_count.data();
     if (P > 1) {
       const size_t hn = (size_t)P * e->n_items;
-      MFB_CUDA(cudaMalloc(&d_hist, sizeof(int32_t) * hn));
+      MFB_CUDA(dev_alloc(&d_hist, sizeof(int32_t) * hn));
       MFB_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(int32_t) * hn, st));
       MFB_LAUNCH(hot_hist_kernel, grid, 256, 0, st, pl.item, n, d_off, nrng, d_row, e->n_items, d_hist);
       hist.resize(hn);
       MFB_CUDA(cudaMemcpyAsync(hist.data(), d_hist, sizeof(int32_t) * hn, cudaMemcpyDeviceToHost, st));
       MFB_CUDA(cudaStreamSynchronize(st));
-      cudaFree(d_hist);
+      dev_free(d_hist);
       counts = hist.data();
     }
     // An item is hot inside a block when the shuffled kernel, running the block with the whole machine
@@ -294,9 +294,9 @@ static int sgd_build_records(mfb_engine *e, const std::vector<int64_t> &ranges, 
     std::vector<uint8_t> cls((size_t)P * e->n_items, 0);
     for (size_t bid = 0; bid < nblk; bid++)
       for (size_t k = 0; k < cand[bid].size(); k++) cls[(bid / P) * (size_t)e->n_items + cand[bid][k].item] = (uint8_t)(k + 1);
-    MFB_CUDA(cudaMalloc(&d_cls, cls.size()));
+    MFB_CUDA(dev_alloc(&d_cls, cls.size()));
     MFB_CUDA(cudaMemcpyAsync(d_cls, cls.data(), cls.size(), cudaMemcpyHostToDevice, st));
-    MFB_CUDA(cudaMalloc(&d_keys, sizeof(uint32_t) * (size_t)n));
+    MFB_CUDA(dev_alloc(&d_keys, sizeof(uint32_t) * (size_t)n));
     MFB_LAUNCH(sgd_shuffle_records_kernel, grid, 256, 0, st, pl.rat_user, pl.item, pl.val, n, d_off, nrng, 0x5EEDULL,
                reinterpret_cast<int4 *>(pl.recs), d_row, e->n_items, d_cls, d_keys);
     MFB_CUDA(cudaStreamSynchronize(st));  // cls (host vector) is copied
@@ -304,7 +304,7 @@ static int sgd_build_records(mfb_engine *e, const std::vector<int64_t> &ranges, 
     MFB_LAUNCH(sgd_shuffle_records_kernel, grid, 256, 0, st, pl.rat_user, pl.item, pl.val, n, d_off, nrng, 0x5EEDULL,
                reinterpret_cast<int4 *>(pl.recs), nullptr, e->n_items, nullptr, nullptr);
     MFB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_off); cudaFree(d_row);
+    dev_free(d_off); dev_free(d_row);
     for (size_t bid = 0; bid < nblk; bid++)
       if (pl.blk_cold_nnz[bid] > 0 && try_hot) pl.blk_cold_share[bid] = (double)cold_max[bid] / (double)pl.blk_cold_nnz[bid];
     return 0;
@@ -313,8 +313,8 @@ static int sgd_build_records(mfb_engine *e, const std::vector<int64_t> &ranges, 
   {
     uint32_t *d_keys2;
     int4 *recs2;
-    MFB_CUDA(cudaMalloc(&d_keys2, sizeof(uint32_t) * (size_t)n));
-    MFB_CUDA(cudaMalloc(&recs2, sizeof(int4) * (size_t)n));
+    MFB_CUDA(dev_alloc(&d_keys2, sizeof(uint32_t) * (size_t)n));
+    MFB_CUDA(dev_alloc(&recs2, sizeof(int4) * (size_t)n));
     int end_bit = 7;
     while ((1 << (end_bit - 7)) < nrng) end_bit++;
     size_t tmp_bytes = 0;
@@ -330,15 +330,15 @@ static int sgd_build_records(mfb_engine *e, const std::vector<int64_t> &ranges, 
     uint32_t *d_q;
     int64_t *d_pos;
     const int nq = (int)queries.size();
-    MFB_CUDA(cudaMalloc(&d_q, sizeof(uint32_t) * (size_t)nq));
-    MFB_CUDA(cudaMalloc(&d_pos, sizeof(int64_t) * (size_t)nq));
+    MFB_CUDA(dev_alloc(&d_q, sizeof(uint32_t) * (size_t)nq));
+    MFB_CUDA(dev_alloc(&d_pos, sizeof(int64_t) * (size_t)nq));
     MFB_CUDA(cudaMemcpyAsync(d_q, queries.data(), sizeof(uint32_t) * (size_t)nq, cudaMemcpyHostToDevice, st));
     MFB_LAUNCH(key_lower_bound_kernel, (nq + 127) / 128, 128, 0, st, d_keys2, n, d_q, nq, d_pos);
     std::vector<int64_t> pos((size_t)nq);
     MFB_CUDA(cudaMemcpyAsync(pos.data(), d_pos, sizeof(int64_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
     MFB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_q); cudaFree(d_pos); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_cls); cudaFree(d_off); cudaFree(d_row);
-    cudaFree(pl.recs);
+    dev_free(d_q); dev_free(d_pos); dev_free(d_keys); dev_free(d_keys2); dev_free(d_cls); dev_free(d_off); dev_free(d_row);
+    dev_free(pl.recs);
     pl.recs = recs2;
     std::vector<int4> lists;
     size_t qi = 0;
@@ -357,10 +357,10 @@ static int sgd_build_records(mfb_engine *e, const std::vector<int64_t> &ranges, 
       if (pl.blk_cold_nnz[bid] > 0) pl.blk_cold_share[bid] = (double)cold_max[bid] / (double)pl.blk_cold_nnz[bid];
     }
     pl.n_hot = (int32_t)lists.size();
-    MFB_CUDA(cudaMalloc(&pl.hot_stat, sizeof(double) * 3));
+    MFB_CUDA(dev_alloc(&pl.hot_stat, sizeof(double) * 3));
     MFB_CUDA(cudaMemsetAsync(pl.hot_stat, 0, sizeof(double) * 3, st));
     pl.hot_stat_age = 0;
-    MFB_CUDA(cudaMalloc(&pl.hot_lists, sizeof(int4) * lists.size()));
+    MFB_CUDA(dev_alloc(&pl.hot_lists, sizeof(int4) * lists.size()));
     MFB_CUDA(cudaMemcpyAsync(pl.hot_lists, lists.data(), sizeof(int4) * lists.size(), cudaMemcpyHostToDevice, st));
     MFB_CUDA(cudaStreamSynchronize(st));
   }
@@ -371,12 +371,12 @@ static int sgd_plan_common(mfb_engine *e) {
   SgdPlan &pl = e->sgd;
   const DevCsr &m = e->mat[MFB_TRAIN];
   cudaStream_t st = e->stream;
-  MFB_CUDA(cudaMalloc(&pl.work_counter, sizeof(int)));
+  MFB_CUDA(dev_alloc(&pl.work_counter, sizeof(int)));
   MFB_CUDA(cudaMemsetAsync(pl.work_counter, 0, sizeof(int), st));
   pl.hot_item_share = 0.0;
   if (m.nnz > 0) {
     int32_t *hist, *d_max;
-    MFB_CUDA(cudaMalloc(&hist, sizeof(int32_t) * ((size_t)e->n_items + 1)));
+    MFB_CUDA(dev_alloc(&hist, sizeof(int32_t) * ((size_t)e->n_items + 1)));
     d_max = hist + e->n_items;
     MFB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int32_t) * ((size_t)e->n_items + 1), st));
     MFB_LAUNCH(item_hist_kernel, (unsigned)((m.nnz + 255) / 256), 256, 0, st, m.rowind, m.nnz, hist);
@@ -387,7 +387,7 @@ static int sgd_plan_common(mfb_engine *e) {
     int32_t mx = 0;
     MFB_CUDA(cudaMemcpyAsync(&mx, d_max, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     double *sq, *d_sum, sum = 0;
-    MFB_CUDA(cudaMalloc(&sq, sizeof(double) * ((size_t)e->n_items + 1)));
+    MFB_CUDA(dev_alloc(&sq, sizeof(double) * ((size_t)e->n_items + 1)));
     d_sum = sq + e->n_items;
     MFB_LAUNCH(sq_count_kernel, (e->n_items + 255) / 256, 256, 0, st, hist, e->n_items, sq);
     MFB_CUDA(cub::DeviceReduce::Sum(nullptr, tmp_bytes, sq, d_sum, e->n_items, st));
@@ -397,8 +397,8 @@ static int sgd_plan_common(mfb_engine *e) {
     pl.item_count.resize((size_t)e->n_items);
     MFB_CUDA(cudaMemcpyAsync(pl.item_count.data(), hist, sizeof(int32_t) * (size_t)e->n_items, cudaMemcpyDeviceToHost, st));
     MFB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(hist);
-    cudaFree(sq);
+    dev_free(hist);
+    dev_free(sq);
     pl.hot_item_share = (double)mx / (double)m.nnz;
     pl.collision_mass = sum / ((double)m.nnz * (double)m.nnz);
   }
@@ -425,7 +425,7 @@ int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int
     pl.nnz = m.nnz;
     pl.blk_nnz[0] = m.nnz;
     pl.runs_built = false;
-    MFB_CUDA(cudaMalloc(&pl.rat_user, sizeof(int32_t) * (size_t)(m.nnz > 0 ? m.nnz : 1)));
+    MFB_CUDA(dev_alloc(&pl.rat_user, sizeof(int32_t) * (size_t)(m.nnz > 0 ? m.nnz : 1)));
     if (m.nnz > 0)
       MFB_LAUNCH(rat_user_kernel, (unsigned)((m.nnz + 255) / 256), 256, 0, st, m.rowptr, e->n_users, m.nnz, pl.rat_user);
     // user bands of the shuffled kernel: equal user counts, rating offsets read back from rowptr
@@ -461,22 +461,22 @@ int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int
     std::vector<int32_t> ids((size_t)std::max(pl.part_item_off[P], 1)), fill(pl.part_item_off.begin(), pl.part_item_off.end() - 1);
     for (int i = 0; i < e->n_items; i++)
       if (item_part[i] >= 0 && item_part[i] < P) ids[fill[item_part[i]]++] = i;
-    MFB_CUDA(cudaMalloc(&pl.part_items, sizeof(int32_t) * ids.size()));
+    MFB_CUDA(dev_alloc(&pl.part_items, sizeof(int32_t) * ids.size()));
     MFB_CUDA(cudaMemcpyAsync(pl.part_items, ids.data(), sizeof(int32_t) * ids.size(), cudaMemcpyHostToDevice, st));
     MFB_CUDA(cudaStreamSynchronize(st));
   }
   int32_t *d_up, *d_ip;
-  MFB_CUDA(cudaMalloc(&d_up, sizeof(int32_t) * e->n_users));
-  MFB_CUDA(cudaMalloc(&d_ip, sizeof(int32_t) * e->n_items));
+  MFB_CUDA(dev_alloc(&d_up, sizeof(int32_t) * e->n_users));
+  MFB_CUDA(dev_alloc(&d_ip, sizeof(int32_t) * e->n_items));
   MFB_CUDA(cudaMemcpyAsync(d_up, user_part, sizeof(int32_t) * e->n_users, cudaMemcpyHostToDevice, st));
   MFB_CUDA(cudaMemcpyAsync(d_ip, item_part, sizeof(int32_t) * e->n_items, cudaMemcpyHostToDevice, st));
   uint64_t *keys, *keys2;
   int32_t *idx, *idx2;
   size_t nn = (size_t)(nnz > 0 ? nnz : 1);
-  MFB_CUDA(cudaMalloc(&keys, sizeof(uint64_t) * nn));
-  MFB_CUDA(cudaMalloc(&keys2, sizeof(uint64_t) * nn));
-  MFB_CUDA(cudaMalloc(&idx, sizeof(int32_t) * nn));
-  MFB_CUDA(cudaMalloc(&idx2, sizeof(int32_t) * nn));
+  MFB_CUDA(dev_alloc(&keys, sizeof(uint64_t) * nn));
+  MFB_CUDA(dev_alloc(&keys2, sizeof(uint64_t) * nn));
+  MFB_CUDA(dev_alloc(&idx, sizeof(int32_t) * nn));
+  MFB_CUDA(dev_alloc(&idx2, sizeof(int32_t) * nn));
   int tb = 256;
   unsigned gb = (unsigned)((nnz + tb - 1) / tb);
   if (nnz > 0) MFB_LAUNCH(sgd_key_kernel, gb, tb, 0, st, m.rowptr, e->n_users, m.rowind, nnz, d_up, d_ip, P, keys, idx);
@@ -487,23 +487,23 @@ int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int
   MFB_TRY(ensure_scratch(e, tmp_bytes));
   MFB_CUDA(cub::DeviceRadixSort::SortPairs(e->scratch, tmp_bytes, keys, keys2, idx, idx2, (int)nnz, 0, end_bit, st));
   // reordered ratings
-  MFB_CUDA(cudaMalloc(&pl.item, sizeof(int32_t) * nn));
-  MFB_CUDA(cudaMalloc(&pl.val, sizeof(float) * nn));
+  MFB_CUDA(dev_alloc(&pl.item, sizeof(int32_t) * nn));
+  MFB_CUDA(dev_alloc(&pl.val, sizeof(float) * nn));
   pl.owns_ratings = true;
   if (nnz > 0) MFB_LAUNCH(sgd_gather_kernel, gb, tb, 0, st, idx2, nnz, m.rowind, m.rowval, pl.item, pl.val);
   // user of every reordered rating (low word of the sorted key) for the shuffled-in-block kernel
-  MFB_CUDA(cudaMalloc(&pl.rat_user, sizeof(int32_t) * nn));
+  MFB_CUDA(dev_alloc(&pl.rat_user, sizeof(int32_t) * nn));
   if (nnz > 0) MFB_LAUNCH(key_user_kernel, gb, tb, 0, st, keys2, nnz, pl.rat_user);
   // runs of equal (block, user): reuse `keys` for the unique keys, `idx` for the run lengths
   int32_t *d_nruns;
-  MFB_CUDA(cudaMalloc(&d_nruns, sizeof(int32_t)));
+  MFB_CUDA(dev_alloc(&d_nruns, sizeof(int32_t)));
   MFB_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, tmp_bytes, keys2, keys, idx, d_nruns, (int)nnz, st));
   MFB_TRY(ensure_scratch(e, tmp_bytes));
   MFB_CUDA(cub::DeviceRunLengthEncode::Encode(e->scratch, tmp_bytes, keys2, keys, idx, d_nruns, (int)nnz, st));
   int32_t nruns = 0;
   MFB_CUDA(cudaMemcpyAsync(&nruns, d_nruns, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   MFB_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_nruns);
+  dev_free(d_nruns);
   if (nnz == 0) nruns = 0;
   // run starts = exclusive scan of the run lengths (into idx2)
   int32_t *run_len = idx, *run_start = idx2;
@@ -518,11 +518,11 @@ int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int
   std::vector<int32_t> bounds(nblk + 1, 0), nnz_at(nblk + 1, 0);
   if (nruns > 0) {
     int32_t *d_bounds;
-    MFB_CUDA(cudaMalloc(&d_bounds, sizeof(int32_t) * (nblk + 1)));
+    MFB_CUDA(dev_alloc(&d_bounds, sizeof(int32_t) * (nblk + 1)));
     MFB_LAUNCH(sgd_blk_bounds_kernel, (nblk + 1 + 255) / 256, 256, 0, st, run_key, nruns, nblk, d_bounds);
     MFB_CUDA(cudaMemcpyAsync(bounds.data(), d_bounds, sizeof(int32_t) * (nblk + 1), cudaMemcpyDeviceToHost, st));
     MFB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_bounds);
+    dev_free(d_bounds);
     // rating offset of each block's first run
     for (int b = 0; b <= nblk; b++) {
       if (bounds[b] >= nruns) {
@@ -568,17 +568,17 @@ int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int
       }
   }
   size_t ns = (size_t)(nseg > 0 ? nseg : 1);
-  MFB_CUDA(cudaMalloc(&pl.seg_user, sizeof(int32_t) * ns));
-  MFB_CUDA(cudaMalloc(&pl.seg_start, sizeof(int32_t) * ns));
-  MFB_CUDA(cudaMalloc(&pl.seg_len, sizeof(int32_t) * ns));
+  MFB_CUDA(dev_alloc(&pl.seg_user, sizeof(int32_t) * ns));
+  MFB_CUDA(dev_alloc(&pl.seg_start, sizeof(int32_t) * ns));
+  MFB_CUDA(dev_alloc(&pl.seg_len, sizeof(int32_t) * ns));
   if (nseg > 0) {
     // longest-first inside every block
     uint64_t *key2 = keys2;  // sorted rating keys no longer needed
     uint64_t *key2_out = keys2 + nseg;  // nnz >= 2 * nseg is not guaranteed: allocate separately if short
     int32_t *sidx, *sidx_out;
     bool own_key_out = (size_t)nnz < 2 * (size_t)nseg;
-    if (own_key_out) MFB_CUDA(cudaMalloc(&key2_out, sizeof(uint64_t) * ns));
-    MFB_CUDA(cudaMalloc(&sidx, sizeof(int32_t) * 2 * ns));
+    if (own_key_out) MFB_CUDA(dev_alloc(&key2_out, sizeof(uint64_t) * ns));
+    MFB_CUDA(dev_alloc(&sidx, sizeof(int32_t) * 2 * ns));
     sidx_out = sidx + nseg;
     int gs = (nseg + tb - 1) / tb;
     MFB_LAUNCH(sgd_seg_key_kernel, gs, tb, 0, st, run_key, run_len, nseg, key2, sidx);
@@ -588,11 +588,11 @@ int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int
     MFB_LAUNCH(sgd_seg_gather_kernel, gs, tb, 0, st, sidx_out, nseg, run_key, run_start, run_len, pl.seg_user,
                pl.seg_start, pl.seg_len);
     MFB_CUDA(cudaStreamSynchronize(st));
-    if (own_key_out) cudaFree(key2_out);
-    cudaFree(sidx);
+    if (own_key_out) dev_free(key2_out);
+    dev_free(sidx);
   }
   MFB_CUDA(cudaStreamSynchronize(st));
-  cudaFree(keys); cudaFree(keys2); cudaFree(idx); cudaFree(idx2); cudaFree(d_up); cudaFree(d_ip);
+  dev_free(keys); dev_free(keys2); dev_free(idx); dev_free(idx2); dev_free(d_up); dev_free(d_ip);
   {  // shuffle blocks = the P x P stratum blocks (block-major order, the dropped bucket excluded)
     std::vector<int64_t> ranges;
     std::vector<int32_t> bids;
