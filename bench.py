@@ -47,7 +47,7 @@ HP = dict(lr=0.002, ureg=0.05, ireg=0.05)
 FALLBACK_HBM_GBS = 6650.0
 ITEM_SHARE_CAP = 232_944 / 100_480_507
 # dram__bytes_read.sum + dram__bytes_write.sum of the SGD kernel launches of one epoch (profiles/r1_sgd_flat.md)
-DRAM_TRAFFIC_BYTES_PER_EPOCH = 10.28e9
+DRAM_TRAFFIC_BYTES_PER_EPOCH = 10.44e9
 
 
 def log(*a):
