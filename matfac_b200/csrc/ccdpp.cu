@@ -14,6 +14,7 @@
 namespace mfb {
 
 constexpr int kCcdChunk = 1024;
+constexpr int kCcdDepth = 8;  // independent loads per lane in flight
 
 // row-sharded runs: the other ranks' copies of the dense u_k / v_k vector being produced (peer memory);
 // every new entry is stored into all of them, so the all-gather rides on the update pass itself
@@ -33,24 +34,49 @@ struct CcdPass {
   int n_seg;
 };
 
-// res[j] += sign * own[row] * other[ind[j]]
+// res[j] += sign * own[row] * other[ind[j]]; only_multi: segments of split rows only (the fused update pass below
+// has already subtracted the single-segment rows)
 __global__ void __launch_bounds__(256) ccd_resid_kernel(const CcdPass p, const float *__restrict__ own,
-                                                        const float *__restrict__ other, float sign) {
+                                                        const float *__restrict__ other, float sign, int only_multi) {
   const int lane = threadIdx.x & 31;
   const int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (seg >= p.n_seg) return;
+  if (only_multi && p.seg_slot[seg] < 0) return;
   const int row = p.seg_row[seg], start = p.seg_start[seg], len = p.seg_len[seg];
   const float a = sign * __ldg(own + row);
-  for (int j = lane; j < len; j += 32) {
-    const int c = __ldg(p.ind + start + j);
-    // own*other is rounded to fp32 before it is added (modelMF.cpp:1041), hence no fma here
-    p.res[start + j] = __fadd_rn(p.res[start + j], __fmul_rn(a, __ldg(other + c)));
+  // kCcdDepth independent (index, residual) loads per lane are issued before the first dependent gather: a pass is
+  // bound by the latency of its short segments, not by bandwidth
+  for (int base = 0; base < len; base += 32 * kCcdDepth) {
+    int c[kCcdDepth];
+    float r[kCcdDepth];
+#pragma unroll
+    for (int d = 0; d < kCcdDepth; d++) {
+      const int j = base + d * 32 + lane;
+      c[d] = j < len ? __ldg(p.ind + start + j) : -1;
+      r[d] = j < len ? p.res[start + j] : 0.f;
+    }
+#pragma unroll
+    for (int d = 0; d < kCcdDepth; d++) {
+      if (c[d] < 0) continue;
+      // own*other is rounded to fp32 before it is added (modelMF.cpp:1041), hence no fma here
+      p.res[start + base + d * 32 + lane] = __fadd_rn(r[d], __fmul_rn(a, __ldg(other + c[d])));
+    }
   }
 }
 
-// own[row] = sum res*other / (reg + sum other^2), fp64 accumulation of fp32 products
+// own[row] = sum res*other / (reg + sum other^2), fp64 accumulation of fp32 products.
+// Fused forms (same statements in the same order, fewer trips through memory — a pass is bound by the latency of
+// its short segments, 209 ratings per user row on the bench matrix, so every pass saved counts in full):
+//   ADDBACK  : the residual add-back of modelMF.cpp:1034-1055, res += own_old[row] * other_old[ind], is applied on
+//              the way in and written back; the update then uses the current `other` (for the column pass u_k has
+//              already been updated once, other_old = its copy from before);
+//   SUBTRACT : after the last update of v_k the subtraction of :1096-1116, res -= own_new[row] * other[ind], runs as a
+//              second loop over the segment the warp has just read (L1 / L2 hits) — single-segment rows only, the
+//              segments of split rows are subtracted by ccd_resid_kernel(only_multi) after ccd_finalize_kernel.
+template <bool ADDBACK, bool SUBTRACT>
 __global__ void __launch_bounds__(256) ccd_update_kernel(const CcdPass p, float *__restrict__ own,
-                                                         const float *__restrict__ other, float reg,
+                                                         const float *__restrict__ other,
+                                                         const float *__restrict__ other_old, float reg,
                                                          double *__restrict__ acc, const Aux *__restrict__ aux_freq,
                                                          int freq_thresh, const CcdPeers pe) {
   const int lane = threadIdx.x & 31;
@@ -58,26 +84,58 @@ __global__ void __launch_bounds__(256) ccd_update_kernel(const CcdPass p, float 
   if (seg >= p.n_seg) return;
   const int row = p.seg_row[seg], start = p.seg_start[seg], len = p.seg_len[seg], slot = p.seg_slot[seg];
   double num = 0.0, den = 0.0;
-  for (int j = lane; j < len; j += 32) {
-    const int c = __ldg(p.ind + start + j);
-    const float o = __ldg(other + c);
-    num += (double)__fmul_rn(p.res[start + j], o);
-    den += (double)__fmul_rn(o, o);
+  const float a_old = ADDBACK ? own[row] : 0.f;
+  for (int base = 0; base < len; base += 32 * kCcdDepth) {
+    int c[kCcdDepth];
+    float r[kCcdDepth], o[kCcdDepth];
+#pragma unroll
+    for (int d = 0; d < kCcdDepth; d++) {
+      const int j = base + d * 32 + lane;
+      c[d] = j < len ? __ldg(p.ind + start + j) : -1;
+      r[d] = j < len ? p.res[start + j] : 0.f;
+    }
+#pragma unroll
+    for (int d = 0; d < kCcdDepth; d++) {
+      o[d] = c[d] >= 0 ? __ldg(other + c[d]) : 0.f;
+      if (ADDBACK && c[d] >= 0) {
+        r[d] = __fadd_rn(r[d], __fmul_rn(a_old, __ldg(other_old + c[d])));
+        p.res[start + base + d * 32 + lane] = r[d];
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < kCcdDepth; d++) {
+      num += (double)__fmul_rn(r[d], o[d]);
+      den += (double)__fmul_rn(o[d], o[d]);
+    }
   }
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) {
     num += __shfl_xor_sync(0xFFFFFFFFu, num, m);
     den += __shfl_xor_sync(0xFFFFFFFFu, den, m);
   }
-  if (lane == 0) {
-    if (slot < 0) {
-      float nv = (float)(num / ((double)reg + den));
-      if (freq_thresh > 0 && aux_freq[row].freq < freq_thresh) nv = 0.f;
-      store_all(own, pe, row, nv);
-    } else {
-      atomicAdd(acc + 2 * (size_t)slot, num);
-      atomicAdd(acc + 2 * (size_t)slot + 1, den);
+  if (slot < 0) {
+    float nv = (float)(num / ((double)reg + den));
+    if (freq_thresh > 0 && aux_freq[row].freq < freq_thresh) nv = 0.f;
+    if (lane == 0) store_all(own, pe, row, nv);
+    if (SUBTRACT) {
+      const float a = -nv;
+      for (int base = 0; base < len; base += 32 * kCcdDepth) {
+        int c[kCcdDepth];
+        float r[kCcdDepth];
+#pragma unroll
+        for (int d = 0; d < kCcdDepth; d++) {
+          const int j = base + d * 32 + lane;
+          c[d] = j < len ? __ldg(p.ind + start + j) : -1;
+          r[d] = j < len ? p.res[start + j] : 0.f;
+        }
+#pragma unroll
+        for (int d = 0; d < kCcdDepth; d++)
+          if (c[d] >= 0) p.res[start + base + d * 32 + lane] = __fadd_rn(r[d], __fmul_rn(a, __ldg(other + c[d])));
+      }
     }
+  } else if (lane == 0) {
+    atomicAdd(acc + 2 * (size_t)slot, num);
+    atomicAdd(acc + 2 * (size_t)slot + 1, den);
   }
 }
 
@@ -112,6 +170,7 @@ int ccdpp_begin_impl(mfb_engine *e) {
   if (!e->res_col) MFB_CUDA(dev_alloc(&e->res_col, sizeof(float) * nn));
   if (!e->uk) MFB_CUDA(dev_alloc(&e->uk, sizeof(float) * e->n_users));
   if (!e->vk) MFB_CUDA(dev_alloc(&e->vk, sizeof(float) * e->n_items));
+  if (!e->uk_old) MFB_CUDA(dev_alloc(&e->uk_old, sizeof(float) * e->n_users));
   // res = gk_csr_Dup(trainMat) (modelMF.cpp:1013); uFac.fill(0) (:1020)
   MFB_CUDA(cudaMemcpyAsync(e->res_row, m.rowval, sizeof(float) * (size_t)m.nnz, cudaMemcpyDeviceToDevice, st));
   MFB_CUDA(cudaMemcpyAsync(e->res_col, m.colval, sizeof(float) * (size_t)m.nnz, cudaMemcpyDeviceToDevice, st));
@@ -155,26 +214,46 @@ int ccdpp_rank1_impl(mfb_engine *e, int32_t k, int first_iter, int32_t inner, fl
   if (uhi > ulo) MFB_LAUNCH(col_extract_kernel, (uhi - ulo + 255) / 256, 256, 0, st, e->U, e->ld, k, ulo, uhi, e->uk, pu);
   if (ihi > ilo) MFB_LAUNCH(col_extract_kernel, (ihi - ilo + 255) / 256, 256, 0, st, e->V, e->ld, k, ilo, ihi, e->vk, pv);
   MFB_TRY(comm_barrier_launch(e));
-  if (!first_iter) {
-    if (g_rows) MFB_LAUNCH(ccd_resid_kernel, g_rows, tb, 0, st, rows, e->uk, e->vk, 1.0f);
-    if (g_cols) MFB_LAUNCH(ccd_resid_kernel, g_cols, tb, 0, st, cols, e->vk, e->uk, 1.0f);
-  }
   // the FreqAdap rule zeroes v_k of infrequent items for k > 0 (modelMF.cpp:1336-1342)
   const int thresh = (item_freq_thresh > 0 && k > 0) ? item_freq_thresh : 0;
+  const bool fuse_add = !first_iter && inner >= 1 && e->opt_ccd_fuse;          // add-back rides on the first updates
+  const bool fuse_sub = inner >= (fuse_add ? 2 : 1) && e->opt_ccd_fuse;        // column subtract rides on the last v_k update
+  if (!first_iter && !fuse_add) {
+    if (g_rows) MFB_LAUNCH(ccd_resid_kernel, g_rows, tb, 0, st, rows, e->uk, e->vk, 1.0f, 0);
+    if (g_cols) MFB_LAUNCH(ccd_resid_kernel, g_cols, tb, 0, st, cols, e->vk, e->uk, 1.0f, 0);
+  }
+  if (fuse_add)  // the column add-back needs u_k as it was before its first update
+    MFB_CUDA(cudaMemcpyAsync(e->uk_old, e->uk, sizeof(float) * (size_t)e->n_users, cudaMemcpyDeviceToDevice, st));
   for (int s = 0; s < inner; s++) {
-    if (g_rows) MFB_LAUNCH(ccd_update_kernel, g_rows, tb, 0, st, rows, e->uk, e->vk, ureg, e->ccd_acc, e->aux_u, 0, pu);
+    if (g_rows) {
+      if (s == 0 && fuse_add)
+        MFB_LAUNCH((ccd_update_kernel<true, false>), g_rows, tb, 0, st, rows, e->uk, e->vk, e->vk, ureg, e->ccd_acc, e->aux_u, 0, pu);
+      else
+        MFB_LAUNCH((ccd_update_kernel<false, false>), g_rows, tb, 0, st, rows, e->uk, e->vk, e->vk, ureg, e->ccd_acc, e->aux_u, 0, pu);
+    }
     if (rp.n_multi)
       MFB_LAUNCH(ccd_finalize_kernel, (rp.n_multi + 255) / 256, 256, 0, st, rp.multi_row, rp.n_multi, e->ccd_acc, e->uk,
                  ureg, e->aux_u, 0, pu);
     MFB_TRY(comm_barrier_launch(e));
-    if (g_cols) MFB_LAUNCH(ccd_update_kernel, g_cols, tb, 0, st, cols, e->vk, e->uk, ireg, e->ccd_acc, e->aux_i, thresh, pv);
+    if (g_cols) {
+      if (s == 0 && fuse_add)
+        MFB_LAUNCH((ccd_update_kernel<true, false>), g_cols, tb, 0, st, cols, e->vk, e->uk, e->uk_old, ireg, e->ccd_acc, e->aux_i, thresh, pv);
+      else if (s == inner - 1 && fuse_sub)
+        MFB_LAUNCH((ccd_update_kernel<false, true>), g_cols, tb, 0, st, cols, e->vk, e->uk, e->uk, ireg, e->ccd_acc, e->aux_i, thresh, pv);
+      else
+        MFB_LAUNCH((ccd_update_kernel<false, false>), g_cols, tb, 0, st, cols, e->vk, e->uk, e->uk, ireg, e->ccd_acc, e->aux_i, thresh, pv);
+    }
     if (cp.n_multi)
       MFB_LAUNCH(ccd_finalize_kernel, (cp.n_multi + 255) / 256, 256, 0, st, cp.multi_row, cp.n_multi, e->ccd_acc, e->vk,
                  ireg, e->aux_i, thresh, pv);
     MFB_TRY(comm_barrier_launch(e));
   }
-  if (g_rows) MFB_LAUNCH(ccd_resid_kernel, g_rows, tb, 0, st, rows, e->uk, e->vk, -1.0f);
-  if (g_cols) MFB_LAUNCH(ccd_resid_kernel, g_cols, tb, 0, st, cols, e->vk, e->uk, -1.0f);
+  if (g_rows) MFB_LAUNCH(ccd_resid_kernel, g_rows, tb, 0, st, rows, e->uk, e->vk, -1.0f, 0);
+  if (fuse_sub) {
+    if (g_cols && cp.n_multi) MFB_LAUNCH(ccd_resid_kernel, g_cols, tb, 0, st, cols, e->vk, e->uk, -1.0f, 1);
+  } else if (g_cols) {
+    MFB_LAUNCH(ccd_resid_kernel, g_cols, tb, 0, st, cols, e->vk, e->uk, -1.0f, 0);
+  }
   if (uhi > ulo) MFB_LAUNCH(col_insert_kernel, (uhi - ulo + 255) / 256, 256, 0, st, e->U, e->ld, k, ulo, uhi, e->uk);
   if (ihi > ilo) MFB_LAUNCH(col_insert_kernel, (ihi - ilo + 255) / 256, 256, 0, st, e->V, e->ld, k, ilo, ihi, e->vk);
   return 0;

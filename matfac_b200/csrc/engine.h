@@ -169,6 +169,7 @@ struct mfb_engine {
   double opt_sgd_hot_stab = 0.5;      // hot CTAs: mini-batch <= value / (learnrate x rating-weighted mean |u|^2)
   int opt_sgd_hot_pace = 1;           // hot CTAs advance through their list in step with the shuffled kernel
   int opt_sgd_hot_batch = 0;          // ratings per round of a hot CTA, 0 = automatic (<= 64 and <= sgd_flat_hot_lr / learnrate)
+  int opt_ccd_fuse = 1;               // CCD++: add-back / column subtract ride on the first / last update passes
   int opt_als_chunk = 16384;          // ratings per CTA before a row is split over several CTAs
   int opt_als_dual = 1;               // short rows: solve the len x len dual system instead of rank x rank
   int opt_als_tensor_cores = 1;       // rank > 64: Gram on tcgen05 (3xTF32); 0 = fp32 CUDA-core Gram
@@ -201,6 +202,7 @@ struct mfb_engine {
   // CCD++ state
   float *res_row = nullptr, *res_col = nullptr;  // residual (CSR order / CSC order)
   float *uk = nullptr, *vk = nullptr;
+  float *uk_old = nullptr;  // u_k before its first update of the rank-one step (fused column add-back)
   double *ccd_acc = nullptr;  // [slots][2]
   size_t ccd_acc_slots = 0;
 

@@ -126,6 +126,7 @@ def main():
             ev = [float(t[0]), float(t[1])]
         out.update(val_rmse=float(np.sqrt(ev[0] / max(ev[1], 1))))
     elif args.algo == "ccdpp":
+        eng.set_option("ccd_fuse", int(os.environ.get("MFB_CCD_FUSE", "1")))
         eng.ccdpp_begin()
         dims = min(r, 8)
         for k in range(dims):  # iter 0 (no add-back)
