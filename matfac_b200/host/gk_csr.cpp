@@ -19,6 +19,90 @@ void gk_csr_Free(gk_csr_t **mat) {
   *mat = NULL;
 }
 
+// ---- binary sidecar of a parsed text CSR (fast ingest) -------------------------------------------
+// The text file stays the source of truth.  With MATFAC_CSR_CACHE=1 (read + write) or =r (read only) in the
+// environment gk_csr_Read keeps `<file>.bin` next to it: a 64-byte header (magic, version, size and mtime of the
+// text file, readvals, numbering, nrows, ncols, nnz) followed by rowptr (int64), rowind (int32) and rowval (fp32).
+// The sidecar is used only while size and mtime of the text file still match; it is written to a temporary name
+// and renamed.  At Netflix scale the parse takes tens of seconds, the sidecar read is bounded by the disk.
+#include <string>
+#include <sys/stat.h>
+#include <unistd.h>
+
+namespace {
+struct BinHeader {
+  char magic[8];       // "MFBCSR1\0"
+  int64_t text_size, text_mtime_ns;
+  int32_t readvals, numbering, nrows, ncols;
+  int64_t nnz;
+  int64_t reserved[2];
+};
+static_assert(sizeof(BinHeader) == 64, "sidecar header is 64 bytes");
+
+int cache_mode() {  // 0 off, 1 read, 2 read + write
+  const char *v = getenv("MATFAC_CSR_CACHE");
+  if (!v || !*v || *v == '0') return 0;
+  return (*v == 'r' || *v == 'R') ? 1 : 2;
+}
+
+bool text_identity(const char *filename, int64_t *size, int64_t *mtime_ns) {
+  struct stat st;
+  if (stat(filename, &st) != 0) return false;
+  *size = (int64_t)st.st_size;
+  *mtime_ns = (int64_t)st.st_mtim.tv_sec * 1000000000LL + (int64_t)st.st_mtim.tv_nsec;
+  return true;
+}
+
+gk_csr_t *sidecar_read(const char *filename, int readvals, int numbering) {
+  int64_t size = 0, mtime = 0;
+  if (!text_identity(filename, &size, &mtime)) return NULL;
+  const std::string bin = std::string(filename) + ".bin";
+  FILE *fp = fopen(bin.c_str(), "rb");
+  if (!fp) return NULL;
+  BinHeader h;
+  gk_csr_t *m = NULL;
+  if (fread(&h, sizeof(h), 1, fp) == 1 && memcmp(h.magic, "MFBCSR1", 8) == 0 && h.text_size == size &&
+      h.text_mtime_ns == mtime && h.readvals == readvals && h.numbering == numbering && h.nrows >= 0 && h.nnz >= 0) {
+    m = csr_alloc();
+    m->nrows = h.nrows;
+    m->ncols = h.ncols;
+    const size_t nnz = (size_t)h.nnz;
+    m->rowptr = (ssize_t *)malloc(sizeof(ssize_t) * ((size_t)h.nrows + 1));
+    m->rowind = (int32_t *)malloc(sizeof(int32_t) * (nnz ? nnz : 1));
+    m->rowval = readvals ? (float *)malloc(sizeof(float) * (nnz ? nnz : 1)) : NULL;
+    bool ok = fread(m->rowptr, sizeof(ssize_t), (size_t)h.nrows + 1, fp) == (size_t)h.nrows + 1 &&
+              fread(m->rowind, sizeof(int32_t), nnz, fp) == nnz &&
+              (!readvals || fread(m->rowval, sizeof(float), nnz, fp) == nnz) && m->rowptr[0] == 0 &&
+              m->rowptr[h.nrows] == (ssize_t)nnz;
+    if (!ok) gk_csr_Free(&m);
+  }
+  fclose(fp);
+  return m;
+}
+
+void sidecar_write(const char *filename, const gk_csr_t *m, int readvals, int numbering) {
+  BinHeader h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, "MFBCSR1", 8);
+  if (!text_identity(filename, &h.text_size, &h.text_mtime_ns)) return;
+  h.readvals = readvals;
+  h.numbering = numbering;
+  h.nrows = m->nrows;
+  h.ncols = m->ncols;
+  h.nnz = (int64_t)m->rowptr[m->nrows];
+  const std::string bin = std::string(filename) + ".bin", tmp = bin + ".tmp" + std::to_string((long)getpid());
+  FILE *fp = fopen(tmp.c_str(), "wb");
+  if (!fp) return;  // read-only directory: the cache is an optimisation, not a requirement
+  const size_t nnz = (size_t)h.nnz;
+  bool ok = fwrite(&h, sizeof(h), 1, fp) == 1 &&
+            fwrite(m->rowptr, sizeof(ssize_t), (size_t)m->nrows + 1, fp) == (size_t)m->nrows + 1 &&
+            fwrite(m->rowind, sizeof(int32_t), nnz, fp) == nnz &&
+            (!readvals || fwrite(m->rowval, sizeof(float), nnz, fp) == nnz);
+  ok = (fclose(fp) == 0) && ok;
+  if (!ok || rename(tmp.c_str(), bin.c_str()) != 0) remove(tmp.c_str());
+}
+}  // namespace
+
 namespace {
 struct Piece {  // one thread's share of the file
   std::vector<int32_t> ind;
@@ -32,6 +116,11 @@ gk_csr_t *gk_csr_Read(char *filename, int format, int readvals, int numbering) {
   if (format != GK_CSR_FMT_CSR) {
     fprintf(stderr, "gk_csr_Read: only GK_CSR_FMT_CSR is supported\n");
     exit(-1);
+  }
+  const int cache = cache_mode();
+  if (cache) {
+    gk_csr_t *cached = sidecar_read(filename, readvals, numbering);
+    if (cached) return cached;
   }
   FILE *fp = fopen(filename, "rb");
   if (!fp) {
@@ -119,6 +208,7 @@ gk_csr_t *gk_csr_Read(char *filename, int format, int readvals, int numbering) {
     }
     k += pc.ind.size();
   }
+  if (cache == 2) sidecar_write(filename, m, readvals, numbering);
   return m;
 }
 

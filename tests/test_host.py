@@ -23,13 +23,15 @@ MF = os.path.join(ROOT, "matfac_b200", "mf")
 HOST_SO = os.path.join(ROOT, "matfac_b200", "libmatfac_host.so")
 
 
-def run_mf(files, dump, threads=1, timeout=600, **flags):
+def run_mf(files, dump, threads=1, timeout=600, env_extra=None, **flags):
     os.makedirs(dump, exist_ok=True)
     cmd = [MF, "--trainmat", files[0], "--valmat", files[1], "--testmat", files[2], "--prefix",
            os.path.join(dump, "gpu"), "--dump", dump]
     for k, v in flags.items():
         cmd += ["--" + k, str(v)]
     env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+    env.pop("MATFAC_CSR_CACHE", None)
+    env.update(env_extra or {})
     p = subprocess.run(cmd, env=env, cwd=dump, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout)
     out = p.stdout.decode(errors="replace")
     assert p.returncode == 0, out[-3000:]
@@ -91,6 +93,55 @@ def test_text_reader_handles_empty_rows_and_parallel_split(tmp_path):
         ptr, ind, val = od.csr(0)
         assert d["nrows"] == n_users and int(d["rowptr"][-1]) == nnz
         assert np.array_equal(ptr, d["rowptr"]) and np.array_equal(ind, d["rowind"]) and np.array_equal(val, d["rowval"])
+
+
+def test_binary_sidecar_matches_the_text_parse_and_tracks_the_text_file(tmp_path):
+    """MATFAC_CSR_CACHE (SURVEY 8f fast ingest): the `.bin` sidecar written after the first parse must give the
+    same CSR / CSC arrays bit for bit, and must be ignored once the text file changes (size or mtime)."""
+    rng = np.random.default_rng(1)
+    n_users, n_items = 3000, 200
+
+    def write(path, seed_shift):
+        r = np.random.default_rng(seed_shift)
+        with open(path, "w") as f:
+            for u in range(n_users):
+                k = 0 if u % 11 == 5 else int(r.integers(1, 40))
+                items = np.sort(r.choice(n_items, size=k, replace=False))
+                f.write(" ".join(f"{i} {r.integers(1, 11) / 2:g}" for i in items) + "\n")
+
+    path = str(tmp_path / "m.csr")
+    write(path, 7)
+    files = [path, path, path]
+
+    def dump(name, cache):
+        out = str(tmp_path / name)
+        run_mf(files, out, threads=3, facdim=2, dry_run=1, env_extra={"MATFAC_CSR_CACHE": cache} if cache else None)
+        return ol.read_csr_dump(os.path.join(out, "train.csr.bin"))
+
+    plain = dump("plain", None)
+    assert not os.path.exists(path + ".bin")
+    first = dump("first", "1")          # parses the text, writes the sidecar
+    assert os.path.exists(path + ".bin")
+    again = dump("again", "r")          # served from the sidecar
+    for d in (first, again):
+        for key in ("rowptr", "rowind", "rowval", "colptr", "colind", "colval"):
+            assert np.array_equal(plain[key], d[key]), key
+        assert d["nrows"] == plain["nrows"] and d["ncols"] == plain["ncols"]
+    # proof that `again` came from the sidecar: a sidecar whose values were tampered with (same header) is served as is
+    with open(path + ".bin", "r+b") as f:
+        f.seek(64 + 8 * (n_users + 1))
+        first_ind = np.frombuffer(f.read(4), np.int32)[0]
+        f.seek(64 + 8 * (n_users + 1))
+        f.write(np.int32(first_ind + 1).tobytes())
+    tampered = dump("tampered", "r")
+    assert tampered["rowind"][0] == first_ind + 1
+    # a different text file (size / mtime changed): the stale sidecar must be ignored
+    write(path, 8)
+    fresh_plain = dump("plain2", None)
+    fresh_cached = dump("cached2", "r")
+    assert not np.array_equal(fresh_plain["rowptr"], plain["rowptr"])
+    for key in ("rowptr", "rowind", "rowval"):
+        assert np.array_equal(fresh_plain[key], fresh_cached[key]), key
 
 
 def test_missing_flags_exit_like_the_reference(tmp_path):
