@@ -648,7 +648,7 @@ extern "C" int mfb_sgd_subepoch(mfb_engine *e, const int32_t *blocks, int32_t nb
 extern "C" int mfb_sgd_epoch_flat(mfb_engine *e, int variant, float learn_rate, float ureg, float ireg, uint64_t seed,
                                   uint64_t counter) {
   MFB_REQUIRE(e, "null engine");
-  MFB_REQUIRE(e->sgd.built && e->sgd.P == 1 && e->sgd.rat_user, "mfb_sgd_epoch_flat: call mfb_sgd_plan(P = 1) first");
+  MFB_REQUIRE(e->sgd.built && e->sgd.P == 1 && e->sgd.recs, "mfb_sgd_epoch_flat: call mfb_sgd_plan(P = 1) first");
   const int32_t whole[2] = {0, 0};
   MFB_REQUIRE(variant >= MFB_MF && variant <= MFB_TMFDROPOUT, "mfb_sgd_epoch_flat: bad variant");
   MFB_REQUIRE(variant == MFB_MF || e->aux_variant == variant, "mfb_sgd_epoch_flat: mfb_set_aux not called for this variant");

@@ -105,17 +105,6 @@ __global__ void sq_count_kernel(const int32_t *__restrict__ hist, int32_t n, dou
   if (i < n) out[i] = (double)hist[i] * (double)hist[i];
 }
 
-__global__ void rat_user_kernel(const int64_t *__restrict__ rowptr, int32_t nrows, int64_t nnz, int32_t *__restrict__ out) {
-  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nnz) return;
-  int lo = 0, hi = nrows;
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (rowptr[mid] <= j) lo = mid; else hi = mid;
-  }
-  out[j] = lo;
-}
-
 // ---- physically shuffled rating records for the shuffled kernel -------------------------------
 // The epoch order of the serial trainers is a random permutation (modelMF.cpp:76-81).  Fetching
 // (user, item, rating) through a permuted index costs three random 4-byte DRAM reads per rating —
@@ -143,8 +132,29 @@ __device__ __forceinline__ uint32_t keyed_bijection(uint32_t x, uint32_t n, uint
   return x;
 }
 
-__global__ void sgd_shuffle_records_kernel(const int32_t *__restrict__ rat_user, const int32_t *__restrict__ item,
-                                           const float *__restrict__ val, int64_t n, const int64_t *__restrict__ blk_off,
+// (user, item, rating) of every rating position as one 16-byte record, in memory order: the shuffle below then
+// gathers ONE sector per rating instead of three (6.3 -> 2.5 ms at 100 M ratings).  user = rat_user[j], or the row
+// of position j by binary search in rowptr when rat_user is null (whole-matrix plans).
+__global__ void sgd_pack_records_kernel(const int64_t *__restrict__ rowptr, int32_t nrows, const int32_t *__restrict__ rat_user,
+                                        const int32_t *__restrict__ item, const float *__restrict__ val, int64_t n,
+                                        int4 *__restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  int user;
+  if (rat_user) {
+    user = rat_user[j];
+  } else {
+    int lo = 0, hi = nrows;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (rowptr[mid] <= j) lo = mid; else hi = mid;
+    }
+    user = lo;
+  }
+  out[j] = make_int4(user, item[j], __float_as_int(val[j]), 0);
+}
+
+__global__ void sgd_shuffle_records_kernel(const int4 *__restrict__ packed, int64_t n, const int64_t *__restrict__ blk_off,
                                            int nblk, uint64_t seed, int4 *__restrict__ recs,
                                            const int32_t *__restrict__ range_row, int32_t n_items,
                                            const uint8_t *__restrict__ cls, uint32_t *__restrict__ keys) {
@@ -158,10 +168,10 @@ __global__ void sgd_shuffle_records_kernel(const int32_t *__restrict__ rat_user,
   const int64_t off = blk_off[lo];
   const uint32_t nb = (uint32_t)(blk_off[lo + 1] - off);
   const int64_t j = off + keyed_bijection((uint32_t)(q - off), nb, seed * 0x100000001B3ull + (uint64_t)lo);
-  const int32_t it = __ldg(item + j);
-  recs[q] = make_int4(__ldg(rat_user + j), it, __float_as_int(__ldg(val + j)), 0);
+  const int4 rec = __ldg(packed + j);
+  recs[q] = rec;
   // sort key of the hot / cold split: range in the high bits, 0 = cold or 1 + the item's hot slot in the low 7
-  if (keys) keys[q] = ((uint32_t)lo << 7) | (uint32_t)cls[(size_t)range_row[lo] * n_items + it];
+  if (keys) keys[q] = ((uint32_t)lo << 7) | (uint32_t)cls[(size_t)range_row[lo] * n_items + rec.y];
 }
 
 // ratings per (user part of the range, item) over the block ranges of (pre-shuffle) rating positions
@@ -288,6 +298,9 @@ static int sgd_build_records(mfb_engine *e, const std::vector<int64_t> &ranges, 
       n_cand += cv.size();
     }
   }
+  int4 *packed;
+  MFB_CUDA(dev_alloc(&packed, sizeof(int4) * (size_t)n));
+  MFB_LAUNCH(sgd_pack_records_kernel, grid, 256, 0, st, e->mat[MFB_TRAIN].rowptr, e->n_users, pl.rat_user, pl.item, pl.val, n, packed);
   uint8_t *d_cls = nullptr;
   uint32_t *d_keys = nullptr;
   if (n_cand > 0) {
@@ -297,14 +310,14 @@ static int sgd_build_records(mfb_engine *e, const std::vector<int64_t> &ranges, 
     MFB_CUDA(dev_alloc(&d_cls, cls.size()));
     MFB_CUDA(cudaMemcpyAsync(d_cls, cls.data(), cls.size(), cudaMemcpyHostToDevice, st));
     MFB_CUDA(dev_alloc(&d_keys, sizeof(uint32_t) * (size_t)n));
-    MFB_LAUNCH(sgd_shuffle_records_kernel, grid, 256, 0, st, pl.rat_user, pl.item, pl.val, n, d_off, nrng, 0x5EEDULL,
+    MFB_LAUNCH(sgd_shuffle_records_kernel, grid, 256, 0, st, packed, n, d_off, nrng, 0x5EEDULL,
                reinterpret_cast<int4 *>(pl.recs), d_row, e->n_items, d_cls, d_keys);
     MFB_CUDA(cudaStreamSynchronize(st));  // cls (host vector) is copied
   } else {
-    MFB_LAUNCH(sgd_shuffle_records_kernel, grid, 256, 0, st, pl.rat_user, pl.item, pl.val, n, d_off, nrng, 0x5EEDULL,
+    MFB_LAUNCH(sgd_shuffle_records_kernel, grid, 256, 0, st, packed, n, d_off, nrng, 0x5EEDULL,
                reinterpret_cast<int4 *>(pl.recs), nullptr, e->n_items, nullptr, nullptr);
     MFB_CUDA(cudaStreamSynchronize(st));
-    dev_free(d_off); dev_free(d_row);
+    dev_free(d_off); dev_free(d_row); dev_free(packed);
     for (size_t bid = 0; bid < nblk; bid++)
       if (pl.blk_cold_nnz[bid] > 0 && try_hot) pl.blk_cold_share[bid] = (double)cold_max[bid] / (double)pl.blk_cold_nnz[bid];
     return 0;
@@ -312,9 +325,8 @@ static int sgd_build_records(mfb_engine *e, const std::vector<int64_t> &ranges, 
   // ---- stable sort by (range, hot slot): cold records stay in shuffled order at the front of the range ----
   {
     uint32_t *d_keys2;
-    int4 *recs2;
+    int4 *recs2 = packed;  // the packed records have been consumed by the shuffle (same stream): reuse the buffer
     MFB_CUDA(dev_alloc(&d_keys2, sizeof(uint32_t) * (size_t)n));
-    MFB_CUDA(dev_alloc(&recs2, sizeof(int4) * (size_t)n));
     int end_bit = 7;
     while ((1 << (end_bit - 7)) < nrng) end_bit++;
     size_t tmp_bytes = 0;
@@ -425,9 +437,7 @@ int sgd_plan_build(mfb_engine *e, int32_t P, const int32_t *user_part, const int
     pl.nnz = m.nnz;
     pl.blk_nnz[0] = m.nnz;
     pl.runs_built = false;
-    MFB_CUDA(dev_alloc(&pl.rat_user, sizeof(int32_t) * (size_t)(m.nnz > 0 ? m.nnz : 1)));
-    if (m.nnz > 0)
-      MFB_LAUNCH(rat_user_kernel, (unsigned)((m.nnz + 255) / 256), 256, 0, st, m.rowptr, e->n_users, m.nnz, pl.rat_user);
+    // (the user of every rating is resolved by sgd_pack_records_kernel straight from rowptr)
     // user bands of the shuffled kernel: equal user counts, rating offsets read back from rowptr
     int nbands_built = 1;
     {
