@@ -95,6 +95,20 @@ __global__ void sgd_blk_bounds_kernel(const uint64_t *__restrict__ run_key, int3
   bounds[b] = lo;
 }
 
+// item counts with the bins in shared memory (n_bins x 4 bytes must fit; one global atomic per touched bin and CTA
+// instead of one per rating: the most rated items serialise 10^5 global atomics on one address otherwise)
+__global__ void __launch_bounds__(1024) item_hist_smem_kernel(const int32_t *__restrict__ ind, int64_t n, int32_t n_bins,
+                                                              int32_t *__restrict__ hist) {
+  extern __shared__ int32_t bins[];
+  for (int i = threadIdx.x; i < n_bins; i += blockDim.x) bins[i] = 0;
+  __syncthreads();
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x, lo = per * blockIdx.x, hi = min(n, lo + per);
+  for (int64_t j = lo + threadIdx.x; j < hi; j += blockDim.x) atomicAdd(bins + __ldg(ind + j), 1);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_bins; i += blockDim.x)
+    if (bins[i]) atomicAdd(hist + i, bins[i]);
+}
+
 __global__ void item_hist_kernel(const int32_t *__restrict__ ind, int64_t n, int32_t *__restrict__ hist) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n) atomicAdd(hist + ind[j], 1);
@@ -391,7 +405,13 @@ static int sgd_plan_common(mfb_engine *e) {
     MFB_CUDA(dev_alloc(&hist, sizeof(int32_t) * ((size_t)e->n_items + 1)));
     d_max = hist + e->n_items;
     MFB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int32_t) * ((size_t)e->n_items + 1), st));
-    MFB_LAUNCH(item_hist_kernel, (unsigned)((m.nnz + 255) / 256), 256, 0, st, m.rowind, m.nnz, hist);
+    const size_t bin_bytes = sizeof(int32_t) * (size_t)e->n_items;
+    if (bin_bytes <= 200 * 1024) {
+      MFB_CUDA(cudaFuncSetAttribute(item_hist_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_bytes));
+      MFB_LAUNCH(item_hist_smem_kernel, e->sm_count, 1024, bin_bytes, st, m.rowind, m.nnz, e->n_items, hist);
+    } else {
+      MFB_LAUNCH(item_hist_kernel, (unsigned)((m.nnz + 255) / 256), 256, 0, st, m.rowind, m.nnz, hist);
+    }
     size_t tmp_bytes = 0;
     MFB_CUDA(cub::DeviceReduce::Max(nullptr, tmp_bytes, hist, d_max, e->n_items, st));
     MFB_TRY(ensure_scratch(e, tmp_bytes));
