@@ -607,6 +607,18 @@ def main():
     if world > 1:
         roofline["per_rank_nnz"] = nnz_per_rank
 
+    # how the epoch was split between the two kernels (diagnostics ABI; outside the timed region)
+    hot_info = None
+    try:
+        if world == 1:
+            _, cold_n, lists = eng.debug_sgd_records(0, 0)
+            st = eng.debug_sgd_hot_batch()
+            hot_info = {"lists": int(len(lists)), "share_of_ratings": 1.0 - cold_n / max(train_nnz, 1),
+                        "longest_list": int(lists[:, 2].max()) if len(lists) else 0, "ratings_per_round": int(st[2]),
+                        "mean_user_norm_sq": float(st[0] / st[1]) if st[1] > 0 else 0.0}
+    except Exception as ex:
+        hot_info = {"error": repr(ex)[:200]}
+
     # the stratified trainer's kernel (user-major runs, concurrency capped for parity) for the record
     stratified = None
     if world == 1:
@@ -683,6 +695,8 @@ def main():
         line["e2e"] = e2e
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
+    if hot_info:
+        line["sgd_hot_rows"] = hot_info
     if stratified:
         line["stratified"] = stratified
     if world == 1 and not args.no_solvers:

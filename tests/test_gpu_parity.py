@@ -351,6 +351,35 @@ def test_sgd_hot_rows_rmse_parity(algo, rank, warps):
     eng.close()
 
 
+@pytest.mark.parametrize("algo", ["TMF", "TMFDropout"])
+def test_sgd_hot_rows_truncated_models_match_oracle_rmse(algo):
+    """TMF / TMF+Dropout through the shuffled kernel with hot-row lists forced in every stratum block (rank truncation
+    and the Poisson-drawn ranks inside sgd_hot_kernel): final validation / test RMSE against the oracle's stratified
+    trainer on the same partitions — 1 % for TMF, 2 % for TMF+Dropout (its ranks come from a different generator than
+    the reference's per-thread mt19937 streams: distributional parity)."""
+    splits = small_problem(3000, 1500, 300000, seed=21)
+    epochs, P, rank = 40, 4, 16
+    flags = dict(ALGO_FLAGS[algo])
+    om, want = _oracle_curve(splits, algo, "sgdpar", rank, epochs, P, 3, flags)
+    om0 = oracle_model(splits, algo, rank, maxiter=epochs, nthreads=P, seed=3, learnrate=0.005, **flags)
+    eng, variant = make_engine(splits, om0, rank, algo, rho=flags.get("rhorms", 0.0), with_csc=False)
+    up, ip, sched = om0.dsgd_plan(P, epochs * P)
+    eng.set_option("sgd_hot_min_count", 60)
+    eng.set_option("sgd_hot_inflight", 0)
+    eng.sgd_plan(P, up, ip)
+    assert sum(len(eng.debug_sgd_records(a, b)[2]) for a in range(P) for b in range(P)) > 50
+    eng.set_option("sgd_block_order", 1)
+    for ep in range(epochs):
+        for k in range(P):
+            eng.sgd_subepoch(sched[ep * P + k], variant, 0.005, HP["ureg"], HP["ireg"], 3, ep * P + k)
+    tol = 0.02 if algo == "TMFDropout" else 0.01
+    got = eng.rmse(E.VAL, E.CURRENT, variant)
+    assert np.isfinite(got) and abs(got - want[-1]) <= tol * want[-1], (got, want[-1])
+    test_got, test_want = eng.rmse(E.TEST, E.CURRENT, variant), om.rmse(2)
+    assert abs(test_got - test_want) <= tol * test_want, (test_got, test_want)
+    eng.close()
+
+
 def test_sgd_netflix_shaped_rank64_matches_oracle():
     """The bench workload at 1/20 scale (same generator, same skew: 24 k users x 17.7 k items,
     5 M ratings, rank 64): shuffled kernel against the oracle's serial SGD, epoch by epoch."""
