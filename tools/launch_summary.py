@@ -9,8 +9,12 @@ rd = csv.reader(lines)
 hdr = next(rd)
 ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
 agg = OrderedDict()
+# optional second argument "engine": keep only the engine's own launches (its kernels and the CUB sorts / scans of
+# its plan builders; the torch kernels of bench.py's synthetic-data generator are dropped)
+engine_only = len(sys.argv) > 2 and sys.argv[2] == "engine"
 for r in rd:
     if len(r) <= vi: continue
+    if engine_only and re.search(r"^(void )?(at::|native::|at_cuda_detail::|cuda::|c10::|compute_cuda_kernel)", r[ki]): continue
     name = re.sub(r"\(.*", "", r[ki]).replace("void ", "").replace("mfb::", "")
     v = float(r[vi].replace(",", ""))
     u = r[ui]
