@@ -132,7 +132,9 @@ int mfb_sgd_epoch_flat(mfb_engine *e, int variant, float learn_rate, float ureg,
  * "sgd_max_hot_inflight" (bound on concurrent updates of the hottest item row, default 8),
  * "sgd_flat_hot_lr" (shuffled kernel: the hottest row's concurrency is capped at value / learn_rate,
  * default 0.15), "sgd_flat_inflight_frac" (shuffled kernel: ratings in flight <= this fraction of
- * the epoch, default 2e-4), "sgd_flat_launch_lr" (shuffled kernel: ratings in flight <= value / learn_rate x the
+ * the epoch, default 2e-4), "sgd_flat_inflight_steady" (the same bound once the user rows have stopped growing — their
+ * rating-weighted mean squared norm within 0.8 .. 1.25 of its value at the previous launch; whole-matrix plans; default
+ * 1e-3, set it to sgd_flat_inflight_frac to switch the relaxation off), "sgd_flat_launch_lr" (shuffled kernel: ratings in flight <= value / learn_rate x the
  * ratings of the launch, default 1.2e-5: a short launch — one stratum block — must not be in flight all at once),
  * "sgd_flat_band_mb" (shuffled kernel, whole-matrix plans: the epoch visits
  * the ratings in bands of users whose rows take this many MB, so that a band of U stays in L2; default

@@ -665,6 +665,7 @@ extern "C" int mfb_set_option(mfb_engine *e, const char *name, double value) {
   else if (n == "sgd_flat_hot_lr") e->opt_sgd_flat_hot_lr = value;
   else if (n == "sgd_flat_inflight_frac") e->opt_sgd_flat_inflight_frac = value;
   else if (n == "sgd_flat_launch_lr") e->opt_sgd_flat_launch_lr = value;
+  else if (n == "sgd_flat_inflight_steady") e->opt_sgd_flat_inflight_steady = value;
   else if (n == "sgd_flat_band_mb") e->opt_sgd_flat_band_mb = value;
   else if (n == "sgd_flat_user_store") e->opt_sgd_flat_user_store = (int)value;
   else if (n == "sgd_flat_debug") e->opt_sgd_flat_debug = (int)value;

@@ -136,6 +136,7 @@ struct SgdPlan {
   int64_t hot_nnz = 0;                            // records in hot lists
   double *hot_stat = nullptr;                     // device [3]: sum degree x |u|^2, sum degree, last batch used
   int hot_stat_age = 0;                           // launches since the statistic was refreshed
+  double last_norm = 0.0;                         // rating-weighted mean |u|^2 at the previous whole-matrix launch
   bool built = false;
   bool runs_built = true;  // user runs present (P == 1 plans build them lazily)
   void release();
@@ -154,6 +155,7 @@ struct mfb_engine {
   double opt_sgd_max_hot_inflight = 8.0;  // bound on concurrent updates of the hottest item row
   double opt_sgd_flat_hot_lr = 0.15;  // shuffled kernel: cap on (hot-row concurrency x learning rate)
   double opt_sgd_flat_inflight_frac = 2e-4;  // shuffled kernel: ratings in flight <= this fraction of the epoch
+  double opt_sgd_flat_inflight_steady = 1e-3;  // the same bound once the user rows have stopped growing (whole-matrix plans)
   double opt_sgd_flat_launch_lr = 1.2e-5;  // shuffled kernel: ratings in flight <= value / learnrate x ratings of the launch
   double opt_sgd_flat_band_mb = 0.0;  // shuffled kernel: user rows per band (MB of U), 0 = one band (the reference's order)
   int opt_sgd_flat_user_store = 0;    // shuffled kernel: 1 = user rows by plain stores (Hogwild on U), 0 = reductions

@@ -383,9 +383,6 @@ static int sgd_build_records(mfb_engine *e, const std::vector<int64_t> &ranges, 
       if (pl.blk_cold_nnz[bid] > 0) pl.blk_cold_share[bid] = (double)cold_max[bid] / (double)pl.blk_cold_nnz[bid];
     }
     pl.n_hot = (int32_t)lists.size();
-    MFB_CUDA(dev_alloc(&pl.hot_stat, sizeof(double) * 3));
-    MFB_CUDA(cudaMemsetAsync(pl.hot_stat, 0, sizeof(double) * 3, st));
-    pl.hot_stat_age = 0;
     MFB_CUDA(dev_alloc(&pl.hot_lists, sizeof(int4) * lists.size()));
     MFB_CUDA(cudaMemcpyAsync(pl.hot_lists, lists.data(), sizeof(int4) * lists.size(), cudaMemcpyHostToDevice, st));
     MFB_CUDA(cudaStreamSynchronize(st));
@@ -399,6 +396,10 @@ static int sgd_plan_common(mfb_engine *e) {
   cudaStream_t st = e->stream;
   MFB_CUDA(dev_alloc(&pl.work_counter, sizeof(int)));
   MFB_CUDA(cudaMemsetAsync(pl.work_counter, 0, sizeof(int), st));
+  MFB_CUDA(dev_alloc(&pl.hot_stat, sizeof(double) * 3));
+  MFB_CUDA(cudaMemsetAsync(pl.hot_stat, 0, sizeof(double) * 3, st));
+  pl.hot_stat_age = 0;
+  pl.last_norm = 0.0;
   pl.hot_item_share = 0.0;
   if (m.nnz > 0) {
     int32_t *hist, *d_max;
@@ -1527,8 +1528,29 @@ int sgd_flat_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int varian
   // enough for the whole machine to hold 1.7 % of it in flight, and there the run diverges although no single row
   // is near the c x lr bound (many rows are stale at once; tools/dsgd_sweep.py: fine at 0.9 %, NaN at 1.7 %,
   // lr = 0.002).  In flight <= sgd_flat_launch_lr / lr x (ratings of the launch), default 1.2e-5: 0.6 % at lr = 0.002.
+  // Bound (ii) is about the growth phase: once the user rows have stopped growing (rating-weighted mean |u|^2 within
+  // 0.8 .. 1.25 of its value at the previous launch) the budget is sgd_flat_inflight_steady (default 1e-3) —
+  // tools/inflight_phase.py, ML-20M shape: strict for the first epoch only gives the curve of strict throughout
+  // (within the 0.6 % run-to-run spread) at 2.6 instead of 6.5 ms per epoch; relaxed from the start is off by
+  // 1.7 - 4.5 % in epochs 1 - 3.  Whole-matrix plans only: the statistic is read back here (one 16-byte copy).
+  double inflight_frac = e->opt_sgd_flat_inflight_frac;
+  bool stat_fresh = false;
+  if (pl.P == 1 && nb == 1) {
+    const DevCsr &m = e->mat[MFB_TRAIN];
+    MFB_CUDA(cudaMemsetAsync(pl.hot_stat, 0, sizeof(double) * 2, e->stream));
+    MFB_LAUNCH(sgd_hot_stat_kernel, e->sm_count * 8, 256, 0, e->stream, e->U, e->ld, m.rowptr, e->n_users, pl.hot_stat);
+    stat_fresh = true;
+    if (e->opt_sgd_flat_inflight_steady > inflight_frac) {
+      double s[2] = {0.0, 0.0};
+      MFB_CUDA(cudaMemcpyAsync(s, pl.hot_stat, sizeof(double) * 2, cudaMemcpyDeviceToHost, e->stream));
+      MFB_CUDA(cudaStreamSynchronize(e->stream));
+      const double norm = s[1] > 0.0 ? s[0] / s[1] : 0.0;
+      if (pl.last_norm > 0.0 && norm > 0.8 * pl.last_norm && norm < 1.25 * pl.last_norm) inflight_frac = e->opt_sgd_flat_inflight_steady;
+      pl.last_norm = std::isfinite(norm) ? norm : 0.0;
+    }
+  }
   const double inflight_cap =
-      std::max(std::min(e->opt_sgd_flat_inflight_frac * (double)std::max<int64_t>(pl.nnz, n_sched),
+      std::max(std::min(inflight_frac * (double)std::max<int64_t>(pl.nnz, n_sched),
                         e->opt_sgd_flat_launch_lr / std::max((double)lr, 1e-12) * (double)n_sched), 8.0);
   double hot_cap = e->opt_sgd_flat_hot_lr / std::max((double)lr, 1e-12);
   const double lr_cap = hot_cap;
@@ -1590,9 +1612,9 @@ int sgd_flat_launch(mfb_engine *e, const int32_t *blocks, int32_t nb, int varian
     while (T * 2 <= 64 && (double)(T * 2) <= w_max) T *= 2;
     if (e->opt_sgd_hot_batch > 0) T = std::min(e->opt_sgd_hot_batch, 64);
     const bool run_cold = n_all > 0 && !(a.debug & 32);
-    // rating-weighted mean |u|^2 for the device-side batch bound: every launch of a whole-matrix plan, every
+    // rating-weighted mean |u|^2 for the device-side batch bound: every launch of a whole-matrix plan (above), every
     // second launch of a stratum-block plan (a quarter of the rows with local ratings is sampled: ~10 us)
-    if (pl.P == 1 || (pl.hot_stat_age++ & 1) == 0) {
+    if (!stat_fresh && (pl.hot_stat_age++ & 1) == 0) {
       const DevCsr &m = e->mat[MFB_TRAIN];
       MFB_CUDA(cudaMemsetAsync(pl.hot_stat, 0, sizeof(double) * 2, e->stream));
       MFB_LAUNCH(sgd_hot_stat_kernel, e->sm_count * 8, 256, 0, e->stream, e->U, e->ld, m.rowptr, e->n_users, pl.hot_stat);
