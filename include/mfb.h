@@ -157,7 +157,9 @@ int mfb_sgd_block_nnz(mfb_engine *e, const int32_t *blocks, int32_t nb, int64_t 
  * "sgd_hot_inflight", "sgd_hot_max_lists": an item of which the shuffled kernel would keep more than sgd_hot_inflight
  * (default 16) updates in flight when it runs the block on the whole machine, and that holds at least
  * sgd_hot_min_count (default 1024) of the block's ratings, is trained by one CTA that keeps the item row in shared
- * memory — the sgd_hot_max_lists (default and maximum 127) most rated ones when there are more; "sgd_hot_batch" ratings per mini-batch round of such a CTA, 0 = automatic).
+ * memory — the sgd_hot_max_lists (default and maximum 127) most rated ones when there are more; "sgd_hot_batch" ratings per mini-batch round of such a CTA, 0 = automatic; "sgd_hot_stages" 8 (default) or 4 rounds
+ * of user rows staged ahead; "sgd_hot_pace" 1 = a list advances in step with the shuffled kernel (default); "sgd_hot_stab"
+ * see mfb_debug_sgd_hot_batch).
  * lists = [*n_lists][3] int32 {item, first record relative to the block, records}; lists may be NULL or hold
  * sgd_hot_max_lists (<= 127) entries. */
 int mfb_debug_sgd_records(mfb_engine *e, int32_t user_part, int32_t item_part, int32_t *records,
@@ -165,7 +167,7 @@ int mfb_debug_sgd_records(mfb_engine *e, int32_t user_part, int32_t item_part, i
 /* Diagnostics: out = {sum over users of degree x |u|^2, sum of degrees, ratings per round the hot CTAs last used}.
  * The batch of a hot CTA is bounded on the device by sgd_hot_stab / (learn_rate x out[0] / out[1]) (option
  * "sgd_hot_stab", default 0.5: a mini-batch of T ratings of one item is only stable while learn_rate x T x |u|^2 < 1)
- * and on the host by 64 and by sgd_flat_hot_lr / learn_rate; zeros when the plan has no hot lists. */
+ * and on the host by 64 and by sgd_flat_hot_lr / learn_rate; out[2] is zero when the plan has no hot lists. */
 int mfb_debug_sgd_hot_batch(mfb_engine *e, double out[3]);
 
 /* ---- ALS (modelMF.cpp:795-882) -------------------------------------------------------------

@@ -1,23 +1,24 @@
-// Stratified SGD on the device: plan building (ratings bucketed once into the P x P stratum
-// grid) and the update kernel.
+// SGD on the device: plan building (ratings bucketed once into the P x P stratum grid, shuffled rating records, hot
+// item lists) and the three update kernels.
 //
 // Reference statements replaced: the per-rating step of modelMF.cpp:83-105 (serial),
 // :275-303 (stratified), :1747-1763 (Hogwild) and its weighted / truncated / Poisson-truncated
 // forms modelInvPopMF.cpp:356-391, modelDropoutSigmoid.cpp:145-194,
 // modelPoissonDropout.cpp:176-229.
 //
-// Kernel design (HBM/L2-bound gather-update, not GEMM-shaped):
-//   * a sub-warp of G lanes owns one user's run of ratings inside a block (the reference's own
-//     visiting order: user-major, CSR order inside the row, modelMF.cpp:279-281) and keeps the
-//     user vector in registers for the whole run — u is read and written once per run instead
-//     of once per rating;
-//   * per rating the item vector is one coalesced 128-bit-per-lane load and store that
-//     bypasses L1 (ld/st.global.cg) so other SMs' updates are seen at L2;
-//   * (item, rating) pairs are fetched G at a time, one per lane, and broadcast by shuffle;
-//     the next item vector is prefetched while the current one is reduced (shuffle tree);
-//   * the IFWMF weight, the TMF rank and the Poisson-drawn rank are resolved per lane at fetch
-//     time (off the dependent chain) and applied in the same pass;
-//   * runs are sorted longest-first so that the serial chain of a heavy user starts at t = 0.
+// Kernels (HBM/L2-bound gather-update, not GEMM-shaped):
+//   * sgd_flat_kernel — serial / Hogwild trainers and the shuffled-inside-blocks order of the multi-GPU path: a warp
+//     takes 32 consecutive records of the physically shuffled record array with one coalesced load, a sub-warp of G
+//     lanes owns one rating, both factor rows are read with 128-bit ld.global.cg and updated with
+//     red.global.add.v4.f32; the groups are visited in a freshly keyed pseudo-random order per epoch, pulled from a
+//     chunk queue;
+//   * sgd_hot_kernel — the most rated item rows of a block: one CTA per item keeps the row in shared memory and trains
+//     its rating list in paced mini-batch rounds over cp.async-staged user rows;
+//   * sgd_run_kernel — the stratified trainers in the reference's own visiting order (user-major, CSR order in the
+//     row, modelMF.cpp:279-281): a persistent sub-warp pulls user runs (longest first) from a work queue and keeps u
+//     in registers for the whole run; (item, rating) pairs are fetched G at a time and broadcast by shuffle, the next
+//     item row is prefetched during the current reduction.
+// The IFWMF weight, the TMF rank and the Poisson-drawn rank are resolved per rating in the same pass in all three.
 #include "engine.h"
 
 #include <cub/cub.cuh>
@@ -644,7 +645,6 @@ struct SgdArgs {
   int rank;
   const int32_t *item;
   const float *val;
-  const int32_t *rat_user;  // flat kernel only
   const int32_t *seg_user, *seg_start, *seg_len;
   int nb, max_cnt, total;  // total = nb * max_cnt segment slots
   int rotate;              // start every run at a pseudo-random offset
@@ -1405,7 +1405,7 @@ static void fill_common(mfb_engine *e, SgdArgs &a, float lr, float ureg, float i
   a.U = e->U; a.V = e->V;
   a.nq = e->ld / 4;
   a.rank = e->rank;
-  a.item = pl.item; a.val = pl.val; a.rat_user = pl.rat_user;
+  a.item = pl.item; a.val = pl.val;
   a.seg_user = pl.seg_user; a.seg_start = pl.seg_start; a.seg_len = pl.seg_len;
   a.lr = lr; a.ureg = ureg; a.ireg = ireg;
   a.aux_u = e->aux_u; a.aux_i = e->aux_i; a.cdf = e->poisson_cdf;
