@@ -1,7 +1,6 @@
 // Params and Data: the hyper-parameter bag and the three rating matrices, with the field names
 // and constructor signatures of the reference (datastruct.h:12-69 Params, :72-136 Data).
-#ifndef _DATASTRUCT_H_
-#define _DATASTRUCT_H_
+#pragma once
 
 #include <iostream>
 #include <numeric>
@@ -13,26 +12,13 @@
 
 class Params {
  public:
-  int nUsers;
-  int nItems;
-  int facDim;
-  int maxIter;
-  int svdFacDim;
-  int seed;
-  float uReg;
-  float iReg;
-  float learnRate;
-  float rhoRMS;
-  float alpha;
-  const char *trainMatFile;
-  const char *testMatFile;
-  const char *valMatFile;
-  const char *graphMatFile;
-  const char *origUFacFile;
-  const char *origIFacFile;
-  const char *initUFacFile;
-  const char *initIFacFile;
-  const char *prefix;
+  // problem and model size, iteration budget, seeds
+  int nUsers, nItems, facDim, maxIter, svdFacDim, seed;
+  // regularisation, step size, and the two knobs of the frequency-aware models (IFWMF / TMF)
+  float uReg, iReg, learnRate, rhoRMS, alpha;
+  // inputs and output prefix (borrowed C strings, see the constructor)
+  const char *trainMatFile, *testMatFile, *valMatFile, *graphMatFile;
+  const char *origUFacFile, *origIFacFile, *initUFacFile, *initIFacFile, *prefix;
 
   // The strings are borrowed (datastruct.h:43-50): they must outlive the Params object.
   Params(int facDim, int maxIter, int svdFacDim, int seed, float uReg, float iReg, float learnRate, float rhoRMS,
@@ -46,16 +32,9 @@ class Params {
 class Data {
  public:
   const char *prefix;
-  gk_csr_t *trainMat;
-  gk_csr_t *testMat;
-  gk_csr_t *valMat;
-  gk_csr_t *graphMat;
-  std::vector<std::vector<double>> origUFac;
-  std::vector<std::vector<double>> origIFac;
-  int facDim;
-  int trainNNZ;
-  int nUsers;
-  int nItems;
+  gk_csr_t *trainMat, *testMat, *valMat, *graphMat;        // owned; freed by the destructor
+  std::vector<std::vector<double>> origUFac, origIFac;      // ground-truth factors of synthetic inputs, if given
+  int facDim, trainNNZ, nUsers, nItems;
 
   Data(gk_csr_t *p_trainMat, gk_csr_t *p_testMat);
   // Reads the three text-CSR files and builds their column indices (datastruct.cpp:3-120).
@@ -70,4 +49,3 @@ class Data {
   void finish();
 };
 
-#endif
