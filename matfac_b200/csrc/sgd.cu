@@ -1122,7 +1122,6 @@ __global__ void __launch_bounds__(512) sgd_hot_kernel(const SgdArgs a, const int
   // loop-invariant addresses: this thread's words of its tile row / of v, its column-sum slice
   const float4 *vq = vs + q;
   const int sum_f = tid % nq, sum_pg = tid / nq;
-  const bool sum_on = tid < np * nq;
   const bool fast = FULL && (Q * T) % 32 == 0 && np * E == T;  // every thread sums E rows of one column
   bool pacing = a.pace != 0;
   const uint32_t row_off = (uint32_t)jl * rowq + q;   // + stage * T * rowq
@@ -1294,23 +1293,26 @@ __global__ void __launch_bounds__(512) sgd_hot_kernel(const SgdArgs a, const int
       }
       continue;
     }
-    if (sum_on) {  // generic ranks: np row groups x nq words
+    // generic ranks / tiny batches: np row groups x nq words, strided over the CTA (it may have fewer threads than
+    // the row has words: rank 256 with one rating per round is 8 threads wide)
+    for (int idx = tid; idx < np * nq; idx += blockDim.x) {
+      const int f = idx % nq, pg = idx / nq;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 *col = tile + st * stage_quads + sum_f;
-      for (int jj = sum_pg; jj < T; jj += np) {
+      const float4 *col = tile + st * stage_quads + f;
+      for (int jj = pg; jj < T; jj += np) {
         const float4 d = col[jj * rowq];
         acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
       }
-      part[sum_pg * nq + sum_f] = acc;
+      part[pg * nq + f] = acc;
     }
     __syncthreads();
-    if (tid < nq) {
-      float4 acc0 = vs[tid];
+    for (int f = tid; f < nq; f += blockDim.x) {
+      float4 acc0 = vs[f];
       for (int pg = 0; pg < np; pg++) {
-        const float4 d0 = part[pg * nq + tid];
+        const float4 d0 = part[pg * nq + f];
         acc0.x += d0.x; acc0.y += d0.y; acc0.z += d0.z; acc0.w += d0.w;
       }
-      vs[tid] = acc0;
+      vs[f] = acc0;
     }
   }
   __syncthreads();

@@ -260,7 +260,7 @@ def test_sgd_hot_lists_partition_the_block_records(P):
     eng.close()
 
 
-@pytest.mark.parametrize("algo,rank,P", [("mf", 64, 1), ("mf", 10, 2), ("IFWMF", 16, 1), ("TMF", 64, 2), ("mf", 128, 1)])
+@pytest.mark.parametrize("algo,rank,P", [("mf", 64, 1), ("mf", 10, 2), ("IFWMF", 16, 1), ("TMF", 64, 2), ("mf", 128, 1), ("mf", 256, 1), ("TMF", 200, 1)])
 def test_sgd_hot_rows_visit_every_rating_once(algo, rank, P):
     """Linear regime: with a tiny learning rate one epoch moves the factors by lr x the summed per-rating
     gradients at the starting point, whatever the order and the concurrency.  The epoch of the shuffled kernel
