@@ -260,7 +260,8 @@ def test_sgd_hot_lists_partition_the_block_records(P):
     eng.close()
 
 
-@pytest.mark.parametrize("algo,rank,P", [("mf", 64, 1), ("mf", 10, 2), ("IFWMF", 16, 1), ("TMF", 64, 2), ("mf", 128, 1), ("mf", 256, 1), ("TMF", 200, 1)])
+@pytest.mark.parametrize("algo,rank,P", [("mf", 64, 1), ("mf", 10, 2), ("IFWMF", 16, 1), ("TMF", 64, 2), ("mf", 128, 1), ("mf", 256, 1), ("TMF", 200, 1),
+                                          ("mf", 32, 1), ("IFWMF", 24, 2), ("mf", 100, 1), ("TMF", 40, 1)])
 def test_sgd_hot_rows_visit_every_rating_once(algo, rank, P):
     """Linear regime: with a tiny learning rate one epoch moves the factors by lr x the summed per-rating
     gradients at the starting point, whatever the order and the concurrency.  The epoch of the shuffled kernel
@@ -301,6 +302,12 @@ def test_sgd_hot_rows_visit_every_rating_once(algo, rank, P):
     assert n_hot > 0 and n_cold == 0
     # the all-cold epoch (vector reductions only, tested against the oracle elsewhere) is the yardstick
     assert rel_err(dU_hot, dU_cold) < 2e-2 and rel_err(dV_hot, dV_cold) < 2e-2
+    # the in-flight budget of this small matrix leaves one rating per round; 32 per round takes the wide code paths
+    # of sgd_hot_kernel (shuffle / shared-memory column sums) — harmless in the linear regime
+    eng.set_option("sgd_hot_batch", 32)
+    dU_wide, dV_wide, _ = run(1)
+    eng.set_option("sgd_hot_batch", 0)
+    assert rel_err(dU_wide, dU_cold) < 2e-2 and rel_err(dV_wide, dV_cold) < 2e-2
     if algo == "mf":
         U64, V64 = U0.astype(np.float64), V0.astype(np.float64)
         e = tr.rowval - np.einsum("ij,ij->i", U64[users], V64[items])
