@@ -122,6 +122,8 @@ gk_csr_t *gk_csr_Read(char *filename, int format, int readvals, int numbering) {
     gk_csr_t *cached = sidecar_read(filename, readvals, numbering);
     if (cached) return cached;
   }
+  const bool timing = getenv("MATFAC_TIMING") != NULL;
+  const double t_begin = omp_get_wtime();
   FILE *fp = fopen(filename, "rb");
   if (!fp) {
     fprintf(stderr, "gk_csr_Read: cannot open %s\n", filename);
@@ -139,6 +141,7 @@ gk_csr_t *gk_csr_Read(char *filename, int format, int readvals, int numbering) {
   if (sz > 0 && buf[sz - 1] != '\n') buf[sz++] = '\n';
   buf[sz] = '\0';
 
+  const double t_read = omp_get_wtime();
   int nt = omp_get_max_threads();
   if (sz < (size_t)1 << 20) nt = 1;
   std::vector<size_t> cut(nt + 1, sz);
@@ -151,7 +154,11 @@ gk_csr_t *gk_csr_Read(char *filename, int format, int readvals, int numbering) {
   std::vector<Piece> pieces(nt);
 #pragma omp parallel for num_threads(nt) schedule(static, 1)
   for (int t = 0; t < nt; t++) {
-    Piece &pc = pieces[t];
+    // a thread-local piece, moved into place at the end: the vectors' end pointers are written on every push_back
+    // and neighbouring Piece objects share cache lines (measured: 8 threads 1.43 s against 1.77 s on one)
+    Piece pc;
+    pc.ind.reserve((size_t)(cut[t + 1] - cut[t]) / 6 + 16);
+    if (readvals) pc.val.reserve((size_t)(cut[t + 1] - cut[t]) / 6 + 16);
     char *p = buf + cut[t], *end = buf + cut[t + 1];
     while (p < end) {
       char *eol = (char *)memchr(p, '\n', end - p);
@@ -181,8 +188,10 @@ gk_csr_t *gk_csr_Read(char *filename, int format, int readvals, int numbering) {
       }
       p = eol + 1;
     }
+    pieces[t] = std::move(pc);
   }
   free(buf);
+  const double t_parse = omp_get_wtime();
   size_t nrows = 0, nnz = 0;
   int32_t maxcol = -1;
   for (auto &pc : pieces) {
@@ -208,6 +217,9 @@ gk_csr_t *gk_csr_Read(char *filename, int format, int readvals, int numbering) {
     }
     k += pc.ind.size();
   }
+  if (timing)
+    fprintf(stderr, "gk_csr_Read %s: file read %.3f s, parse (%d threads) %.3f s, merge %.3f s\n", filename, t_read - t_begin,
+            nt, t_parse - t_read, omp_get_wtime() - t_parse);
   if (cache == 2) sidecar_write(filename, m, readvals, numbering);
   return m;
 }
@@ -223,15 +235,41 @@ void gk_csr_CreateIndex(gk_csr_t *mat, int what) {
   mat->colptr = (ssize_t *)calloc((size_t)nc + 1, sizeof(ssize_t));
   mat->colind = (int32_t *)malloc(sizeof(int32_t) * (nnz ? nnz : 1));
   mat->colval = mat->rowval ? (float *)malloc(sizeof(float) * (nnz ? nnz : 1)) : NULL;
-  for (ssize_t j = 0; j < nnz; j++) mat->colptr[mat->rowind[j] + 1]++;
-  for (int32_t c = 0; c < nc; c++) mat->colptr[c + 1] += mat->colptr[c];
-  std::vector<ssize_t> cursor(mat->colptr, mat->colptr + nc);
-  for (int32_t r = 0; r < nr; r++)
-    for (ssize_t j = mat->rowptr[r]; j < mat->rowptr[r + 1]; j++) {
-      const ssize_t d = cursor[mat->rowind[j]]++;
-      mat->colind[d] = r;
-      if (mat->colval) mat->colval[d] = mat->rowval[j];
+  // Stable counting sort by column (a column lists its rows in ascending order, as trainCCD's binSearch and the
+  // device-built index expect), over OpenMP threads: thread t owns a contiguous range of rows balanced by ratings,
+  // counts its columns, and scatters behind the entries of the threads before it — the result is the serial one bit
+  // for bit.  Small matrices and wide ones (the per-thread counters would outweigh the ratings) stay serial.
+  int nt = omp_get_max_threads();
+  if (nnz < (ssize_t)1 << 20 || (ssize_t)nc * nt > nnz) nt = 1;
+  std::vector<int32_t> row_cut((size_t)nt + 1, nr);
+  row_cut[0] = 0;
+  for (int t = 1; t < nt; t++)
+    row_cut[t] = (int32_t)(std::upper_bound(mat->rowptr, mat->rowptr + nr + 1, nnz / nt * t) - mat->rowptr - 1);
+  std::vector<std::vector<ssize_t>> count((size_t)nt, std::vector<ssize_t>((size_t)nc, 0));
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+  for (int t = 0; t < nt; t++) {
+    std::vector<ssize_t> &cnt = count[t];
+    for (ssize_t j = mat->rowptr[row_cut[t]]; j < mat->rowptr[row_cut[t + 1]]; j++) cnt[mat->rowind[j]]++;
+  }
+  for (int32_t c = 0; c < nc; c++) {  // colptr, and count[t][c] := first slot of thread t in column c
+    ssize_t run = mat->colptr[c];
+    for (int t = 0; t < nt; t++) {
+      const ssize_t k = count[t][c];
+      count[t][c] = run;
+      run += k;
     }
+    mat->colptr[c + 1] = run;
+  }
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+  for (int t = 0; t < nt; t++) {
+    std::vector<ssize_t> &cursor = count[t];
+    for (int32_t r = row_cut[t]; r < row_cut[t + 1]; r++)
+      for (ssize_t j = mat->rowptr[r]; j < mat->rowptr[r + 1]; j++) {
+        const ssize_t d = cursor[mat->rowind[j]]++;
+        mat->colind[d] = r;
+        if (mat->colval) mat->colval[d] = mat->rowval[j];
+      }
+  }
 }
 
 template <typename T>

@@ -95,6 +95,35 @@ def test_text_reader_handles_empty_rows_and_parallel_split(tmp_path):
         assert np.array_equal(ptr, d["rowptr"]) and np.array_equal(ind, d["rowind"]) and np.array_equal(val, d["rowval"])
 
 
+def test_parallel_parse_and_column_index_are_bit_exact(tmp_path):
+    """A matrix large enough (> 2^20 ratings) for the OpenMP paths of the text parser AND of gk_csr_CreateIndex:
+    5 threads must give the arrays of 1 thread and of a stable numpy sort by column, bit for bit."""
+    rng = np.random.default_rng(3)
+    n_users, n_items = 24000, 500
+    path = str(tmp_path / "wide.csr")
+    rows, cols, vals = [], [], []
+    with open(path, "w") as f:
+        for u in range(n_users):
+            k = 0 if u % 13 == 4 else int(rng.integers(20, 100))
+            items = np.sort(rng.choice(n_items, size=k, replace=False))
+            v = rng.integers(1, 11, size=k) / 2
+            f.write(" ".join(f"{i} {x:g}" for i, x in zip(items, v)) + "\n")
+            rows.append(np.full(k, u, np.int32)); cols.append(items.astype(np.int32)); vals.append(v.astype(np.float32))
+    rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
+    assert rows.size > (1 << 20)
+    order = np.argsort(cols, kind="stable")
+    want_colptr = np.zeros(n_items + 1, np.int64)
+    np.cumsum(np.bincount(cols, minlength=n_items), out=want_colptr[1:])
+    files = [path, path, path]
+    for threads in (1, 5):
+        out = str(tmp_path / f"t{threads}")
+        run_mf(files, out, threads=threads, facdim=2, dry_run=1)
+        d = ol.read_csr_dump(os.path.join(out, "train.csr.bin"))
+        assert np.array_equal(d["rowind"], cols) and np.array_equal(d["rowval"], vals)
+        assert np.array_equal(d["colptr"], want_colptr)
+        assert np.array_equal(d["colind"], rows[order]) and np.array_equal(d["colval"], vals[order])
+
+
 def test_binary_sidecar_matches_the_text_parse_and_tracks_the_text_file(tmp_path):
     """MATFAC_CSR_CACHE (SURVEY 8f fast ingest): the `.bin` sidecar written after the first parse must give the
     same CSR / CSC arrays bit for bit, and must be ignored once the text file changes (size or mtime)."""
