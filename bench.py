@@ -611,7 +611,7 @@ def main():
     hot_info = None
     try:
         if world == 1:
-            _, cold_n, lists = eng.debug_sgd_records(0, 0)
+            _, cold_n, lists = eng.debug_sgd_records(0, 0, with_records=False)
             st = eng.debug_sgd_hot_batch()
             hot_info = {"lists": int(len(lists)), "share_of_ratings": 1.0 - cold_n / max(train_nnz, 1),
                         "longest_list": int(lists[:, 2].max()) if len(lists) else 0, "ratings_per_round": int(st[2]),

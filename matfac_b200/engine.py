@@ -211,14 +211,16 @@ class Engine:
         self._check(self.L.mfb_sgd_block_nnz(self.h, _p(b), b.shape[0], C.byref(out)))
         return out.value
 
-    def debug_sgd_records(self, user_part=0, item_part=0):
-        """(records [n][4] int32, cold record count, lists [h][3] int32) of one stratum block (diagnostics)."""
+    def debug_sgd_records(self, user_part=0, item_part=0, with_records=True):
+        """(records [n][4] int32, cold record count, lists [h][3] int32) of one stratum block (diagnostics);
+        with_records=False skips the download of the records (16 bytes per rating)."""
         n = self.sgd_block_nnz([[user_part, item_part]])
-        recs = np.zeros((max(n, 1), 4), np.int32)
+        recs = np.zeros((max(n, 1), 4), np.int32) if with_records else None
         lists = np.zeros((127, 3), np.int32)
         cold, h = C.c_int64(), C.c_int32()
-        self._check(self.L.mfb_debug_sgd_records(self.h, user_part, item_part, _p(recs), C.byref(cold), _p(lists), C.byref(h)))
-        return recs[:n], cold.value, lists[:h.value].copy()
+        self._check(self.L.mfb_debug_sgd_records(self.h, user_part, item_part, _p(recs) if with_records else None,
+                                                 C.byref(cold), _p(lists), C.byref(h)))
+        return (recs[:n] if with_records else None), cold.value, lists[:h.value].copy()
 
     def debug_sgd_hot_batch(self):
         """[sum degree x |u|^2, sum degree, ratings per round the hot CTAs last used] (diagnostics)."""

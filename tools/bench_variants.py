@@ -56,7 +56,7 @@ for name, variant in (("MF", E.MF), ("IFWMF", E.IFWMF), ("TMF", E.TMF), ("TMFDro
         eng.set_aux(variant, ufreq, ifreq, ur, ir, ur, ir, poisson_cdf_table(R) if variant == E.TMFDROPOUT else None)
     eng.upload_factors(U0, V0)
     eng.sgd_plan(1)
-    _, cold, lists = eng.debug_sgd_records(0, 0)
+    _, cold, lists = eng.debug_sgd_records(0, 0, with_records=False)
     ms, curve = [], []
     for ep in range(8):
         eng.event_record(0)

@@ -31,7 +31,7 @@ for hot, frac in ((0, 2e-4), (0, 8e-4), (0, 3.2e-3), (1, 2e-4), (1, 8e-4), (1, 3
     eng.set_option("sgd_flat_inflight_frac", frac / 8)
     eng.sgd_plan(P, user_part, item_part)
     eng.set_option("sgd_block_order", 1)
-    nl = len(eng.debug_sgd_records(0, 0)[2])
+    nl = len(eng.debug_sgd_records(0, 0, with_records=False)[2])
     eng.upload_factors(U0, V0)
     curve, par_ms = [], []
     for ep in range(epochs):

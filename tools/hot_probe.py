@@ -36,7 +36,7 @@ if "1" in which:
         eng.sync(); t0 = time.perf_counter()
         eng.sgd_plan(1)
         eng.sync(); plan_ms = (time.perf_counter() - t0) * 1e3
-        _, cold, lists = eng.debug_sgd_records(0, 0) if hot else (None, train_nnz, [])
+        _, cold, lists = eng.debug_sgd_records(0, 0, with_records=False) if hot else (None, train_nnz, [])
         eng.upload_factors(U0, V0)
         ms, curve = [], []
         for ep in range(epochs):
@@ -72,7 +72,7 @@ if "2" in which:
         eng.sgd_plan(P, user_part, item_part)
         eng.sync(); plan_ms = (time.perf_counter() - t0) * 1e3
         eng.set_option("sgd_block_order", 1)
-        nl = sum(len(eng.debug_sgd_records(a, b)[2]) for a in range(2) for b in range(P)) if hot else 0
+        nl = sum(len(eng.debug_sgd_records(a, b, with_records=False)[2]) for a in range(2) for b in range(P)) if hot else 0
         eng.upload_factors(U0, V0)
         curve, par_ms, tot_ms = [], [], []
         for ep in range(epochs):

@@ -28,7 +28,7 @@ for hot, lists, batch, stages, pace, frac in ((0, 64, 0, 8, 1, 2e-4), (1, 64, 0,
         eng.set_option(k, v)
     eng.upload_factors(U0, V0)
     eng.sgd_plan(1)
-    _, cold, ls = eng.debug_sgd_records(0, 0)
+    _, cold, ls = eng.debug_sgd_records(0, 0, with_records=False)
     got = []
     for ep in range(epochs):
         eng.sgd_epoch_flat(variant, LR, 0.05, 0.05, 1, ep)
