@@ -95,6 +95,29 @@ def test_text_reader_handles_empty_rows_and_parallel_split(tmp_path):
         assert np.array_equal(ptr, d["rowptr"]) and np.array_equal(ind, d["rowind"]) and np.array_equal(val, d["rowval"])
 
 
+@pytest.mark.parametrize("seed", [3, 2147483647])
+def test_parallel_factor_init_is_bit_exact(tmp_path, seed):
+    """Factor matrices large enough (>= 2^16 values) for the OpenMP jump-ahead initialisation: 5 threads must give the
+    oracle's serial std::default_random_engine stream bit for bit (seed 2^31 - 1 is the engine's zero-state corner)."""
+    rng = np.random.default_rng(5)
+    n_users, n_items = 2500, 1300
+    path = str(tmp_path / "m.csr")
+    with open(path, "w") as f:
+        for u in range(n_users):
+            items = np.sort(rng.choice(n_items, size=int(rng.integers(1, 6)), replace=False))
+            f.write(" ".join(f"{i} {rng.integers(1, 11) / 2:g}" for i in items) + "\n")
+    files = [path, path, path]
+    od = ol.OracleData(files=files)
+    m = ol.OracleModel(od, algo="mf", facdim=64, seed=seed, nthreads=1)
+    U, V = m.factors()
+    assert U.size >= (1 << 16) and V.size >= (1 << 16)
+    for threads in (1, 5):
+        dump = str(tmp_path / f"dry{threads}")
+        run_mf(files, dump, threads=threads, facdim=64, seed=seed, dry_run=1)
+        assert np.array_equal(U, ol.read_mat(os.path.join(dump, "init_uFac.bin")))
+        assert np.array_equal(V, ol.read_mat(os.path.join(dump, "init_iFac.bin")))
+
+
 def test_parallel_parse_and_column_index_are_bit_exact(tmp_path):
     """A matrix large enough (> 2^20 ratings) for the OpenMP paths of the text parser AND of gk_csr_CreateIndex:
     5 threads must give the arrays of 1 thread and of a stable numpy sort by column, bit for bit."""
