@@ -128,7 +128,9 @@ int mfb_sgd_subepoch(mfb_engine *e, const int32_t *blocks, int32_t nb, int varia
  * loads and updated with vector reductions.  Needs mfb_sgd_plan(e, 1, NULL, NULL). */
 int mfb_sgd_epoch_flat(mfb_engine *e, int variant, float learn_rate, float ureg, float ireg, uint64_t seed,
                        uint64_t counter);
-/* Tuning knobs: "sgd_workers" (concurrent sub-warps, 0 = automatic), "sgd_warps_per_sm",
+/* Tuning knobs: "sgd_shuffle_seed" (key of the plan-time physical shuffle of the rating records; the host trainers
+ * pass Model::trainSeed before mfb_sgd_plan, as the reference seeds its shuffles with mt19937(trainSeed),
+ * modelMF.cpp:63,78), "sgd_workers" (concurrent sub-warps, 0 = automatic), "sgd_warps_per_sm",
  * "sgd_max_hot_inflight" (bound on concurrent updates of the hottest item row, default 8),
  * "sgd_flat_hot_lr" (shuffled kernel: the hottest row's concurrency is capped at value / learn_rate,
  * default 0.15), "sgd_flat_inflight_frac" (shuffled kernel: ratings in flight <= this fraction of
@@ -213,7 +215,7 @@ int mfb_restore_best(mfb_engine *e);
 int mfb_event_record(mfb_engine *e, int32_t slot /* 0..15 */);
 int mfb_event_elapsed_ms(mfb_engine *e, int32_t slot_a, int32_t slot_b, float *ms);
 
-/* ---- multi-GPU plumbing (one engine per rank; the exchange itself is NCCL on the host side)
+/* ---- multi-GPU plumbing (one engine per GPU; the exchange itself is peer memory, see below)
  * Device pointer and leading dimension (floats) of a factor matrix, and the engine's stream
  * (a cudaStream_t) so a communicator can order its work after the engine's kernels. */
 int mfb_device_factors(mfb_engine *e, int side, void **dev_ptr, int64_t *ld);

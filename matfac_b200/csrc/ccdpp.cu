@@ -256,6 +256,9 @@ int ccdpp_rank1_impl(mfb_engine *e, int32_t k, int first_iter, int32_t inner, fl
   }
   if (uhi > ulo) MFB_LAUNCH(col_insert_kernel, (uhi - ulo + 255) / 256, 256, 0, st, e->U, e->ld, k, ulo, uhi, e->uk);
   if (ihi > ilo) MFB_LAUNCH(col_insert_kernel, (ihi - ilo + 255) / 256, 256, 0, st, e->V, e->ld, k, ilo, ihi, e->vk);
+  // the subtract passes above gather ALL of u_k / v_k; the next rank-one step starts by storing its column into every
+  // peer's u_k / v_k — no rank may get there while a peer is still reading (write-after-read across ranks)
+  MFB_TRY(comm_barrier_launch(e));
   return 0;
 }
 

@@ -137,6 +137,15 @@ static int push_rows(mfb_engine *e, int side, const int32_t *dev_ids, int first,
   return 0;
 }
 
+int comm_check_error(mfb_engine *e) {
+  if (!e->comm.connected || !e->comm.own_flags) return 0;
+  unsigned long long v = 0;
+  MFB_CUDA(cudaMemcpyAsync(&v, e->comm.own_flags + kErrorWord, sizeof(v), cudaMemcpyDeviceToHost, e->stream));
+  MFB_CUDA(cudaStreamSynchronize(e->stream));
+  MFB_REQUIRE(v == 0, "a device-side wait on a peer timed out: rows of a peer never arrived, the factors are incomplete");
+  return 0;
+}
+
 int comm_allgather_range(mfb_engine *e, int side, int first, int n) {
   MFB_TRY(push_rows(e, side, nullptr, first, n, (1 << kMaxRanks) - 1, -1, 0));
   return comm_barrier_launch(e);
@@ -149,7 +158,7 @@ using namespace mfb;
 extern "C" int mfb_comm_init(mfb_engine *e, int32_t rank, int32_t world, uint8_t *handles_out, int64_t *handles_bytes) {
   MFB_REQUIRE(e && handles_out && handles_bytes, "mfb_comm_init: null argument");
   MFB_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, "mfb_comm_init: bad rank / world (<= 8)");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   Comm &c = e->comm;
   c.rank = rank;
   c.world = world;
@@ -175,7 +184,7 @@ extern "C" int mfb_comm_connect(mfb_engine *e, const uint8_t *all_handles, int64
   Comm &c = e->comm;
   MFB_REQUIRE(c.own_flags, "mfb_comm_connect: call mfb_comm_init first");
   MFB_REQUIRE(bytes == (int64_t)sizeof(CommHandles) * c.world, "mfb_comm_connect: expected world x 320 bytes");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   for (int r = 0; r < c.world; r++) {
     if (r == c.rank) {
       c.U[r] = e->U; c.V[r] = e->V; c.uk[r] = e->uk; c.vk[r] = e->vk; c.flags[r] = c.own_flags;
@@ -195,13 +204,13 @@ extern "C" int mfb_comm_connect(mfb_engine *e, const uint8_t *all_handles, int64
 
 extern "C" int mfb_comm_barrier(mfb_engine *e) {
   MFB_REQUIRE(e && e->comm.connected, "mfb_comm_barrier: not connected");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   return comm_barrier_launch(e);
 }
 
 extern "C" int mfb_comm_error(mfb_engine *e, int32_t *timed_out) {
   MFB_REQUIRE(e && timed_out && e->comm.own_flags, "mfb_comm_error: bad argument");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   unsigned long long v = 0;
   MFB_CUDA(cudaMemcpyAsync(&v, e->comm.own_flags + kErrorWord, sizeof(v), cudaMemcpyDeviceToHost, e->stream));
   MFB_CUDA(cudaStreamSynchronize(e->stream));
@@ -214,7 +223,7 @@ extern "C" int mfb_dsgd_push_block(mfb_engine *e, int32_t item_part, int32_t dst
   const SgdPlan &pl = e->sgd;
   MFB_REQUIRE(pl.built && pl.part_items && item_part >= 0 && item_part < pl.P, "mfb_dsgd_push_block: no stratified plan / bad part");
   MFB_REQUIRE(dst_rank >= -1 && dst_rank < e->comm.world, "mfb_dsgd_push_block: bad destination");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   const int first = pl.part_item_off[item_part], n = pl.part_item_off[item_part + 1] - first;
   if (dst_rank < 0)  // to every peer, no flag (followed by a barrier)
     return push_rows(e, MFB_ITEM, pl.part_items + first, 0, n, (1 << kMaxRanks) - 1, -1, 0);
@@ -226,14 +235,14 @@ extern "C" int mfb_comm_wait_block(mfb_engine *e, int32_t src_rank, uint64_t seq
   MFB_REQUIRE(e && e->comm.connected, "mfb_comm_wait_block: not connected");
   MFB_REQUIRE(src_rank >= 0 && src_rank < e->comm.world, "mfb_comm_wait_block: bad source");
   if (src_rank == e->comm.rank) return 0;
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   MFB_LAUNCH(comm_wait_kernel, 1, 32, 0, e->stream, e->comm.own_flags, kBlockSlot + src_rank, (unsigned long long)seq);
   return 0;
 }
 
 extern "C" int mfb_comm_allgather_rows(mfb_engine *e, int side, const int32_t *ids, int32_t first, int32_t n) {
   MFB_REQUIRE(e && e->comm.connected && (side == MFB_USER || side == MFB_ITEM) && n >= 0, "mfb_comm_allgather_rows: bad argument");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   const int32_t *dev_ids = nullptr;
   if (ids && n > 0) {
     MFB_TRY(ensure_scratch(e, sizeof(int32_t) * (size_t)n));

@@ -40,15 +40,31 @@ int fail_cuda(cudaError_t err, const char *expr, const char *file, int line) {
 
 // ---- cached device allocations -------------------------------------------------------------
 namespace {
+struct IdleBlock {
+  void *ptr;
+  cudaStream_t stream;  // stream the freeing engine was working on (nullptr: unknown)
+  cudaEvent_t freed;    // recorded on that stream at free time (nullptr: none)
+};
 struct DevCache {
   std::mutex mu;
   std::unordered_map<void *, std::pair<int, size_t>> live;             // block -> (device, size)
-  std::multimap<std::pair<int, size_t>, void *> idle;                  // (device, size) -> block
+  std::multimap<std::pair<int, size_t>, IdleBlock> idle;               // (device, size) -> block
   size_t idle_bytes = 0;
 };
-DevCache &dev_cache() { static DevCache c; return c; }
+// leaked on purpose: engines destroyed from static destructors (DeviceSession's registry) and exit() handlers
+// still find the cache alive
+DevCache &dev_cache() { static DevCache *c = new DevCache(); return *c; }
 constexpr size_t kDevCacheMaxIdle = (size_t)16 << 30;
+// the stream of the engine whose C-ABI call is running on this thread (enter()); a cached block is handed to another
+// stream only after the work queued on the freeing stream at free time has finished
+thread_local cudaStream_t g_current_stream = nullptr;
 }  // namespace
+
+cudaError_t enter(mfb_engine *e) {
+  g_current_stream = e->stream;
+  return cudaSetDevice(e->device);
+}
+void leave() { g_current_stream = nullptr; }
 
 cudaError_t dev_alloc_bytes(void **p, size_t bytes) {
   if (bytes == 0) bytes = 1;
@@ -56,16 +72,29 @@ cudaError_t dev_alloc_bytes(void **p, size_t bytes) {
   cudaError_t err = cudaGetDevice(&dev);
   if (err != cudaSuccess) return err;
   DevCache &c = dev_cache();
+  IdleBlock got{nullptr, nullptr, nullptr};
   {
     std::lock_guard<std::mutex> lock(c.mu);
     auto it = c.idle.lower_bound({dev, bytes});
     if (it != c.idle.end() && it->first.first == dev && it->first.second <= bytes + bytes / 4 + 4096) {
-      *p = it->second;
-      c.live[*p] = it->first;
+      got = it->second;
+      c.live[got.ptr] = it->first;
       c.idle_bytes -= it->first.second;
       c.idle.erase(it);
-      return cudaSuccess;
     }
+  }
+  if (got.ptr) {
+    if (got.freed) {
+      // same stream: stream order already protects the block; another stream: wait for the freeing stream's work
+      if (got.stream != g_current_stream || g_current_stream == nullptr) {
+        if (g_current_stream) err = cudaStreamWaitEvent(g_current_stream, got.freed, 0);
+        else err = cudaEventSynchronize(got.freed);
+      }
+      cudaEventDestroy(got.freed);
+      if (err != cudaSuccess) return err;
+    }
+    *p = got.ptr;
+    return cudaSuccess;
   }
   err = cudaMalloc(p, bytes);
   if (err != cudaSuccess) {  // out of memory: give the cached blocks back and retry once
@@ -89,18 +118,24 @@ cudaError_t dev_free(void *p) {
     if (it == c.live.end()) return cudaFree(p);  // not ours (never happens inside the engine)
     key = it->second;
     c.live.erase(it);
-    if (c.idle_bytes + key.second <= kDevCacheMaxIdle) {
-      c.idle.emplace(key, p);
-      c.idle_bytes += key.second;
-      return cudaSuccess;
-    }
+    if (c.idle_bytes + key.second > kDevCacheMaxIdle) key.first = -1;
   }
-  return cudaFree(p);
+  if (key.first < 0) return cudaFree(p);  // cudaFree synchronises the device itself
+  IdleBlock b{p, g_current_stream, nullptr};
+  int cur = 0;
+  if (g_current_stream && cudaGetDevice(&cur) == cudaSuccess && cur == key.first &&
+      cudaEventCreateWithFlags(&b.freed, cudaEventDisableTiming) == cudaSuccess) {
+    if (cudaEventRecord(b.freed, g_current_stream) != cudaSuccess) { cudaEventDestroy(b.freed); b.freed = nullptr; (void)cudaGetLastError(); }
+  }
+  std::lock_guard<std::mutex> lock(c.mu);
+  c.idle.emplace(key, b);
+  c.idle_bytes += key.second;
+  return cudaSuccess;
 }
 
 void dev_cache_release(int device) {
   DevCache &c = dev_cache();
-  std::vector<void *> blocks;
+  std::vector<IdleBlock> blocks;
   {
     std::lock_guard<std::mutex> lock(c.mu);
     for (auto it = c.idle.begin(); it != c.idle.end();) {
@@ -116,7 +151,10 @@ void dev_cache_release(int device) {
   int cur = 0;
   cudaGetDevice(&cur);
   if (cur != device) cudaSetDevice(device);
-  for (void *b : blocks) cudaFree(b);
+  for (IdleBlock &b : blocks) {
+    if (b.freed) cudaEventDestroy(b.freed);
+    cudaFree(b.ptr);
+  }
   if (cur != device) cudaSetDevice(cur);
 }
 
@@ -313,6 +351,7 @@ extern "C" int mfb_create(const mfb_config *cfg, mfb_engine **out) {
   MFB_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
   e->sm_count = prop.multiProcessorCount;
   MFB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  MFB_CUDA(mfb::enter(e));
   {
     int lo_prio = 0, hi_prio = 0;
     MFB_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
@@ -342,8 +381,9 @@ extern "C" int mfb_create(const mfb_config *cfg, mfb_engine **out) {
 
 extern "C" void mfb_destroy(mfb_engine *e) {
   if (!e) return;
-  cudaSetDevice(e->device);
+  mfb::enter(e);
   cudaStreamSynchronize(e->stream);
+  cudaStreamSynchronize(e->stream_hot);
   for (int w = 0; w < 3; w++) e->mat[w].release();
   e->sgd.release();
   dev_free(e->U); dev_free(e->V); dev_free(e->bestU); dev_free(e->bestV);
@@ -364,13 +404,15 @@ extern "C" void mfb_destroy(mfb_engine *e) {
   cudaStreamDestroy(e->stream_hot);
   cudaStreamDestroy(e->stream);
   delete e;
+  mfb::leave();
   mfb::dev_cache_release(destroyed_device);
 }
 
 extern "C" int mfb_sync(mfb_engine *e) {
   MFB_REQUIRE(e, "null engine");
+  MFB_CUDA(mfb::enter(e));
   MFB_CUDA(cudaStreamSynchronize(e->stream));
-  return 0;
+  return comm_check_error(e);
 }
 
 extern "C" int mfb_pin_host(void *ptr, uint64_t bytes) {
@@ -401,7 +443,7 @@ extern "C" int mfb_upload_csr(mfb_engine *e, int which, int32_t nrows, int32_t n
   MFB_REQUIRE(rowptr && (nnz == 0 || (rowind && rowval)), "mfb_upload_csr: CSR arrays are required");
   MFB_REQUIRE(nnz >= 0 && nnz < (int64_t)INT32_MAX, "mfb_upload_csr: nnz must fit in int32");
   MFB_REQUIRE(nrows <= e->n_users && ncols <= e->n_items, "mfb_upload_csr: matrix larger than the engine");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   DevCsr &m = e->mat[which];
   // same shape as the resident matrix (an epoch loop that re-uploads its input): keep the allocations,
   // cudaFree / cudaMalloc of GB-sized buffers cost milliseconds each
@@ -411,7 +453,11 @@ extern "C" int mfb_upload_csr(mfb_engine *e, int which, int32_t nrows, int32_t n
   } else {
     m.release();
   }
-  if (which == MFB_TRAIN) e->sgd.release();
+  if (which == MFB_TRAIN) {
+    e->sgd.release();
+    dev_free(e->res_row); dev_free(e->res_col);  // sized by the previous matrix
+    e->res_row = e->res_col = nullptr;
+  }
   m.nrows = nrows;
   m.ncols = ncols;
   m.nnz = nnz;
@@ -484,7 +530,7 @@ extern "C" int mfb_build_csc(mfb_engine *e, int which) {
   MFB_REQUIRE(e && which >= 0 && which < 3, "mfb_build_csc: bad argument");
   DevCsr &m = e->mat[which];
   MFB_REQUIRE(m.rowptr, "mfb_build_csc: matrix not uploaded");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   cudaStream_t st = e->stream;
   dev_free(m.colptr); dev_free(m.colind); dev_free(m.colval);
   m.colptr = nullptr; m.colind = nullptr; m.colval = nullptr;
@@ -523,7 +569,7 @@ extern "C" int mfb_download_csc(mfb_engine *e, int which, int64_t *colptr, int32
   MFB_REQUIRE(e && which >= 0 && which < 3 && colptr && colind && colval, "mfb_download_csc: bad argument");
   const DevCsr &m = e->mat[which];
   MFB_REQUIRE(m.colptr, "mfb_download_csc: no column index on the device");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   MFB_CUDA(cudaMemcpyAsync(colptr, m.colptr, sizeof(int64_t) * ((size_t)e->n_items + 1), cudaMemcpyDeviceToHost, e->stream));
   MFB_CUDA(cudaMemcpyAsync(colind, m.colind, sizeof(int32_t) * (size_t)m.nnz, cudaMemcpyDeviceToHost, e->stream));
   MFB_CUDA(cudaMemcpyAsync(colval, m.colval, sizeof(float) * (size_t)m.nnz, cudaMemcpyDeviceToHost, e->stream));
@@ -543,7 +589,7 @@ static void invalidate_plans(mfb_engine *e) {
 
 extern "C" int mfb_set_masks(mfb_engine *e, const uint8_t *invalid_users, const uint8_t *invalid_items) {
   MFB_REQUIRE(e && invalid_users && invalid_items, "mfb_set_masks: null argument");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   MFB_CUDA(cudaMemcpyAsync(e->bad_user, invalid_users, e->n_users, cudaMemcpyHostToDevice, e->stream));
   MFB_CUDA(cudaMemcpyAsync(e->bad_item, invalid_items, e->n_items, cudaMemcpyHostToDevice, e->stream));
   MFB_CUDA(cudaStreamSynchronize(e->stream));
@@ -563,7 +609,7 @@ extern "C" int mfb_set_row_range(mfb_engine *e, int side, int32_t begin, int32_t
 
 extern "C" int mfb_upload_factors(mfb_engine *e, const float *U, int64_t ldU, const float *V, int64_t ldV) {
   MFB_REQUIRE(e, "null engine");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   size_t w = sizeof(float) * (size_t)e->rank, dp = sizeof(float) * (size_t)e->ld;
   if (U) {
     MFB_REQUIRE(ldU >= e->rank, "mfb_upload_factors: ldU < rank");
@@ -579,7 +625,7 @@ extern "C" int mfb_upload_factors(mfb_engine *e, const float *U, int64_t ldU, co
 
 extern "C" int mfb_download_factors(mfb_engine *e, int which, float *U, int64_t ldU, float *V, int64_t ldV) {
   MFB_REQUIRE(e && (which == MFB_CURRENT || which == MFB_BEST), "mfb_download_factors: bad argument");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   const float *su = which == MFB_BEST ? e->bestU : e->U, *sv = which == MFB_BEST ? e->bestV : e->V;
   size_t w = sizeof(float) * (size_t)e->rank, sp = sizeof(float) * (size_t)e->ld;
   if (U) {
@@ -591,7 +637,7 @@ extern "C" int mfb_download_factors(mfb_engine *e, int which, float *U, int64_t 
     MFB_CUDA(cudaMemcpy2DAsync(V, sizeof(float) * (size_t)ldV, sv, sp, w, e->n_items, cudaMemcpyDeviceToHost, e->stream));
   }
   MFB_CUDA(cudaStreamSynchronize(e->stream));
-  return 0;
+  return comm_check_error(e);  // rows that never arrived from a peer must not be read as factors
 }
 
 extern "C" int mfb_set_aux(mfb_engine *e, int variant, const int32_t *user_freq, const int32_t *item_freq,
@@ -602,7 +648,7 @@ extern "C" int mfb_set_aux(mfb_engine *e, int variant, const int32_t *user_freq,
   MFB_REQUIRE(variant == MFB_MF || (user_train && item_train), "mfb_set_aux: training payloads required");
   MFB_REQUIRE(variant == MFB_MF || variant == MFB_IFWMF || (user_pred && item_pred), "mfb_set_aux: prediction ranks required");
   MFB_REQUIRE(variant != MFB_TMFDROPOUT || poisson_cdf, "mfb_set_aux: poisson_cdf required");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   const int32_t *ut = (const int32_t *)user_train, *it = (const int32_t *)item_train;
   std::vector<Aux> hu(e->n_users), hi(e->n_items);
   for (int u = 0; u < e->n_users; u++) hu[u] = Aux{user_freq[u], ut ? ut[u] : 0, user_pred ? user_pred[u] : 0, 0};
@@ -626,7 +672,11 @@ extern "C" int mfb_sgd_plan(mfb_engine *e, int32_t P, const int32_t *user_part, 
   MFB_REQUIRE(P >= 1 && P <= kMaxBlocks, "mfb_sgd_plan: P must be in 1..64");
   MFB_REQUIRE(P == 1 || (user_part && item_part), "mfb_sgd_plan: partitions required for P > 1");
   MFB_REQUIRE(e->mat[MFB_TRAIN].rowptr, "mfb_sgd_plan: upload the training matrix first");
-  MFB_CUDA(cudaSetDevice(e->device));
+  if (user_part && item_part) {  // a part >= P would land outside the P x P block grid (negative = not trained)
+    for (int u = 0; u < e->n_users; u++) MFB_REQUIRE(user_part[u] < P, "mfb_sgd_plan: user_part entry >= P");
+    for (int i = 0; i < e->n_items; i++) MFB_REQUIRE(item_part[i] < P, "mfb_sgd_plan: item_part entry >= P");
+  }
+  MFB_CUDA(mfb::enter(e));
   return sgd_plan_build(e, P, user_part, item_part);
 }
 
@@ -640,7 +690,7 @@ extern "C" int mfb_sgd_subepoch(mfb_engine *e, const int32_t *blocks, int32_t nb
   for (int i = 0; i < nb; i++)
     MFB_REQUIRE(blocks[2 * i] >= 0 && blocks[2 * i] < e->sgd.P && blocks[2 * i + 1] >= 0 && blocks[2 * i + 1] < e->sgd.P,
                 "mfb_sgd_subepoch: block index out of range");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   if (e->opt_sgd_block_order == 1) return sgd_flat_launch(e, blocks, nb, variant, learn_rate, ureg, ireg, seed, counter);
   return sgd_subepoch_launch(e, blocks, nb, variant, learn_rate, ureg, ireg, seed, counter);
 }
@@ -652,7 +702,7 @@ extern "C" int mfb_sgd_epoch_flat(mfb_engine *e, int variant, float learn_rate, 
   const int32_t whole[2] = {0, 0};
   MFB_REQUIRE(variant >= MFB_MF && variant <= MFB_TMFDROPOUT, "mfb_sgd_epoch_flat: bad variant");
   MFB_REQUIRE(variant == MFB_MF || e->aux_variant == variant, "mfb_sgd_epoch_flat: mfb_set_aux not called for this variant");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   return sgd_flat_launch(e, whole, 1, variant, learn_rate, ureg, ireg, seed, counter);
 }
 
@@ -671,6 +721,7 @@ extern "C" int mfb_set_option(mfb_engine *e, const char *name, double value) {
   else if (n == "sgd_flat_debug") e->opt_sgd_flat_debug = (int)value;
   else if (n == "sgd_atomic") e->opt_sgd_atomic = (int)value;
   else if (n == "sgd_rotate") e->opt_sgd_rotate = (int)value;
+  else if (n == "sgd_shuffle_seed") e->opt_sgd_shuffle_seed = (uint64_t)(int64_t)value;
   else if (n == "sgd_hot") e->opt_sgd_hot = (int)value;
   else if (n == "sgd_hot_min_count") e->opt_sgd_hot_min_count = (int)value;
   else if (n == "sgd_hot_inflight") e->opt_sgd_hot_inflight = value;
@@ -713,13 +764,13 @@ extern "C" int mfb_debug_sgd_records(mfb_engine *e, int32_t user_part, int32_t i
   MFB_REQUIRE(e && e->sgd.built && e->sgd.recs, "mfb_debug_sgd_records: call mfb_sgd_plan first");
   MFB_REQUIRE(user_part >= 0 && user_part < e->sgd.P && item_part >= 0 && item_part < e->sgd.P,
               "mfb_debug_sgd_records: block index out of range");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   return sgd_debug_records(e, user_part, item_part, records, cold_records, lists, n_lists);
 }
 
 extern "C" int mfb_debug_sgd_hot_batch(mfb_engine *e, double out[3]) {
   MFB_REQUIRE(e && out && e->sgd.built, "mfb_debug_sgd_hot_batch: call mfb_sgd_plan first");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   return sgd_debug_hot_batch(e, out);
 }
 
@@ -728,7 +779,7 @@ extern "C" int mfb_als_half_step(mfb_engine *e, int side, float reg) {
   MFB_REQUIRE(e->rank <= 128, "mfb_als_half_step: rank must be <= 128");
   const DevCsr &m = e->mat[MFB_TRAIN];
   MFB_REQUIRE(m.rowptr && (side == MFB_USER || m.colptr), "mfb_als_half_step: training CSR/CSC not uploaded");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   return als_half_step_launch(e, side, reg);
 }
 
@@ -736,14 +787,14 @@ extern "C" int mfb_debug_als_gram(mfb_engine *e, int side, int32_t row, float *o
   MFB_REQUIRE(e && out && padded_rank && (side == MFB_USER || side == MFB_ITEM), "mfb_debug_als_gram: bad argument");
   MFB_REQUIRE(row >= 0 && row < (side == MFB_USER ? e->n_users : e->n_items), "mfb_debug_als_gram: bad row");
   MFB_REQUIRE(e->mat[MFB_TRAIN].rowptr && (side == MFB_USER || e->mat[MFB_TRAIN].colptr), "mfb_debug_als_gram: matrix not uploaded");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   return als_debug_gram(e, side, row, out, padded_rank);
 }
 
 extern "C" int mfb_ccdpp_begin(mfb_engine *e) {
   MFB_REQUIRE(e, "null engine");
   MFB_REQUIRE(e->mat[MFB_TRAIN].rowptr && e->mat[MFB_TRAIN].colptr, "mfb_ccdpp_begin: training CSR and CSC required");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   return ccdpp_begin_impl(e);
 }
 extern "C" int mfb_ccdpp_rank1(mfb_engine *e, int32_t k, int first_iter, int32_t inner, float ureg, float ireg,
@@ -751,12 +802,12 @@ extern "C" int mfb_ccdpp_rank1(mfb_engine *e, int32_t k, int first_iter, int32_t
   MFB_REQUIRE(e && e->res_row, "mfb_ccdpp_rank1: call mfb_ccdpp_begin first");
   MFB_REQUIRE(k >= 0 && k < e->rank && inner >= 0, "mfb_ccdpp_rank1: bad argument");
   MFB_REQUIRE(item_freq_thresh <= 0 || e->aux_i, "mfb_ccdpp_rank1: item frequencies (mfb_set_aux) required");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   return ccdpp_rank1_impl(e, k, first_iter, inner, ureg, ireg, item_freq_thresh);
 }
 extern "C" int mfb_ccdpp_end(mfb_engine *e) {
   MFB_REQUIRE(e, "null engine");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   return ccdpp_end_impl(e);
 }
 
@@ -767,7 +818,7 @@ extern "C" int mfb_eval(mfb_engine *e, int which, int factors, int variant, int 
   MFB_REQUIRE(variant >= MFB_MF && variant <= MFB_TMFDROPOUT, "mfb_eval: bad variant");
   MFB_REQUIRE(e->mat[which].rowptr, "mfb_eval: matrix not uploaded");
   MFB_REQUIRE(variant == MFB_MF || e->aux_variant == variant, "mfb_eval: mfb_set_aux not called for this variant");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   return eval_launch(e, which, factors, variant, weighted, want_norms, out);
 }
 
@@ -778,20 +829,20 @@ extern "C" int mfb_eval_groups(mfb_engine *e, int which, int factors, int varian
   MFB_REQUIRE(variant >= MFB_MF && variant <= MFB_TMFDROPOUT, "mfb_eval_groups: bad variant");
   MFB_REQUIRE(e->mat[which].rowptr, "mfb_eval_groups: matrix not uploaded");
   MFB_REQUIRE(variant == MFB_MF || e->aux_variant == variant, "mfb_eval_groups: mfb_set_aux not called for this variant");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   return eval_groups_launch(e, which, factors, variant, user_group, item_group, out);
 }
 
 extern "C" int mfb_snapshot_best(mfb_engine *e) {
   MFB_REQUIRE(e, "null engine");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   MFB_CUDA(cudaMemcpyAsync(e->bestU, e->U, sizeof(float) * (size_t)e->n_users * e->ld, cudaMemcpyDeviceToDevice, e->stream));
   MFB_CUDA(cudaMemcpyAsync(e->bestV, e->V, sizeof(float) * (size_t)e->n_items * e->ld, cudaMemcpyDeviceToDevice, e->stream));
   return 0;
 }
 extern "C" int mfb_restore_best(mfb_engine *e) {
   MFB_REQUIRE(e, "null engine");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   MFB_CUDA(cudaMemcpyAsync(e->U, e->bestU, sizeof(float) * (size_t)e->n_users * e->ld, cudaMemcpyDeviceToDevice, e->stream));
   MFB_CUDA(cudaMemcpyAsync(e->V, e->bestV, sizeof(float) * (size_t)e->n_items * e->ld, cudaMemcpyDeviceToDevice, e->stream));
   return 0;
@@ -799,13 +850,13 @@ extern "C" int mfb_restore_best(mfb_engine *e) {
 
 extern "C" int mfb_event_record(mfb_engine *e, int32_t slot) {
   MFB_REQUIRE(e && slot >= 0 && slot < 16, "mfb_event_record: bad slot");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   MFB_CUDA(cudaEventRecord(e->events[slot], e->stream));
   return 0;
 }
 extern "C" int mfb_event_elapsed_ms(mfb_engine *e, int32_t a, int32_t b, float *ms) {
   MFB_REQUIRE(e && ms && a >= 0 && a < 16 && b >= 0 && b < 16, "mfb_event_elapsed_ms: bad argument");
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   MFB_CUDA(cudaEventSynchronize(e->events[b]));
   MFB_CUDA(cudaEventElapsedTime(ms, e->events[a], e->events[b]));
   return 0;
@@ -832,7 +883,7 @@ __global__ void pack_rows_kernel(const float4 *__restrict__ src, const int32_t *
 static int pack_impl(mfb_engine *e, int side, const int32_t *ids, int32_t n, void *dev_buf, int unpack) {
   MFB_REQUIRE(e && ids && dev_buf && n >= 0 && (side == MFB_USER || side == MFB_ITEM), "mfb_pack_rows: bad argument");
   if (n == 0) return 0;
-  MFB_CUDA(cudaSetDevice(e->device));
+  MFB_CUDA(mfb::enter(e));
   MFB_TRY(ensure_scratch(e, sizeof(int32_t) * (size_t)n));
   MFB_CUDA(cudaMemcpyAsync(e->scratch, ids, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
   int nq = e->ld / 4;

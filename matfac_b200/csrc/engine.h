@@ -23,6 +23,12 @@ extern std::atomic<uint64_t> g_launches;
 cudaError_t dev_alloc_bytes(void **p, size_t bytes);
 cudaError_t dev_free(void *p);
 void dev_cache_release(int device);
+}  // namespace mfb
+struct mfb_engine;
+namespace mfb {
+// every C-ABI entry: makes the engine's device current and names its stream as the one this thread works on
+cudaError_t enter(mfb_engine *e);
+void leave();
 template <class T>
 inline cudaError_t dev_alloc(T **p, size_t bytes) { return dev_alloc_bytes(reinterpret_cast<void **>(p), bytes); }
 
@@ -163,6 +169,7 @@ struct mfb_engine {
   int opt_sgd_atomic = 1;             // item rows updated by vector reductions (no lost updates)
   int opt_sgd_block_order = 0;        // stratified trainers: 0 = user-major runs (reference order), 1 = shuffled inside the blocks
   int opt_sgd_rotate = 0;             // user runs start at a pseudo-random offset (de-correlates heavy users)
+  uint64_t opt_sgd_shuffle_seed = 0;  // key of the plan-time physical shuffle of the rating records (the host passes trainSeed)
   int opt_sgd_hot = 1;                // shuffled kernel: hot item rows trained by dedicated CTAs (row in shared memory)
   int opt_sgd_hot_min_count = 1024;   // a hot list holds at least this many ratings
   double opt_sgd_hot_inflight = 16.0; // an item is hot inside a block when the shuffled kernel would keep more updates of its row in flight
@@ -242,5 +249,7 @@ int ccdpp_rank1_impl(mfb_engine *e, int32_t k, int first_iter, int32_t inner, fl
                      int32_t item_freq_thresh);
 int ccdpp_end_impl(mfb_engine *e);
 int comm_barrier_launch(mfb_engine *e);
+// non-zero (mfb_last_error set) when a device-side flag wait of this engine has timed out; syncs the stream
+int comm_check_error(mfb_engine *e);
 
 }  // namespace mfb

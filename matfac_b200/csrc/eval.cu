@@ -238,6 +238,7 @@ int eval_launch(mfb_engine *e, int which, int factors, int variant, int weighted
   MFB_CUDA(cudaMemcpyAsync(e->eval_out_host, e->eval_out, sizeof(double) * 4, cudaMemcpyDeviceToHost, e->stream));
   MFB_CUDA(cudaStreamSynchronize(e->stream));
   for (int i = 0; i < 4; i++) out[i] = e->eval_out_host[i];
+  MFB_TRY(comm_check_error(e));  // an evaluation over item rows that never arrived must not be reported
   return 0;
 }
 

@@ -313,6 +313,10 @@ static int sgd_build_records(mfb_engine *e, const std::vector<int64_t> &ranges, 
       n_cand += cv.size();
     }
   }
+  // key of the physical shuffle: derived from the training seed (option sgd_shuffle_seed, set by the host trainers from
+  // Model::trainSeed before the plan is built — the reference seeds its shuffles with mt19937(trainSeed),
+  // modelMF.cpp:63,78), so that group membership and the order of the hot lists differ from seed to seed
+  const uint64_t shuffle_key = 0x5EEDULL ^ mix64(e->opt_sgd_shuffle_seed);
   int4 *packed;
   MFB_CUDA(dev_alloc(&packed, sizeof(int4) * (size_t)n));
   MFB_LAUNCH(sgd_pack_records_kernel, grid, 256, 0, st, e->mat[MFB_TRAIN].rowptr, e->n_users, pl.rat_user, pl.item, pl.val, n, packed);
@@ -325,11 +329,11 @@ static int sgd_build_records(mfb_engine *e, const std::vector<int64_t> &ranges, 
     MFB_CUDA(dev_alloc(&d_cls, cls.size()));
     MFB_CUDA(cudaMemcpyAsync(d_cls, cls.data(), cls.size(), cudaMemcpyHostToDevice, st));
     MFB_CUDA(dev_alloc(&d_keys, sizeof(uint32_t) * (size_t)n));
-    MFB_LAUNCH(sgd_shuffle_records_kernel, grid, 256, 0, st, packed, n, d_off, nrng, 0x5EEDULL,
+    MFB_LAUNCH(sgd_shuffle_records_kernel, grid, 256, 0, st, packed, n, d_off, nrng, shuffle_key,
                reinterpret_cast<int4 *>(pl.recs), d_row, e->n_items, d_cls, d_keys);
     MFB_CUDA(cudaStreamSynchronize(st));  // cls (host vector) is copied
   } else {
-    MFB_LAUNCH(sgd_shuffle_records_kernel, grid, 256, 0, st, packed, n, d_off, nrng, 0x5EEDULL,
+    MFB_LAUNCH(sgd_shuffle_records_kernel, grid, 256, 0, st, packed, n, d_off, nrng, shuffle_key,
                reinterpret_cast<int4 *>(pl.recs), nullptr, e->n_items, nullptr, nullptr);
     MFB_CUDA(cudaStreamSynchronize(st));
     dev_free(d_off); dev_free(d_row); dev_free(packed);
@@ -1129,13 +1133,21 @@ __global__ void __launch_bounds__(512) sgd_hot_kernel(const SgdArgs a, const int
   const int4 *rec_src = a.recs + off + jl;            // + x * Te
   __syncthreads();
   const int rounds = (len + Te - 1) / Te;
+  // the list is walked from a fresh starting round every epoch (round x of the epoch is chunk (x + r0) mod rounds of
+  // the list): the reference reshuffles its whole rating order per epoch (modelMF.cpp:76-81), a list replayed in the
+  // same order would give the most rated rows the same update sequence every time
+  const int r0 = (int)(mix64(a.seed ^ mix64(a.counter_id * 0x9E3779B97F4A7C15ull + (uint64_t)(uint32_t)it)) % (uint64_t)rounds);
+  auto chunk_of = [&](int x) { const int c = x + r0; return c >= rounds ? c - rounds : c; };
   for (int r = -(2 * S - 1); r < rounds; r++) {
     {  // record of round r + 2S - 1
-      const int x = r + 2 * S - 1, j = x * Te + jl;
-      if (lane_on && q == 0 && j < len) cp_async16(rec_ring + (x & (2 * S - 1)) * T + jl, rec_src + x * Te);
+      const int x = r + 2 * S - 1;
+      if (x < rounds) {
+        const int cx = chunk_of(x), j = cx * Te + jl;
+        if (lane_on && q == 0 && j < len) cp_async16(rec_ring + (x & (2 * S - 1)) * T + jl, rec_src + cx * Te);
+      }
     }
     {  // user row (and aux record) of round r + S - 1: its record was committed S iterations ago
-      const int x = r + S - 1, j = x * Te + jl;
+      const int x = r + S - 1, j = (x >= 0 && x < rounds) ? chunk_of(x) * Te + jl : len;
       if (x >= 0 && lane_on && j < len) {
         const int user = rec_ring[(x & (2 * S - 1)) * T + jl].x;
         float4 *dst = tile + (x & (S - 1)) * stage_quads + row_off;
@@ -1152,7 +1164,7 @@ __global__ void __launch_bounds__(512) sgd_hot_kernel(const SgdArgs a, const int
     if (r < 0) continue;
     const int st = r & (S - 1);
     float4 *row = tile + st * stage_quads + row_off;
-    const int j = r * Te + jl;
+    const int j = chunk_of(r) * Te + jl;
     const bool on = lane_on && j < len;
     int4 rec = make_int4(0, 0, 0, 0);
     int pay = 0;

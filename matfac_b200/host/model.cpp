@@ -437,6 +437,7 @@ void Model::runFlatSgd(const Data &data, Model &bestModel, std::unordered_set<in
   Stop st;
   beginTraining(data, bestModel, invalidUsers, invalidItems, st, tag);
   DeviceSession &s = *dev_;
+  s.check(mfb_set_option(s.eng, "sgd_shuffle_seed", (double)(uint32_t)trainSeed));
   s.check(mfb_sgd_plan(s.eng, 1, nullptr, nullptr));
   const int variant = deviceVariant();
   for (int iter = 0; iter < maxIter; iter++) {
@@ -474,6 +475,7 @@ void Model::runStratifiedSgd(const Data &data, Model &bestModel, std::unordered_
   std::cout << "train items: " << trainItems.size() << " itemsPerPart: " << trainItems.size() / P << std::endl;
   std::vector<int> userPart = matfac::partitionIds(trainUsers, P, nUsers);
   std::vector<int> itemPart = matfac::partitionIds(trainItems, P, nItems);
+  s.check(mfb_set_option(s.eng, "sgd_shuffle_seed", (double)(uint32_t)trainSeed));
   s.check(mfb_sgd_plan(s.eng, P, userPart.data(), itemPart.data()));
   const int variant = deviceVariant();
   std::vector<std::pair<int, int>> updateSeq;
