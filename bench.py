@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py — SGD rating-updates/s on a Netflix-shaped synthetic problem at rank 64.
+"""bench.py — SGD rating-updates/s on a Netflix-shaped synthetic problem at rank 64 (+ the other trainers of the path).
 
 Contract (one JSON line on stdout, printed by rank 0):
   python bench.py --gpus N --steps K --warmup W          device arm (this repo's CUDA engine)
@@ -7,21 +7,29 @@ Contract (one JSON line on stdout, printed by rank 0):
                                                          code (oracle/_ref/mf_ref) on host cores
 A "step" is one SGD epoch over the whole training matrix: at N = 1 the serial-SGD trainer
 (ModelMF::train, the CLI default --mf_method sgd) on the shuffled kernel; at N > 1 the stratified
-trainer (DSGD: user strata pinned to ranks, item blocks exchanged after every sub-epoch).
+trainer (ModelMF::trainSGDPar = DSGD: user strata pinned to ranks, item blocks handed from rank to rank
+after every sub-epoch) with the REFERENCE'S partitions and update sequences (modelMF.cpp:229-265,
+util.cpp:1077-1107); the rating-balanced / rotation variant is timed next to it as `dsgd_balanced`.
 
 Workload = BASELINE.json configs[1]: modelMF SGD, rank 64, 480,189 x 17,770, ~100.5 M ratings
-(synthetic, Zipf-skewed positions, ratings from a rank-8 model + noise; random-init factors
-U(-0.01, 0.01) as model.cpp:2331-2350).  Inputs (ratings 0.8 GB + U 123 MB) exceed the 126 MB L2,
-so no explicit L2 flush is done between timed epochs.
+(matfac_b200/synth.py: skewed_problem — a pure function of (shape, seed): both arms, every N and every rank
+see the same matrix; `config.matrix_crc` is the CRC-32 of its arrays).  Inputs (ratings 0.8 GB + U 123 MB)
+exceed the 126 MB L2, so no explicit L2 flush is done between timed epochs.
 
-  value     epochs * valid-ratings / device time (CUDA events on the engine's stream, max over
+  value     ratings visited in the timed epochs / device time (CUDA events on the engine's stream, max over
             ranks), inputs resident in HBM
-  e2e       the same metric through the C ABI with HOST buffers: every step uploads the rating
-            CSR and the factor matrices from pinned host memory, builds the stratum plan, runs
-            one epoch plus the per-epoch evaluation and downloads the factors
-  roofline  algorithmic bytes (16 r + 12 per update) / kernel time vs the measured
-            HBM copy bandwidth of MEASURED_PEAKS.json
+  e2e       the same metric through the C ABI with HOST buffers (N = 1): every step uploads the rating CSR and the
+            factor matrices from pinned host memory, builds the plan, runs one epoch plus the per-epoch
+            evaluation and downloads the factors
+  roofline  algorithmic bytes (16 r + 12 per update) / kernel time vs the measured HBM copy
+            bandwidth of MEASURED_PEAKS.json; `l2` = the same against the measured L2 figures of
+            profiles/r2_l2_probe.json (the factor matrices of this shape are L2-resident)
   cpu_baseline  the reference's OpenMP stratified SGD (trainSGDPar) on a row sample, host cores
+  solvers   ALS epoch seconds at rank 64 and 128, CCD++ rank-one step, objective pass (row-sharded at N > 1)
+  yahoo     BASELINE.json configs[4] (1 M x 625 k, 250 M ratings, rank 64): SGD / DSGD epoch and CCD++ step — the
+            shape whose factors (416 MB) do not fit L2
+  oracle_check (N > 1)  the DSGD path at N ranks against the oracle's trainSGDPar with P = N on the 1/20-scale
+            matrix: same partitions, same update sequences, validation RMSE per epoch side by side
 """
 from __future__ import annotations
 
@@ -40,14 +48,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 RANK = 64
-SHAPE = (480_189, 17_770, 100_480_507)
+SHAPE = (480_189, 17_770, 100_480_507)          # BASELINE.json configs[1] / [2]
+YAHOO_SHAPE = (1_000_990, 624_961, 250_000_000)  # BASELINE.json configs[4]
+DATA_SEED = 20260102
 # learnrate 0.002: at 0.005 the reference itself diverges on this matrix in epoch 0 and falls back on
 # its NaN guard (restore + halve, model.cpp:1487-1498) — measured with the oracle, see DESIGN.md
 HP = dict(lr=0.002, ureg=0.05, ireg=0.05)
 FALLBACK_HBM_GBS = 6650.0
-ITEM_SHARE_CAP = 232_944 / 100_480_507
-# dram__bytes_read.sum + dram__bytes_write.sum of the SGD kernel launches of one epoch (profiles/r1_sgd_flat.md)
-DRAM_TRAFFIC_BYTES_PER_EPOCH = 10.44e9
 
 
 def log(*a):
@@ -55,108 +62,19 @@ def log(*a):
 
 
 # ---------------------------------------------------------------------------------------------
+def make_problem(shape, scale, device):
+    """The bench matrix (or a `scale`d copy: users and ratings scaled, items scaled down to no less than 5 %)."""
+    from matfac_b200 import synth
+    n_users = int(shape[0] * scale)
+    n_items = int(shape[1] * max(scale, 0.05)) if scale < 1 else shape[1]
+    nnz = int(shape[2] * scale)
+    return synth.skewed_problem(n_users, n_items, nnz, DATA_SEED, device=device)
+
+
 def gen_problem(n_users, n_items, nnz, seed, device):
-    """Netflix-shaped training CSR (+ a 1 % validation CSR) generated with torch on `device`.
-    Returns dict of numpy arrays (host)."""
-    import torch
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    dev = torch.device(device)
-
-    def zipf(n, s):
-        w = 1.0 / torch.arange(1, n + 1, dtype=torch.float64, device=dev).pow(s)
-        w = w[torch.randperm(n, generator=g, device=dev)]
-        return w / w.sum()
-
-    pu, pi = zipf(n_users, 0.9), zipf(n_items, 1.05)
-    # head of the item distribution as in the real Netflix Prize data: the most-rated title holds
-    # 232,944 of 100,480,507 ratings (0.232 %); an uncapped Zipf(1.05) head would hold twice that
-    for _ in range(8):
-        pi = pi.clamp(max=ITEM_SHARE_CAP)
-        pi = pi / pi.sum()
-    ci = torch.cumsum(pi, 0)
-    total = int(nnz * 1.01)
-    keys = torch.empty(0, dtype=torch.int64, device=dev)
-    # every user and every item at least once (io.cpp:742-752)
-    base_u = torch.arange(n_users, device=dev, dtype=torch.int64)
-    base_i = torch.searchsorted(ci, torch.rand(n_users, generator=g, device=dev, dtype=torch.float64)).clamp_(max=n_items - 1)
-    base2_i = torch.arange(n_items, device=dev, dtype=torch.int64)
-    base2_u = torch.multinomial(pu.float(), n_items, replacement=True, generator=g)
-    keys = torch.unique(torch.cat([base_u * n_items + base_i, base2_u * n_items + base2_i]))
-    cap = 0.85 * n_items
-    for rnd in range(12):
-        need = total - keys.numel()
-        if need <= 0:
-            break
-        draw = int(need * (1.6 if rnd == 0 else 1.3)) + 1024
-        # user degrees ~ Zipf, capped so that no user exceeds ~85 % of the catalogue
-        deg = torch.clamp(pu * draw, max=cap).round().to(torch.int64)
-        u = torch.repeat_interleave(torch.arange(n_users, device=dev, dtype=torch.int64), deg)
-        i = torch.searchsorted(ci, torch.rand(u.numel(), generator=g, device=dev, dtype=torch.float64)).clamp_(max=n_items - 1)
-        keys = torch.unique(torch.cat([keys, u * n_items + i]))
-        del u, i, deg
-    if keys.numel() > total:
-        drop = torch.randperm(keys.numel(), generator=g, device=dev)[: keys.numel() - total]
-        mask = torch.ones(keys.numel(), dtype=torch.bool, device=dev)
-        mask[drop] = False
-        # never drop a user's or an item's covering pair: re-add them
-        keys = torch.unique(torch.cat([keys[mask], base_u * n_items + base_i, base2_u * n_items + base2_i]))
-    users = (keys // n_items).to(torch.int32)
-    items = (keys % n_items).to(torch.int32)
-    del keys
-    tr_rank = 8
-    us = torch.randn(n_users, tr_rank, generator=g, device=dev)
-    vs = torch.randn(n_items, tr_rank, generator=g, device=dev)
-    vals = torch.empty(users.numel(), dtype=torch.float32, device=dev)
-    step = 1 << 24
-    for s in range(0, users.numel(), step):
-        e = min(s + step, users.numel())
-        d = (us[users[s:e].long()] * vs[items[s:e].long()]).sum(1) / tr_rank ** 0.5
-        vals[s:e] = 3.6 + 1.1 * d + 0.3 * torch.randn(e - s, generator=g, device=dev)
-    vals = (torch.round(vals * 2) / 2).clamp_(1.0, 5.0)
-    # split: 1 % validation, never a user's/item's first rating
-    colour = torch.rand(users.numel(), generator=g, device=dev)
-    first_u = torch.ones(users.numel(), dtype=torch.bool, device=dev)
-    first_u[1:] = users[1:] != users[:-1]
-    order_i = torch.argsort(items.long() * n_users + users.long())
-    si = items[order_i]
-    fi = torch.ones(si.numel(), dtype=torch.bool, device=dev)
-    fi[1:] = si[1:] != si[:-1]
-    first_i = torch.zeros(users.numel(), dtype=torch.bool, device=dev)
-    first_i[order_i[fi]] = True
-    is_val = (colour < 0.01) & ~first_u & ~first_i
-    del order_i, si, fi, colour
-
-    def csr(mask):
-        u, i, v = users[mask], items[mask], vals[mask]
-        ptr = torch.zeros(n_users + 1, dtype=torch.int64, device=dev)
-        ptr[1:] = torch.cumsum(torch.bincount(u.long(), minlength=n_users), 0)
-        return ptr.cpu().numpy(), i.cpu().numpy(), v.cpu().numpy()
-
-    tr, va = csr(~is_val), csr(is_val)
-    return dict(n_users=n_users, n_items=n_items, train=tr, val=va)
-
-
-def shared_problem(n_users, n_items, nnz, seed, rank, dist, device):
-    """N > 1: rank 0 generates the matrix and broadcasts it — the torch generator is not bit-reproducible across
-    processes (atomics in unique / scatter), and every rank must partition the SAME matrix."""
-    import torch
-    prob = gen_problem(n_users, n_items, nnz, seed, device) if rank == 0 else None
-    head = torch.zeros(2, dtype=torch.int64, device=device)
-    if rank == 0:
-        head[0], head[1] = int(prob["train"][0][-1]), int(prob["val"][0][-1])
-    dist.broadcast(head, 0)
-    out = {"n_users": n_users, "n_items": n_items}
-    for name, n in (("train", int(head[0])), ("val", int(head[1]))):
-        arrs = []
-        for k, (dt, ln) in enumerate(((torch.int64, n_users + 1), (torch.int32, n), (torch.float32, n))):
-            t = torch.from_numpy(prob[name][k]).to(device) if rank == 0 else torch.empty(ln, dtype=dt, device=device)
-            dist.broadcast(t, 0)
-            arrs.append(t.cpu().numpy())
-            del t
-        out[name] = tuple(arrs)
-    torch.cuda.empty_cache()
-    return out
+    """The generator under its round-1 name (tools/): same arrays as matfac_b200.synth.skewed_problem."""
+    from matfac_b200 import synth
+    return synth.skewed_problem(n_users, n_items, nnz, seed, device=device)
 
 
 class Mat:
@@ -267,91 +185,316 @@ def measured_hbm_gbs():
     return FALLBACK_HBM_GBS, "fallback"
 
 
+def committed_profile(name):
+    """A committed JSON summary under profiles/ (ncu traffic per launch, the L2 probe), or {}."""
+    p = os.path.join(ROOT, "profiles", name)
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
-def csc_on_device(n_users, n_items, ptr, ind, val, device):
-    """gk_csr_CreateIndex(mat, GK_CSR_COL) as a stable sort by column (torch, set-up only)."""
+
+def masks_of(prob):
+    ptr, ind, _ = prob["train"]
+    bad_u = (np.diff(ptr) == 0).astype(np.uint8)
+    cnt_i = np.bincount(ind, minlength=prob["n_items"])
+    return bad_u, (cnt_i == 0).astype(np.uint8), cnt_i
+
+
+def init_factors(n_users, n_items, r, seed=1):
+    rng = np.random.default_rng(seed)
+    return (rng.uniform(-0.01, 0.01, size=(n_users, r)).astype(np.float32),
+            rng.uniform(-0.01, 0.01, size=(n_items, r)).astype(np.float32))
+
+
+class Ranks:
+    """The process group seen from this rank (a no-op group at N = 1)."""
+
+    def __init__(self, dist, rank, world, local_rank):
+        self.dist, self.rank, self.world, self.local = dist, rank, world, local_rank
+
+    def max(self, x):
+        if self.dist is None:
+            return float(x)
+        import torch
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, xs):
+        if self.dist is None:
+            return [float(x) for x in xs]
+        import torch
+        t = torch.tensor([float(x) for x in xs], dtype=torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+    def gather(self, x):
+        if self.dist is None:
+            return [x]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, x)
+        return out
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+
+# ---------------------------------------------------------------------------------------------
+def run_dsgd(prob, rk, r, plan, warmup, steps, options=None, seed=1, curve=False, U0V0=None):
+    """DSGD over rk.world ranks (one rank in this process).  Returns the timing / RMSE record (max over ranks)."""
     import torch
-    dev = torch.device(device)
-    ind_d = torch.from_numpy(ind).to(dev)
-    deg = torch.from_numpy(np.diff(ptr)).to(dev)
-    rows = torch.repeat_interleave(torch.arange(n_users, device=dev, dtype=torch.int32), deg)
-    order = torch.sort(ind_d.long() * n_users + rows.long()).indices  # (col, row) ascending == stable by col
-    colind = rows[order].cpu().numpy()
-    colval = torch.from_numpy(val).to(dev)[order].cpu().numpy()
-    cnt = torch.bincount(ind_d.long(), minlength=n_items)
-    colptr = np.zeros(n_items + 1, np.int64)
-    colptr[1:] = torch.cumsum(cnt, 0).cpu().numpy()
-    del ind_d, deg, rows, order, cnt
-    torch.cuda.empty_cache()
-    return colptr, colind, colval
+    from matfac_b200 import dsgd
+    from matfac_b200 import engine as E
+    n_users, n_items = prob["n_users"], prob["n_items"]
+    bad_u, bad_i, _ = masks_of(prob)
+    U0, V0 = U0V0 if U0V0 is not None else init_factors(n_users, n_items, r)
+    P = rk.world
+    n_sub = (warmup + steps) * P
+    opts = {"sgd_flat_inflight_frac": 8e-4}
+    opts.update(options or {})
+    d = dsgd.Dsgd(n_users, n_items, r, P, {rk.rank: rk.local}, prob["train"], prob["val"], U0, V0, bad_u, bad_i, n_sub,
+                  plan=plan, seed=seed, exchange=rk.gather, options=opts)
+    eng = d.engines[rk.rank]
+
+    def sync_all():
+        d.barrier()
+        eng.sync()
+        torch.cuda.synchronize()
+        rk.barrier()
+
+    rmse_curve = []
+
+    def val_rmse():
+        d.publish()
+        s = rk.sum(d.eval_sums(E.VAL))
+        d.barrier()
+        return float(np.sqrt(s[0] / s[1])) if s[1] > 0 else float("nan")
+
+    for w in range(warmup):
+        d.run(w * P, (w + 1) * P, HP["lr"], HP["ureg"], HP["ireg"], seed)
+        if curve:
+            rmse_curve.append(val_rmse())
+    sync_all()
+    launches0 = E.launch_count()
+    eng.event_record(0)
+    if curve:  # per-epoch evaluation outside the timed spans
+        ms = 0.0
+        for k in range(steps):
+            eng.event_record(0)
+            d.run((warmup + k) * P, (warmup + k + 1) * P, HP["lr"], HP["ureg"], HP["ireg"], seed)
+            eng.event_record(1)
+            sync_all()
+            ms += eng.event_elapsed_ms(0, 1)
+            rmse_curve.append(val_rmse())
+    else:
+        d.run(warmup * P, (warmup + steps) * P, HP["lr"], HP["ureg"], HP["ireg"], seed)
+        eng.event_record(1)
+        sync_all()
+        ms = eng.event_elapsed_ms(0, 1)  # kernels + exchange pushes + flag waits on this rank's stream
+    launches = E.launch_count() - launches0
+    if eng.comm_error():
+        raise SystemExit(f"[rank {rk.rank}] a device-side wait timed out: the exchange schedule is broken")
+    visited = d.block_nnz(warmup * P, (warmup + steps) * P)[rk.rank]
+    ms_max = rk.max(ms)
+    per_rank = rk.gather(int(visited))
+    total = int(sum(per_rank))
+    rmse = rmse_curve[-1] if curve else val_rmse()
+    out = {"plan": plan, "ms_per_step": ms_max / steps, "value": total / (ms_max * 1e-3), "val_rmse": rmse,
+           "ratings_visited": total, "ratings_visited_per_rank": per_rank, "ms_this_rank": ms, "launches": int(launches),
+           "epochs": warmup + steps}
+    if curve:
+        out["val_rmse_curve"] = rmse_curve
+    d.close()
+    return out
 
 
-def solver_timings(prob, device_index, peak_gbs):
-    """The other trainers of the path on the same matrix (BASELINE.json: 'ALS epoch sec'):
-    ALS at rank 64 and 128, CCD++ (FreqAdap) at rank 64 and the objective pass, CUDA events, one GPU."""
+def solver_timings(prob, rk, peak_gbs, ranks=(64, 128), ccd=True, objective=True, shape_name="netflix"):
+    """The other trainers of the path on the same matrix (BASELINE.json: 'ALS epoch sec'): ALS at rank 64
+    and 128, CCD++ (FreqAdap) at rank 64 and the objective pass.  CUDA events, max over ranks; at N > 1 rows are sharded in
+    contiguous ranges of equal rating counts and the kernels store their output rows into all peers (csrc/comm.cu)."""
     from matfac_b200 import engine as E
     n_users, n_items = prob["n_users"], prob["n_items"]
     ptr, ind, val = prob["train"]
     nnz = int(ptr[-1])
     tr = Mat(n_users, n_items, prob["train"])
-    bad_u = (np.diff(ptr) == 0).astype(np.uint8)
-    cnt_i = np.bincount(ind, minlength=n_items)
+    bad_u, bad_i, cnt_i = masks_of(prob)
     out = {}
-    for r in (64, 128):
-        rng = np.random.default_rng(1)
-        eng = E.Engine(n_users, n_items, r, device=device_index)
+    for r in ranks:
+        U0, V0 = init_factors(n_users, n_items, r)
+        eng = E.Engine(n_users, n_items, r, device=rk.local)
         eng.upload_csr(E.TRAIN, tr, with_csc=False)
         eng.build_csc(E.TRAIN)  # gk_csr_CreateIndex on the device
-        eng.set_masks(bad_u, (cnt_i == 0).astype(np.uint8))
+        eng.set_masks(bad_u, bad_i)
         eng.set_aux(E.MF, np.diff(ptr).astype(np.int32), cnt_i.astype(np.int32))
-        eng.upload_factors(rng.uniform(-0.01, 0.01, (n_users, r)).astype(np.float32),
-                           rng.uniform(-0.01, 0.01, (n_items, r)).astype(np.float32))
-        eng.als_half_step(E.USER, 0.1)
-        eng.als_half_step(E.ITEM, 0.1)  # warm-up epoch: plans are built here
-        ms = []
-        for _ in range(2):
-            eng.event_record(0)
+        eng.upload_factors(U0, V0)
+        if rk.world > 1:
+            eng.comm_connect(rk.gather(eng.comm_init(rk.rank, rk.world)))
+            colptr = np.zeros(n_items + 1, np.int64)
+            np.cumsum(cnt_i, out=colptr[1:])
+            ucut = np.searchsorted(ptr, np.linspace(0, nnz, rk.world + 1)).astype(int)
+            icut = np.searchsorted(colptr, np.linspace(0, nnz, rk.world + 1)).astype(int)
+            ucut[0] = icut[0] = 0
+            ucut[-1], icut[-1] = n_users, n_items
+            eng.set_row_range(E.USER, int(ucut[rk.rank]), int(ucut[rk.rank + 1]))
+            eng.set_row_range(E.ITEM, int(icut[rk.rank]), int(icut[rk.rank + 1]))
+
+        def timed(fn, reps):
+            ms = []
+            for _ in range(reps):
+                eng.sync()
+                rk.barrier()
+                eng.event_record(0)
+                fn()
+                eng.event_record(1)
+                ms.append(eng.event_elapsed_ms(0, 1))
+            return rk.max(float(np.median(ms)))
+
+        def als_epoch():
             eng.als_half_step(E.USER, 0.1)
             eng.als_half_step(E.ITEM, 0.1)
-            eng.event_record(1)
-            ms.append(eng.event_elapsed_ms(0, 1))
-        m = float(np.median(ms))
+
+        als_epoch()  # warm-up epoch: plans are built here
+        m = timed(als_epoch, 2)
         out[f"als_rank{r}"] = {"epoch_ms": m, "epoch_sec": m * 1e-3, "gram_tflops_algorithmic": 4.0 * r * r * nnz / (m * 1e-3) / 1e12,
-                               "gather_gbs": 2.0 * nnz * r * 4 / (m * 1e-3) / 1e9,
-                               "gram": "tcgen05 kind::tf32 x3 split, fp32 TMEM accumulator" if r > 64 else "fp32 FMA register tiles"}
-        if r == 64:
-            eng.upload_factors(rng.uniform(-0.01, 0.01, (n_users, r)).astype(np.float32),
-                               rng.uniform(-0.01, 0.01, (n_items, r)).astype(np.float32))
+                               "gather_gbs": 2.0 * nnz * r * 4 / (m * 1e-3) / 1e9, "gather_bound_ms": 2.0 * nnz * r * 4 / (peak_gbs * 1e9) * 1e3 / rk.world,
+                               "gram": "tcgen05 kind::tf32 x3 split, fp32 TMEM accumulator"}
+        if r == 64 and ccd:
+            eng.upload_factors(U0, V0)
             eng.ccdpp_begin()
             for k in range(4):
                 eng.ccdpp_rank1(k, True, 5, 0.05, 0.05, 75)
-            eng.event_record(0)
-            for k in range(8):
-                eng.ccdpp_rank1(k, False, 5, 0.05, 0.05, 75)
-            eng.event_record(1)
-            mk = eng.event_elapsed_ms(0, 1) / 8
+
+            def ccd_steps():
+                for k in range(8):
+                    eng.ccdpp_rank1(k, False, 5, 0.05, 0.05, 75)
+
+            mk = timed(ccd_steps, 1) / 8
             eng.ccdpp_end()
             gbs = 128.0 * nnz / (mk * 1e-3) / 1e9
-            out["ccdpp_rank64"] = {"ms_per_rank_one_step": mk, "epoch_ms": mk * r, "algorithmic_gbs": gbs, "frac_of_hbm": gbs / peak_gbs,
-                                   "what": "trainCCDPPFreqAdap k-loop body, 128 B per rating per rank-one step (SURVEY 8d)"}
-            for _ in range(2):
+            out["ccdpp_rank64"] = {"ms_per_rank_one_step": mk, "epoch_ms": mk * r, "algorithmic_gbs": gbs,
+                                   "frac_of_hbm": gbs / (peak_gbs * rk.world),
+                                   "what": "trainCCDPPFreqAdap k-loop body, 128 B per rating per rank-one step (SURVEY 8d); "
+                                           "frac_of_hbm is against N x the measured HBM bandwidth"}
+        if r == 64 and objective:
+            def obj():
                 eng.eval(E.TRAIN, E.CURRENT, E.MF, False, True)
-            eng.event_record(0)
-            for _ in range(3):
-                eng.eval(E.TRAIN, E.CURRENT, E.MF, False, True)
-            eng.event_record(1)
-            me = eng.event_elapsed_ms(0, 1) / 3
+            obj(); obj()
+            me = timed(obj, 3)
             out["objective_rank64"] = {"ms_per_pass": me, "algorithmic_gbs": (8.0 + 8.0 * r) * nnz / (me * 1e-3) / 1e9,
                                        "what": "objective + norms over the train matrix, 8 + 8r B per rating; u is reused from registers"}
+        if rk.world > 1:
+            eng.sync()
+            rk.barrier()
+            eng.comm_disconnect()
+            rk.barrier()
         eng.close()
     return out
 
 
+def yahoo_block(rk, peak_gbs, scale, epochs=4):
+    """BASELINE.json configs[4]: Yahoo-R1-shaped matrix (1 M x 625 k, 250 M ratings), rank 64.  U + V = 416 MB do not fit
+    the 126 MB L2: this is the shape on which the HBM roofline binds.  N = 1: shuffled SGD epoch, CCD++ step, objective;
+    N > 1: DSGD (reference plan) epoch and row-sharded CCD++ step."""
+    import torch
+    from matfac_b200 import engine as E
+    t0 = time.time()
+    prob = make_problem(YAHOO_SHAPE, scale, f"cuda:{rk.local}")
+    torch.cuda.empty_cache()
+    n_users, n_items = prob["n_users"], prob["n_items"]
+    nnz = int(prob["train"][0][-1])
+    crcs = rk.gather(prob["crc"])
+    out = {"workload": "modelMF rank 64, Yahoo-R1-shaped synthetic ratings (BASELINE.json configs[4])", "n_users": n_users,
+           "n_items": n_items, "train_nnz": nnz, "matrix_crc": prob["crc"], "same_matrix_on_all_ranks": len(set(crcs)) == 1,
+           "gen_s": time.time() - t0, "factor_bytes": 4 * RANK * (n_users + n_items)}
+    if rk.world == 1:
+        bad_u, bad_i, _ = masks_of(prob)
+        U0, V0 = init_factors(n_users, n_items, RANK)
+        eng = E.Engine(n_users, n_items, RANK, device=rk.local)
+        eng.upload_csr(E.TRAIN, Mat(n_users, n_items, prob["train"]), with_csc=False)
+        eng.upload_csr(E.VAL, Mat(n_users, n_items, prob["val"]), with_csc=False)
+        eng.set_masks(bad_u, bad_i)
+        eng.upload_factors(U0, V0)
+        eng.sgd_plan(1)
+        for ep in range(2):
+            eng.sgd_epoch_flat(E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, ep)
+        eng.sync()
+        eng.event_record(0)
+        for ep in range(epochs):
+            eng.sgd_epoch_flat(E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, 2 + ep)
+        eng.event_record(1)
+        ms = eng.event_elapsed_ms(0, 1) / epochs
+        alg = (16 * RANK + 12) * float(nnz) / (ms * 1e-3) / 1e9
+        prof = committed_profile("r2_ncu_traffic.json").get("yahoo_sgd_epoch", {})
+        out["sgd"] = {"ms_per_epoch": ms, "value": nnz / (ms * 1e-3), "unit": "rating-updates/s", "val_rmse": eng.rmse(E.VAL),
+                      "epochs": 2 + epochs,
+                      "roofline": {"bound": "hbm", "achieved": alg, "peak": peak_gbs, "unit": "GB/s", "frac": alg / peak_gbs,
+                                   "traffic": prof.get("dram_bytes"), "traffic_source": prof.get("source"),
+                                   "algorithmic_bytes_per_update": 16 * RANK + 12}}
+        eng.close()
+        del eng
+    else:
+        d = run_dsgd(prob, rk, RANK, "reference", 2, epochs)
+        out["dsgd"] = d
+    torch.cuda.empty_cache()
+    out["solvers"] = solver_timings(prob, rk, peak_gbs, ranks=(64,), objective=(rk.world == 1), shape_name="yahoo")
+    bound_ms = 128.0 * nnz / (peak_gbs * 1e9) * 1e3 / rk.world
+    if "ccdpp_rank64" in out["solvers"]:
+        out["solvers"]["ccdpp_rank64"]["hbm_bound_ms_per_step"] = bound_ms
+    return out
+
+
+def oracle_check(rk, epochs=10, scale=0.05):
+    """N > 1, outside every timed region: the DSGD path of this run (reference plan, N ranks over peer memory) next to the
+    ORACLE's trainSGDPar with P = N threads on the 1/20-scale bench matrix — same seed, hence the same partitions and
+    update sequences (tests/test_host.py pins the host plan bit for bit), same initial factors (the oracle's).  The oracle
+    is the checker here, nothing of it is timed or shipped."""
+    import torch
+    prob = make_problem(SHAPE, scale, f"cuda:{rk.local}")
+    n_users, n_items = prob["n_users"], prob["n_items"]
+    U0 = torch.zeros(n_users, RANK, dtype=torch.float32, device="cuda")
+    V0 = torch.zeros(n_items, RANK, dtype=torch.float32, device="cuda")
+    ref_curve, ref_s = None, None
+    if rk.rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as ol
+        from matfac_b200 import synth
+        tr = synth.Csr(n_users, n_items, *prob["train"])
+        va = synth.Csr(n_users, n_items, *prob["val"])
+        od = ol.OracleData(tr, va, va)
+        om = ol.OracleModel(od, algo="mf", facdim=RANK, maxiter=epochs, seed=1, nthreads=rk.world, ureg=HP["ureg"],
+                            ireg=HP["ireg"], learnrate=HP["lr"])
+        u0, v0 = om.factors()
+        U0.copy_(torch.from_numpy(u0)); V0.copy_(torch.from_numpy(v0))
+    rk.dist.broadcast(U0, 0)
+    rk.dist.broadcast(V0, 0)
+    dev = run_dsgd(prob, rk, RANK, "reference", 0, epochs, seed=1, curve=True, U0V0=(U0.cpu().numpy(), V0.cpu().numpy()),
+                   options={"sgd_flat_inflight_frac": 2e-4})
+    if rk.rank == 0:
+        t0 = time.time()
+        om.train("sgdpar", keep_history=True)
+        ref_curve = [h[3] for h in om.history()]
+        ref_s = time.time() - t0
+    rk.barrier()
+    if rk.rank != 0:
+        return None
+    last = min(len(ref_curve), len(dev["val_rmse_curve"]))
+    rel = [abs(a - b) / b for a, b in zip(dev["val_rmse_curve"][:last], ref_curve[:last])]
+    return {"what": f"DSGD at {rk.world} ranks vs oracle trainSGDPar P={rk.world}: 1/20-scale matrix, reference partitions + "
+                    "sgdUpdateBlockSeq sequences (seed 1), oracle initial factors; validation RMSE after every epoch",
+            "matrix_crc": prob["crc"], "train_nnz": int(prob["train"][0][-1]), "device_val_rmse": dev["val_rmse_curve"],
+            "oracle_val_rmse": ref_curve, "rel_diff": rel, "oracle_seconds": ref_s,
+            "oracle_seed_spread_note": "profiles/r2_dsgd_oracle_curves.json: the oracle's own curves for seeds 1, 2 and P = 1..8"}
+
+
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_arm(prob, steps, warmup, sample_users=None):
-    """Times the reference's OpenMP stratified SGD (ModelMF::trainSGDPar) on the first
-    `sample_users` users of the workload with every host core.  Uses oracle/_ref/mf_ref (the
-    reference's own code) when present, else the oracle port."""
+def cpu_reference_arm(prob, sample_users=None, epochs=4):
+    """Times the reference's OpenMP stratified SGD (ModelMF::trainSGDPar) on the first `sample_users` users of the
+    workload with every host core: `epochs` epochs, the first is warm-up, the value is the median of the rest
+    (median of steady epochs).  Uses oracle/_ref/mf_ref (the reference's own code) when present, else
+    the oracle port.  The sample holds ~4 % of the ratings: the figure is the sample's throughput, i.e. an
+    EXTRAPOLATION to the full matrix (whose U does not stay in the CPU's caches)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as ol
     from matfac_b200 import synth
@@ -367,39 +510,39 @@ def cpu_reference_arm(prob, steps, warmup, sample_users=None):
     vptr, vind, vval = prob["val"]
     vn = int(vptr[sample_users])
     va = synth.Csr(sample_users, n_items, vptr[: sample_users + 1].copy(), vind[:vn], vval[:vn])
-    epochs = max(1, min(steps, 2))
-    sample = f"first {sample_users} users ({nnz_s} ratings) of the workload, trainSGDPar P={cores}, {epochs} epoch(s)"
-    kind = "port"
-    secs = None
+    kind, secs = "port", None
+    what = f"first {sample_users} users ({nnz_s} ratings = {100.0 * nnz_s / int(ptr[-1]):.1f} % of the workload, extrapolated)"
     if ol.have_ref():
         try:
             d = tempfile.mkdtemp(prefix="mfref_")
             files = synth.write_split_files(d, tr, va, va)
             res = ol.run_ref(files, os.path.join(d, "dump"), algo="mf", method="sgdpar", threads=cores, timeout=900,
-                             facdim=RANK, maxiter=1, seed=1, ureg=HP["ureg"], ireg=HP["ireg"], learnrate=HP["lr"])
-            for line in res["stdout"].splitlines():
-                if "subIterDuration:" in line:
-                    secs = float(line.split("subIterDuration:")[1].split()[0])
+                             facdim=RANK, maxiter=epochs, seed=1, ureg=HP["ureg"], ireg=HP["ireg"], learnrate=HP["lr"])
+            secs = [float(line.split("subIterDuration:")[1].split()[0]) for line in res["stdout"].splitlines()
+                    if "subIterDuration:" in line]
             kind = "reference"
-            epochs = 1
-            sample = f"first {sample_users} users ({nnz_s} ratings) of the workload, mf_ref --mf_method sgdpar, OMP_NUM_THREADS={cores}, epoch 0"
+            sample = f"{what}, mf_ref --mf_method sgdpar, OMP_NUM_THREADS={cores}, median of epochs 1..{len(secs) - 1} of {len(secs)}"
         except Exception as ex:  # fall back to the port
             log("mf_ref failed, using the oracle port:", repr(ex)[:200])
             secs = None
     od = ol.OracleData(tr, va, va)
     om = ol.OracleModel(od, algo="mf", facdim=RANK, maxiter=epochs, seed=1, nthreads=cores, ureg=HP["ureg"],
                         ireg=HP["ireg"], learnrate=HP["lr"])
-    # ratings visited in an epoch of trainSGDPar: P schedules drawn with replacement (util.cpp:1077)
+    # ratings visited per epoch of trainSGDPar: P update sequences drawn with replacement (util.cpp:1077)
     up, ip, sched = om.dsgd_plan(cores, epochs * cores)
     users = np.repeat(np.arange(sample_users), np.diff(tr.rowptr))
     bid = up[users].astype(np.int64) * cores + ip[tr.rowind]
     blk = np.bincount(bid, minlength=cores * cores)
-    visited = sum(int(blk[a * cores + b]) for s in range(epochs * cores) for a, b in sched[s])
-    if secs is None:
+    visited = [sum(int(blk[a * cores + b]) for s in range(e * cores, (e + 1) * cores) for a, b in sched[s]) for e in range(epochs)]
+    if not secs:
         om.train("sgdpar")
-        secs = float(np.sum(om.epoch_seconds()))
-    value = visited / secs
-    return dict(value=value, unit="rating-updates/s", cores=cores, kind=kind, sample=sample), secs / epochs * 1e3
+        secs = [float(x) for x in om.epoch_seconds()]
+        sample = f"{what}, oracle port of trainSGDPar, P={cores}, median of epochs 1..{len(secs) - 1} of {len(secs)}"
+    n = min(len(secs), len(visited))
+    rates = [visited[e] / secs[e] for e in range(1 if n > 1 else 0, n)]
+    value = float(np.median(rates))
+    ms = float(np.median(secs[1:] if len(secs) > 1 else secs)) * 1e3
+    return dict(value=value, unit="rating-updates/s", cores=cores, kind=kind, sample=sample, extrapolated=True), ms
 
 
 # ---------------------------------------------------------------------------------------------
@@ -423,25 +566,28 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-solvers", action="store_true", help="skip the ALS / CCD++ / objective timings")
+    ap.add_argument("--no-yahoo", action="store_true", help="skip the Yahoo-R1-shaped block (BASELINE.json configs[4])")
+    ap.add_argument("--no-oracle-check", action="store_true", help="N > 1: skip the DSGD-vs-oracle RMSE check")
+    ap.add_argument("--dsgd-plan", default="reference", choices=["reference", "balanced"],
+                    help="N > 1: the plan `value` is measured on (the other one is reported next to it)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    n_users, n_items, nnz = (int(SHAPE[0] * args.scale), int(SHAPE[1] * max(args.scale, 0.05) if args.scale < 1 else SHAPE[1]),
-                             int(SHAPE[2] * args.scale))
-    config = {"workload": "modelMF SGD rank 64, Netflix-shaped synthetic ratings (BASELINE.json configs[1])",
-              "n_users": n_users, "n_items": n_items, "rank": RANK, "learnrate": HP["lr"], "ureg": HP["ureg"],
-              "ireg": HP["ireg"], "l2": "inputs larger than L2 (ratings 0.8 GB + U 123 MB), no flush"}
 
     import torch
     have_cuda = torch.cuda.is_available()
+    config = {"workload": "modelMF SGD rank 64, Netflix-shaped synthetic ratings (BASELINE.json configs[1])",
+              "rank": RANK, "learnrate": HP["lr"], "ureg": HP["ureg"], "ireg": HP["ireg"], "data_seed": DATA_SEED,
+              "l2": "inputs larger than L2 (ratings 0.8 GB + U 123 MB), no flush"}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        prob = gen_problem(n_users, n_items, nnz, 20260102, "cuda" if have_cuda else "cpu")
-        cb, ms = cpu_reference_arm(prob, args.steps, args.warmup)
-        config["train_nnz"] = int(prob["train"][0][-1])
+        prob = make_problem(SHAPE, args.scale, f"cuda:{local_rank}" if have_cuda else "cpu")
+        cb, ms = cpu_reference_arm(prob, epochs=max(2, min(args.steps + 1, 4)))
+        config.update(n_users=prob["n_users"], n_items=prob["n_items"], train_nnz=int(prob["train"][0][-1]), matrix_crc=prob["crc"],
+                      same_matrix_on_all_ranks=True)
         line = {"impl": "reference", "metric": "sgd_rating_updates_per_sec", "value": cb["value"], "unit": "rating-updates/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -458,255 +604,222 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rk = Ranks(dist, rank, world, local_rank)
 
     t0 = time.time()
-    if world > 1:
-        prob = shared_problem(n_users, n_items, nnz, 20260102, rank, dist, f"cuda:{local_rank}")
-    else:
-        prob = gen_problem(n_users, n_items, nnz, 20260102, f"cuda:{local_rank}")
+    prob = make_problem(SHAPE, args.scale, f"cuda:{local_rank}")  # every rank generates the same matrix (checked below)
+    torch.cuda.empty_cache()
+    n_users, n_items = prob["n_users"], prob["n_items"]
     ptr, ind, val = prob["train"]
     train_nnz = int(ptr[-1])
-    config["train_nnz"] = train_nnz
-    log(f"[rank {rank}] data: {train_nnz} train ratings, max user degree {int(np.diff(ptr).max())}, gen {time.time()-t0:.1f}s")
-    torch.cuda.empty_cache()
+    crcs = rk.gather(prob["crc"])
+    config.update(n_users=n_users, n_items=n_items, train_nnz=train_nnz, matrix_crc=prob["crc"],
+                  same_matrix_on_all_ranks=len(set(crcs)) == 1)
+    if len(set(crcs)) != 1:
+        raise SystemExit(f"bench.py: the ranks generated different matrices: {crcs}")
+    log(f"[rank {rank}] data: {train_nnz} train ratings, crc {prob['crc']}, max user degree {int(np.diff(ptr).max())}, gen {time.time()-t0:.1f}s")
+    peak, peak_src = measured_hbm_gbs()
 
-    rng = np.random.default_rng(1)
-    U0 = rng.uniform(-0.01, 0.01, size=(n_users, RANK)).astype(np.float32)
-    V0 = rng.uniform(-0.01, 0.01, size=(n_items, RANK)).astype(np.float32)
-    tr = Mat(n_users, n_items, prob["train"])
-    va = Mat(n_users, n_items, prob["val"])
-    bad_u = (np.diff(ptr) == 0).astype(np.uint8)
-    bad_i = (np.bincount(ind, minlength=n_items) == 0).astype(np.uint8)
-
-    eng = E.Engine(n_users, n_items, RANK, device=local_rank)
-    P = world
+    U0, V0 = init_factors(n_users, n_items, RANK)
+    bad_u, bad_i, _ = masks_of(prob)
+    extra = {}
     if world == 1:
+        tr = Mat(n_users, n_items, prob["train"])
+        va = Mat(n_users, n_items, prob["val"])
+        eng = E.Engine(n_users, n_items, RANK, device=local_rank)
         eng.upload_csr(E.TRAIN, tr, with_csc=False)
         eng.upload_csr(E.VAL, va, with_csc=False)
         eng.set_masks(bad_u, bad_i)
         eng.upload_factors(U0, V0)
+        eng.set_option("sgd_shuffle_seed", 1)
         eng.sgd_plan(1)
-        sched_blocks = [np.array([[0, 0]], np.int32)]
-        my_nnz_per_epoch = train_nnz
-    else:
-        # DSGD: user stratum g pinned to rank g (only its CSR rows are uploaded), P = N item
-        # blocks; after every sub-epoch the updated item block is stored straight into the next owner's V
-        # over NVLink by a kernel and ordered by device-side sequence flags (matfac_b200/csrc/comm.cu)
-        from matfac_b200 import dsgd
-        user_part = dsgd.balanced_partition(np.diff(ptr), P)
-        item_part = dsgd.balanced_partition(np.bincount(ind, minlength=n_items), P)
-        mine = user_part == rank
-
-        def local_rows(t):
-            p_, i_, v_ = t
-            rows = np.repeat(mine, np.diff(p_))
-            lptr = np.zeros(n_users + 1, np.int64)
-            np.cumsum(np.where(mine, np.diff(p_), 0), out=lptr[1:])
-            return Mat(n_users, n_items, (lptr, i_[rows], v_[rows]))
-
-        ltr, lva = local_rows(prob["train"]), local_rows(prob["val"])
-        eng.upload_csr(E.TRAIN, ltr, with_csc=False)
-        eng.upload_csr(E.VAL, lva, with_csc=False)
-        eng.set_masks(bad_u, bad_i)
-        eng.upload_factors(U0, V0)
-        # in-flight budget of the shuffled kernel per rank: 8e-4 of the rank's ratings (default 2e-4, calibrated for the
-        # first epochs of small matrices).  tools/dsgd_sweep.py on this matrix, 8 x 8 strata: validation RMSE after 10
-        # epochs 0.5348 at 8e-4 against 0.5321 at 2e-4, epoch 3.5 ms against 6.9 ms (profiles/r1_dsgd_scaling.md)
-        eng.set_option("sgd_flat_inflight_frac", 8e-4)
-        eng.sgd_plan(P, np.where(mine, user_part, -1).astype(np.int32), item_part)
-        eng.set_option("sgd_block_order", 1)  # shuffled inside the blocks: full concurrency
-        blobs = [None] * world
-        dist.all_gather_object(blobs, eng.comm_init(rank, world))
-        eng.comm_connect(blobs)
-        my_nnz_per_epoch = int(ltr.rowptr[-1])
-        sched = dsgd.rotation_schedule(P, (args.warmup + args.steps) * P + 1)
-        transport = dsgd.EngineTransport(eng, rank)
-
-    def epoch(ep):
-        if world == 1:
-            eng.sgd_epoch_flat(E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, ep)
-            return
-        dsgd.run_steps(sched, ep * P, (ep + 1) * P, rank, transport,
-                       lambda block, t: eng.sgd_subepoch(np.array([[rank, block]], np.int32), E.MF, HP["lr"], HP["ureg"],
-                                                         HP["ireg"], 1, t))
-
-    def barrier():
-        if dist is not None:
-            eng.comm_barrier()
+        for w in range(args.warmup):
+            eng.sgd_epoch_flat(E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, w)
         eng.sync()
         torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-
-    for w in range(args.warmup):
-        epoch(w)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+        sampler = ClockSampler(local_rank)
         sampler.start()
-    launches0 = E.launch_count()
-    eng.event_record(0)
-    for k in range(args.steps):
-        epoch(args.warmup + k)
-    eng.event_record(1)
-    barrier()
-    ms_dev = eng.event_elapsed_ms(0, 1)  # CUDA events on the engine's stream: kernels + exchange + waits
-    launches = E.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    ms_total = ms_dev
-    total_nnz = my_nnz_per_epoch
-    nnz_per_rank = [my_nnz_per_epoch]
-    if dist is not None:
-        if eng.comm_error():
-            raise SystemExit(f"[rank {rank}] a device-side wait timed out: the exchange schedule is broken")
-        t = torch.tensor([ms_total, float(my_nnz_per_epoch)], dtype=torch.float64, device="cuda")
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms_total = float(tmax[0])
-        total_nnz = int(tsum[1])
-        allnnz = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
-        dist.all_gather(allnnz, t[1:2].clone())
-        nnz_per_rank = [int(x.item()) for x in allnnz]
-        # every rank publishes the item block it holds, then evaluates its own users' validation rows
-        dsgd.publish(sched, (args.warmup + args.steps) * P - 1, rank, transport)
-    ms_per_step = ms_total / args.steps
-    value = total_nnz / (ms_per_step * 1e-3)
-    ev = eng.eval(E.VAL)
-    if dist is not None:
-        t = torch.tensor([ev[0], ev[1]], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        ev = [float(t[0]), float(t[1])]
-        eng.comm_barrier()
-    val_rmse = float(np.sqrt(ev[0] / ev[1])) if ev[1] > 0 else float("nan")
+        launches0 = E.launch_count()
+        eng.event_record(0)
+        for k in range(args.steps):
+            eng.sgd_epoch_flat(E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, args.warmup + k)
+        eng.event_record(1)
+        eng.sync()
+        torch.cuda.synchronize()
+        ms_dev = eng.event_elapsed_ms(0, 1)
+        launches = E.launch_count() - launches0
+        clocks = sampler.stop()
+        ms_per_step = ms_dev / args.steps
+        value = train_nnz / (ms_per_step * 1e-3)
+        val_rmse = eng.rmse(E.VAL)
+        my_nnz_per_epoch = train_nnz
+        kernel_name = "sgd_flat_kernel<16,1,MF> + sgd_hot_kernel<4,4,MF> (hot item rows, concurrent stream)"
+    else:
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        main_plan = args.dsgd_plan
+        d = run_dsgd(prob, rk, RANK, main_plan, args.warmup, args.steps)
+        clocks = sampler.stop() if rank == 0 else None
+        ms_per_step, value, val_rmse, launches = d["ms_per_step"], d["value"], d["val_rmse"], d["launches"]
+        ms_dev = d["ms_this_rank"]
+        my_nnz_per_epoch = d["ratings_visited_per_rank"][rank] / args.steps
+        extra["dsgd"] = d
+        other = "balanced" if main_plan == "reference" else "reference"
+        try:
+            extra["dsgd_" + other] = run_dsgd(prob, rk, RANK, other, args.warmup, args.steps)
+        except Exception as ex:
+            extra["dsgd_" + other] = {"error": repr(ex)[:300]}
+        kernel_name = "sgd_flat_kernel<16,1,MF> + sgd_hot_kernel<4,4,MF> per stratum block + comm_push_rows_kernel"
     log(f"[rank {rank}] {ms_per_step:.3f} ms/epoch, {value/1e9:.3f} G updates/s, val RMSE after {args.warmup+args.steps} epochs {val_rmse:.4f}")
 
-    if rank != 0:
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
-        return 0
-
-    # roofline of the SGD update kernel.  N = 1: one launch (or one per user band) per epoch, timed by the
-    # events above.  N > 1: rank 0's share of the algorithmic bytes over the same wall of device time,
-    # which also holds the exchange pushes and flag waits of the sub-epochs.
-    peak, peak_src = measured_hbm_gbs()
+    # roofline of the SGD update kernel.  N = 1: the two kernels of an epoch, timed by the events above.  N > 1: rank 0's
+    # share of the algorithmic bytes over the same span of device time, which also holds the exchange pushes and flag
+    # waits of the sub-epochs.
     alg_bytes = (16 * RANK + 12) * float(my_nnz_per_epoch)
     achieved = alg_bytes * args.steps / (ms_dev * 1e-3) / 1e9
+    traffic = committed_profile("r2_ncu_traffic.json").get("netflix_sgd_epoch", {}) if (world == 1 and args.scale == 1.0) else {}
+    l2p = committed_profile("r2_l2_probe.json")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": DRAM_TRAFFIC_BYTES_PER_EPOCH if world == 1 and args.scale == 1.0 else None, "peak_source": peak_src,
-                "kernel": "sgd_flat_kernel<16,1,MF> + sgd_hot_kernel<4,4,MF> (hot item rows, concurrent stream)",
-                "algorithmic_bytes_per_update": 16 * RANK + 12,
+                "traffic": traffic.get("dram_bytes"), "traffic_source": traffic.get("source"), "peak_source": peak_src,
+                "kernel": kernel_name, "algorithmic_bytes_per_update": 16 * RANK + 12,
                 "launches_per_epoch": launches / args.steps,
                 "note": "achieved = algorithmic bytes (u,v read + reduced, 12 B rating record, SURVEY 8d) of one epoch on this rank / "
-                        "its device time (both kernels of the epoch run concurrently inside the timed region); traffic = "
-                        "dram__bytes_read+write of the two kernels per epoch from the ncu --set full captures in profiles/. "
-                        "U (123 MB) and V (4.5 MB) stay in the 126 MB L2, so DRAM traffic is a tenth of the algorithmic bytes and "
-                        "frac can exceed 1: the epoch is bound by L2 reductions and instruction issue, not by HBM (profiles/r1_sgd_flat.md)"}
+                        "its device time; traffic = dram__bytes_read+write of the epoch's kernels from the committed ncu capture "
+                        "(profiles/r2_ncu_traffic.json).  U (123 MB) + V (4.5 MB) stay in the 126 MB L2 on this shape, so DRAM traffic "
+                        "is a fraction of the algorithmic bytes and frac can exceed 1; the bound that applies is `l2`.  The Yahoo-shaped "
+                        "block (`yahoo.sgd.roofline`) is the same kernel with factors that do not fit L2."}
+    if l2p.get("gather_red_gbs"):
+        # the kernel's own access pattern at the L2: 256 B row gathers (ld.global.cg.v4) + red.global.add.v4 on the same rows
+        roofline["l2"] = {"bound": "l2", "achieved": achieved, "peak": l2p["gather_red_gbs"], "unit": "GB/s",
+                          "frac": achieved / l2p["gather_red_gbs"], "peak_source": "tools/l2_probe.cu on this pod (profiles/r2_l2_probe.json): "
+                          "random 256 B row gather + vector reduction on an L2-resident matrix, algorithmic bytes counted the same way",
+                          "l2_read_gbs": l2p.get("l2_read_gbs"), "red_v4_gbs": l2p.get("red_v4_gbs")}
+
     if world > 1:
-        roofline["per_rank_nnz"] = nnz_per_rank
-
-    # how the epoch was split between the two kernels (diagnostics ABI; outside the timed region)
-    hot_info = None
-    try:
-        if world == 1:
-            _, cold_n, lists = eng.debug_sgd_records(0, 0, with_records=False)
-            st = eng.debug_sgd_hot_batch()
-            hot_info = {"lists": int(len(lists)), "share_of_ratings": 1.0 - cold_n / max(train_nnz, 1),
-                        "longest_list": int(lists[:, 2].max()) if len(lists) else 0, "ratings_per_round": int(st[2]),
-                        "mean_user_norm_sq": float(st[0] / st[1]) if st[1] > 0 else 0.0}
-    except Exception as ex:
-        hot_info = {"error": repr(ex)[:200]}
-
-    # the stratified trainer's kernel (user-major runs, concurrency capped for parity) for the record
-    stratified = None
-    if world == 1:
-        try:
-            P = 8
-            prng = np.random.default_rng(7)
-            eng.sgd_plan(P, prng.integers(0, P, n_users).astype(np.int32), prng.integers(0, P, n_items).astype(np.int32))
-            blocks = [np.stack([np.arange(P), (np.arange(P) + s) % P], 1).astype(np.int32) for s in range(P)]
-            for b in blocks:
-                eng.sgd_subepoch(b, E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, 0)
-            eng.event_record(2)
-            for ep in range(3):
-                for b in blocks:
-                    eng.sgd_subepoch(b, E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, ep + 1)
-            eng.event_record(3)
-            ms_s = eng.event_elapsed_ms(2, 3) / 3
-            stratified = {"P": P, "ms_per_epoch": ms_s, "value": train_nnz / (ms_s * 1e-3), "unit": "rating-updates/s",
-                          "what": "trainSGDPar kernel: user-major runs, hot-item concurrency capped at 8 (parity with the reference's order)"}
-            eng.sgd_plan(1)
-        except Exception as ex:
-            stratified = {"error": repr(ex)[:200]}
-
-    # end-to-end through the C ABI with host buffers
-    e2e = None
-    if world == 1 and args.e2e_steps > 0:
-        h = {}
-        keep = []
-        for name, a in (("ptr", ptr), ("ind", ind), ("val", val), ("U", U0.copy()), ("V", V0.copy())):
-            h[name], t = pinned(a)
-            keep.append(t)
-        Uo = np.empty_like(U0); Vo = np.empty_like(V0)
-        Uo, tU = pinned(Uo); Vo, tV = pinned(Vo)
-        trp = Mat(n_users, n_items, (h["ptr"], h["ind"], h["val"]))
-        h2d = h["ptr"].nbytes + h["ind"].nbytes + h["val"].nbytes + h["U"].nbytes + h["V"].nbytes
-        d2h = Uo.nbytes + Vo.nbytes + 64
-        times, parts = [], []
-        for s in range(args.e2e_steps + 1):
-            eng.sync()
-            t1 = time.perf_counter()
-            eng.upload_csr(E.TRAIN, trp, with_csc=False)
-            eng.upload_factors(h["U"], h["V"])
-            t2 = time.perf_counter()
-            eng.sgd_plan(1)
-            t3 = time.perf_counter()
-            eng.sgd_epoch_flat(E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, s)
-            obj = eng.eval(E.TRAIN, E.CURRENT, E.MF, False, True)
-            vr = eng.eval(E.VAL)
-            t4 = time.perf_counter()
-            eng.L.mfb_download_factors(eng.h, E.CURRENT, Uo.ctypes.data, RANK, Vo.ctypes.data, RANK)
-            eng.sync()
-            t5 = time.perf_counter()
-            times.append(t5 - t1)
-            parts.append([t2 - t1, t3 - t2, t4 - t3, t5 - t4])
-        t_e2e = float(np.median(times[1:]))
-        pm = np.median(np.array(parts[1:]), axis=0) * 1e3
-        e2e = {"value": train_nnz / t_e2e, "unit": "rating-updates/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e * 1e3,
-               "ms_breakdown": {"upload": float(pm[0]), "plan": float(pm[1]), "epoch_and_eval": float(pm[2]), "download": float(pm[3])},
-               "what": "per step: upload CSR + factors from pinned host memory, plan, 1 epoch, objective + val RMSE, download factors"}
-
-    cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
-        try:
-            cpu_baseline, _ = cpu_reference_arm(prob, 1, 0)
-        except Exception as ex:
-            cpu_baseline = {"value": None, "unit": "rating-updates/s", "cores": os.cpu_count(), "kind": "port",
-                            "sample": "failed: " + repr(ex)[:200]}
+        roofline["per_rank_nnz_per_epoch"] = [x / args.steps for x in extra["dsgd"]["ratings_visited_per_rank"]]
 
     line = {"metric": "sgd_rating_updates_per_sec", "value": value, "unit": "rating-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "val_rmse": val_rmse}
-    if e2e:
-        line["e2e"] = e2e
-    if cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline
-    if hot_info:
-        line["sgd_hot_rows"] = hot_info
-    if stratified:
-        line["stratified"] = stratified
-    if world == 1 and not args.no_solvers:
+    line.update(extra)
+
+    if world == 1:
+        # how the epoch was split between the two kernels (diagnostics ABI; outside the timed region)
         try:
-            eng.close()
-            torch.cuda.empty_cache()
-            line["solvers"] = solver_timings(prob, local_rank, peak)
+            _, cold_n, lists = eng.debug_sgd_records(0, 0, with_records=False)
+            st = eng.debug_sgd_hot_batch()
+            line["sgd_hot_rows"] = {"lists": int(len(lists)), "share_of_ratings": 1.0 - cold_n / max(train_nnz, 1),
+                                    "longest_list": int(lists[:, 2].max()) if len(lists) else 0, "ratings_per_round": int(st[2]),
+                                    "mean_user_norm_sq": float(st[0] / st[1]) if st[1] > 0 else 0.0}
+        except Exception as ex:
+            line["sgd_hot_rows"] = {"error": repr(ex)[:200]}
+
+        # the stratified trainer's kernel in the reference's visiting order (user-major runs), reference plan, P = 8
+        try:
+            from matfac_b200 import dsgd
+            P = 8
+            up, ip, sched = dsgd.reference_plan(n_users, n_items, bad_u, bad_i, 1, P, 4 * P)
+            eng.sgd_plan(P, up, ip)
+
+            def sub(t):
+                blocks = np.stack([np.arange(P), sched[t]], 1).astype(np.int32)
+                eng.sgd_subepoch(blocks, E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, t)
+            for t in range(P):
+                sub(t)
+            eng.event_record(2)
+            for t in range(P, 4 * P):
+                sub(t)
+            eng.event_record(3)
+            ms_s = eng.event_elapsed_ms(2, 3) / 3
+            visited = sum(eng.sgd_block_nnz(np.stack([np.arange(P), sched[t]], 1).astype(np.int32)) for t in range(P, 4 * P)) / 3
+            line["stratified"] = {"P": P, "ms_per_epoch": ms_s, "value": visited / (ms_s * 1e-3), "unit": "rating-updates/s",
+                                  "what": "trainSGDPar on one GPU: reference partitions + update sequences, user-major runs, "
+                                          "hot-item concurrency capped at 8 (the reference's visiting order)"}
+            eng.sgd_plan(1)
+        except Exception as ex:
+            line["stratified"] = {"error": repr(ex)[:200]}
+
+        # end-to-end through the C ABI with host buffers
+        if args.e2e_steps > 0:
+            h, keep = {}, []
+            for name, a in (("ptr", ptr), ("ind", ind), ("val", val), ("U", U0.copy()), ("V", V0.copy())):
+                h[name], t = pinned(a)
+                keep.append(t)
+            Uo, tU = pinned(np.empty_like(U0))
+            Vo, tV = pinned(np.empty_like(V0))
+            trp = Mat(n_users, n_items, (h["ptr"], h["ind"], h["val"]))
+            h2d = h["ptr"].nbytes + h["ind"].nbytes + h["val"].nbytes + h["U"].nbytes + h["V"].nbytes
+            d2h = Uo.nbytes + Vo.nbytes + 64
+            times, parts = [], []
+            for s in range(args.e2e_steps + 1):
+                eng.sync()
+                t1 = time.perf_counter()
+                eng.upload_csr(E.TRAIN, trp, with_csc=False)
+                eng.upload_factors(h["U"], h["V"])
+                t2 = time.perf_counter()
+                eng.sgd_plan(1)
+                t3 = time.perf_counter()
+                eng.sgd_epoch_flat(E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, s)
+                eng.eval(E.TRAIN, E.CURRENT, E.MF, False, True)
+                eng.eval(E.VAL)
+                t4 = time.perf_counter()
+                eng.L.mfb_download_factors(eng.h, E.CURRENT, Uo.ctypes.data, RANK, Vo.ctypes.data, RANK)
+                eng.sync()
+                t5 = time.perf_counter()
+                times.append(t5 - t1)
+                parts.append([t2 - t1, t3 - t2, t4 - t3, t5 - t4])
+            t_e2e = float(np.median(times[1:]))
+            pm = np.median(np.array(parts[1:]), axis=0) * 1e3
+            line["e2e"] = {"value": train_nnz / t_e2e, "unit": "rating-updates/s", "h2d_bytes_per_step": int(h2d),
+                           "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e * 1e3,
+                           "ms_breakdown": {"upload": float(pm[0]), "plan": float(pm[1]), "epoch_and_eval": float(pm[2]), "download": float(pm[3])},
+                           "what": "per step: upload CSR + factors from pinned host memory, plan, 1 epoch, objective + val RMSE, download factors"}
+            del keep, tU, tV
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+
+        if not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"], _ = cpu_reference_arm(prob)
+            except Exception as ex:
+                line["cpu_baseline"] = {"value": None, "unit": "rating-updates/s", "cores": os.cpu_count(), "kind": "port",
+                                        "sample": "failed: " + repr(ex)[:200]}
+
+    if not args.no_solvers:
+        try:
+            s = solver_timings(prob, rk, peak)
+            if rank == 0:
+                line["solvers"] = s
         except Exception as ex:
             line["solvers"] = {"error": repr(ex)[:300]}
-    print(json.dumps(line), file=real_stdout, flush=True)
+    if world > 1 and not args.no_oracle_check:
+        try:
+            oc = oracle_check(rk)
+            if rank == 0:
+                line["oracle_check"] = oc
+        except Exception as ex:
+            line["oracle_check"] = {"error": repr(ex)[:300]}
+    del prob
+    torch.cuda.empty_cache()
+    if not args.no_yahoo and args.scale == 1.0:
+        try:
+            y = yahoo_block(rk, peak, 1.0)
+            if rank == 0:
+                line["yahoo"] = y
+        except Exception as ex:
+            line["yahoo"] = {"error": repr(ex)[:300]}
+    elif not args.no_yahoo:
+        try:
+            y = yahoo_block(rk, peak, args.scale)
+            if rank == 0:
+                line["yahoo"] = y
+        except Exception as ex:
+            line["yahoo"] = {"error": repr(ex)[:300]}
+    if rank == 0:
+        print(json.dumps(line), file=real_stdout, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -240,6 +240,12 @@ int mfb_set_row_range(mfb_engine *e, int side, int32_t begin, int32_t end);
  * (mfb_set_row_range) into all peers and end with a flag barrier. */
 int mfb_comm_init(mfb_engine *e, int32_t rank, int32_t world, uint8_t *handles_out, int64_t *handles_bytes);
 int mfb_comm_connect(mfb_engine *e, const uint8_t *all_handles, int64_t bytes);
+/* The same for engines that live in ONE process (one host thread driving all visible GPUs, as the host classes do;
+ * several engines on one device are allowed): engines[r] becomes rank r, peer access between their devices is enabled
+ * and the peers' buffers are addressed directly.  The caller issues each step for all ranks before the next step (all
+ * calls are asynchronous; flag waits run on the device).  mfb_comm_disconnect undoes either kind of connection. */
+int mfb_comm_connect_local(mfb_engine **engines, int32_t world);
+int mfb_comm_disconnect(mfb_engine *e);
 /* device-side barrier over all ranks on the engines' streams (every rank must call it) */
 int mfb_comm_barrier(mfb_engine *e);
 /* *timed_out = 1 when a device-side wait gave up (20 s): a peer died or the schedule is inconsistent */

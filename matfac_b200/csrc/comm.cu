@@ -199,6 +199,68 @@ extern "C" int mfb_comm_connect(mfb_engine *e, const uint8_t *all_handles, int64
     MFB_CUDA(cudaIpcOpenMemHandle((void **)&c.flags[r], h.flags, cudaIpcMemLazyEnablePeerAccess));
   }
   c.connected = true;
+  c.ipc = true;
+  return 0;
+}
+
+// Engines of ONE process (one host thread driving several GPUs, or several engines on one device): the peers' buffers
+// are addressed directly — peer access between the devices is enabled here — instead of through CUDA IPC handles.
+// Everything else (push kernels, sequence flags, barriers) is the same code as the one-process-per-GPU path.
+extern "C" int mfb_comm_connect_local(mfb_engine **engines, int32_t world) {
+  MFB_REQUIRE(engines && world >= 1 && world <= kMaxRanks, "mfb_comm_connect_local: 1..8 engines");
+  for (int r = 0; r < world; r++) MFB_REQUIRE(engines[r] && !engines[r]->comm.connected, "mfb_comm_connect_local: null or already connected engine");
+  for (int r = 0; r < world; r++)
+    MFB_REQUIRE(engines[r]->n_users == engines[0]->n_users && engines[r]->n_items == engines[0]->n_items &&
+                    engines[r]->ld == engines[0]->ld, "mfb_comm_connect_local: engines differ in shape");
+  for (int r = 0; r < world; r++) {
+    mfb_engine *e = engines[r];
+    MFB_CUDA(mfb::enter(e));
+    for (int q = 0; q < world; q++) {
+      if (engines[q]->device == e->device) continue;
+      int can = 0;
+      MFB_CUDA(cudaDeviceCanAccessPeer(&can, e->device, engines[q]->device));
+      MFB_REQUIRE(can, "mfb_comm_connect_local: no peer access between two of the devices");
+      cudaError_t pe = cudaDeviceEnablePeerAccess(engines[q]->device, 0);
+      if (pe == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+      else MFB_CUDA(pe);
+    }
+    Comm &c = e->comm;
+    c.rank = r;
+    c.world = world;
+    if (!e->uk) MFB_CUDA(dev_alloc(&e->uk, sizeof(float) * e->n_users));
+    if (!e->vk) MFB_CUDA(dev_alloc(&e->vk, sizeof(float) * e->n_items));
+    if (!c.own_flags) MFB_CUDA(dev_alloc(&c.own_flags, sizeof(unsigned long long) * (kFlagSlots + 2)));
+    MFB_CUDA(cudaMemset(c.own_flags, 0, sizeof(unsigned long long) * (kFlagSlots + 2)));
+    c.barrier_seq = 0;
+  }
+  for (int r = 0; r < world; r++) {
+    Comm &c = engines[r]->comm;
+    for (int q = 0; q < world; q++) {
+      c.U[q] = engines[q]->U; c.V[q] = engines[q]->V; c.uk[q] = engines[q]->uk; c.vk[q] = engines[q]->vk;
+      c.flags[q] = engines[q]->comm.own_flags;
+    }
+    c.connected = true;
+    c.ipc = false;
+  }
+  return 0;
+}
+
+// Drops the connection of an engine (local connections: call it on every engine of the group before any of them is
+// destroyed or re-planned with a different world).
+extern "C" int mfb_comm_disconnect(mfb_engine *e) {
+  MFB_REQUIRE(e, "null engine");
+  MFB_CUDA(mfb::enter(e));
+  MFB_CUDA(cudaStreamSynchronize(e->stream));
+  Comm &c = e->comm;
+  if (c.connected && c.ipc)
+    for (int r = 0; r < c.world; r++) {
+      if (r == c.rank) continue;
+      cudaIpcCloseMemHandle(c.U[r]); cudaIpcCloseMemHandle(c.V[r]); cudaIpcCloseMemHandle(c.uk[r]);
+      cudaIpcCloseMemHandle(c.vk[r]); cudaIpcCloseMemHandle(c.flags[r]);
+    }
+  c.connected = false;
+  c.rank = 0;
+  c.world = 1;
   return 0;
 }
 

@@ -392,7 +392,7 @@ extern "C" void mfb_destroy(mfb_engine *e) {
   dev_free(e->als_ws); dev_free(e->res_row); dev_free(e->res_col); dev_free(e->uk); dev_free(e->vk); dev_free(e->uk_old);
   dev_free(e->ccd_acc); dev_free(e->scratch);
   const int destroyed_device = e->device;
-  if (e->comm.connected)
+  if (e->comm.connected && e->comm.ipc)
     for (int r = 0; r < e->comm.world; r++) {
       if (r == e->comm.rank) continue;
       cudaIpcCloseMemHandle(e->comm.U[r]); cudaIpcCloseMemHandle(e->comm.V[r]); cudaIpcCloseMemHandle(e->comm.uk[r]);

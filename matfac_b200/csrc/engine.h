@@ -103,6 +103,7 @@ constexpr int kFlagSlots = 64;  // 64-bit flag words per engine: [0,8) barrier a
 struct Comm {
   int rank = 0, world = 1;
   bool connected = false;
+  bool ipc = false;  // peers mapped through CUDA IPC (other processes) rather than addressed directly (same process)
   float *U[kMaxRanks] = {}, *V[kMaxRanks] = {}, *uk[kMaxRanks] = {}, *vk[kMaxRanks] = {};
   unsigned long long *flags[kMaxRanks] = {};
   unsigned long long *own_flags = nullptr;  // [kFlagSlots] + ticket + error word

@@ -29,7 +29,7 @@ SYMBOLS = [
     "mfb_restore_best", "mfb_event_record", "mfb_event_elapsed_ms", "mfb_device_factors", "mfb_stream",
     "mfb_pack_rows", "mfb_unpack_rows", "mfb_set_row_range",
     "mfb_build_csc", "mfb_download_csc", "mfb_comm_init", "mfb_comm_connect", "mfb_comm_barrier", "mfb_comm_error", "mfb_dsgd_push_block",
-    "mfb_comm_wait_block", "mfb_comm_allgather_rows",
+    "mfb_comm_wait_block", "mfb_comm_allgather_rows", "mfb_comm_connect_local", "mfb_comm_disconnect",
 ]
 
 
@@ -96,6 +96,8 @@ def load_library():
     L.mfb_set_row_range.argtypes = [vp, C.c_int, i32, i32]
     L.mfb_comm_init.argtypes = [vp, i32, i32, vp, C.POINTER(i64)]
     L.mfb_comm_connect.argtypes = [vp, vp, i64]
+    L.mfb_comm_connect_local.argtypes = [C.POINTER(vp), i32]
+    L.mfb_comm_disconnect.argtypes = [vp]
     L.mfb_comm_barrier.argtypes = [vp]
     L.mfb_comm_error.argtypes = [vp, C.POINTER(i32)]
     L.mfb_dsgd_push_block.argtypes = [vp, i32, i32, u64]
@@ -320,6 +322,9 @@ class Engine:
         buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
         self._check(self.L.mfb_comm_connect(self.h, buf, len(data)))
 
+    def comm_disconnect(self):
+        self._check(self.L.mfb_comm_disconnect(self.h))
+
     def comm_barrier(self):
         self._check(self.L.mfb_comm_barrier(self.h))
 
@@ -339,6 +344,14 @@ class Engine:
         if ids is not None:
             n = ids.shape[0]
         self._check(self.L.mfb_comm_allgather_rows(self.h, side, _p(ids), first, n))
+
+
+def connect_local(engines):
+    """Connect engines of this process as ranks 0..n-1 of one exchange group (mfb_comm_connect_local)."""
+    L = load_library()
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    if L.mfb_comm_connect_local(arr, len(engines)) != 0:
+        raise EngineError(L.mfb_last_error().decode(errors="replace"))
 
 
 def launch_count() -> int:

@@ -3,8 +3,10 @@
 // requested trainer — the same objects and calls as `mf` — and copies results out.
 #include <omp.h>
 
+#include <algorithm>
 #include <cstring>
 #include <memory>
+#include <random>
 
 #include "device_session.h"
 #include "matfac_host.h"
@@ -71,6 +73,36 @@ extern "C" int mfh_train(const mfh_problem *p, mfh_result *out) {
   if (out->best_U) memcpy(out->best_U, best->uFac.data(), ub);
   if (out->best_V) memcpy(out->best_V, best->iFac.data(), vb);
   omp_set_num_threads(savedThreads);
+  return 0;
+}
+
+// The stratified trainers' host plan, exactly as Model::runStratifiedSgd draws it: valid ids shuffled by
+// mt19937(seed) (users, then items), cut into P parts with the reference's boundary rule (modelMF.cpp:229-265), then
+// n_subepochs update sequences from the same engine (util.cpp:1077-1107).  invalid_* are one byte per id (1 = not
+// trained, part -1).  schedule_out = [n_subepochs][P][2] (user part, item part).
+extern "C" int mfh_sgd_plan(int32_t n_users, int32_t n_items, const uint8_t *invalid_users, const uint8_t *invalid_items,
+                            int32_t seed, int32_t P, int32_t n_subepochs, int32_t *user_part_out, int32_t *item_part_out,
+                            int32_t *schedule_out) {
+  if (n_users <= 0 || n_items <= 0 || P < 1 || n_subepochs < 0 || !user_part_out || !item_part_out) return 1;
+  std::vector<int> users, items;
+  for (int u = 0; u < n_users; u++)
+    if (!invalid_users || !invalid_users[u]) users.push_back(u);
+  for (int i = 0; i < n_items; i++)
+    if (!invalid_items || !invalid_items[i]) items.push_back(i);
+  std::mt19937 mt(seed);
+  std::shuffle(users.begin(), users.end(), mt);
+  std::shuffle(items.begin(), items.end(), mt);
+  const std::vector<int> up = matfac::partitionIds(users, P, n_users), ip = matfac::partitionIds(items, P, n_items);
+  memcpy(user_part_out, up.data(), sizeof(int32_t) * (size_t)n_users);
+  memcpy(item_part_out, ip.data(), sizeof(int32_t) * (size_t)n_items);
+  std::vector<std::pair<int, int>> seq;
+  for (int s = 0; s < n_subepochs && schedule_out; s++) {
+    sgdUpdateBlockSeq(P, seq, mt);
+    for (int t = 0; t < P; t++) {
+      schedule_out[((size_t)s * P + t) * 2] = seq[t].first;
+      schedule_out[((size_t)s * P + t) * 2 + 1] = seq[t].second;
+    }
+  }
   return 0;
 }
 

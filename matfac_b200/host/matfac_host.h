@@ -36,6 +36,12 @@ typedef struct mfh_result {
 } mfh_result;
 
 int mfh_train(const mfh_problem *p, mfh_result *out);
+/* Host plan of the stratified trainers (Model::trainSGDPar and twins): reference partitions (modelMF.cpp:229-265) and
+ * n_subepochs update sequences (util.cpp:1077-1107) drawn from mt19937(seed) in the reference's order.  invalid_* are
+ * one byte per id (may be NULL); schedule_out = [n_subepochs][P][2] (may be NULL). */
+int mfh_sgd_plan(int32_t n_users, int32_t n_items, const uint8_t *invalid_users, const uint8_t *invalid_items,
+                 int32_t seed, int32_t P, int32_t n_subepochs, int32_t *user_part_out, int32_t *item_part_out,
+                 int32_t *schedule_out);
 void mfh_release_device(void);
 
 #ifdef __cplusplus

@@ -165,3 +165,182 @@ def write_split_files(dirname: str, train: Csr, val: Csr, test: Csr):
     for m, p in zip((train, val, test), paths):
         write_text_csr(m, p)
     return paths
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Bit-reproducible large problems (bench.py, the multi-GPU tools and the scale tests).
+#
+# Everything below is a pure function of (shape, seed): draws come from a counter-based hash (splitmix64 of
+# (seed, stream, index)), de-duplication is sort-based, the surplus is trimmed by hash rank, and the rating values
+# use only IEEE add / multiply on exactly representable inputs — no atomics, no library RNG stream, no libm call on
+# the data path.  The same call therefore returns the same arrays in every process, on every rank and on "cpu" and
+# "cuda" alike (tests/test_synth.py; bench.py prints the CRC of the arrays so that two runs can be compared).
+_M64 = (1 << 64) - 1
+
+
+def _i64(x: int) -> int:
+    """Python int (mod 2^64) as the two's-complement int64 torch stores."""
+    x &= _M64
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def _lsr(x, k):
+    return (x >> k) & ((1 << (64 - k)) - 1)
+
+
+def _mix64_t(x):
+    """splitmix64 finaliser on an int64 tensor (wrap-around arithmetic)."""
+    x = x + _i64(0x9E3779B97F4A7C15)
+    x = (x ^ _lsr(x, 30)) * _i64(0xBF58476D1CE4E5B9)
+    x = (x ^ _lsr(x, 27)) * _i64(0x94D049BB133111EB)
+    return x ^ _lsr(x, 31)
+
+
+def _mix64_py(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+def _stream_key(seed: int, stream: int) -> int:
+    return _i64(_mix64_py(_mix64_py(seed) ^ (stream * 0xD1B54A32D192ED03 & _M64)))
+
+
+def _hash_t(idx, seed, stream):
+    """64 hashed bits per element of the int64 tensor idx."""
+    return _mix64_t((idx * _i64(0xA24BAED4963EE407)) ^ _stream_key(seed, stream))
+
+
+def _uniform53(h):
+    return _lsr(h, 11).double() * (1.0 / 9007199254740992.0)
+
+
+def _normalish(idx, seed, stream):
+    """Sum of twelve 24-bit uniforms minus 6: mean 0, variance 1, every partial sum exact in float64."""
+    acc = None
+    for k in range(6):
+        h = _hash_t(idx, seed, stream * 16 + k)
+        a = (_lsr(h, 40)).double() * (1.0 / 16777216.0)
+        b = ((h >> 8) & 0xFFFFFF).double() * (1.0 / 16777216.0)
+        acc = a + b if acc is None else acc + a + b
+    return acc - 6.0
+
+
+def _perm_weights(n, s, seed, stream, cap=None):
+    """Zipf(s) weights over n ids in a hashed (id-uncorrelated) order, optionally with the head capped."""
+    w = 1.0 / np.power(np.arange(1, n + 1, dtype=np.float64), s)
+    ids = np.arange(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        k = np.uint64(_mix64_py(_mix64_py(seed) ^ (stream * 0xD1B54A32D192ED03 & _M64)))
+        h = ids * np.uint64(0xA24BAED4963EE407) ^ k
+        h = h + np.uint64(0x9E3779B97F4A7C15)
+        h = (h ^ (h >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        h = (h ^ (h >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        h = h ^ (h >> np.uint64(31))
+    order = np.argsort(h, kind="stable")
+    p = np.empty(n, dtype=np.float64)
+    p[order] = w  # id order[k] gets the k-th largest weight
+    p /= p.sum()
+    if cap is not None:
+        for _ in range(8):
+            p = np.minimum(p, cap)
+            p /= p.sum()
+    return p
+
+
+NETFLIX_TOP_ITEM_SHARE = 232_944 / 100_480_507  # the most rated title of the real Netflix Prize data
+
+
+def array_crc(*arrays) -> str:
+    """CRC-32 of the raw bytes of the arrays, chained — the fingerprint bench.py prints for its input matrix."""
+    import zlib
+    c = 0
+    for a in arrays:
+        c = zlib.crc32(np.ascontiguousarray(a).view(np.uint8).reshape(-1), c)
+    return f"{c:08x}"
+
+
+def skewed_problem(n_users, n_items, nnz, seed, device="cpu", val_frac=0.01, user_s=0.9, item_s=1.05,
+                   item_share_cap=NETFLIX_TOP_ITEM_SHARE, true_rank=8, noise=0.3, max_user_share_of_items=0.85):
+    """Netflix-/Yahoo-shaped rating matrix: Zipf(user_s) user degrees (capped at 85 % of the catalogue), Zipf(item_s)
+    item popularity with the head capped at item_share_cap, every user and item rated at least once (io.cpp:742-752),
+    items ascending inside a row (util.cpp:919), ratings from a rank-`true_rank` model + noise rounded to halves in
+    [1, 5], a `val_frac` validation split that never takes a user's or an item's first rating.
+
+    Returns {"n_users", "n_items", "train": (rowptr int64, rowind int32, rowval fp32), "val": (...), "crc": str} with
+    host numpy arrays.  Deterministic in (arguments) — see the note above."""
+    import torch
+    dev = torch.device(device)
+    pu = _perm_weights(n_users, user_s, seed, 1)
+    pi = _perm_weights(n_items, item_s, seed, 2, cap=item_share_cap)
+    ci = torch.from_numpy(np.cumsum(pi)).to(dev)
+    cu = torch.from_numpy(np.cumsum(pu)).to(dev)
+    total = int(nnz * (1.0 + val_frac))
+    total = min(total, int(0.5 * n_users * n_items))
+    ar_u = torch.arange(n_users, device=dev, dtype=torch.int64)
+    ar_i = torch.arange(n_items, device=dev, dtype=torch.int64)
+    # every user and every item at least once
+    base_i = torch.searchsorted(ci, _uniform53(_hash_t(ar_u, seed, 3))).clamp_(max=n_items - 1)
+    base2_u = torch.searchsorted(cu, _uniform53(_hash_t(ar_i, seed, 4))).clamp_(max=n_users - 1)
+    cover = torch.unique(torch.cat([ar_u * n_items + base_i, base2_u * n_items + ar_i]))
+    keys = cover
+    cap = max_user_share_of_items * n_items
+    for rnd in range(16):
+        need = total - keys.numel()
+        if need <= 0:
+            break
+        draw = int(need * (1.6 if rnd == 0 else 1.3)) + 1024
+        deg_np = np.rint(np.minimum(pu * draw, cap)).astype(np.int64)
+        deg = torch.from_numpy(deg_np).to(dev)
+        u = torch.repeat_interleave(ar_u, deg)
+        idx = torch.arange(u.numel(), device=dev, dtype=torch.int64)
+        i = torch.searchsorted(ci, _uniform53(_hash_t(idx, seed, 16 + rnd))).clamp_(max=n_items - 1)
+        keys = torch.unique(torch.cat([keys, u * n_items + i]))
+        del u, i, idx, deg
+    if keys.numel() > total:
+        # keep the `total` keys of smallest hash; the covering pairs always survive
+        h = _lsr(_hash_t(keys, seed, 5), 1)  # non-negative
+        h[torch.isin(keys, cover)] = -1
+        order = torch.sort(h, stable=True).indices[:total]
+        keys = torch.sort(keys[order]).values
+        del h, order
+    users = keys // n_items
+    items = keys - users * n_items
+    # ratings: exact-arithmetic "normal" factors and noise, float64 dot with a fixed summation order
+    us = torch.stack([_normalish(ar_u, seed, 32 + k) for k in range(true_rank)], 1)
+    vs = torch.stack([_normalish(ar_i, seed, 64 + k) for k in range(true_rank)], 1)
+    scale = 1.1 / float(np.sqrt(true_rank))
+    vals = torch.empty(users.numel(), dtype=torch.float32, device=dev)
+    step = 1 << 24
+    for s in range(0, users.numel(), step):
+        e = min(s + step, users.numel())
+        uu, ii = us[users[s:e]], vs[items[s:e]]
+        d = uu[:, 0] * ii[:, 0]
+        for k in range(1, true_rank):
+            d = d + uu[:, k] * ii[:, k]
+        v = d * scale + 3.6
+        v = v + _normalish(keys[s:e], seed, 7) * noise
+        vals[s:e] = (torch.round(v * 2.0) * 0.5).clamp_(1.0, 5.0).float()
+        del uu, ii, d, v
+    # split: a hashed colour per (user, item); first rating of every user / item stays in train
+    colour = _uniform53(_hash_t(keys, seed, 6))
+    first_u = torch.ones(users.numel(), dtype=torch.bool, device=dev)
+    first_u[1:] = users[1:] != users[:-1]
+    order_i = torch.sort(items * n_users + users).indices  # keys are unique: no ties
+    si = items[order_i]
+    fi = torch.ones(si.numel(), dtype=torch.bool, device=dev)
+    fi[1:] = si[1:] != si[:-1]
+    first_i = torch.zeros(users.numel(), dtype=torch.bool, device=dev)
+    first_i[order_i[fi]] = True
+    is_val = (colour < val_frac) & ~first_u & ~first_i
+    del order_i, si, fi, colour, keys
+
+    def csr(mask):
+        u, i, v = users[mask], items[mask], vals[mask]
+        ptr = torch.zeros(n_users + 1, dtype=torch.int64, device=dev)
+        ptr[1:] = torch.cumsum(torch.bincount(u, minlength=n_users), 0)
+        return ptr.cpu().numpy(), i.to(torch.int32).cpu().numpy(), v.cpu().numpy()
+
+    tr, va = csr(~is_val), csr(is_val)
+    return dict(n_users=n_users, n_items=n_items, train=tr, val=va, crc=array_crc(*tr, *va))

@@ -350,3 +350,22 @@ def test_cli_quartile_report_and_partition_files(tmp_path):
             assert int(line[2 * g]) == sel.sum()
             if sel.sum():
                 assert abs(line[2 * g + 1] - np.sqrt(err2[sel].mean())) < 2e-4 * np.sqrt(err2[sel].mean())
+
+
+@pytest.mark.parametrize("P", [2, 4, 8])
+def test_python_reference_plan_matches_oracle(P):
+    """matfac_b200.dsgd.reference_plan (libmatfac_host.so: mfh_sgd_plan) — the plan the multi-GPU driver and bench.py use —
+    is the oracle's trainSGDPar plan bit for bit: partitions with the part-0 quirk (modelMF.cpp:229-265) and the update
+    sequences of util.cpp:1077-1107 drawn from the same mt19937(seed)."""
+    from matfac_b200 import dsgd
+    splits = golden_problem()
+    od = ol.OracleData(*splits)
+    m = ol.OracleModel(od, algo="mf", facdim=8, seed=3, nthreads=P)
+    m.compute_invalid()
+    bu, bi = m.invalid()
+    up, ip, pairs = m.dsgd_plan(P, 24)
+    up2, ip2, sched = dsgd.reference_plan(od.n_users, od.n_items, bu, bi, 3, P, 24)
+    assert np.array_equal(up, up2) and np.array_equal(ip, ip2)
+    for t in range(24):
+        assert sorted(sched[t]) == list(range(P))
+        assert np.array_equal(sched[t][pairs[t, :, 0]], pairs[t, :, 1])

@@ -23,9 +23,6 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 
-csc_on_device = bench.csc_on_device
-
-
 def main():
     real_stdout = bench._protect_stdout()  # only the JSON line goes to stdout (NCCL prints its banner on fd 1)
     ap = argparse.ArgumentParser()
@@ -46,14 +43,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_users, n_items, nnz = int(bench.SHAPE[0] * args.scale), bench.SHAPE[1], int(bench.SHAPE[2] * args.scale)
     t0 = time.time()
-    if world > 1:
-        prob = bench.shared_problem(n_users, n_items, nnz, 20260102, rank, dist, f"cuda:{local}")
-    else:
-        prob = bench.gen_problem(n_users, n_items, nnz, 20260102, f"cuda:{local}")
+    prob = bench.gen_problem(n_users, n_items, nnz, 20260102, f"cuda:{local}")  # the same matrix on every rank
     ptr, ind, val = prob["train"]
     train_nnz = int(ptr[-1])
     tr = bench.Mat(n_users, n_items, prob["train"])
-    tr.colptr, tr.colind, tr.colval = csc_on_device(n_users, n_items, ptr, ind, val, f"cuda:{local}")
     va = bench.Mat(n_users, n_items, prob["val"])
     bench.log(f"data {train_nnz} ratings in {time.time()-t0:.1f}s")
     r = args.rank
@@ -61,7 +54,8 @@ def main():
     U0 = rng.uniform(-0.01, 0.01, size=(n_users, r)).astype(np.float32)
     V0 = rng.uniform(-0.01, 0.01, size=(n_items, r)).astype(np.float32)
     eng = E.Engine(n_users, n_items, r, device=local)
-    eng.upload_csr(E.TRAIN, tr, with_csc=True)
+    eng.upload_csr(E.TRAIN, tr, with_csc=False)
+    eng.build_csc(E.TRAIN)  # gk_csr_CreateIndex on the device
     eng.upload_csr(E.VAL, va, with_csc=False)
     eng.set_masks((np.diff(ptr) == 0).astype(np.uint8), (np.bincount(ind, minlength=n_items) == 0).astype(np.uint8))
     eng.set_aux(E.MF, np.diff(ptr).astype(np.int32), np.bincount(ind, minlength=n_items).astype(np.int32))
@@ -75,7 +69,9 @@ def main():
         dist.all_gather_object(blobs, eng.comm_init(rank, world))
         eng.comm_connect(blobs)
         ucut = np.searchsorted(ptr, np.linspace(0, train_nnz, world + 1)).astype(int)
-        icut = np.searchsorted(tr.colptr, np.linspace(0, train_nnz, world + 1)).astype(int)
+        colptr = np.zeros(n_items + 1, np.int64)
+        np.cumsum(np.bincount(ind, minlength=n_items), out=colptr[1:])
+        icut = np.searchsorted(colptr, np.linspace(0, train_nnz, world + 1)).astype(int)
         ucut[0] = icut[0] = 0
         ucut[-1], icut[-1] = n_users, n_items
         eng.set_row_range(E.USER, int(ucut[rank]), int(ucut[rank + 1]))
