@@ -489,12 +489,14 @@ def oracle_check(rk, epochs=10, scale=0.05):
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_arm(prob, sample_users=None, epochs=4):
+def cpu_reference_arm(prob, sample_users=None, epochs=101):
     """Times the reference's OpenMP stratified SGD (ModelMF::trainSGDPar) on the first `sample_users` users of the
-    workload with every host core: `epochs` epochs, the first is warm-up, the value is the median of the rest
-    (median of steady epochs).  Uses oracle/_ref/mf_ref (the reference's own code) when present, else
-    the oracle port.  The sample holds ~4 % of the ratings: the figure is the sample's throughput, i.e. an
-    EXTRAPOLATION to the full matrix (whose U does not stay in the CPU's caches)."""
+    workload with every host core.  oracle/_ref/mf_ref is the reference's own code; it prints its epoch timer
+    (`subIterDuration`, modelMF.cpp:309,331) only every DISP_ITER = 50 epochs (const.h:5), so the run does 101 epochs and
+    the value is the median of the printed epochs 0, 50 and 100 (BASELINE.md §4 asks for steady epochs; epoch 0 is the
+    cold one).  Falls back on the oracle port (every epoch timed; median of epochs 1..) when mf_ref is absent.  The sample
+    holds ~4 % of the ratings: the figure is the sample's throughput, i.e. an EXTRAPOLATION to the full matrix (whose U
+    does not stay in the CPU's caches)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as ol
     from matfac_b200 import synth
@@ -502,7 +504,7 @@ def cpu_reference_arm(prob, sample_users=None, epochs=4):
     n_users, n_items = prob["n_users"], prob["n_items"]
     ptr, ind, val = prob["train"]
     if sample_users is None:
-        # ~4 M ratings: a few seconds of CPU work per epoch
+        # ~4 M ratings: ~0.2 s of CPU work per epoch
         sample_users = int(np.searchsorted(ptr, 4_000_000))
         sample_users = max(1000, min(sample_users, n_users))
     nnz_s = int(ptr[sample_users])
@@ -510,39 +512,53 @@ def cpu_reference_arm(prob, sample_users=None, epochs=4):
     vptr, vind, vval = prob["val"]
     vn = int(vptr[sample_users])
     va = synth.Csr(sample_users, n_items, vptr[: sample_users + 1].copy(), vind[:vn], vval[:vn])
-    kind, secs = "port", None
     what = f"first {sample_users} users ({nnz_s} ratings = {100.0 * nnz_s / int(ptr[-1]):.1f} % of the workload, extrapolated)"
+    od = ol.OracleData(tr, va, va)
+
+    def visited_in(epoch_ids, n_epochs):
+        # ratings visited per epoch of trainSGDPar: P update sequences drawn with replacement (util.cpp:1077)
+        om = ol.OracleModel(od, algo="mf", facdim=RANK, maxiter=1, seed=1, nthreads=cores, ureg=HP["ureg"], ireg=HP["ireg"],
+                            learnrate=HP["lr"])
+        up, ip, sched = om.dsgd_plan(cores, n_epochs * cores)
+        users = np.repeat(np.arange(sample_users), np.diff(tr.rowptr))
+        blk = np.bincount(up[users].astype(np.int64) * cores + ip[tr.rowind], minlength=cores * cores)
+        return [sum(int(blk[a * cores + b]) for s in range(e * cores, (e + 1) * cores) for a, b in sched[s]) for e in epoch_ids]
+
+    kind, secs, ids = "port", None, None
     if ol.have_ref():
         try:
             d = tempfile.mkdtemp(prefix="mfref_")
             files = synth.write_split_files(d, tr, va, va)
             res = ol.run_ref(files, os.path.join(d, "dump"), algo="mf", method="sgdpar", threads=cores, timeout=900,
                              facdim=RANK, maxiter=epochs, seed=1, ureg=HP["ureg"], ireg=HP["ireg"], learnrate=HP["lr"])
-            secs = [float(line.split("subIterDuration:")[1].split()[0]) for line in res["stdout"].splitlines()
-                    if "subIterDuration:" in line]
+            secs, ids = [], []
+            for line in res["stdout"].splitlines():
+                if "subIterDuration:" in line and " Iter: " in line:
+                    ids.append(int(line.split(" Iter: ")[1].split()[0]))
+                    secs.append(float(line.split("subIterDuration:")[1].split()[0]))
+            if not secs:
+                raise RuntimeError("no subIterDuration line in the reference's output")
             kind = "reference"
-            sample = f"{what}, mf_ref --mf_method sgdpar, OMP_NUM_THREADS={cores}, median of epochs 1..{len(secs) - 1} of {len(secs)}"
+            sample = (f"{what}, mf_ref --mf_method sgdpar, OMP_NUM_THREADS={cores}, the reference's own epoch timer at epochs "
+                      f"{ids} (it prints every 50th), median")
         except Exception as ex:  # fall back to the port
             log("mf_ref failed, using the oracle port:", repr(ex)[:200])
             secs = None
-    od = ol.OracleData(tr, va, va)
-    om = ol.OracleModel(od, algo="mf", facdim=RANK, maxiter=epochs, seed=1, nthreads=cores, ureg=HP["ureg"],
-                        ireg=HP["ireg"], learnrate=HP["lr"])
-    # ratings visited per epoch of trainSGDPar: P update sequences drawn with replacement (util.cpp:1077)
-    up, ip, sched = om.dsgd_plan(cores, epochs * cores)
-    users = np.repeat(np.arange(sample_users), np.diff(tr.rowptr))
-    bid = up[users].astype(np.int64) * cores + ip[tr.rowind]
-    blk = np.bincount(bid, minlength=cores * cores)
-    visited = [sum(int(blk[a * cores + b]) for s in range(e * cores, (e + 1) * cores) for a, b in sched[s]) for e in range(epochs)]
     if not secs:
+        n = 4
+        om = ol.OracleModel(od, algo="mf", facdim=RANK, maxiter=n, seed=1, nthreads=cores, ureg=HP["ureg"], ireg=HP["ireg"],
+                            learnrate=HP["lr"])
         om.train("sgdpar")
         secs = [float(x) for x in om.epoch_seconds()]
-        sample = f"{what}, oracle port of trainSGDPar, P={cores}, median of epochs 1..{len(secs) - 1} of {len(secs)}"
-    n = min(len(secs), len(visited))
-    rates = [visited[e] / secs[e] for e in range(1 if n > 1 else 0, n)]
+        ids = list(range(len(secs)))
+        if len(secs) > 1:
+            secs, ids = secs[1:], ids[1:]
+        sample = f"{what}, oracle port of trainSGDPar, P={cores}, median of epochs {ids}"
+    visited = visited_in(ids, max(ids) + 1)
+    rates = [v / s for v, s in zip(visited, secs)]
     value = float(np.median(rates))
-    ms = float(np.median(secs[1:] if len(secs) > 1 else secs)) * 1e3
-    return dict(value=value, unit="rating-updates/s", cores=cores, kind=kind, sample=sample, extrapolated=True), ms
+    return dict(value=value, unit="rating-updates/s", cores=cores, kind=kind, sample=sample, extrapolated=True,
+                epoch_seconds=secs), float(np.median(secs)) * 1e3
 
 
 # ---------------------------------------------------------------------------------------------
@@ -585,7 +601,7 @@ def main():
         if rank != 0:
             return 0
         prob = make_problem(SHAPE, args.scale, f"cuda:{local_rank}" if have_cuda else "cpu")
-        cb, ms = cpu_reference_arm(prob, epochs=max(2, min(args.steps + 1, 4)))
+        cb, ms = cpu_reference_arm(prob)
         config.update(n_users=prob["n_users"], n_items=prob["n_items"], train_nnz=int(prob["train"][0][-1]), matrix_crc=prob["crc"],
                       same_matrix_on_all_ranks=True)
         line = {"impl": "reference", "metric": "sgd_rating_updates_per_sec", "value": cb["value"], "unit": "rating-updates/s",

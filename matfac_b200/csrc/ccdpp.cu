@@ -269,7 +269,9 @@ int ccdpp_end_impl(mfb_engine *e) {
     MFB_TRY(comm_allgather_range(e, MFB_USER, e->row_begin[MFB_USER], e->row_end[MFB_USER] - e->row_begin[MFB_USER]));
     MFB_TRY(comm_allgather_range(e, MFB_ITEM, e->row_begin[MFB_ITEM], e->row_end[MFB_ITEM] - e->row_begin[MFB_ITEM]));
   }
-  MFB_CUDA(cudaStreamSynchronize(e->stream));
+  // no host synchronisation here: with several engines in one process the caller issues every step for all ranks
+  // before any of them can finish (the barriers above wait for peers on the device); the cached allocator orders
+  // the reuse of the freed blocks behind this stream's work
   dev_free(e->res_row); dev_free(e->res_col);
   e->res_row = e->res_col = nullptr;
   return 0;
