@@ -59,6 +59,8 @@ const char *mfb_last_error(void);
 /* number of kernels launched by all engines of this process since load (bench.py "gpu_launches") */
 uint64_t mfb_launch_count(void);
 
+/* number of visible CUDA devices (0 when there is none or the driver is missing) */
+int32_t mfb_device_count(void);
 int mfb_create(const mfb_config *cfg, mfb_engine **out);
 void mfb_destroy(mfb_engine *e);
 int mfb_sync(mfb_engine *e);

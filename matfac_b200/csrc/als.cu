@@ -122,16 +122,23 @@ struct CholScratch {  // floats, carved from the (by then free) L / tile region
 };
 
 #define MFB_T(a, b) acc[b][a]
-template <int TR, class S>
-__device__ __forceinline__ void chol_solve(float (&acc)[TR][TR], float *sm, int tx, int ty) {
+struct CtaBarrier {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+// barrier over a sub-group of warps of the CTA (bar.sync id, count): the solver groups of the warp-specialised kernel
+struct NamedBarrier {
+  int id, count;
+  __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+};
+// (R, C) = tile row / tile column of the thread (R >= C works, everything else idles through the barriers; threads
+// without a tile pass R = -1, C = -2); pan / dg / yb = CholScratch regions, bv = right-hand side in, solution out.
+template <int TR, class Bar>
+__device__ __forceinline__ void chol_solve_core(float (&acc)[TR][TR], float *pan, float *dg, float *yb, float *bv, int R, int C,
+                                                const Bar &bar) {
   using K = CholScratch<TR>;
-  static_assert(K::total <= S::RP * S::LDL, "Cholesky scratch must fit the L region");
-  float *pan = sm + S::off_L + K::off_pan, *dg = sm + S::off_L + K::off_dg, *yb = sm + S::off_L + K::off_y;
-  float *bv = sm + S::off_b;
-  const int R = tx, C = ty;
   const bool on_diag = R == C;
   float rhs[TR], dinv[TR];
-  __syncthreads();  // the right-hand side is complete, the L / tile region is free
+  bar();  // the right-hand side is complete, the scratch region is free
 #pragma unroll
   for (int a = 0; a < TR; a++) {
     rhs[a] = on_diag ? bv[tile_idx<TR>(R, a)] : 0.f;
@@ -169,7 +176,7 @@ __device__ __forceinline__ void chol_solve(float (&acc)[TR][TR], float *sm, int 
       sts_vec<TR>(dj + K::T2, dinv);
       sts_vec<TR>(yb + j * TR, rhs);
     }
-    __syncthreads();
+    bar();
     if (C == j && R > j) {
       float di[TR];
       lds_vec<TR>(dj + K::T2, di);
@@ -193,7 +200,7 @@ __device__ __forceinline__ void chol_solve(float (&acc)[TR][TR], float *sm, int 
         sts_vec<TR>(pj + R * K::TS + c * TR, col);
       }
     }
-    __syncthreads();
+    bar();
     if (C > j && R >= C) {
       float yj[TR];
 #pragma unroll
@@ -229,7 +236,7 @@ __device__ __forceinline__ void chol_solve(float (&acc)[TR][TR], float *sm, int 
 #pragma unroll
       for (int c = 0; c < TR; c++) bv[tile_idx<TR>(i, c)] = x[c];
     }
-    __syncthreads();
+    bar();
     if (R == i && C < i) {
       float x[TR], z[TR];
       lds_vec<TR>(yb + i * TR, x);
@@ -243,10 +250,18 @@ __device__ __forceinline__ void chol_solve(float (&acc)[TR][TR], float *sm, int 
       }
       sts_vec<TR>(yb + C * TR, z);
     }
-    __syncthreads();
+    bar();
   }
 }
 #undef MFB_T
+
+template <int TR, class S>
+__device__ __forceinline__ void chol_solve(float (&acc)[TR][TR], float *sm, int tx, int ty) {
+  using K = CholScratch<TR>;
+  static_assert(K::total <= S::RP * S::LDL, "Cholesky scratch must fit the L region");
+  chol_solve_core<TR>(acc, sm + S::off_L + K::off_pan, sm + S::off_L + K::off_dg, sm + S::off_L + K::off_y, sm + S::off_b, tx, ty,
+                      CtaBarrier());
+}
 
 template <int TR>
 __device__ __forceinline__ void add_reg_diag(float (&acc)[TR][TR], int tx, int ty, int rank, float reg) {
@@ -437,17 +452,33 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Waits for the phase of `parity` to complete.  Bounded: a protocol bug must not hang the GPU — after ~4 s without
+// progress the kernel traps (the launch fails with an error the host reports) instead of spinning for ever.
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0 = 0;
+  for (uint32_t spins = 1;; spins++) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((spins & 0x3FFu) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) asm volatile("trap;");
+    }
+  }
 }
 // SM100 shared-memory matrix descriptor: start address, leading / stride byte offsets (all >> 4),
 // descriptor version 1, no swizzle.  K-major: LBO = stride between core matrices along K,
@@ -723,6 +754,472 @@ __global__ void __launch_bounds__(256, 4) als_dual_kernel(const AlsArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised persistent ALS half-step for rank 33..128 (padded rank RP = 64 or 128): one CTA per SM, TMEM and the
+// mbarriers set up once per CTA, rows taken round-robin from the longest-first segment list.
+//
+//   producers (4 warps)   fetch the rated factor rows of a 32-rating tile with 16-byte cp.async copies counted on an
+//                         mbarrier (a ring of raw stages keeps several tiles in flight across row boundaries; the
+//                         (item, rating) pairs are requested two tiles earlier still).  One cp.async.bulk per row was
+//                         measured first: a 256 .. 512-byte bulk copy costs ~100 cycles of the SM's TMA unit, 3 - 4 k
+//                         cycles per 32-row tile — profiles/r2_als.md — so scattered rows go through LDGSTS and TMA is
+//                         kept for contiguous blocks (csrc/ccdpp.cu).  Then every value is split into tf32 big + small, transposed into the K-major
+//                         operand layout of the tensor core and accumulate the right-hand side b = sum r f on CUDA
+//                         cores; thread 0 issues the MMAs of the tile and commits them to mbarriers.
+//   tensor core           ONE tcgen05.mma per 8 ratings gives both products of the 3xTF32 scheme: the operand tile holds
+//                         [big dims; small dims] as 2 RP rows.  RP = 128: A = big (M = 128), B = [big; small] (N = 256):
+//                         D = [big big^T | big small^T].  RP = 64: A = [big; small] (M = 128), B = big (N = 64):
+//                         D = [big big^T ; small big^T].  G = BB + X + X^T is formed when the accumulator is drained
+//                         (the third product of the scheme is the transpose of the second).  One accumulator per solver group in
+//                         TMEM: the next rows multiply while earlier ones are drained.
+//   solver groups         G groups of 5 warps; group g takes rows g, g + G, ...: four of its warps (one per TMEM lane
+//                         quadrant) drain the accumulator into lower-triangle tiles in shared memory, 136 threads — one
+//                         per tile (R >= C) of the 16 x 16 tile grid — hold a tile in registers and run the tile
+//                         Cholesky + both triangular solves (chol_solve_core) with barriers over the group only, so G
+//                         rows are being solved while the next Gram is accumulated.
+constexpr int kWsKT = 32;            // ratings per tile
+constexpr int kWsProducers = 128;
+constexpr int kWsGroupThreads = 160;
+constexpr uint32_t kWsSbo = 144;     // bytes between 8-dim core matrices (16 B of padding: conflict-free transposing stores)
+
+template <int TR>
+struct AlsWs {
+  static constexpr int RP = 16 * TR;
+  static constexpr int MCORES = 2 * RP / 8;                       // core matrices along M of [big; small]
+  static constexpr uint32_t LBO = MCORES * kWsSbo;                // bytes between 4-rating K groups
+  static constexpr uint32_t OP_BYTES = (kWsKT / 4) * LBO;         // one operand stage
+  static constexpr int NS = TR == 8 ? 2 : 3;                      // operand stages
+  static constexpr int NR = TR == 8 ? 4 : 8;                      // raw stages (tiles of gathered factor rows in flight)
+  static constexpr int MR = NR + 2;                               // (item, rating) ring
+  static constexpr uint32_t RAW_ROW = RP * 4;                     // bytes per staged factor row
+  static constexpr uint32_t RAW_BYTES = kWsKT * RAW_ROW;
+  static constexpr int G = TR == 8 ? 2 : 4;                       // solver groups
+  static constexpr int NTHREADS = kWsProducers + G * kWsGroupThreads;
+  static constexpr int ACC_COLS = TR == 8 ? 256 : 64;             // TMEM columns of one accumulator
+  static constexpr int NACC = G;                                  // one accumulator per solver group: group g drains the
+                                                                  // phases of "its" accumulator in order (no parity aliasing)
+  static constexpr int TMEM_COLS = NACC * ACC_COLS;
+  static constexpr int T2 = TR * TR, TS = T2 + 4;                 // tile stride (floats): conflict-free 128-bit loads
+  static constexpr int GS_FLOATS = 136 * TS;                      // lower-triangle tiles of one Gram
+  // byte offsets from the 1024-aligned base
+  static constexpr uint32_t off_op = 0;
+  static constexpr uint32_t off_raw = off_op + NS * OP_BYTES;
+  static constexpr uint32_t off_gs = off_raw + NR * RAW_BYTES;
+  static constexpr uint32_t off_bvec = off_gs + G * GS_FLOATS * 4;            // [NACC][RP]
+  static constexpr uint32_t off_bred = off_bvec + NACC * RP * 4;              // [4][RP]
+  static constexpr uint32_t off_gbv = off_bred + 4 * RP * 4;                  // [G][RP]
+  static constexpr uint32_t off_meta = off_gbv + G * RP * 4;                  // [MR][32] item, [MR][32] rate
+  static constexpr uint32_t off_bars = off_meta + MR * 32 * 8;                // mbarriers
+  static constexpr int n_bars = NR + NS + 3 * NACC;
+  static constexpr uint32_t off_tmem = off_bars + n_bars * 8;
+  static constexpr size_t bytes = off_tmem + 16 + 1024;
+  static_assert(CholScratch<TR>::total <= GS_FLOATS, "Cholesky scratch is carved from the drained tile buffer");
+  static_assert(bytes <= 227 * 1024, "shared memory budget");
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// one factor row global -> shared through the bulk-copy engine (TMA, non-tensor form); completion is counted in bytes
+// on the mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// tile coordinate / element index of matrix index x under tile_idx<TR> (its inverse)
+template <int TR>
+__device__ __forceinline__ void tile_of(int x, int &t, int &e) {
+  if (TR <= 4) { t = x / TR; e = x % TR; }
+  else { t = (x & 63) >> 2; e = ((x >> 6) << 2) | (x & 3); }
+}
+__device__ __forceinline__ int tri_index(int R, int C) { return R * (R + 1) / 2 + C; }
+
+template <int TR>
+__global__ void __launch_bounds__(AlsWs<TR>::NTHREADS, 1) als_ws_kernel(const AlsArgs a) {
+  using W = AlsWs<TR>;
+  constexpr int RP = W::RP, NS = W::NS, NR = W::NR, G = W::G;
+  extern __shared__ uint8_t sm_raw[];
+  uint8_t *smb = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smb);
+  float *bvec = reinterpret_cast<float *>(smb + W::off_bvec);
+  float *bred = reinterpret_cast<float *>(smb + W::off_bred);
+  int *meta_item = reinterpret_cast<int *>(smb + W::off_meta);
+  float *meta_rate = reinterpret_cast<float *>(smb + W::off_meta + W::MR * 32 * 4);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smb + W::off_bars);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smb + W::off_tmem);
+  // mbarriers: raw_full[NR] | op_empty[NS] | acc_full[NACC] | rhs_full[NACC] | acc_empty[NACC]
+  constexpr int NACC = W::NACC;
+  const uint32_t bar_raw = smem_u32(bars), bar_op = bar_raw + NR * 8, bar_accf = bar_op + NS * 8, bar_rhs = bar_accf + NACC * 8,
+                 bar_acce = bar_rhs + NACC * 8;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int n_rows = (int)blockIdx.x < a.nseg ? (a.nseg - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int nq = a.ld >> 2;
+
+  if (tid == 0) {
+    for (int i = 0; i < NR; i++) mbar_init(bar_raw + i * 8, kWsProducers);
+    for (int i = 0; i < NS; i++) mbar_init(bar_op + i * 8, 1);
+    for (int i = 0; i < NACC; i++) {
+      mbar_init(bar_accf + i * 8, 1);
+      mbar_init(bar_rhs + i * 8, 1);
+      mbar_init(bar_acce + i * 8, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(W::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (tid < kWsProducers) {
+    // ================================= producers =================================
+    const int w = tid >> 5;
+    // instruction descriptor: D = F32, A = B = TF32, both K-major; RP = 128: M = 128, N = 256; RP = 64: M = 128, N = 64
+    constexpr uint32_t NDIM = TR == 8 ? 256u : 64u;
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((NDIM >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr int D = NR - 1;      // tiles whose factor rows are in flight
+    constexpr int MR = W::MR;      // meta ring: tiles g .. g + D + 1 are live
+    constexpr int QP = RP / 4;     // 16-byte units per staged row
+    // A cursor walks the tiles of this CTA's rows (row i = segment seg0 + blockIdx.x + i * gridDim.x); the descriptor of
+    // the next row is fetched when a row is entered, so that the dependent loads are off the critical path.
+    struct Cursor { int i, t, ntiles, start, len, nstart, nlen; };
+    auto fetch_next = [&](Cursor &c) {
+      c.nstart = c.nlen = 0;
+      if (c.i + 1 < n_rows) {
+        const int seg = a.seg0 + (int)blockIdx.x + (c.i + 1) * (int)gridDim.x;
+        c.nstart = __ldg(a.seg_start + seg);
+        c.nlen = __ldg(a.seg_len + seg);
+      }
+    };
+    auto init_cursor = [&](Cursor &c) {
+      c.i = 0; c.t = 0; c.ntiles = 1; c.start = c.len = 0;
+      if (n_rows > 0) {
+        const int seg = a.seg0 + (int)blockIdx.x;
+        c.start = __ldg(a.seg_start + seg);
+        c.len = __ldg(a.seg_len + seg);
+        c.ntiles = (c.len + kWsKT - 1) / kWsKT;
+      }
+      fetch_next(c);
+    };
+    auto advance = [&](Cursor &c) {
+      if (++c.t == c.ntiles) {
+        c.i++; c.t = 0;
+        c.start = c.nstart; c.len = c.nlen;
+        c.ntiles = (c.len + kWsKT - 1) / kWsKT;
+        fetch_next(c);
+      }
+    };
+    Cursor cm, ci, cc;  // meta-load cursor (warp 0), copy-issue cursor, consume cursor
+    init_cursor(cm);
+    ci = cm;
+    cc = cm;
+    int gm = 0, gi = 0;  // tiles whose meta has been requested / whose row copies have been issued
+    // warp 0, lane l: (item, rating) of rating l of the tile under cm -> registers (pf_*), stored to the meta ring one
+    // iteration later: the global-load latency (a fresh 128-byte line per tile) overlaps a whole tile of work
+    int pf_it = 0, pf_slot = -1;
+    float pf_rt = 0.f;
+    auto meta_request = [&]() {
+      const int j = cm.t * kWsKT + lane;
+      pf_it = 0; pf_rt = 0.f;
+      if (j < cm.len) {
+        pf_it = __ldg(a.ind + cm.start + j);
+        pf_rt = __ldg(a.val + cm.start + j);
+      }
+      if (!(pf_rt > 0.f)) pf_rt = 0.f;  // rating > 0 filter (modelMF.cpp:819); padding lanes
+      pf_slot = gm % MR;
+      gm++;
+      advance(cm);
+    };
+    auto meta_commit = [&]() {
+      if (pf_slot >= 0) {
+        meta_item[pf_slot * 32 + lane] = pf_it;
+        meta_rate[pf_slot * 32 + lane] = pf_rt;
+        pf_slot = -1;
+      }
+    };
+    // all producers: the factor rows of tile gi, 16 bytes per cp.async, a row = QP consecutive threads (coalesced);
+    // completion is counted on raw_full[stage] (cp.async.mbarrier.arrive.noinc: one arrival per producer thread)
+    auto issue_rows = [&]() {
+      const int s = gi % NR, ms = gi % MR;
+      const uint32_t dst0 = sbase + W::off_raw + s * W::RAW_BYTES;
+#pragma unroll
+      for (int k = 0; k < kWsKT * QP / kWsProducers; k++) {
+        const int idx = tid + k * kWsProducers, j = idx / QP, q = idx % QP;
+        if (q < nq && meta_rate[ms * 32 + j] > 0.f)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + j * W::RAW_ROW + q * 16),
+                       "l"(a.Fin + (size_t)meta_item[ms * 32 + j] * a.ld + q * 4)
+                       : "memory");
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_raw + s * 8) : "memory");
+      gi++;
+      advance(ci);
+    };
+    // prologue: meta of tiles 0 .. D, copies of tiles 0 .. D - 1, request for tile D + 1
+    if (w == 0) {
+      for (int k = 0; k <= D && cm.i < n_rows; k++) { meta_request(); meta_commit(); }
+      if (cm.i < n_rows) meta_request();
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int k = 0; k < D && ci.i < n_rows; k++) issue_rows();
+    float4 bacc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int g = 0; cc.i < n_rows; g++) {
+      if (w == 0) {  // meta of tile g + D + 1 (requested one iteration ago) into the ring, request tile g + D + 2
+        meta_commit();
+        if (cm.i < n_rows) meta_request();
+      }
+      if (ci.i < n_rows) issue_rows();  // tile g + D, into the stage the previous iteration has finished reading
+      const int s = g % NR, ms = g % MR;
+      mbar_wait(bar_raw + s * 8, (uint32_t)(g / NR) & 1u);
+      const float4 *raw4 = reinterpret_cast<const float4 *>(smb + W::off_raw + s * W::RAW_BYTES);
+      // this thread's ratings of the tile: RP = 128: 8w .. 8w + 7, one 16-byte unit q = lane of each;
+      // RP = 64: 8w + 4h .. + 3 with h = lane / 16, q = lane % 16
+      constexpr int NI = TR == 8 ? 8 : 4;
+      const int q = TR == 8 ? lane : (lane & 15);
+      const int j0 = TR == 8 ? 8 * w : 8 * w + 4 * (lane >> 4);
+      float4 f[NI];
+#pragma unroll
+      for (int i = 0; i < NI; i++) {
+        const float rt = meta_rate[ms * 32 + j0 + i];
+        f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rt > 0.f && q < nq) f[i] = raw4[(j0 + i) * (RP / 4) + q];
+        bacc.x = fmaf(rt, f[i].x, bacc.x);
+        bacc.y = fmaf(rt, f[i].y, bacc.y);
+        bacc.z = fmaf(rt, f[i].z, bacc.z);
+        bacc.w = fmaf(rt, f[i].w, bacc.w);
+      }
+      const int os = g % NS;
+      if (g >= NS) mbar_wait(bar_op + os * 8, (uint32_t)(g / NS - 1) & 1u);  // the MMAs that read this stage are done
+      const uint32_t op0 = sbase + W::off_op + os * W::OP_BYTES;
+#pragma unroll
+      for (int hh = 0; hh < NI / 4; hh++) {
+        const int kg = (j0 >> 2) + hh;  // 4-rating K group of the tile
+        const float fe[4][4] = {{f[4 * hh].x, f[4 * hh + 1].x, f[4 * hh + 2].x, f[4 * hh + 3].x},
+                                {f[4 * hh].y, f[4 * hh + 1].y, f[4 * hh + 2].y, f[4 * hh + 3].y},
+                                {f[4 * hh].z, f[4 * hh + 1].z, f[4 * hh + 2].z, f[4 * hh + 3].z},
+                                {f[4 * hh].w, f[4 * hh + 1].w, f[4 * hh + 2].w, f[4 * hh + 3].w}};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int mdim = 4 * q + e;
+          float bg[4], sl[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            bg[i] = round_tf32(fe[e][i]);
+            sl[i] = round_tf32(fe[e][i] - bg[i]);
+          }
+          const uint32_t off = (uint32_t)kg * W::LBO + (uint32_t)(mdim >> 3) * kWsSbo + (uint32_t)(mdim & 7) * 16;
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(op0 + off), "f"(bg[0]), "f"(bg[1]), "f"(bg[2]), "f"(bg[3]) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(op0 + off + (RP / 8) * kWsSbo), "f"(sl[0]), "f"(sl[1]), "f"(sl[2]), "f"(sl[3]) : "memory");
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the tensor core
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int acc = cc.i % NACC;
+      const bool first = cc.t == 0, last = cc.t == cc.ntiles - 1;
+      if (tid == 0) {
+        if (first && cc.i >= NACC) mbar_wait(bar_acce + acc * 8, (uint32_t)(cc.i / NACC - 1) & 1u);  // accumulator drained
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d = tmem_base + (uint32_t)acc * W::ACC_COLS;
+        const int kmax = last ? (cc.len - cc.t * kWsKT + 7) / 8 : kWsKT / 8;  // K steps of 8 ratings that hold data
+#pragma unroll
+        for (int k8 = 0; k8 < kWsKT / 8; k8++) {
+          if (k8 >= kmax) break;
+          const uint64_t desc = umma_desc_kmajor(op0 + k8 * 2 * W::LBO, W::LBO, kWsSbo);
+          umma_tf32(d, desc, desc, idesc, (first && k8 == 0) ? 0u : 1u);
+        }
+        umma_commit(bar_op + os * 8);
+        if (last) umma_commit(bar_accf + acc * 8);
+      }
+      if (last) {
+        // right-hand side of the row: 4 warp partials (RP = 64: two half-warp partials folded first)
+        if (TR != 8) {
+          bacc.x += __shfl_xor_sync(0xFFFFFFFFu, bacc.x, 16);
+          bacc.y += __shfl_xor_sync(0xFFFFFFFFu, bacc.y, 16);
+          bacc.z += __shfl_xor_sync(0xFFFFFFFFu, bacc.z, 16);
+          bacc.w += __shfl_xor_sync(0xFFFFFFFFu, bacc.w, 16);
+        }
+        if (TR == 8 || lane < 16) *reinterpret_cast<float4 *>(bred + w * RP + q * 4) = bacc;
+        bacc = make_float4(0.f, 0.f, 0.f, 0.f);
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // thread 0 is past its wait: bvec[acc] is free
+        if (tid < RP) bvec[acc * RP + tid] = (bred[tid] + bred[RP + tid]) + (bred[2 * RP + tid] + bred[3 * RP + tid]);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == 0) mbar_arrive(bar_rhs + acc * 8);
+      }
+      advance(cc);
+    }
+  } else {
+    // ================================= solver groups =================================
+    const int st = tid - kWsProducers, g = st / kWsGroupThreads, t = st % kWsGroupThreads;
+    float *Gs = reinterpret_cast<float *>(smb + W::off_gs) + (size_t)g * W::GS_FLOATS;
+    float *gbv = reinterpret_cast<float *>(smb + W::off_gbv) + g * RP;
+    using K = CholScratch<TR>;
+    const NamedBarrier group_bar{8 + g, kWsGroupThreads};
+    int R = -1, C = -2;
+    if (t < 136) {
+      R = 0;
+      while ((R + 1) * (R + 2) / 2 <= t) R++;
+      C = t - R * (R + 1) / 2;
+    }
+    const int p = 32 * ((tid >> 5) & 3) + lane;  // TMEM lane this thread may read (its warp's quadrant)
+    for (int i = g; i < n_rows; i += G) {
+      const int acc = i % NACC;  // == g
+      const uint32_t par = (uint32_t)(i / NACC) & 1u;
+      const int seg = a.seg0 + (int)blockIdx.x + i * (int)gridDim.x;
+      const int row = a.seg_row[seg], slot = a.seg_slot[seg];
+      if (t < 128) {
+        mbar_wait(bar_accf + acc * 8, par);
+        mbar_wait(bar_rhs + acc * 8, par);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tad = tmem_base + (uint32_t)acc * W::ACC_COLS + ((uint32_t)(p & ~31) << 16);
+        uint32_t v[32], x[32];
+        if (TR == 8) {
+          int ta, ea;
+          tile_of<TR>(p, ta, ea);
+          for (int c0 = 0; c0 < RP; c0 += 32) {  // G(a, b) = BB + BS for tile(a) <= tile(b)
+            tmem_ld32(tad + c0, v);
+            tmem_ld32(tad + RP + c0, x);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k4 = 0; k4 < 8; k4++) {
+              int tb, eb;
+              tile_of<TR>(c0 + 4 * k4, tb, eb);
+              if (ta <= tb)
+                *reinterpret_cast<float4 *>(Gs + tri_index(tb, ta) * W::TS + ea * TR + eb) =
+                    make_float4(__uint_as_float(v[4 * k4]) + __uint_as_float(x[4 * k4]), __uint_as_float(v[4 * k4 + 1]) + __uint_as_float(x[4 * k4 + 1]),
+                                __uint_as_float(v[4 * k4 + 2]) + __uint_as_float(x[4 * k4 + 2]), __uint_as_float(v[4 * k4 + 3]) + __uint_as_float(x[4 * k4 + 3]));
+            }
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+          for (int c0 = 0; c0 < RP; c0 += 32) {  // + BS^T: G(c, a) += BS[a][c] for tile(c) <= tile(a)
+            tmem_ld32(tad + RP + c0, x);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 32; k++) {
+              int tc, ec;
+              tile_of<TR>(c0 + k, tc, ec);
+              if (tc <= ta) Gs[tri_index(ta, tc) * W::TS + ec * TR + ea] += __uint_as_float(x[k]);
+            }
+          }
+        } else {
+          // lanes 0..63: BB rows, lanes 64..127: SB rows (small big^T)
+          const int arow = p & 63;
+          int ta, ea;
+          tile_of<TR>(arow, ta, ea);
+          if (p < 64) {
+            for (int c0 = 0; c0 < RP; c0 += 32) {
+              tmem_ld32(tad + c0, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int k4 = 0; k4 < 8; k4++) {
+                const int tb = (c0 + 4 * k4) / TR;
+                if (ta <= tb)
+                  *reinterpret_cast<float4 *>(Gs + tri_index(tb, ta) * W::TS + ea * TR) =
+                      make_float4(__uint_as_float(v[4 * k4]), __uint_as_float(v[4 * k4 + 1]), __uint_as_float(v[4 * k4 + 2]), __uint_as_float(v[4 * k4 + 3]));
+              }
+            }
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+          if (p >= 64) {
+            for (int c0 = 0; c0 < RP; c0 += 32) {  // + SB: G(a, b) += SB[a][b]
+              tmem_ld32(tad + c0, x);
+              tmem_ld_wait();
+#pragma unroll
+              for (int k4 = 0; k4 < 8; k4++) {
+                const int tb = (c0 + 4 * k4) / TR;
+                if (ta <= tb) {
+                  float4 *dst = reinterpret_cast<float4 *>(Gs + tri_index(tb, ta) * W::TS + ea * TR);
+                  float4 o = *dst;
+                  o.x += __uint_as_float(x[4 * k4]); o.y += __uint_as_float(x[4 * k4 + 1]);
+                  o.z += __uint_as_float(x[4 * k4 + 2]); o.w += __uint_as_float(x[4 * k4 + 3]);
+                  *dst = o;
+                }
+              }
+            }
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+          if (p >= 64) {
+            for (int c0 = 0; c0 < RP; c0 += 32) {  // + SB^T: G(c, a) += SB[a][c]
+              tmem_ld32(tad + c0, x);
+              tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 32; k++) {
+                int tc, ec;
+                tile_of<TR>(c0 + k, tc, ec);
+                if (tc <= ta) Gs[tri_index(ta, tc) * W::TS + ec * TR + ea] += __uint_as_float(x[k]);
+              }
+            }
+          }
+        }
+        if (t < RP) gbv[t] = bvec[acc * RP + t];
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(bar_acce + acc * 8);  // accumulator and bvec[acc] may be reused
+      }
+      group_bar();
+      float tile[TR][TR];
+#pragma unroll
+      for (int ii = 0; ii < TR; ii++) {
+        float rowv[TR];
+        if (t < 136) lds_vec<TR>(Gs + tri_index(R, C) * W::TS + ii * TR, rowv);
+#pragma unroll
+        for (int jj = 0; jj < TR; jj++) tile[ii][jj] = t < 136 ? rowv[jj] : 0.f;
+      }
+      group_bar();  // every tile is in registers: the buffer becomes the Cholesky scratch
+      if (slot >= 0) {
+        // segment of a split row: add the partial Gram / right-hand side into the row's workspace (als_solve_ws_kernel)
+        float *wsp = a.ws + (size_t)slot * (RP * RP + RP);
+        if (t < 136) {
+#pragma unroll
+          for (int ii = 0; ii < TR; ii++)
+#pragma unroll
+            for (int jj = 0; jj < TR; jj++) atomicAdd(wsp + tile_idx<TR>(C, ii) * RP + tile_idx<TR>(R, jj), tile[ii][jj]);
+        }
+        if (t < RP) atomicAdd(wsp + RP * RP + t, gbv[t]);
+        group_bar();
+        continue;
+      }
+      if (t < 136) add_reg_diag<TR>(tile, R, C, a.rank, a.reg);
+      chol_solve_core<TR>(tile, Gs + K::off_pan, Gs + K::off_dg, Gs + K::off_y, gbv, R, C, group_bar);
+      store_solution(a, row, t, gbv);
+      group_bar();  // the solution has been read: the buffers may be overwritten by the next row
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(W::TMEM_COLS) : "memory");
+}
+
+template <int TR>
+static int launch_als_ws(mfb_engine *e, AlsArgs b, int n_primal) {
+  using W = AlsWs<TR>;
+  if (n_primal <= 0) return 0;
+  MFB_CUDA(cudaFuncSetAttribute(als_ws_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::bytes));
+  b.seg0 = 0;
+  b.nseg = n_primal;
+  const int grid = std::min(e->sm_count, n_primal);
+  MFB_LAUNCH((als_ws_kernel<TR>), grid, W::NTHREADS, W::bytes, e->stream, b);
+  return 0;
+}
+
 template <int TRD>
 static int launch_dual(mfb_engine *e, AlsArgs b, int seg0, int count) {
   if (count <= 0) return 0;
@@ -755,8 +1252,16 @@ static int launch_als(mfb_engine *e, const AlsArgs &a, const SegPlan &sp) {
   // shorter ones through the dual system whose padded size is at most half of that
   const int n64 = sp.n_longer[0], n32 = sp.n_longer[1], n16 = sp.n_longer[2];
   int n_primal = sp.n_seg;
+  bool n_primal_done = false;
   if (e->opt_als_dual) n_primal = TR == 8 ? n64 : TR == 4 ? n32 : TR == 2 ? n16 : sp.n_seg;
-  if (TR == 8 && e->opt_als_tensor_cores) {
+  if constexpr (TR == 8 || TR == 4) {
+    if (e->opt_als_tensor_cores == 1) {
+      MFB_TRY(launch_als_ws<TR>(e, b, n_primal));
+      n_primal_done = true;
+    }
+  }
+  if (n_primal_done) {
+  } else if (TR == 8 && e->opt_als_tensor_cores) {  // als_tensor_cores = 2: the round-1 kernel (one CTA per row)
     MFB_CUDA(cudaFuncSetAttribute(als_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AlsTcSmem::bytes));
     if (n_primal > 0) MFB_LAUNCH(als_gram_tc_kernel, n_primal, 256, AlsTcSmem::bytes, e->stream, b);
   } else if (n_primal > 0) {

@@ -11,6 +11,10 @@
 // longer than a chunk are split over warps that combine through fp64 atomics.
 #include "engine.h"
 
+#include <cub/cub.cuh>
+
+#include <algorithm>
+
 namespace mfb {
 
 constexpr int kCcdChunk = 1024;
@@ -162,26 +166,332 @@ __global__ void col_insert_kernel(float *__restrict__ F, int ld, int k, int lo, 
   if (i < hi) F[(size_t)i * ld + k] = in[i];
 }
 
+
+// ---- shared-memory staged passes ------------------------------------------------------------------------------
+// A pass gathers one entry of the dense vector `other` per rating.  Every lane of a warp hits a different 128-byte
+// line, so the gather costs one L1 wavefront per rating: 100 M ratings / 148 SMs at one wavefront per cycle is the
+// ~0.3 ms every pass of the plain kernels takes, whatever the memory system delivers (profiles/r1_ncu_ccdpp.txt: L2 at
+// 69 %, a 32-byte sector moved per 4-byte entry).  Here the gathered vector sits in shared memory instead (random
+// 4-byte reads: a few bank conflicts per warp, not 32 wavefronts): the index / residual streams are then the only
+// global traffic and the pass is bound by HBM.  A vector that does not fit is cut into blocks of kCcdBlock entries;
+// every row is split at the block boundaries (its indices ascend: datastruct.cpp:18 / util.cpp:919) and a CTA serves
+// the sub-segments of ONE block with that block of `other` (and of `other_old` for the fused column add-back) staged.
+// Partial sums of a split row meet in the fp64 accumulators, ccd_finalize_kernel closes the row — the same arithmetic
+// as the plain kernels' split rows.
+constexpr int kCcdBlock = 24576;  // entries per staged block: 96 KB, two arrays = 192 KB
+
+struct CcdBlk {
+  const int32_t *off;  // [nb + 1] first segment of every block (device)
+  int nb, block, gather_n, ctas_per_blk;
+};
+
+// One block of the gathered vector global -> shared through the bulk-copy engine (TMA, cp.async.bulk): contiguous, up to
+// 96 KB, issued by one thread in 16 KB pieces and counted in bytes on an mbarrier — the case the engine is built for
+// (a per-thread load loop spends ~20 us of latency-bound iterations on the same block).  The vectors are allocated with
+// 4 floats of slack so that the copy may round the block up to 16 bytes.
+__device__ __forceinline__ void ccd_stage_issue(uint32_t bar, float *dst, const float *src, int n) {
+  const uint32_t bytes = (uint32_t)((n + 3) & ~3) * 4u;
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
+  for (uint32_t off = 0; off < bytes; off += 16384u) {
+    const uint32_t piece = bytes - off < 16384u ? bytes - off : 16384u;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d0 + off),
+                 "l"(reinterpret_cast<const char *>(src) + off), "r"(piece), "r"(bar)
+                 : "memory");
+  }
+}
+// all threads: initialise the barrier (thread 0), issue the copies (thread 0) and wait for them
+__device__ __forceinline__ void ccd_stage(uint64_t *bar_mem, float *dst0, const float *src0, float *dst1, const float *src1, int n) {
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(bar_mem);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(dst1 ? 2u : 1u));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ccd_stage_issue(bar, dst0, src0, n);
+    if (dst1) ccd_stage_issue(bar, dst1, src1, n);
+  }
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar)
+        : "memory");
+  }
+}
+
+template <bool ADDBACK, bool TWO>
+__global__ void __launch_bounds__(512) ccd_update_sm_kernel(const CcdPass p, float *__restrict__ own, const float *__restrict__ other,
+                                                            const float *__restrict__ other_old, float reg, double *__restrict__ acc,
+                                                            const Aux *__restrict__ aux_freq, int freq_thresh, const CcdPeers pe,
+                                                            const CcdBlk bk) {
+  extern __shared__ __align__(16) float ccd_sm[];
+  const int b = blockIdx.x / bk.ctas_per_blk, ci = blockIdx.x % bk.ctas_per_blk;
+  const int g_lo = b * bk.block, g_n = min(bk.block, bk.gather_n - g_lo);
+  __shared__ uint64_t stage_bar;
+  float *so = ccd_sm, *sold = TWO ? ccd_sm + bk.block : ccd_sm;
+  ccd_stage(&stage_bar, so, other + g_lo, TWO ? sold : nullptr, other_old + g_lo, g_n);
+  const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  const int seg_hi = bk.off[b + 1];
+  for (int seg = bk.off[b] + ci * wpc + (threadIdx.x >> 5); seg < seg_hi; seg += bk.ctas_per_blk * wpc) {
+    const int row = p.seg_row[seg], start = p.seg_start[seg], len = p.seg_len[seg], slot = p.seg_slot[seg];
+    double num = 0.0, den = 0.0;
+    const float a_old = ADDBACK ? own[row] : 0.f;
+    for (int base = 0; base < len; base += 32 * kCcdDepth) {
+      int c[kCcdDepth];
+      float r[kCcdDepth], o[kCcdDepth];
+#pragma unroll
+      for (int d = 0; d < kCcdDepth; d++) {
+        const int j = base + d * 32 + lane;
+        c[d] = j < len ? __ldg(p.ind + start + j) - g_lo : -1;
+        r[d] = j < len ? p.res[start + j] : 0.f;
+      }
+#pragma unroll
+      for (int d = 0; d < kCcdDepth; d++) {
+        o[d] = c[d] >= 0 ? so[c[d]] : 0.f;
+        if (ADDBACK && c[d] >= 0) {
+          r[d] = __fadd_rn(r[d], __fmul_rn(a_old, sold[c[d]]));
+          p.res[start + base + d * 32 + lane] = r[d];
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < kCcdDepth; d++) {
+        num += (double)__fmul_rn(r[d], o[d]);
+        den += (double)__fmul_rn(o[d], o[d]);
+      }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      num += __shfl_xor_sync(0xFFFFFFFFu, num, m);
+      den += __shfl_xor_sync(0xFFFFFFFFu, den, m);
+    }
+    if (slot < 0) {
+      float nv = (float)(num / ((double)reg + den));
+      if (freq_thresh > 0 && aux_freq[row].freq < freq_thresh) nv = 0.f;
+      if (lane == 0) store_all(own, pe, row, nv);
+    } else if (lane == 0) {
+      atomicAdd(acc + 2 * (size_t)slot, num);
+      atomicAdd(acc + 2 * (size_t)slot + 1, den);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(512) ccd_resid_sm_kernel(const CcdPass p, const float *__restrict__ own, const float *__restrict__ other,
+                                                           float sign, const CcdBlk bk) {
+  extern __shared__ __align__(16) float ccd_sm[];
+  const int b = blockIdx.x / bk.ctas_per_blk, ci = blockIdx.x % bk.ctas_per_blk;
+  const int g_lo = b * bk.block, g_n = min(bk.block, bk.gather_n - g_lo);
+  __shared__ uint64_t stage_bar;
+  ccd_stage(&stage_bar, ccd_sm, other + g_lo, nullptr, nullptr, g_n);
+  const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  const int seg_hi = bk.off[b + 1];
+  for (int seg = bk.off[b] + ci * wpc + (threadIdx.x >> 5); seg < seg_hi; seg += bk.ctas_per_blk * wpc) {
+    const int row = p.seg_row[seg], start = p.seg_start[seg], len = p.seg_len[seg];
+    const float a = sign * __ldg(own + row);
+    for (int base = 0; base < len; base += 32 * kCcdDepth) {
+      int c[kCcdDepth];
+      float r[kCcdDepth];
+#pragma unroll
+      for (int d = 0; d < kCcdDepth; d++) {
+        const int j = base + d * 32 + lane;
+        c[d] = j < len ? __ldg(p.ind + start + j) - g_lo : -1;
+        r[d] = j < len ? p.res[start + j] : 0.f;
+      }
+#pragma unroll
+      for (int d = 0; d < kCcdDepth; d++)
+        if (c[d] >= 0) p.res[start + base + d * 32 + lane] = __fadd_rn(r[d], __fmul_rn(a, ccd_sm[c[d]]));
+    }
+  }
+}
+
+// plan of the sub-segments (row x block of the gathered index range), block-major
+__global__ void ccd_blk_count_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ ind, const uint8_t *__restrict__ mask,
+                                     int32_t row_lo, int32_t n, int nb, int block, int chunk, int32_t *__restrict__ nch,
+                                     int32_t *__restrict__ valid) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)n * nb) return;
+  const int b = (int)(t / n), i = (int)(t - (int64_t)b * n), r = row_lo + i;
+  const int64_t s = ptr[r], len = ptr[r + 1] - s;
+  const bool ok = len > 0 && !(mask && mask[r]);
+  if (b == 0) valid[i] = ok ? 1 : 0;
+  int cnt = 0;
+  if (ok) {
+    auto lower = [&](int key) {
+      int64_t lo = 0, hi = len;
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (ind[s + mid] < key) lo = mid + 1; else hi = mid;
+      }
+      return lo;
+    };
+    const int64_t a0 = lower(b * block), a1 = b + 1 < nb ? lower((b + 1) * block) : len;
+    cnt = (int)((a1 - a0 + chunk - 1) / chunk);
+  }
+  nch[t] = cnt;
+}
+
+__global__ void ccd_blk_fill_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ ind, int32_t row_lo, int32_t n, int nb,
+                                    int block, int chunk, const int32_t *__restrict__ nch, const int32_t *__restrict__ off,
+                                    const int32_t *__restrict__ slot_of, int32_t *__restrict__ seg_row, int32_t *__restrict__ seg_start,
+                                    int32_t *__restrict__ seg_len, int32_t *__restrict__ seg_slot, int32_t *__restrict__ multi_row) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)n * nb) return;
+  const int b = (int)(t / n), i = (int)(t - (int64_t)b * n), r = row_lo + i;
+  const int cnt = nch[t];
+  if (b == 0 && (cnt > 0 || slot_of[i + 1] > slot_of[i])) multi_row[slot_of[i]] = r;
+  if (cnt == 0) return;
+  const int64_t s = ptr[r], len = ptr[r + 1] - s;
+  auto lower = [&](int key) {
+    int64_t lo = 0, hi = len;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (ind[s + mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  };
+  const int64_t a0 = lower(b * block), a1 = b + 1 < nb ? lower((b + 1) * block) : len;
+  const int64_t per = (a1 - a0 + cnt - 1) / cnt;
+  for (int k = 0; k < cnt; k++) {
+    const int64_t lo = a0 + k * per, hi = lo + per < a1 ? lo + per : a1;
+    const int q = off[t] + k;
+    seg_row[q] = r;
+    seg_start[q] = (int32_t)(s + lo);
+    seg_len[q] = (int32_t)(hi - lo);
+    seg_slot[q] = slot_of[i];
+  }
+}
+
+// block_off (host, [nb + 1]) and d_off (device copy) describe the segment range of every block
+static int build_block_seg_plan(mfb_engine *e, const int64_t *ptr, const int32_t *ind, const uint8_t *mask, int32_t row_lo,
+                                int32_t row_hi, int nb, SegPlan *out, std::vector<int32_t> *block_off, int32_t **d_off) {
+  out->release();
+  out->built = true;
+  block_off->assign((size_t)nb + 1, 0);
+  const int32_t n = row_hi - row_lo;
+  cudaStream_t st = e->stream;
+  if (!*d_off) MFB_CUDA(dev_alloc(d_off, sizeof(int32_t) * ((size_t)nb + 1)));
+  MFB_CUDA(cudaMemsetAsync(*d_off, 0, sizeof(int32_t) * ((size_t)nb + 1), st));
+  if (n <= 0) return 0;
+  const size_t total = (size_t)n * nb;
+  int32_t *nch, *off, *valid, *slot_of;
+  MFB_CUDA(dev_alloc(&nch, sizeof(int32_t) * (2 * (total + 1) + 2 * ((size_t)n + 1))));
+  off = nch + total + 1;
+  valid = off + total + 1;
+  slot_of = valid + n + 1;
+  MFB_CUDA(cudaMemsetAsync(nch, 0, sizeof(int32_t) * (2 * (total + 1) + 2 * ((size_t)n + 1)), st));
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  MFB_LAUNCH(ccd_blk_count_kernel, grid, 256, 0, st, ptr, ind, mask, row_lo, n, nb, kCcdBlock, kCcdChunk, nch, valid);
+  size_t tmp_bytes = 0, tmp2 = 0;
+  MFB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, nch, off, (int)(total + 1), st));
+  MFB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, valid, slot_of, n + 1, st));
+  MFB_TRY(ensure_scratch(e, std::max(tmp_bytes, tmp2)));
+  MFB_CUDA(cub::DeviceScan::ExclusiveSum(e->scratch, tmp_bytes, nch, off, (int)(total + 1), st));
+  MFB_CUDA(cub::DeviceScan::ExclusiveSum(e->scratch, tmp2, valid, slot_of, n + 1, st));
+  std::vector<int32_t> h_off(total + 1);
+  int32_t n_valid = 0;
+  MFB_CUDA(cudaMemcpyAsync(h_off.data(), off, sizeof(int32_t) * (total + 1), cudaMemcpyDeviceToHost, st));
+  MFB_CUDA(cudaMemcpyAsync(&n_valid, slot_of + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  MFB_CUDA(cudaStreamSynchronize(st));
+  for (int b = 0; b <= nb; b++) (*block_off)[b] = h_off[(size_t)b * n];
+  const int32_t ns = h_off[total];
+  out->n_seg = ns;
+  out->n_multi = n_valid;
+  out->max_len = kCcdChunk;
+  MFB_CUDA(cudaMemcpyAsync(*d_off, block_off->data(), sizeof(int32_t) * ((size_t)nb + 1), cudaMemcpyHostToDevice, st));
+  const size_t nsz = (size_t)std::max(ns, 1), nmz = (size_t)std::max(n_valid, 1);
+  MFB_CUDA(dev_alloc(&out->row, sizeof(int32_t) * nsz));
+  MFB_CUDA(dev_alloc(&out->start, sizeof(int32_t) * nsz));
+  MFB_CUDA(dev_alloc(&out->len, sizeof(int32_t) * nsz));
+  MFB_CUDA(dev_alloc(&out->slot, sizeof(int32_t) * nsz));
+  MFB_CUDA(dev_alloc(&out->multi_row, sizeof(int32_t) * nmz));
+  if (ns > 0)
+    MFB_LAUNCH(ccd_blk_fill_kernel, grid, 256, 0, st, ptr, ind, row_lo, n, nb, kCcdBlock, kCcdChunk, nch, off, slot_of, out->row,
+               out->start, out->len, out->slot, out->multi_row);
+  MFB_CUDA(cudaStreamSynchronize(st));  // block_off (host vector) has been copied
+  dev_free(nch);
+  return 0;
+}
+
+// Which plan a side's passes use: 0 = plain kernels (gather through L1 / L2), 1 = the whole gathered vector staged
+// (one block, the ordinary row plan), 2 = blocked plan.  Blocking pays while the sub-segments stay long enough for a
+// warp (>= 64 ratings on average).
+static int ccd_side_mode(const mfb_engine *e, int64_t nnz_side, int n_rows_side, int gather_n) {
+  if (!e->opt_ccd_smem || gather_n <= 0) return 0;
+  const int nb = (gather_n + kCcdBlock - 1) / kCcdBlock;
+  if (nb == 1) return 1;
+  if (n_rows_side <= 0 || (double)nnz_side / ((double)n_rows_side * nb) < 64.0) return 0;
+  return 2;
+}
+
+// With lazy module loading (the CUDA 12 default) the first launch of a kernel loads it, and that load waits for the
+// device.  Several engines of ONE process exchange through spinning barrier kernels: a variant launched for the first
+// time while a peer's barrier is already spinning (the add-back forms first run in the second sweep) would then block
+// the host thread that still has to issue that peer's partner — a deadlock until the flag wait times out.  So every
+// kernel of the rank-one step is loaded here, before the first barrier exists.
+static int ccd_preload_kernels() {
+  cudaFuncAttributes fa;
+  MFB_CUDA(cudaFuncGetAttributes(&fa, ccd_resid_kernel));
+  MFB_CUDA(cudaFuncGetAttributes(&fa, ccd_update_kernel<false, false>));
+  MFB_CUDA(cudaFuncGetAttributes(&fa, ccd_update_kernel<true, false>));
+  MFB_CUDA(cudaFuncGetAttributes(&fa, ccd_update_kernel<false, true>));
+  MFB_CUDA(cudaFuncGetAttributes(&fa, ccd_update_sm_kernel<false, false>));
+  MFB_CUDA(cudaFuncGetAttributes(&fa, ccd_update_sm_kernel<true, false>));
+  MFB_CUDA(cudaFuncGetAttributes(&fa, ccd_update_sm_kernel<true, true>));
+  MFB_CUDA(cudaFuncGetAttributes(&fa, ccd_resid_sm_kernel));
+  MFB_CUDA(cudaFuncGetAttributes(&fa, ccd_finalize_kernel));
+  MFB_CUDA(cudaFuncGetAttributes(&fa, col_extract_kernel));
+  MFB_CUDA(cudaFuncGetAttributes(&fa, col_insert_kernel));
+  return 0;
+}
+
 int ccdpp_begin_impl(mfb_engine *e) {
   DevCsr &m = e->mat[MFB_TRAIN];
   cudaStream_t st = e->stream;
+  MFB_TRY(ccd_preload_kernels());
   size_t nn = (size_t)(m.nnz > 0 ? m.nnz : 1);
   if (!e->res_row) MFB_CUDA(dev_alloc(&e->res_row, sizeof(float) * nn));
   if (!e->res_col) MFB_CUDA(dev_alloc(&e->res_col, sizeof(float) * nn));
-  if (!e->uk) MFB_CUDA(dev_alloc(&e->uk, sizeof(float) * e->n_users));
-  if (!e->vk) MFB_CUDA(dev_alloc(&e->vk, sizeof(float) * e->n_items));
-  if (!e->uk_old) MFB_CUDA(dev_alloc(&e->uk_old, sizeof(float) * e->n_users));
+  if (!e->uk) MFB_CUDA(dev_alloc(&e->uk, sizeof(float) * ((size_t)e->n_users + 4)));
+  if (!e->vk) MFB_CUDA(dev_alloc(&e->vk, sizeof(float) * ((size_t)e->n_items + 4)));
+  if (!e->uk_old) MFB_CUDA(dev_alloc(&e->uk_old, sizeof(float) * ((size_t)e->n_users + 4)));
   // res = gk_csr_Dup(trainMat) (modelMF.cpp:1013); uFac.fill(0) (:1020)
   MFB_CUDA(cudaMemcpyAsync(e->res_row, m.rowval, sizeof(float) * (size_t)m.nnz, cudaMemcpyDeviceToDevice, st));
   MFB_CUDA(cudaMemcpyAsync(e->res_col, m.colval, sizeof(float) * (size_t)m.nnz, cudaMemcpyDeviceToDevice, st));
   MFB_CUDA(cudaMemsetAsync(e->U, 0, sizeof(float) * (size_t)e->n_users * e->ld, st));
-  if (!m.ccd_rows.built)
-    MFB_TRY(build_seg_plan(e, m.rowptr, e->n_users, e->bad_user, e->row_begin[MFB_USER], e->row_end[MFB_USER],
-                           kCcdChunk, &m.ccd_rows));
-  if (!m.ccd_cols.built)
-    MFB_TRY(build_seg_plan(e, m.colptr, e->n_items, e->bad_item, e->row_begin[MFB_ITEM], e->row_end[MFB_ITEM],
-                           kCcdChunk, &m.ccd_cols));
-  size_t slots = (size_t)max(m.ccd_rows.n_multi, m.ccd_cols.n_multi);
+  const int ulo = e->row_begin[MFB_USER], uhi = e->row_end[MFB_USER], ilo = e->row_begin[MFB_ITEM], ihi = e->row_end[MFB_ITEM];
+  if (!m.ccd_rows.built) {
+    MFB_TRY(build_seg_plan(e, m.rowptr, e->n_users, e->bad_user, ulo, uhi, kCcdChunk, &m.ccd_rows));
+    const int64_t nnz_side = (int64_t)((double)m.nnz * (double)(uhi - ulo) / std::max(e->n_users, 1));
+    m.ccd_rows_mode = ccd_side_mode(e, nnz_side, uhi - ulo, e->n_items);  // the row passes gather v_k
+    if (m.ccd_rows_mode == 2) {
+      MFB_TRY(build_block_seg_plan(e, m.rowptr, m.rowind, e->bad_user, ulo, uhi, (e->n_items + kCcdBlock - 1) / kCcdBlock,
+                                   &m.ccd_rows_blk, &m.ccd_rows_blk_off, &m.ccd_rows_doff));
+    } else if (m.ccd_rows_mode == 1) {
+      const int32_t off2[2] = {0, m.ccd_rows.n_seg};
+      if (!m.ccd_rows_doff) MFB_CUDA(dev_alloc(&m.ccd_rows_doff, sizeof(off2)));
+      MFB_CUDA(cudaMemcpy(m.ccd_rows_doff, off2, sizeof(off2), cudaMemcpyHostToDevice));
+    }
+  }
+  if (!m.ccd_cols.built) {
+    MFB_TRY(build_seg_plan(e, m.colptr, e->n_items, e->bad_item, ilo, ihi, kCcdChunk, &m.ccd_cols));
+    const int64_t nnz_side = (int64_t)((double)m.nnz * (double)(ihi - ilo) / std::max(e->n_items, 1));
+    m.ccd_cols_mode = ccd_side_mode(e, nnz_side, ihi - ilo, e->n_users);  // the column passes gather u_k
+    if (m.ccd_cols_mode == 2) {
+      MFB_TRY(build_block_seg_plan(e, m.colptr, m.colind, e->bad_item, ilo, ihi, (e->n_users + kCcdBlock - 1) / kCcdBlock,
+                                   &m.ccd_cols_blk, &m.ccd_cols_blk_off, &m.ccd_cols_doff));
+    } else if (m.ccd_cols_mode == 1) {
+      const int32_t off2[2] = {0, m.ccd_cols.n_seg};
+      if (!m.ccd_cols_doff) MFB_CUDA(dev_alloc(&m.ccd_cols_doff, sizeof(off2)));
+      MFB_CUDA(cudaMemcpy(m.ccd_cols_doff, off2, sizeof(off2), cudaMemcpyHostToDevice));
+    }
+  }
+  size_t slots = (size_t)std::max(std::max(m.ccd_rows.n_multi, m.ccd_cols.n_multi), std::max(m.ccd_rows_blk.n_multi, m.ccd_cols_blk.n_multi));
   if (slots > e->ccd_acc_slots) {
     if (e->ccd_acc) MFB_CUDA(dev_free(e->ccd_acc));
     e->ccd_acc = nullptr;
@@ -192,15 +502,86 @@ int ccdpp_begin_impl(mfb_engine *e) {
   return 0;
 }
 
+namespace {
+// one side (rows = users over the CSR residual, columns = items over the CSC residual) of the rank-one step
+struct CcdSide {
+  CcdPass plain, blk;
+  int mode, nb, gather_n;
+  const int32_t *doff;
+  const SegPlan *sp_plain, *sp_blk;
+};
+
+template <bool ADDBACK, bool TWO>
+int ccd_launch_update_sm(mfb_engine *e, const CcdPass &p, float *own, const float *other, const float *other_old, float reg,
+                         const Aux *aux, int thresh, const CcdPeers &pe, const CcdSide &sd) {
+  const int n_stage = (std::min(kCcdBlock, sd.gather_n) + 3) & ~3;
+  const size_t smem = sizeof(float) * (size_t)(TWO ? kCcdBlock + n_stage : n_stage);
+  CcdBlk bk{sd.doff, sd.nb, kCcdBlock, sd.gather_n, std::max(1, e->sm_count * (smem > 100 * 1024 ? 1 : 2) / sd.nb)};
+  MFB_CUDA(cudaFuncSetAttribute(ccd_update_sm_kernel<ADDBACK, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MFB_LAUNCH((ccd_update_sm_kernel<ADDBACK, TWO>), sd.nb * bk.ctas_per_blk, 512, smem, e->stream, p, own, other, other_old, reg,
+             e->ccd_acc, aux, thresh, pe, bk);
+  return 0;
+}
+
+int ccd_launch_resid_sm(mfb_engine *e, const CcdPass &p, const float *own, const float *other, float sign, const CcdSide &sd) {
+  const size_t smem = sizeof(float) * (size_t)((std::min(kCcdBlock, sd.gather_n) + 3) & ~3);
+  CcdBlk bk{sd.doff, sd.nb, kCcdBlock, sd.gather_n, std::max(1, e->sm_count * 2 / sd.nb)};
+  MFB_CUDA(cudaFuncSetAttribute(ccd_resid_sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MFB_LAUNCH(ccd_resid_sm_kernel, sd.nb * bk.ctas_per_blk, 512, smem, e->stream, p, own, other, sign, bk);
+  return 0;
+}
+
+// own[row] = sum res * other / (reg + sum other^2) over the side's rows; addback / subtract: the fused forms of
+// ccd_update_kernel (subtract only exists for the plain kernels; the staged passes subtract in a pass of their own)
+int ccd_update_side(mfb_engine *e, const CcdSide &sd, float *own, const float *other, const float *other_old, float reg,
+                    const Aux *aux, int thresh, const CcdPeers &pe, bool addback, bool subtract) {
+  cudaStream_t st = e->stream;
+  const int tb = 256, wpb = tb / 32;
+  const SegPlan *sp = sd.mode == 2 ? sd.sp_blk : sd.sp_plain;
+  const CcdPass &p = sd.mode == 2 ? sd.blk : sd.plain;
+  if (p.n_seg > 0) {
+    if (sd.mode == 0) {
+      const int grid = (p.n_seg + wpb - 1) / wpb;
+      if (addback) MFB_LAUNCH((ccd_update_kernel<true, false>), grid, tb, 0, st, p, own, other, other_old, reg, e->ccd_acc, aux, thresh, pe);
+      else if (subtract) MFB_LAUNCH((ccd_update_kernel<false, true>), grid, tb, 0, st, p, own, other, other, reg, e->ccd_acc, aux, thresh, pe);
+      else MFB_LAUNCH((ccd_update_kernel<false, false>), grid, tb, 0, st, p, own, other, other, reg, e->ccd_acc, aux, thresh, pe);
+    } else if (addback && other_old != other) {
+      MFB_TRY((ccd_launch_update_sm<true, true>(e, p, own, other, other_old, reg, aux, thresh, pe, sd)));
+    } else if (addback) {
+      MFB_TRY((ccd_launch_update_sm<true, false>(e, p, own, other, other, reg, aux, thresh, pe, sd)));
+    } else {
+      MFB_TRY((ccd_launch_update_sm<false, false>(e, p, own, other, other, reg, aux, thresh, pe, sd)));
+    }
+  }
+  if (sp->n_multi)
+    MFB_LAUNCH(ccd_finalize_kernel, (sp->n_multi + 255) / 256, 256, 0, st, sp->multi_row, sp->n_multi, e->ccd_acc, own, reg, aux,
+               thresh, pe);
+  return 0;
+}
+
+int ccd_resid_side(mfb_engine *e, const CcdSide &sd, const float *own, const float *other, float sign, int only_multi) {
+  const CcdPass &p = sd.mode == 2 ? sd.blk : sd.plain;
+  if (p.n_seg <= 0) return 0;
+  if (sd.mode == 0) {
+    const int tb = 256, wpb = tb / 32;
+    MFB_LAUNCH(ccd_resid_kernel, (p.n_seg + wpb - 1) / wpb, tb, 0, e->stream, p, own, other, sign, only_multi);
+    return 0;
+  }
+  return ccd_launch_resid_sm(e, p, own, other, sign, sd);
+}
+}  // namespace
+
 int ccdpp_rank1_impl(mfb_engine *e, int32_t k, int first_iter, int32_t inner, float ureg, float ireg,
                      int32_t item_freq_thresh) {
   DevCsr &m = e->mat[MFB_TRAIN];
   cudaStream_t st = e->stream;
-  const SegPlan &rp = m.ccd_rows, &cp = m.ccd_cols;
-  CcdPass rows{m.rowind, e->res_row, rp.row, rp.start, rp.len, rp.slot, rp.n_seg};
-  CcdPass cols{m.colind, e->res_col, cp.row, cp.start, cp.len, cp.slot, cp.n_seg};
-  const int tb = 256, wpb = tb / 32;
-  const int g_rows = (rp.n_seg + wpb - 1) / wpb, g_cols = (cp.n_seg + wpb - 1) / wpb;
+  const SegPlan &rp = m.ccd_rows, &cp = m.ccd_cols, &rb = m.ccd_rows_blk, &cb = m.ccd_cols_blk;
+  CcdSide rows{{m.rowind, e->res_row, rp.row, rp.start, rp.len, rp.slot, rp.n_seg},
+               {m.rowind, e->res_row, rb.row, rb.start, rb.len, rb.slot, rb.n_seg},
+               m.ccd_rows_mode, m.ccd_rows_mode == 2 ? (int)m.ccd_rows_blk_off.size() - 1 : 1, e->n_items, m.ccd_rows_doff, &rp, &rb};
+  CcdSide cols{{m.colind, e->res_col, cp.row, cp.start, cp.len, cp.slot, cp.n_seg},
+               {m.colind, e->res_col, cb.row, cb.start, cb.len, cb.slot, cb.n_seg},
+               m.ccd_cols_mode, m.ccd_cols_mode == 2 ? (int)m.ccd_cols_blk_off.size() - 1 : 1, e->n_users, m.ccd_cols_doff, &cp, &cb};
   // row-sharded: this rank owns users [ulo, uhi) and items [ilo, ihi); every new u_k / v_k entry is also
   // stored into the peers' vectors and a flag barrier closes each pass
   const int ulo = e->row_begin[MFB_USER], uhi = e->row_end[MFB_USER], ilo = e->row_begin[MFB_ITEM], ihi = e->row_end[MFB_ITEM];
@@ -217,42 +598,26 @@ int ccdpp_rank1_impl(mfb_engine *e, int32_t k, int first_iter, int32_t inner, fl
   // the FreqAdap rule zeroes v_k of infrequent items for k > 0 (modelMF.cpp:1336-1342)
   const int thresh = (item_freq_thresh > 0 && k > 0) ? item_freq_thresh : 0;
   const bool fuse_add = !first_iter && inner >= 1 && e->opt_ccd_fuse;          // add-back rides on the first updates
-  const bool fuse_sub = inner >= (fuse_add ? 2 : 1) && e->opt_ccd_fuse;        // column subtract rides on the last v_k update
+  // the column subtract rides on the last v_k update pass (plain kernels only)
+  const bool fuse_sub = inner >= (fuse_add ? 2 : 1) && e->opt_ccd_fuse && cols.mode == 0;
   if (!first_iter && !fuse_add) {
-    if (g_rows) MFB_LAUNCH(ccd_resid_kernel, g_rows, tb, 0, st, rows, e->uk, e->vk, 1.0f, 0);
-    if (g_cols) MFB_LAUNCH(ccd_resid_kernel, g_cols, tb, 0, st, cols, e->vk, e->uk, 1.0f, 0);
+    MFB_TRY(ccd_resid_side(e, rows, e->uk, e->vk, 1.0f, 0));
+    MFB_TRY(ccd_resid_side(e, cols, e->vk, e->uk, 1.0f, 0));
   }
   if (fuse_add)  // the column add-back needs u_k as it was before its first update
     MFB_CUDA(cudaMemcpyAsync(e->uk_old, e->uk, sizeof(float) * (size_t)e->n_users, cudaMemcpyDeviceToDevice, st));
   for (int s = 0; s < inner; s++) {
-    if (g_rows) {
-      if (s == 0 && fuse_add)
-        MFB_LAUNCH((ccd_update_kernel<true, false>), g_rows, tb, 0, st, rows, e->uk, e->vk, e->vk, ureg, e->ccd_acc, e->aux_u, 0, pu);
-      else
-        MFB_LAUNCH((ccd_update_kernel<false, false>), g_rows, tb, 0, st, rows, e->uk, e->vk, e->vk, ureg, e->ccd_acc, e->aux_u, 0, pu);
-    }
-    if (rp.n_multi)
-      MFB_LAUNCH(ccd_finalize_kernel, (rp.n_multi + 255) / 256, 256, 0, st, rp.multi_row, rp.n_multi, e->ccd_acc, e->uk,
-                 ureg, e->aux_u, 0, pu);
+    MFB_TRY(ccd_update_side(e, rows, e->uk, e->vk, e->vk, ureg, e->aux_u, 0, pu, s == 0 && fuse_add, false));
     MFB_TRY(comm_barrier_launch(e));
-    if (g_cols) {
-      if (s == 0 && fuse_add)
-        MFB_LAUNCH((ccd_update_kernel<true, false>), g_cols, tb, 0, st, cols, e->vk, e->uk, e->uk_old, ireg, e->ccd_acc, e->aux_i, thresh, pv);
-      else if (s == inner - 1 && fuse_sub)
-        MFB_LAUNCH((ccd_update_kernel<false, true>), g_cols, tb, 0, st, cols, e->vk, e->uk, e->uk, ireg, e->ccd_acc, e->aux_i, thresh, pv);
-      else
-        MFB_LAUNCH((ccd_update_kernel<false, false>), g_cols, tb, 0, st, cols, e->vk, e->uk, e->uk, ireg, e->ccd_acc, e->aux_i, thresh, pv);
-    }
-    if (cp.n_multi)
-      MFB_LAUNCH(ccd_finalize_kernel, (cp.n_multi + 255) / 256, 256, 0, st, cp.multi_row, cp.n_multi, e->ccd_acc, e->vk,
-                 ireg, e->aux_i, thresh, pv);
+    MFB_TRY(ccd_update_side(e, cols, e->vk, e->uk, e->uk_old, ireg, e->aux_i, thresh, pv, s == 0 && fuse_add,
+                            s == inner - 1 && fuse_sub && !(s == 0 && fuse_add)));
     MFB_TRY(comm_barrier_launch(e));
   }
-  if (g_rows) MFB_LAUNCH(ccd_resid_kernel, g_rows, tb, 0, st, rows, e->uk, e->vk, -1.0f, 0);
+  MFB_TRY(ccd_resid_side(e, rows, e->uk, e->vk, -1.0f, 0));
   if (fuse_sub) {
-    if (g_cols && cp.n_multi) MFB_LAUNCH(ccd_resid_kernel, g_cols, tb, 0, st, cols, e->vk, e->uk, -1.0f, 1);
-  } else if (g_cols) {
-    MFB_LAUNCH(ccd_resid_kernel, g_cols, tb, 0, st, cols, e->vk, e->uk, -1.0f, 0);
+    if (cp.n_multi) MFB_TRY(ccd_resid_side(e, cols, e->vk, e->uk, -1.0f, 1));
+  } else {
+    MFB_TRY(ccd_resid_side(e, cols, e->vk, e->uk, -1.0f, 0));
   }
   if (uhi > ulo) MFB_LAUNCH(col_insert_kernel, (uhi - ulo + 255) / 256, 256, 0, st, e->U, e->ld, k, ulo, uhi, e->uk);
   if (ihi > ilo) MFB_LAUNCH(col_insert_kernel, (ihi - ilo + 255) / 256, 256, 0, st, e->V, e->ld, k, ilo, ihi, e->vk);

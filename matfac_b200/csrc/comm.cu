@@ -43,6 +43,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 __device__ __forceinline__ void wait_flag(const unsigned long long *p, unsigned long long want, unsigned long long *err) {
   const unsigned long long t0 = global_ns();
   while (ld_acquire_sys(p) < want) {
+    if (*reinterpret_cast<volatile unsigned long long *>(err) != 0ull) break;  // an earlier wait already failed: do not add 20 s per wait
     __nanosleep(200);
     if (global_ns() - t0 > kWaitTimeoutNs) {
       atomicExch(err, 1ull);
@@ -162,8 +163,8 @@ extern "C" int mfb_comm_init(mfb_engine *e, int32_t rank, int32_t world, uint8_t
   Comm &c = e->comm;
   c.rank = rank;
   c.world = world;
-  if (!e->uk) MFB_CUDA(dev_alloc(&e->uk, sizeof(float) * e->n_users));
-  if (!e->vk) MFB_CUDA(dev_alloc(&e->vk, sizeof(float) * e->n_items));
+  if (!e->uk) MFB_CUDA(dev_alloc(&e->uk, sizeof(float) * ((size_t)e->n_users + 4)));
+  if (!e->vk) MFB_CUDA(dev_alloc(&e->vk, sizeof(float) * ((size_t)e->n_items + 4)));
   if (!c.own_flags) {
     MFB_CUDA(dev_alloc(&c.own_flags, sizeof(unsigned long long) * (kFlagSlots + 2)));
     MFB_CUDA(cudaMemset(c.own_flags, 0, sizeof(unsigned long long) * (kFlagSlots + 2)));
@@ -208,6 +209,12 @@ extern "C" int mfb_comm_connect(mfb_engine *e, const uint8_t *all_handles, int64
 // Everything else (push kernels, sequence flags, barriers) is the same code as the one-process-per-GPU path.
 extern "C" int mfb_comm_connect_local(mfb_engine **engines, int32_t world) {
   MFB_REQUIRE(engines && world >= 1 && world <= kMaxRanks, "mfb_comm_connect_local: 1..8 engines");
+  {  // load the exchange kernels now: a lazy first load must not happen while a peer's flag wait is already spinning
+    cudaFuncAttributes fa;
+    MFB_CUDA(cudaFuncGetAttributes(&fa, comm_barrier_kernel));
+    MFB_CUDA(cudaFuncGetAttributes(&fa, comm_wait_kernel));
+    MFB_CUDA(cudaFuncGetAttributes(&fa, comm_push_rows_kernel));
+  }
   for (int r = 0; r < world; r++) MFB_REQUIRE(engines[r] && !engines[r]->comm.connected, "mfb_comm_connect_local: null or already connected engine");
   for (int r = 0; r < world; r++)
     MFB_REQUIRE(engines[r]->n_users == engines[0]->n_users && engines[r]->n_items == engines[0]->n_items &&
@@ -227,8 +234,8 @@ extern "C" int mfb_comm_connect_local(mfb_engine **engines, int32_t world) {
     Comm &c = e->comm;
     c.rank = r;
     c.world = world;
-    if (!e->uk) MFB_CUDA(dev_alloc(&e->uk, sizeof(float) * e->n_users));
-    if (!e->vk) MFB_CUDA(dev_alloc(&e->vk, sizeof(float) * e->n_items));
+    if (!e->uk) MFB_CUDA(dev_alloc(&e->uk, sizeof(float) * ((size_t)e->n_users + 4)));
+    if (!e->vk) MFB_CUDA(dev_alloc(&e->vk, sizeof(float) * ((size_t)e->n_items + 4)));
     if (!c.own_flags) MFB_CUDA(dev_alloc(&c.own_flags, sizeof(unsigned long long) * (kFlagSlots + 2)));
     MFB_CUDA(cudaMemset(c.own_flags, 0, sizeof(unsigned long long) * (kFlagSlots + 2)));
     c.barrier_seq = 0;

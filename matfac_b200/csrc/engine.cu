@@ -163,9 +163,17 @@ void SegPlan::release() {
   *this = SegPlan();
 }
 
+void DevCsr::release_ccd() {
+  ccd_rows.release(); ccd_cols.release(); ccd_rows_blk.release(); ccd_cols_blk.release();
+  dev_free(ccd_rows_doff); dev_free(ccd_cols_doff);
+  ccd_rows_doff = ccd_cols_doff = nullptr;
+  ccd_rows_blk_off.clear(); ccd_cols_blk_off.clear();
+  ccd_rows_mode = ccd_cols_mode = 0;
+}
+
 void DevCsr::release() {
   dev_free(rowptr); dev_free(colptr); dev_free(rowind); dev_free(colind); dev_free(rowval); dev_free(colval);
-  eval_rows.release(); als_rows.release(); als_cols.release(); ccd_rows.release(); ccd_cols.release();
+  eval_rows.release(); als_rows.release(); als_cols.release(); release_ccd();
   *this = DevCsr();
 }
 
@@ -327,6 +335,12 @@ using namespace mfb;
 extern "C" const char *mfb_last_error(void) { return g_last_error.c_str(); }
 extern "C" uint64_t mfb_launch_count(void) { return g_launches.load(); }
 
+extern "C" int32_t mfb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  return n;
+}
+
 extern "C" int mfb_create(const mfb_config *cfg, mfb_engine **out) {
   MFB_REQUIRE(cfg && out, "mfb_create: null argument");
   MFB_REQUIRE(cfg->n_users > 0 && cfg->n_items > 0, "mfb_create: empty matrix");
@@ -449,7 +463,7 @@ extern "C" int mfb_upload_csr(mfb_engine *e, int which, int32_t nrows, int32_t n
   // cudaFree / cudaMalloc of GB-sized buffers cost milliseconds each
   const bool reuse = m.rowptr && m.nnz == nnz && m.nrows == nrows && m.ncols == ncols && ((colptr != nullptr) == (m.colptr != nullptr));
   if (reuse) {
-    m.eval_rows.release(); m.als_rows.release(); m.als_cols.release(); m.ccd_rows.release(); m.ccd_cols.release();
+    m.eval_rows.release(); m.als_rows.release(); m.als_cols.release(); m.release_ccd();
   } else {
     m.release();
   }
@@ -534,7 +548,7 @@ extern "C" int mfb_build_csc(mfb_engine *e, int which) {
   cudaStream_t st = e->stream;
   dev_free(m.colptr); dev_free(m.colind); dev_free(m.colval);
   m.colptr = nullptr; m.colind = nullptr; m.colval = nullptr;
-  m.als_cols.release(); m.ccd_cols.release();
+  m.als_cols.release(); m.release_ccd();
   const int64_t nnz = m.nnz;
   const size_t nn = (size_t)(nnz > 0 ? nnz : 1);
   MFB_CUDA(dev_alloc(&m.colptr, sizeof(int64_t) * ((size_t)e->n_items + 1)));
@@ -582,8 +596,7 @@ static void invalidate_plans(mfb_engine *e) {
     e->mat[w].eval_rows.release();
     e->mat[w].als_rows.release();
     e->mat[w].als_cols.release();
-    e->mat[w].ccd_rows.release();
-    e->mat[w].ccd_cols.release();
+    e->mat[w].release_ccd();
   }
 }
 
@@ -734,6 +747,7 @@ extern "C" int mfb_set_option(mfb_engine *e, const char *name, double value) {
   else if (n == "sgd_hot_stab") e->opt_sgd_hot_stab = value;
   else if (n == "sgd_hot_stages") e->opt_sgd_hot_stages = (int)value;
   else if (n == "ccd_fuse") e->opt_ccd_fuse = (int)value;
+  else if (n == "ccd_smem") { e->opt_ccd_smem = (int)value; for (int w = 0; w < 3; w++) e->mat[w].release_ccd(); }
   else if (n == "als_tensor_cores") e->opt_als_tensor_cores = (int)value;
   else if (n == "als_dual") e->opt_als_dual = (int)value;
   else if (n == "als_chunk") {

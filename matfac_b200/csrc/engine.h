@@ -83,6 +83,13 @@ struct DevCsr {
   SegPlan eval_rows;   // chunked, for mfb_eval
   SegPlan als_rows, als_cols;
   SegPlan ccd_rows, ccd_cols;
+  // CCD++ passes with the gathered vector staged in shared memory (csrc/ccdpp.cu): mode 0 = plain kernels, 1 = whole
+  // vector staged over the plain plan, 2 = plan split at the block boundaries of the gathered index range
+  SegPlan ccd_rows_blk, ccd_cols_blk;
+  std::vector<int32_t> ccd_rows_blk_off, ccd_cols_blk_off;  // [blocks + 1] first segment of every block
+  int32_t *ccd_rows_doff = nullptr, *ccd_cols_doff = nullptr;  // device copies
+  int ccd_rows_mode = 0, ccd_cols_mode = 0;
+  void release_ccd();
   void release();
 };
 
@@ -179,6 +186,7 @@ struct mfb_engine {
   double opt_sgd_hot_stab = 0.5;      // hot CTAs: mini-batch <= value / (learnrate x rating-weighted mean |u|^2)
   int opt_sgd_hot_pace = 1;           // hot CTAs advance through their list in step with the shuffled kernel
   int opt_sgd_hot_batch = 0;          // ratings per round of a hot CTA, 0 = automatic (<= 64 and <= sgd_flat_hot_lr / learnrate)
+  int opt_ccd_smem = 1;               // CCD++: gathered u_k / v_k staged in shared memory where the shape allows
   int opt_ccd_fuse = 1;               // CCD++: add-back / column subtract ride on the first / last update passes
   int opt_als_chunk = 16384;          // ratings per CTA before a row is split over several CTAs
   int opt_als_dual = 1;               // short rows: solve the len x len dual system instead of rank x rank

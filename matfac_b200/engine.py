@@ -22,7 +22,7 @@ VARIANT = {"mf": MF, "IFWMF": IFWMF, "TMF": TMF, "TMFDropout": TMFDROPOUT}
 
 # every symbol include/mfb.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "mfb_last_error", "mfb_launch_count", "mfb_create", "mfb_destroy", "mfb_sync", "mfb_pin_host",
+    "mfb_last_error", "mfb_launch_count", "mfb_device_count", "mfb_create", "mfb_destroy", "mfb_sync", "mfb_pin_host",
     "mfb_unpin_host", "mfb_upload_csr", "mfb_set_masks", "mfb_upload_factors", "mfb_download_factors",
     "mfb_set_aux", "mfb_sgd_plan", "mfb_sgd_subepoch", "mfb_sgd_block_nnz", "mfb_debug_sgd_records", "mfb_debug_sgd_hot_batch", "mfb_sgd_epoch_flat", "mfb_set_option", "mfb_als_half_step", "mfb_debug_als_gram",
     "mfb_ccdpp_begin", "mfb_ccdpp_rank1", "mfb_ccdpp_end", "mfb_eval", "mfb_eval_groups", "mfb_snapshot_best",

@@ -178,14 +178,31 @@ int Model::deviceVariant() const { return MFB_MF; }
 void Model::uploadAux(DeviceSession &, const Data *, std::unordered_set<int> &, std::unordered_set<int> &) {}
 
 void Model::uploadFactors(DeviceSession &s) {
-  s.check(mfb_upload_factors(s.eng, uFac.data(), facDim, iFac.data(), facDim));
+  for (int r = 0; r < s.world(); r++) s.check(mfb_upload_factors(s.engineOf(r), uFac.data(), facDim, iFac.data(), facDim));
+}
+
+// the model's auxiliaries into every engine of the session (uploadAux writes to s.eng)
+void Model::uploadAuxAll(DeviceSession &s, const Data *data, std::unordered_set<int> &invalidUsers,
+                         std::unordered_set<int> &invalidItems) {
+  uploadAux(s, data, invalidUsers, invalidItems);
+  for (size_t w = 0; w < s.workers.size(); w++) {
+    std::swap(s.eng, s.workers[w]);
+    uploadAux(s, nullptr, invalidUsers, invalidItems);
+    std::swap(s.eng, s.workers[w]);
+  }
 }
 
 // objective = true: weighted SSE over train + uReg |U|^2 + iReg |V|^2; false: RMSE over `which`
 double Model::deviceEval(DeviceSession &s, int which, bool objective) {
   double out[4] = {0, 0, 0, 0};
   const int variant = deviceVariant();
-  s.check(mfb_eval(s.eng, which, MFB_CURRENT, variant, objective && variant == MFB_IFWMF, objective, out));
+  // row-sharded sessions: every engine evaluates its own rows (and the norms of its own ranges), the sums add up
+  const int nEval = s.mode == matfac::GROUP_ROWS ? s.world() : 1;
+  for (int r = 0; r < nEval; r++) {
+    double part[4] = {0, 0, 0, 0};
+    s.check(mfb_eval(s.engineOf(r), which, MFB_CURRENT, variant, objective && variant == MFB_IFWMF, objective, part));
+    for (int k = 0; k < 4; k++) out[k] += part[k];
+  }
   if (objective) return out[0] + out[2] * uReg + out[3] * iReg;
   return sqrt(out[0] / out[1]);
 }
@@ -196,7 +213,7 @@ double Model::RMSE(gk_csr_t *mat, std::unordered_set<int> &invalidUsers, std::un
   DeviceSession &s = DeviceSession::forMatrix(mat, nUsers, nItems, facDim, &which);
   s.setMasks(invalidUsers, invalidItems);
   uploadFactors(s);
-  uploadAux(s, nullptr, invalidUsers, invalidItems);
+  uploadAuxAll(s, nullptr, invalidUsers, invalidItems);
   return deviceEval(s, which, false);
 }
 
@@ -218,7 +235,16 @@ void Model::groupSE(gk_csr_t *mat, const std::vector<uint8_t> &userGroup, const 
     s = &DeviceSession::forMatrix(mat, nUsers, nItems, facDim, &which);
     s->setMasks(invalidUsers, invalidItems);
     uploadFactors(*s);
-    uploadAux(*s, nullptr, invalidUsers, invalidItems);
+    uploadAuxAll(*s, nullptr, invalidUsers, invalidItems);
+  }
+  if (s->mode == matfac::GROUP_ROWS && s->world() > 1) {  // every engine its own rows
+    for (int k = 0; k < 32; k++) out[k] = 0;
+    for (int r = 0; r < s->world(); r++) {
+      double part[32];
+      s->check(mfb_eval_groups(s->engineOf(r), which, MFB_CURRENT, deviceVariant(), ug.data(), ig.data(), part));
+      for (int k = 0; k < 32; k++) out[k] += part[k];
+    }
+    return;
   }
   s->check(mfb_eval_groups(s->eng, which, MFB_CURRENT, deviceVariant(), ug.data(), ig.data(), out));
 }
@@ -256,7 +282,7 @@ double Model::objective(const Data &data, std::unordered_set<int> &invalidUsers,
   DeviceSession &s = DeviceSession::forData(data, facDim);
   s.setMasks(invalidUsers, invalidItems);
   uploadFactors(s);
-  uploadAux(s, &data, invalidUsers, invalidItems);
+  uploadAuxAll(s, &data, invalidUsers, invalidItems);
   return deviceEval(s, MFB_TRAIN, true);
 }
 
@@ -290,6 +316,7 @@ bool Model::isTerminateModel(Model &bestModel, const Data &data, int iter, int &
         } else {
           dev_->check(mfb_upload_factors(dev_->eng, bestModel.uFac.data(), facDim, bestModel.iFac.data(), facDim));
         }
+        dev_->broadcastFactors();  // the other engines of the session restart from the same factors
       } else {
         uFac = bestModel.uFac;
         iFac = bestModel.iFac;
@@ -367,7 +394,7 @@ bool Model::isTerminateModel(Model &bestModel, const Data &data, int iter, int &
 // Common preamble of every trainer (modelMF.cpp:34-61): invalid ids, initial objective and
 // validation RMSE — plus the device set-up that replaces the host arrays.
 void Model::beginTraining(const Data &data, Model &bestModel, std::unordered_set<int> &invalidUsers,
-                          std::unordered_set<int> &invalidItems, Stop &st, const char *tag) {
+                          std::unordered_set<int> &invalidItems, Stop &st, const char *tag, int groupMode) {
   (void)bestModel;
   gk_csr_t *trainMat = data.trainMat;
   std::vector<std::unordered_set<int>> uISet;
@@ -377,9 +404,10 @@ void Model::beginTraining(const Data &data, Model &bestModel, std::unordered_set
   for (int item = trainMat->ncols; item < data.nItems; item++) invalidItems.insert(item);
 
   DeviceSession &s = DeviceSession::forData(data, facDim);
+  s.ensureGroup((matfac::GroupMode)groupMode);  // every visible GPU for the trainers that shard
   s.setMasks(invalidUsers, invalidItems);
   uploadFactors(s);
-  uploadAux(s, &data, invalidUsers, invalidItems);
+  uploadAuxAll(s, &data, invalidUsers, invalidItems);
   dev_ = &s;
   bestOnDevice_ = false;
 
@@ -460,7 +488,7 @@ void Model::runFlatSgd(const Data &data, Model &bestModel, std::unordered_set<in
 void Model::runStratifiedSgd(const Data &data, Model &bestModel, std::unordered_set<int> &invalidUsers,
                              std::unordered_set<int> &invalidItems, const char *tag, bool saves) {
   Stop st;
-  beginTraining(data, bestModel, invalidUsers, invalidItems, st, tag);
+  beginTraining(data, bestModel, invalidUsers, invalidItems, st, tag, matfac::GROUP_STRATA);
   DeviceSession &s = *dev_;
   gk_csr_t *trainMat = data.trainMat;
   std::vector<int> trainUsers = matfac::validIds(trainMat->nrows, invalidUsers);
@@ -475,21 +503,81 @@ void Model::runStratifiedSgd(const Data &data, Model &bestModel, std::unordered_
   std::cout << "train items: " << trainItems.size() << " itemsPerPart: " << trainItems.size() / P << std::endl;
   std::vector<int> userPart = matfac::partitionIds(trainUsers, P, nUsers);
   std::vector<int> itemPart = matfac::partitionIds(trainItems, P, nItems);
-  s.check(mfb_set_option(s.eng, "sgd_shuffle_seed", (double)(uint32_t)trainSeed));
-  s.check(mfb_sgd_plan(s.eng, P, userPart.data(), itemPart.data()));
+  // Several GPUs: user part p is pinned to engine p mod N — that engine plans and trains only the ratings
+  // of its own user parts — and an item part travels to the engine that needs it in the next sub-epoch (peer-memory
+  // push + sequence flag, csrc/comm.cu).  With one engine this is the plain P x P plan.
+  const int N = s.world();
+  std::vector<std::vector<int32_t>> ownUsers(N);
+  for (int r = 0; r < N; r++) {
+    std::vector<int> mine(userPart);
+    if (N > 1)
+      for (int u = 0; u < nUsers; u++) {
+        if (mine[u] >= 0 && mine[u] % N != r) mine[u] = -1;
+        else if (mine[u] >= 0) ownUsers[r].push_back(u);
+      }
+    s.check(mfb_set_option(s.engineOf(r), "sgd_shuffle_seed", (double)(uint32_t)trainSeed));
+    // every user's run starts at its own pseudo-random item and wraps: thousands of runs that all begin at the lowest
+    // item ids would hit the same few item rows at once (measured: the 1/20-scale bench matrix diverges in epoch 1
+    // without it at learnrate 0.002, where the reference's own trainSGDPar does not; profiles/r2_dsgd_parity.md)
+    s.check(mfb_set_option(s.engineOf(r), "sgd_rotate", 1));
+    s.check(mfb_sgd_plan(s.engineOf(r), P, mine.data(), itemPart.data()));
+  }
   const int variant = deviceVariant();
-  std::vector<std::pair<int, int>> updateSeq;
-  std::vector<int32_t> blocks(2 * (size_t)P);
+  std::vector<std::pair<int, int>> updateSeq, nextSeq;
+  std::vector<int> holder(P, -1);                              // engine that holds the current rows of an item part (-1: all)
+  std::vector<std::vector<uint64_t>> pushed(N, std::vector<uint64_t>(N, 0));  // pushes issued src -> dst so far
+  sgdUpdateBlockSeq(P, updateSeq, mt);
   for (int iter = 0; iter < maxIter; iter++) {
     s.check(mfb_event_record(s.eng, 0));
     for (int k = 0; k < P; k++) {
-      sgdUpdateBlockSeq(P, updateSeq, mt);
+      const bool lastOfEpoch = k == P - 1;
+      // the reference draws one sequence per sub-epoch from the same engine (modelMF.cpp:274); drawing the next one
+      // before this sub-epoch is launched (to know where every item part goes) leaves the stream unchanged
+      if (!lastOfEpoch || iter + 1 < maxIter) sgdUpdateBlockSeq(P, nextSeq, mt);
+      std::vector<std::vector<int32_t>> blocks(N);
       for (int t = 0; t < P; t++) {
-        blocks[2 * t] = updateSeq[t].first;
-        blocks[2 * t + 1] = updateSeq[t].second;
+        const int r = N > 1 ? updateSeq[t].first % N : 0;
+        blocks[r].push_back(updateSeq[t].first);
+        blocks[r].push_back(updateSeq[t].second);
       }
-      s.check(mfb_sgd_subepoch(s.eng, blocks.data(), P, variant, learnRate, uReg, iReg, (uint64_t)(uint32_t)trainSeed,
-                               (uint64_t)iter * P + k));
+      for (int r = 0; r < N; r++) {
+        if (blocks[r].empty()) continue;
+        mfb_engine *e = s.engineOf(r);
+        if (N > 1) {  // wait until every item part of this sub-epoch has arrived from its previous holder
+          std::vector<char> seen(N, 0);
+          for (size_t b = 1; b < blocks[r].size(); b += 2) {
+            const int h = holder[blocks[r][b]];
+            if (h >= 0 && h != r && !seen[h]) {
+              seen[h] = 1;
+              s.check(mfb_comm_wait_block(e, h, pushed[h][r]));
+            }
+          }
+        }
+        s.check(mfb_sgd_subepoch(e, blocks[r].data(), (int32_t)(blocks[r].size() / 2), variant, learnRate, uReg, iReg,
+                                 (uint64_t)(uint32_t)trainSeed, (uint64_t)iter * P + k));
+      }
+      if (N > 1) {
+        for (int t = 0; t < P; t++) holder[updateSeq[t].second] = updateSeq[t].first % N;
+        if (!lastOfEpoch) {
+          // hand every item part to the engine that trains it next; holder[] keeps naming the source of the newest
+          // rows, which is what the receiver waits on (pushes of one source complete in issue order)
+          for (int t = 0; t < P; t++) {
+            const int part = nextSeq[t].second, dst = nextSeq[t].first % N, src = holder[part];
+            if (src >= 0 && src != dst) s.check(mfb_dsgd_push_block(s.engineOf(src), part, dst, ++pushed[src][dst]));
+          }
+        }
+      }
+      updateSeq.swap(nextSeq);
+    }
+    if (N > 1) {
+      // end of the epoch: every engine publishes the item parts it holds and its own users' rows to all peers, so
+      // that the evaluation (engine 0) and the next epoch start from complete, identical factors everywhere
+      for (int b = 0; b < P; b++)
+        if (holder[b] >= 0) s.check(mfb_dsgd_push_block(s.engineOf(holder[b]), b, -1, 0));
+      for (int r = 0; r < N; r++)
+        s.check(mfb_comm_allgather_rows(s.engineOf(r), MFB_USER, ownUsers[r].empty() ? nullptr : ownUsers[r].data(), 0,
+                                        (int32_t)ownUsers[r].size()));
+      std::fill(holder.begin(), holder.end(), -1);
     }
     s.check(mfb_event_record(s.eng, 1));
     const double dur = elapsedSeconds(s);

@@ -125,6 +125,8 @@ class Model {
   // upload the per-user / per-item auxiliaries this model's update and prediction rules need
   virtual void uploadAux(matfac::DeviceSession &s, const Data *data, std::unordered_set<int> &invalidUsers,
                          std::unordered_set<int> &invalidItems);
+  void uploadAuxAll(matfac::DeviceSession &s, const Data *data, std::unordered_set<int> &invalidUsers,
+                    std::unordered_set<int> &invalidItems);
   void copyScalarsFrom(const Model &o);
   void uploadFactors(matfac::DeviceSession &s);
   double deviceEval(matfac::DeviceSession &s, int which, bool objective);
@@ -134,8 +136,9 @@ class Model {
     int bestIter = -1;
     double bestObj = 0, prevObj = 0, bestValRMSE = 0, prevValRMSE = 0;
   };
+  // groupMode: matfac::GroupMode — how the session's engines (one per visible GPU) share this trainer's work
   void beginTraining(const Data &data, Model &bestModel, std::unordered_set<int> &invalidUsers,
-                     std::unordered_set<int> &invalidItems, Stop &st, const char *tag);
+                     std::unordered_set<int> &invalidItems, Stop &st, const char *tag, int groupMode = 0);
   void endTraining(Model &bestModel);
   void syncBest(Model &bestModel);
   // returns true when training must stop; prints the reference's progress line

@@ -33,12 +33,13 @@ void ModelMF::trainALS(const Data &data, Model &bestModel, std::unordered_set<in
                        std::unordered_set<int> &invalidItems) {
   std::cout << "\nModelMF::trainALS trainSeed: " << trainSeed;
   Stop st;
-  beginTraining(data, bestModel, invalidUsers, invalidItems, st, "ModelMF::trainALS");
+  // rows sharded over every visible GPU: each engine solves its row range and stores the solved rows into all peers
+  beginTraining(data, bestModel, invalidUsers, invalidItems, st, "ModelMF::trainALS", matfac::GROUP_ROWS);
   DeviceSession &s = *dev_;
   for (int iter = 0; iter < maxIter; iter++) {
     s.check(mfb_event_record(s.eng, 0));
-    s.check(mfb_als_half_step(s.eng, MFB_USER, uReg));
-    s.check(mfb_als_half_step(s.eng, MFB_ITEM, iReg));
+    for (int r = 0; r < s.world(); r++) s.check(mfb_als_half_step(s.engineOf(r), MFB_USER, uReg));
+    for (int r = 0; r < s.world(); r++) s.check(mfb_als_half_step(s.engineOf(r), MFB_ITEM, iReg));
     s.check(mfb_event_record(s.eng, 1));
     float ms = 0;
     s.check(mfb_event_elapsed_ms(s.eng, 0, 1, &ms));
@@ -53,7 +54,7 @@ void ModelMF::runCcdpp(const Data &data, Model &bestModel, std::unordered_set<in
                        std::unordered_set<int> &invalidItems, bool freqAdap, const char *tag) {
   std::cout << "\n" << tag << " trainSeed: " << trainSeed;
   Stop st;
-  beginTraining(data, bestModel, invalidUsers, invalidItems, st, tag);
+  beginTraining(data, bestModel, invalidUsers, invalidItems, st, tag, matfac::GROUP_ROWS);
   DeviceSession &s = *dev_;
   if (freqAdap) {
     // itemFreq of the train matrix feeds the "fewer than 75 ratings" rule (modelMF.cpp:1204-1206,1336)
@@ -61,22 +62,25 @@ void ModelMF::runCcdpp(const Data &data, Model &bestModel, std::unordered_set<in
     std::vector<int32_t> uf(nUsers, 0), itf(nItems, 0);
     for (size_t u = 0; u < freq.first.size(); u++) uf[u] = (int32_t)freq.first[u];
     for (size_t i = 0; i < freq.second.size(); i++) itf[i] = (int32_t)freq.second[i];
-    s.check(mfb_set_aux(s.eng, MFB_MF, uf.data(), itf.data(), nullptr, nullptr, nullptr, nullptr, nullptr));
+    for (int r = 0; r < s.world(); r++)
+      s.check(mfb_set_aux(s.engineOf(r), MFB_MF, uf.data(), itf.data(), nullptr, nullptr, nullptr, nullptr, nullptr));
   }
   std::mt19937 mt(trainSeed);
   std::vector<int> dims(facDim);
   std::iota(dims.begin(), dims.end(), 0);
-  s.check(mfb_ccdpp_begin(s.eng));  // residual = ratings, U = 0 (modelMF.cpp:1013,1020)
+  for (int r = 0; r < s.world(); r++) s.check(mfb_ccdpp_begin(s.engineOf(r)));  // residual = ratings, U = 0 (modelMF.cpp:1013,1020)
   for (int iter = 0; iter < maxIter; iter++) {
     s.check(mfb_event_record(s.eng, 0));
     if (!freqAdap) std::shuffle(dims.begin(), dims.end(), mt);  // commented out in the FreqAdap twin (:1271)
-    for (int k : dims) s.check(mfb_ccdpp_rank1(s.eng, k, iter == 0, 5, uReg, iReg, freqAdap ? 75 : 0));
+    for (int k : dims)  // step by step for all engines: the barriers between the passes run on the devices
+      for (int r = 0; r < s.world(); r++)
+        s.check(mfb_ccdpp_rank1(s.engineOf(r), k, iter == 0, 5, uReg, iReg, freqAdap ? 75 : 0));
     s.check(mfb_event_record(s.eng, 1));
     float ms = 0;
     s.check(mfb_event_elapsed_ms(s.eng, 0, 1, &ms));
     if (afterEpoch(data, bestModel, iter, st, invalidUsers, invalidItems, ms * 1e-3, tag, true)) break;
   }
-  s.check(mfb_ccdpp_end(s.eng));
+  for (int r = 0; r < s.world(); r++) s.check(mfb_ccdpp_end(s.engineOf(r)));
   endTraining(bestModel);
   bestModel.saveFacs(std::string(data.prefix));
   std::cout << "\nBest model validation RMSE: " << bestModel.RMSE(data.valMat, invalidUsers, invalidItems) << std::endl;

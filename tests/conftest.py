@@ -1,7 +1,12 @@
 import os
 import sys
 
+import os
+
 import pytest
+
+# engines of one process wait for each other on the device (tests/test_multi_rank.py): load every kernel up front
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests")):

@@ -369,3 +369,49 @@ def test_python_reference_plan_matches_oracle(P):
     for t in range(24):
         assert sorted(sched[t]) == list(range(P))
         assert np.array_equal(sched[t][pairs[t, :, 0]], pairs[t, :, 1])
+
+
+def _two_engine_devices():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return "0,1" if torch.cuda.device_count() >= 2 else "0,0"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,extra", [("als", dict(ureg=0.1, ireg=0.1)), ("ccd++", {}), ("ccdpp_plain", {})])
+def test_cli_sharded_trainers_on_several_engines_match_oracle(tmp_path, method, extra):
+    """`mf` with several engines in one process (MATFAC_DEVICES; two GPUs when the box has them, else two engines on
+    one GPU — the same peer-memory protocol): row-sharded ALS / CCD++ against the oracle, as the single-engine test."""
+    files = synth.write_split_files(str(tmp_path), *synth.make_splits(500, 300, 40000, seed=13))
+    fl = dict(BASE); fl.update(extra); fl["maxiter"] = 4
+    dump = str(tmp_path / "gpu")
+    out = run_mf(files, dump, threads=2, algo="mf", mf_method=method, env_extra={"MATFAC_DEVICES": _two_engine_devices() + ",0"}, **fl)
+    assert "3 GPUs, peer memory" in out
+    m = oracle_run(files, "mf", method, 2, fl)
+    U, V = m.factors(); bU, bV = m.factors(best=True)
+    for name, want in (("last_uFac", U), ("last_iFac", V), ("best_uFac", bU), ("best_iFac", bV)):
+        got = ol.read_mat(os.path.join(dump, name + ".bin"))
+        assert rel_err(got, want) < 1e-4, (name, rel_err(got, want))
+    res = dict(line.split(None, 1) for line in open(os.path.join(dump, "result.txt")))
+    assert abs(float(res["best_val_rmse"]) - m.rmse(1, best=True)) < 1e-4 * m.rmse(1, best=True)
+    assert abs(float(res["last_objective"]) - m.objective()) < 1e-4 * m.objective()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("algo,threads,extra", [("mf", 4, {}), ("mf", 3, {}), ("IFWMF", 4, dict(rhorms=100.0))])
+def test_cli_stratified_sgd_on_several_engines_matches_oracle(tmp_path, algo, threads, extra):
+    """`mf --mf_method sgdpar` over two engines: P = OMP threads user / item parts as in the reference, user part p on
+    engine p mod 2, item parts pushed between the engines.  Same bar as the single-engine CLI test: best-model
+    validation / test RMSE within 0.5 % of the oracle's trainSGDPar after the same number of epochs."""
+    files = synth.write_split_files(str(tmp_path), *synth.make_splits(3000, 1500, 300000, seed=21))
+    fl = dict(BASE); fl.update(extra); fl.update(facdim=10, maxiter=40)
+    dump = str(tmp_path / "gpu")
+    out = run_mf(files, dump, threads=threads, algo=algo, mf_method="sgdpar", env_extra={"MATFAC_DEVICES": _two_engine_devices()}, **fl)
+    assert "2 GPUs, peer memory" in out
+    m = oracle_run(files, algo, "sgdpar", threads, fl)
+    res = dict(line.split(None, 1) for line in open(os.path.join(dump, "result.txt")))
+    for key, want in (("best_val_rmse", m.rmse(1, best=True)), ("best_test_rmse", m.rmse(2, best=True))):
+        got = float(res[key])
+        assert abs(got - want) <= 0.005 * want, (key, got, want)
+    assert abs(float(res["learn_rate"]) - m.learn_rate) < 1e-9

@@ -43,13 +43,15 @@ def main():
     out = {"matrix": {"n_users": nu, "n_items": ni, "train_nnz": int(ptr[-1]), "crc": prob["crc"]}, "lr": a.lr,
            "inflight_frac": a.inflight, "curves": {}, "ms_per_epoch": {}}
     for cfg in a.configs:
-        plan, order = cfg.split(":")
+        parts = cfg.split(":")  # plan:block_order[:option=value[,option=value...]]
+        plan, order = parts[0], parts[1]
+        extra = dict((kv.split("=")[0], float(kv.split("=")[1])) for kv in parts[2].split(",")) if len(parts) > 2 else {}
         for world in a.worlds:
             for seed in (1, 2):
                 t0 = time.time()
                 d = dsgd.Dsgd(nu, ni, 64, world, {r: r % ndev for r in range(world)}, prob["train"], prob["val"], U0, V0, bad_u,
                               bad_i, a.epochs * world, plan=plan, seed=seed, block_order=int(order),
-                              options={"sgd_flat_inflight_frac": a.inflight})
+                              options=dict({"sgd_flat_inflight_frac": a.inflight}, **extra))
                 curve, ms = [], []
                 e0 = d.engines[0]
                 for ep in range(a.epochs):
@@ -63,7 +65,7 @@ def main():
                     ms.append(e0.event_elapsed_ms(0, 1))
                 err = any(e.comm_error() for e in d.engines.values()) if world > 1 else False
                 d.close()
-                key = f"{plan}_order{order}_N{world}_seed{seed}"
+                key = f"{cfg}_N{world}_seed{seed}"
                 out["curves"][key] = curve
                 out["ms_per_epoch"][key] = float(np.median(ms))
                 print(key, f"{time.time()-t0:.0f}s", f"{np.median(ms):.2f}ms", "COMM_ERROR" if err else "",
