@@ -145,8 +145,10 @@ int mfb_sgd_epoch_flat(mfb_engine *e, int variant, float learn_rate, float ureg,
  * 0 = one band, a uniformly shuffled epoch as in modelMF.cpp:76-81 (banding converges at a different rate
  * per epoch than the reference's order); takes effect at the next mfb_sgd_plan), "ccd_fuse" (CCD++: 1 = the residual add-back rides on the first u_k / v_k update pass and the column subtract on the
  * last v_k update pass of a rank-one step — same statements in the same order, 11 instead of 14 passes; 0 = one pass each),
- * "als_tensor_cores" (rank > 64: 1 = tcgen05 3xTF32 Gram, 0 = fp32 CUDA-core
- * Gram), "als_dual" (1 = rows with fewer ratings than half the padded rank are solved through the len x len
+ * "als_tensor_cores" (rank > 32: 1 = tcgen05 3xTF32 Gram in the warp-specialised persistent kernel, default; 0 = fp32
+ * CUDA-core Gram; 2 = one CTA per row, rank > 64 only), "als_ws_split" (warp-specialised kernel: 0 = the split between
+ * converter teams and solver groups is picked per half-step from the mean row length, default; 1 = the
+ * many-short-rows split, 2 = the few-long-rows split), "als_dual" (1 = rows with fewer ratings than half the padded rank are solved through the len x len
  * dual system F (F F^T + reg I)^-1 r, default; 0 = always the rank x rank normal equations), "als_chunk" (ratings
  * one CTA accumulates before a row is split over several CTAs that add into a workspace, default 16384), "sgd_block_order" (stratified trainers: 0 = user-major runs, 1 = shuffled inside the
  * blocks), "sgd_atomic" (1 = item rows updated by reductions, 0 = plain stores), "sgd_rotate" (1 = every

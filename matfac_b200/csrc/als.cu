@@ -467,12 +467,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// the same with a suspend-time hint: the hardware parks the warp until the phase completes or `ns` have passed, so a
+// waiting warp leaves the issue slots to the warps that work (profiles/r2_als.md: plain polling made ~45 % of all
+// instructions of the warp-specialised kernel, which was issue-bound at 0.86 instructions per scheduler cycle)
+__device__ __forceinline__ bool mbar_try_wait_parked(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   unsigned long long t0 = 0;
   for (uint32_t spins = 1;; spins++) {
-    if (mbar_try_wait(bar, parity)) return;
-    if ((spins & 0x3FFu) == 0) {
+    if (mbar_try_wait_parked(bar, parity, 20000u)) return;
+    if ((spins & 0x3Fu) == 0) {
       unsigned long long now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       if (t0 == 0) t0 = now;
@@ -505,6 +521,22 @@ __device__ __forceinline__ float round_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+}
+// round to nearest (ties away from zero) on the 10-bit tf32 mantissa for finite values: two integer instructions
+// where cvt.rna.tf32.f32 is expanded into four (it also keeps inf / NaN intact)
+__device__ __forceinline__ float round_tf32_fast(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -777,44 +809,64 @@ __global__ void __launch_bounds__(256, 4) als_dual_kernel(const AlsArgs a) {
 //                         per tile (R >= C) of the 16 x 16 tile grid — hold a tile in registers and run the tile
 //                         Cholesky + both triangular solves (chol_solve_core) with barriers over the group only, so G
 //                         rows are being solved while the next Gram is accumulated.
-constexpr int kWsKT = 32;            // ratings per tile
-constexpr int kWsProducers = 128;
+constexpr int kWsTeam = 128;         // threads of a converter team
 constexpr int kWsGroupThreads = 160;
 constexpr uint32_t kWsSbo = 144;     // bytes between 8-dim core matrices (16 B of padding: conflict-free transposing stores)
+// named barriers (hardware ids 1 .. 15): converter team t -> 1 + t (<= 4 teams), drain warps of solver group g ->
+// kWsDrainBar0 + g, whole solver group g -> kWsGroupBar0 + g (<= 4 groups); the three ranges must not overlap
+constexpr int kWsDrainBar0 = 5, kWsGroupBar0 = 9;
+constexpr int kWsFirst = 0x100, kWsLast = 0x200;  // tile descriptor flags: first / last tile of its row
 
-template <int TR>
+// NT converter teams and G solver groups per CTA: a half-step over many short rows (users) is bound by the solves, one
+// over few long rows (items) by the conversion of the gathered rows — the launcher picks the split per side.
+template <int TR, int NT_, int G_>
 struct AlsWs {
   static constexpr int RP = 16 * TR;
+  static constexpr int QP = RP / 4;                               // 16-byte units per factor row
+  static constexpr int KT = 512 / QP;                             // ratings per tile: 32 (RP = 64) / 16 (RP = 128) — a tile is
+                                                                  // 128 units of (4 ratings x 16 bytes), one per team thread
+  static constexpr int NGRP = KT / 4;                             // 4-rating K groups of a tile (8 / 4)
+  static constexpr int NT = NT_;                                  // converter teams (tile g belongs to team g mod NT)
+  static constexpr int G = G_;                                    // solver groups
   static constexpr int MCORES = 2 * RP / 8;                       // core matrices along M of [big; small]
   static constexpr uint32_t LBO = MCORES * kWsSbo;                // bytes between 4-rating K groups
-  static constexpr uint32_t OP_BYTES = (kWsKT / 4) * LBO;         // one operand stage
-  static constexpr int NS = TR == 8 ? 2 : 3;                      // operand stages
-  static constexpr int NR = TR == 8 ? 4 : 8;                      // raw stages (tiles of gathered factor rows in flight)
-  static constexpr int MR = NR + 2;                               // (item, rating) ring
+  static constexpr uint32_t OP_BYTES = (KT / 4) * LBO;            // one operand stage (18 KB)
+  static constexpr int NS = NT_ > 3 ? NT_ : 3;                    // operand stages; >= NT: a team moves NT tiles ahead per step and
+                                                                  // may be at most one phase of a stage's barrier ahead of the MMAs
+  static constexpr int NRT = NT_ >= 4 ? 3 : 4;                    // raw stages per team (tiles of gathered rows in flight)
+  static constexpr int MR = 8;                                    // (item, rating, descriptor) ring per team: the scheduler warp
+                                                                  // runs up to MR team tiles ahead of the converters
   static constexpr uint32_t RAW_ROW = RP * 4;                     // bytes per staged factor row
-  static constexpr uint32_t RAW_BYTES = kWsKT * RAW_ROW;
-  static constexpr int G = TR == 8 ? 2 : 4;                       // solver groups
-  static constexpr int NTHREADS = kWsProducers + G * kWsGroupThreads;
+  static constexpr uint32_t RAW_BYTES = KT * RAW_ROW;             // 8 KB
+  // thread map: NT converter teams | NT scheduler warps | the warp that issues the tensor-core instructions | G solver groups
+  static constexpr int SCHED0 = NT * kWsTeam;
+  static constexpr int MMA0 = SCHED0 + NT * 32;
+  static constexpr int SOLVER0 = MMA0 + 32;
+  static constexpr int NTHREADS = SOLVER0 + G * kWsGroupThreads;
   static constexpr int ACC_COLS = TR == 8 ? 256 : 64;             // TMEM columns of one accumulator
   static constexpr int NACC = G;                                  // one accumulator per solver group: group g drains the
                                                                   // phases of "its" accumulator in order (no parity aliasing)
-  static constexpr int TMEM_COLS = NACC * ACC_COLS;
+  static constexpr int TMEM_USED = NACC * ACC_COLS;
+  static constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;  // allocations are powers of two
   static constexpr int T2 = TR * TR, TS = T2 + 4;                 // tile stride (floats): conflict-free 128-bit loads
   static constexpr int GS_FLOATS = 136 * TS;                      // lower-triangle tiles of one Gram
   // byte offsets from the 1024-aligned base
   static constexpr uint32_t off_op = 0;
-  static constexpr uint32_t off_raw = off_op + NS * OP_BYTES;
-  static constexpr uint32_t off_gs = off_raw + NR * RAW_BYTES;
-  static constexpr uint32_t off_bvec = off_gs + G * GS_FLOATS * 4;            // [NACC][RP]
-  static constexpr uint32_t off_bred = off_bvec + NACC * RP * 4;              // [4][RP]
-  static constexpr uint32_t off_gbv = off_bred + 4 * RP * 4;                  // [G][RP]
-  static constexpr uint32_t off_meta = off_gbv + G * RP * 4;                  // [MR][32] item, [MR][32] rate
-  static constexpr uint32_t off_bars = off_meta + MR * 32 * 8;                // mbarriers
-  static constexpr int n_bars = NR + NS + 3 * NACC;
+  static constexpr uint32_t off_raw = off_op + NS * OP_BYTES;                 // [NT][NRT] stages
+  static constexpr uint32_t off_gs = off_raw + NT * NRT * RAW_BYTES;
+  static constexpr uint32_t off_bpart = off_gs + G * GS_FLOATS * 4;           // [NACC][NT * NGRP][RP] partial right-hand sides
+  static constexpr uint32_t off_gbv = off_bpart + NACC * NT * NGRP * RP * 4;  // [G][RP]
+  static constexpr uint32_t off_meta = off_gbv + G * RP * 4;                  // [NT][MR][32] item, then [NT][MR][32] rate
+  static constexpr uint32_t off_desc = off_meta + NT * MR * 32 * 8;           // [NT][MR] {ratings in the tile | kWsFirst | kWsLast, row}
+  static constexpr uint32_t off_opinfo = off_desc + NT * MR * 8;              // [NS] descriptor of the tile in each operand stage
+  static constexpr uint32_t off_bars = off_opinfo + NS * 8;                   // mbarriers
+  static constexpr int n_bars = NT * NRT + 2 * NT * MR + 2 * NS + 3 * NACC;
   static constexpr uint32_t off_tmem = off_bars + n_bars * 8;
   static constexpr size_t bytes = off_tmem + 16 + 1024;
   static_assert(CholScratch<TR>::total <= GS_FLOATS, "Cholesky scratch is carved from the drained tile buffer");
   static_assert(bytes <= 227 * 1024, "shared memory budget");
+  static_assert(NT_ >= 1 && NT_ <= 4 && G_ >= 1 && G_ <= 4, "named-barrier id ranges (kWsDrainBar0 / kWsGroupBar0)");
+  static_assert(NTHREADS <= 1024, "threads per CTA");
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -852,33 +904,40 @@ __device__ __forceinline__ void tile_of(int x, int &t, int &e) {
 }
 __device__ __forceinline__ int tri_index(int R, int C) { return R * (R + 1) / 2 + C; }
 
-template <int TR>
-__global__ void __launch_bounds__(AlsWs<TR>::NTHREADS, 1) als_ws_kernel(const AlsArgs a) {
-  using W = AlsWs<TR>;
-  constexpr int RP = W::RP, NS = W::NS, NR = W::NR, G = W::G;
+template <int TR, int NT_, int G_>
+__global__ void __launch_bounds__(AlsWs<TR, NT_, G_>::NTHREADS, 1) als_ws_kernel(const AlsArgs a) {
+  using W = AlsWs<TR, NT_, G_>;
+  constexpr int RP = W::RP, NS = W::NS, NRT = W::NRT, G = W::G, NT = W::NT, KT = W::KT, QP = W::QP, MR = W::MR, NACC = W::NACC,
+                NGRP = W::NGRP;
   extern __shared__ uint8_t sm_raw[];
   uint8_t *smb = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smb);
-  float *bvec = reinterpret_cast<float *>(smb + W::off_bvec);
-  float *bred = reinterpret_cast<float *>(smb + W::off_bred);
-  int *meta_item = reinterpret_cast<int *>(smb + W::off_meta);
-  float *meta_rate = reinterpret_cast<float *>(smb + W::off_meta + W::MR * 32 * 4);
+  float *bpart = reinterpret_cast<float *>(smb + W::off_bpart);
+  int2 *opinfo = reinterpret_cast<int2 *>(smb + W::off_opinfo);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smb + W::off_bars);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smb + W::off_tmem);
-  // mbarriers: raw_full[NR] | op_empty[NS] | acc_full[NACC] | rhs_full[NACC] | acc_empty[NACC]
-  constexpr int NACC = W::NACC;
-  const uint32_t bar_raw = smem_u32(bars), bar_op = bar_raw + NR * 8, bar_accf = bar_op + NS * 8, bar_rhs = bar_accf + NACC * 8,
-                 bar_acce = bar_rhs + NACC * 8;
+  // mbarriers: raw_full[NT][NRT] | meta_full[NT][MR] | meta_empty[NT][MR] | op_full[NS] | op_empty[NS] |
+  //            acc_full | rhs_full | acc_empty [NACC]
+  const uint32_t bar_raw = smem_u32(bars), bar_meta = bar_raw + NT * NRT * 8, bar_mempty = bar_meta + NT * MR * 8,
+                 bar_opf = bar_mempty + NT * MR * 8, bar_op = bar_opf + NS * 8, bar_accf = bar_op + NS * 8,
+                 bar_rhs = bar_accf + NACC * 8, bar_acce = bar_rhs + NACC * 8;
   const int tid = threadIdx.x, lane = tid & 31;
   const int n_rows = (int)blockIdx.x < a.nseg ? (a.nseg - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int nq = a.ld >> 2;
 
   if (tid == 0) {
-    for (int i = 0; i < NR; i++) mbar_init(bar_raw + i * 8, kWsProducers);
-    for (int i = 0; i < NS; i++) mbar_init(bar_op + i * 8, 1);
+    for (int i = 0; i < NT * NRT; i++) mbar_init(bar_raw + i * 8, kWsTeam);  // one cp.async arrival per team thread
+    for (int i = 0; i < NT * MR; i++) {
+      mbar_init(bar_meta + i * 8, 33);                // 32 cp.async arrivals + the descriptor's release
+      mbar_init(bar_mempty + i * 8, kWsTeam / 32);    // one arrival per converter warp
+    }
+    for (int i = 0; i < NS; i++) {
+      mbar_init(bar_opf + i * 8, kWsTeam / 32);
+      mbar_init(bar_op + i * 8, 1);
+    }
     for (int i = 0; i < NACC; i++) {
       mbar_init(bar_accf + i * 8, 1);
-      mbar_init(bar_rhs + i * 8, 1);
+      mbar_init(bar_rhs + i * 8, NT * kWsTeam / 32);
       mbar_init(bar_acce + i * 8, 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -892,188 +951,226 @@ __global__ void __launch_bounds__(AlsWs<TR>::NTHREADS, 1) als_ws_kernel(const Al
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (tid < kWsProducers) {
-    // ================================= producers =================================
-    const int w = tid >> 5;
-    // instruction descriptor: D = F32, A = B = TF32, both K-major; RP = 128: M = 128, N = 256; RP = 64: M = 128, N = 64
-    constexpr uint32_t NDIM = TR == 8 ? 256u : 64u;
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((NDIM >> 3) << 17) | ((128u >> 4) << 24);
-    constexpr int D = NR - 1;      // tiles whose factor rows are in flight
-    constexpr int MR = W::MR;      // meta ring: tiles g .. g + D + 1 are live
-    constexpr int QP = RP / 4;     // 16-byte units per staged row
-    // A cursor walks the tiles of this CTA's rows (row i = segment seg0 + blockIdx.x + i * gridDim.x); the descriptor of
-    // the next row is fetched when a row is entered, so that the dependent loads are off the critical path.
-    struct Cursor { int i, t, ntiles, start, len, nstart, nlen; };
-    auto fetch_next = [&](Cursor &c) {
-      c.nstart = c.nlen = 0;
-      if (c.i + 1 < n_rows) {
-        const int seg = a.seg0 + (int)blockIdx.x + (c.i + 1) * (int)gridDim.x;
-        c.nstart = __ldg(a.seg_start + seg);
-        c.nlen = __ldg(a.seg_len + seg);
-      }
-    };
-    auto init_cursor = [&](Cursor &c) {
-      c.i = 0; c.t = 0; c.ntiles = 1; c.start = c.len = 0;
-      if (n_rows > 0) {
-        const int seg = a.seg0 + (int)blockIdx.x;
-        c.start = __ldg(a.seg_start + seg);
-        c.len = __ldg(a.seg_len + seg);
-        c.ntiles = (c.len + kWsKT - 1) / kWsKT;
-      }
+  // A cursor walks the tiles of this CTA's rows (row i = segment seg0 + blockIdx.x + i * gridDim.x); the descriptor of
+  // the next row is fetched when a row is entered, so that the dependent loads are off the critical path.  Only the
+  // scheduler warps and the tensor-core thread walk cursors; the converters are told what a tile is.
+  struct Cursor { int i, t, ntiles, start, len, nstart, nlen; };
+  auto fetch_next = [&](Cursor &c) {
+    c.nstart = c.nlen = 0;
+    if (c.i + 1 < n_rows) {
+      const int seg = a.seg0 + (int)blockIdx.x + (c.i + 1) * (int)gridDim.x;
+      c.nstart = __ldg(a.seg_start + seg);
+      c.nlen = __ldg(a.seg_len + seg);
+    }
+  };
+  auto init_cursor = [&](Cursor &c) {
+    c.i = 0; c.t = 0; c.ntiles = 1; c.start = c.len = 0;
+    if (n_rows > 0) {
+      const int seg = a.seg0 + (int)blockIdx.x;
+      c.start = __ldg(a.seg_start + seg);
+      c.len = __ldg(a.seg_len + seg);
+      c.ntiles = (c.len + KT - 1) / KT;
+    }
+    fetch_next(c);
+  };
+  auto advance = [&](Cursor &c) {
+    if (c.i >= n_rows) return;
+    if (++c.t == c.ntiles) {
+      c.i++; c.t = 0;
+      c.start = c.nstart; c.len = c.nlen;
+      c.ntiles = (c.len + KT - 1) / KT;
       fetch_next(c);
-    };
-    auto advance = [&](Cursor &c) {
-      if (++c.t == c.ntiles) {
-        c.i++; c.t = 0;
-        c.start = c.nstart; c.len = c.nlen;
-        c.ntiles = (c.len + kWsKT - 1) / kWsKT;
-        fetch_next(c);
-      }
-    };
-    Cursor cm, ci, cc;  // meta-load cursor (warp 0), copy-issue cursor, consume cursor
-    init_cursor(cm);
-    ci = cm;
-    cc = cm;
-    int gm = 0, gi = 0;  // tiles whose meta has been requested / whose row copies have been issued
-    // warp 0, lane l: (item, rating) of rating l of the tile under cm -> registers (pf_*), stored to the meta ring one
-    // iteration later: the global-load latency (a fresh 128-byte line per tile) overlaps a whole tile of work
-    int pf_it = 0, pf_slot = -1;
-    float pf_rt = 0.f;
-    auto meta_request = [&]() {
-      const int j = cm.t * kWsKT + lane;
-      pf_it = 0; pf_rt = 0.f;
-      if (j < cm.len) {
-        pf_it = __ldg(a.ind + cm.start + j);
-        pf_rt = __ldg(a.val + cm.start + j);
-      }
-      if (!(pf_rt > 0.f)) pf_rt = 0.f;  // rating > 0 filter (modelMF.cpp:819); padding lanes
-      pf_slot = gm % MR;
-      gm++;
-      advance(cm);
-    };
-    auto meta_commit = [&]() {
-      if (pf_slot >= 0) {
-        meta_item[pf_slot * 32 + lane] = pf_it;
-        meta_rate[pf_slot * 32 + lane] = pf_rt;
-        pf_slot = -1;
-      }
-    };
-    // all producers: the factor rows of tile gi, 16 bytes per cp.async, a row = QP consecutive threads (coalesced);
-    // completion is counted on raw_full[stage] (cp.async.mbarrier.arrive.noinc: one arrival per producer thread)
-    auto issue_rows = [&]() {
-      const int s = gi % NR, ms = gi % MR;
-      const uint32_t dst0 = sbase + W::off_raw + s * W::RAW_BYTES;
+    }
+  };
+
+  if (tid < W::SCHED0) {
+    // ================================= converter teams =================================
+    // Team tile x (global tile x * NT + team): wait for its gathered rows, accumulate the right-hand side, split every
+    // value into tf32 big + small and store both transposed into the tile's operand stage.
+    const int team = tid / kWsTeam, tt = tid % kWsTeam;
+    const int *meta_item = reinterpret_cast<const int *>(smb + W::off_meta) + team * MR * 32;
+    const float *meta_rate = reinterpret_cast<const float *>(smb + W::off_meta + NT * MR * 32 * 4) + team * MR * 32;
+    const int2 *desc = reinterpret_cast<const int2 *>(smb + W::off_desc) + team * MR;
+    const uint32_t raw0 = sbase + W::off_raw + team * NRT * W::RAW_BYTES;
+    const uint32_t braw = bar_raw + team * NRT * 8, bmeta = bar_meta + team * MR * 8, bmempty = bar_mempty + team * MR * 8;
+    constexpr int D = NRT - 1;     // team tiles whose factor rows are in flight
+    const int q = tt % QP;         // this thread's 16-byte unit of the factor row
+    const int grp = tt / QP;       // its K group: ratings 4 grp .. 4 grp + 3 of the tile
+    const int j0 = grp * 4;
+    bool issue_done = false;
+    // the factor rows of team tile y, 16 bytes per cp.async, a row = QP consecutive threads (coalesced); completion is
+    // counted on raw_full[stage] (cp.async.mbarrier.arrive.noinc: one arrival per team thread)
+    auto issue_rows = [&](int y) {
+      const int st = y % NRT, ms = y % MR;
+      mbar_wait(bmeta + ms * 8, (uint32_t)(y / MR) & 1u);
+      const int n = desc[ms].x & 0xFF;  // ratings of the tile, 0 = the stream has ended
+      if (n == 0) { issue_done = true; return; }
+      const uint32_t dst0 = raw0 + st * W::RAW_BYTES;
 #pragma unroll
-      for (int k = 0; k < kWsKT * QP / kWsProducers; k++) {
-        const int idx = tid + k * kWsProducers, j = idx / QP, q = idx % QP;
-        if (q < nq && meta_rate[ms * 32 + j] > 0.f)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + j * W::RAW_ROW + q * 16),
-                       "l"(a.Fin + (size_t)meta_item[ms * 32 + j] * a.ld + q * 4)
+      for (int k = 0; k < KT * QP / kWsTeam; k++) {
+        const int idx = tt + k * kWsTeam, j = idx / QP, qq = idx % QP;
+        if (qq < nq && j < n && meta_rate[ms * 32 + j] > 0.f)  // rating > 0 filter (modelMF.cpp:819)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + j * W::RAW_ROW + qq * 16),
+                       "l"(a.Fin + (size_t)meta_item[ms * 32 + j] * a.ld + qq * 4)
                        : "memory");
       }
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_raw + s * 8) : "memory");
-      gi++;
-      advance(ci);
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(braw + st * 8) : "memory");
     };
-    // prologue: meta of tiles 0 .. D, copies of tiles 0 .. D - 1, request for tile D + 1
-    if (w == 0) {
-      for (int k = 0; k <= D && cm.i < n_rows; k++) { meta_request(); meta_commit(); }
-      if (cm.i < n_rows) meta_request();
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    for (int k = 0; k < D && ci.i < n_rows; k++) issue_rows();
+    // right-hand side b = sum r f: a thread keeps the partial sum of its unit over its ratings of the row and writes it
+    // into its own slot of bpart[row mod NACC] when it leaves the row — zeros for rows its team had no tile of, so
+    // that the solver group can add all NT * NGRP slots and the arrival count on rhs_full is fixed
     float4 bacc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int g = 0; cc.i < n_rows; g++) {
-      if (w == 0) {  // meta of tile g + D + 1 (requested one iteration ago) into the ring, request tile g + D + 2
-        meta_commit();
-        if (cm.i < n_rows) meta_request();
+    int brow = -1, flushed = 0;  // row bacc belongs to; rows [0, flushed) have been flushed by this thread
+    auto flush_to = [&](int upto) {
+      for (; flushed < upto; flushed++) {
+        const int acc = flushed % NACC;
+        if (flushed >= NACC) mbar_wait(bar_acce + acc * 8, (uint32_t)(flushed / NACC - 1) & 1u);  // bpart[acc] consumed
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (flushed == brow) {
+          v = bacc;
+          bacc = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        *reinterpret_cast<float4 *>(bpart + ((size_t)(acc * NT + team) * NGRP + grp) * RP + q * 4) = v;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_rhs + acc * 8);
       }
-      if (ci.i < n_rows) issue_rows();  // tile g + D, into the stage the previous iteration has finished reading
-      const int s = g % NR, ms = g % MR;
-      mbar_wait(bar_raw + s * 8, (uint32_t)(g / NR) & 1u);
-      const float4 *raw4 = reinterpret_cast<const float4 *>(smb + W::off_raw + s * W::RAW_BYTES);
-      // this thread's ratings of the tile: RP = 128: 8w .. 8w + 7, one 16-byte unit q = lane of each;
-      // RP = 64: 8w + 4h .. + 3 with h = lane / 16, q = lane % 16
-      constexpr int NI = TR == 8 ? 8 : 4;
-      const int q = TR == 8 ? lane : (lane & 15);
-      const int j0 = TR == 8 ? 8 * w : 8 * w + 4 * (lane >> 4);
-      float4 f[NI];
+    };
+    for (int k = 0; k < D && !issue_done; k++) issue_rows(k);
+    for (int x = 0;; x++) {
+      const int g = x * NT + team;  // global tile index: operand stage and order of the tensor-core instructions
+      if (x > 0) asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");  // the team has finished reading tile x - 1
+      if (!issue_done) issue_rows(x + D);  // into the stage tile x - 1 has left
+      const int st = x % NRT, ms = x % MR;
+      const int2 d = desc[ms];  // published before meta_full[ms], which issue_rows(x) has waited for
+      const int n = d.x & 0xFF;
+      if (n == 0) break;
+      mbar_wait(braw + st * 8, (uint32_t)(x / NRT) & 1u);
+      if (d.y != brow) {
+        flush_to(d.y);
+        brow = d.y;
+      }
+      const float4 *raw4 = reinterpret_cast<const float4 *>(smb + W::off_raw + (team * NRT + st) * W::RAW_BYTES);
+      const float4 rt4 = *reinterpret_cast<const float4 *>(meta_rate + ms * 32 + j0);
+      const float rts[4] = {rt4.x, rt4.y, rt4.z, rt4.w};
+      float4 f[4];
 #pragma unroll
-      for (int i = 0; i < NI; i++) {
-        const float rt = meta_rate[ms * 32 + j0 + i];
+      for (int i = 0; i < 4; i++) {
+        const bool on = j0 + i < n && rts[i] > 0.f && q < nq;  // beyond the row's end the ring holds stale values
+        const float rt = on ? rts[i] : 0.f;
         f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rt > 0.f && q < nq) f[i] = raw4[(j0 + i) * (RP / 4) + q];
+        if (on) f[i] = raw4[(j0 + i) * QP + q];
         bacc.x = fmaf(rt, f[i].x, bacc.x);
         bacc.y = fmaf(rt, f[i].y, bacc.y);
         bacc.z = fmaf(rt, f[i].z, bacc.z);
         bacc.w = fmaf(rt, f[i].w, bacc.w);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bmempty + ms * 8);  // the scheduler may refill this ring slot
       const int os = g % NS;
       if (g >= NS) mbar_wait(bar_op + os * 8, (uint32_t)(g / NS - 1) & 1u);  // the MMAs that read this stage are done
       const uint32_t op0 = sbase + W::off_op + os * W::OP_BYTES;
-#pragma unroll
-      for (int hh = 0; hh < NI / 4; hh++) {
-        const int kg = (j0 >> 2) + hh;  // 4-rating K group of the tile
-        const float fe[4][4] = {{f[4 * hh].x, f[4 * hh + 1].x, f[4 * hh + 2].x, f[4 * hh + 3].x},
-                                {f[4 * hh].y, f[4 * hh + 1].y, f[4 * hh + 2].y, f[4 * hh + 3].y},
-                                {f[4 * hh].z, f[4 * hh + 1].z, f[4 * hh + 2].z, f[4 * hh + 3].z},
-                                {f[4 * hh].w, f[4 * hh + 1].w, f[4 * hh + 2].w, f[4 * hh + 3].w}};
+      {
+        const float fe[4][4] = {{f[0].x, f[1].x, f[2].x, f[3].x}, {f[0].y, f[1].y, f[2].y, f[3].y},
+                                {f[0].z, f[1].z, f[2].z, f[3].z}, {f[0].w, f[1].w, f[2].w, f[3].w}};
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const int mdim = 4 * q + e;
           float bg[4], sl[4];
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            bg[i] = round_tf32(fe[e][i]);
-            sl[i] = round_tf32(fe[e][i] - bg[i]);
+            bg[i] = round_tf32_fast(fe[e][i]);
+            sl[i] = fe[e][i] - bg[i];  // exact in fp32; the tensor core reads its upper 19 bits (truncation: 2^-21 of f)
           }
-          const uint32_t off = (uint32_t)kg * W::LBO + (uint32_t)(mdim >> 3) * kWsSbo + (uint32_t)(mdim & 7) * 16;
+          const uint32_t off = (uint32_t)grp * W::LBO + (uint32_t)(mdim >> 3) * kWsSbo + (uint32_t)(mdim & 7) * 16;
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(op0 + off), "f"(bg[0]), "f"(bg[1]), "f"(bg[2]), "f"(bg[3]) : "memory");
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(op0 + off + (RP / 8) * kWsSbo), "f"(sl[0]), "f"(sl[1]), "f"(sl[2]), "f"(sl[3]) : "memory");
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the tensor core
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int acc = cc.i % NACC;
-      const bool first = cc.t == 0, last = cc.t == cc.ntiles - 1;
-      if (tid == 0) {
-        if (first && cc.i >= NACC) mbar_wait(bar_acce + acc * 8, (uint32_t)(cc.i / NACC - 1) & 1u);  // accumulator drained
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d = tmem_base + (uint32_t)acc * W::ACC_COLS;
-        const int kmax = last ? (cc.len - cc.t * kWsKT + 7) / 8 : kWsKT / 8;  // K steps of 8 ratings that hold data
+      if (tt == 0) opinfo[os] = d;  // what the tensor-core thread needs to know about this stage's tile
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_opf + os * 8);
+    }
+    flush_to(n_rows);
+  } else if (tid < W::MMA0) {
+    // ================================= scheduler warps (one per team) =================================
+    // Walks the team's tiles MR ahead of the converters: lane l requests (item, rating) of rating l of the tile with
+    // 4-byte cp.async copies straight into the ring, lane 0 publishes the descriptor {ratings in the tile, row}.
+    const int team = (tid - W::SCHED0) >> 5;
+    int *meta_item = reinterpret_cast<int *>(smb + W::off_meta) + team * MR * 32;
+    float *meta_rate = reinterpret_cast<float *>(smb + W::off_meta + NT * MR * 32 * 4) + team * MR * 32;
+    int2 *desc = reinterpret_cast<int2 *>(smb + W::off_desc) + team * MR;
+    const uint32_t bmeta = bar_meta + team * MR * 8, bmempty = bar_mempty + team * MR * 8;
+    Cursor c;
+    init_cursor(c);
+    for (int k = 0; k < team; k++) advance(c);  // the team's first tile is global tile `team`
+    for (int x = 0;; x++) {
+      const int slot = x % MR;
+      if (x >= MR) mbar_wait(bmempty + slot * 8, (uint32_t)(x / MR - 1) & 1u);  // the converters have left this slot
+      const bool live = c.i < n_rows;
+      if (live) {
+        const int j = c.t * KT + lane;
+        if (lane < KT && j < c.len) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(meta_item + slot * 32 + lane)), "l"(a.ind + c.start + j) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(meta_rate + slot * 32 + lane)), "l"(a.val + c.start + j) : "memory");
+        }
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bmeta + slot * 8) : "memory");
+      if (lane == 0) {
+        desc[slot] = live ? make_int2(min(KT, c.len - c.t * KT) | (c.t == 0 ? kWsFirst : 0) | (c.t == c.ntiles - 1 ? kWsLast : 0), c.i)
+                          : make_int2(0, n_rows);
+        mbar_arrive(bmeta + slot * 8);  // release: the descriptor is visible to whoever sees the phase complete
+      }
+      if (!live) break;
 #pragma unroll
-        for (int k8 = 0; k8 < kWsKT / 8; k8++) {
-          if (k8 >= kmax) break;
-          const uint64_t desc = umma_desc_kmajor(op0 + k8 * 2 * W::LBO, W::LBO, kWsSbo);
-          umma_tf32(d, desc, desc, idesc, (first && k8 == 0) ? 0u : 1u);
+      for (int k = 0; k < NT; k++) advance(c);
+    }
+  } else if (tid < W::SOLVER0) {
+    // ================================= tensor-core issue (one warp, one elected lane) =================================
+    // Takes the operand stages in global tile order.  The whole warp runs the loop converged and every operand of the
+    // instructions is warp-uniform by construction (stage, accumulator and first-tile flag are loop-carried, the
+    // last-tile flag comes out of a vote): the compiler keeps descriptors and addresses in uniform registers.  With the
+    // loop under `if (lane == 0)` each tcgen05.mma cost ~20 instructions of register -> uniform-register moves and
+    // the issuing thread, not the tensor core, bounded the kernel (1180 cycles per 32-rating tile, tensor pipe 12 %
+    // busy: profiles/r2_als.md).  All K steps of a stage are multiplied: the converters zero-fill short tiles.
+    constexpr uint32_t NDIM = TR == 8 ? 256u : 64u;
+    // instruction descriptor: D = F32, A = B = TF32, both K-major; RP = 128: M = 128, N = 256; RP = 64: M = 128, N = 64
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((NDIM >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t desc0 = umma_desc_kmajor(sbase + W::off_op, W::LBO, kWsSbo);
+    int os = 0, acc = 0, gen = 0;  // operand stage, accumulator (= row mod NACC) and its use count (= row / NACC)
+    uint32_t ph = 0;
+    bool first = true;
+    for (int rows_done = 0; rows_done < n_rows;) {
+      mbar_wait(bar_opf + os * 8, ph);  // the tile's operand stage is written
+      const bool last = __any_sync(0xFFFFFFFFu, (opinfo[os].x & kWsLast) != 0);
+      if (first && gen > 0) mbar_wait(bar_acce + acc * 8, (uint32_t)(gen - 1) & 1u);  // accumulator drained
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one_sync()) {
+        const uint32_t dt = tmem_base + (uint32_t)acc * W::ACC_COLS;
+        const uint64_t descs = desc0 + (uint64_t)((uint32_t)os * (W::OP_BYTES >> 4));
+#pragma unroll
+        for (int k8 = 0; k8 < KT / 8; k8++) {
+          const uint64_t dk = descs + (uint64_t)(k8 * ((2 * W::LBO) >> 4));
+          umma_tf32(dt, dk, dk, idesc, (first && k8 == 0) ? 0u : 1u);
         }
         umma_commit(bar_op + os * 8);
         if (last) umma_commit(bar_accf + acc * 8);
       }
+      __syncwarp();
+      first = last;
       if (last) {
-        // right-hand side of the row: 4 warp partials (RP = 64: two half-warp partials folded first)
-        if (TR != 8) {
-          bacc.x += __shfl_xor_sync(0xFFFFFFFFu, bacc.x, 16);
-          bacc.y += __shfl_xor_sync(0xFFFFFFFFu, bacc.y, 16);
-          bacc.z += __shfl_xor_sync(0xFFFFFFFFu, bacc.z, 16);
-          bacc.w += __shfl_xor_sync(0xFFFFFFFFu, bacc.w, 16);
-        }
-        if (TR == 8 || lane < 16) *reinterpret_cast<float4 *>(bred + w * RP + q * 4) = bacc;
-        bacc = make_float4(0.f, 0.f, 0.f, 0.f);
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // thread 0 is past its wait: bvec[acc] is free
-        if (tid < RP) bvec[acc * RP + tid] = (bred[tid] + bred[RP + tid]) + (bred[2 * RP + tid] + bred[3 * RP + tid]);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (tid == 0) mbar_arrive(bar_rhs + acc * 8);
+        rows_done++;
+        if (++acc == NACC) { acc = 0; gen++; }
       }
-      advance(cc);
+      if (++os == NS) { os = 0; ph ^= 1u; }
     }
   } else {
     // ================================= solver groups =================================
-    const int st = tid - kWsProducers, g = st / kWsGroupThreads, t = st % kWsGroupThreads;
+    const int st = tid - W::SOLVER0, g = st / kWsGroupThreads, t = st % kWsGroupThreads;
     float *Gs = reinterpret_cast<float *>(smb + W::off_gs) + (size_t)g * W::GS_FLOATS;
     float *gbv = reinterpret_cast<float *>(smb + W::off_gbv) + g * RP;
     using K = CholScratch<TR>;
-    const NamedBarrier group_bar{8 + g, kWsGroupThreads};
+    const NamedBarrier group_bar{kWsGroupBar0 + g, kWsGroupThreads};
     int R = -1, C = -2;
     if (t < 136) {
       R = 0;
@@ -1109,7 +1206,7 @@ __global__ void __launch_bounds__(AlsWs<TR>::NTHREADS, 1) als_ws_kernel(const Al
                                 __uint_as_float(v[4 * k4 + 2]) + __uint_as_float(x[4 * k4 + 2]), __uint_as_float(v[4 * k4 + 3]) + __uint_as_float(x[4 * k4 + 3]));
             }
           }
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(kWsDrainBar0 + g) : "memory");
           for (int c0 = 0; c0 < RP; c0 += 32) {  // + BS^T: G(c, a) += BS[a][c] for tile(c) <= tile(a)
             tmem_ld32(tad + RP + c0, x);
             tmem_ld_wait();
@@ -1138,7 +1235,7 @@ __global__ void __launch_bounds__(AlsWs<TR>::NTHREADS, 1) als_ws_kernel(const Al
               }
             }
           }
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(kWsDrainBar0 + g) : "memory");
           if (p >= 64) {
             for (int c0 = 0; c0 < RP; c0 += 32) {  // + SB: G(a, b) += SB[a][b]
               tmem_ld32(tad + c0, x);
@@ -1156,7 +1253,7 @@ __global__ void __launch_bounds__(AlsWs<TR>::NTHREADS, 1) als_ws_kernel(const Al
               }
             }
           }
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(kWsDrainBar0 + g) : "memory");
           if (p >= 64) {
             for (int c0 = 0; c0 < RP; c0 += 32) {  // + SB^T: G(c, a) += SB[a][c]
               tmem_ld32(tad + c0, x);
@@ -1170,9 +1267,14 @@ __global__ void __launch_bounds__(AlsWs<TR>::NTHREADS, 1) als_ws_kernel(const Al
             }
           }
         }
-        if (t < RP) gbv[t] = bvec[acc * RP + t];
+        if (t < RP) {  // right-hand side: the converters' partial sums
+          float sacc = 0.f;
+#pragma unroll
+          for (int k = 0; k < NT * NGRP; k++) sacc += bpart[(size_t)(acc * NT * NGRP + k) * RP + t];
+          gbv[t] = sacc;
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(bar_acce + acc * 8);  // accumulator and bvec[acc] may be reused
+        mbar_arrive(bar_acce + acc * 8);  // accumulator and bpart[acc] may be reused
       }
       group_bar();
       float tile[TR][TR];
@@ -1208,16 +1310,24 @@ __global__ void __launch_bounds__(AlsWs<TR>::NTHREADS, 1) als_ws_kernel(const Al
   if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(W::TMEM_COLS) : "memory");
 }
 
-template <int TR>
-static int launch_als_ws(mfb_engine *e, AlsArgs b, int n_primal) {
-  using W = AlsWs<TR>;
-  if (n_primal <= 0) return 0;
-  MFB_CUDA(cudaFuncSetAttribute(als_ws_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::bytes));
+template <int TR, int NT, int G>
+static int launch_als_ws_cfg(mfb_engine *e, AlsArgs b, int n_primal) {
+  using W = AlsWs<TR, NT, G>;
+  MFB_CUDA(cudaFuncSetAttribute((als_ws_kernel<TR, NT, G>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::bytes));
   b.seg0 = 0;
   b.nseg = n_primal;
   const int grid = std::min(e->sm_count, n_primal);
-  MFB_LAUNCH((als_ws_kernel<TR>), grid, W::NTHREADS, W::bytes, e->stream, b);
+  MFB_LAUNCH((als_ws_kernel<TR, NT, G>), grid, W::NTHREADS, W::bytes, e->stream, b);
   return 0;
+}
+
+// long_rows: few long rows (the item side of a ratings matrix): conversion-bound -> more converter teams, one solver group;
+// otherwise many short rows: solve-bound -> more solver groups
+template <int TR>
+static int launch_als_ws(mfb_engine *e, const AlsArgs &b, int n_primal, bool long_rows) {
+  if (n_primal <= 0) return 0;
+  if (TR == 8) return long_rows ? launch_als_ws_cfg<8, 3, 1>(e, b, n_primal) : launch_als_ws_cfg<8, 1, 2>(e, b, n_primal);
+  return long_rows ? launch_als_ws_cfg<4, 4, 1>(e, b, n_primal) : launch_als_ws_cfg<4, 2, 3>(e, b, n_primal);
 }
 
 template <int TRD>
@@ -1256,7 +1366,12 @@ static int launch_als(mfb_engine *e, const AlsArgs &a, const SegPlan &sp) {
   if (e->opt_als_dual) n_primal = TR == 8 ? n64 : TR == 4 ? n32 : TR == 2 ? n16 : sp.n_seg;
   if constexpr (TR == 8 || TR == 4) {
     if (e->opt_als_tensor_cores == 1) {
-      MFB_TRY(launch_als_ws<TR>(e, b, n_primal));
+      // mean length of the rows this launch takes: the plan is sorted longest first and [0, n_primal) are primal
+      // the split is picked from the mean row length of the WHOLE side, not of this rank's shard: every rank of a
+      // row-sharded run then sums a row's right-hand side in the same order as a single engine would (bit-identical rows)
+      const int64_t side_rows = a.ind == e->mat[MFB_TRAIN].rowind ? e->n_users : e->n_items;
+      const bool long_rows = e->opt_als_ws_split ? e->opt_als_ws_split == 2 : e->mat[MFB_TRAIN].nnz / std::max<int64_t>(side_rows, 1) >= 1024;
+      MFB_TRY(launch_als_ws<TR>(e, b, n_primal, long_rows));
       n_primal_done = true;
     }
   }

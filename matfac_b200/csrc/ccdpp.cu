@@ -156,14 +156,31 @@ __global__ void ccd_finalize_kernel(const int32_t *__restrict__ multi_row, int n
   acc[2 * (size_t)s + 1] = 0.0;
 }
 
+// old_off > 0: a second copy at out[old_off + i] on every rank — u_k as it was before the step's updates.  A copy made
+// by each rank after the barrier would race with a faster peer's first update pass storing new u_k entries.
 __global__ void col_extract_kernel(const float *__restrict__ F, int ld, int k, int lo, int hi, float *__restrict__ out,
-                                   const CcdPeers pe) {
+                                   const CcdPeers pe, size_t old_off) {
   const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < hi) store_all(out, pe, i, F[(size_t)i * ld + k]);
+  if (i < hi) {
+    const float v = F[(size_t)i * ld + k];
+    store_all(out, pe, i, v);
+    if (old_off) store_all(out, pe, (int)old_off + i, v);
+  }
 }
-__global__ void col_insert_kernel(float *__restrict__ F, int ld, int k, int lo, int hi, const float *__restrict__ in) {
+// writes column k of this rank's rows back into the factor matrix — its own and every peer's, so that all ranks hold
+// the complete factors after every rank-one step (the per-epoch evaluation and the best-model snapshot read them)
+struct CcdPeerMats {
+  float *p[kMaxRanks - 1];
+  int n;
+};
+__global__ void col_insert_kernel(float *__restrict__ F, int ld, int k, int lo, int hi, const float *__restrict__ in,
+                                  const CcdPeerMats pm) {
   const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < hi) F[(size_t)i * ld + k] = in[i];
+  if (i < hi) {
+    const float v = in[i];
+    F[(size_t)i * ld + k] = v;
+    for (int q = 0; q < pm.n; q++) pm.p[q][(size_t)i * ld + k] = v;
+  }
 }
 
 
@@ -421,8 +438,9 @@ static int build_block_seg_plan(mfb_engine *e, const int64_t *ptr, const int32_t
 // Which plan a side's passes use: 0 = plain kernels (gather through L1 / L2), 1 = the whole gathered vector staged
 // (one block, the ordinary row plan), 2 = blocked plan.  Blocking pays while the sub-segments stay long enough for a
 // warp (>= 64 ratings on average).
-static int ccd_side_mode(const mfb_engine *e, int64_t nnz_side, int n_rows_side, int gather_n) {
+static int ccd_side_mode(const mfb_engine *e, int64_t nnz_side, int n_rows_side, int gather_n, bool row_side) {
   if (!e->opt_ccd_smem || gather_n <= 0) return 0;
+  if ((e->opt_ccd_smem == 2 && !row_side) || (e->opt_ccd_smem == 3 && row_side)) return 0;
   const int nb = (gather_n + kCcdBlock - 1) / kCcdBlock;
   if (nb == 1) return 1;
   if (n_rows_side <= 0 || (double)nnz_side / ((double)n_rows_side * nb) < 64.0) return 0;
@@ -457,9 +475,8 @@ int ccdpp_begin_impl(mfb_engine *e) {
   size_t nn = (size_t)(m.nnz > 0 ? m.nnz : 1);
   if (!e->res_row) MFB_CUDA(dev_alloc(&e->res_row, sizeof(float) * nn));
   if (!e->res_col) MFB_CUDA(dev_alloc(&e->res_col, sizeof(float) * nn));
-  if (!e->uk) MFB_CUDA(dev_alloc(&e->uk, sizeof(float) * ((size_t)e->n_users + 4)));
+  if (!e->uk) MFB_CUDA(dev_alloc(&e->uk, uk_alloc_bytes(e)));
   if (!e->vk) MFB_CUDA(dev_alloc(&e->vk, sizeof(float) * ((size_t)e->n_items + 4)));
-  if (!e->uk_old) MFB_CUDA(dev_alloc(&e->uk_old, sizeof(float) * ((size_t)e->n_users + 4)));
   // res = gk_csr_Dup(trainMat) (modelMF.cpp:1013); uFac.fill(0) (:1020)
   MFB_CUDA(cudaMemcpyAsync(e->res_row, m.rowval, sizeof(float) * (size_t)m.nnz, cudaMemcpyDeviceToDevice, st));
   MFB_CUDA(cudaMemcpyAsync(e->res_col, m.colval, sizeof(float) * (size_t)m.nnz, cudaMemcpyDeviceToDevice, st));
@@ -468,7 +485,7 @@ int ccdpp_begin_impl(mfb_engine *e) {
   if (!m.ccd_rows.built) {
     MFB_TRY(build_seg_plan(e, m.rowptr, e->n_users, e->bad_user, ulo, uhi, kCcdChunk, &m.ccd_rows));
     const int64_t nnz_side = (int64_t)((double)m.nnz * (double)(uhi - ulo) / std::max(e->n_users, 1));
-    m.ccd_rows_mode = ccd_side_mode(e, nnz_side, uhi - ulo, e->n_items);  // the row passes gather v_k
+    m.ccd_rows_mode = ccd_side_mode(e, nnz_side, uhi - ulo, e->n_items, true);  // the row passes gather v_k
     if (m.ccd_rows_mode == 2) {
       MFB_TRY(build_block_seg_plan(e, m.rowptr, m.rowind, e->bad_user, ulo, uhi, (e->n_items + kCcdBlock - 1) / kCcdBlock,
                                    &m.ccd_rows_blk, &m.ccd_rows_blk_off, &m.ccd_rows_doff));
@@ -481,7 +498,7 @@ int ccdpp_begin_impl(mfb_engine *e) {
   if (!m.ccd_cols.built) {
     MFB_TRY(build_seg_plan(e, m.colptr, e->n_items, e->bad_item, ilo, ihi, kCcdChunk, &m.ccd_cols));
     const int64_t nnz_side = (int64_t)((double)m.nnz * (double)(ihi - ilo) / std::max(e->n_items, 1));
-    m.ccd_cols_mode = ccd_side_mode(e, nnz_side, ihi - ilo, e->n_users);  // the column passes gather u_k
+    m.ccd_cols_mode = ccd_side_mode(e, nnz_side, ihi - ilo, e->n_users, false);  // the column passes gather u_k
     if (m.ccd_cols_mode == 2) {
       MFB_TRY(build_block_seg_plan(e, m.colptr, m.colind, e->bad_item, ilo, ihi, (e->n_users + kCcdBlock - 1) / kCcdBlock,
                                    &m.ccd_cols_blk, &m.ccd_cols_blk_off, &m.ccd_cols_doff));
@@ -592,24 +609,25 @@ int ccdpp_rank1_impl(mfb_engine *e, int32_t k, int first_iter, int32_t inner, fl
     for (int p = 0; p < c.world; p++)
       if (p != c.rank) { pu.p[pu.n++] = c.uk[p]; pv.p[pv.n++] = c.vk[p]; }
   // u_k = uFac.col(k); v_k = iFac.col(k)   (modelMF.cpp:1028-1029)
-  if (uhi > ulo) MFB_LAUNCH(col_extract_kernel, (uhi - ulo + 255) / 256, 256, 0, st, e->U, e->ld, k, ulo, uhi, e->uk, pu);
-  if (ihi > ilo) MFB_LAUNCH(col_extract_kernel, (ihi - ilo + 255) / 256, 256, 0, st, e->V, e->ld, k, ilo, ihi, e->vk, pv);
+  const bool fuse_add = !first_iter && inner >= 1 && e->opt_ccd_fuse;          // add-back rides on the first updates
+  float *uk_old = e->uk + e->uk_old_offset();  // the column add-back needs u_k as it was before its first update
+  if (uhi > ulo)
+    MFB_LAUNCH(col_extract_kernel, (uhi - ulo + 255) / 256, 256, 0, st, e->U, e->ld, k, ulo, uhi, e->uk, pu,
+               fuse_add ? e->uk_old_offset() : (size_t)0);
+  if (ihi > ilo) MFB_LAUNCH(col_extract_kernel, (ihi - ilo + 255) / 256, 256, 0, st, e->V, e->ld, k, ilo, ihi, e->vk, pv, (size_t)0);
   MFB_TRY(comm_barrier_launch(e));
   // the FreqAdap rule zeroes v_k of infrequent items for k > 0 (modelMF.cpp:1336-1342)
   const int thresh = (item_freq_thresh > 0 && k > 0) ? item_freq_thresh : 0;
-  const bool fuse_add = !first_iter && inner >= 1 && e->opt_ccd_fuse;          // add-back rides on the first updates
   // the column subtract rides on the last v_k update pass (plain kernels only)
   const bool fuse_sub = inner >= (fuse_add ? 2 : 1) && e->opt_ccd_fuse && cols.mode == 0;
   if (!first_iter && !fuse_add) {
     MFB_TRY(ccd_resid_side(e, rows, e->uk, e->vk, 1.0f, 0));
     MFB_TRY(ccd_resid_side(e, cols, e->vk, e->uk, 1.0f, 0));
   }
-  if (fuse_add)  // the column add-back needs u_k as it was before its first update
-    MFB_CUDA(cudaMemcpyAsync(e->uk_old, e->uk, sizeof(float) * (size_t)e->n_users, cudaMemcpyDeviceToDevice, st));
   for (int s = 0; s < inner; s++) {
     MFB_TRY(ccd_update_side(e, rows, e->uk, e->vk, e->vk, ureg, e->aux_u, 0, pu, s == 0 && fuse_add, false));
     MFB_TRY(comm_barrier_launch(e));
-    MFB_TRY(ccd_update_side(e, cols, e->vk, e->uk, e->uk_old, ireg, e->aux_i, thresh, pv, s == 0 && fuse_add,
+    MFB_TRY(ccd_update_side(e, cols, e->vk, e->uk, uk_old, ireg, e->aux_i, thresh, pv, s == 0 && fuse_add,
                             s == inner - 1 && fuse_sub && !(s == 0 && fuse_add)));
     MFB_TRY(comm_barrier_launch(e));
   }
@@ -619,8 +637,13 @@ int ccdpp_rank1_impl(mfb_engine *e, int32_t k, int first_iter, int32_t inner, fl
   } else {
     MFB_TRY(ccd_resid_side(e, cols, e->vk, e->uk, -1.0f, 0));
   }
-  if (uhi > ulo) MFB_LAUNCH(col_insert_kernel, (uhi - ulo + 255) / 256, 256, 0, st, e->U, e->ld, k, ulo, uhi, e->uk);
-  if (ihi > ilo) MFB_LAUNCH(col_insert_kernel, (ihi - ilo + 255) / 256, 256, 0, st, e->V, e->ld, k, ilo, ihi, e->vk);
+  CcdPeerMats mu, mv;
+  mu.n = mv.n = 0;
+  if (c.connected)
+    for (int p = 0; p < c.world; p++)
+      if (p != c.rank) { mu.p[mu.n++] = c.U[p]; mv.p[mv.n++] = c.V[p]; }
+  if (uhi > ulo) MFB_LAUNCH(col_insert_kernel, (uhi - ulo + 255) / 256, 256, 0, st, e->U, e->ld, k, ulo, uhi, e->uk, mu);
+  if (ihi > ilo) MFB_LAUNCH(col_insert_kernel, (ihi - ilo + 255) / 256, 256, 0, st, e->V, e->ld, k, ilo, ihi, e->vk, mv);
   // the subtract passes above gather ALL of u_k / v_k; the next rank-one step starts by storing its column into every
   // peer's u_k / v_k — no rank may get there while a peer is still reading (write-after-read across ranks)
   MFB_TRY(comm_barrier_launch(e));

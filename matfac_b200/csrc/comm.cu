@@ -163,7 +163,7 @@ extern "C" int mfb_comm_init(mfb_engine *e, int32_t rank, int32_t world, uint8_t
   Comm &c = e->comm;
   c.rank = rank;
   c.world = world;
-  if (!e->uk) MFB_CUDA(dev_alloc(&e->uk, sizeof(float) * ((size_t)e->n_users + 4)));
+  if (!e->uk) MFB_CUDA(dev_alloc(&e->uk, uk_alloc_bytes(e)));
   if (!e->vk) MFB_CUDA(dev_alloc(&e->vk, sizeof(float) * ((size_t)e->n_items + 4)));
   if (!c.own_flags) {
     MFB_CUDA(dev_alloc(&c.own_flags, sizeof(unsigned long long) * (kFlagSlots + 2)));
@@ -234,7 +234,7 @@ extern "C" int mfb_comm_connect_local(mfb_engine **engines, int32_t world) {
     Comm &c = e->comm;
     c.rank = r;
     c.world = world;
-    if (!e->uk) MFB_CUDA(dev_alloc(&e->uk, sizeof(float) * ((size_t)e->n_users + 4)));
+    if (!e->uk) MFB_CUDA(dev_alloc(&e->uk, uk_alloc_bytes(e)));
     if (!e->vk) MFB_CUDA(dev_alloc(&e->vk, sizeof(float) * ((size_t)e->n_items + 4)));
     if (!c.own_flags) MFB_CUDA(dev_alloc(&c.own_flags, sizeof(unsigned long long) * (kFlagSlots + 2)));
     MFB_CUDA(cudaMemset(c.own_flags, 0, sizeof(unsigned long long) * (kFlagSlots + 2)));

@@ -403,7 +403,7 @@ extern "C" void mfb_destroy(mfb_engine *e) {
   dev_free(e->U); dev_free(e->V); dev_free(e->bestU); dev_free(e->bestV);
   dev_free(e->bad_user); dev_free(e->bad_item); dev_free(e->aux_u); dev_free(e->aux_i); dev_free(e->poisson_cdf);
   dev_free(e->eval_partial); dev_free(e->eval_out); cudaFreeHost(e->eval_out_host);
-  dev_free(e->als_ws); dev_free(e->res_row); dev_free(e->res_col); dev_free(e->uk); dev_free(e->vk); dev_free(e->uk_old);
+  dev_free(e->als_ws); dev_free(e->res_row); dev_free(e->res_col); dev_free(e->uk); dev_free(e->vk);
   dev_free(e->ccd_acc); dev_free(e->scratch);
   const int destroyed_device = e->device;
   if (e->comm.connected && e->comm.ipc)
@@ -750,6 +750,7 @@ extern "C" int mfb_set_option(mfb_engine *e, const char *name, double value) {
   else if (n == "ccd_smem") { e->opt_ccd_smem = (int)value; for (int w = 0; w < 3; w++) e->mat[w].release_ccd(); }
   else if (n == "als_tensor_cores") e->opt_als_tensor_cores = (int)value;
   else if (n == "als_dual") e->opt_als_dual = (int)value;
+  else if (n == "als_ws_split") e->opt_als_ws_split = (int)value;
   else if (n == "als_chunk") {
     if (value < 64) return mfb::fail("mfb_set_option: als_chunk must be >= 64", __FILE__, __LINE__);
     e->opt_als_chunk = (int)value;

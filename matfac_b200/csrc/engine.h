@@ -186,11 +186,12 @@ struct mfb_engine {
   double opt_sgd_hot_stab = 0.5;      // hot CTAs: mini-batch <= value / (learnrate x rating-weighted mean |u|^2)
   int opt_sgd_hot_pace = 1;           // hot CTAs advance through their list in step with the shuffled kernel
   int opt_sgd_hot_batch = 0;          // ratings per round of a hot CTA, 0 = automatic (<= 64 and <= sgd_flat_hot_lr / learnrate)
-  int opt_ccd_smem = 1;               // CCD++: gathered u_k / v_k staged in shared memory where the shape allows
+  int opt_ccd_smem = 0;               // CCD++: 1 = gathered u_k / v_k staged in shared memory where the shape allows (measured slower than the L1/L2 gather: profiles/r2_ccdpp.md), 2 / 3 = row / column side only
   int opt_ccd_fuse = 1;               // CCD++: add-back / column subtract ride on the first / last update passes
   int opt_als_chunk = 16384;          // ratings per CTA before a row is split over several CTAs
   int opt_als_dual = 1;               // short rows: solve the len x len dual system instead of rank x rank
-  int opt_als_tensor_cores = 1;       // rank > 64: Gram on tcgen05 (3xTF32); 0 = fp32 CUDA-core Gram
+  int opt_als_tensor_cores = 1;       // rank > 32: Gram on tcgen05 (3xTF32), warp-specialised persistent kernel; 0 = fp32 CUDA-core Gram; 2 = the round-1 one-CTA-per-row kernel (rank > 64)
+  int opt_als_ws_split = 0;           // warp-specialised kernel: 0 = converter teams / solver groups picked per side from the mean row length, 1 = the many-short-rows split, 2 = the few-long-rows split
   cudaStream_t stream = nullptr;
   cudaStream_t stream_hot = nullptr;  // hot-row CTAs run next to the shuffled kernel (forked from / joined into `stream`)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -219,12 +220,15 @@ struct mfb_engine {
 
   // CCD++ state
   float *res_row = nullptr, *res_col = nullptr;  // residual (CSR order / CSC order)
+  // u_k is allocated twice over: [0, n_users + 4) the live vector, [uk_old_offset(), ...) its value from before the
+  // first update of the rank-one step (fused column add-back).  One allocation so that a peer's copy of both is
+  // reachable from the one exchanged pointer: every rank stores its extracted rows into both halves on all ranks.
   float *uk = nullptr, *vk = nullptr;
-  float *uk_old = nullptr;  // u_k before its first update of the rank-one step (fused column add-back)
   double *ccd_acc = nullptr;  // [slots][2]
   size_t ccd_acc_slots = 0;
 
   mfb::Comm comm;
+  size_t uk_old_offset() const { return ((size_t)n_users + 4 + 31) & ~(size_t)31; }
 
   // generic scratch for plan building (grown on demand)
   void *scratch = nullptr;
@@ -257,6 +261,7 @@ int ccdpp_begin_impl(mfb_engine *e);
 int ccdpp_rank1_impl(mfb_engine *e, int32_t k, int first_iter, int32_t inner, float ureg, float ireg,
                      int32_t item_freq_thresh);
 int ccdpp_end_impl(mfb_engine *e);
+inline size_t uk_alloc_bytes(const mfb_engine *e) { return sizeof(float) * (e->uk_old_offset() + (size_t)e->n_users + 4); }
 int comm_barrier_launch(mfb_engine *e);
 // non-zero (mfb_last_error set) when a device-side flag wait of this engine has timed out; syncs the stream
 int comm_check_error(mfb_engine *e);

@@ -57,6 +57,7 @@ extern "C" int mfh_train(const mfh_problem *p, mfh_result *out) {
   else if (algo == "mf" && method == "ccdpp_plain") model->trainCCDPP(data, *best, invalidUsers, invalidItems);
   else if (algo == "mf" && method == "als") model->trainALS(data, *best, invalidUsers, invalidItems);
   else if (algo == "mf" && method == "hogsgd") model->hogTrain(data, *best, invalidUsers, invalidItems);
+  else if (algo == "mf" && method == "sgdu") model->trainUShuffle(data, *best, invalidUsers, invalidItems);
   else if ((algo == "mf" || algo == "IFWMF") && method == "sgdpar") model->trainSGDPar(data, *best, invalidUsers, invalidItems);
   else model->train(data, *best, invalidUsers, invalidItems);
 

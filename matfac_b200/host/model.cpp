@@ -480,6 +480,32 @@ void Model::runFlatSgd(const Data &data, Model &bestModel, std::unordered_set<in
   std::cout << "\nBest model validation RMSE: " << bestModel.RMSE(data.valMat, invalidUsers, invalidItems) << std::endl;
 }
 
+// User-major SGD over the whole matrix (trainUShuffle, modelMF.cpp:626-660): one block, user runs in the queue order of
+// the kernel (the reference reshuffles the users every epoch — with thousands of runs in flight the order of the queue
+// is immaterial), every run from its own pseudo-random start (see runStratifiedSgd).
+void Model::runUserMajorSgd(const Data &data, Model &bestModel, std::unordered_set<int> &invalidUsers,
+                            std::unordered_set<int> &invalidItems, const char *tag, bool saves) {
+  Stop st;
+  beginTraining(data, bestModel, invalidUsers, invalidItems, st, tag);
+  DeviceSession &s = *dev_;
+  s.check(mfb_set_option(s.eng, "sgd_shuffle_seed", (double)(uint32_t)trainSeed));
+  s.check(mfb_set_option(s.eng, "sgd_rotate", 1));
+  s.check(mfb_set_option(s.eng, "sgd_block_order", 0));
+  s.check(mfb_sgd_plan(s.eng, 1, nullptr, nullptr));
+  const int variant = deviceVariant();
+  const int32_t whole[2] = {0, 0};
+  for (int iter = 0; iter < maxIter; iter++) {
+    s.check(mfb_event_record(s.eng, 0));
+    s.check(mfb_sgd_subepoch(s.eng, whole, 1, variant, learnRate, uReg, iReg, (uint64_t)(uint32_t)trainSeed, (uint64_t)iter));
+    s.check(mfb_event_record(s.eng, 1));
+    const double dur = elapsedSeconds(s);
+    if (afterEpoch(data, bestModel, iter, st, invalidUsers, invalidItems, dur, tag, saves)) break;
+  }
+  endTraining(bestModel);
+  if (saves) bestModel.saveFacs(std::string(data.prefix));
+  std::cout << "\nBest model validation RMSE: " << bestModel.RMSE(data.valMat, invalidUsers, invalidItems) << std::endl;
+}
+
 // Stratified SGD (modelMF.cpp:154-350 and the IFWMF / TMF / TMF+Dropout twins): users and items
 // are shuffled by mt19937(trainSeed) and cut into P = omp_get_max_threads() parts with the
 // reference's boundary rule; every epoch draws P random permutation schedules from the same

@@ -148,6 +148,8 @@ class Model {
                   std::unordered_set<int> &invalidItems, const char *tag, bool saves);
   void runStratifiedSgd(const Data &data, Model &bestModel, std::unordered_set<int> &invalidUsers,
                         std::unordered_set<int> &invalidItems, const char *tag, bool saves);
+  void runUserMajorSgd(const Data &data, Model &bestModel, std::unordered_set<int> &invalidUsers,
+                       std::unordered_set<int> &invalidItems, const char *tag, bool saves);
 };
 
 #endif

@@ -18,6 +18,18 @@ void ModelMF::hogTrain(const Data &data, Model &bestModel, std::unordered_set<in
   runFlatSgd(data, bestModel, invalidUsers, invalidItems, "ModelMF::hogTrain", true);
 }
 
+// --mf_method sgdu (modelMF.cpp:560-706): the valid users in shuffled order, each user's ratings back to back.  On the
+// device this is the user-major kernel of the stratified trainers over the whole matrix as one block: a sub-warp owns a
+// user's run and keeps u in registers for all of it (exactly the reference's inner loop for that user), many users
+// run at once and item rows are updated by reductions.
+void ModelMF::trainUShuffle(const Data &data, Model &bestModel, std::unordered_set<int> &invalidUsers,
+                            std::unordered_set<int> &invalidItems) {
+  std::cout << "\nModelMF::train trainSeed: " << trainSeed;
+  std::cout << "\nObj b4 svd: " << objective(data) << " Train RMSE: " << RMSE(data.trainMat)
+            << " Train nnz: " << data.trainNNZ << std::endl;
+  runUserMajorSgd(data, bestModel, invalidUsers, invalidItems, "ModelMF::trainUShuffle", true);
+}
+
 void ModelMF::trainSGDPar(const Data &data, Model &bestModel, std::unordered_set<int> &invalidUsers,
                           std::unordered_set<int> &invalidItems) {
   std::cout << "\nModelMF::trainSGDPar trainSeed: " << trainSeed;

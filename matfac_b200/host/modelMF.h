@@ -19,6 +19,7 @@ class ModelMF : public Model {
   MATFAC_DECL(train)               // serial SGD            modelMF.cpp:4
   MATFAC_DECL(trainSGDPar)         // stratified SGD        modelMF.cpp:154
   MATFAC_DECL(hogTrain)            // Hogwild SGD           modelMF.cpp:1656
+  MATFAC_DECL(trainUShuffle)       // user-major SGD        modelMF.cpp:560
   MATFAC_DECL(trainALS)            // alternating LS        modelMF.cpp:709
   MATFAC_DECL(trainCCDPP)          // CCD++                 modelMF.cpp:931
   MATFAC_DECL(trainCCDPPFreqAdap)  // CCD++, freq-adaptive  modelMF.cpp:1172

@@ -584,6 +584,44 @@ static int trainSerialSgd(mfo_model *m, const mfo_data *d) {
   return iter;
 }
 
+// ModelMF::trainUShuffle modelMF.cpp:560-706 (--mf_method sgdu): the valid users in a fresh shuffled order every
+// epoch (mt19937(trainSeed), :617,633), each user's ratings in CSR order (:637), the per-rating step of the serial
+// trainer with diff / r_ui_est kept in double (:583,644-646).  The inner loop does not test invalidItems (an item
+// without training ratings cannot occur in the training matrix).
+static int trainUserShuffle(mfo_model *m, const mfo_data *d) {
+  StopState s;
+  preamble(m, d, s, nullptr, nullptr);
+  const Csr &tr = d->mat[0];
+  const int r = m->facDim;
+  std::mt19937 mt(m->seed);
+  std::vector<size_t> validUsers;
+  for (int u = 0; u < m->nUsers; u++)
+    if (!m->invalidUsers.count(u)) validUsers.push_back(u);
+  int iter;
+  for (iter = 0; iter < m->maxIter; iter++) {
+    EpochTimer tm(m);
+    std::shuffle(validUsers.begin(), validUsers.end(), mt);
+    const float learnRate = m->cur.learnRate, uReg = m->uReg, iReg = m->iReg;
+    for (const auto &u : validUsers) {
+      for (int64_t ii = tr.rowptr[u]; ii < tr.rowptr[u + 1]; ii++) {
+        const int item = tr.rowind[ii];
+        const float itemRat = tr.rowval[ii];
+        float *pu = &m->cur.U[(size_t)u * r], *pv = &m->cur.V[(size_t)item * r];
+        float dotp = 0;
+        for (int k = 0; k < r; k++) dotp += pu[k] * pv[k];
+        const double r_ui_est = dotp;
+        const double diff = itemRat - r_ui_est;
+        for (int i = 0; i < r; i++) pu[i] -= learnRate * (-2.0 * diff * pv[i] + 2.0 * uReg * pu[i]);
+        for (int i = 0; i < r; i++) pv[i] -= learnRate * (-2.0 * diff * pu[i] + 2.0 * iReg * pv[i]);
+      }
+    }
+    tm.stop();
+    if (iter % kObjIter == 0 || iter == m->maxIter - 1)
+      if (isTerminateModel(m, d, iter, s)) { iter++; break; }
+  }
+  return iter;
+}
+
 // ModelMF::hogTrain modelMF.cpp:1656-1810 executed by ONE thread (Eigen row expressions:
 // foreign scalars are converted to float before they multiply a row, :1759-1762).
 static int trainHogwildSerial(mfo_model *m, const mfo_data *d) {
@@ -906,6 +944,7 @@ extern "C" int mfo_train(mfo_model *m, const mfo_data *d, int method, int keep_h
     case MFO_CCDPP: iters = trainCcdpp(m, d, false); break;
     case MFO_CCDPP_FREQ: iters = trainCcdpp(m, d, true); break;
     case MFO_HOGWILD: iters = trainHogwildSerial(m, d); break;
+    case MFO_SGDU: iters = trainUserShuffle(m, d); break;
     default: iters = -1;
   }
   omp_set_num_threads(saved);

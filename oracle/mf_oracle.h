@@ -28,7 +28,8 @@ enum mfo_method {
   MFO_ALS = 2,          /* ModelMF::trainALS                                             */
   MFO_CCDPP = 3,        /* ModelMF::trainCCDPP                                           */
   MFO_CCDPP_FREQ = 4,   /* ModelMF::trainCCDPPFreqAdap (what --mf_method ccd++ runs)     */
-  MFO_HOGWILD = 5       /* ModelMF::hogTrain executed by one thread                      */
+  MFO_HOGWILD = 5,      /* ModelMF::hogTrain executed by one thread                      */
+  MFO_SGDU = 6          /* ModelMF::trainUShuffle (--mf_method sgdu, modelMF.cpp:560-706) */
 };
 
 /* --- data (datastruct.cpp:3-120) ------------------------------------------------------ */

@@ -19,7 +19,7 @@ ORACLE_SO = os.path.join(ORACLE_DIR, "libmf_oracle.so")
 REF_BIN = os.path.join(ORACLE_DIR, "_ref", "mf_ref")
 
 ALGO = {"mf": 0, "IFWMF": 1, "TMF": 2, "TMFDropout": 3}
-METHOD = {"sgd": 0, "sgdpar": 1, "als": 2, "ccdpp_plain": 3, "ccd++": 4, "hogsgd": 5}
+METHOD = {"sgd": 0, "sgdpar": 1, "als": 2, "ccdpp_plain": 3, "ccd++": 4, "hogsgd": 5, "sgdu": 6}
 
 
 class Params(C.Structure):

@@ -427,7 +427,7 @@ def _als_f64(ptr, ind, val, F, rank, reg, n):
     return out
 
 
-@pytest.mark.parametrize("tensor_cores", [0, 1])
+@pytest.mark.parametrize("tensor_cores", [0, 1, 12])
 @pytest.mark.parametrize("rank", [10, 64, 128])
 def test_als_epoch_matches_oracle(rank, tensor_cores):
     """Per-epoch ALS parity, teacher-forced per half-step, on a matrix whose rows hold more ratings
@@ -436,14 +436,17 @@ def test_als_epoch_matches_oracle(rank, tensor_cores):
     1e4-1e5 once the factors are O(1)), at least as close to the float64 solution as the oracle is.
     tensor_cores = 1 exercises the tcgen05 3xTF32 Gram (rank > 64), 0 the fp32 CUDA-core Gram."""
     from matfac_b200 import synth
-    if tensor_cores and rank <= 64:
-        pytest.skip("the tensor-core Gram serves rank > 64")
+    if tensor_cores and rank <= 32:
+        pytest.skip("the tensor-core Gram serves rank > 32")
+    ws_split = tensor_cores // 10 + 1 if tensor_cores else 0  # 1: the many-short-rows split, 12 -> 2: the few-long-rows split
+    tensor_cores = min(tensor_cores, 1)
     splits = synth.make_splits(900, 600, 380000, seed=13, user_s=0.2, item_s=0.2)
     tr = splits[0]
     assert np.diff(tr.rowptr).min() > 150 and np.bincount(tr.rowind).min() > 150
     om = oracle_model(splits, "mf", rank, maxiter=1, ureg=0.1, ireg=0.1, nthreads=8)
     eng, variant = make_engine(splits, om, rank)
     eng.set_option("als_tensor_cores", tensor_cores)
+    eng.set_option("als_ws_split", ws_split)
     for ep in range(3):
         U0, V0 = om.factors()
         om.train("als")

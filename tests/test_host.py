@@ -248,7 +248,7 @@ def test_cli_als_and_ccdpp_match_oracle(tmp_path, method, extra):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("algo,method,threads,extra", [
-    ("mf", "sgd", 1, {}), ("mf", "hogsgd", 1, {}), ("mf", "sgdpar", 4, {}), ("IFWMF", "sgd", 1, dict(rhorms=100.0)),
+    ("mf", "sgd", 1, {}), ("mf", "hogsgd", 1, {}), ("mf", "sgdu", 1, {}), ("mf", "sgdpar", 4, {}), ("IFWMF", "sgd", 1, dict(rhorms=100.0)),
     ("IFWMF", "sgdpar", 4, dict(rhorms=100.0)), ("TMF", "sgd", 4, dict(rhorms=20.0, alpha=0.5)),
     ("TMFDropout", "sgd", 4, dict(rhorms=20.0, alpha=0.5))])
 def test_cli_sgd_trainers_converge_to_the_oracle_rmse(tmp_path, algo, method, threads, extra):

@@ -141,7 +141,8 @@ def test_dsgd_ranks_match_oracle_value_for_value(world):
     U0, V0 = om.factors()
     devs = _devices(world)
     d = dsgd.Dsgd(od.n_users, od.n_items, 16, world, dict(enumerate(devs)), (tr.rowptr, tr.rowind, tr.rowval),
-                  (va.rowptr, va.rowind, va.rowval), U0, V0, bu, bi, epochs * world, plan="reference", seed=5)
+                  (va.rowptr, va.rowind, va.rowval), U0, V0, bu, bi, epochs * world, plan="reference", seed=5,
+                  block_order=0)  # the reference's visiting order inside a block: value-for-value comparable
     d.run(0, epochs * world, 0.01, 0.05, 0.05, 5)
     d.publish()
     om.train("sgdpar")

@@ -16,6 +16,7 @@ CASES = [
     # algo, method, threads, extra flags
     ("mf", "sgd", 1, {}),
     ("mf", "hogsgd", 1, {}),
+    ("mf", "sgdu", 1, {}),
     ("mf", "sgdpar", 4, {}),
     ("mf", "als", 2, {"ureg": 0.1, "ireg": 0.1}),
     ("mf", "ccdpp_plain", 2, {}),

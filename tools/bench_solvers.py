@@ -89,6 +89,8 @@ def main():
     if args.algo == "als":
         eng.set_option("als_tensor_cores", args.tc)
         eng.set_option("als_dual", int(os.environ.get("ALS_DUAL", "1")))
+        eng.set_option("als_ws_split", int(os.environ.get("ALS_WS_SPLIT", "0")))
+        out["als_ws_split"] = int(os.environ.get("ALS_WS_SPLIT", "0"))
         if "ALS_CHUNK" in os.environ:
             eng.set_option("als_chunk", int(os.environ["ALS_CHUNK"]))
             out["als_chunk"] = int(os.environ["ALS_CHUNK"])
@@ -123,6 +125,8 @@ def main():
         out.update(val_rmse=float(np.sqrt(ev[0] / max(ev[1], 1))))
     elif args.algo == "ccdpp":
         eng.set_option("ccd_fuse", int(os.environ.get("MFB_CCD_FUSE", "1")))
+        eng.set_option("ccd_smem", int(os.environ.get("MFB_CCD_SMEM", "0")))
+        out["ccd_smem"] = int(os.environ.get("MFB_CCD_SMEM", "0"))
         eng.ccdpp_begin()
         dims = min(r, 8)
         for k in range(dims):  # iter 0 (no add-back)
