@@ -145,6 +145,11 @@ int mfb_sgd_epoch_flat(mfb_engine *e, int variant, float learn_rate, float ureg,
  * 0 = one band, a uniformly shuffled epoch as in modelMF.cpp:76-81 (banding converges at a different rate
  * per epoch than the reference's order); takes effect at the next mfb_sgd_plan), "ccd_fuse" (CCD++: 1 = the residual add-back rides on the first u_k / v_k update pass and the column subtract on the
  * last v_k update pass of a rank-one step — same statements in the same order, 11 instead of 14 passes; 0 = one pass each),
+ * "copy_overlap" (1 = mfb_upload_csr / mfb_upload_factors / mfb_download_factors return without synchronising:
+ * factor copies run on a copy stream — an upload behind the rating upload and next to mfb_sgd_plan, a download next to
+ * the evaluations queued after it; the caller keeps the host buffers (pinned) valid and untouched until mfb_sync; every
+ * call that touches the factors is ordered behind a pending copy on the device; default 0 = copies complete before the
+ * call returns),
  * "als_tensor_cores" (rank > 32: 1 = tcgen05 3xTF32 Gram in the warp-specialised persistent kernel, default; 0 = fp32
  * CUDA-core Gram; 2 = one CTA per row, rank > 64 only), "als_ws_split" (warp-specialised kernel: 0 = the split between
  * converter teams and solver groups is picked per half-step from the mean row length, default; 1 = the

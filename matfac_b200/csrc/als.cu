@@ -816,6 +816,7 @@ constexpr uint32_t kWsSbo = 144;     // bytes between 8-dim core matrices (16 B 
 // kWsDrainBar0 + g, whole solver group g -> kWsGroupBar0 + g (<= 4 groups); the three ranges must not overlap
 constexpr int kWsDrainBar0 = 5, kWsGroupBar0 = 9;
 constexpr int kWsFirst = 0x100, kWsLast = 0x200;  // tile descriptor flags: first / last tile of its row
+constexpr int kWsClassShift = 12;                 // tile descriptor: (tile index within the row) mod NT
 
 // NT converter teams and G solver groups per CTA: a half-step over many short rows (users) is bound by the solves, one
 // over few long rows (items) by the conversion of the gathered rows — the launcher picks the split per side.
@@ -831,9 +832,10 @@ struct AlsWs {
   static constexpr int MCORES = 2 * RP / 8;                       // core matrices along M of [big; small]
   static constexpr uint32_t LBO = MCORES * kWsSbo;                // bytes between 4-rating K groups
   static constexpr uint32_t OP_BYTES = (KT / 4) * LBO;            // one operand stage (18 KB)
-  static constexpr int NS = NT_ > 3 ? NT_ : 3;                    // operand stages; >= NT: a team moves NT tiles ahead per step and
-                                                                  // may be at most one phase of a stage's barrier ahead of the MMAs
-  static constexpr int NRT = NT_ >= 4 ? 3 : 4;                    // raw stages per team (tiles of gathered rows in flight)
+  static constexpr int NS = NT_ + (NT_ >= 4 ? 1 : 2);             // operand stages; >= NT: a team moves NT tiles ahead per step and
+                                                                  // may be at most one phase of a stage's barrier ahead of the MMAs;
+                                                                  // > NT: a team does not wait for the MMAs of its own previous tile
+  static constexpr int NRT = NT_ >= 3 ? 3 : 4;                    // raw stages per team (tiles of gathered rows in flight); shared-memory budget
   static constexpr int MR = 8;                                    // (item, rating, descriptor) ring per team: the scheduler warp
                                                                   // runs up to MR team tiles ahead of the converters
   static constexpr uint32_t RAW_ROW = RP * 4;                     // bytes per staged factor row
@@ -844,8 +846,10 @@ struct AlsWs {
   static constexpr int SOLVER0 = MMA0 + 32;
   static constexpr int NTHREADS = SOLVER0 + G * kWsGroupThreads;
   static constexpr int ACC_COLS = TR == 8 ? 256 : 64;             // TMEM columns of one accumulator
-  static constexpr int NACC = G;                                  // one accumulator per solver group: group g drains the
-                                                                  // phases of "its" accumulator in order (no parity aliasing)
+  static constexpr int NACC = G == 1 ? 2 : G;                     // accumulators: row i multiplies into accumulator i mod NACC and
+                                                                  // is drained by group i mod G — NACC is a multiple of G, so a
+                                                                  // group sees the phases of an accumulator in order; a single
+                                                                  // group gets two (the next row multiplies while it drains)
   static constexpr int TMEM_USED = NACC * ACC_COLS;
   static constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;  // allocations are powers of two
   static constexpr int T2 = TR * TR, TS = T2 + 4;                 // tile stride (floats): conflict-free 128-bit loads
@@ -860,7 +864,7 @@ struct AlsWs {
   static constexpr uint32_t off_desc = off_meta + NT * MR * 32 * 8;           // [NT][MR] {ratings in the tile | kWsFirst | kWsLast, row}
   static constexpr uint32_t off_opinfo = off_desc + NT * MR * 8;              // [NS] descriptor of the tile in each operand stage
   static constexpr uint32_t off_bars = off_opinfo + NS * 8;                   // mbarriers
-  static constexpr int n_bars = NT * NRT + 2 * NT * MR + 2 * NS + 3 * NACC;
+  static constexpr int n_bars = 2 * NT * MR + 2 * NS + 3 * NACC;
   static constexpr uint32_t off_tmem = off_bars + n_bars * 8;
   static constexpr size_t bytes = off_tmem + 16 + 1024;
   static_assert(CholScratch<TR>::total <= GS_FLOATS, "Cholesky scratch is carved from the drained tile buffer");
@@ -916,9 +920,8 @@ __global__ void __launch_bounds__(AlsWs<TR, NT_, G_>::NTHREADS, 1) als_ws_kernel
   int2 *opinfo = reinterpret_cast<int2 *>(smb + W::off_opinfo);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smb + W::off_bars);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smb + W::off_tmem);
-  // mbarriers: raw_full[NT][NRT] | meta_full[NT][MR] | meta_empty[NT][MR] | op_full[NS] | op_empty[NS] |
-  //            acc_full | rhs_full | acc_empty [NACC]
-  const uint32_t bar_raw = smem_u32(bars), bar_meta = bar_raw + NT * NRT * 8, bar_mempty = bar_meta + NT * MR * 8,
+  // mbarriers: meta_full[NT][MR] | meta_empty[NT][MR] | op_full[NS] | op_empty[NS] | acc_full | rhs_full | acc_empty [NACC]
+  const uint32_t bar_meta = smem_u32(bars), bar_mempty = bar_meta + NT * MR * 8,
                  bar_opf = bar_mempty + NT * MR * 8, bar_op = bar_opf + NS * 8, bar_accf = bar_op + NS * 8,
                  bar_rhs = bar_accf + NACC * 8, bar_acce = bar_rhs + NACC * 8;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -926,7 +929,6 @@ __global__ void __launch_bounds__(AlsWs<TR, NT_, G_>::NTHREADS, 1) als_ws_kernel
   const int nq = a.ld >> 2;
 
   if (tid == 0) {
-    for (int i = 0; i < NT * NRT; i++) mbar_init(bar_raw + i * 8, kWsTeam);  // one cp.async arrival per team thread
     for (int i = 0; i < NT * MR; i++) {
       mbar_init(bar_meta + i * 8, 33);                // 32 cp.async arrivals + the descriptor's release
       mbar_init(bar_mempty + i * 8, kWsTeam / 32);    // one arrival per converter warp
@@ -992,62 +994,72 @@ __global__ void __launch_bounds__(AlsWs<TR, NT_, G_>::NTHREADS, 1) als_ws_kernel
     const float *meta_rate = reinterpret_cast<const float *>(smb + W::off_meta + NT * MR * 32 * 4) + team * MR * 32;
     const int2 *desc = reinterpret_cast<const int2 *>(smb + W::off_desc) + team * MR;
     const uint32_t raw0 = sbase + W::off_raw + team * NRT * W::RAW_BYTES;
-    const uint32_t braw = bar_raw + team * NRT * 8, bmeta = bar_meta + team * MR * 8, bmempty = bar_mempty + team * MR * 8;
+    const uint32_t bmeta = bar_meta + team * MR * 8, bmempty = bar_mempty + team * MR * 8;
     constexpr int D = NRT - 1;     // team tiles whose factor rows are in flight
     const int q = tt % QP;         // this thread's 16-byte unit of the factor row
     const int grp = tt / QP;       // its K group: ratings 4 grp .. 4 grp + 3 of the tile
     const int j0 = grp * 4;
     bool issue_done = false;
-    // the factor rows of team tile y, 16 bytes per cp.async, a row = QP consecutive threads (coalesced); completion is
-    // counted on raw_full[stage] (cp.async.mbarrier.arrive.noinc: one arrival per team thread)
+    // the factor rows of team tile y, 16 bytes per cp.async: thread (grp, q) copies unit q of ratings 4 grp .. 4 grp + 3 —
+    // exactly what it converts later, so a raw stage needs no barrier at all (its own cp.async group tells the thread
+    // when its 64 bytes have landed) and the warps of a team run independently; a warp instruction still covers two
+    // whole factor rows (coalesced).  One commit group per tile, also after the stream has ended (empty groups keep
+    // the wait_group arithmetic fixed).
     auto issue_rows = [&](int y) {
-      const int st = y % NRT, ms = y % MR;
-      mbar_wait(bmeta + ms * 8, (uint32_t)(y / MR) & 1u);
-      const int n = desc[ms].x & 0xFF;  // ratings of the tile, 0 = the stream has ended
-      if (n == 0) { issue_done = true; return; }
-      const uint32_t dst0 = raw0 + st * W::RAW_BYTES;
+      if (!issue_done) {
+        const int st = y % NRT, ms = y % MR;
+        mbar_wait(bmeta + ms * 8, (uint32_t)(y / MR) & 1u);
+        const int n = desc[ms].x & 0xFF;  // ratings of the tile, 0 = the stream has ended
+        if (n == 0) issue_done = true;
+        else if (q < nq) {
+          const uint32_t dst0 = raw0 + st * W::RAW_BYTES + q * 16;
+          const int4 it4 = *reinterpret_cast<const int4 *>(meta_item + ms * 32 + j0);
+          const float4 rt4 = *reinterpret_cast<const float4 *>(meta_rate + ms * 32 + j0);
+          const int its[4] = {it4.x, it4.y, it4.z, it4.w};
+          const float rts[4] = {rt4.x, rt4.y, rt4.z, rt4.w};
 #pragma unroll
-      for (int k = 0; k < KT * QP / kWsTeam; k++) {
-        const int idx = tt + k * kWsTeam, j = idx / QP, qq = idx % QP;
-        if (qq < nq && j < n && meta_rate[ms * 32 + j] > 0.f)  // rating > 0 filter (modelMF.cpp:819)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + j * W::RAW_ROW + qq * 16),
-                       "l"(a.Fin + (size_t)meta_item[ms * 32 + j] * a.ld + qq * 4)
-                       : "memory");
+          for (int k = 0; k < 4; k++)
+            if (j0 + k < n && rts[k] > 0.f)  // rating > 0 filter (modelMF.cpp:819); beyond the row's end the ring is stale
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (j0 + k) * W::RAW_ROW),
+                           "l"(a.Fin + (size_t)its[k] * a.ld + q * 4)
+                           : "memory");
+        }
       }
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(braw + st * 8) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
     // right-hand side b = sum r f: a thread keeps the partial sum of its unit over its ratings of the row and writes it
-    // into its own slot of bpart[row mod NACC] when it leaves the row — zeros for rows its team had no tile of, so
-    // that the solver group can add all NT * NGRP slots and the arrival count on rhs_full is fixed
+    // into bpart[row mod NACC] when it leaves the row.  The slot is picked by the CLASS of the team's tiles in this row
+    // (tile index within the row mod NT — one class per team and row), not by the team: which team gets a row's first
+    // tile depends on how many tiles the CTA has seen before, and a row must not be summed in a different order
+    // because of that (row-sharded runs reproduce a single engine bit for bit).  The solver group adds the classes the
+    // row has; a team arrives on rhs_full for every row, also for rows it had no tile of (fixed arrival count).
     float4 bacc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int brow = -1, flushed = 0;  // row bacc belongs to; rows [0, flushed) have been flushed by this thread
+    int brow = -1, bcls = 0, flushed = 0;  // row / class bacc belongs to; rows [0, flushed) have been flushed by this thread
     auto flush_to = [&](int upto) {
       for (; flushed < upto; flushed++) {
         const int acc = flushed % NACC;
         if (flushed >= NACC) mbar_wait(bar_acce + acc * 8, (uint32_t)(flushed / NACC - 1) & 1u);  // bpart[acc] consumed
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (flushed == brow) {
-          v = bacc;
+          *reinterpret_cast<float4 *>(bpart + ((size_t)(acc * NT + bcls) * NGRP + grp) * RP + q * 4) = bacc;
           bacc = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        *reinterpret_cast<float4 *>(bpart + ((size_t)(acc * NT + team) * NGRP + grp) * RP + q * 4) = v;
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_rhs + acc * 8);
       }
     };
-    for (int k = 0; k < D && !issue_done; k++) issue_rows(k);
+    for (int k = 0; k < D; k++) issue_rows(k);
     for (int x = 0;; x++) {
       const int g = x * NT + team;  // global tile index: operand stage and order of the tensor-core instructions
-      if (x > 0) asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");  // the team has finished reading tile x - 1
-      if (!issue_done) issue_rows(x + D);  // into the stage tile x - 1 has left
+      issue_rows(x + D);  // into the stage this thread read tile x - 1 from
       const int st = x % NRT, ms = x % MR;
       const int2 d = desc[ms];  // published before meta_full[ms], which issue_rows(x) has waited for
       const int n = d.x & 0xFF;
       if (n == 0) break;
-      mbar_wait(braw + st * 8, (uint32_t)(x / NRT) & 1u);
+      asm volatile("cp.async.wait_group %0;" ::"n"(D) : "memory");  // this thread's copies of tile x have landed
       if (d.y != brow) {
         flush_to(d.y);
         brow = d.y;
+        bcls = (d.x >> kWsClassShift) & 3;
       }
       const float4 *raw4 = reinterpret_cast<const float4 *>(smb + W::off_raw + (team * NRT + st) * W::RAW_BYTES);
       const float4 rt4 = *reinterpret_cast<const float4 *>(meta_rate + ms * 32 + j0);
@@ -1117,7 +1129,8 @@ __global__ void __launch_bounds__(AlsWs<TR, NT_, G_>::NTHREADS, 1) als_ws_kernel
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bmeta + slot * 8) : "memory");
       if (lane == 0) {
-        desc[slot] = live ? make_int2(min(KT, c.len - c.t * KT) | (c.t == 0 ? kWsFirst : 0) | (c.t == c.ntiles - 1 ? kWsLast : 0), c.i)
+        desc[slot] = live ? make_int2(min(KT, c.len - c.t * KT) | (c.t == 0 ? kWsFirst : 0) | (c.t == c.ntiles - 1 ? kWsLast : 0) |
+                                          ((c.t % NT) << kWsClassShift), c.i)
                           : make_int2(0, n_rows);
         mbar_arrive(bmeta + slot * 8);  // release: the descriptor is visible to whoever sees the phase complete
       }
@@ -1179,7 +1192,7 @@ __global__ void __launch_bounds__(AlsWs<TR, NT_, G_>::NTHREADS, 1) als_ws_kernel
     }
     const int p = 32 * ((tid >> 5) & 3) + lane;  // TMEM lane this thread may read (its warp's quadrant)
     for (int i = g; i < n_rows; i += G) {
-      const int acc = i % NACC;  // == g
+      const int acc = i % NACC;
       const uint32_t par = (uint32_t)(i / NACC) & 1u;
       const int seg = a.seg0 + (int)blockIdx.x + i * (int)gridDim.x;
       const int row = a.seg_row[seg], slot = a.seg_slot[seg];
@@ -1267,10 +1280,10 @@ __global__ void __launch_bounds__(AlsWs<TR, NT_, G_>::NTHREADS, 1) als_ws_kernel
             }
           }
         }
-        if (t < RP) {  // right-hand side: the converters' partial sums
+        if (t < RP) {  // right-hand side: the converters' partial sums, one class per tile-in-row index mod NT
+          const int ncls = min(NT, (a.seg_len[seg] + KT - 1) / KT);
           float sacc = 0.f;
-#pragma unroll
-          for (int k = 0; k < NT * NGRP; k++) sacc += bpart[(size_t)(acc * NT * NGRP + k) * RP + t];
+          for (int k = 0; k < ncls * NGRP; k++) sacc += bpart[(size_t)(acc * NT * NGRP + k) * RP + t];
           gbv[t] = sacc;
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1327,7 +1340,7 @@ template <int TR>
 static int launch_als_ws(mfb_engine *e, const AlsArgs &b, int n_primal, bool long_rows) {
   if (n_primal <= 0) return 0;
   if (TR == 8) return long_rows ? launch_als_ws_cfg<8, 3, 1>(e, b, n_primal) : launch_als_ws_cfg<8, 1, 2>(e, b, n_primal);
-  return long_rows ? launch_als_ws_cfg<4, 4, 1>(e, b, n_primal) : launch_als_ws_cfg<4, 2, 3>(e, b, n_primal);
+  return long_rows ? launch_als_ws_cfg<4, 4, 1>(e, b, n_primal) : launch_als_ws_cfg<4, 2, 4>(e, b, n_primal);
 }
 
 template <int TRD>

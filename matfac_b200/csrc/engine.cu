@@ -60,9 +60,31 @@ constexpr size_t kDevCacheMaxIdle = (size_t)16 << 30;
 thread_local cudaStream_t g_current_stream = nullptr;
 }  // namespace
 
-cudaError_t enter(mfb_engine *e) {
+cudaError_t enter(mfb_engine *e, int join) {
   g_current_stream = e->stream;
-  return cudaSetDevice(e->device);
+  cudaError_t err = cudaSetDevice(e->device);
+  if (err != cudaSuccess) return err;
+  if ((join & kJoinUpload) && e->upload_pending) {
+    e->upload_pending = false;
+    if ((err = cudaStreamWaitEvent(e->stream, e->ev_upload, 0)) != cudaSuccess) return err;
+  }
+  if ((join & kJoinDownload) && e->download_pending) {
+    e->download_pending = false;
+    if ((err = cudaStreamWaitEvent(e->stream, e->ev_download, 0)) != cudaSuccess) return err;
+  }
+  return cudaSuccess;
+}
+// the copy stream starts behind everything queued on the engine's stream so far
+static cudaError_t fork_copy_stream(mfb_engine *e) {
+  cudaError_t err;
+  if (!e->stream_copy) {
+    if ((err = cudaStreamCreateWithFlags(&e->stream_copy, cudaStreamNonBlocking)) != cudaSuccess) return err;
+    if ((err = cudaEventCreateWithFlags(&e->ev_copy_mark, cudaEventDisableTiming)) != cudaSuccess) return err;
+    if ((err = cudaEventCreateWithFlags(&e->ev_upload, cudaEventDisableTiming)) != cudaSuccess) return err;
+    if ((err = cudaEventCreateWithFlags(&e->ev_download, cudaEventDisableTiming)) != cudaSuccess) return err;
+  }
+  if ((err = cudaEventRecord(e->ev_copy_mark, e->stream)) != cudaSuccess) return err;
+  return cudaStreamWaitEvent(e->stream_copy, e->ev_copy_mark, 0);
 }
 void leave() { g_current_stream = nullptr; }
 
@@ -398,6 +420,11 @@ extern "C" void mfb_destroy(mfb_engine *e) {
   mfb::enter(e);
   cudaStreamSynchronize(e->stream);
   cudaStreamSynchronize(e->stream_hot);
+  if (e->stream_copy) {
+    cudaStreamSynchronize(e->stream_copy);
+    cudaEventDestroy(e->ev_copy_mark); cudaEventDestroy(e->ev_upload); cudaEventDestroy(e->ev_download);
+    cudaStreamDestroy(e->stream_copy);
+  }
   for (int w = 0; w < 3; w++) e->mat[w].release();
   e->sgd.release();
   dev_free(e->U); dev_free(e->V); dev_free(e->bestU); dev_free(e->bestV);
@@ -426,6 +453,7 @@ extern "C" int mfb_sync(mfb_engine *e) {
   MFB_REQUIRE(e, "null engine");
   MFB_CUDA(mfb::enter(e));
   MFB_CUDA(cudaStreamSynchronize(e->stream));
+  if (e->stream_copy) MFB_CUDA(cudaStreamSynchronize(e->stream_copy));
   return comm_check_error(e);
 }
 
@@ -457,7 +485,7 @@ extern "C" int mfb_upload_csr(mfb_engine *e, int which, int32_t nrows, int32_t n
   MFB_REQUIRE(rowptr && (nnz == 0 || (rowind && rowval)), "mfb_upload_csr: CSR arrays are required");
   MFB_REQUIRE(nnz >= 0 && nnz < (int64_t)INT32_MAX, "mfb_upload_csr: nnz must fit in int32");
   MFB_REQUIRE(nrows <= e->n_users && ncols <= e->n_items, "mfb_upload_csr: matrix larger than the engine");
-  MFB_CUDA(mfb::enter(e));
+  MFB_CUDA(mfb::enter(e, 0));  // the ratings do not touch the factors: no need to wait for a factor copy
   DevCsr &m = e->mat[which];
   // same shape as the resident matrix (an epoch loop that re-uploads its input): keep the allocations,
   // cudaFree / cudaMalloc of GB-sized buffers cost milliseconds each
@@ -508,8 +536,9 @@ extern "C" int mfb_upload_csr(mfb_engine *e, int which, int32_t nrows, int32_t n
       MFB_CUDA(cudaMemcpyAsync(m.colval, colval, sizeof(float) * (size_t)nnz, cudaMemcpyHostToDevice, e->stream));
     }
   }
-  // the host arrays are only borrowed for the duration of the call
-  MFB_CUDA(cudaStreamSynchronize(e->stream));
+  // the host arrays are only borrowed for the duration of the call — unless the caller has asked for overlapped
+  // copies ("copy_overlap": buffers stay valid until the next mfb_sync)
+  if (!e->opt_copy_overlap) MFB_CUDA(cudaStreamSynchronize(e->stream));
   return 0;
 }
 
@@ -624,13 +653,25 @@ extern "C" int mfb_upload_factors(mfb_engine *e, const float *U, int64_t ldU, co
   MFB_REQUIRE(e, "null engine");
   MFB_CUDA(mfb::enter(e));
   size_t w = sizeof(float) * (size_t)e->rank, dp = sizeof(float) * (size_t)e->ld;
+  // "copy_overlap": the copy runs on the copy stream behind what is queued now (e.g. the rating upload, so that the
+  // two do not share the link) and next to what is queued after it and does not touch the factors (mfb_sgd_plan)
+  cudaStream_t st = e->stream;
+  if (e->opt_copy_overlap) {
+    MFB_CUDA(fork_copy_stream(e));
+    st = e->stream_copy;
+  }
   if (U) {
     MFB_REQUIRE(ldU >= e->rank, "mfb_upload_factors: ldU < rank");
-    MFB_CUDA(cudaMemcpy2DAsync(e->U, dp, U, sizeof(float) * (size_t)ldU, w, e->n_users, cudaMemcpyHostToDevice, e->stream));
+    MFB_CUDA(cudaMemcpy2DAsync(e->U, dp, U, sizeof(float) * (size_t)ldU, w, e->n_users, cudaMemcpyHostToDevice, st));
   }
   if (V) {
     MFB_REQUIRE(ldV >= e->rank, "mfb_upload_factors: ldV < rank");
-    MFB_CUDA(cudaMemcpy2DAsync(e->V, dp, V, sizeof(float) * (size_t)ldV, w, e->n_items, cudaMemcpyHostToDevice, e->stream));
+    MFB_CUDA(cudaMemcpy2DAsync(e->V, dp, V, sizeof(float) * (size_t)ldV, w, e->n_items, cudaMemcpyHostToDevice, st));
+  }
+  if (e->opt_copy_overlap) {
+    MFB_CUDA(cudaEventRecord(e->ev_upload, e->stream_copy));
+    e->upload_pending = true;
+    return 0;
   }
   MFB_CUDA(cudaStreamSynchronize(e->stream));
   return 0;
@@ -641,13 +682,25 @@ extern "C" int mfb_download_factors(mfb_engine *e, int which, float *U, int64_t 
   MFB_CUDA(mfb::enter(e));
   const float *su = which == MFB_BEST ? e->bestU : e->U, *sv = which == MFB_BEST ? e->bestV : e->V;
   size_t w = sizeof(float) * (size_t)e->rank, sp = sizeof(float) * (size_t)e->ld;
+  // "copy_overlap": the copy leaves on the copy stream once everything queued so far has finished and runs next to
+  // the evaluations queued after it; the host buffers are complete after mfb_sync
+  cudaStream_t st = e->stream;
+  if (e->opt_copy_overlap) {
+    MFB_CUDA(fork_copy_stream(e));
+    st = e->stream_copy;
+  }
   if (U) {
     MFB_REQUIRE(ldU >= e->rank, "mfb_download_factors: ldU < rank");
-    MFB_CUDA(cudaMemcpy2DAsync(U, sizeof(float) * (size_t)ldU, su, sp, w, e->n_users, cudaMemcpyDeviceToHost, e->stream));
+    MFB_CUDA(cudaMemcpy2DAsync(U, sizeof(float) * (size_t)ldU, su, sp, w, e->n_users, cudaMemcpyDeviceToHost, st));
   }
   if (V) {
     MFB_REQUIRE(ldV >= e->rank, "mfb_download_factors: ldV < rank");
-    MFB_CUDA(cudaMemcpy2DAsync(V, sizeof(float) * (size_t)ldV, sv, sp, w, e->n_items, cudaMemcpyDeviceToHost, e->stream));
+    MFB_CUDA(cudaMemcpy2DAsync(V, sizeof(float) * (size_t)ldV, sv, sp, w, e->n_items, cudaMemcpyDeviceToHost, st));
+  }
+  if (e->opt_copy_overlap) {
+    MFB_CUDA(cudaEventRecord(e->ev_download, e->stream_copy));
+    e->download_pending = true;
+    return 0;
   }
   MFB_CUDA(cudaStreamSynchronize(e->stream));
   return comm_check_error(e);  // rows that never arrived from a peer must not be read as factors
@@ -689,7 +742,7 @@ extern "C" int mfb_sgd_plan(mfb_engine *e, int32_t P, const int32_t *user_part, 
     for (int u = 0; u < e->n_users; u++) MFB_REQUIRE(user_part[u] < P, "mfb_sgd_plan: user_part entry >= P");
     for (int i = 0; i < e->n_items; i++) MFB_REQUIRE(item_part[i] < P, "mfb_sgd_plan: item_part entry >= P");
   }
-  MFB_CUDA(mfb::enter(e));
+  MFB_CUDA(mfb::enter(e, 0));  // the plan reads the ratings only: it may run next to a factor upload
   return sgd_plan_build(e, P, user_part, item_part);
 }
 
@@ -751,6 +804,7 @@ extern "C" int mfb_set_option(mfb_engine *e, const char *name, double value) {
   else if (n == "als_tensor_cores") e->opt_als_tensor_cores = (int)value;
   else if (n == "als_dual") e->opt_als_dual = (int)value;
   else if (n == "als_ws_split") e->opt_als_ws_split = (int)value;
+  else if (n == "copy_overlap") e->opt_copy_overlap = (int)value;
   else if (n == "als_chunk") {
     if (value < 64) return mfb::fail("mfb_set_option: als_chunk must be >= 64", __FILE__, __LINE__);
     e->opt_als_chunk = (int)value;
@@ -833,7 +887,7 @@ extern "C" int mfb_eval(mfb_engine *e, int which, int factors, int variant, int 
   MFB_REQUIRE(variant >= MFB_MF && variant <= MFB_TMFDROPOUT, "mfb_eval: bad variant");
   MFB_REQUIRE(e->mat[which].rowptr, "mfb_eval: matrix not uploaded");
   MFB_REQUIRE(variant == MFB_MF || e->aux_variant == variant, "mfb_eval: mfb_set_aux not called for this variant");
-  MFB_CUDA(mfb::enter(e));
+  MFB_CUDA(mfb::enter(e, kJoinUpload));  // reads the factors: may run next to a factor download
   return eval_launch(e, which, factors, variant, weighted, want_norms, out);
 }
 

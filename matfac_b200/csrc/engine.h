@@ -26,8 +26,12 @@ void dev_cache_release(int device);
 }  // namespace mfb
 struct mfb_engine;
 namespace mfb {
-// every C-ABI entry: makes the engine's device current and names its stream as the one this thread works on
-cudaError_t enter(mfb_engine *e);
+// every C-ABI entry: makes the engine's device current and names its stream as the one this thread works on; with
+// option "copy_overlap" it also orders the engine's stream behind factor copies still running on the copy stream —
+// kJoinUpload: behind a pending factor upload (everything that touches U / V), kJoinDownload: behind a pending factor
+// download (everything that WRITES U / V; evaluations may run next to it)
+constexpr int kJoinUpload = 1, kJoinDownload = 2, kJoinAll = 3;
+cudaError_t enter(mfb_engine *e, int join = kJoinAll);
 void leave();
 template <class T>
 inline cudaError_t dev_alloc(T **p, size_t bytes) { return dev_alloc_bytes(reinterpret_cast<void **>(p), bytes); }
@@ -195,6 +199,11 @@ struct mfb_engine {
   cudaStream_t stream = nullptr;
   cudaStream_t stream_hot = nullptr;  // hot-row CTAs run next to the shuffled kernel (forked from / joined into `stream`)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // option "copy_overlap": factor uploads / downloads go to their own stream and return without synchronising
+  int opt_copy_overlap = 0;
+  cudaStream_t stream_copy = nullptr;
+  cudaEvent_t ev_copy_mark = nullptr, ev_upload = nullptr, ev_download = nullptr;
+  bool upload_pending = false, download_pending = false;
   cudaEvent_t events[16] = {};
 
   float *U = nullptr, *V = nullptr;          // [n][ld] fp32, padding columns are zero

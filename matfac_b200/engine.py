@@ -170,10 +170,15 @@ class Engine:
         self._check(self.L.mfb_upload_factors(self.h, _p(U), 0 if U is None else U.shape[1], _p(V),
                                               0 if V is None else V.shape[1]))
 
-    def download_factors(self, which=CURRENT):
-        U = np.empty((self.n_users, self.rank), np.float32)
-        V = np.empty((self.n_items, self.rank), np.float32)
-        self._check(self.L.mfb_download_factors(self.h, which, _p(U), self.rank, _p(V), self.rank))
+    def download_factors(self, which=CURRENT, into=None):
+        """into = (U, V): caller-owned float32 buffers — with option copy_overlap they are complete after sync()."""
+        if into is not None:
+            U, V = into
+            assert U.dtype == np.float32 and V.dtype == np.float32 and U.flags.c_contiguous and V.flags.c_contiguous
+        else:
+            U = np.empty((self.n_users, self.rank), np.float32)
+            V = np.empty((self.n_items, self.rank), np.float32)
+        self._check(self.L.mfb_download_factors(self.h, which, _p(U), U.shape[1], _p(V), V.shape[1]))
         return U, V
 
     def set_aux(self, variant, user_freq, item_freq, user_train=None, item_train=None, user_pred=None,

@@ -676,3 +676,46 @@ def test_pack_unpack_rows_roundtrip():
     mask = np.ones(V0.shape[0], bool); mask[ids] = False
     assert not V1[mask].any()
     eng.close()
+
+
+def test_overlapped_copies_give_the_same_results():
+    """Option copy_overlap (the end-to-end step of bench.py): uploads and downloads return without synchronising, the
+    factor upload runs next to the plan, the download next to the evaluations.  Results must equal the synchronous
+    calls: the evaluation of the uploaded factors, and the factors after a (deterministic) ALS half-step."""
+    splits = small_problem(700, 400, 60000, seed=17)
+    tr, va = splits[0], splits[1]
+    om = oracle_model(splits, "mf", 64, maxiter=1, ureg=0.1, ireg=0.1, nthreads=4)
+    eng, _ = make_engine(splits, om, 64)
+    rng = np.random.default_rng(3)
+    U0, V0 = om.factors()
+    Ua = rng.standard_normal(U0.shape).astype(np.float32)
+    Va = rng.standard_normal(V0.shape).astype(np.float32)
+    # synchronous reference
+    eng.upload_csr(E.TRAIN, tr)
+    eng.upload_factors(Ua, Va)
+    eng.sgd_plan(1)
+    want_obj = eng.eval(E.TRAIN, E.CURRENT, E.MF, False, True)
+    want_val = eng.eval(E.VAL)
+    eng.als_half_step(E.USER, 0.1)
+    Uw, Vw = eng.download_factors()
+    # overlapped: same calls, nothing synchronises until sync()
+    eng.set_option("copy_overlap", 1)
+    Ug, Vg = np.zeros_like(Uw), np.zeros_like(Vw)
+    for rep in range(3):
+        eng.upload_factors(np.zeros_like(Ua), np.zeros_like(Va))
+        eng.sync()
+        eng.upload_csr(E.TRAIN, tr)
+        eng.upload_factors(Ua, Va)
+        eng.sgd_plan(1)
+        got_obj = eng.eval(E.TRAIN, E.CURRENT, E.MF, False, True)
+        got_val = eng.eval(E.VAL)
+        eng.als_half_step(E.USER, 0.1)
+        eng.download_factors(into=(Ug, Vg))
+        after = eng.eval(E.VAL)  # runs next to the download
+        eng.als_half_step(E.ITEM, 0.1)  # writes V: must be ordered behind the download on the device
+        eng.sync()
+        assert np.array_equal(got_obj, want_obj) and np.array_equal(got_val, want_val)
+        assert np.array_equal(Ug, Uw) and np.array_equal(Vg, Vw)
+        assert after[1] == want_val[1]
+    eng.set_option("copy_overlap", 0)
+    eng.close()
