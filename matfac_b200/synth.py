@@ -148,6 +148,30 @@ def make_splits(n_users, n_items, nnz, seed=20260101, fracs=(0.8, 0.1, 0.1), **k
     return tuple(out)
 
 
+def make_ranking_splits(n_users, n_items, nnz, seed=20260101, **kw):
+    """Leave-one-out style splits for the ranking metrics (model.cpp:981-1332 read the FIRST rating of every user's
+    row in the validation / test matrix unconditionally): every user holds at least one validation and one test
+    rating, none of them among its training items; the rest of the ratings go to train."""
+    users, items, vals = make_ratings(n_users, n_items, nnz, seed=seed, **kw)
+    rng = np.random.default_rng(seed + 11)
+    key = rng.random(users.shape[0])
+    order = np.lexsort((key, users))  # by user, random inside a user
+    users, items, vals = users[order], items[order], vals[order]
+    first = np.ones(users.shape[0], dtype=bool)
+    first[1:] = users[1:] != users[:-1]
+    pos = np.arange(users.shape[0]) - np.maximum.accumulate(np.where(first, np.arange(users.shape[0]), 0))
+    deg = np.bincount(users, minlength=n_users)
+    assert deg.min() >= 3, "every user needs at least three ratings"
+    extra = rng.random(users.shape[0])
+    te = (pos == 0) | ((pos >= 3) & (extra < 0.05))
+    va = (pos == 1) | ((pos >= 3) & (extra >= 0.05) & (extra < 0.10))
+    tr = ~(te | va)
+    out = []
+    for m in (tr, va, te):
+        out.append(coo_to_csr(users[m], items[m], vals[m], n_users).build_csc())
+    return tuple(out)
+
+
 def write_text_csr(mat: Csr, path: str) -> None:
     """The reference's input format: one line per user, ``item rating item rating ...``,
     0-indexed (python/convert_scipy_sparse_to_text_csr.py:19-26; datastruct.cpp:16)."""

@@ -26,6 +26,7 @@
 #include <numeric>
 #include <random>
 #include <string>
+#include <tuple>
 #include <unordered_set>
 #include <utility>
 #include <vector>
@@ -980,6 +981,107 @@ extern "C" double mfo_rmse(const mfo_model *m, const mfo_data *d, int which, int
 }
 extern "C" double mfo_objective(const mfo_model *m, const mfo_data *d) {
   return objectiveMasked(m, m->cur, d->mat[0]);
+}
+
+// ---- ranking metrics (model.cpp:760-1332) ------------------------------------------------------------------
+// hitRate / arHR family (model.cpp:981-1332): the user's test item is the FIRST rating of its row in testMat; all items
+// that are neither rated by the user in the training matrix nor invalid are scored with estRating and the N best kept
+// in a heap ordered by descComp (util.cpp:760: a.second > b.second, i.e. the smallest kept score on top), sorted, and
+// searched for the test item.  Returns its position or -1.
+static int topNPosition(const mfo_model *m, const Facs &f, const Csr &tr, int u, int testItem, int N) {
+  std::unordered_set<int> uTrItems;
+  for (int64_t ii = tr.rowptr[u]; ii < tr.rowptr[u + 1]; ii++) uTrItems.insert(tr.rowind[ii]);
+  auto descComp = [](const std::pair<int, double> &a, const std::pair<int, double> &b) { return a.second > b.second; };
+  std::vector<std::pair<int, double>> topN;
+  std::make_heap(topN.begin(), topN.end(), descComp);
+  for (int item = 0; item < tr.ncols; item++) {
+    if (uTrItems.count(item) || m->invalidItems.count(item) > 0) continue;
+    topN.push_back(std::make_pair(item, estRating(m, f, u, item)));
+    std::push_heap(topN.begin(), topN.end(), descComp);
+    if ((int)topN.size() > N) {
+      std::pop_heap(topN.begin(), topN.end(), descComp);
+      topN.pop_back();
+    }
+  }
+  std::sort(topN.begin(), topN.end(), descComp);
+  for (size_t pos = 0; pos < topN.size(); pos++)
+    if (testItem == topN[pos].first) return (int)pos;
+  return -1;
+}
+
+// one user's term of NDCG / NDCGU / NDCGI (model.cpp:776-826): the N = 10 best predicted of the user's test ratings,
+// DCG in prediction order over the ideal DCG of THOSE ratings; false when the user does not count
+static bool ndcgUser(const mfo_model *m, const Facs &f, const Csr &te, int u, const uint8_t *filtItems, double *term) {
+  const int N = 10;
+  typedef std::tuple<int, float, float> Triplet;  // item, actual, predicted
+  auto byPred = [](const Triplet &a, const Triplet &b) { return std::get<2>(a) > std::get<2>(b); };
+  auto byAct = [](const Triplet &a, const Triplet &b) { return std::get<1>(a) > std::get<1>(b); };
+  std::vector<Triplet> rs;
+  for (int64_t ii = te.rowptr[u]; ii < te.rowptr[u + 1]; ii++) {
+    int item = te.rowind[ii];
+    if (m->invalidItems.count(item) > 0) continue;
+    if (filtItems && !filtItems[item]) continue;
+    float rat = te.rowval[ii];
+    float pred = estRating(m, f, u, item);
+    rs.push_back(Triplet(item, rat, pred));
+    std::push_heap(rs.begin(), rs.end(), byPred);
+    if ((int)rs.size() > N) {
+      std::pop_heap(rs.begin(), rs.end(), byPred);
+      rs.pop_back();
+    }
+  }
+  if (rs.size() < 2) return false;
+  std::sort(rs.begin(), rs.end(), byPred);
+  float u_ndcg = 0.0;
+  for (int i = 0; i < N && i < (int)rs.size(); i++) u_ndcg += (std::pow(2.0, std::get<1>(rs[i])) - 1) / std::log2((i + 1) + 1);
+  std::sort(rs.begin(), rs.end(), byAct);
+  float u_dcg_max = 0.0;
+  for (int i = 0; i < N && i < (int)rs.size(); i++) u_dcg_max += (std::pow(2.0, std::get<1>(rs[i])) - 1) / std::log2((i + 1) + 1);
+  if (!(u_dcg_max > kEps)) return false;
+  *term = u_ndcg / u_dcg_max;
+  return true;
+}
+
+// out[0..2] = hitRate, arHR, NDCG (model.cpp:1158, :981, :760);
+// out[3..8] = hitRateU {first, second}, arHRU {first, second}, NDCGU {first, second} for filt_users (:1277, :1100, :833);
+// out[9..14] = the I variants for filt_items (:1214, :1037, :907).  Filters: uint8 per id, 1 = in the set; NULL = skip.
+extern "C" void mfo_rank_metrics(const mfo_model *m, const mfo_data *d, int which, int best, const uint8_t *filt_users,
+                                 const uint8_t *filt_items, double out[15]) {
+  const Facs &f = best ? m->best : m->cur;
+  const Csr &tr = d->mat[0], &te = d->mat[which];
+  for (int k = 0; k < 15; k++) out[k] = 0;
+  // three passes of the hitRate family: no filter, users, items
+  for (int pass = 0; pass < 3; pass++) {
+    if ((pass == 1 && !filt_users) || (pass == 2 && !filt_items)) continue;
+    double hits10 = 0, hits1000 = 0, nVal = 0;
+    for (int u = 0; u < tr.nrows; u++) {
+      if (m->invalidUsers.count(u) > 0) continue;
+      if (pass == 1 && !filt_users[u]) continue;
+      const int testItem = te.rowind[te.rowptr[u]];
+      if (pass == 2 && !filt_items[testItem]) continue;
+      if (topNPosition(m, f, tr, u, testItem, 10) >= 0) hits10 += 1;  // N = 10 (:1164)
+      const int pos = topNPosition(m, f, tr, u, testItem, 1000);       // N = 1000 (:985)
+      if (pos >= 0) hits1000 += 1.0 / (pos + 1);
+      nVal += 1;
+    }
+    if (pass == 0) { out[0] = hits10 / nVal; out[1] = hits1000 / nVal; }
+    else { double *o = out + (pass == 1 ? 3 : 9); o[0] = hits10; o[1] = hits10 / nVal; o[2] = hits1000; o[3] = hits1000 / nVal; }
+  }
+  for (int pass = 0; pass < 3; pass++) {
+    if ((pass == 1 && !filt_users) || (pass == 2 && !filt_items)) continue;
+    double ndcg = 0;
+    int nVal = 0;
+    for (int u = 0; u < te.nrows; u++) {
+      if (m->invalidUsers.count(u) > 0) continue;
+      if (pass == 1 && !filt_users[u]) continue;
+      double term;
+      if (!ndcgUser(m, f, te, u, pass == 2 ? filt_items : nullptr, &term)) continue;
+      ndcg += term;
+      nVal++;
+    }
+    if (pass == 0) out[2] = ndcg / nVal;
+    else { double *o = out + (pass == 1 ? 7 : 13); o[0] = nVal; o[1] = ndcg / nVal; }
+  }
 }
 
 extern "C" void mfo_dsgd_plan(const mfo_model *mc, const mfo_data *d, int P, int n_subepochs,

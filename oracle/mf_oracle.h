@@ -78,6 +78,13 @@ double mfo_rmse(const mfo_model *m, const mfo_data *d, int which, int best);
 /* objective (model.cpp:1770-1815; IFWMF modelInvPopMF.cpp:3-55) */
 double mfo_objective(const mfo_model *m, const mfo_data *d);
 
+/* ranking metrics (model.cpp:760-1332) of the current (best = 0) or best model against matrix `which` (1 val, 2 test);
+ * every valid user must hold at least one rating in that matrix (the reference reads the first one unconditionally).
+ * out[0..2] = hitRate, arHR, NDCG; out[3..8] = hitRateU, arHRU, NDCGU as {first, second} pairs for filt_users;
+ * out[9..14] = hitRateI, arHRI, NDCGI for filt_items (uint8 per id, 1 = in the filter set; NULL skips the variants) */
+void mfo_rank_metrics(const mfo_model *m, const mfo_data *d, int which, int best, const uint8_t *filt_users,
+                      const uint8_t *filt_items, double out[15]);
+
 /* DSGD bookkeeping exposed for bit-exact checks of the host-side schedule code:
  * user_part/item_part: part id per id, -1 for invalid ids; schedule: n_subepochs * P pairs (row,col)
  * drawn from the same mt19937 stream the trainer uses (shuffles first, then schedules). */

@@ -206,6 +206,31 @@ int main(int argc, char **argv) {
     fprintf(fp, "last_test_rmse %.17g\n", mfModel->RMSE(data.testMat, invalidUsers, invalidItems));
     fprintf(fp, "last_objective %.17g\n", mfModel->objective(data, invalidUsers, invalidItems));
     fprintf(fp, "learn_rate %.9g\n", (double)mfModel->learnRate);
+    if (flag(kv, "rank_metrics", "0") == "1") {
+      // the reference's own ranking metrics (model.cpp:760-1332) of the best model; filters: users u % 3 == 0, items i % 2 == 0
+      std::unordered_set<int> fu, fi;
+      for (int u = 0; u < data.nUsers; u += 3) fu.insert(u);
+      for (int i = 0; i < data.nItems; i += 2) fi.insert(i);
+      const char *names[2] = {"val", "test"};
+      gk_csr_t *mats[2] = {data.valMat, data.testMat};
+      for (int w = 0; w < 2; w++) {
+        fprintf(fp, "%s_hr %.17g\n", names[w], bestModel->hitRate(data, invalidUsers, invalidItems, mats[w]));
+        fprintf(fp, "%s_arhr %.17g\n", names[w], bestModel->arHR(data, invalidUsers, invalidItems, mats[w]));
+        fprintf(fp, "%s_ndcg %.17g\n", names[w], bestModel->NDCG(invalidUsers, invalidItems, mats[w]));
+        auto a = bestModel->hitRateU(data, fu, invalidUsers, invalidItems, mats[w]);
+        fprintf(fp, "%s_hru_first %.17g\n%s_hru %.17g\n", names[w], (double)a.first, names[w], a.second);
+        auto b = bestModel->arHRU(data, fu, invalidUsers, invalidItems, mats[w]);
+        fprintf(fp, "%s_arhru_first %.17g\n%s_arhru %.17g\n", names[w], b.first, names[w], b.second);
+        auto c = bestModel->NDCGU(fu, invalidUsers, invalidItems, mats[w]);
+        fprintf(fp, "%s_ndcgu_first %.17g\n%s_ndcgu %.17g\n", names[w], (double)c.first, names[w], c.second);
+        auto d2 = bestModel->hitRateI(data, fi, invalidUsers, invalidItems, mats[w]);
+        fprintf(fp, "%s_hri_first %.17g\n%s_hri %.17g\n", names[w], (double)d2.first, names[w], d2.second);
+        auto e2 = bestModel->arHRI(data, fi, invalidUsers, invalidItems, mats[w]);
+        fprintf(fp, "%s_arhri_first %.17g\n%s_arhri %.17g\n", names[w], e2.first, names[w], e2.second);
+        auto f2 = bestModel->NDCGI(fi, invalidUsers, invalidItems, mats[w]);
+        fprintf(fp, "%s_ndcgi_first %.17g\n%s_ndcgi %.17g\n", names[w], (double)f2.first, names[w], f2.second);
+      }
+    }
     fprintf(fp, "signature %s\n", bestModel->modelSignature().c_str());
     fclose(fp);
   }

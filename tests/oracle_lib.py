@@ -71,6 +71,7 @@ def lib():
         L.mfo_objective.restype = C.c_double
         L.mfo_objective.argtypes = [C.c_void_p, C.c_void_p]
         L.mfo_dsgd_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mfo_rank_metrics.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mfo_tmf_ranks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.mfo_ifw_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mfo_ccdpp_dim_order.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -146,6 +147,17 @@ class OracleModel:
     def set_factors(self, U, V):
         U = np.ascontiguousarray(U, np.float32); V = np.ascontiguousarray(V, np.float32)
         lib().mfo_set_factors(self.h, _p(U), _p(V))
+
+    RANK_KEYS = ("hr", "arhr", "ndcg", "hru_first", "hru", "arhru_first", "arhru", "ndcgu_first", "ndcgu",
+                 "hri_first", "hri", "arhri_first", "arhri", "ndcgi_first", "ndcgi")
+
+    def rank_metrics(self, which, best=False, filt_users=None, filt_items=None):
+        """Ranking metrics of model.cpp:760-1332 as a dict keyed like the lines ref_driver writes (RANK_KEYS)."""
+        out = np.zeros(15, np.float64)
+        fu = None if filt_users is None else np.ascontiguousarray(filt_users, np.uint8)
+        fi = None if filt_items is None else np.ascontiguousarray(filt_items, np.uint8)
+        lib().mfo_rank_metrics(self.h, self.data.h, which, int(best), _p(fu), _p(fi), _p(out))
+        return dict(zip(self.RANK_KEYS, out.tolist()))
 
     def history(self):
         out = []

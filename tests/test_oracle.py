@@ -123,3 +123,58 @@ def test_stratum_schedule_is_a_permutation_matrix():
     counts = np.bincount(up[up >= 0], minlength=4)
     per = (up >= 0).sum() // 4
     assert counts[0] == per + 1 and counts[1] == per
+
+
+# ---- ranking metrics (model.cpp:760-1332) -----------------------------------------------------------------------
+RANK_CASES = [("mf", "sgd", 1, {}), ("TMF", "sgd", 2, {"rhorms": 20.0, "alpha": 0.5})]
+RANK_BASE = dict(facdim=8, maxiter=12, seed=3, ureg=0.05, ireg=0.05, learnrate=0.02)
+
+
+def ranking_problem():
+    return synth.make_ranking_splits(300, 200, 9000, seed=5, user_s=0.3)
+
+
+def rank_filters(n_users, n_items):
+    fu = np.zeros(n_users, np.uint8); fu[::3] = 1   # the sets ref_driver.cpp builds for --rank_metrics 1
+    fi = np.zeros(n_items, np.uint8); fi[::2] = 1
+    return fu, fi
+
+
+def oracle_rank_dict(m, od):
+    fu, fi = rank_filters(od.n_users, od.n_items)
+    out = {}
+    for which, name in ((1, "val"), (2, "test")):
+        for k, v in m.rank_metrics(which, best=True, filt_users=fu, filt_items=fi).items():
+            out[f"{name}_{k}"] = v
+    return out
+
+
+@pytest.mark.parametrize("algo,method,threads,extra", RANK_CASES)
+def test_oracle_ranking_metrics_match_reference_binary(tmp_path, algo, method, threads, extra):
+    """hitRate / arHR / NDCG and their U / I variants of the best model, computed by the reference's own model.cpp."""
+    if not ol.have_ref():
+        pytest.skip("oracle/_ref/mf_ref not built (no /root/reference on this machine)")
+    files = synth.write_split_files(str(tmp_path), *ranking_problem())
+    fl = dict(RANK_BASE); fl.update(extra)
+    ref = ol.run_ref(files, str(tmp_path / "dump"), algo=algo, method=method, threads=threads, rank_metrics=1, **fl)
+    od = ol.OracleData(files=files)
+    m = make_model(od, algo, threads, fl)
+    m.train(method)
+    got = oracle_rank_dict(m, od)
+    assert ref["val_hr"] > 0.02 and ref["val_ndcg"] > 0.5  # a trained model: the metrics are not trivially zero
+    for k, v in got.items():
+        assert abs(v - ref[k]) <= 1e-12 * max(1.0, abs(ref[k])), (k, v, ref[k])
+
+
+@pytest.mark.parametrize("algo,method,threads,extra", RANK_CASES)
+def test_oracle_ranking_metrics_against_golden_vectors(algo, method, threads, extra):
+    path = os.path.join(GOLDEN, f"rank_{algo}_{method}.json")
+    if not os.path.exists(path):
+        pytest.skip("golden vector missing: run tests/golden/make_golden.py in the build container")
+    g = json.load(open(path))
+    fl = dict(RANK_BASE); fl.update(extra)
+    od = ol.OracleData(*ranking_problem())
+    m = make_model(od, algo, threads, fl)
+    m.train(method)
+    for k, v in oracle_rank_dict(m, od).items():
+        assert abs(v - g[k]) <= 1e-12 * max(1.0, abs(g[k])), (k, v, g[k])
