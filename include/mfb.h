@@ -209,6 +209,23 @@ int mfb_ccdpp_end(mfb_engine *e);
 int mfb_eval(mfb_engine *e, int which, int factors, int variant, int weighted, int want_norms,
              double out[4]);
 
+/* Ranking positions — the candidate scan of Model::hitRate / arHR and their U / I variants (model.cpp:981-1332).  For
+ * every user: the number of candidate items (not invalid, inside the training matrix, not rated by the user in the
+ * TRAIN matrix, not the test item itself) whose estRating exceeds that of the user's test item, which is the first
+ * rating of its row in matrix `which` (MFB_VAL or MFB_TEST, model.cpp:992).  That count is the test item's 0-based
+ * position in the reference's sorted top-N list (scores tie with probability zero), so pos[u] < 10 is a hit of
+ * hitRate, 1 / (pos[u] + 1) with pos[u] < 1000 the term of arHR, and the U / I variants are host-side filters over
+ * the same array.  pos[u] = -1: the user does not count (invalid, or no rating in `which` — the reference reads the
+ * row's first entry unconditionally); -2: counted, but the test item is not a candidate (never a hit).
+ * test_item (optional, [n_users]) receives the test items.  MFB_MF / MFB_IFWMF with rank <= 64: dense U V^T on
+ * tcgen05 (3xTF32 split, option "rank_tensor_cores" = 1, default) with the count fused into the epilogue; otherwise
+ * (and for the pair-dependent prediction ranks of MFB_TMF / MFB_TMFDROPOUT) one CTA per user on CUDA cores, rounded
+ * exactly as the reference's loops. */
+int mfb_rank_positions(mfb_engine *e, int which, int factors, int variant, int32_t *pos, int32_t *test_item);
+/* estRating of every rating of matrix `which`, CSR order (NaN where the user or the item is masked): the
+ * predictions Model::NDCG / NDCGU / NDCGI (model.cpp:760-978) rank, [nnz of the matrix] floats. */
+int mfb_predict(mfb_engine *e, int which, int factors, int variant, float *pred);
+
 /* Filtered evaluation in one pass (quartileRMSEs, main.cpp:700-768, which calls Model::RMSE(mat, filtItems, ...)
  * model.cpp:348-394, ::SE :397-443 and ::RMSEU :446-486 once per part): user_group[n_users] / item_group[n_items]
  * give every id a group 0..7 or 255 (in no group).  out[((side * 8) + g) * 2 + {0,1}] = sum of squared errors and

@@ -805,6 +805,7 @@ extern "C" int mfb_set_option(mfb_engine *e, const char *name, double value) {
   else if (n == "als_dual") e->opt_als_dual = (int)value;
   else if (n == "als_ws_split") e->opt_als_ws_split = (int)value;
   else if (n == "copy_overlap") e->opt_copy_overlap = (int)value;
+  else if (n == "rank_tensor_cores") e->opt_rank_tensor_cores = (int)value;
   else if (n == "als_chunk") {
     if (value < 64) return mfb::fail("mfb_set_option: als_chunk must be >= 64", __FILE__, __LINE__);
     e->opt_als_chunk = (int)value;
@@ -889,6 +890,26 @@ extern "C" int mfb_eval(mfb_engine *e, int which, int factors, int variant, int 
   MFB_REQUIRE(variant == MFB_MF || e->aux_variant == variant, "mfb_eval: mfb_set_aux not called for this variant");
   MFB_CUDA(mfb::enter(e, kJoinUpload));  // reads the factors: may run next to a factor download
   return eval_launch(e, which, factors, variant, weighted, want_norms, out);
+}
+
+extern "C" int mfb_rank_positions(mfb_engine *e, int which, int factors, int variant, int32_t *pos, int32_t *test_item) {
+  MFB_REQUIRE(e && pos && (which == MFB_VAL || which == MFB_TEST), "mfb_rank_positions: bad argument");
+  MFB_REQUIRE(factors == MFB_CURRENT || factors == MFB_BEST, "mfb_rank_positions: bad factor set");
+  MFB_REQUIRE(variant >= MFB_MF && variant <= MFB_TMFDROPOUT, "mfb_rank_positions: bad variant");
+  MFB_REQUIRE(e->mat[which].rowptr && e->mat[MFB_TRAIN].rowptr, "mfb_rank_positions: upload the training and the evaluated matrix first");
+  MFB_REQUIRE(variant == MFB_MF || e->aux_variant == variant, "mfb_rank_positions: mfb_set_aux not called for this variant");
+  MFB_CUDA(mfb::enter(e, kJoinUpload));
+  return rank_positions_launch(e, which, factors, variant, pos, test_item);
+}
+
+extern "C" int mfb_predict(mfb_engine *e, int which, int factors, int variant, float *pred) {
+  MFB_REQUIRE(e && which >= 0 && which < 3, "mfb_predict: bad argument");
+  MFB_REQUIRE(factors == MFB_CURRENT || factors == MFB_BEST, "mfb_predict: bad factor set");
+  MFB_REQUIRE(variant >= MFB_MF && variant <= MFB_TMFDROPOUT, "mfb_predict: bad variant");
+  MFB_REQUIRE(e->mat[which].rowptr && (pred || e->mat[which].nnz == 0), "mfb_predict: matrix not uploaded / null output");
+  MFB_REQUIRE(variant == MFB_MF || e->aux_variant == variant, "mfb_predict: mfb_set_aux not called for this variant");
+  MFB_CUDA(mfb::enter(e, kJoinUpload));
+  return rank_predict_launch(e, which, factors, variant, pred);
 }
 
 extern "C" int mfb_eval_groups(mfb_engine *e, int which, int factors, int variant, const uint8_t *user_group,

@@ -195,6 +195,7 @@ struct mfb_engine {
   int opt_als_chunk = 16384;          // ratings per CTA before a row is split over several CTAs
   int opt_als_dual = 1;               // short rows: solve the len x len dual system instead of rank x rank
   int opt_als_tensor_cores = 1;       // rank > 32: Gram on tcgen05 (3xTF32), warp-specialised persistent kernel; 0 = fp32 CUDA-core Gram; 2 = the round-1 one-CTA-per-row kernel (rank > 64)
+  int opt_rank_tensor_cores = 1;      // ranking positions: 1 = dense U V^T on tcgen05 where the model allows (rank <= 64, plain dot), 0 = CUDA cores
   int opt_als_ws_split = 0;           // warp-specialised kernel: 0 = converter teams / solver groups picked per side from the mean row length, 1 = the many-short-rows split, 2 = the few-long-rows split
   cudaStream_t stream = nullptr;
   cudaStream_t stream_hot = nullptr;  // hot-row CTAs run next to the shuffled kernel (forked from / joined into `stream`)
@@ -264,6 +265,8 @@ int sgd_debug_records(mfb_engine *e, int32_t a, int32_t b, int32_t *recs_out, in
 int eval_launch(mfb_engine *e, int which, int factors, int variant, int weighted, int want_norms, double out[4]);
 int eval_groups_launch(mfb_engine *e, int which, int factors, int variant, const uint8_t *user_group,
                        const uint8_t *item_group, double *out);
+int rank_positions_launch(mfb_engine *e, int which, int factors, int variant, int32_t *pos_host, int32_t *test_item_host);
+int rank_predict_launch(mfb_engine *e, int which, int factors, int variant, float *pred_host);
 int als_half_step_launch(mfb_engine *e, int side, float reg);
 int als_debug_gram(mfb_engine *e, int side, int32_t row, float *out, int32_t *rp_out);
 int ccdpp_begin_impl(mfb_engine *e);

@@ -25,7 +25,7 @@ SYMBOLS = [
     "mfb_last_error", "mfb_launch_count", "mfb_device_count", "mfb_create", "mfb_destroy", "mfb_sync", "mfb_pin_host",
     "mfb_unpin_host", "mfb_upload_csr", "mfb_set_masks", "mfb_upload_factors", "mfb_download_factors",
     "mfb_set_aux", "mfb_sgd_plan", "mfb_sgd_subepoch", "mfb_sgd_block_nnz", "mfb_debug_sgd_records", "mfb_debug_sgd_hot_batch", "mfb_sgd_epoch_flat", "mfb_set_option", "mfb_als_half_step", "mfb_debug_als_gram",
-    "mfb_ccdpp_begin", "mfb_ccdpp_rank1", "mfb_ccdpp_end", "mfb_eval", "mfb_eval_groups", "mfb_snapshot_best",
+    "mfb_ccdpp_begin", "mfb_ccdpp_rank1", "mfb_ccdpp_end", "mfb_eval", "mfb_eval_groups", "mfb_rank_positions", "mfb_predict", "mfb_snapshot_best",
     "mfb_restore_best", "mfb_event_record", "mfb_event_elapsed_ms", "mfb_device_factors", "mfb_stream",
     "mfb_pack_rows", "mfb_unpack_rows", "mfb_set_row_range",
     "mfb_build_csc", "mfb_download_csc", "mfb_comm_init", "mfb_comm_connect", "mfb_comm_barrier", "mfb_comm_error", "mfb_dsgd_push_block",
@@ -84,6 +84,8 @@ def load_library():
     L.mfb_ccdpp_end.argtypes = [vp]
     L.mfb_eval.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.mfb_eval_groups.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.mfb_rank_positions.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.mfb_predict.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
     L.mfb_snapshot_best.argtypes = [vp]
     L.mfb_restore_best.argtypes = [vp]
     L.mfb_event_record.argtypes = [vp, i32]
@@ -268,6 +270,18 @@ class Engine:
         out = np.zeros(32, np.float64)
         self._check(self.L.mfb_eval_groups(self.h, which, factors, variant, _p(ug), _p(ig), _p(out)))
         return out.reshape(2, 8, 2)
+
+    def rank_positions(self, which, factors=CURRENT, variant=MF):
+        """(pos, test_item) per user: see mfb_rank_positions in include/mfb.h."""
+        pos = np.zeros(self.n_users, np.int32)
+        tst = np.zeros(self.n_users, np.int32)
+        self._check(self.L.mfb_rank_positions(self.h, which, factors, variant, _p(pos), _p(tst)))
+        return pos, tst
+
+    def predict(self, which, nnz, factors=CURRENT, variant=MF):
+        pred = np.zeros(max(int(nnz), 1), np.float32)
+        self._check(self.L.mfb_predict(self.h, which, factors, variant, _p(pred)))
+        return pred[: int(nnz)]
 
     def rmse(self, which, factors=CURRENT, variant=MF):
         o = self.eval(which, factors, variant)

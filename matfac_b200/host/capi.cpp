@@ -107,4 +107,57 @@ extern "C" int mfh_sgd_plan(int32_t n_users, int32_t n_items, const uint8_t *inv
   return 0;
 }
 
+// Ranking metrics of a given factor pair through the host classes (Model::hitRate / arHR / NDCG and their U / I
+// variants): out[0..2] = hitRate, arHR, NDCG; out[3..8] = {first, second} of hitRateU, arHRU, NDCGU; out[9..14] = the I
+// variants (zeros where the filter is NULL) — the layout of the oracle's mfo_rank_metrics.
+extern "C" int mfh_rank_metrics(const mfh_problem *p, const float *U, const float *V, const uint8_t *invalid_users,
+                                const uint8_t *invalid_items, int which, const uint8_t *filt_users, const uint8_t *filt_items,
+                                double out[15]) {
+  if (!p || !U || !V || !out || (which != 1 && which != 2)) return 1;
+  std::string empty, trainName = "<memory>", prefix = p->prefix ? p->prefix : "/tmp/matfac";
+  Params params(p->facdim, p->maxiter, 5, p->seed, p->ureg, p->ireg, p->learnrate, p->rhorms, p->alpha, trainName,
+                trainName, trainName, empty, empty, empty, empty, empty, prefix);
+  Data data(fromArrays(p->train), fromArrays(p->val), fromArrays(p->test), p->facdim, prefix.c_str());
+  params.nUsers = data.nUsers;
+  params.nItems = data.nItems;
+  auto freq = getRowColFreq(data.trainMat);
+  std::vector<double> userFreq = freq.first, itemFreq = freq.second, noRank;
+  std::unique_ptr<Model> model;
+  const std::string algo = p->algo ? p->algo : "mf";
+  if (algo == "mf") model.reset(new ModelMF(params, params.seed));
+  else if (algo == "IFWMF") model.reset(new ModelInvPopMF(params, params.seed, userFreq, itemFreq));
+  else if (algo == "TMF") model.reset(new ModelDropoutSigmoid(params, params.seed, noRank, noRank, userFreq, itemFreq));
+  else if (algo == "TMFDropout") model.reset(new ModelPoissonDropout(params, params.seed, noRank, noRank, userFreq, itemFreq));
+  else return 2;
+  memcpy(model->uFac.data(), U, sizeof(float) * (size_t)data.nUsers * p->facdim);
+  memcpy(model->iFac.data(), V, sizeof(float) * (size_t)data.nItems * p->facdim);
+  std::unordered_set<int> invalidUsers, invalidItems, fu, fi;
+  for (int u = 0; u < data.nUsers; u++) {
+    if (invalid_users && invalid_users[u]) invalidUsers.insert(u);
+    if (filt_users && filt_users[u]) fu.insert(u);
+  }
+  for (int i = 0; i < data.nItems; i++) {
+    if (invalid_items && invalid_items[i]) invalidItems.insert(i);
+    if (filt_items && filt_items[i]) fi.insert(i);
+  }
+  gk_csr_t *mat = which == 1 ? data.valMat : data.testMat;
+  for (int k = 0; k < 15; k++) out[k] = 0;
+  out[0] = model->hitRate(data, invalidUsers, invalidItems, mat);
+  out[1] = model->arHR(data, invalidUsers, invalidItems, mat);
+  out[2] = model->NDCG(invalidUsers, invalidItems, mat);
+  if (filt_users) {
+    auto a = model->hitRateU(data, fu, invalidUsers, invalidItems, mat);
+    auto b = model->arHRU(data, fu, invalidUsers, invalidItems, mat);
+    auto c = model->NDCGU(fu, invalidUsers, invalidItems, mat);
+    out[3] = a.first; out[4] = a.second; out[5] = b.first; out[6] = b.second; out[7] = c.first; out[8] = c.second;
+  }
+  if (filt_items) {
+    auto a = model->hitRateI(data, fi, invalidUsers, invalidItems, mat);
+    auto b = model->arHRI(data, fi, invalidUsers, invalidItems, mat);
+    auto c = model->NDCGI(fi, invalidUsers, invalidItems, mat);
+    out[9] = a.first; out[10] = a.second; out[11] = b.first; out[12] = b.second; out[13] = c.first; out[14] = c.second;
+  }
+  return 0;
+}
+
 extern "C" void mfh_release_device(void) { matfac::DeviceSession::dropAll(); }

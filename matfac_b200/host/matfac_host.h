@@ -42,6 +42,12 @@ int mfh_train(const mfh_problem *p, mfh_result *out);
 int mfh_sgd_plan(int32_t n_users, int32_t n_items, const uint8_t *invalid_users, const uint8_t *invalid_items,
                  int32_t seed, int32_t P, int32_t n_subepochs, int32_t *user_part_out, int32_t *item_part_out,
                  int32_t *schedule_out);
+/* Ranking metrics (model.cpp:760-1332) of the factor pair (U, V: [n][facdim]) through the host classes, against matrix
+ * `which` (1 = val, 2 = test) of the problem; invalid_* / filt_*: one byte per id (may be NULL).  out[0..2] = hitRate,
+ * arHR, NDCG; out[3..8] = hitRateU, arHRU, NDCGU as {first, second}; out[9..14] = hitRateI, arHRI, NDCGI. */
+int mfh_rank_metrics(const mfh_problem *p, const float *U, const float *V, const uint8_t *invalid_users,
+                     const uint8_t *invalid_items, int which, const uint8_t *filt_users, const uint8_t *filt_items,
+                     double out[15]);
 void mfh_release_device(void);
 
 #ifdef __cplusplus

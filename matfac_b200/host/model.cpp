@@ -249,6 +249,123 @@ void Model::groupSE(gk_csr_t *mat, const std::vector<uint8_t> &userGroup, const 
   s->check(mfb_eval_groups(s->eng, which, MFB_CURRENT, deviceVariant(), ug.data(), ig.data(), out));
 }
 
+// ---- ranking metrics (model.cpp:760-1332) ------------------------------------------------------------------------
+void Model::rankPositions(const Data &data, gk_csr_t *testMat, std::unordered_set<int> &invalidUsers,
+                          std::unordered_set<int> &invalidItems, std::vector<int32_t> &pos, std::vector<int32_t> &testItem) {
+  DeviceSession &s = DeviceSession::forData(data, facDim);
+  const int which = s.slotOf(testMat);
+  if (which != MFB_VAL && which != MFB_TEST) matfac::fatal("ranking metrics: testMat must be the validation or the test matrix of data");
+  s.setMasks(invalidUsers, invalidItems);
+  uploadFactors(s);
+  uploadAuxAll(s, &data, invalidUsers, invalidItems);
+  pos.assign(nUsers, -1);
+  testItem.assign(nUsers, -1);
+  s.check(mfb_rank_positions(s.eng, which, MFB_CURRENT, deviceVariant(), pos.data(), testItem.data()));
+}
+
+// hitRate / arHR and their U / I variants differ in who counts (model.cpp:1000, :1050-1057, :1113) and in what a hit is
+// worth (:1024 vs :1196); the position of the test item in the sorted list of the N best candidates is the device's count
+std::pair<double, double> Model::hitStats(const Data &data, gk_csr_t *testMat, std::unordered_set<int> &invalidUsers,
+                                          std::unordered_set<int> &invalidItems, const std::unordered_set<int> *filtUsers,
+                                          const std::unordered_set<int> *filtItems, int N, bool reciprocal) {
+  std::vector<int32_t> pos, tst;
+  rankPositions(data, testMat, invalidUsers, invalidItems, pos, tst);
+  double hits = 0, counted = 0;
+  for (int u = 0; u < data.trainMat->nrows && u < nUsers; u++) {
+    if (pos[u] == -1) continue;  // invalid user (or no rating to test against)
+    if (filtUsers && filtUsers->count(u) == 0) continue;
+    if (filtItems && filtItems->count(tst[u]) == 0) continue;
+    if (pos[u] >= 0 && pos[u] < N) hits += reciprocal ? 1.0 / (pos[u] + 1) : 1.0;
+    counted += 1;
+  }
+  return std::make_pair(hits, counted);
+}
+
+double Model::hitRate(const Data &data, std::unordered_set<int> &invalidUsers, std::unordered_set<int> &invalidItems, gk_csr_t *testMat) {
+  auto hc = hitStats(data, testMat, invalidUsers, invalidItems, nullptr, nullptr, 10, false);
+  return hc.first / hc.second;
+}
+std::pair<int, double> Model::hitRateU(const Data &data, std::unordered_set<int> &filtUsers, std::unordered_set<int> &invalidUsers,
+                                       std::unordered_set<int> &invalidItems, gk_csr_t *testMat) {
+  auto hc = hitStats(data, testMat, invalidUsers, invalidItems, &filtUsers, nullptr, 10, false);
+  return std::make_pair((int)hc.first, hc.first / hc.second);
+}
+std::pair<int, double> Model::hitRateI(const Data &data, std::unordered_set<int> &filtItems, std::unordered_set<int> &invalidUsers,
+                                       std::unordered_set<int> &invalidItems, gk_csr_t *testMat) {
+  auto hc = hitStats(data, testMat, invalidUsers, invalidItems, nullptr, &filtItems, 10, false);
+  return std::make_pair((int)hc.first, hc.first / hc.second);
+}
+double Model::arHR(const Data &data, std::unordered_set<int> &invalidUsers, std::unordered_set<int> &invalidItems, gk_csr_t *testMat) {
+  auto hc = hitStats(data, testMat, invalidUsers, invalidItems, nullptr, nullptr, 1000, true);
+  return hc.first / hc.second;
+}
+std::pair<double, double> Model::arHRU(const Data &data, std::unordered_set<int> &filtUsers, std::unordered_set<int> &invalidUsers,
+                                       std::unordered_set<int> &invalidItems, gk_csr_t *testMat) {
+  auto hc = hitStats(data, testMat, invalidUsers, invalidItems, &filtUsers, nullptr, 1000, true);
+  return std::make_pair(hc.first, hc.first / hc.second);
+}
+std::pair<double, double> Model::arHRI(const Data &data, std::unordered_set<int> &filtItems, std::unordered_set<int> &invalidUsers,
+                                       std::unordered_set<int> &invalidItems, gk_csr_t *testMat) {
+  auto hc = hitStats(data, testMat, invalidUsers, invalidItems, nullptr, &filtItems, 1000, true);
+  return std::make_pair(hc.first, hc.first / hc.second);
+}
+
+// NDCG / NDCGU / NDCGI (model.cpp:760-978): per user the N = 10 best predicted of its test ratings (heap ordered by the
+// prediction), DCG in that order over the ideal DCG of those same ratings; users with fewer than two ratings left or a
+// zero ideal DCG do not count.  The predictions are the device's (mfb_predict); the per-user heaps are a few entries.
+std::pair<int, double> Model::ndcgStats(gk_csr_t *testMat, std::unordered_set<int> &invalidUsers, std::unordered_set<int> &invalidItems,
+                                        const std::unordered_set<int> *filtUsers, const std::unordered_set<int> *filtItems) {
+  int which = 0;
+  DeviceSession &s = DeviceSession::forMatrix(testMat, nUsers, nItems, facDim, &which);
+  s.setMasks(invalidUsers, invalidItems);
+  uploadFactors(s);
+  uploadAuxAll(s, nullptr, invalidUsers, invalidItems);
+  const int64_t nnz = testMat->rowptr[testMat->nrows];
+  std::vector<float> pred((size_t)std::max<int64_t>(nnz, 1));
+  s.check(mfb_predict(s.eng, which, MFB_CURRENT, deviceVariant(), pred.data()));
+  const int N = 10;
+  typedef std::tuple<int, float, float> Triplet;  // item, actual, predicted
+  auto byPred = [](const Triplet &a, const Triplet &b) { return std::get<2>(a) > std::get<2>(b); };
+  auto byAct = [](const Triplet &a, const Triplet &b) { return std::get<1>(a) > std::get<1>(b); };
+  int nValUsers = 0;
+  double ndcg = 0;
+  for (int u = 0; u < testMat->nrows; u++) {
+    if (invalidUsers.count(u) > 0 || (filtUsers && filtUsers->count(u) == 0)) continue;
+    std::vector<Triplet> rs;
+    for (int64_t ii = testMat->rowptr[u]; ii < testMat->rowptr[u + 1]; ii++) {
+      const int item = testMat->rowind[ii];
+      if (invalidItems.count(item) > 0 || (filtItems && filtItems->count(item) == 0)) continue;
+      rs.push_back(Triplet(item, testMat->rowval[ii], pred[ii]));
+      std::push_heap(rs.begin(), rs.end(), byPred);
+      if ((int)rs.size() > N) {
+        std::pop_heap(rs.begin(), rs.end(), byPred);
+        rs.pop_back();
+      }
+    }
+    if (rs.size() < 2) continue;
+    std::sort(rs.begin(), rs.end(), byPred);
+    float u_ndcg = 0.0, u_dcg_max = 0.0;
+    for (int i = 0; i < N && i < (int)rs.size(); i++) u_ndcg += (std::pow(2.0, std::get<1>(rs[i])) - 1) / std::log2((i + 1) + 1);
+    std::sort(rs.begin(), rs.end(), byAct);
+    for (int i = 0; i < N && i < (int)rs.size(); i++) u_dcg_max += (std::pow(2.0, std::get<1>(rs[i])) - 1) / std::log2((i + 1) + 1);
+    if (!(u_dcg_max > EPS)) continue;
+    ndcg += u_ndcg / u_dcg_max;
+    nValUsers++;
+  }
+  return std::make_pair(nValUsers, ndcg / nValUsers);
+}
+double Model::NDCG(std::unordered_set<int> &invalidUsers, std::unordered_set<int> &invalidItems, gk_csr_t *testMat) {
+  return ndcgStats(testMat, invalidUsers, invalidItems, nullptr, nullptr).second;
+}
+std::pair<int, double> Model::NDCGU(std::unordered_set<int> &filtUsers, std::unordered_set<int> &invalidUsers,
+                                    std::unordered_set<int> &invalidItems, gk_csr_t *testMat) {
+  return ndcgStats(testMat, invalidUsers, invalidItems, &filtUsers, nullptr);
+}
+std::pair<int, double> Model::NDCGI(std::unordered_set<int> &filtItems, std::unordered_set<int> &invalidUsers,
+                                    std::unordered_set<int> &invalidItems, gk_csr_t *testMat) {
+  return ndcgStats(testMat, invalidUsers, invalidItems, nullptr, &filtItems);
+}
+
 static std::vector<uint8_t> groupOf(const std::unordered_set<int> &ids, int n) {
   std::vector<uint8_t> g(n, 255);
   for (int id : ids)

@@ -104,6 +104,24 @@ class Model {
   // 0..7 or 255; out[((side * 8) + part) * 2 + {0, 1}] = squared error, count (side 0 = items, 1 = users)
   void groupSE(gk_csr_t *mat, const std::vector<uint8_t> &userGroup, const std::vector<uint8_t> &itemGroup,
                std::unordered_set<int> &invalidUsers, std::unordered_set<int> &invalidItems, double out[32]);
+  // ranking metrics (model.cpp:760-1332).  The candidate scan — every item scored for every user — runs on the device
+  // (mfb_rank_positions: dense U V^T on the tensor cores where the model allows), the heaps of the reference reduce to
+  // one position per user; NDCG ranks the device's predictions of the test ratings (mfb_predict).
+  double hitRate(const Data &data, std::unordered_set<int> &invalidUsers, std::unordered_set<int> &invalidItems, gk_csr_t *testMat);
+  std::pair<int, double> hitRateU(const Data &data, std::unordered_set<int> &filtUsers, std::unordered_set<int> &invalidUsers,
+                                  std::unordered_set<int> &invalidItems, gk_csr_t *testMat);
+  std::pair<int, double> hitRateI(const Data &data, std::unordered_set<int> &filtItems, std::unordered_set<int> &invalidUsers,
+                                  std::unordered_set<int> &invalidItems, gk_csr_t *testMat);
+  double arHR(const Data &data, std::unordered_set<int> &invalidUsers, std::unordered_set<int> &invalidItems, gk_csr_t *testMat);
+  std::pair<double, double> arHRU(const Data &data, std::unordered_set<int> &filtUsers, std::unordered_set<int> &invalidUsers,
+                                  std::unordered_set<int> &invalidItems, gk_csr_t *testMat);
+  std::pair<double, double> arHRI(const Data &data, std::unordered_set<int> &filtItems, std::unordered_set<int> &invalidUsers,
+                                  std::unordered_set<int> &invalidItems, gk_csr_t *testMat);
+  double NDCG(std::unordered_set<int> &invalidUsers, std::unordered_set<int> &invalidItems, gk_csr_t *testMat);
+  std::pair<int, double> NDCGU(std::unordered_set<int> &filtUsers, std::unordered_set<int> &invalidUsers,
+                               std::unordered_set<int> &invalidItems, gk_csr_t *testMat);
+  std::pair<int, double> NDCGI(std::unordered_set<int> &filtItems, std::unordered_set<int> &invalidUsers,
+                               std::unordered_set<int> &invalidItems, gk_csr_t *testMat);
   virtual double estRating(int user, int item);
   std::string modelSignature();
   void display();
@@ -130,6 +148,15 @@ class Model {
   void copyScalarsFrom(const Model &o);
   void uploadFactors(matfac::DeviceSession &s);
   double deviceEval(matfac::DeviceSession &s, int which, bool objective);
+  // per user: position of its test item among the candidates (mfb_rank_positions) and the test item
+  void rankPositions(const Data &data, gk_csr_t *testMat, std::unordered_set<int> &invalidUsers,
+                     std::unordered_set<int> &invalidItems, std::vector<int32_t> &pos, std::vector<int32_t> &testItem);
+  // {hits, counted users} of the hit-rate family: N = list length, reciprocal = arHR's 1 / (pos + 1) instead of 1
+  std::pair<double, double> hitStats(const Data &data, gk_csr_t *testMat, std::unordered_set<int> &invalidUsers,
+                                     std::unordered_set<int> &invalidItems, const std::unordered_set<int> *filtUsers,
+                                     const std::unordered_set<int> *filtItems, int N, bool reciprocal);
+  std::pair<int, double> ndcgStats(gk_csr_t *testMat, std::unordered_set<int> &invalidUsers, std::unordered_set<int> &invalidItems,
+                                   const std::unordered_set<int> *filtUsers, const std::unordered_set<int> *filtItems);
 
   // shared trainer skeletons
   struct Stop {

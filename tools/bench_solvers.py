@@ -26,7 +26,7 @@ import bench  # noqa: E402
 def main():
     real_stdout = bench._protect_stdout()  # only the JSON line goes to stdout (NCCL prints its banner on fd 1)
     ap = argparse.ArgumentParser()
-    ap.add_argument("--algo", default="als", choices=["als", "ccdpp", "eval"])
+    ap.add_argument("--algo", default="als", choices=["als", "ccdpp", "eval", "rank"])
     ap.add_argument("--rank", type=int, default=128)
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--epochs", type=int, default=3)
@@ -141,6 +141,23 @@ def main():
         out.update(ms_per_rank1=ms_k, epoch_ms=ms_k * r, algorithmic_gbs=128.0 * train_nnz / (ms_k * 1e-3) / 1e9,
                    frac_of_hbm=128.0 * train_nnz / (ms_k * 1e-3) / 1e9 / peak_gbs, dims_timed=dims)
         eng.ccdpp_end()
+    elif args.algo == "rank":
+        # hit-rate positions of every user against the validation matrix: dense U V^T (users x items x rank) with the
+        # count fused into the epilogue; wall time of the whole call (split, sparse pass, GEMM, download of the positions)
+        eng.upload_factors(rng.standard_normal((n_users, r)).astype(np.float32), rng.standard_normal((n_items, r)).astype(np.float32))
+        res = {}
+        for tc in ([1, 0] if args.scale <= 0.05 else [1]):
+            eng.set_option("rank_tensor_cores", tc)
+            eng.rank_positions(E.VAL)
+            t = []
+            for _ in range(3):
+                eng.sync(); t0 = time.perf_counter()
+                pos, tst = eng.rank_positions(E.VAL)
+                t.append(time.perf_counter() - t0)
+            sec = float(np.median(t))
+            res["tcgen05" if tc else "cuda_cores"] = {"seconds": sec, "dense_tflops": 2.0 * n_users * n_items * r / sec / 1e12,
+                                                     "users_counted": int((pos != -1).sum()), "hit_rate": float(((pos >= 0) & (pos < 10)).sum() / max((pos != -1).sum(), 1))}
+        out.update(rank_positions=res, flops_counted="2 x users x items x rank (one product per pair; the 3xTF32 split issues three)")
     else:
         for _ in range(2):
             eng.eval(E.TRAIN, E.CURRENT, E.MF, False, True)
