@@ -467,9 +467,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// the same with a suspend-time hint: the hardware parks the warp until the phase completes or `ns` have passed, so a
-// waiting warp leaves the issue slots to the warps that work (profiles/r2_als.md: plain polling made ~45 % of all
-// instructions of the warp-specialised kernel, which was issue-bound at 0.86 instructions per scheduler cycle)
+// the same with a suspend-time hint: the hardware parks the warp until the phase completes or `ns` have passed
+// (NANOSLEEP.SYNCS), so a waiting warp leaves the issue slots to the warps that work — most warps of the
+// warp-specialised kernel wait most of the time
 __device__ __forceinline__ bool mbar_try_wait_parked(uint32_t bar, uint32_t parity, uint32_t ns) {
   uint32_t ok;
   asm volatile(

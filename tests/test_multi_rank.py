@@ -204,7 +204,10 @@ def test_dsgd_ranks_rmse_matches_oracle_on_bench_shape(world):
     # the oracle's own two seeds are up to 15 % apart at equal epochs, at P = 8 about 1 %: profiles/r2_dsgd_parity.md), so
     # the band is the oracle's two curves widened by their own distance at that epoch, plus the 0.5 % bar; the device must
     # never be worse than that, and at the last epoch not worse than the oracle's worse seed + 0.5 %.
+    # Below the band the bar is 5 %: with the ratings of a block in shuffled order (block_order = 1, the only order that
+    # converges on this matrix at every N: profiles/r2_dsgd_parity.md) the device falls FASTER than the reference's
+    # user-major sweep through the steep part of the curve (2 - 4 % lower at P = 4) and meets it again when both flatten.
     for ep in range(knee, epochs):
         spread = hi[ep] - lo[ep]
-        assert (lo[ep] - spread) * 0.995 <= got[ep] <= (hi[ep] + spread) * 1.005, (ep,) + msg
+        assert (lo[ep] - spread) * 0.95 <= got[ep] <= (hi[ep] + spread) * 1.005, (ep,) + msg
     assert got[-1] <= hi[-1] * 1.005 + (hi[-1] - lo[-1]), msg
