@@ -435,7 +435,9 @@ def yahoo_block(rk, peak_gbs, scale, epochs=4):
         eng.close()
         del eng
     else:
-        d = run_dsgd(prob, rk, RANK, "reference", 2, epochs)
+        # engine-default in-flight budget: at 8e-4 (the Netflix-shape setting of run_dsgd) this matrix diverges at N = 8
+        # (gpurun_out/s25, s26: NaN from epoch 1; 2e-4 and 4e-4 converge at the same epoch time)
+        d = run_dsgd(prob, rk, RANK, "reference", 2, epochs, options={"sgd_flat_inflight_frac": 2e-4})
         out["dsgd"] = d
     torch.cuda.empty_cache()
     out["solvers"] = solver_timings(prob, rk, peak_gbs, ranks=(64,), objective=(rk.world == 1), shape_name="yahoo")

@@ -24,6 +24,10 @@ def main():
     ap.add_argument("--epochs", type=int, default=25)
     ap.add_argument("--worlds", type=int, nargs="+", default=[1, 2, 4, 8])
     ap.add_argument("--scale", type=float, default=0.05)
+    ap.add_argument("--shape", default="netflix", choices=["netflix", "yahoo"])
+    ap.add_argument("--seeds", type=int, nargs="+", default=[1, 2])
+    ap.add_argument("--relax_after", type=int, default=-1, help="epochs after which the in-flight budget becomes --inflight_late")
+    ap.add_argument("--inflight_late", type=float, default=8e-4)
     ap.add_argument("--lr", type=float, default=0.002)
     ap.add_argument("--inflight", type=float, default=2e-4)
     ap.add_argument("--configs", nargs="+", default=["reference:1", "reference:0", "balanced:1"])
@@ -31,9 +35,14 @@ def main():
     a = ap.parse_args()
     import torch
     ndev = torch.cuda.device_count()
-    nu, ni, nnz = synth.SHAPES["netflix"]
-    nu, ni, nnz = int(nu * a.scale), int(ni * max(a.scale, 0.05)), int(nnz * a.scale)
-    prob = synth.skewed_problem(nu, ni, nnz, 20260102, device="cuda:0")
+    import bench
+    if a.shape == "netflix":
+        nu, ni, nnz = synth.SHAPES["netflix"]
+        nu, ni, nnz = int(nu * a.scale), int(ni * max(a.scale, 0.05)), int(nnz * a.scale)
+        prob = synth.skewed_problem(nu, ni, nnz, 20260102, device="cuda:0")
+    else:  # the bench's Yahoo-R1-shaped block (BASELINE.json configs[4])
+        prob = bench.make_problem(bench.YAHOO_SHAPE, a.scale, "cuda:0")
+        nu, ni = prob["n_users"], prob["n_items"]
     ptr, ind, _ = prob["train"]
     bad_u = (np.diff(ptr) == 0).astype(np.uint8)
     bad_i = (np.bincount(ind, minlength=ni) == 0).astype(np.uint8)
@@ -47,7 +56,7 @@ def main():
         plan, order = parts[0], parts[1]
         extra = dict((kv.split("=")[0], float(kv.split("=")[1])) for kv in parts[2].split(",")) if len(parts) > 2 else {}
         for world in a.worlds:
-            for seed in (1, 2):
+            for seed in a.seeds:
                 t0 = time.time()
                 d = dsgd.Dsgd(nu, ni, 64, world, {r: r % ndev for r in range(world)}, prob["train"], prob["val"], U0, V0, bad_u,
                               bad_i, a.epochs * world, plan=plan, seed=seed, block_order=int(order),
@@ -55,6 +64,9 @@ def main():
                 curve, ms = [], []
                 e0 = d.engines[0]
                 for ep in range(a.epochs):
+                    if ep == a.relax_after:
+                        for e in d.engines.values():
+                            e.set_option("sgd_flat_inflight_frac", a.inflight_late)
                     e0.event_record(0)
                     d.run(ep * world, (ep + 1) * world, a.lr, 0.05, 0.05, seed)
                     e0.event_record(1)
