@@ -200,6 +200,18 @@ int mfb_ccdpp_rank1(mfb_engine *e, int32_t k, int first_iter, int32_t inner, flo
                     int32_t item_freq_thresh);
 int mfb_ccdpp_end(mfb_engine *e);
 
+/* ---- CCD (modelMF.cpp:1426-1653 trainCCD, --mf_method ccd) ---------------------------------
+ * Between mfb_ccdpp_begin and mfb_ccdpp_end (same residual state: ratings in both views, U = 0).
+ * One half of an epoch: side = MFB_USER: every valid user visits its dims in the order
+ * dim_order[u][0..rank) and sets u_k = sum((res + u_k v_k) v_k) / (reg + sum v_k^2) over its row,
+ * then subtracts (new - old) v_k from the row's residuals (:1527-1566); MFB_ITEM: the same over
+ * the columns (:1569-1606).  dim_order = host [n_users | n_items][rank] bytes (the reference draws
+ * one std::shuffle per valid row from a single mt19937(trainSeed), :1537,1577; entries of invalid
+ * rows are ignored), NULL = 0 .. rank-1 for every row.  The train matrix needs both views with
+ * sorted indices (the residual of the other view is patched through the reference's binary
+ * search, util.cpp:847).  One engine only (rows of the two sides exchange residuals). */
+int mfb_ccd_half_step(mfb_engine *e, int side, float reg, const uint8_t *dim_order);
+
 /* ---- evaluation (model.cpp:214-251 RMSE, :1770-1815 objective, modelInvPopMF.cpp:3-55) ----
  * One fused pass over `which`: out[0] = sum of (weighted) squared errors over ratings whose
  * user and item are valid, out[1] = their count, out[2] = sum_u |U_u|^2 and out[3] =

@@ -875,6 +875,14 @@ extern "C" int mfb_ccdpp_rank1(mfb_engine *e, int32_t k, int first_iter, int32_t
   MFB_CUDA(mfb::enter(e));
   return ccdpp_rank1_impl(e, k, first_iter, inner, ureg, ireg, item_freq_thresh);
 }
+extern "C" int mfb_ccd_half_step(mfb_engine *e, int side, float reg, const uint8_t *dim_order) {
+  MFB_REQUIRE(e && e->res_row && e->res_col, "mfb_ccd_half_step: call mfb_ccdpp_begin first");
+  MFB_REQUIRE(side == MFB_USER || side == MFB_ITEM, "mfb_ccd_half_step: bad side");
+  MFB_REQUIRE(e->mat[MFB_TRAIN].rowptr && e->mat[MFB_TRAIN].colptr, "mfb_ccd_half_step: train matrix needs both views");
+  MFB_REQUIRE(!e->comm.connected, "mfb_ccd_half_step: one engine only (the two sides exchange residuals)");
+  MFB_CUDA(mfb::enter(e));
+  return ccd_half_step_impl(e, side, reg, dim_order);
+}
 extern "C" int mfb_ccdpp_end(mfb_engine *e) {
   MFB_REQUIRE(e, "null engine");
   MFB_CUDA(mfb::enter(e));

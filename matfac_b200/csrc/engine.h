@@ -273,6 +273,7 @@ int ccdpp_begin_impl(mfb_engine *e);
 int ccdpp_rank1_impl(mfb_engine *e, int32_t k, int first_iter, int32_t inner, float ureg, float ireg,
                      int32_t item_freq_thresh);
 int ccdpp_end_impl(mfb_engine *e);
+int ccd_half_step_impl(mfb_engine *e, int side, float reg, const uint8_t *dims_host);
 inline size_t uk_alloc_bytes(const mfb_engine *e) { return sizeof(float) * (e->uk_old_offset() + (size_t)e->n_users + 4); }
 int comm_barrier_launch(mfb_engine *e);
 // non-zero (mfb_last_error set) when a device-side flag wait of this engine has timed out; syncs the stream

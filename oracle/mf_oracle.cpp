@@ -930,6 +930,113 @@ static int trainCcdpp(mfo_model *m, const mfo_data *d, bool freqAdap) {
   return iter;
 }
 
+// util.cpp:847-864 binSearch: position of key in sortedArr[lb..ub], -1 when absent
+static int64_t binSearch(const std::vector<int32_t> &sortedArr, int key, int64_t ub, int64_t lb) {
+  int64_t ind = -1;
+  while (ub >= lb) {
+    int64_t midP = (ub + lb) / 2;
+    if (sortedArr[midP] == key) { ind = midP; break; }
+    else if (sortedArr[midP] < key) lb = midP + 1;
+    else ub = midP - 1;
+  }
+  return ind;
+}
+
+// ModelMF::trainCCD modelMF.cpp:1426-1653 (--mf_method ccd): cyclic coordinate descent one ROW at a time.  residual =
+// gk_csr_Dup(trainMat) with both views kept (:1511); U = 0 (:1518-1523).  Per epoch every valid user visits its dims in
+// a fresh std::shuffle of 0..r-1 drawn from the ONE mt19937(trainSeed) (:1495,1537-1538), num / denom / newV / upd in
+// double over float products (:1541-1565), each residual entry patched in the other view through binSearch; then the
+// items the same way over the CSC view (:1569-1606).  The reference draws the shuffles inside an OpenMP loop from the
+// shared engine — defined only for one thread, which is what this restates (rows in index order).
+static int trainCcd(mfo_model *m, const mfo_data *d) {
+  const Csr &tr = d->mat[0];
+  const int r = m->facDim;
+  const int nUsers = m->nUsers, nItems = m->nItems;
+  StopState s;
+  preamble(m, d, s, nullptr, nullptr);
+  std::mt19937 mt(m->seed);
+  std::vector<int> dims(r);
+  std::iota(dims.begin(), dims.end(), 0);
+  std::vector<float> resRow(tr.rowval), resCol(tr.colval);
+  std::fill(m->cur.U.begin(), m->cur.U.end(), 0.0f);
+  int iter;
+  for (iter = 0; iter < m->maxIter; iter++) {
+    EpochTimer tm(m);
+    for (int u = 0; u < nUsers; u++) {
+      if (m->invalidUsers.count(u) > 0) continue;
+      std::vector<int> udims(dims);
+      std::shuffle(udims.begin(), udims.end(), mt);
+      for (const auto &k : udims) {
+        double num = 0, denom = m->uReg, newV;
+        for (int64_t ii = tr.rowptr[u]; ii < tr.rowptr[u + 1]; ii++) {
+          int item = tr.rowind[ii];
+          num += (resRow[ii] + m->u(u, k) * m->v(item, k)) * m->v(item, k);
+          denom += m->v(item, k) * m->v(item, k);
+        }
+        newV = num / denom;
+        for (int64_t ii = tr.rowptr[u]; ii < tr.rowptr[u + 1]; ii++) {
+          int item = tr.rowind[ii];
+          double upd = (newV - m->u(u, k)) * m->v(item, k);
+          resRow[ii] -= upd;
+          int64_t pos = binSearch(tr.colind, u, tr.colptr[item + 1] - 1, tr.colptr[item]);
+          if (pos != -1) resCol[pos] -= upd;
+        }
+        m->u(u, k) = newV;
+      }
+    }
+    for (int item = 0; item < nItems; item++) {
+      if (m->invalidItems.count(item) > 0 || item >= tr.ncols) continue;
+      std::vector<int> udims(dims);
+      std::shuffle(udims.begin(), udims.end(), mt);
+      for (const auto &k : udims) {
+        double num = 0, denom = m->iReg, newV;
+        for (int64_t uu = tr.colptr[item]; uu < tr.colptr[item + 1]; uu++) {
+          int u = tr.colind[uu];
+          num += (resCol[uu] + m->u(u, k) * m->v(item, k)) * m->u(u, k);
+          denom += m->u(u, k) * m->u(u, k);
+        }
+        newV = num / denom;
+        for (int64_t uu = tr.colptr[item]; uu < tr.colptr[item + 1]; uu++) {
+          int u = tr.colind[uu];
+          double upd = (newV - m->v(item, k)) * m->u(u, k);
+          resCol[uu] -= upd;
+          int64_t pos = binSearch(tr.rowind, item, tr.rowptr[u + 1] - 1, tr.rowptr[u]);
+          if (pos != -1) resRow[pos] -= upd;
+        }
+        m->v(item, k) = newV;
+      }
+    }
+    tm.stop();
+    if (iter % kObjIter == 0 || iter == m->maxIter - 1)
+      if (isTerminateModel(m, d, iter, s)) { iter++; break; }
+  }
+  return iter;
+}
+
+// the dims order every valid row of trainCCD draws (one shared mt19937(seed); per epoch the valid users in index order, then
+// the valid items): out = [n_epochs][n_valid_users + n_valid_items][r]
+extern "C" void mfo_ccd_dim_orders(const mfo_model *m, const mfo_data *d, int n_epochs, uint8_t *out) {
+  const int r = m->facDim;
+  std::mt19937 mt(m->seed);
+  std::vector<int> dims(r);
+  std::iota(dims.begin(), dims.end(), 0);
+  size_t o = 0;
+  for (int e = 0; e < n_epochs; e++) {
+    for (int u = 0; u < m->nUsers; u++) {
+      if (m->invalidUsers.count(u) > 0) continue;
+      std::vector<int> udims(dims);
+      std::shuffle(udims.begin(), udims.end(), mt);
+      for (int k = 0; k < r; k++) out[o++] = (uint8_t)udims[k];
+    }
+    for (int item = 0; item < m->nItems; item++) {
+      if (m->invalidItems.count(item) > 0 || item >= d->mat[0].ncols) continue;
+      std::vector<int> udims(dims);
+      std::shuffle(udims.begin(), udims.end(), mt);
+      for (int k = 0; k < r; k++) out[o++] = (uint8_t)udims[k];
+    }
+  }
+}
+
 extern "C" int mfo_train(mfo_model *m, const mfo_data *d, int method, int keep_history) {
   m->keepHistory = keep_history;
   m->hist.clear();
@@ -946,6 +1053,7 @@ extern "C" int mfo_train(mfo_model *m, const mfo_data *d, int method, int keep_h
     case MFO_CCDPP_FREQ: iters = trainCcdpp(m, d, true); break;
     case MFO_HOGWILD: iters = trainHogwildSerial(m, d); break;
     case MFO_SGDU: iters = trainUserShuffle(m, d); break;
+    case MFO_CCD: iters = trainCcd(m, d); break;
     default: iters = -1;
   }
   omp_set_num_threads(saved);

@@ -29,7 +29,8 @@ enum mfo_method {
   MFO_CCDPP = 3,        /* ModelMF::trainCCDPP                                           */
   MFO_CCDPP_FREQ = 4,   /* ModelMF::trainCCDPPFreqAdap (what --mf_method ccd++ runs)     */
   MFO_HOGWILD = 5,      /* ModelMF::hogTrain executed by one thread                      */
-  MFO_SGDU = 6          /* ModelMF::trainUShuffle (--mf_method sgdu, modelMF.cpp:560-706) */
+  MFO_SGDU = 6,         /* ModelMF::trainUShuffle (--mf_method sgdu, modelMF.cpp:560-706) */
+  MFO_CCD = 7           /* ModelMF::trainCCD (--mf_method ccd, modelMF.cpp:1426-1653) by one thread */
 };
 
 /* --- data (datastruct.cpp:3-120) ------------------------------------------------------ */
@@ -96,6 +97,8 @@ void mfo_tmf_ranks(const mfo_model *m, int32_t *user_rank, int32_t *item_rank, i
 void mfo_ifw_weights(const mfo_model *m, const mfo_data *d, double *inv_pop_u, double *inv_pop_i);
 /* dims order of trainCCDPP for n_epochs epochs: out[n_epochs][r] */
 void mfo_ccdpp_dim_order(int seed, int r, int n_epochs, int32_t *out);
+/* trainCCD: the shuffled dims of every valid row, [n_epochs][valid users then valid items][r] (modelMF.cpp:1537,1577) */
+void mfo_ccd_dim_orders(const mfo_model *m, const mfo_data *d, int n_epochs, uint8_t *out);
 /* batched fp32 solve used by ALS (pivoted LDL^T), for unit checks: A is [n][r][r] row-major */
 void mfo_ldlt_solve(int n, int r, const float *A, const float *b, float *x);
 

@@ -19,7 +19,7 @@ ORACLE_SO = os.path.join(ORACLE_DIR, "libmf_oracle.so")
 REF_BIN = os.path.join(ORACLE_DIR, "_ref", "mf_ref")
 
 ALGO = {"mf": 0, "IFWMF": 1, "TMF": 2, "TMFDropout": 3}
-METHOD = {"sgd": 0, "sgdpar": 1, "als": 2, "ccdpp_plain": 3, "ccd++": 4, "hogsgd": 5, "sgdu": 6}
+METHOD = {"sgd": 0, "sgdpar": 1, "als": 2, "ccdpp_plain": 3, "ccd++": 4, "hogsgd": 5, "sgdu": 6, "ccd": 7}
 
 
 class Params(C.Structure):
@@ -75,6 +75,7 @@ def lib():
         L.mfo_tmf_ranks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.mfo_ifw_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mfo_ccdpp_dim_order.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.mfo_ccd_dim_orders.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.mfo_ldlt_solve.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     return _lib
 
@@ -208,6 +209,21 @@ class OracleModel:
         pu = np.zeros(self.data.n_users, np.float64); pi = np.zeros(self.data.n_items, np.float64)
         lib().mfo_ifw_weights(self.h, self.data.h, _p(pu), _p(pi))
         return pu, pi
+
+    def ccd_dim_orders(self, n_epochs):
+        """trainCCD's per-row dims orders: list over epochs of (user orders [n_users][r], item orders [n_items][r]) uint8,
+        rows of invalid ids left as the identity (they are never visited)."""
+        bu, bi = self.invalid()
+        vu, vi = np.nonzero(bu == 0)[0], np.nonzero(bi == 0)[0]
+        r = self.r
+        flat = np.zeros((n_epochs, len(vu) + len(vi), r), np.uint8)
+        lib().mfo_ccd_dim_orders(self.h, self.data.h, n_epochs, _p(flat))
+        out = []
+        for e in range(n_epochs):
+            du = np.tile(np.arange(r, dtype=np.uint8), (self.data.n_users, 1)); di = np.tile(np.arange(r, dtype=np.uint8), (self.data.n_items, 1))
+            du[vu] = flat[e, :len(vu)]; di[vi] = flat[e, len(vu):]
+            out.append((du, di))
+        return out
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -21,6 +21,7 @@ CASES = [
     ("mf", "als", 2, {"ureg": 0.1, "ireg": 0.1}),
     ("mf", "ccdpp_plain", 2, {}),
     ("mf", "ccd++", 2, {}),
+    ("mf", "ccd", 1, {}),
     ("IFWMF", "sgd", 1, {"rhorms": 1000.0}),
     ("IFWMF", "sgdpar", 3, {"rhorms": 1000.0}),
     ("TMF", "sgd", 4, {"rhorms": 20.0, "alpha": 0.5}),
