@@ -55,6 +55,7 @@ extern "C" int mfh_train(const mfh_problem *p, mfh_result *out) {
   std::unordered_set<int> invalidUsers, invalidItems;
   if (algo == "mf" && method == "ccd++") model->trainCCDPPFreqAdap(data, *best, invalidUsers, invalidItems);
   else if (algo == "mf" && method == "ccdpp_plain") model->trainCCDPP(data, *best, invalidUsers, invalidItems);
+  else if (algo == "mf" && method == "ccd") model->trainCCD(data, *best, invalidUsers, invalidItems);
   else if (algo == "mf" && method == "als") model->trainALS(data, *best, invalidUsers, invalidItems);
   else if (algo == "mf" && method == "hogsgd") model->hogTrain(data, *best, invalidUsers, invalidItems);
   else if (algo == "mf" && method == "sgdu") model->trainUShuffle(data, *best, invalidUsers, invalidItems);

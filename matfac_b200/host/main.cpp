@@ -282,7 +282,8 @@ int main(int argc, char **argv) {
     else if (mf_method == "hogsgd") mfModel->hogTrain(data, *bestModel, invalidUsers, invalidItems);
     else if (mf_method == "sgdpar") mfModel->trainSGDPar(data, *bestModel, invalidUsers, invalidItems);
     else if (mf_method == "sgdu") mfModel->trainUShuffle(data, *bestModel, invalidUsers, invalidItems);
-    else if (mf_method == "ccd" || mf_method == "sgdparsvd") {
+    else if (mf_method == "ccd") mfModel->trainCCD(data, *bestModel, invalidUsers, invalidItems);
+    else if (mf_method == "sgdparsvd") {
       std::cerr << "--mf_method " << mf_method << " is not provided by the GPU engine" << std::endl;
       return -1;
     } else mfModel->train(data, *bestModel, invalidUsers, invalidItems);

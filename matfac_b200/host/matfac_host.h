@@ -20,7 +20,7 @@ typedef struct mfh_csr {
 typedef struct mfh_problem {
   mfh_csr train, val, test;
   const char *algo;      /* mf | IFWMF | TMF | TMFDropout           (main.cpp:45) */
-  const char *mf_method; /* sgd | sgdpar | hogsgd | als | ccd++ | ccdpp_plain (main.cpp:44) */
+  const char *mf_method; /* sgd | sgdpar | hogsgd | als | ccd++ | ccdpp_plain | ccd | sgdu (main.cpp:44) */
   int32_t facdim, maxiter, seed;
   int32_t num_parts;     /* P of the stratified trainers; 0 = omp_get_max_threads() like the reference */
   float ureg, ireg, learnrate, rhorms, alpha;

@@ -107,3 +107,51 @@ void ModelMF::trainCCDPPFreqAdap(const Data &data, Model &bestModel, std::unorde
                                  std::unordered_set<int> &invalidItems) {
   runCcdpp(data, bestModel, invalidUsers, invalidItems, true, "ModelMF::trainCCDPPFreqAdap");
 }
+
+// --mf_method ccd (modelMF.cpp:1426-1653): coordinate descent row by row over the residual matrix.  The visiting
+// order of every row's dims comes from the reference's single mt19937(trainSeed) — one std::shuffle per valid user in
+// index order, then one per valid item, every epoch (:1495,1537,1577; defined for one thread there) — drawn here and
+// handed to the device with the half-step.  One engine: the two sides exchange residuals.
+void ModelMF::trainCCD(const Data &data, Model &bestModel, std::unordered_set<int> &invalidUsers,
+                       std::unordered_set<int> &invalidItems) {
+  const char *tag = "ModelMF::trainCCD";
+  std::cout << "\n" << tag << " trainSeed: " << trainSeed;
+  if (facDim > 256) {
+    std::cerr << "\ntrainCCD: facDim > 256 not supported" << std::endl;
+    return;
+  }
+  Stop st;
+  beginTraining(data, bestModel, invalidUsers, invalidItems, st, tag, matfac::GROUP_NONE);
+  DeviceSession &s = *dev_;
+  std::mt19937 mt(trainSeed);
+  std::vector<int> dims(facDim);
+  std::iota(dims.begin(), dims.end(), 0);
+  std::vector<uint8_t> uOrder((size_t)nUsers * facDim), iOrder((size_t)nItems * facDim);
+  const int nCols = data.trainMat->ncols;
+  s.check(mfb_ccdpp_begin(s.eng));  // residual = gk_csr_Dup(trainMat), U = 0 (:1511,1518)
+  for (int iter = 0; iter < maxIter; iter++) {
+    s.check(mfb_event_record(s.eng, 0));
+    for (int u = 0; u < nUsers; u++) {
+      if (invalidUsers.count(u) > 0) continue;
+      std::vector<int> udims(dims);
+      std::shuffle(udims.begin(), udims.end(), mt);
+      for (int k = 0; k < facDim; k++) uOrder[(size_t)u * facDim + k] = (uint8_t)udims[k];
+    }
+    s.check(mfb_ccd_half_step(s.eng, MFB_USER, uReg, uOrder.data()));
+    for (int item = 0; item < nItems; item++) {
+      if (invalidItems.count(item) > 0 || item >= nCols) continue;
+      std::vector<int> udims(dims);
+      std::shuffle(udims.begin(), udims.end(), mt);
+      for (int k = 0; k < facDim; k++) iOrder[(size_t)item * facDim + k] = (uint8_t)udims[k];
+    }
+    s.check(mfb_ccd_half_step(s.eng, MFB_ITEM, iReg, iOrder.data()));
+    s.check(mfb_event_record(s.eng, 1));
+    float ms = 0;
+    s.check(mfb_event_elapsed_ms(s.eng, 0, 1, &ms));
+    if (afterEpoch(data, bestModel, iter, st, invalidUsers, invalidItems, ms * 1e-3, tag, true)) break;
+  }
+  s.check(mfb_ccdpp_end(s.eng));
+  endTraining(bestModel);
+  bestModel.saveFacs(std::string(data.prefix));
+  std::cout << "\nBest model validation RMSE: " << bestModel.RMSE(data.valMat, invalidUsers, invalidItems) << std::endl;
+}

@@ -23,6 +23,7 @@ class ModelMF : public Model {
   MATFAC_DECL(trainALS)            // alternating LS        modelMF.cpp:709
   MATFAC_DECL(trainCCDPP)          // CCD++                 modelMF.cpp:931
   MATFAC_DECL(trainCCDPPFreqAdap)  // CCD++, freq-adaptive  modelMF.cpp:1172
+  MATFAC_DECL(trainCCD)            // CCD, row by row       modelMF.cpp:1426
 #undef MATFAC_DECL
 
  private:

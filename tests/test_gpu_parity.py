@@ -575,6 +575,31 @@ def test_ccdpp_matches_oracle(rank, freq_adap):
     eng.close()
 
 
+@pytest.mark.parametrize("shape", [(500, 300, 40000), (6000, 40, 120000)])
+@pytest.mark.parametrize("rank", [8, 64])
+def test_ccd_matches_oracle(rank, shape):
+    """trainCCD (modelMF.cpp:1426-1653) row by row with the reference's per-row dims orders: factors and objective after
+    every epoch within 1e-4.  The second shape has columns of ~3000 ratings (whole-CTA rows) and rows in every register class."""
+    splits = small_problem(*shape, seed=13)
+    epochs = 3
+    om = oracle_model(splits, "mf", rank, maxiter=epochs, nthreads=1)
+    eng, variant = make_engine(splits, om, rank)
+    orders = om.ccd_dim_orders(epochs)
+    om.train("ccd", keep_history=True)
+    hist = om.history()
+    eng.ccdpp_begin()
+    for ep in range(epochs):
+        eng.ccd_half_step(E.USER, HP["ureg"], orders[ep][0])
+        eng.ccd_half_step(E.ITEM, HP["ireg"], orders[ep][1])
+        U, V = eng.download_factors()
+        assert rel_err(U, hist[ep][0]) < 1e-4, (ep, rel_err(U, hist[ep][0]))
+        assert rel_err(V, hist[ep][1]) < 1e-4, (ep, rel_err(V, hist[ep][1]))
+        obj = eng.objective(HP["ureg"], HP["ireg"])
+        assert abs(obj - hist[ep][2]) < 1e-4 * hist[ep][2]
+    eng.ccdpp_end()
+    eng.close()
+
+
 def test_device_column_index_is_bit_exact():
     """mfb_build_csc == gk_csr_CreateIndex(mat, GK_CSR_COL): the oracle's CSC arrays, bit for bit, including
     empty rows / columns and a matrix narrower than the engine."""

@@ -220,7 +220,7 @@ def oracle_run(files, algo, method, threads, fl):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("method,extra", [("als", dict(ureg=0.1, ireg=0.1)), ("ccd++", {}), ("ccdpp_plain", {})])
+@pytest.mark.parametrize("method,extra", [("als", dict(ureg=0.1, ireg=0.1)), ("ccd++", {}), ("ccdpp_plain", {}), ("ccd", {})])
 def test_cli_als_and_ccdpp_match_oracle(tmp_path, method, extra):
     """Deterministic trainers through the whole stack: best and last factors within 1e-4."""
     files = synth.write_split_files(str(tmp_path), *synth.make_splits(500, 300, 40000, seed=13))
