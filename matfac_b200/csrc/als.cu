@@ -22,31 +22,6 @@ namespace mfb {
 
 constexpr int kAlsTile = 32;    // factor rows staged per pipeline stage
 
-struct AlsArgs {
-  const float *Fin;  // opposite side's factors [.][ld]
-  float *Fout;       // this side's factors
-  int ld, rank;
-  const int32_t *ind;
-  const float *val;
-  const int32_t *seg_row, *seg_start, *seg_len, *seg_slot;
-  const int32_t *multi_row;
-  float *ws;
-  float reg;
-  // row-sharded runs: the other ranks' copies of this side's factors (peer memory); every solved row
-  // is stored into all of them, i.e. the all-gather is fused into the solve epilogue
-  float *Fpeer[kMaxRanks - 1];
-  int n_peer;
-  int seg0, nseg;  // segments [seg0, seg0 + nseg) of the plan belong to this launch (sorted longest first)
-};
-
-__device__ __forceinline__ void store_solution(const AlsArgs &a, int row, int tid, const float *bv) {
-  if (tid < a.ld) {
-    const float x = tid < a.rank ? bv[tid] : 0.f;
-    a.Fout[(size_t)row * a.ld + tid] = x;
-    for (int p = 0; p < a.n_peer; p++) a.Fpeer[p][(size_t)row * a.ld + tid] = x;
-  }
-}
-
 template <int TR>
 __device__ __forceinline__ int tile_idx(int t, int i) {
   // element owned by thread coordinate t, local index i; for TR = 8 the tile is two strided

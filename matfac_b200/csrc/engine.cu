@@ -875,6 +875,11 @@ extern "C" int mfb_ccdpp_rank1(mfb_engine *e, int32_t k, int first_iter, int32_t
   MFB_CUDA(mfb::enter(e));
   return ccdpp_rank1_impl(e, k, first_iter, inner, ureg, ireg, item_freq_thresh);
 }
+extern "C" int mfb_debug_chol64(mfb_engine *e, int32_t n, const float *records, float *x, int32_t rank, float reg) {
+  MFB_REQUIRE(e && records && x && n > 0 && rank > 0 && rank <= 64, "mfb_debug_chol64: bad argument");
+  MFB_CUDA(mfb::enter(e));
+  return als_debug_chol64(e, n, records, x, rank, reg);
+}
 extern "C" int mfb_ccd_half_step(mfb_engine *e, int side, float reg, const uint8_t *dim_order) {
   MFB_REQUIRE(e && e->res_row && e->res_col, "mfb_ccd_half_step: call mfb_ccdpp_begin first");
   MFB_REQUIRE(side == MFB_USER || side == MFB_ITEM, "mfb_ccd_half_step: bad side");

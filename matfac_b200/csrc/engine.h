@@ -247,6 +247,36 @@ struct mfb_engine {
 
 namespace mfb {
 
+// ---- ALS (csrc/als.cu, csrc/als_mn.cu) ----
+struct AlsArgs {
+  const float *Fin;  // opposite side's factors [.][ld]
+  float *Fout;       // this side's factors
+  int ld, rank;
+  const int32_t *ind;
+  const float *val;
+  const int32_t *seg_row, *seg_start, *seg_len, *seg_slot;
+  const int32_t *multi_row;
+  float *ws;
+  float reg;
+  // row-sharded runs: the other ranks' copies of this side's factors (peer memory); every solved row
+  // is stored into all of them, i.e. the all-gather is fused into the solve epilogue
+  float *Fpeer[kMaxRanks - 1];
+  int n_peer;
+  int seg0, nseg;  // segments [seg0, seg0 + nseg) of the plan belong to this launch (sorted longest first)
+};
+
+__device__ __forceinline__ void store_solution(const AlsArgs &a, int row, int tid, const float *bv) {
+  if (tid < a.ld) {
+    const float x = tid < a.rank ? bv[tid] : 0.f;
+    a.Fout[(size_t)row * a.ld + tid] = x;
+    for (int p = 0; p < a.n_peer; p++) a.Fpeer[p][(size_t)row * a.ld + tid] = x;
+  }
+}
+// the rank-64 path on MN-major tensor-core operands (csrc/als_mn.cu): Gram records to global memory, then a batched
+// warp-per-matrix Cholesky; n_primal = leading segments of the plan that go through the rank x rank normal equations
+int als_mn_half_step(mfb_engine *e, const AlsArgs &a, const SegPlan &sp, int n_primal);
+int als_debug_chol64(mfb_engine *e, int32_t n, const float *rec_host, float *x_host, int32_t rank, float reg);
+
 int ensure_scratch(mfb_engine *e, size_t bytes);
 // Builds a SegPlan over rows [row_lo,row_hi) of ptr (device int64 [nrows+1]), sorted longest first
 // (by_length) or left in memory order; rows whose mask

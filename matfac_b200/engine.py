@@ -25,7 +25,7 @@ SYMBOLS = [
     "mfb_last_error", "mfb_launch_count", "mfb_device_count", "mfb_create", "mfb_destroy", "mfb_sync", "mfb_pin_host",
     "mfb_unpin_host", "mfb_upload_csr", "mfb_set_masks", "mfb_upload_factors", "mfb_download_factors",
     "mfb_set_aux", "mfb_sgd_plan", "mfb_sgd_subepoch", "mfb_sgd_block_nnz", "mfb_debug_sgd_records", "mfb_debug_sgd_hot_batch", "mfb_sgd_epoch_flat", "mfb_set_option", "mfb_als_half_step", "mfb_debug_als_gram",
-    "mfb_ccdpp_begin", "mfb_ccdpp_rank1", "mfb_ccdpp_end", "mfb_ccd_half_step", "mfb_eval", "mfb_eval_groups", "mfb_rank_positions", "mfb_predict", "mfb_snapshot_best",
+    "mfb_ccdpp_begin", "mfb_ccdpp_rank1", "mfb_ccdpp_end", "mfb_ccd_half_step", "mfb_debug_chol64", "mfb_eval", "mfb_eval_groups", "mfb_rank_positions", "mfb_predict", "mfb_snapshot_best",
     "mfb_restore_best", "mfb_event_record", "mfb_event_elapsed_ms", "mfb_device_factors", "mfb_stream",
     "mfb_pack_rows", "mfb_unpack_rows", "mfb_set_row_range",
     "mfb_build_csc", "mfb_download_csc", "mfb_comm_init", "mfb_comm_connect", "mfb_comm_barrier", "mfb_comm_error", "mfb_dsgd_push_block",
@@ -83,6 +83,7 @@ def load_library():
     L.mfb_ccdpp_rank1.argtypes = [vp, i32, C.c_int, i32, f32, f32, i32]
     L.mfb_ccdpp_end.argtypes = [vp]
     L.mfb_ccd_half_step.argtypes = [vp, C.c_int, f32, vp]
+    L.mfb_debug_chol64.argtypes = [vp, i32, vp, vp, i32, f32]
     L.mfb_eval.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.mfb_eval_groups.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.mfb_rank_positions.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
@@ -262,6 +263,13 @@ class Engine:
             d = np.ascontiguousarray(dim_order, np.uint8)
             assert d.shape == ((self.n_users if side == USER else self.n_items), self.rank)
         self._check(self.L.mfb_ccd_half_step(self.h, side, reg, None if d is None else d.ctypes.data_as(C.c_void_p)))
+
+    def debug_chol64(self, records, rank, reg):
+        """Batched rank-64 solver on host records [n][2240] (see mfb_debug_chol64); returns x [n][64]."""
+        rec = np.ascontiguousarray(records, np.float32)
+        x = np.zeros((rec.shape[0], 64), np.float32)
+        self._check(self.L.mfb_debug_chol64(self.h, rec.shape[0], rec.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), rank, reg))
+        return x
 
     def ccdpp_end(self):
         self._check(self.L.mfb_ccdpp_end(self.h))

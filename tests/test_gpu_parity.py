@@ -600,6 +600,46 @@ def test_ccd_matches_oracle(rank, shape):
     eng.close()
 
 
+def chol64_records(G, b):
+    """Host image of the ALS rank-64 solver's records: compact lower triangle (row r at 4 (r/4 + 1)(2 (r/4) + r%4), padded
+    to four floats) + right-hand side."""
+    n = G.shape[0]
+    rec = np.zeros((n, 2240), np.float32)
+    for r in range(64):
+        m, s_ = r >> 2, r & 3
+        off = 4 * (m + 1) * (2 * m + s_)
+        rec[:, off:off + r + 1] = G[:, r, :r + 1]
+    rec[:, 2176:] = b
+    return rec
+
+
+@pytest.mark.parametrize("rank", [64, 50, 33])
+def test_batched_chol64_matches_float64_solve(rank):
+    """als_chol64_kernel (one warp per matrix, blocked left-looking Cholesky) against numpy's float64 solve on Gram matrices of
+    random factor rows: more matrices than one wave of warps, short and long rows, padded ranks."""
+    rng = np.random.default_rng(7)
+    n = 5000
+    G = np.zeros((n, 64, 64), np.float64); b = np.zeros((n, 64), np.float64)
+    for lo in range(0, n, 500):
+        k = int(rng.integers(40, 400))
+        X = np.zeros((500, k, 64), np.float32)
+        X[:, :, :rank] = rng.normal(size=(500, k, rank)).astype(np.float32) * 0.3
+        r = rng.uniform(1, 5, size=(500, k)).astype(np.float32)
+        G[lo:lo + 500] = np.einsum("nkr,nks->nrs", X.astype(np.float64), X.astype(np.float64))
+        b[lo:lo + 500] = np.einsum("nk,nkr->nr", r.astype(np.float64), X.astype(np.float64))
+    reg = 0.1
+    A = G.copy()
+    for d in range(64):
+        A[:, d, d] = A[:, d, d] + reg if d < rank else 1.0
+    want = np.linalg.solve(A, b[:, :, None])[:, :, 0]
+    eng = E.Engine(10, 10, rank)
+    x = eng.debug_chol64(chol64_records(G.astype(np.float32), b.astype(np.float32)), rank, reg)
+    eng.close()
+    assert np.all(x[:, rank:] == 0)
+    err = np.linalg.norm(x - want, axis=1) / np.linalg.norm(want, axis=1)
+    assert err.max() < 1e-4, (err.max(), int(err.argmax()))
+
+
 def test_device_column_index_is_bit_exact():
     """mfb_build_csc == gk_csr_CreateIndex(mat, GK_CSR_COL): the oracle's CSC arrays, bit for bit, including
     empty rows / columns and a matrix narrower than the engine."""
