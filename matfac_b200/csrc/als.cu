@@ -1352,8 +1352,20 @@ static int launch_als(mfb_engine *e, const AlsArgs &a, const SegPlan &sp) {
   int n_primal = sp.n_seg;
   bool n_primal_done = false;
   if (e->opt_als_dual) n_primal = TR == 8 ? n64 : TR == 4 ? n32 : TR == 2 ? n16 : sp.n_seg;
-  if constexpr (TR == 8 || TR == 4) {
+  if constexpr (TR == 4) {
     if (e->opt_als_tensor_cores == 1) {
+      // rank 33 .. 64: Gram records on MN-major tensor-core operands + batched warp-per-matrix solve (csrc/als_mn.cu);
+      // split rows are summed into their own record there, the short rows below go through the dual kernels as before
+      MFB_TRY(als_mn_half_step(e, b, sp, n_primal));
+      if (n_primal < sp.n_seg) {
+        MFB_TRY(launch_dual<2>(e, b, n32, n16 - n32));
+        MFB_TRY(launch_dual<1>(e, b, n16, sp.n_seg - n16));
+      }
+      return 0;
+    }
+  }
+  if constexpr (TR == 8 || TR == 4) {
+    if (e->opt_als_tensor_cores == 1 || (TR == 4 && e->opt_als_tensor_cores == 3)) {  // 3: the round-2 converter kernel at rank <= 64
       // mean length of the rows this launch takes: the plan is sorted longest first and [0, n_primal) are primal
       // the split is picked from the mean row length of the WHOLE side, not of this rank's shard: every rank of a
       // row-sharded run then sums a row's right-hand side in the same order as a single engine would (bit-identical rows)

@@ -47,6 +47,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity)
       : "memory");
 }
+// the same with a suspend-time hint: a warp that expects to wait long is parked by the hardware instead of spinning
+// through the issue slots of the warps that have work
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, uint32_t ns) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "MPW_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra MPD_%=;\n\t"
+      "bra MPW_%=;\n\t"
+      "MPD_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -98,6 +112,7 @@ __device__ __forceinline__ void warp_chol64(float *M, float *dinv, int lane, int
   row1[r1] = r1 < rank ? row1[r1] + reg : 1.0f;
   __syncwarp();
   float4 *R0 = reinterpret_cast<float4 *>(row0), *R1 = reinterpret_cast<float4 *>(row1);
+#pragma unroll 1
   for (int J = 0; J < 16; J++) {
     // rows 4J .. 4J + 3 hold J + 1 units of 16 bytes each
     const float4 *B0 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J));
@@ -106,12 +121,14 @@ __device__ __forceinline__ void warp_chol64(float *M, float *dinv, int lane, int
     float4 t1 = R1[J], t0 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (two) {
       t0 = R0[J];
+#pragma unroll 1
       for (int k = 0; k < J; k++) {
         const float4 b0 = B0[k], b1 = B1[k], b2 = B2[k], b3 = B3[k], a0 = R0[k], a1 = R1[k];
         t0.x = sub_dot4(a0, b0, t0.x); t0.y = sub_dot4(a0, b1, t0.y); t0.z = sub_dot4(a0, b2, t0.z); t0.w = sub_dot4(a0, b3, t0.w);
         t1.x = sub_dot4(a1, b0, t1.x); t1.y = sub_dot4(a1, b1, t1.y); t1.z = sub_dot4(a1, b2, t1.z); t1.w = sub_dot4(a1, b3, t1.w);
       }
     } else {
+#pragma unroll 2
       for (int k = 0; k < J; k++) {
         const float4 b0 = B0[k], b1 = B1[k], b2 = B2[k], b3 = B3[k], a1 = R1[k];
         t1.x = sub_dot4(a1, b0, t1.x); t1.y = sub_dot4(a1, b1, t1.y); t1.z = sub_dot4(a1, b2, t1.z); t1.w = sub_dot4(a1, b3, t1.w);
@@ -144,6 +161,7 @@ __device__ __forceinline__ void warp_chol64(float *M, float *dinv, int lane, int
   // L y = b, block column by block column; y0 / y1 carry the running right-hand side of rows lane / lane + 32
   const float *bv = M + kRecG;
   float y0 = bv[r0], y1 = bv[r1];
+#pragma unroll 1
   for (int J = 0; J < 16; J++) {
     const float4 *B0 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J));
     const float4 q1 = B0[2 * J + 1], q2 = B0[3 * J + 2], q3 = B0[4 * J + 3];  // unit J of rows 4J + 1 .. 4J + 3
@@ -164,6 +182,7 @@ __device__ __forceinline__ void warp_chol64(float *M, float *dinv, int lane, int
     else { if ((lane >> 2) == J - 8) y1 = pick4(z, lane & 3); }
   }
   // L^T x = y, from the last block column backwards
+#pragma unroll 1
   for (int J = 15; J >= 0; J--) {
     const float *S0 = M + chol_row_off(4 * J);
     const float *S1 = S0 + 4 * (J + 1), *S2 = S1 + 4 * (J + 1), *S3 = S2 + 4 * (J + 1);
@@ -189,9 +208,14 @@ __device__ __forceinline__ void warp_chol64(float *M, float *dinv, int lane, int
   x1 = y1;
 }
 
-constexpr int kCholWarps = 12;
-constexpr uint32_t kCholWarpBytes = 2 * kRecBytes + 256;  // two record buffers + the inverse diagonal
-constexpr uint32_t kCholSmem = kCholWarps * kCholWarpBytes + kCholWarps * 16 + 128;
+// NW warps per CTA, NB record buffers per warp (2: the next record is fetched while the current one is solved; 1: more
+// warps fit the shared memory and hide each other's fetches)
+template <int NW, int NB>
+struct CholCfg {
+  static constexpr uint32_t warp_bytes = NB * kRecBytes + 256;  // record buffers + the inverse diagonal
+  static constexpr uint32_t smem = NW * warp_bytes + NW * 16 + 128;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+};
 
 struct CholArgs {
   const float *rec;     // [n_jobs][kRecFloats]
@@ -205,20 +229,24 @@ struct CholArgs {
   int n_peer;
 };
 
-__global__ void __launch_bounds__(kCholWarps * 32, 1) als_chol64_kernel(const CholArgs a) {
+template <int NW, int NB>
+__global__ void __launch_bounds__(NW * 32, 1) als_chol64_kernel(const CholArgs a) {
+  using C = CholCfg<NW, NB>;
   extern __shared__ __align__(128) uint8_t smraw[];
-  uint8_t *smb = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smraw) + 127) & ~(uintptr_t)127);
+  // offset arithmetic on the shared array itself (not through an integer): the compiler keeps the shared address space
+  // and emits LDS / STS — through a uintptr_t round trip every access of the solver became a generic LD.E / ST.E
+  uint8_t *smb = smraw + ((128u - (smem_u32(smraw) & 127u)) & 127u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t *mine = smb + (size_t)warp * kCholWarpBytes;
-  float *dinv = reinterpret_cast<float *>(mine + 2 * kRecBytes);
-  const uint32_t bars = smem_u32(smb + (size_t)kCholWarps * kCholWarpBytes) + warp * 16;
+  uint8_t *mine = smb + (size_t)warp * C::warp_bytes;
+  float *dinv = reinterpret_cast<float *>(mine + NB * kRecBytes);
+  const uint32_t bars = smem_u32(smb + (size_t)NW * C::warp_bytes) + warp * 16;
   if (lane == 0) {
     mbar_init(bars, 1);
     mbar_init(bars + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  const int stride = (int)gridDim.x * kCholWarps;
+  const int stride = (int)gridDim.x * NW;
   auto next_job = [&](int j) {  // first job >= j (on this warp's stride) that has a matrix to solve
     while (j < a.n_seg && a.seg_slot[j] >= 0) j += stride;
     return j;
@@ -230,13 +258,13 @@ __global__ void __launch_bounds__(kCholWarps * 32, 1) als_chol64_kernel(const Ch
       bulk_g2s(smem_u32(mine + b * kRecBytes), a.rec + (size_t)j * kRecFloats, kRecBytes, bars + b * 8);
     }
   };
-  int j = next_job((int)blockIdx.x * kCholWarps + warp);
+  int j = next_job((int)blockIdx.x * NW + warp);
   if (j < a.n_jobs) fetch(j, 0);
   uint32_t ph = 0u;  // bit b: phase parity of buffer b's barrier
-  for (int b = 0; j < a.n_jobs; b ^= 1) {
+  for (int b = 0; j < a.n_jobs; b = (b + 1) % NB) {
     const int jn = next_job(j + stride);
     __syncwarp();
-    if (jn < a.n_jobs) fetch(jn, b ^ 1);
+    if (NB > 1 && jn < a.n_jobs) fetch(jn, b ^ 1);
     mbar_wait(bars + b * 8, (ph >> b) & 1u);
     ph ^= 1u << b;
     float x0, x1;
@@ -253,15 +281,397 @@ __global__ void __launch_bounds__(kCholWarps * 32, 1) als_chol64_kernel(const Ch
       if (lane + 32 < a.ld) op[lane + 32] = x1;
     }
     j = jn;
+    if (NB == 1 && j < a.n_jobs) {
+      __syncwarp();
+      fetch(j, 0);
+    }
   }
+}
+
+template <int NW, int NB>
+int launch_chol64_cfg(mfb_engine *e, const CholArgs &c) {
+  using C = CholCfg<NW, NB>;
+  MFB_CUDA(cudaFuncSetAttribute((als_chol64_kernel<NW, NB>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
+  const int grid = std::min(e->sm_count, (c.n_jobs + NW - 1) / NW);
+  MFB_LAUNCH((als_chol64_kernel<NW, NB>), grid, NW * 32, C::smem, e->stream, c);
+  return 0;
 }
 
 int launch_chol64(mfb_engine *e, const CholArgs &c) {
   if (c.n_jobs <= 0) return 0;
-  MFB_CUDA(cudaFuncSetAttribute(als_chol64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholSmem));
-  const int grid = std::min(e->sm_count, (c.n_jobs + kCholWarps - 1) / kCholWarps);
-  MFB_LAUNCH(als_chol64_kernel, grid, kCholWarps * 32, kCholSmem, e->stream, c);
-  return 0;
+  switch (e->opt_als_chol_warps) {
+    case 12: return launch_chol64_cfg<12, 2>(e, c);
+    case 16: return launch_chol64_cfg<16, 1>(e, c);
+    case 20: return launch_chol64_cfg<20, 1>(e, c);
+    default: return launch_chol64_cfg<24, 1>(e, c);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tf32 split of the gathered side's factors
+__device__ __forceinline__ float round_tf32_fast(float x) {  // nearest, ties away, finite values (two integer instructions)
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+__global__ void __launch_bounds__(256) als_split_kernel(const float *__restrict__ F, int ld, int n, float *__restrict__ Fs) {
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t row = t >> 4;
+  const int q = (int)(t & 15);
+  if (row > n) return;
+  float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < n && 4 * q < ld) f = *reinterpret_cast<const float4 *>(F + row * ld + 4 * q);
+  const float4 b = make_float4(round_tf32_fast(f.x), round_tf32_fast(f.y), round_tf32_fast(f.z), round_tf32_fast(f.w));
+  const float4 sm = make_float4(f.x - b.x, f.y - b.y, f.z - b.z, f.w - b.w);  // exact in fp32; the tensor core reads its upper 19 bits
+  *reinterpret_cast<float4 *>(Fs + row * 128 + 4 * q) = b;
+  *reinterpret_cast<float4 *>(Fs + row * 128 + 64 + 4 * q) = sm;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gram records on MN-major operands
+constexpr int kGnKT = 32;                     // ratings per tile
+constexpr uint32_t kGnBlock = 4096;           // one operand block: 32 dims x 32 ratings (LBO: stride between 32-dim blocks)
+constexpr uint32_t kGnSbo = 512;              // 4 ratings x 128 bytes (stride between groups of 4 ratings)
+constexpr uint32_t kGnStage = 5 * kGnBlock;   // big 0-31 | big 32-63 | small 0-31 | small 32-63 | ratings (n = 0: r_big, n = 1: r_small)
+constexpr int kGnStages = 8;
+constexpr int kGnDepth = 6;                   // tiles whose copies a producer thread keeps in flight (< kGnStages)
+constexpr int kGnMeta = 8;                    // (item, rating) of a tile is requested this many tiles ahead (> kGnDepth: it rides in an
+                                              // earlier commit group than the one that is waited for before it is read)
+constexpr int kGnProducers = 128;             // thread t: ratings t / 8 and t / 8 + 16 of the tile, chunk t % 8 of every 128-byte block of their split rows
+constexpr int kGnAcc = 4;                     // accumulators in TMEM: row i -> i mod 4
+constexpr int kGnAccCols = 128;               // D in columns [0, 64), D2 in [64, 80)
+constexpr int kGnDrainTeams = 2;              // row i is drained by team i mod 2 (4 warps, one per TMEM lane quadrant)
+constexpr int kGnMma0 = kGnProducers, kGnDrain0 = kGnMma0 + 32;
+constexpr int kGnThreads = kGnDrain0 + kGnDrainTeams * 128;
+constexpr int kGnFirst = 1, kGnLast = 2;
+
+struct GramSmem {
+  static constexpr uint32_t off_stage = 0;
+  static constexpr uint32_t off_rec = off_stage + kGnStages * kGnStage;               // [teams][2] record staging
+  static constexpr uint32_t off_tmp = off_rec + kGnDrainTeams * 2 * kRecBytes;        // [teams][64] small x r_big
+  static constexpr uint32_t off_meta = off_tmp + kGnDrainTeams * 64 * 4;              // [kGnMeta][producers] {item, rating} x 2: thread-private ring
+  static constexpr uint32_t off_tflags = off_meta + kGnMeta * kGnProducers * 16;     // [kGnMeta] flags of the tiles the cursor has visited
+  static constexpr uint32_t off_info = off_tflags + kGnMeta * 4;                      // [stages] tile flags
+  static constexpr uint32_t off_bars = off_info + kGnStages * 4;                      // op_full | op_empty | acc_full | acc_empty
+  static constexpr int n_bars = 2 * kGnStages + 2 * kGnAcc;
+  static constexpr uint32_t off_tmem = off_bars + n_bars * 8;
+  static constexpr size_t bytes = off_tmem + 16 + 1024;
+  static_assert(bytes <= 227 * 1024, "shared memory budget");
+  static_assert(kGnMeta > kGnDepth && kGnDepth < kGnStages, "pipeline depths");
+};
+
+struct GramArgs {
+  const float *Fs;      // [zero_row + 1][128] split factors of the gathered side
+  int zero_row;
+  const int32_t *ind;
+  const float *val;
+  const int32_t *seg_start, *seg_len, *seg_slot;
+  int nseg;             // segments [0, nseg) of the plan (longest first); CTA b takes b, b + grid, ...
+  float *rec;           // [nseg + split rows][kRecFloats]
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {  // SWIZZLE_128B_BASE32B, version 1
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((kGnBlock >> 4) & 0x3FFF) << 16;  // leading byte offset: next block of 32 dims
+  d |= (uint64_t)((kGnSbo >> 4) & 0x3FFF) << 32;    // stride byte offset: next group of 4 ratings
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t &a, uint32_t &b) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
+}
+
+__global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramArgs a) {
+  using S = GramSmem;
+  extern __shared__ __align__(1024) uint8_t sm_raw[];
+  uint8_t *smb = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);  // stays a shared-space pointer (LDS / STS)
+  const uint32_t sbase = smem_u32(smb);
+  int *opinfo = reinterpret_cast<int *>(smb + S::off_info);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smb + S::off_tmem);
+  const uint32_t bar_opf = sbase + S::off_bars, bar_ope = bar_opf + kGnStages * 8, bar_accf = bar_ope + kGnStages * 8,
+                 bar_acce = bar_accf + kGnAcc * 8;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int n_rows = (int)blockIdx.x < a.nseg ? (a.nseg - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (tid == 0) {
+    for (int i = 0; i < kGnStages; i++) {
+      mbar_init(bar_opf + i * 8, kGnProducers / 32);
+      mbar_init(bar_ope + i * 8, 1);
+    }
+    for (int i = 0; i < kGnAcc; i++) {
+      mbar_init(bar_accf + i * 8, 1);
+      mbar_init(bar_acce + i * 8, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // the ratings block of every stage is zero except the two floats a producer writes per rating
+  for (int i = tid; i < kGnStages * (int)(kGnBlock / 16); i += kGnThreads) {
+    const int stg = i / (int)(kGnBlock / 16), u = i % (int)(kGnBlock / 16);
+    *reinterpret_cast<float4 *>(smb + S::off_stage + stg * kGnStage + 4 * kGnBlock + u * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kGnAcc * kGnAccCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (tid < kGnProducers) {
+    // ================================= producers =================================
+    // ONE cursor walks the tiles of this CTA's rows (row i = segment blockIdx.x + i * gridDim.x), kGnMeta tiles ahead of
+    // the copies: it requests the (item, rating) pairs of a tile and records the tile's flags; the bounds of the next two
+    // rows are fetched when a row is entered (a whole row of lead time for the dependent loads).
+    struct Cursor { int i, t, ntiles, start, len, s1, l1, s2, l2; };
+    auto load_seg = [&](int i, int &st_, int &ln_) {
+      st_ = ln_ = 0;
+      if (i < n_rows) {
+        const int seg = (int)blockIdx.x + i * (int)gridDim.x;
+        st_ = __ldg(a.seg_start + seg);
+        ln_ = __ldg(a.seg_len + seg);
+      }
+    };
+    auto advance = [&](Cursor &c) {
+      if (c.i >= n_rows) return;
+      if (++c.t == c.ntiles) {
+        c.i++; c.t = 0;
+        c.start = c.s1; c.len = c.l1;
+        c.ntiles = (c.len + kGnKT - 1) / kGnKT;
+        c.s1 = c.s2; c.l1 = c.l2;
+        load_seg(c.i + 2, c.s2, c.l2);
+      }
+    };
+    // thread t: chunk t % 8 of each of the four 128-byte blocks of the split rows of ratings t / 8 and t / 8 + 16 of the tile.
+    // Eight neighbouring lanes copy one contiguous 128-byte block of one rating; its swizzled destination covers all 32
+    // banks, so a warp's copy is written in the minimum of four shared-memory wavefronts.
+    const int o = tid >> 3, cg = tid & 7;
+    const uint32_t kq = (uint32_t)o & 3u;
+    const uint32_t base_off = (uint32_t)(o >> 2) * kGnSbo + kq * 128u + ((((uint32_t)cg >> 1) ^ kq) << 5) + ((uint32_t)cg & 1u) * 16u;
+    const uint32_t roff = 4u * kGnBlock + (uint32_t)(o >> 2) * kGnSbo + kq * 128u + (kq << 5);
+    constexpr uint32_t kSecond = 4u * kGnSbo;  // rating + 16: four groups of 4 ratings further
+    // {item, rating} x 2 of tile x: requested kGnMeta tiles ahead with 4-byte cp.async into the thread's own ring slot (no
+    // other thread reads it), in the commit group of tile x - kGnMeta; that group has been waited for (wait_group kGnDepth
+    // at iteration x - 1 covers groups <= x - 1 - kGnDepth) before iteration x reads it
+    const uint32_t meta0 = sbase + S::off_meta + (uint32_t)tid * 16u;
+    const int4 *meta_ptr = reinterpret_cast<const int4 *>(smb + S::off_meta) + tid;
+    int *tflags = reinterpret_cast<int *>(smb + S::off_tflags);
+    int n_tiles = -1;
+    auto request_meta = [&](const Cursor &c, int x) {
+      const bool alive = c.i < n_rows;
+      if (!alive && n_tiles < 0) n_tiles = x;
+      const uint32_t dst = meta0 + (uint32_t)(x % kGnMeta) * (kGnProducers * 16u);
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int jj = c.t * kGnKT + o + 16 * e;
+        if (alive && jj < c.len) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 8 * e), "l"(a.ind + c.start + jj) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 8 * e + 4), "l"(a.val + c.start + jj) : "memory");
+        } else {
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + 8 * e), "r"(0), "r"(0) : "memory");  // rating 0: filtered out
+        }
+      }
+      if (tid == 0) tflags[x % kGnMeta] = alive ? ((c.t == 0 ? kGnFirst : 0) | (c.t == c.ntiles - 1 ? kGnLast : 0)) : 0;
+    };
+    Cursor nxt;
+    nxt.i = 0; nxt.t = 0;
+    load_seg(0, nxt.start, nxt.len);
+    nxt.ntiles = (nxt.len + kGnKT - 1) / kGnKT;
+    load_seg(1, nxt.s1, nxt.l1);
+    load_seg(2, nxt.s2, nxt.l2);
+    for (int x = 0; x < kGnMeta; x++) {
+      request_meta(nxt, x);
+      advance(nxt);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    for (int g = 0;; g++) {
+      const bool live = n_tiles < 0 || g < n_tiles;
+      if (live) {
+        const int stg = g % kGnStages;
+        const int4 mt = meta_ptr[(g % kGnMeta) * kGnProducers];
+        if (g >= kGnStages) mbar_wait(bar_ope + stg * 8, (uint32_t)(g / kGnStages - 1) & 1u);  // the MMAs that read this stage are done
+        if (tid == 0) opinfo[stg] = tflags[g % kGnMeta];  // only now: the tensor-core warp has read the previous tile's flags
+        const uint32_t dst0 = sbase + S::off_stage + (uint32_t)stg * kGnStage;
+        const int its[2] = {mt.x, mt.z};
+        const float rts[2] = {__int_as_float(mt.y), __int_as_float(mt.w)};
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const bool on = rts[e] > 0.f;  // rating > 0 filter (modelMF.cpp:819); beyond the row's end the ring holds 0
+          const float *src = a.Fs + (size_t)(on ? its[e] : a.zero_row) * 128 + cg * 4;
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + base_off + e * kSecond + i * kGnBlock), "l"(src + 32 * i) : "memory");
+          if (cg == 0) {
+            const float rb = on ? round_tf32_fast(rts[e]) : 0.f;
+            const float rs = on ? rts[e] - rb : 0.f;
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(dst0 + roff + e * kSecond), "f"(rb), "f"(rs) : "memory");
+          }
+        }
+        request_meta(nxt, g + kGnMeta);  // into the slot that was just read
+        advance(nxt);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      const int gd = g - kGnDepth;
+      if (gd >= 0) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kGnDepth) : "memory");  // this thread's copies of tile gd have landed
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_opf + (gd % kGnStages) * 8);
+      }
+      if (n_tiles >= 0 && gd >= n_tiles - 1) break;
+    }
+  } else if (tid < kGnDrain0) {
+    // ================================= tensor-core issue =================================
+    // instruction descriptors: D = F32, A = B = TF32, both MN-major; M = 128; N = 64 (Gram) / 16 (right-hand side)
+    constexpr uint32_t idesc_g = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t idesc_r = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t desc0 = umma_desc_mn(sbase + S::off_stage);
+    int os = 0, acc = 0, gen = 0;
+    uint32_t ph = 0;
+    bool first = true;
+    for (int rows_done = 0; rows_done < n_rows;) {
+      mbar_wait(bar_opf + os * 8, ph);
+      const bool last = __any_sync(0xFFFFFFFFu, (opinfo[os] & kGnLast) != 0);
+      if (first && gen > 0) mbar_wait(bar_acce + acc * 8, (uint32_t)(gen - 1) & 1u);  // accumulator drained
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one_sync()) {
+        const uint32_t dt = tmem_base + (uint32_t)acc * kGnAccCols;
+        const uint64_t descs = desc0 + (uint64_t)((uint32_t)os * (kGnStage >> 4));
+#pragma unroll
+        for (int k8 = 0; k8 < kGnKT / 8; k8++) {
+          const uint64_t dk = descs + (uint64_t)(k8 * ((2 * kGnSbo) >> 4));
+          const uint32_t accum = (first && k8 == 0) ? 0u : 1u;
+          umma_tf32(dt, dk, dk, idesc_g, accum);
+          umma_tf32(dt + 64, dk, dk + (uint64_t)((4 * kGnBlock) >> 4), idesc_r, accum);
+        }
+        umma_commit(bar_ope + os * 8);
+        if (last) umma_commit(bar_accf + acc * 8);
+      }
+      __syncwarp();
+      first = last;
+      if (last) {
+        rows_done++;
+        if (++acc == kGnAcc) { acc = 0; gen++; }
+      }
+      if (++os == kGnStages) { os = 0; ph ^= 1u; }
+    }
+  } else {
+    // ================================= drain teams =================================
+    const int dt = tid - kGnDrain0, team = dt >> 7, t = dt & 127;
+    const int p = 32 * ((tid >> 5) & 3) + lane;  // TMEM lane this thread may read (its warp's quadrant)
+    const int arow = p & 63;
+    float *tmp = reinterpret_cast<float *>(smb + S::off_tmp) + team * 64;
+    const int bar_id = 1 + team;
+    auto team_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
+    int n = 0;
+    for (int i = team; i < n_rows; i += kGnDrainTeams, n++) {
+      const int acc = i % kGnAcc;
+      const uint32_t par = (uint32_t)(i / kGnAcc) & 1u;
+      const int seg = (int)blockIdx.x + i * (int)gridDim.x;
+      const int slot = a.seg_slot[seg];
+      float *Sr = reinterpret_cast<float *>(smb + S::off_rec + (uint32_t)(team * 2 + (n & 1)) * kRecBytes);
+      if (t == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the store that read this buffer two rows ago
+      mbar_wait_parked(bar_accf + acc * 8, par, 20000u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tad = tmem_base + (uint32_t)acc * kGnAccCols + ((uint32_t)(p & ~31) << 16);
+      uint32_t v[64], r0, r1;
+      {
+        uint32_t lo[32], hi[32];
+        tmem_ld32(tad, lo);
+        tmem_ld32(tad + 32, hi);
+        tmem_ld2(tad + 64, r0, r1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < 32; k++) { v[k] = lo[k]; v[32 + k] = hi[k]; }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(bar_acce + acc * 8);  // everything of this accumulator is in registers
+      team_bar();                        // the staging buffer is free (thread 0 has waited for its last store)
+      float4 *rowp = reinterpret_cast<float4 *>(Sr + chol_row_off(arow));
+      if (p < 64) {  // big big^T: units 0 .. arow / 4 of row arow
+#pragma unroll
+        for (int u = 0; u < 16; u++)
+          if (4 * u <= arow)
+            rowp[u] = make_float4(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]), __uint_as_float(v[4 * u + 2]), __uint_as_float(v[4 * u + 3]));
+      } else {
+        tmp[arow] = __uint_as_float(r0);  // small x r_big
+      }
+      team_bar();
+      if (p >= 64) {  // + small big^T, lower part of row arow (the diagonal once here, once below)
+#pragma unroll
+        for (int u = 0; u < 16; u++)
+          if (4 * u <= arow) {
+            float4 o = rowp[u];
+            o.x += __uint_as_float(v[4 * u]); o.y += __uint_as_float(v[4 * u + 1]);
+            o.z += __uint_as_float(v[4 * u + 2]); o.w += __uint_as_float(v[4 * u + 3]);
+            rowp[u] = o;
+          }
+      } else {
+        Sr[kRecG + arow] = __uint_as_float(r0) + __uint_as_float(r1) + tmp[arow];  // big r_big + big r_small + small r_big
+      }
+      team_bar();
+      if (p >= 64) {  // + (small big^T)^T: G(c, arow) += SB[arow][c] for c >= arow
+#pragma unroll
+        for (int c = 0; c < 64; c++)
+          if (c >= arow) Sr[chol_row_off(c) + arow] += __uint_as_float(v[c]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      team_bar();
+      if (slot < 0) {
+        if (t == 0) {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.rec + (size_t)seg * kRecFloats),
+                       "r"(smem_u32(Sr)), "r"(kRecBytes)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else {  // segment of a split row: add into the row's record
+        float *dst = a.rec + ((size_t)a.nseg + slot) * kRecFloats;
+        for (int k = t; k < kRecFloats; k += 128) atomicAdd(dst + k, Sr[k]);
+        if (t == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");  // keeps the wait_group arithmetic fixed
+      }
+    }
+    if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the last stores have completed
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kGnAcc * kGnAccCols) : "memory");
 }
 
 }  // namespace
@@ -288,8 +698,37 @@ int als_debug_chol64(mfb_engine *e, int32_t n, const float *rec_host, float *x_h
 }
 
 int als_mn_half_step(mfb_engine *e, const AlsArgs &a, const SegPlan &sp, int n_primal) {
-  (void)e; (void)a; (void)sp; (void)n_primal;
-  return fail("als_mn_half_step: not built yet", __FILE__, __LINE__);
+  if (n_primal <= 0) return 0;
+  cudaStream_t st = e->stream;
+  const int n_in = a.Fin == e->V ? e->n_items : e->n_users;
+  float *Fs = nullptr, *rec = nullptr;
+  MFB_CUDA(dev_alloc(&Fs, sizeof(float) * 128 * ((size_t)n_in + 1)));
+  const size_t n_rec = (size_t)n_primal + (size_t)sp.n_multi;
+  MFB_CUDA(dev_alloc(&rec, n_rec * kRecBytes));
+  if (sp.n_multi > 0) MFB_CUDA(cudaMemsetAsync(rec + (size_t)n_primal * kRecFloats, 0, (size_t)sp.n_multi * kRecBytes, st));
+  {
+    const int64_t total = ((int64_t)n_in + 1) * 16;  // one thread per 4 dims
+    MFB_LAUNCH(als_split_kernel, (unsigned)((total + 255) / 256), 256, 0, st, a.Fin, a.ld, n_in, Fs);
+  }
+  GramArgs g;
+  g.Fs = Fs; g.zero_row = n_in;
+  g.ind = a.ind; g.val = a.val;
+  g.seg_start = a.seg_start; g.seg_len = a.seg_len; g.seg_slot = a.seg_slot;
+  g.nseg = n_primal;
+  g.rec = rec;
+  MFB_CUDA(cudaFuncSetAttribute(als_gram_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GramSmem::bytes));
+  const int grid = std::min(e->sm_count, n_primal);
+  MFB_LAUNCH(als_gram_mn_kernel, grid, kGnThreads, GramSmem::bytes, st, g);
+  CholArgs c;
+  c.rec = rec; c.n_jobs = (int)n_rec; c.n_seg = n_primal;
+  c.seg_row = a.seg_row; c.seg_slot = a.seg_slot; c.multi_row = a.multi_row;
+  c.Fout = a.Fout; c.ld = a.ld; c.rank = a.rank; c.reg = a.reg;
+  c.n_peer = a.n_peer;
+  for (int p = 0; p < a.n_peer; p++) c.Fpeer[p] = a.Fpeer[p];
+  MFB_TRY(launch_chol64(e, c));
+  dev_free(Fs);
+  dev_free(rec);
+  return 0;
 }
 
 }  // namespace mfb
