@@ -20,7 +20,10 @@ exceed the 126 MB L2, so no explicit L2 flush is done between timed epochs.
             ranks), inputs resident in HBM
   e2e       the same metric through the C ABI with HOST buffers (N = 1): every step uploads the rating CSR and the
             factor matrices from pinned host memory, builds the plan, runs one epoch plus the per-epoch
-            evaluation and downloads the factors
+            evaluation and downloads the factors.  Headline: two such steps in flight (two engines, one host
+            thread each, taking turns on the link and on the SMs) = throughput of complete steps;
+            e2e_one_in_flight = the latency of a single step; e2e_resident_ratings = the step of a training
+            run (ratings uploaded once)
   roofline  algorithmic bytes (16 r + 12 per update) / kernel time vs the measured HBM copy
             bandwidth of MEASURED_PEAKS.json; `l2` = the same against the measured L2 figures of
             profiles/r2_l2_probe.json (the factor matrices of this shape are L2-resident)
@@ -804,6 +807,69 @@ def main():
                 eng.L.mfb_download_factors(eng.h, E.CURRENT, Uo.ctypes.data, RANK, Vo.ctypes.data, RANK)
                 eng.sync()
                 times_res.append(time.perf_counter() - t1)
+            # Two steps in flight: a second engine on the same GPU, one host thread per engine, every thread runs the SAME
+            # complete steps as above (upload CSR + factors, plan, epoch, objective + validation, download, sync) — one
+            # engine's PCIe transfers run next to the other's kernels, as a caller that pipelines its batches would have it.
+            # Every byte of every step still crosses the link inside the timed region.
+            piped = None
+            try:
+                import threading
+                eng2 = E.Engine(n_users, n_items, RANK, device=local_rank)
+                eng2.upload_csr(E.VAL, va, with_csc=False)
+                eng2.set_masks(bad_u, bad_i)
+                eng2.set_option("sgd_shuffle_seed", 1)
+                eng2.set_option("copy_overlap", 1)
+                Uo2, tU2 = pinned(np.empty_like(U0))
+                Vo2, tV2 = pinned(np.empty_like(V0))
+                K = max(2, args.e2e_steps)
+                gate = threading.Barrier(2)
+                link_turn, sm_turn = threading.Lock(), threading.Lock()
+                span, errs, evs = {}, [], {}
+
+                def pipeline(idx, en, uo, vo):
+                    try:
+                        for s in range(K + 1):
+                            if s == 1:
+                                en.sync()
+                                gate.wait()
+                                span[idx, 0] = time.perf_counter()
+                            with link_turn:  # the two pipelines take turns on the link and on the SMs: one uploads while the other computes
+                                en.upload_csr(E.TRAIN, trp, with_csc=False)
+                                en.upload_factors(h["U"], h["V"])
+                            with sm_turn:
+                                en.sgd_plan(1)
+                                en.sgd_epoch_flat(E.MF, HP["lr"], HP["ureg"], HP["ireg"], 1, s)
+                                en.L.mfb_download_factors(en.h, E.CURRENT, uo.ctypes.data, RANK, vo.ctypes.data, RANK)
+                                en.eval(E.TRAIN, E.CURRENT, E.MF, False, True)
+                                evs[idx] = en.eval(E.VAL)
+                                en.sync()
+                        span[idx, 1] = time.perf_counter()
+                    except Exception as ex:  # noqa: BLE001
+                        errs.append(repr(ex)[:200])
+                        try:
+                            gate.abort()
+                        except Exception:  # noqa: BLE001
+                            pass
+
+                ths = [threading.Thread(target=pipeline, args=(0, eng, Uo, Vo)), threading.Thread(target=pipeline, args=(1, eng2, Uo2, Vo2))]
+                for t in ths:
+                    t.start()
+                for t in ths:
+                    t.join()
+                if errs:
+                    raise RuntimeError("; ".join(errs))
+                wall = max(span[0, 1], span[1, 1]) - min(span[0, 0], span[1, 0])
+                t_pipe = wall / (2 * K)
+                piped = {"value": train_nnz / t_pipe, "unit": "rating-updates/s", "ms_per_step": t_pipe * 1e3, "steps_timed": 2 * K,
+                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                         "val_rmse_last_step": [float(np.sqrt(evs[i][0] / max(evs[i][1], 1))) for i in (0, 1)],
+                         "what": "two engines on the GPU, one host thread each, both run complete steps (upload CSR + factors from pinned "
+                                 "host memory, plan, 1 epoch, objective + val RMSE, factor download, sync) and take turns on the link and on the SMs; "
+                                 "wall time of all steps / steps: one engine's uploads overlap the other's kernels"}
+                eng2.close()
+                del eng2, tU2, tV2
+            except Exception as ex:  # noqa: BLE001
+                piped = {"error": repr(ex)[:300]}
             eng.set_option("copy_overlap", 0)
             t_res = float(np.median(times_res[1:]))
             line["e2e_resident_ratings"] = {"value": train_nnz / t_res, "unit": "rating-updates/s", "ms_per_step": t_res * 1e3,
@@ -812,13 +878,21 @@ def main():
                                                     "CSR and the plan stay on the device (uploaded / built once)"}
             t_e2e = float(np.median(times[1:]))
             pm = np.median(np.array(parts[1:]), axis=0) * 1e3
-            line["e2e"] = {"value": train_nnz / t_e2e, "unit": "rating-updates/s", "h2d_bytes_per_step": int(h2d),
+            one = {"value": train_nnz / t_e2e, "unit": "rating-updates/s", "h2d_bytes_per_step": int(h2d),
                            "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e * 1e3,
                            "ms_breakdown": {"upload_and_plan": float(pm[0]), "epoch_eval_and_download": float(pm[1]), "download_tail": float(pm[2])},
                            "val_rmse_last_step": float(np.sqrt(ev[0] / max(ev[1], 1))),
                            "what": "per step: upload CSR + factors from pinned host memory (the factor upload runs next to the plan "
                                    "kernels), plan, 1 epoch, factor download issued next to objective + val RMSE (the copy engine is "
                                    "starved by the evaluation's HBM traffic: no gain there, tools/e2e_probe.py), sync"}
+            # headline: two steps in flight (throughput of complete steps, every byte of every step on the link); the single
+            # step's latency stays next to it
+            if piped and "value" in piped:
+                line["e2e"] = piped
+                line["e2e_one_in_flight"] = one
+            else:
+                line["e2e"] = one
+                line["e2e_two_in_flight"] = piped
             del keep, tU, tV
         eng.close()
         del eng

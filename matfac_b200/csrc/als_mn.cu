@@ -208,6 +208,116 @@ __device__ __forceinline__ void warp_chol64(float *M, float *dinv, int lane, int
   x1 = y1;
 }
 
+// Two matrices per warp: lanes 0-15 solve the record at M0, lanes 16-31 the one at M1 (the caller passes each lane ITS
+// matrix); lane q of a half owns rows q, q + 16, q + 32, q + 48.  The four rows of a block column that every lane needs
+// ("broadcast" loads: a warp-wide LDS.128 costs four shared-memory wavefronts whatever its addresses) now serve two
+// matrices and up to 64 FMAs per lane, and the granularity of idle rows drops from 32 to 16.  Shuffles stay inside a half.
+__device__ __forceinline__ void halfwarp_chol64(float *M, float *dinv, int q, int rank, float reg, float (&x)[4]) {
+  float *rowp[4];
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    const int r = q + 16 * p;
+    rowp[p] = M + chol_row_off(r);
+    rowp[p][r] = r < rank ? rowp[p][r] + reg : 1.0f;
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int J = 0; J < 16; J++) {
+    const float4 *B0 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J));
+    const float4 *B1 = B0 + (J + 1), *B2 = B1 + (J + 1), *B3 = B2 + (J + 1);
+    const int p0 = J >> 2;  // passes below p0 hold finished rows only
+    float4 t[4];
+#pragma unroll
+    for (int p = 0; p < 4; p++) t[p] = p >= p0 ? reinterpret_cast<const float4 *>(rowp[p])[J] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int k = 0; k < J; k++) {
+      const float4 b0 = B0[k], b1 = B1[k], b2 = B2[k], b3 = B3[k];
+#pragma unroll
+      for (int p = 0; p < 4; p++)
+        if (p >= p0) {
+          const float4 a = reinterpret_cast<const float4 *>(rowp[p])[k];
+          t[p].x = sub_dot4(a, b0, t[p].x); t[p].y = sub_dot4(a, b1, t[p].y);
+          t[p].z = sub_dot4(a, b2, t[p].z); t[p].w = sub_dot4(a, b3, t[p].w);
+        }
+    }
+    const int src = (4 * J) & 15;
+    const float4 ts = p0 == 0 ? t[0] : p0 == 1 ? t[1] : p0 == 2 ? t[2] : t[3];
+    const float d00 = __shfl_sync(0xffffffffu, ts.x, src, 16);
+    const float d10 = __shfl_sync(0xffffffffu, ts.x, src + 1, 16), d11 = __shfl_sync(0xffffffffu, ts.y, src + 1, 16);
+    const float d20 = __shfl_sync(0xffffffffu, ts.x, src + 2, 16), d21 = __shfl_sync(0xffffffffu, ts.y, src + 2, 16),
+                d22 = __shfl_sync(0xffffffffu, ts.z, src + 2, 16);
+    const float d30 = __shfl_sync(0xffffffffu, ts.x, src + 3, 16), d31 = __shfl_sync(0xffffffffu, ts.y, src + 3, 16),
+                d32 = __shfl_sync(0xffffffffu, ts.z, src + 3, 16), d33 = __shfl_sync(0xffffffffu, ts.w, src + 3, 16);
+    Blk4 b;
+    b.i0 = rsqrt_nr(d00);
+    b.l10 = d10 * b.i0; b.l20 = d20 * b.i0; b.l30 = d30 * b.i0;
+    b.i1 = rsqrt_nr(fmaf(-b.l10, b.l10, d11));
+    b.l21 = fmaf(-b.l20, b.l10, d21) * b.i1;
+    b.l31 = fmaf(-b.l30, b.l10, d31) * b.i1;
+    b.i2 = rsqrt_nr(fmaf(-b.l21, b.l21, fmaf(-b.l20, b.l20, d22)));
+    b.l32 = fmaf(-b.l31, b.l21, fmaf(-b.l30, b.l20, d32)) * b.i2;
+    b.i3 = rsqrt_nr(fmaf(-b.l32, b.l32, fmaf(-b.l31, b.l31, fmaf(-b.l30, b.l30, d33))));
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+      if (p >= p0 && q + 16 * p >= 4 * J) reinterpret_cast<float4 *>(rowp[p])[J] = blk_solve(b, t[p]);
+    if (q == 0) reinterpret_cast<float4 *>(dinv)[J] = make_float4(b.i0, b.i1, b.i2, b.i3);
+    __syncwarp();
+  }
+  const float *bv = M + kRecG;
+  float y[4];
+#pragma unroll
+  for (int p = 0; p < 4; p++) y[p] = bv[q + 16 * p];
+#pragma unroll 1
+  for (int J = 0; J < 16; J++) {
+    const float4 *B0 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J));
+    const float4 q1 = B0[2 * J + 1], q2 = B0[3 * J + 2], q3 = B0[4 * J + 3];
+    const float4 di = reinterpret_cast<const float4 *>(dinv)[J];
+    const int p0 = J >> 2, src = (4 * J) & 15;
+    const float sel = p0 == 0 ? y[0] : p0 == 1 ? y[1] : p0 == 2 ? y[2] : y[3];
+    const float c0 = __shfl_sync(0xffffffffu, sel, src, 16), c1 = __shfl_sync(0xffffffffu, sel, src + 1, 16),
+                c2 = __shfl_sync(0xffffffffu, sel, src + 2, 16), c3 = __shfl_sync(0xffffffffu, sel, src + 3, 16);
+    float4 z;
+    z.x = c0 * di.x;
+    z.y = fmaf(-q1.x, z.x, c1) * di.y;
+    z.z = fmaf(-q2.y, z.y, fmaf(-q2.x, z.x, c2)) * di.z;
+    z.w = fmaf(-q3.z, z.z, fmaf(-q3.y, z.y, fmaf(-q3.x, z.x, c3))) * di.w;
+    const bool owner = (q >> 2) == (J & 3);
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+      if (p >= p0) {
+        if (q + 16 * p > 4 * J + 3) y[p] = sub_dot4(reinterpret_cast<const float4 *>(rowp[p])[J], z, y[p]);
+        if (p == p0 && owner) y[p] = pick4(z, q & 3);
+      }
+  }
+#pragma unroll 1
+  for (int J = 15; J >= 0; J--) {
+    const float *S0 = M + chol_row_off(4 * J);
+    const float *S1 = S0 + 4 * (J + 1), *S2 = S1 + 4 * (J + 1), *S3 = S2 + 4 * (J + 1);
+    const float4 q1 = reinterpret_cast<const float4 *>(S1)[J], q2 = reinterpret_cast<const float4 *>(S2)[J],
+                 q3 = reinterpret_cast<const float4 *>(S3)[J];
+    const float4 di = reinterpret_cast<const float4 *>(dinv)[J];
+    const int p0 = J >> 2, src = (4 * J) & 15;
+    const float sel = p0 == 0 ? y[0] : p0 == 1 ? y[1] : p0 == 2 ? y[2] : y[3];
+    const float c0 = __shfl_sync(0xffffffffu, sel, src, 16), c1 = __shfl_sync(0xffffffffu, sel, src + 1, 16),
+                c2 = __shfl_sync(0xffffffffu, sel, src + 2, 16), c3 = __shfl_sync(0xffffffffu, sel, src + 3, 16);
+    float4 v;
+    v.w = c3 * di.w;
+    v.z = fmaf(-q3.z, v.w, c2) * di.z;
+    v.y = fmaf(-q3.y, v.w, fmaf(-q2.y, v.z, c1)) * di.y;
+    v.x = fmaf(-q3.x, v.w, fmaf(-q2.x, v.z, fmaf(-q1.x, v.y, c0))) * di.x;
+    const bool owner = (q >> 2) == (J & 3);
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+      if (p <= p0) {
+        const int r = q + 16 * p;
+        if (r < 4 * J) y[p] = fmaf(-S3[r], v.w, fmaf(-S2[r], v.z, fmaf(-S1[r], v.y, fmaf(-S0[r], v.x, y[p]))));
+        if (p == p0 && owner) y[p] = pick4(v, q & 3);
+      }
+  }
+#pragma unroll
+  for (int p = 0; p < 4; p++) x[p] = y[p];
+}
+
 // NW warps per CTA, NB record buffers per warp (2: the next record is fetched while the current one is solved; 1: more
 // warps fit the shared memory and hide each other's fetches)
 template <int NW, int NB>
@@ -288,6 +398,73 @@ __global__ void __launch_bounds__(NW * 32, 1) als_chol64_kernel(const CholArgs a
   }
 }
 
+// Two jobs per warp and round (halfwarp_chol64): jobs 2i and 2i + 1 of the warp's stride share a warp; a half whose
+// job has nothing to solve (segment of a split row, or past the end) idles through the round on whatever its buffer holds.
+template <int NW>
+struct Chol2Cfg {
+  static constexpr uint32_t warp_bytes = 2 * kRecBytes + 512;  // two records + two inverse diagonals
+  static constexpr uint32_t smem = NW * warp_bytes + NW * 16 + 128;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+};
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1) als_chol64x2_kernel(const CholArgs a) {
+  using C = Chol2Cfg<NW>;
+  extern __shared__ __align__(128) uint8_t smraw[];
+  uint8_t *smb = smraw + ((128u - (smem_u32(smraw) & 127u)) & 127u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, h = lane >> 4, q = lane & 15;
+  uint8_t *mine = smb + (size_t)warp * C::warp_bytes;
+  float *M = reinterpret_cast<float *>(mine + h * kRecBytes);
+  float *dinv = reinterpret_cast<float *>(mine + 2 * kRecBytes + h * 256);
+  const uint32_t bar = smem_u32(smb + (size_t)NW * C::warp_bytes) + warp * 16;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int n_pairs = (a.n_jobs + 1) / 2;
+  uint32_t ph = 0u;
+  for (int pr = (int)blockIdx.x * NW + warp; pr < n_pairs; pr += (int)gridDim.x * NW) {
+    const int j = 2 * pr + h;
+    const bool valid = j < a.n_jobs && !(j < a.n_seg && a.seg_slot[j] >= 0);
+    const unsigned vm = __ballot_sync(0xffffffffu, valid);
+    const bool v0 = (vm & 1u) != 0, v1 = (vm & 0x10000u) != 0;
+    if (!v0 && !v1) continue;
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive_expect_tx(bar, (v0 ? kRecBytes : 0u) + (v1 ? kRecBytes : 0u));
+      if (v0) bulk_g2s(smem_u32(mine), a.rec + (size_t)(2 * pr) * kRecFloats, kRecBytes, bar);
+      if (v1) bulk_g2s(smem_u32(mine + kRecBytes), a.rec + (size_t)(2 * pr + 1) * kRecFloats, kRecBytes, bar);
+    }
+    mbar_wait(bar, ph);
+    ph ^= 1u;
+    float x[4];
+    halfwarp_chol64(M, dinv, q, a.rank, a.reg, x);
+    if (valid) {
+      const int row = j < a.n_seg ? a.seg_row[j] : a.multi_row[j - a.n_seg];
+#pragma unroll
+      for (int p = 0; p < 4; p++) {
+        const int d = q + 16 * p;
+        const float v = d < a.rank ? x[p] : 0.f;
+        if (d < a.ld) {
+          a.Fout[(size_t)row * a.ld + d] = v;
+          for (int pp = 0; pp < a.n_peer; pp++) a.Fpeer[pp][(size_t)row * a.ld + d] = v;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int NW>
+int launch_chol64x2_cfg(mfb_engine *e, const CholArgs &c) {
+  using C = Chol2Cfg<NW>;
+  MFB_CUDA(cudaFuncSetAttribute((als_chol64x2_kernel<NW>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
+  const int n_pairs = (c.n_jobs + 1) / 2;
+  const int grid = std::min(e->sm_count, (n_pairs + NW - 1) / NW);
+  MFB_LAUNCH((als_chol64x2_kernel<NW>), grid, NW * 32, C::smem, e->stream, c);
+  return 0;
+}
+
 template <int NW, int NB>
 int launch_chol64_cfg(mfb_engine *e, const CholArgs &c) {
   using C = CholCfg<NW, NB>;
@@ -303,7 +480,9 @@ int launch_chol64(mfb_engine *e, const CholArgs &c) {
     case 12: return launch_chol64_cfg<12, 2>(e, c);
     case 16: return launch_chol64_cfg<16, 1>(e, c);
     case 20: return launch_chol64_cfg<20, 1>(e, c);
-    default: return launch_chol64_cfg<24, 1>(e, c);
+    case 24: return launch_chol64_cfg<24, 1>(e, c);
+    case 208: return launch_chol64x2_cfg<8>(e, c);
+    default: return launch_chol64x2_cfg<12>(e, c);  // 212: two matrices per warp, 12 warps
   }
 }
 
@@ -330,10 +509,15 @@ __global__ void __launch_bounds__(256) als_split_kernel(const float *__restrict_
 constexpr int kGnKT = 32;                     // ratings per tile
 constexpr uint32_t kGnBlock = 4096;           // one operand block: 32 dims x 32 ratings (LBO: stride between 32-dim blocks)
 constexpr uint32_t kGnSbo = 512;              // 4 ratings x 128 bytes (stride between groups of 4 ratings)
-constexpr uint32_t kGnStage = 5 * kGnBlock;   // big 0-31 | big 32-63 | small 0-31 | small 32-63 | ratings (n = 0: r_big, n = 1: r_small)
-constexpr int kGnStages = 8;
-constexpr int kGnDepth = 6;                   // tiles whose copies a producer thread keeps in flight (< kGnStages)
-constexpr int kGnMeta = 8;                    // (item, rating) of a tile is requested this many tiles ahead (> kGnDepth: it rides in an
+constexpr uint32_t kGnStage = 5 * kGnBlock;   // small 0-31 | small 32-63 | big 0-31 | big 32-63 | ratings (n = 0: r_big, n = 1: r_small).
+                                              // A = all four blocks (M = 128: rows 0-63 small, 64-127 big); B starts at the big
+                                              // blocks and runs into the ratings block (N = 80): ONE tcgen05.mma per 8 ratings gives
+                                              // small big^T, big big^T and both products of the right-hand side — the kernel is bound
+                                              // by shared-memory bandwidth (profiles/r2_als_mn.md) and a second MMA for the
+                                              // right-hand side re-read the 4 KB of A
+constexpr int kGnStages = 9;
+constexpr int kGnDepth = 7;                   // tiles whose copies a producer thread keeps in flight (< kGnStages)
+constexpr int kGnMeta = 9;                    // (item, rating) of a tile is requested this many tiles ahead (> kGnDepth: it rides in an
                                               // earlier commit group than the one that is waited for before it is read)
 constexpr int kGnProducers = 128;             // thread t: ratings t / 8 and t / 8 + 16 of the tile, chunk t % 8 of every 128-byte block of their split rows
 constexpr int kGnAcc = 4;                     // accumulators in TMEM: row i -> i mod 4
@@ -345,8 +529,8 @@ constexpr int kGnFirst = 1, kGnLast = 2;
 
 struct GramSmem {
   static constexpr uint32_t off_stage = 0;
-  static constexpr uint32_t off_rec = off_stage + kGnStages * kGnStage;               // [teams][2] record staging
-  static constexpr uint32_t off_tmp = off_rec + kGnDrainTeams * 2 * kRecBytes;        // [teams][64] small x r_big
+  static constexpr uint32_t off_rec = off_stage + kGnStages * kGnStage;               // [teams] record staging
+  static constexpr uint32_t off_tmp = off_rec + kGnDrainTeams * kRecBytes;        // [teams][64] small x r_big
   static constexpr uint32_t off_meta = off_tmp + kGnDrainTeams * 64 * 4;              // [kGnMeta][producers] {item, rating} x 2: thread-private ring
   static constexpr uint32_t off_tflags = off_meta + kGnMeta * kGnProducers * 16;     // [kGnMeta] flags of the tiles the cursor has visited
   static constexpr uint32_t off_info = off_tflags + kGnMeta * 4;                      // [stages] tile flags
@@ -365,6 +549,7 @@ struct GramArgs {
   const float *val;
   const int32_t *seg_start, *seg_len, *seg_slot;
   int nseg;             // segments [0, nseg) of the plan (longest first); CTA b takes b, b + grid, ...
+  int debug_mode;       // timing experiments (results are wrong): 1 = every rating gathers row (item & 1023): L2-hot rows
   float *rec;           // [nseg + split rows][kRecFloats]
 };
 
@@ -484,7 +669,7 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
     const int o = tid >> 3, cg = tid & 7;
     const uint32_t kq = (uint32_t)o & 3u;
     const uint32_t base_off = (uint32_t)(o >> 2) * kGnSbo + kq * 128u + ((((uint32_t)cg >> 1) ^ kq) << 5) + ((uint32_t)cg & 1u) * 16u;
-    const uint32_t roff = 4u * kGnBlock + (uint32_t)(o >> 2) * kGnSbo + kq * 128u + (kq << 5);
+    const uint32_t roff = 4u * kGnBlock + (uint32_t)(o >> 2) * kGnSbo + kq * 128u + (kq << 5);  // n = 0, 1 of rating o in the ratings block
     constexpr uint32_t kSecond = 4u * kGnSbo;  // rating + 16: four groups of 4 ratings further
     // {item, rating} x 2 of tile x: requested kGnMeta tiles ahead with 4-byte cp.async into the thread's own ring slot (no
     // other thread reads it), in the commit group of tile x - kGnMeta; that group has been waited for (wait_group kGnDepth
@@ -534,10 +719,10 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const bool on = rts[e] > 0.f;  // rating > 0 filter (modelMF.cpp:819); beyond the row's end the ring holds 0
-          const float *src = a.Fs + (size_t)(on ? its[e] : a.zero_row) * 128 + cg * 4;
+          const float *src = a.Fs + (size_t)(on ? (a.debug_mode == 1 ? (its[e] & 1023) : its[e]) : a.zero_row) * 128 + cg * 4;
 #pragma unroll
           for (int i = 0; i < 4; i++)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + base_off + e * kSecond + i * kGnBlock), "l"(src + 32 * i) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + base_off + e * kSecond + ((i + 2) & 3) * kGnBlock), "l"(src + 32 * i) : "memory");  // big -> blocks 2, 3; small -> 0, 1
           if (cg == 0) {
             const float rb = on ? round_tf32_fast(rts[e]) : 0.f;
             const float rs = on ? rts[e] - rb : 0.f;
@@ -559,9 +744,8 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
     }
   } else if (tid < kGnDrain0) {
     // ================================= tensor-core issue =================================
-    // instruction descriptors: D = F32, A = B = TF32, both MN-major; M = 128; N = 64 (Gram) / 16 (right-hand side)
-    constexpr uint32_t idesc_g = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-    constexpr uint32_t idesc_r = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+    // instruction descriptor: D = F32, A = B = TF32, both MN-major; M = 128 ([small; big]), N = 80 ([big | r_big r_small 0 ..])
+    constexpr uint32_t idesc_g = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((80u >> 3) << 17) | ((128u >> 4) << 24);
     const uint64_t desc0 = umma_desc_mn(sbase + S::off_stage);
     int os = 0, acc = 0, gen = 0;
     uint32_t ph = 0;
@@ -577,9 +761,7 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
 #pragma unroll
         for (int k8 = 0; k8 < kGnKT / 8; k8++) {
           const uint64_t dk = descs + (uint64_t)(k8 * ((2 * kGnSbo) >> 4));
-          const uint32_t accum = (first && k8 == 0) ? 0u : 1u;
-          umma_tf32(dt, dk, dk, idesc_g, accum);
-          umma_tf32(dt + 64, dk, dk + (uint64_t)((4 * kGnBlock) >> 4), idesc_r, accum);
+          umma_tf32(dt, dk, dk + (uint64_t)((2 * kGnBlock) >> 4), idesc_g, (first && k8 == 0) ? 0u : 1u);
         }
         umma_commit(bar_ope + os * 8);
         if (last) umma_commit(bar_accf + acc * 8);
@@ -597,6 +779,7 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
     const int dt = tid - kGnDrain0, team = dt >> 7, t = dt & 127;
     const int p = 32 * ((tid >> 5) & 3) + lane;  // TMEM lane this thread may read (its warp's quadrant)
     const int arow = p & 63;
+    const bool bb = p >= 64;  // accumulator rows 64 .. 127 = big x [big | ratings], rows 0 .. 63 = small x [big | ratings]
     float *tmp = reinterpret_cast<float *>(smb + S::off_tmp) + team * 64;
     const int bar_id = 1 + team;
     auto team_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
@@ -606,8 +789,8 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
       const uint32_t par = (uint32_t)(i / kGnAcc) & 1u;
       const int seg = (int)blockIdx.x + i * (int)gridDim.x;
       const int slot = a.seg_slot[seg];
-      float *Sr = reinterpret_cast<float *>(smb + S::off_rec + (uint32_t)(team * 2 + (n & 1)) * kRecBytes);
-      if (t == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the store that read this buffer two rows ago
+      float *Sr = reinterpret_cast<float *>(smb + S::off_rec + (uint32_t)team * kRecBytes);
+      if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous row's store has read the buffer
       mbar_wait_parked(bar_accf + acc * 8, par, 20000u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tad = tmem_base + (uint32_t)acc * kGnAccCols + ((uint32_t)(p & ~31) << 16);
@@ -625,7 +808,7 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
       mbar_arrive(bar_acce + acc * 8);  // everything of this accumulator is in registers
       team_bar();                        // the staging buffer is free (thread 0 has waited for its last store)
       float4 *rowp = reinterpret_cast<float4 *>(Sr + chol_row_off(arow));
-      if (p < 64) {  // big big^T: units 0 .. arow / 4 of row arow
+      if (bb) {  // big big^T: units 0 .. arow / 4 of row arow
 #pragma unroll
         for (int u = 0; u < 16; u++)
           if (4 * u <= arow)
@@ -634,7 +817,7 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
         tmp[arow] = __uint_as_float(r0);  // small x r_big
       }
       team_bar();
-      if (p >= 64) {  // + small big^T, lower part of row arow (the diagonal once here, once below)
+      if (!bb) {  // + small big^T, lower part of row arow (the diagonal once here, once below)
 #pragma unroll
         for (int u = 0; u < 16; u++)
           if (4 * u <= arow) {
@@ -647,7 +830,7 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
         Sr[kRecG + arow] = __uint_as_float(r0) + __uint_as_float(r1) + tmp[arow];  // big r_big + big r_small + small r_big
       }
       team_bar();
-      if (p >= 64) {  // + (small big^T)^T: G(c, arow) += SB[arow][c] for c >= arow
+      if (!bb) {  // + (small big^T)^T: G(c, arow) += SB[arow][c] for c >= arow
 #pragma unroll
         for (int c = 0; c < 64; c++)
           if (c >= arow) Sr[chol_row_off(c) + arow] += __uint_as_float(v[c]);
@@ -715,6 +898,7 @@ int als_mn_half_step(mfb_engine *e, const AlsArgs &a, const SegPlan &sp, int n_p
   g.ind = a.ind; g.val = a.val;
   g.seg_start = a.seg_start; g.seg_len = a.seg_len; g.seg_slot = a.seg_slot;
   g.nseg = n_primal;
+  g.debug_mode = e->opt_als_debug;
   g.rec = rec;
   MFB_CUDA(cudaFuncSetAttribute(als_gram_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GramSmem::bytes));
   const int grid = std::min(e->sm_count, n_primal);

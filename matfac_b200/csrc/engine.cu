@@ -805,6 +805,7 @@ extern "C" int mfb_set_option(mfb_engine *e, const char *name, double value) {
   else if (n == "als_dual") e->opt_als_dual = (int)value;
   else if (n == "als_ws_split") e->opt_als_ws_split = (int)value;
   else if (n == "als_chol_warps") e->opt_als_chol_warps = (int)value;
+  else if (n == "als_debug") e->opt_als_debug = (int)value;
   else if (n == "copy_overlap") e->opt_copy_overlap = (int)value;
   else if (n == "rank_tensor_cores") e->opt_rank_tensor_cores = (int)value;
   else if (n == "als_chunk") {

@@ -613,26 +613,31 @@ def chol64_records(G, b):
     return rec
 
 
+@pytest.mark.parametrize("cfg", [0, 12, 24])
 @pytest.mark.parametrize("rank", [64, 50, 33])
-def test_batched_chol64_matches_float64_solve(rank):
+def test_batched_chol64_matches_float64_solve(rank, cfg):
     """als_chol64_kernel (one warp per matrix, blocked left-looking Cholesky) against numpy's float64 solve on Gram matrices of
-    random factor rows: more matrices than one wave of warps, short and long rows, padded ranks."""
+    random factor rows: more matrices than one wave of warps, short and long rows, padded ranks.  cfg = option als_chol_warps:
+    0 = default (two matrices per warp), 12 = one matrix per warp with two record buffers, 24 = one matrix, one buffer, 24 warps."""
     rng = np.random.default_rng(7)
-    n = 5000
+    n = 5001
     G = np.zeros((n, 64, 64), np.float64); b = np.zeros((n, 64), np.float64)
-    for lo in range(0, n, 500):
+    for lo in range(0, 5000, 500):
         k = int(rng.integers(40, 400))
         X = np.zeros((500, k, 64), np.float32)
         X[:, :, :rank] = rng.normal(size=(500, k, rank)).astype(np.float32) * 0.3
         r = rng.uniform(1, 5, size=(500, k)).astype(np.float32)
         G[lo:lo + 500] = np.einsum("nkr,nks->nrs", X.astype(np.float64), X.astype(np.float64))
         b[lo:lo + 500] = np.einsum("nk,nkr->nr", r.astype(np.float64), X.astype(np.float64))
+    G[5000] = G[0]; b[5000] = b[0]  # an odd number of matrices: the last warp of the paired variant solves one
     reg = 0.1
     A = G.copy()
     for d in range(64):
         A[:, d, d] = A[:, d, d] + reg if d < rank else 1.0
     want = np.linalg.solve(A, b[:, :, None])[:, :, 0]
     eng = E.Engine(10, 10, rank)
+    if cfg:
+        eng.set_option("als_chol_warps", cfg)
     x = eng.debug_chol64(chol64_records(G.astype(np.float32), b.astype(np.float32)), rank, reg)
     eng.close()
     assert np.all(x[:, rank:] == 0)

@@ -90,6 +90,9 @@ def main():
         eng.set_option("als_tensor_cores", args.tc)
         eng.set_option("als_dual", int(os.environ.get("ALS_DUAL", "1")))
         eng.set_option("als_ws_split", int(os.environ.get("ALS_WS_SPLIT", "0")))
+        if "ALS_DEBUG" in os.environ:
+            eng.set_option("als_debug", int(os.environ["ALS_DEBUG"]))
+            out["als_debug"] = int(os.environ["ALS_DEBUG"])
         if "ALS_CHOL_WARPS" in os.environ:
             eng.set_option("als_chol_warps", int(os.environ["ALS_CHOL_WARPS"]))
             out["als_chol_warps"] = int(os.environ["ALS_CHOL_WARPS"])
