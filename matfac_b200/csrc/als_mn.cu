@@ -516,10 +516,10 @@ constexpr uint32_t kGnStage = 5 * kGnBlock;   // small 0-31 | small 32-63 | big 
                                               // by shared-memory bandwidth (profiles/r2_als_mn.md) and a second MMA for the
                                               // right-hand side re-read the 4 KB of A
 constexpr int kGnStages = 9;
-constexpr int kGnDepth = 7;                   // tiles whose copies a producer thread keeps in flight (< kGnStages)
-constexpr int kGnMeta = 9;                    // (item, rating) of a tile is requested this many tiles ahead (> kGnDepth: it rides in an
-                                              // earlier commit group than the one that is waited for before it is read)
-constexpr int kGnProducers = 128;             // thread t: ratings t / 8 and t / 8 + 16 of the tile, chunk t % 8 of every 128-byte block of their split rows
+constexpr int kGnProducers = 128;             // 4 producer warps, each owns every 4th tile
+constexpr int kGnAhead = 4;                   // a warp requests the (item, rating) pairs of its tile y + 4 while it copies tile y; it waits
+                                              // for its commit group y - 3 at the end of iteration y (pairs of tile y + 1 ready, at most
+                                              // four of its tiles in flight) but never for the stage it has just filled
 constexpr int kGnAcc = 4;                     // accumulators in TMEM: row i -> i mod 4
 constexpr int kGnAccCols = 128;               // D in columns [0, 64), D2 in [64, 80)
 constexpr int kGnDrainTeams = 2;              // row i is drained by team i mod 2 (4 warps, one per TMEM lane quadrant)
@@ -531,15 +531,16 @@ struct GramSmem {
   static constexpr uint32_t off_stage = 0;
   static constexpr uint32_t off_rec = off_stage + kGnStages * kGnStage;               // [teams] record staging
   static constexpr uint32_t off_tmp = off_rec + kGnDrainTeams * kRecBytes;        // [teams][64] small x r_big
-  static constexpr uint32_t off_meta = off_tmp + kGnDrainTeams * 64 * 4;              // [kGnMeta][producers] {item, rating} x 2: thread-private ring
-  static constexpr uint32_t off_tflags = off_meta + kGnMeta * kGnProducers * 16;     // [kGnMeta] flags of the tiles the cursor has visited
-  static constexpr uint32_t off_info = off_tflags + kGnMeta * 4;                      // [stages] tile flags
-  static constexpr uint32_t off_bars = off_info + kGnStages * 4;                      // op_full | op_empty | acc_full | acc_empty
+  static constexpr uint32_t off_meta = off_tmp + kGnDrainTeams * 64 * 4;              // [producer warps][kGnAhead][32] {item, rating}: warp-private rings
+  static constexpr uint32_t off_tflags = off_meta + (kGnProducers / 32) * kGnAhead * 256;  // [producer warps][kGnAhead] flags of the tiles a cursor has visited
+  static constexpr uint32_t off_info = off_tflags + (kGnProducers / 32) * kGnAhead * 4;                    // [stages] tile flags
+  static constexpr uint32_t off_bars = (off_info + kGnStages * 4 + 15u) & ~15u;                     // op_full | op_empty | acc_full | acc_empty
   static constexpr int n_bars = 2 * kGnStages + 2 * kGnAcc;
   static constexpr uint32_t off_tmem = off_bars + n_bars * 8;
   static constexpr size_t bytes = off_tmem + 16 + 1024;
   static_assert(bytes <= 227 * 1024, "shared memory budget");
-  static_assert(kGnMeta > kGnDepth && kGnDepth < kGnStages, "pipeline depths");
+  static_assert(off_bars % 8 == 0 && off_meta % 16 == 0 && off_rec % 16 == 0, "alignment of mbarriers / rings / bulk-copy source");
+  static_assert(kGnAhead >= 2, "pipeline depths");
 };
 
 struct GramArgs {
@@ -549,7 +550,8 @@ struct GramArgs {
   const float *val;
   const int32_t *seg_start, *seg_len, *seg_slot;
   int nseg;             // segments [0, nseg) of the plan (longest first); CTA b takes b, b + grid, ...
-  int debug_mode;       // timing experiments (results are wrong): 1 = every rating gathers row (item & 1023): L2-hot rows
+  int debug_mode;       // timing experiments (results are wrong): 1 = every rating gathers row (item & 1023): L2-hot rows;
+                        // 2 = no factor-row copies at all (the MMAs read stale stages); 3 = copies, but no MMAs (commits only)
   float *rec;           // [nseg + split rows][kRecFloats]
 };
 
@@ -615,7 +617,7 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
 
   if (tid == 0) {
     for (int i = 0; i < kGnStages; i++) {
-      mbar_init(bar_opf + i * 8, kGnProducers / 32);
+      mbar_init(bar_opf + i * 8, 33);  // the owning producer warp: 32 cp.async completions + lane 0
       mbar_init(bar_ope + i * 8, 1);
     }
     for (int i = 0; i < kGnAcc; i++) {
@@ -641,9 +643,15 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
 
   if (tid < kGnProducers) {
     // ================================= producers =================================
-    // ONE cursor walks the tiles of this CTA's rows (row i = segment blockIdx.x + i * gridDim.x), kGnMeta tiles ahead of
-    // the copies: it requests the (item, rating) pairs of a tile and records the tile's flags; the bounds of the next two
-    // rows are fetched when a row is entered (a whole row of lead time for the dependent loads).
+    // Every producer WARP owns whole tiles: warp w copies global tiles w, w + NPW, ... — the warps run independently of
+    // each other.  (With all warps co-operating on every tile the kernel ran at the latency of ONE warp's ~170-instruction
+    // loop per tile: removing the copies or the MMAs altogether did not change its time, profiles/r2_als_mn.md.)
+    // Lane l = (o8 = l / 8, c = l % 8): chunk c of each of the four 128-byte blocks of the split rows of ratings o8, o8 + 4, ...,
+    // o8 + 28 of the tile — eight neighbouring lanes copy one contiguous 128-byte block of one rating, its swizzled destination
+    // covers all 32 banks.  A warp-private cursor walks the warp's tiles kGnAhead of them ahead of the copies and requests
+    // their (item, rating) pairs (lane l: pair l of the tile) into a warp-private ring.
+    constexpr int NPW = kGnProducers / 32;
+    const int w = tid >> 5;
     struct Cursor { int i, t, ntiles, start, len, s1, l1, s2, l2; };
     auto load_seg = [&](int i, int &st_, int &ln_) {
       st_ = ln_ = 0;
@@ -663,36 +671,25 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
         load_seg(c.i + 2, c.s2, c.l2);
       }
     };
-    // thread t: chunk t % 8 of each of the four 128-byte blocks of the split rows of ratings t / 8 and t / 8 + 16 of the tile.
-    // Eight neighbouring lanes copy one contiguous 128-byte block of one rating; its swizzled destination covers all 32
-    // banks, so a warp's copy is written in the minimum of four shared-memory wavefronts.
-    const int o = tid >> 3, cg = tid & 7;
-    const uint32_t kq = (uint32_t)o & 3u;
-    const uint32_t base_off = (uint32_t)(o >> 2) * kGnSbo + kq * 128u + ((((uint32_t)cg >> 1) ^ kq) << 5) + ((uint32_t)cg & 1u) * 16u;
-    const uint32_t roff = 4u * kGnBlock + (uint32_t)(o >> 2) * kGnSbo + kq * 128u + (kq << 5);  // n = 0, 1 of rating o in the ratings block
-    constexpr uint32_t kSecond = 4u * kGnSbo;  // rating + 16: four groups of 4 ratings further
-    // {item, rating} x 2 of tile x: requested kGnMeta tiles ahead with 4-byte cp.async into the thread's own ring slot (no
-    // other thread reads it), in the commit group of tile x - kGnMeta; that group has been waited for (wait_group kGnDepth
-    // at iteration x - 1 covers groups <= x - 1 - kGnDepth) before iteration x reads it
-    const uint32_t meta0 = sbase + S::off_meta + (uint32_t)tid * 16u;
-    const int4 *meta_ptr = reinterpret_cast<const int4 *>(smb + S::off_meta) + tid;
-    int *tflags = reinterpret_cast<int *>(smb + S::off_tflags);
-    int n_tiles = -1;
-    auto request_meta = [&](const Cursor &c, int x) {
+    const int o8 = lane >> 3, cg = lane & 7;
+    const uint32_t base_off = (uint32_t)o8 * 128u + ((((uint32_t)cg >> 1) ^ (uint32_t)o8) << 5) + ((uint32_t)cg & 1u) * 16u;
+    const uint32_t roff = 4u * kGnBlock + (uint32_t)o8 * 128u + ((uint32_t)o8 << 5);  // n = 0, 1 of rating o8 (+ 4 m: + m * kGnSbo)
+    const uint32_t meta0 = sbase + S::off_meta + (uint32_t)w * (kGnAhead * 256u);     // [kGnAhead][32] {item, rating}
+    const int2 *meta_ptr = reinterpret_cast<const int2 *>(smb + S::off_meta) + w * (kGnAhead * 32);
+    int *tflags = reinterpret_cast<int *>(smb + S::off_tflags) + w * kGnAhead;
+    int ny = -1;  // number of this warp's tiles, known once the cursor has run off the end
+    auto request_meta = [&](const Cursor &c, int y) {  // y = index among this warp's tiles
       const bool alive = c.i < n_rows;
-      if (!alive && n_tiles < 0) n_tiles = x;
-      const uint32_t dst = meta0 + (uint32_t)(x % kGnMeta) * (kGnProducers * 16u);
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int jj = c.t * kGnKT + o + 16 * e;
-        if (alive && jj < c.len) {
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 8 * e), "l"(a.ind + c.start + jj) : "memory");
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 8 * e + 4), "l"(a.val + c.start + jj) : "memory");
-        } else {
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + 8 * e), "r"(0), "r"(0) : "memory");  // rating 0: filtered out
-        }
+      if (!alive && ny < 0) ny = y;
+      const uint32_t dst = meta0 + (uint32_t)(y % kGnAhead) * 256u + (uint32_t)lane * 8u;
+      const int jj = c.t * kGnKT + lane;
+      if (alive && jj < c.len) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(a.ind + c.start + jj) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4), "l"(a.val + c.start + jj) : "memory");
+      } else {
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(0), "r"(0) : "memory");  // rating 0: filtered out
       }
-      if (tid == 0) tflags[x % kGnMeta] = alive ? ((c.t == 0 ? kGnFirst : 0) | (c.t == c.ntiles - 1 ? kGnLast : 0)) : 0;
+      if (lane == 0) tflags[y % kGnAhead] = alive ? ((c.t == 0 ? kGnFirst : 0) | (c.t == c.ntiles - 1 ? kGnLast : 0)) : 0;
     };
     Cursor nxt;
     nxt.i = 0; nxt.t = 0;
@@ -700,48 +697,56 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
     nxt.ntiles = (nxt.len + kGnKT - 1) / kGnKT;
     load_seg(1, nxt.s1, nxt.l1);
     load_seg(2, nxt.s2, nxt.l2);
-    for (int x = 0; x < kGnMeta; x++) {
-      request_meta(nxt, x);
-      advance(nxt);
+    for (int k = 0; k < w; k++) advance(nxt);  // the warp's first tile is global tile w
+    for (int y = 0; y < kGnAhead; y++) {
+      request_meta(nxt, y);
+      for (int k = 0; k < NPW; k++) advance(nxt);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    for (int g = 0;; g++) {
-      const bool live = n_tiles < 0 || g < n_tiles;
+    __syncwarp();
+    for (int y = 0;; y++) {
+      const bool live = ny < 0 || y < ny;
       if (live) {
+        const int g = w + NPW * y;  // global tile: its operand stage and its place in the tensor-core warp's order
         const int stg = g % kGnStages;
-        const int4 mt = meta_ptr[(g % kGnMeta) * kGnProducers];
         if (g >= kGnStages) mbar_wait(bar_ope + stg * 8, (uint32_t)(g / kGnStages - 1) & 1u);  // the MMAs that read this stage are done
-        if (tid == 0) opinfo[stg] = tflags[g % kGnMeta];  // only now: the tensor-core warp has read the previous tile's flags
+        if (lane == 0) opinfo[stg] = tflags[y % kGnAhead];  // only now: the tensor-core warp has read the previous tile's flags
         const uint32_t dst0 = sbase + S::off_stage + (uint32_t)stg * kGnStage;
-        const int its[2] = {mt.x, mt.z};
-        const float rts[2] = {__int_as_float(mt.y), __int_as_float(mt.w)};
+        const int2 *mp = meta_ptr + (y % kGnAhead) * 32 + o8;
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const bool on = rts[e] > 0.f;  // rating > 0 filter (modelMF.cpp:819); beyond the row's end the ring holds 0
-          const float *src = a.Fs + (size_t)(on ? (a.debug_mode == 1 ? (its[e] & 1023) : its[e]) : a.zero_row) * 128 + cg * 4;
+        for (int m = 0; m < 8; m++) {
+          const int2 mt = mp[4 * m];  // rating 4 m + o8 of the tile
+          const float rt = __int_as_float(mt.y);
+          const bool on = rt > 0.f;  // rating > 0 filter (modelMF.cpp:819); beyond the row's end the ring holds 0
+          const int row = on ? (a.debug_mode == 1 ? (mt.x & 1023) : mt.x) : a.zero_row;
+          const float *src = a.Fs + (size_t)row * 128 + cg * 4;
+          if (a.debug_mode != 2) {
 #pragma unroll
-          for (int i = 0; i < 4; i++)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + base_off + e * kSecond + ((i + 2) & 3) * kGnBlock), "l"(src + 32 * i) : "memory");  // big -> blocks 2, 3; small -> 0, 1
+            for (int i = 0; i < 4; i++)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + base_off + m * kGnSbo + ((i + 2) & 3) * kGnBlock), "l"(src + 32 * i) : "memory");  // big -> blocks 2, 3; small -> 0, 1
+          }
           if (cg == 0) {
-            const float rb = on ? round_tf32_fast(rts[e]) : 0.f;
-            const float rs = on ? rts[e] - rb : 0.f;
-            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(dst0 + roff + e * kSecond), "f"(rb), "f"(rs) : "memory");
+            const float rb = on ? round_tf32_fast(rt) : 0.f;
+            const float rs = on ? rt - rb : 0.f;
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(dst0 + roff + m * kGnSbo), "f"(rb), "f"(rs) : "memory");
           }
         }
-        request_meta(nxt, g + kGnMeta);  // into the slot that was just read
-        advance(nxt);
+        // the stage is full when every lane's copies have landed (the hardware arrives for the lane then: the warp does not
+        // wait for its data) and lane 0 has arrived for the ratings / flags the lanes stored themselves
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_opf + stg * 8) : "memory");
+        __syncwarp();                        // every lane has read the ring slot that is refilled now, and stored its ratings
+        if (lane == 0) mbar_arrive(bar_opf + stg * 8);
+        request_meta(nxt, y + kGnAhead);
+        for (int k = 0; k < NPW; k++) advance(nxt);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      const int gd = g - kGnDepth;
-      if (gd >= 0) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(kGnDepth) : "memory");  // this thread's copies of tile gd have landed
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_opf + (gd % kGnStages) * 8);
-      }
-      if (n_tiles >= 0 && gd >= n_tiles - 1) break;
+      // pairs requested with tile y - (kGnAhead - 1) are read in the next iteration; this also bounds a warp's copies in flight
+      asm volatile("cp.async.wait_group %0;" ::"n"(kGnAhead - 1) : "memory");
+      __syncwarp();
+      if (ny >= 0 && y >= ny - 1) break;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (tid < kGnDrain0) {
     // ================================= tensor-core issue =================================
     // instruction descriptor: D = F32, A = B = TF32, both MN-major; M = 128 ([small; big]), N = 80 ([big | r_big r_small 0 ..])
@@ -754,6 +759,7 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
       mbar_wait(bar_opf + os * 8, ph);
       const bool last = __any_sync(0xFFFFFFFFu, (opinfo[os] & kGnLast) != 0);
       if (first && gen > 0) mbar_wait(bar_acce + acc * 8, (uint32_t)(gen - 1) & 1u);  // accumulator drained
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the stage was written through the generic proxy (cp.async, st.shared)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one_sync()) {
         const uint32_t dt = tmem_base + (uint32_t)acc * kGnAccCols;
@@ -761,7 +767,7 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
 #pragma unroll
         for (int k8 = 0; k8 < kGnKT / 8; k8++) {
           const uint64_t dk = descs + (uint64_t)(k8 * ((2 * kGnSbo) >> 4));
-          umma_tf32(dt, dk, dk + (uint64_t)((2 * kGnBlock) >> 4), idesc_g, (first && k8 == 0) ? 0u : 1u);
+          if (a.debug_mode != 3) umma_tf32(dt, dk, dk + (uint64_t)((2 * kGnBlock) >> 4), idesc_g, (first && k8 == 0) ? 0u : 1u);
         }
         umma_commit(bar_ope + os * 8);
         if (last) umma_commit(bar_accf + acc * 8);
