@@ -229,7 +229,7 @@ __device__ __forceinline__ void halfwarp_chol64(float *M, float *dinv, int q, in
     float4 t[4];
 #pragma unroll
     for (int p = 0; p < 4; p++) t[p] = p >= p0 ? reinterpret_cast<const float4 *>(rowp[p])[J] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
+#pragma unroll 2
     for (int k = 0; k < J; k++) {
       const float4 b0 = B0[k], b1 = B1[k], b2 = B2[k], b3 = B3[k];
 #pragma unroll
@@ -551,7 +551,8 @@ struct GramArgs {
   const int32_t *seg_start, *seg_len, *seg_slot;
   int nseg;             // segments [0, nseg) of the plan (longest first); CTA b takes b, b + grid, ...
   int debug_mode;       // timing experiments (results are wrong): 1 = every rating gathers row (item & 1023): L2-hot rows;
-                        // 2 = no factor-row copies at all (the MMAs read stale stages); 3 = copies, but no MMAs (commits only)
+                        // 2 = no factor-row copies at all (the MMAs read stale stages); 3 = copies, but no MMAs (commits only);
+                        // 4 = the four MMAs of a tile go to four different accumulators
   float *rec;           // [nseg + split rows][kRecFloats]
 };
 
@@ -767,7 +768,8 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
 #pragma unroll
         for (int k8 = 0; k8 < kGnKT / 8; k8++) {
           const uint64_t dk = descs + (uint64_t)(k8 * ((2 * kGnSbo) >> 4));
-          if (a.debug_mode != 3) umma_tf32(dt, dk, dk + (uint64_t)((2 * kGnBlock) >> 4), idesc_g, (first && k8 == 0) ? 0u : 1u);
+          const uint32_t dtk = a.debug_mode == 4 ? tmem_base + (uint32_t)((acc + k8) % kGnAcc) * kGnAccCols : dt;  // 4: no accumulate chain
+          if (a.debug_mode != 3) umma_tf32(dtk, dk, dk + (uint64_t)((2 * kGnBlock) >> 4), idesc_g, (first && k8 == 0) ? 0u : 1u);
         }
         umma_commit(bar_ope + os * 8);
         if (last) umma_commit(bar_accf + acc * 8);
