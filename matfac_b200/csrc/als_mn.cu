@@ -574,6 +574,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_tf32_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {  // D += A B
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -751,10 +760,16 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
   } else if (tid < kGnDrain0) {
     // ================================= tensor-core issue =================================
     // instruction descriptor: D = F32, A = B = TF32, both MN-major; M = 128 ([small; big]), N = 80 ([big | r_big r_small 0 ..])
+    // This warp's loop is the pace of the kernel once the producers run ahead (profiles/r2_als_mn.md: a handful of extra
+    // instructions per MMA cost 10 %): the descriptors are {low word = address field that moves, high word = constant},
+    // advanced by 32-bit adds; the first MMA of a tile carries the accumulate predicate, the other three are unconditional.
     constexpr uint32_t idesc_g = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((80u >> 3) << 17) | ((128u >> 4) << 24);
     const uint64_t desc0 = umma_desc_mn(sbase + S::off_stage);
+    const uint32_t desc_hi = (uint32_t)(desc0 >> 32), lo0 = (uint32_t)desc0;
+    constexpr uint32_t kStep = (2 * kGnSbo) >> 4, kBoff = (2 * kGnBlock) >> 4, kStageStep = kGnStage >> 4;
+    const bool no_mma = a.debug_mode == 3;
     int os = 0, acc = 0, gen = 0;
-    uint32_t ph = 0;
+    uint32_t ph = 0, lo = lo0;
     bool first = true;
     for (int rows_done = 0; rows_done < n_rows;) {
       mbar_wait(bar_opf + os * 8, ph);
@@ -764,12 +779,12 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one_sync()) {
         const uint32_t dt = tmem_base + (uint32_t)acc * kGnAccCols;
-        const uint64_t descs = desc0 + (uint64_t)((uint32_t)os * (kGnStage >> 4));
-#pragma unroll
-        for (int k8 = 0; k8 < kGnKT / 8; k8++) {
-          const uint64_t dk = descs + (uint64_t)(k8 * ((2 * kGnSbo) >> 4));
-          const uint32_t dtk = a.debug_mode == 4 ? tmem_base + (uint32_t)((acc + k8) % kGnAcc) * kGnAccCols : dt;  // 4: no accumulate chain
-          if (a.debug_mode != 3) umma_tf32(dtk, dk, dk + (uint64_t)((2 * kGnBlock) >> 4), idesc_g, (first && k8 == 0) ? 0u : 1u);
+        if (!no_mma) {
+          auto dsc = [&](uint32_t l) { return ((uint64_t)desc_hi << 32) | l; };
+          umma_tf32(dt, dsc(lo), dsc(lo + kBoff), idesc_g, first ? 0u : 1u);
+          umma_tf32_acc(dt, dsc(lo + kStep), dsc(lo + kStep + kBoff), idesc_g);
+          umma_tf32_acc(dt, dsc(lo + 2 * kStep), dsc(lo + 2 * kStep + kBoff), idesc_g);
+          umma_tf32_acc(dt, dsc(lo + 3 * kStep), dsc(lo + 3 * kStep + kBoff), idesc_g);
         }
         umma_commit(bar_ope + os * 8);
         if (last) umma_commit(bar_accf + acc * 8);
@@ -780,7 +795,8 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
         rows_done++;
         if (++acc == kGnAcc) { acc = 0; gen++; }
       }
-      if (++os == kGnStages) { os = 0; ph ^= 1u; }
+      lo += kStageStep;
+      if (++os == kGnStages) { os = 0; ph ^= 1u; lo = lo0; }
     }
   } else {
     // ================================= drain teams =================================
