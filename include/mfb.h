@@ -191,9 +191,10 @@ int mfb_als_half_step(mfb_engine *e, int side, float reg);
 int mfb_debug_als_gram(mfb_engine *e, int side, int32_t row, float *out, int32_t *padded_rank);
 
 /* Diagnostics: the batched rank-64 solver of the ALS half-step (csrc/als_mn.cu) on n host records.  A record is
- * 2240 floats: the lower triangle of the Gram matrix row by row, row r at float offset 4 (r/4 + 1)(2 (r/4) + r%4) and
- * padded to a multiple of four floats, then the 64 floats of the right-hand side.  x = [n][64]: the solutions of
- * (G + reg I) x = b with rows / columns >= rank replaced by the identity. */
+ * 2440 floats: the lower triangle of the Gram matrix row by row — row r holds r / 4 + 1 units of four floats and starts at
+ * the first unit at or after the end of row r - 1 whose index mod 8 is not taken by an earlier row of its group of
+ * eight rows (a bank-conflict-free placement; 594 units) — then the 64 floats of the right-hand side.  x = [n][64]: the
+ * solutions of (G + reg I) x = b with rows / columns >= rank replaced by the identity. */
 int mfb_debug_chol64(mfb_engine *e, int32_t n, const float *records, float *x, int32_t rank, float reg);
 
 /* ---- CCD++ (modelMF.cpp:1013-1121 trainCCDPP; :1258-1375 trainCCDPPFreqAdap) ---------------

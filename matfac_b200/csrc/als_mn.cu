@@ -27,9 +27,16 @@
 namespace mfb {
 namespace {
 
-constexpr int kRecG = 2176;            // floats of the compact lower triangle: row r starts at chol_row_off(r), padded to 4
+// Record of one row: the lower triangle of G row by row, then the right-hand side.  Row r holds r / 4 + 1 units of 16 bytes and
+// starts at the first unit at or after the end of row r - 1 whose index mod 8 differs from those of the earlier rows of its
+// group of eight rows (r / 8): eight neighbouring rows then sit in eight different 16-byte bank groups at every unit index, so
+// a quarter warp's LDS.128 / STS.128 over eight rows is conflict free (the packed triangle cost the solver 47 % of its
+// shared-memory wavefronts in bank conflicts; profiles/r2_als_mn.md).  594 units instead of 544.
+constexpr int kRecG = 2376;            // floats of the triangle
 constexpr int kRecFloats = kRecG + 64; // + right-hand side
-constexpr uint32_t kRecBytes = kRecFloats * 4;  // 8960
+constexpr uint32_t kRecBytes = kRecFloats * 4;  // 9760
+__constant__ int c_row_off[64] = {0, 4, 8, 12, 16, 24, 52, 60, 68, 80, 92, 104, 116, 140, 160, 184, 200, 220, 240, 260, 280, 308, 332, 384, 408, 436, 464, 492, 520, 572, 608, 644, 676, 712, 748, 784, 820, 860, 920, 960, 1000, 1044, 1088, 1132, 1176, 1232, 1284, 1340, 1388, 1440, 1492, 1544, 1596, 1656, 1712, 1796, 1852, 1912, 1972, 2032, 2092, 2176, 2244, 2312};  // float offset of row r
+[[maybe_unused]] static const int h_row_off[64] = {0, 4, 8, 12, 16, 24, 52, 60, 68, 80, 92, 104, 116, 140, 160, 184, 200, 220, 240, 260, 280, 308, 332, 384, 408, 436, 464, 492, 520, 572, 608, 644, 676, 712, 748, 784, 820, 860, 920, 960, 1000, 1044, 1088, 1132, 1176, 1232, 1284, 1340, 1388, 1440, 1492, 1544, 1596, 1656, 1712, 1796, 1852, 1912, 1972, 2032, 2092, 2176, 2244, 2312};
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -75,10 +82,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 
 // ---------------------------------------------------------------------------------------------
 // batched Cholesky solve, one warp per 64 x 64 system
-__host__ __device__ __forceinline__ int chol_row_off(int r) {
-  const int m = r >> 2, s = r & 3;
-  return 4 * (m + 1) * (2 * m + s);
-}
+__device__ __forceinline__ int chol_row_off(int r) { return c_row_off[r]; }
 __device__ __forceinline__ float rsqrt_nr(float d) {
   const float r = d > 0.f ? rsqrtf(d) : 0.f;
   return r * fmaf(-0.5f * d * r, r, 1.5f);  // one Newton step on the hardware approximation
@@ -115,8 +119,8 @@ __device__ __forceinline__ void warp_chol64(float *M, float *dinv, int lane, int
 #pragma unroll 1
   for (int J = 0; J < 16; J++) {
     // rows 4J .. 4J + 3 hold J + 1 units of 16 bytes each
-    const float4 *B0 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J));
-    const float4 *B1 = B0 + (J + 1), *B2 = B1 + (J + 1), *B3 = B2 + (J + 1);
+    const float4 *B0 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J)), *B1 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J + 1)),
+                 *B2 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J + 2)), *B3 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J + 3));
     const bool two = J < 8;  // rows 0 .. 31 are still below or inside the block column
     float4 t1 = R1[J], t0 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (two) {
@@ -163,8 +167,8 @@ __device__ __forceinline__ void warp_chol64(float *M, float *dinv, int lane, int
   float y0 = bv[r0], y1 = bv[r1];
 #pragma unroll 1
   for (int J = 0; J < 16; J++) {
-    const float4 *B0 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J));
-    const float4 q1 = B0[2 * J + 1], q2 = B0[3 * J + 2], q3 = B0[4 * J + 3];  // unit J of rows 4J + 1 .. 4J + 3
+    const float4 q1 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J + 1))[J], q2 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J + 2))[J],
+                 q3 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J + 3))[J];  // unit J of rows 4J + 1 .. 4J + 3
     const float4 di = reinterpret_cast<const float4 *>(dinv)[J];
     const bool two = J < 8;
     const int src = (4 * J) & 31;
@@ -184,8 +188,7 @@ __device__ __forceinline__ void warp_chol64(float *M, float *dinv, int lane, int
   // L^T x = y, from the last block column backwards
 #pragma unroll 1
   for (int J = 15; J >= 0; J--) {
-    const float *S0 = M + chol_row_off(4 * J);
-    const float *S1 = S0 + 4 * (J + 1), *S2 = S1 + 4 * (J + 1), *S3 = S2 + 4 * (J + 1);
+    const float *S0 = M + chol_row_off(4 * J), *S1 = M + chol_row_off(4 * J + 1), *S2 = M + chol_row_off(4 * J + 2), *S3 = M + chol_row_off(4 * J + 3);
     const float4 q1 = reinterpret_cast<const float4 *>(S1)[J], q2 = reinterpret_cast<const float4 *>(S2)[J],
                  q3 = reinterpret_cast<const float4 *>(S3)[J];
     const float4 di = reinterpret_cast<const float4 *>(dinv)[J];
@@ -208,6 +211,21 @@ __device__ __forceinline__ void warp_chol64(float *M, float *dinv, int lane, int
   x1 = y1;
 }
 
+template <int P0>
+__device__ __forceinline__ void hw_kloop(const float4 *B0, const float4 *B1, const float4 *B2, const float4 *B3, float *const (&rowp)[4], int J,
+                                         float4 (&t)[4]) {
+#pragma unroll 2
+  for (int k = 0; k < J; k++) {
+    const float4 b0 = B0[k], b1 = B1[k], b2 = B2[k], b3 = B3[k];
+#pragma unroll
+    for (int p = P0; p < 4; p++) {
+      const float4 a = reinterpret_cast<const float4 *>(rowp[p])[k];
+      t[p].x = sub_dot4(a, b0, t[p].x); t[p].y = sub_dot4(a, b1, t[p].y);
+      t[p].z = sub_dot4(a, b2, t[p].z); t[p].w = sub_dot4(a, b3, t[p].w);
+    }
+  }
+}
+
 // Two matrices per warp: lanes 0-15 solve the record at M0, lanes 16-31 the one at M1 (the caller passes each lane ITS
 // matrix); lane q of a half owns rows q, q + 16, q + 32, q + 48.  The four rows of a block column that every lane needs
 // ("broadcast" loads: a warp-wide LDS.128 costs four shared-memory wavefronts whatever its addresses) now serve two
@@ -223,22 +241,17 @@ __device__ __forceinline__ void halfwarp_chol64(float *M, float *dinv, int q, in
   __syncwarp();
 #pragma unroll 1
   for (int J = 0; J < 16; J++) {
-    const float4 *B0 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J));
-    const float4 *B1 = B0 + (J + 1), *B2 = B1 + (J + 1), *B3 = B2 + (J + 1);
+    const float4 *B0 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J)), *B1 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J + 1)),
+                 *B2 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J + 2)), *B3 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J + 3));
     const int p0 = J >> 2;  // passes below p0 hold finished rows only
     float4 t[4];
 #pragma unroll
     for (int p = 0; p < 4; p++) t[p] = p >= p0 ? reinterpret_cast<const float4 *>(rowp[p])[J] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-    for (int k = 0; k < J; k++) {
-      const float4 b0 = B0[k], b1 = B1[k], b2 = B2[k], b3 = B3[k];
-#pragma unroll
-      for (int p = 0; p < 4; p++)
-        if (p >= p0) {
-          const float4 a = reinterpret_cast<const float4 *>(rowp[p])[k];
-          t[p].x = sub_dot4(a, b0, t[p].x); t[p].y = sub_dot4(a, b1, t[p].y);
-          t[p].z = sub_dot4(a, b2, t[p].z); t[p].w = sub_dot4(a, b3, t[p].w);
-        }
+    switch (p0) {  // warp-uniform: the loop body of each case is straight-line code
+      case 0: hw_kloop<0>(B0, B1, B2, B3, rowp, J, t); break;
+      case 1: hw_kloop<1>(B0, B1, B2, B3, rowp, J, t); break;
+      case 2: hw_kloop<2>(B0, B1, B2, B3, rowp, J, t); break;
+      default: hw_kloop<3>(B0, B1, B2, B3, rowp, J, t); break;
     }
     const int src = (4 * J) & 15;
     const float4 ts = p0 == 0 ? t[0] : p0 == 1 ? t[1] : p0 == 2 ? t[2] : t[3];
@@ -269,8 +282,8 @@ __device__ __forceinline__ void halfwarp_chol64(float *M, float *dinv, int q, in
   for (int p = 0; p < 4; p++) y[p] = bv[q + 16 * p];
 #pragma unroll 1
   for (int J = 0; J < 16; J++) {
-    const float4 *B0 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J));
-    const float4 q1 = B0[2 * J + 1], q2 = B0[3 * J + 2], q3 = B0[4 * J + 3];
+    const float4 q1 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J + 1))[J], q2 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J + 2))[J],
+                 q3 = reinterpret_cast<const float4 *>(M + chol_row_off(4 * J + 3))[J];
     const float4 di = reinterpret_cast<const float4 *>(dinv)[J];
     const int p0 = J >> 2, src = (4 * J) & 15;
     const float sel = p0 == 0 ? y[0] : p0 == 1 ? y[1] : p0 == 2 ? y[2] : y[3];
@@ -291,8 +304,7 @@ __device__ __forceinline__ void halfwarp_chol64(float *M, float *dinv, int q, in
   }
 #pragma unroll 1
   for (int J = 15; J >= 0; J--) {
-    const float *S0 = M + chol_row_off(4 * J);
-    const float *S1 = S0 + 4 * (J + 1), *S2 = S1 + 4 * (J + 1), *S3 = S2 + 4 * (J + 1);
+    const float *S0 = M + chol_row_off(4 * J), *S1 = M + chol_row_off(4 * J + 1), *S2 = M + chol_row_off(4 * J + 2), *S3 = M + chol_row_off(4 * J + 3);
     const float4 q1 = reinterpret_cast<const float4 *>(S1)[J], q2 = reinterpret_cast<const float4 *>(S2)[J],
                  q3 = reinterpret_cast<const float4 *>(S3)[J];
     const float4 di = reinterpret_cast<const float4 *>(dinv)[J];
@@ -477,12 +489,12 @@ int launch_chol64_cfg(mfb_engine *e, const CholArgs &c) {
 int launch_chol64(mfb_engine *e, const CholArgs &c) {
   if (c.n_jobs <= 0) return 0;
   switch (e->opt_als_chol_warps) {
-    case 12: return launch_chol64_cfg<12, 2>(e, c);
+    case 11: return launch_chol64_cfg<11, 2>(e, c);
     case 16: return launch_chol64_cfg<16, 1>(e, c);
     case 20: return launch_chol64_cfg<20, 1>(e, c);
-    case 24: return launch_chol64_cfg<24, 1>(e, c);
+    case 22: return launch_chol64_cfg<22, 1>(e, c);
     case 208: return launch_chol64x2_cfg<8>(e, c);
-    default: return launch_chol64x2_cfg<12>(e, c);  // 212: two matrices per warp, 12 warps
+    default: return launch_chol64x2_cfg<11>(e, c);  // 211: two matrices per warp, 11 warps
   }
 }
 

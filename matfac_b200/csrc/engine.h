@@ -196,7 +196,7 @@ struct mfb_engine {
   int opt_als_dual = 1;               // short rows: solve the len x len dual system instead of rank x rank
   int opt_als_tensor_cores = 1;       // rank > 32: Gram on tcgen05 (3xTF32), warp-specialised persistent kernel; 0 = fp32 CUDA-core Gram; 2 = the round-1 one-CTA-per-row kernel (rank > 64); rank 33 .. 64 with 1: MN-major operands + batched solve (csrc/als_mn.cu), 3 = the converter kernel there too
   int opt_rank_tensor_cores = 1;      // ranking positions: 1 = dense U V^T on tcgen05 where the model allows (rank <= 64, plain dot), 0 = CUDA cores
-  int opt_als_chol_warps = 212;       // batched rank-64 solver: 212 (default) / 208: two matrices per warp (half-warps), 12 / 8 warps per CTA; 12: one matrix per warp, two record buffers; 16 / 20 / 24: one matrix, one buffer
+  int opt_als_chol_warps = 211;       // batched rank-64 solver: 211 (default) / 208: two matrices per warp (half-warps), 11 / 8 warps per CTA; 11: one matrix per warp, two record buffers; 16 / 20 / 22: one matrix, one buffer
   int opt_als_debug = 0;              // timing experiments of csrc/als_mn.cu (results are wrong when set)
   int opt_als_ws_split = 0;           // warp-specialised kernel: 0 = converter teams / solver groups picked per side from the mean row length, 1 = the many-short-rows split, 2 = the few-long-rows split
   cudaStream_t stream = nullptr;

@@ -265,7 +265,7 @@ class Engine:
         self._check(self.L.mfb_ccd_half_step(self.h, side, reg, None if d is None else d.ctypes.data_as(C.c_void_p)))
 
     def debug_chol64(self, records, rank, reg):
-        """Batched rank-64 solver on host records [n][2240] (see mfb_debug_chol64); returns x [n][64]."""
+        """Batched rank-64 solver on host records [n][2440] (see mfb_debug_chol64); returns x [n][64]."""
         rec = np.ascontiguousarray(records, np.float32)
         x = np.zeros((rec.shape[0], 64), np.float32)
         self._check(self.L.mfb_debug_chol64(self.h, rec.shape[0], rec.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), rank, reg))

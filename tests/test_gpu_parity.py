@@ -600,25 +600,40 @@ def test_ccd_matches_oracle(rank, shape):
     eng.close()
 
 
-def chol64_records(G, b):
-    """Host image of the ALS rank-64 solver's records: compact lower triangle (row r at 4 (r/4 + 1)(2 (r/4) + r%4), padded
-    to four floats) + right-hand side."""
-    n = G.shape[0]
-    rec = np.zeros((n, 2240), np.float32)
+def chol64_row_offsets():
+    """Float offset of every row of the solver's record (include/mfb.h, mfb_debug_chol64): row r holds r // 4 + 1 units of four
+    floats and starts at the first unit at or after the end of row r - 1 whose index mod 8 is not taken by an earlier row of its
+    group of eight rows."""
+    offs, end, used = [], 0, set()
     for r in range(64):
-        m, s_ = r >> 2, r & 3
-        off = 4 * (m + 1) * (2 * m + s_)
+        if r % 8 == 0:
+            used = set()
+        o = end
+        while o % 8 in used:
+            o += 1
+        used.add(o % 8)
+        offs.append(4 * o)
+        end = o + r // 4 + 1
+    assert 4 * end == 2376
+    return offs
+
+
+def chol64_records(G, b):
+    """Host image of the ALS rank-64 solver's records: lower triangle row by row (chol64_row_offsets) + right-hand side."""
+    n = G.shape[0]
+    rec = np.zeros((n, 2440), np.float32)
+    for r, off in enumerate(chol64_row_offsets()):
         rec[:, off:off + r + 1] = G[:, r, :r + 1]
-    rec[:, 2176:] = b
+    rec[:, 2376:] = b
     return rec
 
 
-@pytest.mark.parametrize("cfg", [0, 12, 24])
+@pytest.mark.parametrize("cfg", [0, 11, 22])
 @pytest.mark.parametrize("rank", [64, 50, 33])
 def test_batched_chol64_matches_float64_solve(rank, cfg):
     """als_chol64_kernel (one warp per matrix, blocked left-looking Cholesky) against numpy's float64 solve on Gram matrices of
     random factor rows: more matrices than one wave of warps, short and long rows, padded ranks.  cfg = option als_chol_warps:
-    0 = default (two matrices per warp), 12 = one matrix per warp with two record buffers, 24 = one matrix, one buffer, 24 warps."""
+    0 = default (two matrices per warp), 11 = one matrix per warp with two record buffers, 22 = one matrix, one buffer, 22 warps."""
     rng = np.random.default_rng(7)
     n = 5001
     G = np.zeros((n, 64, 64), np.float64); b = np.zeros((n, 64), np.float64)
