@@ -528,7 +528,7 @@ constexpr uint32_t kGnStage = 5 * kGnBlock;   // small 0-31 | small 32-63 | big 
                                               // by shared-memory bandwidth (profiles/r2_als_mn.md) and a second MMA for the
                                               // right-hand side re-read the 4 KB of A
 constexpr int kGnStages = 9;
-constexpr int kGnProducers = 128;             // 4 producer warps, each owns every 4th tile
+constexpr int kGnProducers = 128;             // 4 producer warps, each owns every 4th tile (8 warps: same kernel time, the MMAs set the pace)
 constexpr int kGnAhead = 4;                   // a warp requests the (item, rating) pairs of its tile y + 4 while it copies tile y; it waits
                                               // for its commit group y - 3 at the end of iteration y (pairs of tile y + 1 ready, at most
                                               // four of its tiles in flight) but never for the stage it has just filled
@@ -564,7 +564,7 @@ struct GramArgs {
   int nseg;             // segments [0, nseg) of the plan (longest first); CTA b takes b, b + grid, ...
   int debug_mode;       // timing experiments (results are wrong): 1 = every rating gathers row (item & 1023): L2-hot rows;
                         // 2 = no factor-row copies at all (the MMAs read stale stages); 3 = copies, but no MMAs (commits only);
-                        // 4 = the four MMAs of a tile go to four different accumulators
+                        // 4 = unused; 5 / 6 = MMAs with N = 16 / M = 64
   float *rec;           // [nseg + split rows][kRecFloats]
 };
 
@@ -683,9 +683,11 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
         ln_ = __ldg(a.seg_len + seg);
       }
     };
-    auto advance = [&](Cursor &c) {
-      if (c.i >= n_rows) return;
-      if (++c.t == c.ntiles) {
+    auto advance_n = [&](Cursor &c, int n) {  // n tiles further (whole rows at a time)
+      while (n > 0 && c.i < n_rows) {
+        const int rem = c.ntiles - c.t;
+        if (n < rem) { c.t += n; return; }
+        n -= rem;
         c.i++; c.t = 0;
         c.start = c.s1; c.len = c.l1;
         c.ntiles = (c.len + kGnKT - 1) / kGnKT;
@@ -719,10 +721,10 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
     nxt.ntiles = (nxt.len + kGnKT - 1) / kGnKT;
     load_seg(1, nxt.s1, nxt.l1);
     load_seg(2, nxt.s2, nxt.l2);
-    for (int k = 0; k < w; k++) advance(nxt);  // the warp's first tile is global tile w
+    advance_n(nxt, w);  // the warp's first tile is global tile w
     for (int y = 0; y < kGnAhead; y++) {
       request_meta(nxt, y);
-      for (int k = 0; k < NPW; k++) advance(nxt);
+      advance_n(nxt, NPW);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -760,7 +762,7 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
         __syncwarp();                        // every lane has read the ring slot that is refilled now, and stored its ratings
         if (lane == 0) mbar_arrive(bar_opf + stg * 8);
         request_meta(nxt, y + kGnAhead);
-        for (int k = 0; k < NPW; k++) advance(nxt);
+        advance_n(nxt, NPW);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
       // pairs requested with tile y - (kGnAhead - 1) are read in the next iteration; this also bounds a warp's copies in flight
@@ -780,6 +782,9 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
     const uint32_t desc_hi = (uint32_t)(desc0 >> 32), lo0 = (uint32_t)desc0;
     constexpr uint32_t kStep = (2 * kGnSbo) >> 4, kBoff = (2 * kGnBlock) >> 4, kStageStep = kGnStage >> 4;
     const bool no_mma = a.debug_mode == 3;
+    // timing experiments: 5 = N = 16 instead of 80 (B and the math shrink, A stays), 6 = M = 64 (half of A)
+    const uint32_t idesc_run = a.debug_mode == 5 ? ((idesc_g & ~(0x3Fu << 17)) | ((16u >> 3) << 17))
+                             : a.debug_mode == 6 ? ((idesc_g & ~(0x1Fu << 24)) | ((64u >> 4) << 24)) : idesc_g;
     int os = 0, acc = 0, gen = 0;
     uint32_t ph = 0, lo = lo0;
     bool first = true;
@@ -793,10 +798,10 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
         const uint32_t dt = tmem_base + (uint32_t)acc * kGnAccCols;
         if (!no_mma) {
           auto dsc = [&](uint32_t l) { return ((uint64_t)desc_hi << 32) | l; };
-          umma_tf32(dt, dsc(lo), dsc(lo + kBoff), idesc_g, first ? 0u : 1u);
-          umma_tf32_acc(dt, dsc(lo + kStep), dsc(lo + kStep + kBoff), idesc_g);
-          umma_tf32_acc(dt, dsc(lo + 2 * kStep), dsc(lo + 2 * kStep + kBoff), idesc_g);
-          umma_tf32_acc(dt, dsc(lo + 3 * kStep), dsc(lo + 3 * kStep + kBoff), idesc_g);
+          umma_tf32(dt, dsc(lo), dsc(lo + kBoff), idesc_run, first ? 0u : 1u);
+          umma_tf32_acc(dt, dsc(lo + kStep), dsc(lo + kStep + kBoff), idesc_run);
+          umma_tf32_acc(dt, dsc(lo + 2 * kStep), dsc(lo + 2 * kStep + kBoff), idesc_run);
+          umma_tf32_acc(dt, dsc(lo + 3 * kStep), dsc(lo + 3 * kStep + kBoff), idesc_run);
         }
         umma_commit(bar_ope + os * 8);
         if (last) umma_commit(bar_accf + acc * 8);
