@@ -529,9 +529,8 @@ constexpr uint32_t kGnStage = 5 * kGnBlock;   // small 0-31 | small 32-63 | big 
                                               // right-hand side re-read the 4 KB of A
 constexpr int kGnStages = 9;
 constexpr int kGnProducers = 128;             // 4 producer warps, each owns every 4th tile (8 warps: same kernel time, the MMAs set the pace)
-constexpr int kGnAhead = 4;                   // a warp requests the (item, rating) pairs of its tile y + 4 while it copies tile y; it waits
-                                              // for its commit group y - 3 at the end of iteration y (pairs of tile y + 1 ready, at most
-                                              // four of its tiles in flight) but never for the stage it has just filled
+constexpr int kGnAhead = 4;                   // a warp's ring holds the (item, rating) pairs of its next four tiles; the pairs of the fifth
+                                              // are on their way in registers
 constexpr int kGnAcc = 4;                     // accumulators in TMEM: row i -> i mod 4
 constexpr int kGnAccCols = 128;               // D in columns [0, 64), D2 in [64, 80)
 constexpr int kGnDrainTeams = 2;              // row i is drained by team i mod 2 (4 warps, one per TMEM lane quadrant)
@@ -702,18 +701,22 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
     const int2 *meta_ptr = reinterpret_cast<const int2 *>(smb + S::off_meta) + w * (kGnAhead * 32);
     int *tflags = reinterpret_cast<int *>(smb + S::off_tflags) + w * kGnAhead;
     int ny = -1;  // number of this warp's tiles, known once the cursor has run off the end
-    auto request_meta = [&](const Cursor &c, int y) {  // y = index among this warp's tiles
+    // lane l loads pair l of the cursor's tile with ordinary loads (NOT cp.async: the stage-full arrival below waits for every
+    // cp.async the lane has in flight, and these come from DRAM) and stores it into the ring one iteration later
+    auto load_pair = [&](const Cursor &c, int y, int &it, int &rt, int &fl) {  // y = index among this warp's tiles
       const bool alive = c.i < n_rows;
       if (!alive && ny < 0) ny = y;
-      const uint32_t dst = meta0 + (uint32_t)(y % kGnAhead) * 256u + (uint32_t)lane * 8u;
+      it = 0; rt = 0;  // rating 0: filtered out
       const int jj = c.t * kGnKT + lane;
       if (alive && jj < c.len) {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(a.ind + c.start + jj) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4), "l"(a.val + c.start + jj) : "memory");
-      } else {
-        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(0), "r"(0) : "memory");  // rating 0: filtered out
+        it = __ldg(a.ind + c.start + jj);
+        rt = __float_as_int(__ldg(a.val + c.start + jj));
       }
-      if (lane == 0) tflags[y % kGnAhead] = alive ? ((c.t == 0 ? kGnFirst : 0) | (c.t == c.ntiles - 1 ? kGnLast : 0)) : 0;
+      fl = alive ? ((c.t == 0 ? kGnFirst : 0) | (c.t == c.ntiles - 1 ? kGnLast : 0)) : 0;
+    };
+    auto store_pair = [&](int y, int it, int rt, int fl) {
+      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(meta0 + (uint32_t)(y % kGnAhead) * 256u + (uint32_t)lane * 8u), "r"(it), "r"(rt) : "memory");
+      if (lane == 0) tflags[y % kGnAhead] = fl;
     };
     Cursor nxt;
     nxt.i = 0; nxt.t = 0;
@@ -722,55 +725,52 @@ __global__ void __launch_bounds__(kGnThreads, 1) als_gram_mn_kernel(const GramAr
     load_seg(1, nxt.s1, nxt.l1);
     load_seg(2, nxt.s2, nxt.l2);
     advance_n(nxt, w);  // the warp's first tile is global tile w
+    int p_it, p_rt, p_fl;  // the pair / flags of tile y + kGnAhead while tile y is copied
     for (int y = 0; y < kGnAhead; y++) {
-      request_meta(nxt, y);
+      load_pair(nxt, y, p_it, p_rt, p_fl);
+      store_pair(y, p_it, p_rt, p_fl);
       advance_n(nxt, NPW);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    load_pair(nxt, kGnAhead, p_it, p_rt, p_fl);
     __syncwarp();
     for (int y = 0;; y++) {
       const bool live = ny < 0 || y < ny;
-      if (live) {
-        const int g = w + NPW * y;  // global tile: its operand stage and its place in the tensor-core warp's order
-        const int stg = g % kGnStages;
-        if (g >= kGnStages) mbar_wait(bar_ope + stg * 8, (uint32_t)(g / kGnStages - 1) & 1u);  // the MMAs that read this stage are done
-        if (lane == 0) opinfo[stg] = tflags[y % kGnAhead];  // only now: the tensor-core warp has read the previous tile's flags
-        const uint32_t dst0 = sbase + S::off_stage + (uint32_t)stg * kGnStage;
-        const int2 *mp = meta_ptr + (y % kGnAhead) * 32 + o8;
+      if (!live) break;
+      const int g = w + NPW * y;  // global tile: its operand stage and its place in the tensor-core warp's order
+      const int stg = g % kGnStages;
+      if (g >= kGnStages) mbar_wait(bar_ope + stg * 8, (uint32_t)(g / kGnStages - 1) & 1u);  // the MMAs that read this stage are done
+      if (lane == 0) opinfo[stg] = tflags[y % kGnAhead];  // only now: the tensor-core warp has read the previous tile's flags
+      const uint32_t dst0 = sbase + S::off_stage + (uint32_t)stg * kGnStage;
+      const int2 *mp = meta_ptr + (y % kGnAhead) * 32 + o8;
 #pragma unroll
-        for (int m = 0; m < 8; m++) {
-          const int2 mt = mp[4 * m];  // rating 4 m + o8 of the tile
-          const float rt = __int_as_float(mt.y);
-          const bool on = rt > 0.f;  // rating > 0 filter (modelMF.cpp:819); beyond the row's end the ring holds 0
-          const int row = on ? (a.debug_mode == 1 ? (mt.x & 1023) : mt.x) : a.zero_row;
-          const float *src = a.Fs + (size_t)row * 128 + cg * 4;
-          if (a.debug_mode != 2) {
+      for (int m = 0; m < 8; m++) {
+        const int2 mt = mp[4 * m];  // rating 4 m + o8 of the tile
+        const float rt = __int_as_float(mt.y);
+        const bool on = rt > 0.f;  // rating > 0 filter (modelMF.cpp:819); beyond the row's end the ring holds 0
+        const int row = on ? (a.debug_mode == 1 ? (mt.x & 1023) : mt.x) : a.zero_row;
+        const float *src = a.Fs + (size_t)row * 128 + cg * 4;
+        if (a.debug_mode != 2) {
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + base_off + m * kGnSbo + ((i + 2) & 3) * kGnBlock), "l"(src + 32 * i) : "memory");  // big -> blocks 2, 3; small -> 0, 1
-          }
-          if (cg == 0) {
-            const float rb = on ? round_tf32_fast(rt) : 0.f;
-            const float rs = on ? rt - rb : 0.f;
-            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(dst0 + roff + m * kGnSbo), "f"(rb), "f"(rs) : "memory");
-          }
+          for (int i = 0; i < 4; i++)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + base_off + m * kGnSbo + ((i + 2) & 3) * kGnBlock), "l"(src + 32 * i) : "memory");  // big -> blocks 2, 3; small -> 0, 1
         }
-        // the stage is full when every lane's copies have landed (the hardware arrives for the lane then: the warp does not
-        // wait for its data) and lane 0 has arrived for the ratings / flags the lanes stored themselves
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_opf + stg * 8) : "memory");
-        __syncwarp();                        // every lane has read the ring slot that is refilled now, and stored its ratings
-        if (lane == 0) mbar_arrive(bar_opf + stg * 8);
-        request_meta(nxt, y + kGnAhead);
-        advance_n(nxt, NPW);
+        if (cg == 0) {
+          const float rb = on ? round_tf32_fast(rt) : 0.f;
+          const float rs = on ? rt - rb : 0.f;
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(dst0 + roff + m * kGnSbo), "f"(rb), "f"(rs) : "memory");
+        }
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      // pairs requested with tile y - (kGnAhead - 1) are read in the next iteration; this also bounds a warp's copies in flight
-      asm volatile("cp.async.wait_group %0;" ::"n"(kGnAhead - 1) : "memory");
+      // the stage is full when every lane's copies have landed (the hardware arrives for the lane then: the warp does not
+      // wait for its data) and lane 0 has arrived for the ratings / flags the lanes stored themselves
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_opf + stg * 8) : "memory");
+      __syncwarp();                        // every lane has read the ring slot that is refilled now, and stored its ratings
+      if (lane == 0) mbar_arrive(bar_opf + stg * 8);
+      store_pair(y + kGnAhead, p_it, p_rt, p_fl);            // loaded one iteration ago
+      advance_n(nxt, NPW);
+      load_pair(nxt, y + kGnAhead + 1, p_it, p_rt, p_fl);    // in flight during the next tile's copies
       __syncwarp();
-      if (ny >= 0 && y >= ny - 1) break;
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (tid < kGnDrain0) {
     // ================================= tensor-core issue =================================
     // instruction descriptor: D = F32, A = B = TF32, both MN-major; M = 128 ([small; big]), N = 80 ([big | r_big r_small 0 ..])
