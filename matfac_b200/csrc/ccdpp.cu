@@ -184,6 +184,236 @@ __global__ void col_insert_kernel(float *__restrict__ F, int ld, int k, int lo, 
 }
 
 
+// ---- warp-streamed passes (option ccd_stream = 2; measured equal to the warp-per-segment kernels, profiles/r2_ccdpp.md) -----
+// One warp per chunk of consecutive segments.  The warp streams the chunk's contiguous range of the index / residual
+// arrays in batches of 256 ratings (8 per lane, coalesced) and ALWAYS has the next batch in flight while it works on the
+// current one, whatever the rows look like; the segments are then only boundaries inside the stream: per batch the warp
+// walks the segments that overlap it, adds the ratings that fall into [start, start + len) to the per-lane fp64 partial
+// sums and closes a row when its last rating has passed.  Segment descriptors are fetched 32 at a time (one per lane)
+// and handed round by shuffle.  Streaming loads carry the evict-first hint so that L1 keeps the gathered vector.
+constexpr int kCcdBatch = 256;
+
+struct CcdDesc {
+  int row, start, len, slot;
+  float a;
+};
+// lane l holds the descriptor of segment sb + l (a = own[row] when WITH_A)
+template <bool WITH_A>
+__device__ __forceinline__ CcdDesc ccd_load_descs(const CcdPass &p, int sb, int s1, int lane, const float *own) {
+  CcdDesc d{0, 0, 0, -1, 0.f};
+  const int s = sb + lane;
+  if (s < s1) {
+    d.row = __ldg(p.seg_row + s); d.start = __ldg(p.seg_start + s); d.len = __ldg(p.seg_len + s); d.slot = __ldg(p.seg_slot + s);
+    if (WITH_A) d.a = own[d.row];
+  }
+  return d;
+}
+__device__ __forceinline__ CcdDesc ccd_pick_desc(const CcdDesc &d, int src) {
+  CcdDesc o;
+  o.row = __shfl_sync(0xFFFFFFFFu, d.row, src); o.start = __shfl_sync(0xFFFFFFFFu, d.start, src);
+  o.len = __shfl_sync(0xFFFFFFFFu, d.len, src); o.slot = __shfl_sync(0xFFFFFFFFu, d.slot, src);
+  o.a = __shfl_sync(0xFFFFFFFFu, d.a, src);
+  return o;
+}
+
+// STAGED: persistent CTAs (one per SM) keep the whole gathered vector in shared memory — a gather of 32 different
+// 128-byte lines costs 32 L1 wavefronts (the ~0.3 ms per pass that every global-gather variant of these kernels ends up
+// at: 100 M ratings / 148 SMs at one wavefront per cycle), the same gather from shared memory a few bank conflicts —
+// and their warps take chunks in turn.  The add-back of a row pass reads the same vector (v_k has not moved yet).
+constexpr int kCcdStagedThreads = 768;
+__device__ __forceinline__ void ccd_stage(uint64_t *bar_mem, float *dst0, const float *src0, float *dst1, const float *src1, int n);
+
+template <bool ADDBACK, bool SUBTRACT, bool STAGED>
+__global__ void __launch_bounds__(STAGED ? kCcdStagedThreads : 256, STAGED ? 1 : 3)
+    ccd_update_flat_kernel(const CcdPass p, const int32_t *__restrict__ chunk_seg, int n_chunk, float *__restrict__ own,
+                           const float *__restrict__ other, const float *__restrict__ other_old, float reg, double *__restrict__ acc,
+                           const Aux *__restrict__ aux_freq, int freq_thresh, const CcdPeers pe, int gather_n) {
+  constexpr int D = kCcdBatch / 32;
+  extern __shared__ __align__(16) float ccd_sm[];
+  __shared__ uint64_t stage_bar;
+  if (STAGED) ccd_stage(&stage_bar, ccd_sm, other, nullptr, nullptr, gather_n);
+  const int lane = threadIdx.x & 31;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_chunk; w += n_warps) {
+  const int s0 = chunk_seg[w], s1 = chunk_seg[w + 1];
+  int sb = s0;
+  CcdDesc dl = ccd_load_descs<ADDBACK>(p, sb, s1, lane, own);
+  CcdDesc cur = ccd_pick_desc(dl, 0);
+  const int g0 = cur.start;
+  const int g1 = __ldg(p.seg_start + s1 - 1) + __ldg(p.seg_len + s1 - 1);
+  int seg = s0;
+  int c[D], cn[D];
+  float r[D], rn[D], o[D], q[D];
+#pragma unroll
+  for (int d = 0; d < D; d++) {
+    const int pos = g0 + d * 32 + lane;
+    c[d] = pos < g1 ? __ldcs(p.ind + pos) : -1;
+    r[d] = pos < g1 ? __ldcs(p.res + pos) : 0.f;
+  }
+  double num = 0.0, den = 0.0;
+  for (int base = g0; base < g1; base += kCcdBatch) {
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+      if (STAGED) {
+        o[d] = c[d] >= 0 ? ccd_sm[c[d]] : 0.f;
+        if (ADDBACK) q[d] = o[d];
+      } else {
+        o[d] = c[d] >= 0 ? __ldg(other + c[d]) : 0.f;
+        if (ADDBACK) q[d] = c[d] >= 0 ? __ldg(other_old + c[d]) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < D; d++) {  // the next batch travels while this one is reduced
+      const int pos = base + kCcdBatch + d * 32 + lane;
+      cn[d] = pos < g1 ? __ldcs(p.ind + pos) : -1;
+      rn[d] = pos < g1 ? __ldcs(p.res + pos) : 0.f;
+    }
+    const int bend = min(base + kCcdBatch, g1);
+    while (seg < s1 && cur.start < bend) {
+      const int send = cur.start + cur.len;
+#pragma unroll
+      for (int d = 0; d < D; d++) {
+        const int pos = base + d * 32 + lane;
+        if (pos >= cur.start && pos < send) {
+          float rr = r[d];
+          if (ADDBACK) {
+            rr = __fadd_rn(rr, __fmul_rn(cur.a, q[d]));
+            p.res[pos] = rr;
+          }
+          num += (double)__fmul_rn(rr, o[d]);
+          den += (double)__fmul_rn(o[d], o[d]);
+        }
+      }
+      if (send > bend) break;  // the row continues in the next batch
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+        num += __shfl_xor_sync(0xFFFFFFFFu, num, m);
+        den += __shfl_xor_sync(0xFFFFFFFFu, den, m);
+      }
+      if (cur.slot < 0) {
+        float nv = (float)(num / ((double)reg + den));
+        if (freq_thresh > 0 && aux_freq[cur.row].freq < freq_thresh) nv = 0.f;
+        if (lane == 0) store_all(own, pe, cur.row, nv);
+        if (SUBTRACT) {  // the row's ratings have just passed through L1 / L2
+          const float a = -nv;
+          for (int j = cur.start + lane; j < send; j += 32)
+            p.res[j] = __fadd_rn(p.res[j], __fmul_rn(a, __ldg(other + __ldg(p.ind + j))));
+        }
+      } else if (lane == 0) {
+        atomicAdd(acc + 2 * (size_t)cur.slot, num);
+        atomicAdd(acc + 2 * (size_t)cur.slot + 1, den);
+      }
+      num = 0.0; den = 0.0;
+      seg++;
+      if (seg - sb == 32) {
+        sb = seg;
+        dl = ccd_load_descs<ADDBACK>(p, sb, s1, lane, own);
+      }
+      cur = ccd_pick_desc(dl, seg - sb);
+    }
+#pragma unroll
+    for (int d = 0; d < D; d++) { c[d] = cn[d]; r[d] = rn[d]; }
+  }
+  }
+}
+
+// res[j] += sign * own[row] * other[ind[j]], the same stream
+template <bool STAGED>
+__global__ void __launch_bounds__(STAGED ? kCcdStagedThreads : 256, STAGED ? 1 : 4)
+    ccd_resid_flat_kernel(const CcdPass p, const int32_t *__restrict__ chunk_seg, int n_chunk, const float *__restrict__ own,
+                          const float *__restrict__ other, float sign, int gather_n) {
+  constexpr int D = kCcdBatch / 32;
+  extern __shared__ __align__(16) float ccd_sm[];
+  __shared__ uint64_t stage_bar;
+  if (STAGED) ccd_stage(&stage_bar, ccd_sm, other, nullptr, nullptr, gather_n);
+  const int lane = threadIdx.x & 31;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_chunk; w += n_warps) {
+  const int s0 = chunk_seg[w], s1 = chunk_seg[w + 1];
+  int sb = s0;
+  CcdDesc dl = ccd_load_descs<true>(p, sb, s1, lane, own);
+  CcdDesc cur = ccd_pick_desc(dl, 0);
+  const int g0 = cur.start;
+  const int g1 = __ldg(p.seg_start + s1 - 1) + __ldg(p.seg_len + s1 - 1);
+  int seg = s0;
+  int c[D], cn[D];
+  float r[D], rn[D], o[D];
+#pragma unroll
+  for (int d = 0; d < D; d++) {
+    const int pos = g0 + d * 32 + lane;
+    c[d] = pos < g1 ? __ldcs(p.ind + pos) : -1;
+    r[d] = pos < g1 ? __ldcs(p.res + pos) : 0.f;
+  }
+  for (int base = g0; base < g1; base += kCcdBatch) {
+#pragma unroll
+    for (int d = 0; d < D; d++) o[d] = c[d] >= 0 ? (STAGED ? ccd_sm[c[d]] : __ldg(other + c[d])) : 0.f;
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+      const int pos = base + kCcdBatch + d * 32 + lane;
+      cn[d] = pos < g1 ? __ldcs(p.ind + pos) : -1;
+      rn[d] = pos < g1 ? __ldcs(p.res + pos) : 0.f;
+    }
+    const int bend = min(base + kCcdBatch, g1);
+    while (seg < s1 && cur.start < bend) {
+      const int send = cur.start + cur.len;
+      const float a = sign * cur.a;
+#pragma unroll
+      for (int d = 0; d < D; d++) {
+        const int pos = base + d * 32 + lane;
+        if (pos >= cur.start && pos < send) __stcs(p.res + pos, __fadd_rn(r[d], __fmul_rn(a, o[d])));
+      }
+      if (send > bend) break;
+      seg++;
+      if (seg - sb == 32) {
+        sb = seg;
+        dl = ccd_load_descs<true>(p, sb, s1, lane, own);
+      }
+      cur = ccd_pick_desc(dl, seg - sb);
+    }
+#pragma unroll
+    for (int d = 0; d < D; d++) { c[d] = cn[d]; r[d] = rn[d]; }
+  }
+  }
+}
+
+constexpr size_t kCcdStagedMaxBytes = 200 * 1024;  // of the 227 KB a CTA may have
+static size_t ccd_flat_smem(int gather_n) { return sizeof(float) * (size_t)((gather_n + 3) & ~3); }
+static bool ccd_flat_staged(const mfb_engine *e, int gather_n) {
+  return e->opt_ccd_stage && gather_n > 0 && ccd_flat_smem(gather_n) <= kCcdStagedMaxBytes;
+}
+constexpr int kCcdCapMax = 8192;  // ratings per chunk of the warp-streamed kernels: engine option ccd_cap (default 4096), >= kCcdChunk so that every segment fits a chunk
+static int ccd_cap(const mfb_engine *e) { return std::min(kCcdCapMax, std::max(kCcdChunk, e->opt_ccd_cap & ~3)); }
+// groups the (memory-ordered) segments of a plan into chunks, one per warp: a chunk's segments span at most ccd_cap ratings
+static int build_chunk_plan(mfb_engine *e, SegPlan *sp) {
+  dev_free(sp->chunk_seg);
+  sp->chunk_seg = nullptr;
+  sp->n_chunk = 0;
+  const int ns = sp->n_seg;
+  if (ns <= 0) return 0;
+  const int cap = ccd_cap(e);
+  std::vector<int32_t> start((size_t)ns), len((size_t)ns), cut;
+  MFB_CUDA(cudaMemcpyAsync(start.data(), sp->start, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, e->stream));
+  MFB_CUDA(cudaMemcpyAsync(len.data(), sp->len, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, e->stream));
+  MFB_CUDA(cudaStreamSynchronize(e->stream));
+  cut.reserve((size_t)ns / 8 + 2);
+  cut.push_back(0);
+  int32_t first = start[0];
+  for (int s = 0; s < ns; s++) {
+    MFB_REQUIRE(len[s] <= cap && (s == 0 || start[s] >= start[s - 1] + len[s - 1]), "ccd chunk plan: segments not in memory order");
+    if (start[s] + len[s] - first > cap) {
+      cut.push_back(s);
+      first = start[s];
+    }
+  }
+  cut.push_back(ns);
+  sp->n_chunk = (int32_t)cut.size() - 1;
+  MFB_CUDA(dev_alloc(&sp->chunk_seg, sizeof(int32_t) * cut.size()));
+  MFB_CUDA(cudaMemcpyAsync(sp->chunk_seg, cut.data(), sizeof(int32_t) * cut.size(), cudaMemcpyHostToDevice, e->stream));
+  MFB_CUDA(cudaStreamSynchronize(e->stream));  // `cut` leaves scope
+  return 0;
+}
+
+
 // ---- shared-memory staged passes ------------------------------------------------------------------------------
 // A pass gathers one entry of the dense vector `other` per rating.  Every lane of a warp hits a different 128-byte
 // line, so the gather costs one L1 wavefront per rating: 100 M ratings / 148 SMs at one wavefront per cycle is the
@@ -452,7 +682,7 @@ static int ccd_side_mode(const mfb_engine *e, int64_t nnz_side, int n_rows_side,
 // time while a peer's barrier is already spinning (the add-back forms first run in the second sweep) would then block
 // the host thread that still has to issue that peer's partner — a deadlock until the flag wait times out.  So every
 // kernel of the rank-one step is loaded here, before the first barrier exists.
-static int ccd_preload_kernels() {
+static int ccd_preload_kernels(const mfb_engine *e) {
   cudaFuncAttributes fa;
   MFB_CUDA(cudaFuncGetAttributes(&fa, ccd_resid_kernel));
   MFB_CUDA(cudaFuncGetAttributes(&fa, ccd_update_kernel<false, false>));
@@ -462,6 +692,13 @@ static int ccd_preload_kernels() {
   MFB_CUDA(cudaFuncGetAttributes(&fa, ccd_update_sm_kernel<true, false>));
   MFB_CUDA(cudaFuncGetAttributes(&fa, ccd_update_sm_kernel<true, true>));
   MFB_CUDA(cudaFuncGetAttributes(&fa, ccd_resid_sm_kernel));
+  MFB_CUDA(cudaFuncGetAttributes(&fa, ccd_update_flat_kernel<false, false, false>));
+  MFB_CUDA(cudaFuncGetAttributes(&fa, ccd_update_flat_kernel<true, false, false>));
+  MFB_CUDA(cudaFuncGetAttributes(&fa, ccd_update_flat_kernel<false, true, false>));
+  MFB_CUDA(cudaFuncGetAttributes(&fa, ccd_resid_flat_kernel<false>));
+  MFB_CUDA(cudaFuncSetAttribute(ccd_update_flat_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCcdStagedMaxBytes));
+  MFB_CUDA(cudaFuncSetAttribute(ccd_update_flat_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCcdStagedMaxBytes));
+  MFB_CUDA(cudaFuncSetAttribute(ccd_resid_flat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCcdStagedMaxBytes));
   MFB_CUDA(cudaFuncGetAttributes(&fa, ccd_finalize_kernel));
   MFB_CUDA(cudaFuncGetAttributes(&fa, col_extract_kernel));
   MFB_CUDA(cudaFuncGetAttributes(&fa, col_insert_kernel));
@@ -471,7 +708,7 @@ static int ccd_preload_kernels() {
 int ccdpp_begin_impl(mfb_engine *e) {
   DevCsr &m = e->mat[MFB_TRAIN];
   cudaStream_t st = e->stream;
-  MFB_TRY(ccd_preload_kernels());
+  MFB_TRY(ccd_preload_kernels(e));
   size_t nn = (size_t)(m.nnz > 0 ? m.nnz : 1);
   if (!e->res_row) MFB_CUDA(dev_alloc(&e->res_row, sizeof(float) * nn));
   if (!e->res_col) MFB_CUDA(dev_alloc(&e->res_col, sizeof(float) * nn));
@@ -483,7 +720,8 @@ int ccdpp_begin_impl(mfb_engine *e) {
   MFB_CUDA(cudaMemsetAsync(e->U, 0, sizeof(float) * (size_t)e->n_users * e->ld, st));
   const int ulo = e->row_begin[MFB_USER], uhi = e->row_end[MFB_USER], ilo = e->row_begin[MFB_ITEM], ihi = e->row_end[MFB_ITEM];
   if (!m.ccd_rows.built) {
-    MFB_TRY(build_seg_plan(e, m.rowptr, e->n_users, e->bad_user, ulo, uhi, kCcdChunk, &m.ccd_rows));
+    MFB_TRY(build_seg_plan(e, m.rowptr, e->n_users, e->bad_user, ulo, uhi, kCcdChunk, &m.ccd_rows, e->opt_ccd_stream == 0));
+    if (e->opt_ccd_stream == 2) MFB_TRY(build_chunk_plan(e, &m.ccd_rows));
     const int64_t nnz_side = (int64_t)((double)m.nnz * (double)(uhi - ulo) / std::max(e->n_users, 1));
     m.ccd_rows_mode = ccd_side_mode(e, nnz_side, uhi - ulo, e->n_items, true);  // the row passes gather v_k
     if (m.ccd_rows_mode == 2) {
@@ -496,7 +734,8 @@ int ccdpp_begin_impl(mfb_engine *e) {
     }
   }
   if (!m.ccd_cols.built) {
-    MFB_TRY(build_seg_plan(e, m.colptr, e->n_items, e->bad_item, ilo, ihi, kCcdChunk, &m.ccd_cols));
+    MFB_TRY(build_seg_plan(e, m.colptr, e->n_items, e->bad_item, ilo, ihi, kCcdChunk, &m.ccd_cols, e->opt_ccd_stream == 0));
+    if (e->opt_ccd_stream == 2) MFB_TRY(build_chunk_plan(e, &m.ccd_cols));
     const int64_t nnz_side = (int64_t)((double)m.nnz * (double)(ihi - ilo) / std::max(e->n_items, 1));
     m.ccd_cols_mode = ccd_side_mode(e, nnz_side, ihi - ilo, e->n_users, false);  // the column passes gather u_k
     if (m.ccd_cols_mode == 2) {
@@ -557,7 +796,17 @@ int ccd_update_side(mfb_engine *e, const CcdSide &sd, float *own, const float *o
   const SegPlan *sp = sd.mode == 2 ? sd.sp_blk : sd.sp_plain;
   const CcdPass &p = sd.mode == 2 ? sd.blk : sd.plain;
   if (p.n_seg > 0) {
-    if (sd.mode == 0) {
+    if (sd.mode == 0 && e->opt_ccd_stream == 2 && sp->n_chunk > 0) {
+      const int grid = (sp->n_chunk + wpb - 1) / wpb;
+      // the whole gathered vector staged in shared memory when it fits and the add-back reads the same vector
+      const bool staged = ccd_flat_staged(e, sd.gather_n) && !subtract && (!addback || other_old == other);
+      const size_t sm = ccd_flat_smem(sd.gather_n);
+      if (staged && addback) MFB_LAUNCH((ccd_update_flat_kernel<true, false, true>), e->sm_count, kCcdStagedThreads, sm, st, p, sp->chunk_seg, sp->n_chunk, own, other, other_old, reg, e->ccd_acc, aux, thresh, pe, sd.gather_n);
+      else if (staged) MFB_LAUNCH((ccd_update_flat_kernel<false, false, true>), e->sm_count, kCcdStagedThreads, sm, st, p, sp->chunk_seg, sp->n_chunk, own, other, other, reg, e->ccd_acc, aux, thresh, pe, sd.gather_n);
+      else if (addback) MFB_LAUNCH((ccd_update_flat_kernel<true, false, false>), grid, tb, 0, st, p, sp->chunk_seg, sp->n_chunk, own, other, other_old, reg, e->ccd_acc, aux, thresh, pe, sd.gather_n);
+      else if (subtract) MFB_LAUNCH((ccd_update_flat_kernel<false, true, false>), grid, tb, 0, st, p, sp->chunk_seg, sp->n_chunk, own, other, other, reg, e->ccd_acc, aux, thresh, pe, sd.gather_n);
+      else MFB_LAUNCH((ccd_update_flat_kernel<false, false, false>), grid, tb, 0, st, p, sp->chunk_seg, sp->n_chunk, own, other, other, reg, e->ccd_acc, aux, thresh, pe, sd.gather_n);
+    } else if (sd.mode == 0) {
       const int grid = (p.n_seg + wpb - 1) / wpb;
       if (addback) MFB_LAUNCH((ccd_update_kernel<true, false>), grid, tb, 0, st, p, own, other, other_old, reg, e->ccd_acc, aux, thresh, pe);
       else if (subtract) MFB_LAUNCH((ccd_update_kernel<false, true>), grid, tb, 0, st, p, own, other, other, reg, e->ccd_acc, aux, thresh, pe);
@@ -579,6 +828,15 @@ int ccd_update_side(mfb_engine *e, const CcdSide &sd, float *own, const float *o
 int ccd_resid_side(mfb_engine *e, const CcdSide &sd, const float *own, const float *other, float sign, int only_multi) {
   const CcdPass &p = sd.mode == 2 ? sd.blk : sd.plain;
   if (p.n_seg <= 0) return 0;
+  if (sd.mode == 0 && e->opt_ccd_stream == 2 && !only_multi && sd.sp_plain->n_chunk > 0) {
+    if (ccd_flat_staged(e, sd.gather_n))
+      MFB_LAUNCH(ccd_resid_flat_kernel<true>, e->sm_count, kCcdStagedThreads, ccd_flat_smem(sd.gather_n), e->stream, p, sd.sp_plain->chunk_seg,
+                 sd.sp_plain->n_chunk, own, other, sign, sd.gather_n);
+    else
+      MFB_LAUNCH(ccd_resid_flat_kernel<false>, (sd.sp_plain->n_chunk + 7) / 8, 256, 0, e->stream, p, sd.sp_plain->chunk_seg, sd.sp_plain->n_chunk,
+                 own, other, sign, sd.gather_n);
+    return 0;
+  }
   if (sd.mode == 0) {
     const int tb = 256, wpb = tb / 32;
     MFB_LAUNCH(ccd_resid_kernel, (p.n_seg + wpb - 1) / wpb, tb, 0, e->stream, p, own, other, sign, only_multi);

@@ -181,7 +181,7 @@ void dev_cache_release(int device) {
 }
 
 void SegPlan::release() {
-  dev_free(row); dev_free(start); dev_free(len); dev_free(slot); dev_free(multi_row);
+  dev_free(row); dev_free(start); dev_free(len); dev_free(slot); dev_free(multi_row); dev_free(chunk_seg);
   *this = SegPlan();
 }
 
@@ -800,6 +800,9 @@ extern "C" int mfb_set_option(mfb_engine *e, const char *name, double value) {
   else if (n == "sgd_hot_stab") e->opt_sgd_hot_stab = value;
   else if (n == "sgd_hot_stages") e->opt_sgd_hot_stages = (int)value;
   else if (n == "ccd_fuse") e->opt_ccd_fuse = (int)value;
+  else if (n == "ccd_cap") { e->opt_ccd_cap = (int)value; for (int w = 0; w < 3; w++) e->mat[w].release_ccd(); }
+  else if (n == "ccd_stage") e->opt_ccd_stage = (int)value;
+  else if (n == "ccd_stream") { e->opt_ccd_stream = (int)value; for (int w = 0; w < 3; w++) e->mat[w].release_ccd(); }  // length-sorted vs memory-ordered plans
   else if (n == "ccd_smem") { e->opt_ccd_smem = (int)value; for (int w = 0; w < 3; w++) e->mat[w].release_ccd(); }
   else if (n == "als_tensor_cores") e->opt_als_tensor_cores = (int)value;
   else if (n == "als_dual") e->opt_als_dual = (int)value;

@@ -74,6 +74,10 @@ struct SegPlan {
   int32_t *len = nullptr;      // [n_seg]
   int32_t *slot = nullptr;     // [n_seg]
   int32_t *multi_row = nullptr;  // [n_multi] row id of each slot
+  // CCD++ (memory-ordered plans): consecutive segments grouped into chunks that span at most ccd_cap ratings of
+  // the index / residual arrays (warp-streamed kernels, option ccd_stream = 2) — chunk c holds segments [chunk_seg[c], chunk_seg[c + 1])
+  int32_t *chunk_seg = nullptr;  // [n_chunk + 1]
+  int32_t n_chunk = 0;
   bool built = false;
   void release();
 };
@@ -191,6 +195,9 @@ struct mfb_engine {
   int opt_sgd_hot_pace = 1;           // hot CTAs advance through their list in step with the shuffled kernel
   int opt_sgd_hot_batch = 0;          // ratings per round of a hot CTA, 0 = automatic (<= 64 and <= sgd_flat_hot_lr / learnrate)
   int opt_ccd_smem = 0;               // CCD++: 1 = gathered u_k / v_k staged in shared memory where the shape allows (measured slower than the L1/L2 gather: profiles/r2_ccdpp.md), 2 / 3 = row / column side only
+  int opt_ccd_stream = 0;             // CCD++ passes: 0 = one warp per row segment, segments sorted by length (default); 1 = the same kernels over the segments in memory order; 2 = warp-streamed chunks of consecutive segments with the next batch always in flight (ccd_update_flat_kernel).  All three measure 3.87 - 3.89 ms per rank-one step on the Netflix shape (profiles/r2_ccdpp.md)
+  int opt_ccd_stage = 0;              // CCD++ warp-streamed kernels: 1 = the gathered vector staged in shared memory by persistent CTAs when it fits 200 KB (measured slower: the pass turns issue-bound)
+  int opt_ccd_cap = 4096;             // CCD++ warp-streamed kernels: ratings per chunk (one warp per chunk)
   int opt_ccd_fuse = 1;               // CCD++: add-back / column subtract ride on the first / last update passes
   int opt_als_chunk = 16384;          // ratings per CTA before a row is split over several CTAs
   int opt_als_dual = 1;               // short rows: solve the len x len dual system instead of rank x rank

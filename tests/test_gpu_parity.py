@@ -575,6 +575,33 @@ def test_ccdpp_matches_oracle(rank, freq_adap):
     eng.close()
 
 
+@pytest.mark.parametrize("stream", [(0, 0), (1, 0), (2, 0), (2, 1)])
+@pytest.mark.parametrize("fuse", [1, 0])
+def test_ccdpp_split_rows_both_kernel_families(stream, fuse):
+    """Columns of 3000 ratings are split over several segments (fp64 accumulators + finalize pass) and a chunk of the
+    warp-streamed kernels (option ccd_stream = 2; with and without the gathered vector staged in shared memory) holds
+    many short user rows; the warp-per-segment kernels over both plan orders (ccd_stream = 0 / 1) and the unfused pass
+    sequence (ccd_fuse = 0) must give the same factors."""
+    splits = small_problem(6000, 40, 120000, seed=17)
+    epochs, rank = 2, 8
+    om = oracle_model(splits, "mf", rank, maxiter=epochs, nthreads=4)
+    eng, _ = make_engine(splits, om, rank)
+    eng.set_option("ccd_stream", stream[0])
+    eng.set_option("ccd_stage", stream[1])
+    eng.set_option("ccd_fuse", fuse)
+    om.train("ccd++", keep_history=True)
+    hist = om.history()
+    eng.ccdpp_begin()
+    for ep in range(epochs):
+        for k in range(rank):
+            eng.ccdpp_rank1(k, ep == 0, 5, HP["ureg"], HP["ireg"], 75)
+        U, V = eng.download_factors()
+        assert rel_err(U, hist[ep][0]) < 1e-4, (ep, rel_err(U, hist[ep][0]))
+        assert rel_err(V, hist[ep][1]) < 1e-4, (ep, rel_err(V, hist[ep][1]))
+    eng.ccdpp_end()
+    eng.close()
+
+
 @pytest.mark.parametrize("shape", [(500, 300, 40000), (6000, 40, 120000)])
 @pytest.mark.parametrize("rank", [8, 64])
 def test_ccd_matches_oracle(rank, shape):

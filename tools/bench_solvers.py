@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--epochs", type=int, default=3)
     ap.add_argument("--tc", type=int, default=1)
     ap.add_argument("--reg", type=float, default=0.1)
+    ap.add_argument("--shape", default="netflix", choices=["netflix", "yahoo"])
     args = ap.parse_args()
     import torch
     from matfac_b200 import engine as E
@@ -41,7 +42,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n_users, n_items, nnz = int(bench.SHAPE[0] * args.scale), bench.SHAPE[1], int(bench.SHAPE[2] * args.scale)
+    shape = bench.YAHOO_SHAPE if args.shape == "yahoo" else bench.SHAPE
+    n_users, n_items, nnz = int(shape[0] * args.scale), shape[1], int(shape[2] * args.scale)
     t0 = time.time()
     prob = bench.gen_problem(n_users, n_items, nnz, 20260102, f"cuda:{local}")  # the same matrix on every rank
     ptr, ind, val = prob["train"]
@@ -133,20 +135,37 @@ def main():
         eng.set_option("ccd_fuse", int(os.environ.get("MFB_CCD_FUSE", "1")))
         eng.set_option("ccd_smem", int(os.environ.get("MFB_CCD_SMEM", "0")))
         out["ccd_smem"] = int(os.environ.get("MFB_CCD_SMEM", "0"))
-        eng.ccdpp_begin()
         dims = min(r, 8)
-        for k in range(dims):  # iter 0 (no add-back)
-            eng.ccdpp_rank1(k, True, 5, 0.05, 0.05, 75)
-        eng.sync()
-        eng.event_record(0)
-        for k in range(dims):
-            eng.ccdpp_rank1(k, False, 5, 0.05, 0.05, 75)
-        eng.event_record(1)
-        eng.sync()
-        ms_k = finish([eng.event_elapsed_ms(0, 1)]) / dims
+
+        def run_ccdpp(stream, cap=4096, stage=0):
+            eng.set_option("ccd_stage", stage)
+            eng.set_option("ccd_stream", stream)
+            eng.set_option("ccd_cap", cap)
+            eng.ccdpp_begin()
+            for k in range(dims):  # iter 0 (no add-back)
+                eng.ccdpp_rank1(k, True, 5, 0.05, 0.05, 75)
+            eng.sync()
+            eng.event_record(0)
+            for k in range(dims):
+                eng.ccdpp_rank1(k, False, 5, 0.05, 0.05, 75)
+            eng.event_record(1)
+            eng.sync()
+            ms = eng.event_elapsed_ms(0, 1) / dims
+            eng.ccdpp_end()
+            return ms
+
+        # MFB_CCD_SWEEP = "stream[:cap[:stage]],..." (engine options ccd_stream / ccd_cap / ccd_stage) times every listed configuration in this process (this rank's time)
+        sweep = os.environ.get("MFB_CCD_SWEEP", "")
+        if sweep:
+            out["sweep_ms_per_rank1"] = {}
+            for cfg in sweep.split(","):
+                out["sweep_ms_per_rank1"][cfg] = run_ccdpp(*(int(x) for x in cfg.split(":")))
+                bench.log(f"ccd sweep {cfg}: {out['sweep_ms_per_rank1'][cfg]:.3f} ms")
+        stream, cap, stage = int(os.environ.get("MFB_CCD_STREAM", "0")), int(os.environ.get("MFB_CCD_CAP", "4096")), int(os.environ.get("MFB_CCD_STAGE", "0"))
+        out.update(ccd_stream=stream, ccd_cap=cap, ccd_stage=stage)
+        ms_k = finish([run_ccdpp(stream, cap, stage) * dims]) / dims
         out.update(ms_per_rank1=ms_k, epoch_ms=ms_k * r, algorithmic_gbs=128.0 * train_nnz / (ms_k * 1e-3) / 1e9,
                    frac_of_hbm=128.0 * train_nnz / (ms_k * 1e-3) / 1e9 / peak_gbs, dims_timed=dims)
-        eng.ccdpp_end()
     elif args.algo == "rank":
         # hit-rate positions of every user against the validation matrix: dense U V^T (users x items x rank) with the
         # count fused into the epilogue; wall time of the whole call (split, sparse pass, GEMM, download of the positions)
