@@ -18,7 +18,8 @@ exceed the 126 MB L2, so no explicit L2 flush is done between timed epochs.
 
   value     ratings visited in the timed epochs / device time (CUDA events on the engine's stream, max over
             ranks), inputs resident in HBM
-  e2e       the same metric through the C ABI with HOST buffers (N = 1): every step uploads the rating CSR and the
+  e2e       the same metric through the C ABI with HOST buffers (N > 1: dsgd_e2e, every rank uploads its user stratum
+            and the factors every step; N = 1): every step uploads the rating CSR and the
             factor matrices from pinned host memory, builds the plan, runs one epoch plus the per-epoch
             evaluation and downloads the factors.  Headline: two such steps in flight (two engines, one host
             thread each, taking turns on the link and on the SMs) = throughput of complete steps;
@@ -311,6 +312,95 @@ def run_dsgd(prob, rk, r, plan, warmup, steps, options=None, seed=1, curve=False
         out["val_rmse_curve"] = rmse_curve
     d.close()
     return out
+
+
+def dsgd_e2e(prob, rk, r, steps):
+    """End-to-end DSGD step at N > 1 through the C ABI with HOST buffers, one rank per process.  Every step, every rank:
+    uploads ITS user stratum's rating rows (train + validation CSR) and the initial factors from pinned host memory,
+    plans its blocks, runs one epoch of rk.world sub-epochs (item blocks stored peer to peer), makes V complete on every
+    rank, evaluates its share of the validation RMSE (summed over the ranks by the process group) and downloads the
+    factors.  Wall clock between cross-rank barriers, max over ranks; value = ratings visited / that time.
+
+    Every collective below runs on every rank whatever happened locally (a rank that failed keeps answering them), and
+    the device-side waits time out by themselves (csrc/comm.cu), so a failure ends as {"error": ...} in the line."""
+    import torch
+    from matfac_b200 import dsgd
+    from matfac_b200 import engine as E
+    n_users, n_items = prob["n_users"], prob["n_items"]
+    bad_u, bad_i, _ = masks_of(prob)
+    U0, V0 = init_factors(n_users, n_items, r)
+    P = rk.world
+    err, d, eng = None, None, None
+    try:
+        d = dsgd.Dsgd(n_users, n_items, r, P, {rk.rank: rk.local}, prob["train"], prob["val"], U0, V0, bad_u, bad_i, (steps + 1) * P,
+                      plan="reference", seed=1, exchange=rk.gather, options={"sgd_flat_inflight_frac": 8e-4})
+        eng = d.engines[rk.rank]
+        mine = d.user_part == rk.rank
+        ltr, lva = dsgd.local_rows(n_users, n_items, prob["train"], mine), dsgd.local_rows(n_users, n_items, prob["val"], mine)
+        keep, h = [], {}
+        for name, a in (("tp", ltr.rowptr), ("ti", ltr.rowind), ("tv", ltr.rowval), ("vp", lva.rowptr), ("vi", lva.rowind),
+                        ("vv", lva.rowval), ("U", U0), ("V", V0), ("Uo", np.empty_like(U0)), ("Vo", np.empty_like(V0))):
+            h[name], t = pinned(a)
+            keep.append(t)
+        trp, vap = Mat(n_users, n_items, (h["tp"], h["ti"], h["tv"])), Mat(n_users, n_items, (h["vp"], h["vi"], h["vv"]))
+        up_local = np.where(mine, d.user_part, -1).astype(np.int32)
+        h2d = sum(h[k].nbytes for k in ("tp", "ti", "tv", "vp", "vi", "vv", "U", "V"))
+        d2h = h["Uo"].nbytes + h["Vo"].nbytes + 16
+    except Exception as ex:  # noqa: BLE001
+        err = repr(ex)[:300]
+        h2d = d2h = 0
+    times, visited, rmse = [], [], float("nan")
+    for s in range(steps + 1):
+        if err is None:
+            try:
+                d.barrier()
+                eng.sync()
+            except Exception as ex:  # noqa: BLE001
+                err = repr(ex)[:300]
+        rk.barrier()
+        t1 = time.perf_counter()
+        sums, n_vis = np.zeros(2), 0
+        if err is None:
+            try:
+                eng.upload_csr(E.TRAIN, trp, with_csc=False)
+                eng.upload_csr(E.VAL, vap, with_csc=False)
+                eng.upload_factors(h["U"], h["V"])
+                eng.sgd_plan(P, up_local, d.item_part)
+                d.barrier()  # no peer stores item rows into this rank's V before its factor upload has landed
+                d.run(s * P, (s + 1) * P, HP["lr"], HP["ureg"], HP["ireg"], 1)
+                d.publish()
+                sums = d.eval_sums(E.VAL)
+                eng.L.mfb_download_factors(eng.h, E.CURRENT, h["Uo"].ctypes.data, r, h["Vo"].ctypes.data, r)
+                eng.sync()
+                n_vis = d.block_nnz(s * P, (s + 1) * P)[rk.rank]
+                if eng.comm_error():
+                    err = "a device-side wait timed out"
+            except Exception as ex:  # noqa: BLE001
+                err = repr(ex)[:300]
+        tot = rk.sum([float(sums[0]), float(sums[1]), float(n_vis), 1.0 if err else 0.0])  # the step's result: validation SSE / count over all ranks
+        dt = time.perf_counter() - t1
+        times.append(rk.max(dt))
+        visited.append(tot[2])
+        if tot[3] > 0:
+            err = err or "another rank failed"
+        rmse = float(np.sqrt(tot[0] / tot[1])) if tot[1] > 0 else float("nan")
+    try:
+        if d is not None:
+            d.close()
+    except Exception:  # noqa: BLE001
+        pass
+    torch.cuda.empty_cache()
+    if err is not None:
+        return {"error": err}
+    h2d_all, d2h_all = rk.sum([float(h2d)])[0], rk.sum([float(d2h)])[0]
+    t = float(np.sum(times[1:]))
+    return {"value": float(np.sum(visited[1:])) / t, "unit": "rating-updates/s", "ms_per_step": t / steps * 1e3, "steps_timed": steps,
+            "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all), "val_rmse_last_step": rmse,
+            "h2d_bytes_per_step_this_rank": int(h2d),
+            "what": "per step and rank: upload this rank's user stratum (train + validation CSR) and the factors from pinned host memory, "
+                    "plan, one DSGD epoch (reference partitions + update sequences, item blocks peer to peer), V made complete on every "
+                    "rank, validation RMSE summed over the ranks, factor download; wall clock between cross-rank barriers, max over ranks; "
+                    "bytes are summed over the ranks"}
 
 
 def solver_timings(prob, rk, peak_gbs, ranks=(64, 128), ccd=True, objective=True, shape_name="netflix"):
@@ -909,6 +999,13 @@ def main():
                 line["cpu_baseline"] = {"value": None, "unit": "rating-updates/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": "failed: " + repr(ex)[:200]}
 
+    if world > 1 and args.e2e_steps > 0:
+        try:
+            e2e = dsgd_e2e(prob, rk, RANK, max(2, args.e2e_steps))
+        except Exception as ex:
+            e2e = {"error": repr(ex)[:300]}
+        if rank == 0:
+            line["e2e"] = e2e
     if not args.no_solvers:
         try:
             s = solver_timings(prob, rk, peak)
