@@ -145,6 +145,10 @@ int mfb_sgd_epoch_flat(mfb_engine *e, int variant, float learn_rate, float ureg,
  * 0 = one band, a uniformly shuffled epoch as in modelMF.cpp:76-81 (banding converges at a different rate
  * per epoch than the reference's order); takes effect at the next mfb_sgd_plan), "ccd_fuse" (CCD++: 1 = the residual add-back rides on the first u_k / v_k update pass and the column subtract on the
  * last v_k update pass of a rank-one step — same statements in the same order, 11 instead of 14 passes; 0 = one pass each),
+ * "ccd_stream" (CCD++ passes: 0 = one warp per row segment, segments sorted by length, the default; 1 = the same kernels over
+ * the segments in memory order; 2 = warp-streamed chunks of consecutive segments, the next batch of ratings always in flight;
+ * "ccd_cap" = ratings per chunk, default 4096; "ccd_stage" = 1 keeps the gathered vector in shared memory when it fits —
+ * all measured equal or slower than the default, profiles/r2_ccdpp.md; the plans are rebuilt at the next mfb_ccdpp_begin),
  * "copy_overlap" (1 = mfb_upload_csr / mfb_upload_factors / mfb_download_factors return without synchronising:
  * factor copies run on a copy stream — an upload behind the rating upload and next to mfb_sgd_plan, a download next to
  * the evaluations queued after it; the caller keeps the host buffers (pinned) valid and untouched until mfb_sync; every
