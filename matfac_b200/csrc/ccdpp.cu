@@ -216,10 +216,11 @@ __device__ __forceinline__ CcdDesc ccd_pick_desc(const CcdDesc &d, int src) {
   return o;
 }
 
-// STAGED: persistent CTAs (one per SM) keep the whole gathered vector in shared memory — a gather of 32 different
-// 128-byte lines costs 32 L1 wavefronts (the ~0.3 ms per pass that every global-gather variant of these kernels ends up
-// at: 100 M ratings / 148 SMs at one wavefront per cycle), the same gather from shared memory a few bank conflicts —
-// and their warps take chunks in turn.  The add-back of a row pass reads the same vector (v_k has not moved yet).
+// STAGED (option ccd_stage): persistent CTAs (one per SM) keep the whole gathered vector in shared memory and their warps
+// take chunks in turn; the add-back of a row pass reads the same vector (v_k has not moved yet).  Measured on the Netflix
+// shape (profiles/r2_ccdpp.md): the gather leaves L2 (152 M -> 54 M sectors per pass, L2 at 19 %) and the pass becomes
+// issue-bound instead — 194 M warp instructions for 503 k rows, 54 % of the issue slots at 24 warps per SM — 374 us against
+// ~310 us with the gather through L1: off by default.
 constexpr int kCcdStagedThreads = 768;
 __device__ __forceinline__ void ccd_stage(uint64_t *bar_mem, float *dst0, const float *src0, float *dst1, const float *src1, int n);
 
@@ -415,12 +416,11 @@ static int build_chunk_plan(mfb_engine *e, SegPlan *sp) {
 
 
 // ---- shared-memory staged passes ------------------------------------------------------------------------------
-// A pass gathers one entry of the dense vector `other` per rating.  Every lane of a warp hits a different 128-byte
-// line, so the gather costs one L1 wavefront per rating: 100 M ratings / 148 SMs at one wavefront per cycle is the
-// ~0.3 ms every pass of the plain kernels takes, whatever the memory system delivers (profiles/r1_ncu_ccdpp.txt: L2 at
-// 69 %, a 32-byte sector moved per 4-byte entry).  Here the gathered vector sits in shared memory instead (random
-// 4-byte reads: a few bank conflicts per warp, not 32 wavefronts): the index / residual streams are then the only
-// global traffic and the pass is bound by HBM.  A vector that does not fit is cut into blocks of kCcdBlock entries;
+// A pass gathers one entry of the dense vector `other` per rating; every lane of a warp hits a different 128-byte line
+// and a 32-byte sector moves per 4-byte entry (profiles/r1_ncu_ccdpp.txt: L2 at 69 % in the column pass).  Here the
+// gathered vector sits in shared memory instead (random 4-byte reads: a few bank conflicts per warp) and the index /
+// residual streams are the only global traffic.  Measured slower than the plain kernels (option ccd_smem, off by
+// default; profiles/r2_ccdpp.md has the numbers of every kernel family).  A vector that does not fit is cut into blocks of kCcdBlock entries;
 // every row is split at the block boundaries (its indices ascend: datastruct.cpp:18 / util.cpp:919) and a CTA serves
 // the sub-segments of ONE block with that block of `other` (and of `other_old` for the fused column add-back) staged.
 // Partial sums of a split row meet in the fp64 accumulators, ccd_finalize_kernel closes the row — the same arithmetic
